@@ -1,0 +1,127 @@
+/* waveformer_b200 - C ABI of the B200 (sm_100a) kernels behind the WaveFormer 3D-segmentation hot path.
+ *
+ * The reference has NO native boundary on this path: it is pure Python that calls ptwt / torch.  The
+ * entry points below are what a maintainer binds (ctypes stub in INTEGRATION.md) at the Python call sites named on
+ * each function.  Conventions:
+ *   - plain device pointers + sizes; no torch / C++ types; every call is asynchronous on `stream` (a cudaStream_t
+ *     passed as void*; NULL = the legacy default stream);
+ *   - returns 0 on success, a negative wf_status otherwise (wf_error_string gives the text); nothing aborts;
+ *   - dtype: WF_F32 or WF_BF16 is the storage type of activations; all arithmetic accumulates in fp32;
+ *   - no global state except a lazily created per-device attribute cache (max dynamic shared memory opt-in).
+ */
+#ifndef WAVEFORMER_B200_H
+#define WAVEFORMER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    WF_OK = 0,
+    WF_ERR_BAD_DTYPE = -1,     /* dtype is neither WF_F32 nor WF_BF16 */
+    WF_ERR_BAD_SHAPE = -2,     /* odd extent, zero size, head_dim unsupported, window does not tile the grid ... */
+    WF_ERR_NULL_POINTER = -3,
+    WF_ERR_MISALIGNED = -4,    /* a pointer / stride breaks the 16-byte alignment the vector path needs */
+    WF_ERR_CUDA = -5,          /* a CUDA runtime call failed; wf_last_cuda_error() has the code */
+    WF_ERR_WORKSPACE = -6,     /* workspace too small; query with the *_workspace_bytes function */
+    WF_ERR_UNSUPPORTED = -7
+} wf_status;
+
+typedef enum { WF_F32 = 0, WF_BF16 = 1 } wf_dtype;
+
+const char *wf_version(void);
+const char *wf_error_string(int status);
+int wf_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Kernel group 1: 3D Haar analysis, one level.
+ * Replaces ptwt.wavedec3(x, 'db1', level=1, mode='zero') as called by WaveletTransform3D.forward
+ * (reference network_models/wave_helper.py:349-353) from Block.multi_scale_forward (wave_helper.py:484-486),
+ * including the two permute().contiguous() copies around it when the channels-last entry point is used.
+ *
+ * Sub-band k (0..6) = aad, ada, add, daa, dad, dda, ddd (letter order D,H,W; a = low, d = high), each shaped like
+ * the LL output; band k starts at hf + k * hf_band_stride elements.  hf == NULL skips the seven detail writes (the
+ * caller discards them: only the last block of a stage keeps its details, reference waveformer.py:287-288).
+ * Extents D, H, W must be even.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* x: [n, D, H, W] contiguous (n = every leading dim folded, as ptwt does); ll and each band: [n, D/2, H/2, W/2]. */
+int wf_dwt3d_ncdhw(const void *x, void *ll, void *hf, int dtype, int64_t n, int D, int H, int W,
+                   int64_t hf_band_stride, void *stream);
+
+/* x: [B, D, H, W, C], channel stride 1, voxel stride x_vox_stride elements (>= C; lets the input be a channel
+ * slice of a wider buffer); ll: [B, D/2, H/2, W/2, C] with voxel stride ll_vox_stride; bands: voxel stride C. */
+int wf_dwt3d_ndhwc(const void *x, void *ll, void *hf, int dtype, int B, int D, int H, int W, int C,
+                   int64_t x_vox_stride, int64_t ll_vox_stride, int64_t hf_band_stride, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Kernel group 3: 3D Haar synthesis, one level, fused with the optional high-frequency gate and with the write into
+ * a wider (concatenation) buffer.
+ * Replaces ptwt.waverec3((ll,) + details, 'db1') in UnetrIDWTBlock.forward (reference
+ * network_models/idwt_upsample.py:159-160), the per-sub-band gate multiply of HFRefinementRes.forward
+ * (idwt_upsample.py:49, `x * refined`) and the torch.cat((out, skip), 1) at idwt_upsample.py:163 (the synthesis
+ * writes channels [0, C) of the concat buffer directly).  Also the adjoint (= inverse) used for DWT gradients.
+ * hf == NULL means all-zero details.  gate (optional, same layout as hf) multiplies each detail before synthesis.
+ * ---------------------------------------------------------------------------------------------------------- */
+int wf_idwt3d_ncdhw(const void *ll, const void *hf, const void *gate, void *x, int dtype, int64_t n, int d, int h,
+                    int w, int64_t hf_band_stride, void *stream);
+
+int wf_idwt3d_ndhwc(const void *ll, const void *hf, const void *gate, void *x, int dtype, int B, int d, int h, int w,
+                    int C, int64_t ll_vox_stride, int64_t hf_band_stride, int64_t x_vox_stride, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Kernel group 2: multiscale window attention on the LL band.
+ * Replaces Block.window_partition (reference network_models/wave_helper.py:450-461), Attention.forward
+ * (network_models/attention.py:83-104) and the reshape-only "window reverse" (wave_helper.py:498-499) in one call.
+ *
+ * x:    [B, D1, H1, W1, C] channels-last, contiguous.  Windows of ws^3 tokens tile the grid, window order
+ *       (b, zblk, yblk, xblk), token order (dz, dy, dx).
+ * out:  [B * nW * ws^3, C] contiguous in WINDOW order; the reference re-reads exactly this buffer as
+ *       [B, D1, H1, W1, C] without an inverse permute, so `out` viewed with that shape IS the reference result.
+ * bias: dense relative-position bias produced by wf_relpos_bias_expand, fp32 [heads, N, N] stored TRANSPOSED
+ *       (bias_t[h][j][i] = table[index[i][j]][h]) so a warp of queries reads it coalesced.
+ * Weights are in `dtype`; qkv_w [3C, C], qkv_b [3C], proj_w [C, C], proj_b [C] (PyTorch Linear layout).
+ * head_dim = C / heads must be 8, 16, 32 or 64; scale multiplies q after its bias (attention.py:88).
+ * ---------------------------------------------------------------------------------------------------------- */
+int wf_relpos_bias_expand(const void *table, int table_dtype, const int64_t *index, float *bias_t, int heads, int N,
+                          int table_rows, void *stream);
+
+size_t wf_window_attn_workspace_bytes(int dtype, int B, int D1, int H1, int W1, int C, int heads, int ws);
+
+int wf_window_attn_fwd(const void *x, const void *qkv_w, const void *qkv_b, const void *proj_w, const void *proj_b,
+                       const float *bias_t, void *out, void *workspace, size_t workspace_bytes, int dtype, int B,
+                       int D1, int H1, int W1, int C, int heads, int ws, float scale, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Sliding-window stitching (re-hosted MONAI inferer, reference monai/inferers/utils.py:216-299).
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* Gather `nwin` windows (roi r0 x r1 x r2, starts in `starts` = int32 [nwin][4] = {batch index, z0, y0, x0}, device
+ * memory) from vol [Bv, C, D, H, W] fp32 into win [nwin, C, r0, r1, r2] (dtype, NCDHW contiguous) or, when
+ * channels_last != 0, [nwin, r0, r1, r2, C].  Replaces torch.cat([inputs[s] ...]) at inferers/utils.py:223. */
+int wf_sw_gather(const float *vol, void *win, const int32_t *starts, int nwin, int dtype, int channels_last, int C,
+                 int D, int H, int W, int r0, int r1, int r2, void *stream);
+
+/* acc[b, k, z0+z, y0+y, x0+x] += max(gz[z]*gy[y]*gx[x], floor) * seg[n, k, z, y, x] for every window n (atomic
+ * adds: windows of one call may overlap).  seg: [nwin, K, r0, r1, r2] NCDHW or NDHWC (channels_last).  gz/gy/gx are
+ * the 1-D gaussian factors of compute_importance_map (monai/data/utils.py:1121-1138).  Replaces
+ * `seg *= w; out[slice] += seg` at inferers/utils.py:287-289 / :351-360. */
+int wf_sw_accumulate(const void *seg, float *acc, const int32_t *starts, const float *gz, const float *gy,
+                     const float *gx, float floor_w, int nwin, int dtype, int channels_last, int K, int D, int H,
+                     int W, int r0, int r1, int r2, void *stream);
+
+/* acc[b, k, z, y, x] /= sum over every window w of `all_starts` (int32 [nall][4], the FULL window list of the
+ * volume batch, not just this rank's) covering the voxel of max(gz*gy*gx, floor).  The count map is geometry only,
+ * so it is recomputed here instead of being stored and reduced (inferers/utils.py:265-276, :298-299).
+ * labels (optional, uint8 [Bv, D, H, W]) receives argmax over k (4_predict.py:241). */
+int wf_sw_finalize(float *acc, uint8_t *labels, const int32_t *all_starts, int nall, const float *gz, const float *gy,
+                   const float *gx, float floor_w, int Bv, int K, int D, int H, int W, int r0, int r1, int r2,
+                   void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WAVEFORMER_B200_H */

@@ -1,0 +1,86 @@
+"""GPU parity: the re-hosted sliding-window inferer vs fixtures from MONAI's inferer (reference) and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sliding_window as osw
+from oracle.state import ModelConfig, make_state_dict
+
+from helpers import assert_input_matches, load_npz, max_rel, seeded_randn
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _strict_fp32():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+@pytest.mark.parametrize("name,shape,roi,ov,mode,bs", [
+    ("a", (1, 2, 40, 36, 30), (16, 16, 16), 0.5, "gaussian", 2),
+    ("b", (2, 2, 20, 33, 17), (16, 16, 16), 0.25, "gaussian", 3),
+    ("c", (1, 2, 12, 40, 16), (16, 16, 16), 0.5, "constant", 4),
+])
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_stitching_matches_monai_fixture(name, shape, roi, ov, mode, bs, channels_last):
+    from waveformer_b200.inferers import SlidingWindowInferer
+    g = load_npz("sliding_window_small.npz")
+    wconv = (seeded_randn((3, 2, 3, 3, 3), 600) * 0.2).cuda()
+    x = seeded_randn(shape, 610 + ord(name))
+    assert_input_matches(x, g[f"{name}_in_sum"])
+    inf = SlidingWindowInferer(roi_size=roi, sw_batch_size=bs, overlap=ov, mode=mode, compute_dtype=torch.float32,
+                               channels_last=channels_last, return_labels=True)
+    y = inf(x.cuda(), lambda p: torch.nn.functional.conv3d(p, wconv, padding=1))
+    assert tuple(y.shape) == tuple(g[f"{name}_out"].shape)
+    assert max_rel(y.cpu(), g[f"{name}_out"]) < 1e-5
+    assert torch.equal(inf.labels.cpu().long(), y.argmax(1).cpu())
+
+
+def test_identity_network_returns_input():
+    from waveformer_b200.inferers import sliding_window_inference
+    x = seeded_randn((1, 3, 40, 24, 30), 9).cuda()
+    y = sliding_window_inference(x, (16, 16, 16), 2, lambda p: p, overlap=0.5, mode="gaussian")
+    assert float((y - x).abs().max()) < 1e-5
+
+
+def test_volume_240x240x155_fp32_matches_reference():
+    """BASELINE config 3 geometry, fp32: the product inferer + product model vs the reference inferer + reference
+    model run on the CPU (tests/golden/volume_240x240x155.npz, 32768 sampled logits)."""
+    from waveformer_b200.inferers import SlidingWindowInferer
+    from waveformer_b200.network_models import Waveformer
+    cfg = ModelConfig(img_size=(128,) * 3)
+    g = load_npz("volume_240x240x155.npz")
+    x = seeded_randn((1, 4, 240, 240, 155), 0)
+    assert_input_matches(x, g["in_sum"])
+    m = Waveformer(**cfg.kwargs()).eval()
+    m.load_state_dict(make_state_dict(cfg, seed=0), strict=True)
+    m = m.cuda().to(memory_format=torch.channels_last_3d)
+    inf = SlidingWindowInferer(roi_size=(128,) * 3, sw_batch_size=2, overlap=0.5, mode="gaussian", return_labels=True)
+    with torch.no_grad():
+        y = inf(x.cuda(), m)
+    assert y.shape == (1, 4, 240, 240, 155)
+    assert max_rel(y.reshape(-1).cpu()[g["pos"]], g["logits"]) <= 1e-4
+    hist = np.bincount(inf.labels.reshape(-1).cpu().numpy(), minlength=4)
+    assert np.abs(hist - g["label_hist"]).sum() <= 2e-4 * hist.sum()
+
+
+def test_volume_240x240x155_bf16_matches_reference():
+    from waveformer_b200.inferers import SlidingWindowInferer
+    from waveformer_b200.network_models import Waveformer
+    cfg = ModelConfig(img_size=(128,) * 3)
+    g = load_npz("volume_240x240x155.npz")
+    x = seeded_randn((1, 4, 240, 240, 155), 0)
+    m = Waveformer(**cfg.kwargs()).eval()
+    m.load_state_dict(make_state_dict(cfg, seed=0), strict=True)
+    m = m.cuda().to(torch.bfloat16).to(memory_format=torch.channels_last_3d)
+    inf = SlidingWindowInferer(roi_size=(128,) * 3, sw_batch_size=2, overlap=0.5, mode="gaussian", return_labels=True)
+    with torch.no_grad():
+        y = inf(x.cuda(), m)
+    assert y.dtype == torch.float32
+    assert max_rel(y.reshape(-1).cpu()[g["pos"]], g["logits"]) <= 2e-2
+    hist = np.bincount(inf.labels.reshape(-1).cpu().numpy(), minlength=4)
+    assert np.abs(hist - g["label_hist"]).sum() <= 2 * 1e-3 * hist.sum()   # >= 99.9 % label agreement => histogram shift <= 2 * 0.1 %

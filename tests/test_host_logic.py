@@ -1,0 +1,180 @@
+"""CPU tier: C-ABI exports, state_dict contract, window geometry and the sharded-inferer orchestration (gloo)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from oracle import sliding_window as osw
+from oracle.state import ModelConfig, relative_position_index
+
+from helpers import load_json, seeded_randn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from waveformer_b200 import _lib, build
+    path = build.build()
+    assert os.path.exists(path)
+    header = open(os.path.join(ROOT, "include", "waveformer_b200.h")).read()
+    declared = set(re.findall(r"\b(wf_[a-z0-9_]+)\s*\(", header))
+    declared -= {"wf_status", "wf_dtype"}
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    handle = _lib.lib()                         # loads without a GPU; no compute call is made here
+    for name in declared:
+        assert hasattr(handle, name), name
+    assert b"sm_100a" in handle.wf_version()
+    assert handle.wf_error_string(-2).startswith(b"bad shape")
+
+
+def test_library_is_sm100a_only():
+    from waveformer_b200 import build
+    out = subprocess.run(["cuobjdump", "-lelf", build.build()], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_ops_refuse_cpu_tensors():
+    from waveformer_b200 import ops
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.dwt3d(torch.zeros(1, 4, 4, 4))
+    with pytest.raises(RuntimeError):
+        ops.dwt3d_channels_last(torch.zeros(1, 4, 4, 4, 8))
+
+
+def test_product_does_not_import_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "waveformer_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+
+
+@pytest.mark.parametrize("img", [64, 128])
+def test_state_dict_contract(img):
+    from waveformer_b200.network_models import Waveformer, create_waveformer
+    cfg = ModelConfig(img_size=(img,) * 3)
+    m = Waveformer(**cfg.kwargs())
+    got = [[k, list(v.shape)] for k, v in m.state_dict().items()]
+    assert got == load_json(f"state_dict_spec_{img}.json")
+    idx = m.state_dict()["waveformer_encoder.block1.0.attn.relative_position_index"]
+    assert idx.dtype == torch.int64 and torch.equal(idx, relative_position_index(cfg.window_size(0)))
+    m2 = create_waveformer(dict(img_size=(img,) * 3, patch_size=2, in_chans=4, out_chans=4, depths=[2] * 4,
+                                embed_dims=[48, 96, 192, 384], num_heads=[3, 6, 12, 24], drop_path_rate=0.1))
+    assert list(m2.state_dict().keys()) == [k for k, _ in got]
+    assert m2.hf_refinement is False                      # the flattened-config quirk is preserved
+    assert [b.need_hf for b in m.waveformer_encoder.block1] == [False, True]
+
+
+def test_public_names_match_reference_package():
+    import waveformer_b200.network_models as nm
+    want = ["Waveformer", "create_waveformer", "ProjectionHead", "ChannelCalibration", "MultiscaleTransformer", "Block",
+            "PatchMerging", "PatchMergingV2", "CCF_FFN", "Mlp", "WaveletTransform3D", "DWConv", "OverlapPatchEmbed",
+            "PatchEmbed", "PosCNN", "ProjectionUpsample", "IDWTBlock", "HFRefinementRes", "Attention"]
+    assert sorted(nm.__all__) == sorted(want)
+    for n in want:
+        assert hasattr(nm, n)
+    with pytest.raises(AssertionError):
+        nm.Attention(50, num_heads=3)
+
+
+@pytest.mark.parametrize("size,roi,ov", [((240, 240, 155), (128,) * 3, 0.5), ((40, 36, 30), (16,) * 3, 0.5),
+                                          ((20, 33, 17), (16,) * 3, 0.25), ((128, 128, 128), (128,) * 3, 0.5),
+                                          ((130, 128, 200), (128,) * 3, 0.75)])
+def test_window_geometry_matches_oracle(size, roi, ov):
+    from waveformer_b200 import inferers as inf
+    iv = inf.scan_interval(size, roi, (ov,) * 3)
+    assert iv == osw.scan_interval(size, roi, ov)
+    assert inf.window_starts(size, roi, iv) == osw.window_starts(size, roi, iv)
+    fac, floor = inf.gaussian_factors(roi, "gaussian", (0.125,) * 3)
+    w = torch.clamp((fac[0][:, None, None] * fac[1][None, :, None]) * fac[2][None, None, :], min=floor)
+    assert torch.equal(w, osw.importance_map(roi, "gaussian", 0.125))
+
+
+def test_window_list_240x240x155_is_the_reference_one():
+    from waveformer_b200 import inferers as inf
+    g = load_json("windows_240x240x155.json")
+    st = inf.window_starts((240, 240, 155), (128,) * 3, inf.scan_interval((240, 240, 155), (128,) * 3, (0.5,) * 3))
+    assert [list(s) for s in st] == g["starts"] and len(st) == 18
+
+
+@pytest.mark.parametrize("n,bs,world", [(18, 2, 1), (18, 2, 2), (18, 2, 4), (18, 2, 8), (1152, 2, 8), (7, 3, 4), (1, 2, 8)])
+def test_shard_batches_cover_each_window_once(n, bs, world):
+    from waveformer_b200.inferers import shard_batches
+    seen = []
+    sizes = []
+    for r in range(world):
+        mine = [i for b in shard_batches(n, bs, r, world) for i in b]
+        sizes.append(len(mine))
+        seen += mine
+    assert sorted(seen) == list(range(n))
+    assert max(sizes) - min(sizes) <= bs
+
+
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+from oracle import sliding_window as osw
+from waveformer_b200 import inferers, ops
+from helpers import seeded_randn
+
+# The CUDA stitching kernels cannot run here; stand-ins with the same contracts (built on the oracle's arithmetic)
+# let the test exercise the ORCHESTRATION: sharding, the single reduce, finalisation on rank 0.
+def sw_gather(vol, starts, roi, dtype, channels_last):
+    wins = [vol[b:b + 1, :, z:z + roi[0], y:y + roi[1], x:x + roi[2]] for b, z, y, x in starts.tolist()]
+    w = torch.cat(wins, 0).to(dtype)
+    return w.permute(0, 2, 3, 4, 1).contiguous() if channels_last else w
+def sw_accumulate(seg, acc, starts, gz, gy, gx, floor, channels_last):
+    if channels_last: seg = seg.permute(0, 4, 1, 2, 3)
+    w = torch.clamp((gz[:, None, None] * gy[None, :, None]) * gx[None, None, :], min=floor)
+    for (b, z, y, x), s in zip(starts.tolist(), seg):
+        acc[b, :, z:z + s.shape[1], y:y + s.shape[2], x:x + s.shape[3]] += s.float() * w
+def sw_finalize(acc, all_starts, gz, gy, gx, floor, roi, labels=None):
+    w = torch.clamp((gz[:, None, None] * gy[None, :, None]) * gx[None, None, :], min=floor)
+    cnt = torch.zeros((acc.shape[0], 1) + tuple(acc.shape[2:]))
+    for b, z, y, x in all_starts.tolist():
+        cnt[b, 0, z:z + roi[0], y:y + roi[1], x:x + roi[2]] += w
+    acc /= cnt
+ops.sw_gather, ops.sw_accumulate, ops.sw_finalize = sw_gather, sw_accumulate, sw_finalize
+class _T(torch.Tensor): pass
+torch.Tensor.is_cuda = property(lambda self: True)   # let the host path accept CPU tensors in this test only
+
+dist.init_process_group("gloo", init_method="env://")
+rank, world = dist.get_rank(), dist.get_world_size()
+wconv = seeded_randn((3, 2, 3, 3, 3), 600) * 0.2
+net = lambda p: torch.nn.functional.conv3d(p.float(), wconv, padding=1)
+for case, shape in (("split-volume", (1, 2, 40, 36, 30)), ("three-volumes", (3, 2, 24, 36, 30)), ("whole-volumes", (2, 2, 24, 20, 30))):
+    x = seeded_randn(shape, 77)
+    inf = inferers.SlidingWindowInferer(roi_size=(16, 16, 16), sw_batch_size=2, overlap=0.5, mode="gaussian",
+                                        compute_dtype=torch.float32, channels_last=False)
+    y = inf(x, net)
+    want = osw.sliding_window_inference(x, (16, 16, 16), 2, net, 0.5, "gaussian")
+    owned = inf.owned_volumes
+    if case == "split-volume":
+        assert owned == ([0] if rank == 0 else []) and (y is None) == (rank != 0)
+    got_owned = [None] * world
+    dist.all_gather_object(got_owned, owned)
+    assert sorted(v for o in got_owned for v in o) == list(range(shape[0])), got_owned   # every volume exactly once
+    if owned:
+        err = float((y - want[owned]).abs().max() / want.abs().max())
+        assert err < 1e-5, (case, err)
+    print("OK", case, rank, owned)
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("world", [2])
+def test_sharded_inferer_two_ranks_gloo(tmp_path, world):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", OMP_NUM_THREADS="2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
+           "127.0.0.1", "--master-port", "29533", str(script), ROOT]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert "OK" in res.stdout

@@ -1,0 +1,64 @@
+"""ctypes binding of the C ABI in include/waveformer_b200.h.
+
+There is NO CPU fallback: if the CUDA library is missing or cannot be loaded, every op raises.  The library is only
+*loaded* here (which works without a GPU, so the CPU test tier can check the exported symbols); launching anything
+needs a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+from .build import LIB_PATH
+
+_c = ctypes
+_VOIDP, _I, _I64, _F, _SZ = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float, _c.c_size_t
+
+# name -> (restype, argtypes); mirrors include/waveformer_b200.h one to one
+SIGNATURES = {
+    "wf_version": (_c.c_char_p, []),
+    "wf_error_string": (_c.c_char_p, [_I]),
+    "wf_last_cuda_error": (_I, []),
+    "wf_dwt3d_ncdhw": (_I, [_VOIDP, _VOIDP, _VOIDP, _I, _I64, _I, _I, _I, _I64, _VOIDP]),
+    "wf_dwt3d_ndhwc": (_I, [_VOIDP, _VOIDP, _VOIDP, _I, _I, _I, _I, _I, _I, _I64, _I64, _I64, _VOIDP]),
+    "wf_idwt3d_ncdhw": (_I, [_VOIDP, _VOIDP, _VOIDP, _VOIDP, _I, _I64, _I, _I, _I, _I64, _VOIDP]),
+    "wf_idwt3d_ndhwc": (_I, [_VOIDP, _VOIDP, _VOIDP, _VOIDP, _I, _I, _I, _I, _I, _I, _I64, _I64, _I64, _VOIDP]),
+    "wf_relpos_bias_expand": (_I, [_VOIDP, _I, _VOIDP, _VOIDP, _I, _I, _I, _VOIDP]),
+    "wf_window_attn_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I, _I, _I, _I]),
+    "wf_window_attn_fwd": (_I, [_VOIDP] * 8 + [_SZ, _I, _I, _I, _I, _I, _I, _I, _I, _F, _VOIDP]),
+    "wf_sw_gather": (_I, [_VOIDP, _VOIDP, _VOIDP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VOIDP]),
+    "wf_sw_accumulate": (_I, [_VOIDP] * 6 + [_F, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VOIDP]),
+    "wf_sw_finalize": (_I, [_VOIDP, _VOIDP, _VOIDP, _I, _VOIDP, _VOIDP, _VOIDP, _F] + [_I] * 8 + [_VOIDP]),
+}
+
+_LIB: Optional[ctypes.CDLL] = None
+
+
+class WaveformerB200Error(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    """Load (once) and return the CUDA library; raises if it has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise WaveformerB200Error(
+                f"{LIB_PATH} is missing - build it with `python -m waveformer_b200.build` "
+                "(waveformer_b200 has no CPU fallback)")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError here = header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = handle
+    return _LIB
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = lib().wf_error_string(status).decode()
+        if status == -2:
+            raise ValueError(f"{what}: {msg}")
+        raise WaveformerB200Error(f"{what}: {msg} (status {status})")

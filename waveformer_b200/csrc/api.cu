@@ -1,0 +1,65 @@
+// C-ABI glue: version / errors and the window-attention dispatcher (see include/waveformer_b200.h).
+#include "wf_common.cuh"
+
+namespace wf {
+int g_last_cuda_error = 0;
+
+template <typename T>
+int attn_simt_forward(const T *x, const T *qkv_w, const T *qkv_b, const T *proj_w, const T *proj_b,
+                      const float *bias_t, T *out, void *workspace, int B, int D1, int H1, int W1, int C, int heads,
+                      int ws, float scale, cudaStream_t st);
+}  // namespace wf
+
+extern "C" const char *wf_version(void) { return "waveformer_b200 0.1.0 (sm_100a)"; }
+
+extern "C" int wf_last_cuda_error(void) { return wf::g_last_cuda_error; }
+
+extern "C" const char *wf_error_string(int status) {
+    switch (status) {
+        case WF_OK: return "ok";
+        case WF_ERR_BAD_DTYPE: return "unsupported dtype (expected WF_F32 or WF_BF16)";
+        case WF_ERR_BAD_SHAPE: return "bad shape (odd extent, empty tensor, window does not tile the grid, or unsupported head_dim)";
+        case WF_ERR_NULL_POINTER: return "null pointer";
+        case WF_ERR_MISALIGNED: return "pointer or stride not 16-byte aligned";
+        case WF_ERR_CUDA: return cudaGetErrorString((cudaError_t)wf::g_last_cuda_error);
+        case WF_ERR_WORKSPACE: return "workspace too small";
+        case WF_ERR_UNSUPPORTED: return "unsupported configuration";
+        default: return "unknown status";
+    }
+}
+
+static int check_attn_shape(int B, int D1, int H1, int W1, int C, int heads, int ws) {
+    if (B <= 0 || C <= 0 || heads <= 0 || ws <= 0 || D1 <= 0 || H1 <= 0 || W1 <= 0) return WF_ERR_BAD_SHAPE;
+    if (C % heads) return WF_ERR_BAD_SHAPE;
+    if (D1 % ws || H1 % ws || W1 % ws) return WF_ERR_BAD_SHAPE;
+    const int hd = C / heads;
+    if (hd != 8 && hd != 16 && hd != 32 && hd != 64) return WF_ERR_BAD_SHAPE;
+    return WF_OK;
+}
+
+extern "C" size_t wf_window_attn_workspace_bytes(int dtype, int B, int D1, int H1, int W1, int C, int heads, int ws) {
+    if (check_attn_shape(B, D1, H1, W1, C, heads, ws) != WF_OK) return 0;
+    const size_t e = dtype == WF_F32 ? 4 : 2;
+    const size_t tokens = (size_t)B * D1 * H1 * W1;
+    return 4 * tokens * (size_t)C * e + 256;  // q, k, v (head-major) and the pre-projection output
+}
+
+extern "C" int wf_window_attn_fwd(const void *x, const void *qkv_w, const void *qkv_b, const void *proj_w,
+                                  const void *proj_b, const float *bias_t, void *out, void *workspace,
+                                  size_t workspace_bytes, int dtype, int B, int D1, int H1, int W1, int C, int heads,
+                                  int ws, float scale, void *stream) {
+    if (!x || !qkv_w || !proj_w || !proj_b || !bias_t || !out || !workspace) return WF_ERR_NULL_POINTER;
+    const int rc = check_attn_shape(B, D1, H1, W1, C, heads, ws);
+    if (rc != WF_OK) return rc;
+    if (dtype != WF_F32 && dtype != WF_BF16) return WF_ERR_BAD_DTYPE;
+    if (workspace_bytes < wf_window_attn_workspace_bytes(dtype, B, D1, H1, W1, C, heads, ws)) return WF_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == WF_F32)
+        return wf::attn_simt_forward<float>((const float *)x, (const float *)qkv_w, (const float *)qkv_b,
+                                            (const float *)proj_w, (const float *)proj_b, bias_t, (float *)out,
+                                            workspace, B, D1, H1, W1, C, heads, ws, scale, st);
+    return wf::attn_simt_forward<__nv_bfloat16>((const __nv_bfloat16 *)x, (const __nv_bfloat16 *)qkv_w,
+                                                (const __nv_bfloat16 *)qkv_b, (const __nv_bfloat16 *)proj_w,
+                                                (const __nv_bfloat16 *)proj_b, bias_t, (__nv_bfloat16 *)out, workspace,
+                                                B, D1, H1, W1, C, heads, ws, scale, st);
+}

@@ -1,0 +1,145 @@
+// Sliding-window stitching kernels (re-hosted MONAI inferer; reference monai/inferers/utils.py:216-299,
+// monai/data/utils.py:1121-1138).  All are streaming, HBM-bound, fp32 accumulation.
+#include "wf_common.cuh"
+
+namespace wf {
+
+// vol [Bv, C, D, H, W] fp32 -> win [nwin, C, r0, r1, r2] (or [nwin, r0, r1, r2, C]) in T
+template <typename T, bool CL>
+__global__ void __launch_bounds__(256) sw_gather_kernel(const float *__restrict__ vol, T *__restrict__ win,
+                                                        const int32_t *__restrict__ starts, int64_t total, int C, int D,
+                                                        int H, int W, int r0, int r1, int r2) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int64_t t = idx;
+    int c, x, y, z;
+    if (CL) {
+        c = (int)(t % C); t /= C;
+        x = (int)(t % r2); t /= r2;
+        y = (int)(t % r1); t /= r1;
+        z = (int)(t % r0); t /= r0;
+    } else {
+        x = (int)(t % r2); t /= r2;
+        y = (int)(t % r1); t /= r1;
+        z = (int)(t % r0); t /= r0;
+        c = (int)(t % C); t /= C;
+    }
+    const int n = (int)t;
+    const int b = starts[4 * n], z0 = starts[4 * n + 1], y0 = starts[4 * n + 2], x0 = starts[4 * n + 3];
+    const float v = __ldg(vol + ((((int64_t)b * C + c) * D + z0 + z) * H + y0 + y) * (int64_t)W + x0 + x);
+    win[idx] = from_f32<T>(v);
+}
+
+template <typename T, bool CL>
+__global__ void __launch_bounds__(256) sw_accumulate_kernel(const T *__restrict__ seg, float *__restrict__ acc,
+                                                            const int32_t *__restrict__ starts,
+                                                            const float *__restrict__ gz, const float *__restrict__ gy,
+                                                            const float *__restrict__ gx, float floor_w, int64_t total,
+                                                            int K, int D, int H, int W, int r0, int r1, int r2) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int64_t t = idx;
+    int c, x, y, z;
+    if (CL) {
+        c = (int)(t % K); t /= K;
+        x = (int)(t % r2); t /= r2;
+        y = (int)(t % r1); t /= r1;
+        z = (int)(t % r0); t /= r0;
+    } else {
+        x = (int)(t % r2); t /= r2;
+        y = (int)(t % r1); t /= r1;
+        z = (int)(t % r0); t /= r0;
+        c = (int)(t % K); t /= K;
+    }
+    const int n = (int)t;
+    const int b = starts[4 * n], z0 = starts[4 * n + 1], y0 = starts[4 * n + 2], x0 = starts[4 * n + 3];
+    // importance weight exactly as compute_importance_map builds it: ((gz*gy)*gx) in fp32, clamped from below
+    const float wgt = fmaxf((gz[z] * gy[y]) * gx[x], floor_w);
+    const float v = to_f32(seg[idx]) * wgt;
+    atomicAdd(acc + ((((int64_t)b * K + c) * D + z0 + z) * H + y0 + y) * (int64_t)W + x0 + x, v);
+}
+
+// one thread per voxel: count = sum of window weights covering it; acc[:, k] /= count; optional argmax
+__global__ void __launch_bounds__(256) sw_finalize_kernel(float *__restrict__ acc, uint8_t *__restrict__ labels,
+                                                          const int32_t *__restrict__ all_starts, int nall,
+                                                          const float *__restrict__ gz, const float *__restrict__ gy,
+                                                          const float *__restrict__ gx, float floor_w, int64_t total,
+                                                          int K, int D, int H, int W, int r0, int r1, int r2) {
+    extern __shared__ int32_t s_starts[];
+    for (int i = threadIdx.x; i < 4 * nall; i += blockDim.x) s_starts[i] = all_starts[i];
+    __syncthreads();
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int64_t t = idx;
+    const int x = (int)(t % W); t /= W;
+    const int y = (int)(t % H); t /= H;
+    const int z = (int)(t % D); t /= D;
+    const int b = (int)t;
+    float count = 0.f;
+    for (int n = 0; n < nall; ++n) {  // same order as the reference's `for __s in slices: count_map[__s] += w`
+        if (s_starts[4 * n] != b) continue;
+        const int lz = z - s_starts[4 * n + 1], ly = y - s_starts[4 * n + 2], lx = x - s_starts[4 * n + 3];
+        if ((unsigned)lz < (unsigned)r0 && (unsigned)ly < (unsigned)r1 && (unsigned)lx < (unsigned)r2)
+            count += fmaxf((gz[lz] * gy[ly]) * gx[lx], floor_w);
+    }
+    const int64_t plane = (int64_t)D * H * W;
+    const int64_t sp = ((int64_t)z * H + y) * W + x;
+    float best = -INFINITY;
+    int arg = 0;
+    for (int k = 0; k < K; ++k) {
+        float *p = acc + ((int64_t)b * K + k) * plane + sp;
+        const float v = *p / count;
+        *p = v;
+        if (v > best) { best = v; arg = k; }
+    }
+    if (labels) labels[idx] = (uint8_t)arg;
+}
+
+}  // namespace wf
+
+using namespace wf;
+
+static inline unsigned blocks_for(int64_t total) { return (unsigned)((total + 255) / 256); }
+
+extern "C" int wf_sw_gather(const float *vol, void *win, const int32_t *starts, int nwin, int dtype, int channels_last,
+                            int C, int D, int H, int W, int r0, int r1, int r2, void *stream) {
+    if (!vol || !win || !starts) return WF_ERR_NULL_POINTER;
+    if (nwin <= 0 || C <= 0 || r0 <= 0 || r1 <= 0 || r2 <= 0 || r0 > D || r1 > H || r2 > W) return WF_ERR_BAD_SHAPE;
+    const int64_t total = (int64_t)nwin * C * r0 * r1 * r2;
+    cudaStream_t st = (cudaStream_t)stream;
+#define WF_G(T_, CL_) sw_gather_kernel<T_, CL_><<<blocks_for(total), 256, 0, st>>>(vol, (T_ *)win, starts, total, C, D, H, W, r0, r1, r2)
+    if (dtype == WF_F32) { if (channels_last) WF_G(float, true); else WF_G(float, false); }
+    else if (dtype == WF_BF16) { if (channels_last) WF_G(__nv_bfloat16, true); else WF_G(__nv_bfloat16, false); }
+    else return WF_ERR_BAD_DTYPE;
+#undef WF_G
+    WF_LAUNCH_CHECK();
+    return WF_OK;
+}
+
+extern "C" int wf_sw_accumulate(const void *seg, float *acc, const int32_t *starts, const float *gz, const float *gy,
+                                const float *gx, float floor_w, int nwin, int dtype, int channels_last, int K, int D,
+                                int H, int W, int r0, int r1, int r2, void *stream) {
+    if (!seg || !acc || !starts || !gz || !gy || !gx) return WF_ERR_NULL_POINTER;
+    if (nwin <= 0 || K <= 0 || r0 <= 0 || r1 <= 0 || r2 <= 0 || r0 > D || r1 > H || r2 > W) return WF_ERR_BAD_SHAPE;
+    const int64_t total = (int64_t)nwin * K * r0 * r1 * r2;
+    cudaStream_t st = (cudaStream_t)stream;
+#define WF_A(T_, CL_) sw_accumulate_kernel<T_, CL_><<<blocks_for(total), 256, 0, st>>>((const T_ *)seg, acc, starts, gz, gy, gx, floor_w, total, K, D, H, W, r0, r1, r2)
+    if (dtype == WF_F32) { if (channels_last) WF_A(float, true); else WF_A(float, false); }
+    else if (dtype == WF_BF16) { if (channels_last) WF_A(__nv_bfloat16, true); else WF_A(__nv_bfloat16, false); }
+    else return WF_ERR_BAD_DTYPE;
+#undef WF_A
+    WF_LAUNCH_CHECK();
+    return WF_OK;
+}
+
+extern "C" int wf_sw_finalize(float *acc, uint8_t *labels, const int32_t *all_starts, int nall, const float *gz,
+                              const float *gy, const float *gx, float floor_w, int Bv, int K, int D, int H, int W,
+                              int r0, int r1, int r2, void *stream) {
+    if (!acc || !all_starts || !gz || !gy || !gx) return WF_ERR_NULL_POINTER;
+    if (nall <= 0 || nall > 8192 || Bv <= 0 || K <= 0) return WF_ERR_BAD_SHAPE;
+    const int64_t total = (int64_t)Bv * D * H * W;
+    sw_finalize_kernel<<<blocks_for(total), 256, (size_t)nall * 16, (cudaStream_t)stream>>>(
+        acc, labels, all_starts, nall, gz, gy, gx, floor_w, total, K, D, H, W, r0, r1, r2);
+    WF_LAUNCH_CHECK();
+    return WF_OK;
+}

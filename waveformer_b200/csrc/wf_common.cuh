@@ -1,0 +1,96 @@
+// Shared device/host helpers for the waveformer_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/waveformer_b200.h"
+
+namespace wf {
+
+extern int g_last_cuda_error;
+
+inline int cuda_fail(cudaError_t e) {
+    g_last_cuda_error = (int)e;
+    return WF_ERR_CUDA;
+}
+
+#define WF_CUDA_CHECK(expr)                                      \
+    do {                                                         \
+        cudaError_t _e = (expr);                                 \
+        if (_e != cudaSuccess) return ::wf::cuda_fail(_e);       \
+    } while (0)
+
+#define WF_LAUNCH_CHECK() WF_CUDA_CHECK(cudaPeekAtLastError())
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+constexpr int kNumSMs = 148;  // B200
+
+// ---- 16-byte packets of activations ---------------------------------------------------------------------------
+template <typename T> struct Pack;  // VEC elements of T in one 16-byte global transaction
+template <> struct Pack<float> {
+    static constexpr int VEC = 4;
+    using raw = float4;
+    __device__ static inline void unpack(const raw &r, float (&v)[4]) { v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w; }
+    __device__ static inline raw pack(const float (&v)[4]) { return make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct Pack<__nv_bfloat16> {
+    static constexpr int VEC = 8;
+    using raw = uint4;
+    __device__ static inline void unpack(const raw &r, float (&v)[8]) {
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {  // bf16 -> fp32 is a 16-bit shift
+            v[2 * i] = __uint_as_float(w[i] << 16);
+            v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+    __device__ static inline raw pack(const float (&v)[8]) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t *>(&h);
+        }
+        return make_uint4(w[0], w[1], w[2], w[3]);
+    }
+};
+
+// streaming (evict-first) 16-byte global accesses: every byte of the Haar kernels is touched exactly once
+template <typename R> __device__ inline R ld_stream(const void *p) { return __ldcs(reinterpret_cast<const R *>(p)); }
+template <typename R> __device__ inline void st_stream(void *p, const R &v) { __stcs(reinterpret_cast<R *>(p), v); }
+
+template <typename T> __device__ inline float to_f32(T v);
+template <> __device__ inline float to_f32<float>(float v) { return v; }
+template <> __device__ inline float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ inline T from_f32(float v);
+template <> __device__ inline float from_f32<float>(float v) { return v; }
+template <> __device__ inline __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// ---- the 2x2x2 Haar butterfly (orthonormal, symmetric => the same routine analyses and synthesises) -----------
+// in : v[m], m = (i<<2)|(j<<1)|k  = sample at (2z+i, 2y+j, 2x+k)
+// out: c[n], n = (p<<2)|(q<<1)|r  = sub-band (D-kind p, H-kind q, W-kind r): aaa,aad,ada,add,daa,dad,dda,ddd
+__device__ inline void haar8(const float (&v)[8], float (&c)[8]) {
+    const float s = 0.35355339059327378f;  // 1 / (2*sqrt(2))
+    // W axis (bit 0)
+    const float a00 = v[0] + v[1], d00 = v[0] - v[1];
+    const float a01 = v[2] + v[3], d01 = v[2] - v[3];
+    const float a10 = v[4] + v[5], d10 = v[4] - v[5];
+    const float a11 = v[6] + v[7], d11 = v[6] - v[7];
+    // H axis (bit 1)
+    const float aa0 = a00 + a01, da0 = a00 - a01, ad0 = d00 + d01, dd0 = d00 - d01;
+    const float aa1 = a10 + a11, da1 = a10 - a11, ad1 = d10 + d11, dd1 = d10 - d11;
+    // D axis (bit 2)
+    c[0] = s * (aa0 + aa1);
+    c[1] = s * (ad0 + ad1);
+    c[2] = s * (da0 + da1);
+    c[3] = s * (dd0 + dd1);
+    c[4] = s * (aa0 - aa1);
+    c[5] = s * (ad0 - ad1);
+    c[6] = s * (da0 - da1);
+    c[7] = s * (dd0 - dd1);
+}
+
+}  // namespace wf

@@ -1,0 +1,62 @@
+"""``Attention`` - multiscale window self-attention on the LL band, same API as the reference
+(``network_models/attention.py:15-104``), computed by the hand-written CUDA kernels behind ``wf_window_attn_fwd``."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+
+def build_relative_position_index(ws: int) -> torch.Tensor:
+    """int64 [ws^3, ws^3] buffer of ``attention.py:43-57``.  The depth offset is weighted by ``3*ws - 1`` (not
+    ``(2*ws-1)**2``), so different offsets share table rows; checkpoints depend on it, so it is kept."""
+    r = torch.arange(ws)
+    z, y, x = torch.meshgrid(r, r, r, indexing="ij")
+    lin = (z * (3 * ws - 1) + y * (2 * ws - 1) + x).flatten()
+    shift = (ws - 1) * ((3 * ws - 1) + (2 * ws - 1) + 1)
+    return (lin[:, None] - lin[None, :] + shift).long()
+
+
+class Attention(nn.Module):
+    def __init__(self, dim, num_heads=8, qkv_bias=False, qk_scale=None, attn_drop=0., proj_drop=0., window_size=6,
+                 img_size=(48, 48, 48)):
+        super().__init__()
+        assert dim % num_heads == 0, f"dim {dim} should be divided by num_heads {num_heads}."
+        self.dim = dim
+        self.num_heads = num_heads
+        self.head_dim = dim // num_heads
+        self.scale = qk_scale or self.head_dim ** -0.5
+        self.window_size = window_size
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(proj_drop)
+        self.relative_position_bias_table = nn.Parameter(torch.zeros((2 * window_size - 1) ** 3, num_heads))
+        self.register_buffer("relative_position_index", build_relative_position_index(window_size))
+        nn.init.trunc_normal_(self.relative_position_bias_table, std=.02)
+        self.softmax = nn.Softmax(dim=-1)
+        self._bias_cache = None  # (key, dense transposed bias)
+
+    def _dense_bias(self) -> torch.Tensor:
+        t = self.relative_position_bias_table
+        key = (t._version, t.data_ptr(), t.device, t.dtype)
+        if self.training or self._bias_cache is None or self._bias_cache[0] != key:
+            self._bias_cache = (key, ops.relpos_bias_expand(t.detach(), self.relative_position_index))
+        return self._bias_cache[1]
+
+    def forward_grid(self, x: torch.Tensor) -> torch.Tensor:
+        """x [B, D1, H1, W1, C] channels-last LL grid -> window-major result viewed as [B, D1, H1, W1, C]
+        (window partition and the reference's reshape-only reverse are part of the kernel's addressing)."""
+        if self.training and (self.attn_drop.p > 0 or self.proj_drop.p > 0):
+            raise NotImplementedError("attention dropout is not part of the fused kernel (the path uses p = 0)")
+        return ops.window_attention(x, self.qkv.weight, self.qkv.bias, self.proj.weight, self.proj.bias,
+                                    self.relative_position_bias_table, self.relative_position_index,
+                                    self._dense_bias(), self.num_heads, self.window_size, self.scale)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        b_, n, c = x.shape
+        ws = self.window_size
+        if n != ws ** 3 or c != self.dim:
+            raise ValueError(f"expected [B_, {ws ** 3}, {self.dim}], got {tuple(x.shape)}")
+        return self.forward_grid(x.reshape(b_, ws, ws, ws, c)).reshape(b_, n, c)

@@ -1,0 +1,129 @@
+"""``Waveformer`` - the U-shaped segmentation network, same constructor / forward / ``state_dict`` as the reference
+(``network_models/network_backbone.py:131-431``)."""
+from __future__ import annotations
+
+from functools import partial
+from typing import Tuple, Union
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .blocks import UnetOutBlock, UnetrBasicBlock, UnetrUpBlock
+from .idwt_upsample import UnetrIDWTBlock
+from .legacy import ProjectionHead  # noqa: F401  (re-exported like the reference)
+from .wave_helper import ProjectionUpsample
+from .waveformer import MultiscaleTransformer
+
+
+class ChannelCalibration(nn.Module):
+    """SE-style bottleneck recalibration of the deepest feature map (``network_backbone.py:66-128``)."""
+
+    def __init__(self, in_channels: int = 384, reduction_ratio: int = 4, norm_layer: type = nn.BatchNorm3d):
+        super().__init__()
+        r = in_channels // reduction_ratio
+        self.reduce = nn.Conv3d(in_channels, r, kernel_size=1)
+        self.norm_reduce = norm_layer(r)
+        self.conv = nn.Conv3d(r, r, kernel_size=3, padding=1)
+        self.norm_conv = norm_layer(r)
+        self.expand = nn.Conv3d(r, in_channels, kernel_size=1)
+        self.norm_expand = norm_layer(in_channels)
+        self.global_pool = nn.AdaptiveAvgPool3d(1)
+        self.fc1 = nn.Linear(in_channels, r)
+        self.fc2 = nn.Linear(r, in_channels)
+        self.residual = nn.Conv3d(in_channels, in_channels, kernel_size=1)
+        self.sigmoid = nn.Sigmoid()
+        self.relu = nn.ReLU()
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        identity = self.residual(x)
+        t = self.relu(self.norm_reduce(self.reduce(x)))
+        t = self.relu(self.norm_conv(self.conv(t)))
+        t = self.norm_expand(self.expand(t))
+        se = t.mean(dim=(2, 3, 4))
+        se = self.sigmoid(self.fc2(F.relu(self.fc1(se))))
+        return self.relu(t * se[:, :, None, None, None] + identity)
+
+
+class Waveformer(nn.Module):
+    def __init__(self, img_size: Tuple[int, int, int] = (96, 96, 96), patch_size: int = 2, in_chans: int = 1,
+                 out_chans: int = 13, depths: list = None, feat_size: list = None, num_heads: list = None,
+                 drop_path_rate: float = 0.1, layer_scale_init_value: float = 1e-6, hidden_size: int = 768,
+                 norm_name: Union[Tuple, str] = "instance", conv_block: bool = True, res_block: bool = True,
+                 spatial_dims: int = 3, use_checkpoint: bool = False, network_config: dict = None) -> None:
+        super().__init__()
+        depths = depths or [2, 2, 2, 2]
+        feat_size = feat_size or [48, 96, 192, 384]
+        num_heads = num_heads or [3, 6, 12, 24]
+        self.img_size = img_size
+        self.hidden_size = hidden_size
+        self.patch_size = patch_size
+        self.num_heads = num_heads
+        self.in_chans = in_chans
+        self.out_chans = out_chans
+        self.depths = depths
+        self.drop_path_rate = drop_path_rate
+        self.feat_size = feat_size
+        self.layer_scale_init_value = layer_scale_init_value
+        self.spatial_dims = spatial_dims
+        self.network_config = network_config or {}
+        # NB: create_waveformer passes the FLAT kwargs dict here, so 'transformer' is normally absent
+        # and every option below falls back to its default - kept as is.
+        self.transformer_config = self.network_config.get('transformer', {})
+        self.hf_refinement = self.transformer_config.get('hf_refinement', False)
+        self.out_indice = list(range(len(self.depths)))
+        tc = self.transformer_config
+        self.waveformer_encoder = MultiscaleTransformer(
+            img_size=self.img_size, in_chans=self.in_chans, patch_size=self.patch_size, num_classes=self.out_chans,
+            embed_dims=tc.get('embed_dims', self.feat_size), depths=tc.get('depths', self.depths),
+            num_heads=tc.get('num_heads', self.num_heads), drop_path_rate=tc.get('drop_path_rate', self.drop_path_rate),
+            mlp_ratios=tc.get('mlp_ratios', [4, 4, 4, 4]), decom_levels=tc.get('decom_levels', [3, 2, 1, 0]),
+            multi_scale_attention=tc.get('multi_scale_attention', True), qkv_bias=True,
+            norm_layer=partial(nn.LayerNorm, eps=1e-6), attn_drop_rate=0, drop_rate=0,
+            network_config=self.network_config)
+        f = self.feat_size
+        enc = dict(spatial_dims=spatial_dims, kernel_size=3, stride=1, norm_name=norm_name, res_block=res_block)
+        self.encoder1 = UnetrBasicBlock(in_channels=self.in_chans, out_channels=f[0], **enc)
+        self.encoder2 = UnetrBasicBlock(in_channels=f[0], out_channels=f[0], **enc)
+        self.encoder3 = UnetrBasicBlock(in_channels=f[1], out_channels=f[1], **enc)
+        self.encoder4 = UnetrBasicBlock(in_channels=f[2], out_channels=f[2], **enc)
+        self.encoder10 = ChannelCalibration(in_channels=f[3], reduction_ratio=4, norm_layer=nn.InstanceNorm3d)
+        dec = dict(spatial_dims=spatial_dims, in_channels=f[3], hf_refinement=self.hf_refinement, wavelet='db1',
+                   kernel_size=3, norm_name=norm_name, res_block=res_block)
+        self.decoder4 = UnetrIDWTBlock(out_channels=f[2], stage=1, **dec)
+        self.decoder3 = UnetrIDWTBlock(out_channels=f[1], stage=2, **dec)
+        self.decoder2 = UnetrIDWTBlock(out_channels=f[0], stage=3, **dec)
+        self.learnable_up4 = ProjectionUpsample(in_channels=f[2], out_channels=f[0], stride=4, residual=True,
+                                                use_double_conv=True)
+        self.learnable_up3 = ProjectionUpsample(in_channels=f[1], out_channels=f[0], stride=2, residual=True)
+        self.decoder1 = UnetrUpBlock(spatial_dims=spatial_dims, in_channels=f[0] * 3, out_channels=f[0], kernel_size=3,
+                                     upsample_kernel_size=2, norm_name=norm_name, res_block=res_block)
+        self.out = UnetOutBlock(spatial_dims=spatial_dims, in_channels=f[0], out_channels=self.out_chans)
+
+    def forward(self, x_in: torch.Tensor) -> torch.Tensor:
+        if not x_in.is_cuda:
+            raise RuntimeError("waveformer_b200.Waveformer runs on CUDA (B200) only; there is no CPU fallback")
+        dtype = self.out.conv.conv.weight.dtype
+        if x_in.dtype != dtype:
+            x_in = x_in.to(dtype)
+        x_in = x_in.contiguous(memory_format=torch.channels_last_3d)
+        outs, outs_hf = self.waveformer_encoder(x_in)
+        enc0 = self.encoder1(x_in)
+        enc1 = self.encoder2(outs[0])
+        enc2 = self.encoder3(outs[1])
+        enc3 = self.encoder4(outs[2])
+        dec5 = self.encoder10(outs[3])
+        dec4 = self.decoder4(dec5, enc3, outs_hf[-1])
+        dec3 = self.decoder3(dec5, enc2, outs_hf[-2])
+        dec2 = self.decoder2(dec5, enc1, outs_hf[-3])
+        combined = torch.cat([self.learnable_up4(dec4), self.learnable_up3(dec3), dec2], dim=1)
+        return self.out(self.decoder1(combined, enc0))
+
+
+def create_waveformer(network_config: dict) -> Waveformer:
+    return Waveformer(
+        img_size=network_config['img_size'], patch_size=network_config['patch_size'],
+        in_chans=network_config['in_chans'], out_chans=network_config['out_chans'], depths=network_config['depths'],
+        feat_size=network_config['embed_dims'], num_heads=network_config['num_heads'],
+        drop_path_rate=network_config['drop_path_rate'], use_checkpoint=network_config.get('use_checkpoint', False),
+        network_config=network_config)

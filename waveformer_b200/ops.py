@@ -1,0 +1,391 @@
+"""Torch-level operators over the C ABI (include/waveformer_b200.h).
+
+PyTorch is plumbing here: it owns device memory and streams; every operator below launches hand-written sm_100a
+kernels from ``waveformer_b200/lib/libwaveformer_b200.so`` on the CURRENT CUDA stream of the input's device and
+raises if the tensor is not on a CUDA device (no CPU fallback).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+DETAIL_KEYS = ("aad", "ada", "add", "daa", "dad", "dda", "ddd")  # ptwt's key order (letter order = D, H, W)
+
+LAUNCHES = 0  # number of kernel-launching C-ABI calls made by this process (bench.py reports it)
+
+
+def _count(n: int = 1) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return 0
+    if t.dtype == torch.bfloat16:
+        return 1
+    # same convention as ptwt, which raises ValueError for dtypes it does not support
+    raise ValueError(f"waveformer_b200: dtype {t.dtype} not supported (float32 or bfloat16)")
+
+
+def _need_cuda(*tensors: Optional[torch.Tensor]) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("waveformer_b200 operators run on CUDA tensors only (there is no CPU fallback)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError("waveformer_b200: tensors live on different devices")
+    return dev
+
+
+def _stream(dev: torch.device) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# ====================================================================================================== Haar ====
+def _dwt_ncdhw_raw(x: torch.Tensor, need_hf: bool) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    dev = _need_cuda(x)
+    if x.dim() < 3:
+        raise ValueError("expected at least 3 dims [..., D, H, W]")
+    D, H, W = x.shape[-3:]
+    if D % 2 or H % 2 or W % 2:
+        raise ValueError(f"waveformer_b200 Haar transform needs even extents, got {(D, H, W)}")
+    x = x.contiguous()
+    lead = tuple(x.shape[:-3])
+    n = 1
+    for v in lead:
+        n *= v
+    ll = torch.empty(lead + (D // 2, H // 2, W // 2), dtype=x.dtype, device=dev)
+    hf = torch.empty((7,) + tuple(ll.shape), dtype=x.dtype, device=dev) if need_hf else None
+    with torch.cuda.device(dev):
+        st = _lib.lib().wf_dwt3d_ncdhw(x.data_ptr(), ll.data_ptr(), _ptr(hf), _dtype_code(x), n, D, H, W, ll.numel(),
+                                       _stream(dev))
+    _lib.check(st, "wf_dwt3d_ncdhw")
+    _count()
+    return ll, hf
+
+
+def _idwt_ncdhw_raw(ll: torch.Tensor, hf: Optional[torch.Tensor], gate: Optional[torch.Tensor] = None) -> torch.Tensor:
+    dev = _need_cuda(ll, hf, gate)
+    ll = ll.contiguous()
+    d, h, w = ll.shape[-3:]
+    lead = tuple(ll.shape[:-3])
+    n = 1
+    for v in lead:
+        n *= v
+    if hf is not None:
+        hf = hf.contiguous()
+        if tuple(hf.shape) != (7,) + tuple(ll.shape) or hf.dtype != ll.dtype:
+            raise ValueError("detail stack must be [7, *ll.shape] with ll's dtype")
+    if gate is not None:
+        gate = gate.contiguous()
+        if hf is None or gate.shape != hf.shape or gate.dtype != ll.dtype:
+            raise ValueError("gate must match the detail stack")
+    x = torch.empty(lead + (2 * d, 2 * h, 2 * w), dtype=ll.dtype, device=dev)
+    with torch.cuda.device(dev):
+        st = _lib.lib().wf_idwt3d_ncdhw(ll.data_ptr(), _ptr(hf), _ptr(gate), x.data_ptr(), _dtype_code(ll), n, d, h, w,
+                                        ll.numel(), _stream(dev))
+    _lib.check(st, "wf_idwt3d_ncdhw")
+    _count()
+    return x
+
+
+def _dwt_ndhwc_raw(x: torch.Tensor, need_hf: bool) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    dev = _need_cuda(x)
+    if x.dim() != 5:
+        raise ValueError("expected [B, D, H, W, C]")
+    B, D, H, W, C = x.shape
+    if D % 2 or H % 2 or W % 2:
+        raise ValueError(f"waveformer_b200 Haar transform needs even extents, got {(D, H, W)}")
+    xs = _voxel_stride(x)
+    if xs is None:
+        x = x.contiguous()
+        xs = C
+    ll = torch.empty((B, D // 2, H // 2, W // 2, C), dtype=x.dtype, device=dev)
+    hf = torch.empty((7,) + tuple(ll.shape), dtype=x.dtype, device=dev) if need_hf else None
+    with torch.cuda.device(dev):
+        st = _lib.lib().wf_dwt3d_ndhwc(x.data_ptr(), ll.data_ptr(), _ptr(hf), _dtype_code(x), B, D, H, W, C, xs, C,
+                                       ll.numel(), _stream(dev))
+    _lib.check(st, "wf_dwt3d_ndhwc")
+    _count()
+    return ll, hf
+
+
+def _voxel_stride(t: torch.Tensor) -> Optional[int]:
+    """Voxel stride of a [B, D, H, W, C] tensor that is dense over voxels with a (possibly wider) channel pitch."""
+    B, D, H, W, C = t.shape
+    s = t.stride()
+    vs = s[3]
+    if s[4] == 1 and vs >= C and s[2] == W * vs and s[1] == H * W * vs and (B == 1 or s[0] == D * H * W * vs):
+        return vs
+    return None
+
+
+def _idwt_ndhwc_raw(ll: torch.Tensor, hf: Optional[torch.Tensor], gate: Optional[torch.Tensor] = None,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    dev = _need_cuda(ll, hf, gate, out)
+    if ll.dim() != 5:
+        raise ValueError("expected ll [B, d, h, w, C]")
+    B, d, h, w, C = ll.shape
+    lls = _voxel_stride(ll)
+    if lls is None:
+        ll = ll.contiguous()
+        lls = C
+    if hf is not None:
+        hf = hf.contiguous()
+        if tuple(hf.shape) != (7, B, d, h, w, C) or hf.dtype != ll.dtype:
+            raise ValueError("detail stack must be [7, B, d, h, w, C] with ll's dtype")
+    if gate is not None:
+        gate = gate.contiguous()
+        if hf is None or gate.shape != hf.shape or gate.dtype != ll.dtype:
+            raise ValueError("gate must match the detail stack")
+    if out is None:
+        out = torch.empty((B, 2 * d, 2 * h, 2 * w, C), dtype=ll.dtype, device=dev)
+    if tuple(out.shape) != (B, 2 * d, 2 * h, 2 * w, C) or out.dtype != ll.dtype:
+        raise ValueError("out must be [B, 2d, 2h, 2w, C] with ll's dtype")
+    xs = _voxel_stride(out)
+    if xs is None:
+        raise ValueError("out must be voxel-dense with channel stride 1 (a channel slice of an NDHWC buffer)")
+    with torch.cuda.device(dev):
+        st = _lib.lib().wf_idwt3d_ndhwc(ll.data_ptr(), _ptr(hf), _ptr(gate), out.data_ptr(), _dtype_code(ll), B, d, h, w,
+                                        C, lls, B * d * h * w * C, xs, _stream(dev))
+    _lib.check(st, "wf_idwt3d_ndhwc")
+    _count()
+    return out
+
+
+class _DwtNCDHW(torch.autograd.Function):
+    """Orthonormal transform: the adjoint of analysis is synthesis, so backward is one IDWT launch."""
+
+    @staticmethod
+    def forward(ctx, x, need_hf):
+        ll, hf = _dwt_ncdhw_raw(x, need_hf)
+        ctx.need_hf = need_hf
+        if need_hf:
+            return ll, hf
+        return ll, x.new_empty(0)
+
+    @staticmethod
+    def backward(ctx, g_ll, g_hf):
+        hf = g_hf if (ctx.need_hf and g_hf is not None and g_hf.numel()) else None
+        return _idwt_ncdhw_raw(g_ll, hf), None
+
+
+class _IdwtNCDHW(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ll, hf, gate):
+        ctx.save_for_backward(hf if gate is not None else None, gate)
+        return _idwt_ncdhw_raw(ll, hf, gate)
+
+    @staticmethod
+    def backward(ctx, g):
+        hf, gate = ctx.saved_tensors
+        g_ll, g_c = _dwt_ncdhw_raw(g, True)
+        if gate is None:
+            return g_ll, g_c, None
+        return g_ll, g_c * gate, g_c * hf
+
+
+class _DwtNDHWC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, need_hf):
+        ll, hf = _dwt_ndhwc_raw(x, need_hf)
+        ctx.need_hf = need_hf
+        if need_hf:
+            return ll, hf
+        return ll, x.new_empty(0)
+
+    @staticmethod
+    def backward(ctx, g_ll, g_hf):
+        hf = g_hf if (ctx.need_hf and g_hf is not None and g_hf.numel()) else None
+        return _idwt_ndhwc_raw(g_ll, hf), None
+
+
+class _IdwtNDHWC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ll, hf, gate, out):
+        ctx.save_for_backward(hf if gate is not None else None, gate)
+        res = _idwt_ndhwc_raw(ll, hf, gate, out)
+        if out is not None:
+            ctx.mark_dirty(out)
+        return res
+
+    @staticmethod
+    def backward(ctx, g):
+        hf, gate = ctx.saved_tensors
+        g_ll, g_c = _dwt_ndhwc_raw(g, True)
+        if gate is None:
+            return g_ll, g_c, None, None
+        return g_ll, g_c * gate, g_c * hf, None
+
+
+def dwt3d(x: torch.Tensor, need_hf: bool = True):
+    """One Haar level on ``x[..., D, H, W]`` -> ``(ll, hf)``; ``hf`` is ``[7, *ll.shape]`` in DETAIL_KEYS order."""
+    ll, hf = _DwtNCDHW.apply(x, need_hf)
+    return ll, (hf if need_hf else None)
+
+
+def idwt3d(ll: torch.Tensor, hf: Optional[torch.Tensor], gate: Optional[torch.Tensor] = None) -> torch.Tensor:
+    return _IdwtNCDHW.apply(ll, hf, gate)
+
+
+def dwt3d_channels_last(x: torch.Tensor, need_hf: bool = True):
+    """One Haar level on channels-last ``x[B, D, H, W, C]`` -> ``ll[B, d, h, w, C]``, ``hf[7, B, d, h, w, C]``."""
+    ll, hf = _DwtNDHWC.apply(x, need_hf)
+    return ll, (hf if need_hf else None)
+
+
+def idwt3d_channels_last(ll: torch.Tensor, hf: Optional[torch.Tensor], gate: Optional[torch.Tensor] = None,
+                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Synthesis into ``out`` (may be a channel slice ``buf[..., :C]`` of a wider NDHWC buffer = fused concat)."""
+    return _IdwtNDHWC.apply(ll, hf, gate, out)
+
+
+# ================================================================================================= attention ====
+def relpos_bias_expand(table: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
+    """Dense transposed bias ``bias_t[h, j, i] = table[index[i, j], h]`` (fp32) for wf_window_attn_fwd."""
+    dev = _need_cuda(table, index)
+    if index.dtype != torch.int64 or index.dim() != 2 or index.shape[0] != index.shape[1]:
+        raise ValueError("relative_position_index must be int64 [N, N]")
+    table = table.contiguous()
+    index = index.contiguous()
+    heads, n = table.shape[1], index.shape[0]
+    out = torch.empty((heads, n, n), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        st = _lib.lib().wf_relpos_bias_expand(table.data_ptr(), _dtype_code(table), index.data_ptr(), out.data_ptr(),
+                                              heads, n, table.shape[0], _stream(dev))
+    _lib.check(st, "wf_relpos_bias_expand")
+    _count()
+    return out
+
+
+def _window_attention_raw(x, qkv_w, qkv_b, proj_w, proj_b, bias_t, heads: int, ws: int, scale: float) -> torch.Tensor:
+    dev = _need_cuda(x, qkv_w, qkv_b, proj_w, proj_b, bias_t)
+    if x.dim() != 5:
+        raise ValueError("expected x [B, D1, H1, W1, C]")
+    B, D1, H1, W1, C = x.shape
+    code = _dtype_code(x)
+    x = x.contiguous()
+    ws_args = (code, B, D1, H1, W1, C, heads, ws)
+    L = _lib.lib()
+    nbytes = L.wf_window_attn_workspace_bytes(*ws_args)
+    if nbytes == 0:
+        raise ValueError(f"window attention: unsupported geometry grid={(D1, H1, W1)} C={C} heads={heads} ws={ws}")
+    work = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    out = torch.empty_like(x)
+    cast = lambda t: None if t is None else t.detach().to(x.dtype).contiguous()
+    qkv_w, qkv_b, proj_w, proj_b = cast(qkv_w), cast(qkv_b), cast(proj_w), cast(proj_b)
+    with torch.cuda.device(dev):
+        st = L.wf_window_attn_fwd(x.data_ptr(), qkv_w.data_ptr(), _ptr(qkv_b), proj_w.data_ptr(), proj_b.data_ptr(),
+                                  bias_t.data_ptr(), out.data_ptr(), work.data_ptr(), nbytes, code, B, D1, H1, W1, C,
+                                  heads, ws, float(scale), _stream(dev))
+    _lib.check(st, "wf_window_attn_fwd")
+    _count(3)
+    return out
+
+
+def _window_partition(x: torch.Tensor, ws: int) -> torch.Tensor:
+    b, d, h, w, c = x.shape
+    x = x.reshape(b, d // ws, ws, h // ws, ws, w // ws, ws, c)
+    return x.permute(0, 1, 3, 5, 2, 4, 6, 7).reshape(-1, ws * ws * ws, c)
+
+
+class _WindowAttention(torch.autograd.Function):
+    """Forward = the CUDA kernels.  Backward (training, BASELINE config 5) currently re-derives the gradient by
+    recomputing the window attention with torch ops under autograd - a library path, listed as a gap in DESIGN.md."""
+
+    @staticmethod
+    def forward(ctx, x, qkv_w, qkv_b, proj_w, proj_b, table, index, bias_t, heads, ws, scale):
+        ctx.save_for_backward(x, qkv_w, qkv_b, proj_w, proj_b, table, index)
+        ctx.cfg = (heads, ws, scale)
+        return _window_attention_raw(x, qkv_w, qkv_b, proj_w, proj_b, bias_t, heads, ws, scale)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, qkv_w, qkv_b, proj_w, proj_b, table, index = ctx.saved_tensors
+        heads, ws, scale = ctx.cfg
+        with torch.enable_grad():
+            leaves = [t.detach().float().requires_grad_(True) for t in (x, qkv_w, qkv_b, proj_w, proj_b, table)]
+            xx, wq, bq, wp, bp, tb = leaves
+            win = _window_partition(xx, ws)
+            b_, n, c = win.shape
+            qkv = torch.nn.functional.linear(win, wq, bq).reshape(b_, n, 3, heads, c // heads).permute(2, 0, 3, 1, 4)
+            s = (qkv[0] * scale) @ qkv[1].transpose(-2, -1)
+            s = s + tb[index.reshape(-1)].reshape(n, n, heads).permute(2, 0, 1)[None]
+            o = (torch.softmax(s, -1) @ qkv[2]).transpose(1, 2).reshape(b_, n, c)
+            y = torch.nn.functional.linear(o, wp, bp).reshape(x.shape)
+            grads = torch.autograd.grad(y, leaves, g.float())
+        srcs = (x, qkv_w, qkv_b, proj_w, proj_b, table)
+        out = [gr.to(s_.dtype) for gr, s_ in zip(grads, srcs)]
+        return out[0], out[1], out[2], out[3], out[4], out[5], None, None, None, None, None
+
+
+def window_attention(x, qkv_w, qkv_b, proj_w, proj_b, table, index, bias_t, heads: int, ws: int, scale: float):
+    """Window partition + attention + reshape-only reverse on channels-last ``x[B, D1, H1, W1, C]``.
+
+    Returns the window-major result buffer viewed as ``[B, D1, H1, W1, C]`` - exactly what the reference produces at
+    ``wave_helper.py:497-499`` (it never applies the inverse permute)."""
+    return _WindowAttention.apply(x, qkv_w, qkv_b, proj_w, proj_b, table, index, bias_t, heads, ws, scale)
+
+
+# ============================================================================================ sliding window ====
+def sw_gather(vol: torch.Tensor, starts: torch.Tensor, roi, dtype: torch.dtype, channels_last: bool) -> torch.Tensor:
+    dev = _need_cuda(vol, starts)
+    if vol.dtype != torch.float32 or vol.dim() != 5:
+        raise ValueError("volume must be fp32 [Bv, C, D, H, W]")
+    vol = vol.contiguous()
+    _, C, D, H, W = vol.shape
+    n = starts.shape[0]
+    r0, r1, r2 = roi
+    shape = (n, r0, r1, r2, C) if channels_last else (n, C, r0, r1, r2)
+    win = torch.empty(shape, dtype=dtype, device=dev)
+    with torch.cuda.device(dev):
+        st = _lib.lib().wf_sw_gather(vol.data_ptr(), win.data_ptr(), starts.data_ptr(), n, _dtype_code(win),
+                                     int(channels_last), C, D, H, W, r0, r1, r2, _stream(dev))
+    _lib.check(st, "wf_sw_gather")
+    _count()
+    return win
+
+
+def sw_accumulate(seg: torch.Tensor, acc: torch.Tensor, starts: torch.Tensor, gz, gy, gx, floor_w: float,
+                  channels_last: bool) -> None:
+    dev = _need_cuda(seg, acc, starts, gz, gy, gx)
+    seg = seg.contiguous()
+    n = seg.shape[0]
+    if channels_last:
+        _, r0, r1, r2, K = seg.shape
+    else:
+        _, K, r0, r1, r2 = seg.shape
+    _, K2, D, H, W = acc.shape
+    if K2 != K or acc.dtype != torch.float32 or not acc.is_contiguous():
+        raise ValueError("accumulator must be contiguous fp32 [Bv, K, D, H, W]")
+    with torch.cuda.device(dev):
+        st = _lib.lib().wf_sw_accumulate(seg.data_ptr(), acc.data_ptr(), starts.data_ptr(), gz.data_ptr(), gy.data_ptr(),
+                                         gx.data_ptr(), float(floor_w), n, _dtype_code(seg), int(channels_last), K, D, H,
+                                         W, r0, r1, r2, _stream(dev))
+    _lib.check(st, "wf_sw_accumulate")
+    _count()
+
+
+def sw_finalize(acc: torch.Tensor, all_starts: torch.Tensor, gz, gy, gx, floor_w: float, roi,
+                labels: Optional[torch.Tensor] = None) -> None:
+    dev = _need_cuda(acc, all_starts, gz, gy, gx, labels)
+    Bv, K, D, H, W = acc.shape
+    r0, r1, r2 = roi
+    with torch.cuda.device(dev):
+        st = _lib.lib().wf_sw_finalize(acc.data_ptr(), _ptr(labels), all_starts.data_ptr(), all_starts.shape[0],
+                                       gz.data_ptr(), gy.data_ptr(), gx.data_ptr(), float(floor_w), Bv, K, D, H, W, r0,
+                                       r1, r2, _stream(dev))
+    _lib.check(st, "wf_sw_finalize")
+    _count()
