@@ -96,6 +96,30 @@ int wf_window_attn_fwd(const void *x, const void *qkv_w, const void *qkv_b, cons
                        int D1, int H1, int W1, int C, int heads, int ws, float scale, void *stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Block glue that dominated the step as library calls, channels-last, fp32 accumulate.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* Depthwise 3x3x3 convolution, zero padding 1: y[b,z,y,x,c] = bias[c] + sum_taps w27[tap][c] * x[b,z+dz,y+dy,x+dx,c].
+ * Replaces CCF_FFN.dwconv (reference network_models/wave_helper.py:231-232,283) and ProjectionUpsample.conv1[1]
+ * (wave_helper.py:44).  x, y: [B, D, H, W, C] dense channels-last; w27: fp32 [27][C], tap = (dz+1)*9+(dy+1)*3+(dx+1),
+ * i.e. the [C,1,3,3,3] weight transposed; bias: fp32 [C] or NULL. */
+int wf_dwconv3d_ndhwc(const void *x, const float *w27, const float *bias, void *y, int dtype, int B, int D, int H, int W,
+                      int C, void *stream);
+
+/* Affine-free InstanceNorm3d statistics of x [B, S voxels, C] (voxel stride x_vox_stride): sums is scratch
+ * (fp64 [B][C][2]), mean_rstd receives fp32 [B][C][2] = (mean, 1/sqrt(var + eps)), biased variance.
+ * Replaces the statistics half of nn.InstanceNorm3d in MONAI UnetResBlock (monai/networks/blocks/dynunet_block.py:
+ * 98-111) and ChannelCalibration (reference network_models/network_backbone.py:118-121). */
+int wf_instnorm_stats_ndhwc(const void *x, double *sums, float *mean_rstd, int dtype, int B, int64_t S, int C,
+                            int64_t x_vox_stride, float eps, void *stream);
+
+/* y = act((x - mean) * rstd + R) with R = 0 (res NULL), res (res_mean_rstd NULL) or (res - mean_r) * rstd_r.
+ * act: 0 none, 1 ReLU, 2 LeakyReLU(slope).  Fuses norm + residual add + activation of dynunet_block.py:100-110. */
+int wf_instnorm_apply_ndhwc(const void *x, const float *mean_rstd, const void *res, const float *res_mean_rstd, void *y,
+                            int act, float slope, int dtype, int B, int64_t S, int C, int64_t x_vox_stride,
+                            int64_t res_vox_stride, int64_t y_vox_stride, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Sliding-window stitching (re-hosted MONAI inferer, reference monai/inferers/utils.py:216-299).
  * ---------------------------------------------------------------------------------------------------------- */
 

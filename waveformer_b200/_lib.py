@@ -27,6 +27,9 @@ SIGNATURES = {
     "wf_relpos_bias_expand": (_I, [_VOIDP, _I, _VOIDP, _VOIDP, _I, _I, _I, _VOIDP]),
     "wf_window_attn_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I, _I, _I, _I]),
     "wf_window_attn_fwd": (_I, [_VOIDP] * 8 + [_SZ, _I, _I, _I, _I, _I, _I, _I, _I, _F, _VOIDP]),
+    "wf_dwconv3d_ndhwc": (_I, [_VOIDP, _VOIDP, _VOIDP, _VOIDP, _I, _I, _I, _I, _I, _I, _VOIDP]),
+    "wf_instnorm_stats_ndhwc": (_I, [_VOIDP, _VOIDP, _VOIDP, _I, _I, _I64, _I, _I64, _F, _VOIDP]),
+    "wf_instnorm_apply_ndhwc": (_I, [_VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _I, _F, _I, _I, _I64, _I, _I64, _I64, _I64, _VOIDP]),
     "wf_sw_gather": (_I, [_VOIDP, _VOIDP, _VOIDP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VOIDP]),
     "wf_sw_accumulate": (_I, [_VOIDP] * 6 + [_F, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VOIDP]),
     "wf_sw_finalize": (_I, [_VOIDP, _VOIDP, _VOIDP, _I, _VOIDP, _VOIDP, _VOIDP, _F] + [_I] * 8 + [_VOIDP]),

@@ -1,0 +1,184 @@
+// InstanceNorm3d (affine-free) on channels-last activations, fused with the activation and the residual add that
+// follow it in the reference's conv blocks (sm_100a).
+//
+// Reference call sites: MONAI UnetResBlock.forward (monai/networks/blocks/dynunet_block.py:98-111: norm1 + lrelu,
+// norm2, norm3, `out += residual`, lrelu) and ChannelCalibration.forward (network_models/network_backbone.py:118-128).
+// torch's instance_norm copies channels-last tensors to NCDHW and back (35 % of the step before this kernel).
+// Two streaming passes: per-(b, c) sum / sum-of-squares (fp32 per thread, fp64 across blocks, so E[x^2]-E[x]^2 does
+// not cancel), then y = act((x - mean) * rstd [+ (r - mean_r) * rstd_r | + r]).
+#include "wf_common.cuh"
+
+namespace wf {
+
+template <typename T, int VEC> struct NVec {
+    __device__ static inline void load(const T *p, float (&v)[VEC]) {
+        if constexpr (VEC == 1) v[0] = to_f32(*p);
+        else Pack<T>::unpack(*reinterpret_cast<const typename Pack<T>::raw *>(p), v);
+    }
+    __device__ static inline void store(T *p, const float (&v)[VEC]) {
+        if constexpr (VEC == 1) *p = from_f32<T>(v[0]);
+        else *reinterpret_cast<typename Pack<T>::raw *>(p) = Pack<T>::pack(v);
+    }
+};
+
+// grid (chunks, B); each block reduces `vox_per_block` voxels of one batch element for all channels
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) instnorm_stats_kernel(const T *__restrict__ x, double *__restrict__ sums,
+                                                             int64_t S, int C, int cvecs, int64_t vox_per_block,
+                                                             int64_t xs) {
+    extern __shared__ float red[];  // [256][2*VEC]
+    const int b = blockIdx.y;
+    const int group = 256 / cvecs;  // voxels handled per sweep
+    const int tid = threadIdx.x;
+    const int cv = tid % cvecs;
+    const int vg = tid / cvecs;
+    const int64_t v0 = (int64_t)blockIdx.x * vox_per_block;
+    const int64_t v1 = min(S, v0 + vox_per_block);
+    float s[VEC], q[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) s[e] = q[e] = 0.f;
+    if (vg < group) {
+        const T *base = x + (int64_t)b * S * xs + cv * VEC;
+        for (int64_t v = v0 + vg; v < v1; v += group) {
+            float f[VEC];
+            NVec<T, VEC>::load(base + v * xs, f);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                s[e] += f[e];
+                q[e] = fmaf(f[e], f[e], q[e]);
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+        red[tid * 2 * VEC + e] = s[e];
+        red[tid * 2 * VEC + VEC + e] = q[e];
+    }
+    __syncthreads();
+    // thread t < cvecs*2*VEC sums column t over the voxel groups
+    const int ncol = cvecs * 2 * VEC;
+    for (int col = tid; col < ncol; col += 256) {
+        const int ccv = col / (2 * VEC), e2 = col % (2 * VEC);
+        double a = 0.0;
+        for (int g = 0; g < group; ++g) a += (double)red[(g * cvecs + ccv) * 2 * VEC + e2];
+        const int c = ccv * VEC + (e2 % VEC);
+        atomicAdd(sums + ((int64_t)b * C + c) * 2 + (e2 / VEC), a);
+    }
+}
+
+__global__ void instnorm_finalize_kernel(const double *__restrict__ sums, float *__restrict__ mr, int n, double inv_s,
+                                         double eps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double mean = sums[2 * i] * inv_s;
+    double var = sums[2 * i + 1] * inv_s - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    mr[2 * i] = (float)mean;
+    mr[2 * i + 1] = (float)(1.0 / sqrt(var + eps));
+}
+
+// act: 0 none, 1 relu, 2 leaky relu (slope)
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) instnorm_apply_kernel(const T *__restrict__ x, const float *__restrict__ mr,
+                                                             const T *__restrict__ res, const float *__restrict__ res_mr,
+                                                             T *__restrict__ y, int64_t total, int64_t S, int C,
+                                                             int cvecs, int64_t xs, int64_t rs, int64_t ys, int act,
+                                                             float slope) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int cv = (int)(idx % cvecs);
+    const int64_t vox = idx / cvecs;  // b*S + v
+    const int64_t b = vox / S;
+    const int c0 = cv * VEC;
+    float f[VEC];
+    NVec<T, VEC>::load(x + vox * xs + c0, f);
+    const float *m = mr + ((int64_t)b * C + c0) * 2;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) f[e] = (f[e] - __ldg(m + 2 * e)) * __ldg(m + 2 * e + 1);
+    if (res != nullptr) {
+        float r[VEC];
+        NVec<T, VEC>::load(res + vox * rs + c0, r);
+        if (res_mr != nullptr) {
+            const float *m2 = res_mr + ((int64_t)b * C + c0) * 2;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) r[e] = (r[e] - __ldg(m2 + 2 * e)) * __ldg(m2 + 2 * e + 1);
+        }
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) f[e] += r[e];
+    }
+    if (act == 1) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) f[e] = fmaxf(f[e], 0.f);
+    } else if (act == 2) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) f[e] = f[e] > 0.f ? f[e] : f[e] * slope;
+    }
+    NVec<T, VEC>::store(y + vox * ys + c0, f);
+}
+
+template <typename T>
+static int stats_launch(const T *x, double *sums, float *mr, int B, int64_t S, int C, int64_t xs, float eps, cudaStream_t st) {
+    constexpr int V = Pack<T>::VEC;
+    WF_CUDA_CHECK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)B * C, st));
+    const bool vec = (C % V == 0) && (C / V <= 256) && aligned16(x) && (xs * sizeof(T)) % 16 == 0;
+    const int64_t vpb = 2048;
+    dim3 grid((unsigned)((S + vpb - 1) / vpb), (unsigned)B);
+    if (vec) {
+        instnorm_stats_kernel<T, V><<<grid, 256, 256 * 2 * V * sizeof(float), st>>>(x, sums, S, C, C / V, vpb, xs);
+    } else {
+        if (C > 256) return WF_ERR_UNSUPPORTED;
+        instnorm_stats_kernel<T, 1><<<grid, 256, 256 * 2 * sizeof(float), st>>>(x, sums, S, C, C, vpb, xs);
+    }
+    WF_LAUNCH_CHECK();
+    const int n = B * C;
+    instnorm_finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(sums, mr, n, 1.0 / (double)S, (double)eps);
+    WF_LAUNCH_CHECK();
+    return WF_OK;
+}
+
+template <typename T>
+static int apply_launch(const T *x, const float *mr, const T *res, const float *res_mr, T *y, int B, int64_t S, int C,
+                        int64_t xs, int64_t rs, int64_t ys, int act, float slope, cudaStream_t st) {
+    constexpr int V = Pack<T>::VEC;
+    const size_t e = sizeof(T);
+    const bool vec = (C % V == 0) && aligned16(x) && aligned16(y) && (xs * e) % 16 == 0 && (ys * e) % 16 == 0 &&
+                     (res == nullptr || (aligned16(res) && (rs * e) % 16 == 0));
+    if (vec) {
+        const int64_t total = (int64_t)B * S * (C / V);
+        instnorm_apply_kernel<T, V><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, mr, res, res_mr, y, total, S, C, C / V, xs, rs, ys, act, slope);
+    } else {
+        const int64_t total = (int64_t)B * S * C;
+        instnorm_apply_kernel<T, 1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, mr, res, res_mr, y, total, S, C, C, xs, rs, ys, act, slope);
+    }
+    WF_LAUNCH_CHECK();
+    return WF_OK;
+}
+
+}  // namespace wf
+
+extern "C" int wf_instnorm_stats_ndhwc(const void *x, double *sums, float *mean_rstd, int dtype, int B, int64_t S, int C,
+                                       int64_t x_vox_stride, float eps, void *stream) {
+    if (!x || !sums || !mean_rstd) return WF_ERR_NULL_POINTER;
+    if (B <= 0 || S <= 0 || C <= 0 || x_vox_stride < C) return WF_ERR_BAD_SHAPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == WF_F32) return wf::stats_launch<float>((const float *)x, sums, mean_rstd, B, S, C, x_vox_stride, eps, st);
+    if (dtype == WF_BF16)
+        return wf::stats_launch<__nv_bfloat16>((const __nv_bfloat16 *)x, sums, mean_rstd, B, S, C, x_vox_stride, eps, st);
+    return WF_ERR_BAD_DTYPE;
+}
+
+extern "C" int wf_instnorm_apply_ndhwc(const void *x, const float *mean_rstd, const void *res, const float *res_mean_rstd,
+                                       void *y, int act, float slope, int dtype, int B, int64_t S, int C,
+                                       int64_t x_vox_stride, int64_t res_vox_stride, int64_t y_vox_stride, void *stream) {
+    if (!x || !mean_rstd || !y) return WF_ERR_NULL_POINTER;
+    if (B <= 0 || S <= 0 || C <= 0 || x_vox_stride < C || y_vox_stride < C || (res && res_vox_stride < C)) return WF_ERR_BAD_SHAPE;
+    if (act < 0 || act > 2) return WF_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == WF_F32)
+        return wf::apply_launch<float>((const float *)x, mean_rstd, (const float *)res, res_mean_rstd, (float *)y, B, S, C,
+                                       x_vox_stride, res_vox_stride, y_vox_stride, act, slope, st);
+    if (dtype == WF_BF16)
+        return wf::apply_launch<__nv_bfloat16>((const __nv_bfloat16 *)x, mean_rstd, (const __nv_bfloat16 *)res, res_mean_rstd,
+                                               (__nv_bfloat16 *)y, B, S, C, x_vox_stride, res_vox_stride, y_vox_stride, act, slope, st);
+    return WF_ERR_BAD_DTYPE;
+}

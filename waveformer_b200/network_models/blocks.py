@@ -14,6 +14,13 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .. import ops
+
+
+def use_fused(x: torch.Tensor) -> bool:
+    """Inference on CUDA takes the fused sm_100a kernels; autograd (training) keeps the differentiable torch modules."""
+    return x.is_cuda and not torch.is_grad_enabled()
+
 
 def _same_padding(kernel_size: int, stride: int) -> int:
     pad = (kernel_size - stride + 1) / 2  # dynunet_block.py:301-310
@@ -72,6 +79,13 @@ class UnetResBlock(nn.Module):
             self.norm3 = _norm(norm_name, out_channels)
 
     def forward(self, inp: torch.Tensor) -> torch.Tensor:
+        if use_fused(inp):
+            # InstanceNorm + LeakyReLU, and InstanceNorm (+ InstanceNorm'd shortcut) + add + LeakyReLU: one kernel each
+            out = ops.instance_norm_act(self.conv1(inp), "leakyrelu", 0.01, eps=self.norm1.eps)
+            out = self.conv2(out)
+            if self.downsample:
+                return ops.instance_norm_act(out, "leakyrelu", 0.01, res=self.conv3(inp), res_norm=True, eps=self.norm2.eps)
+            return ops.instance_norm_act(out, "leakyrelu", 0.01, res=inp, eps=self.norm2.eps)
         out = self.lrelu(self.norm1(self.conv1(inp)))
         out = self.norm2(self.conv2(out))
         res = self.norm3(self.conv3(inp)) if self.downsample else inp
@@ -89,6 +103,9 @@ class UnetBasicBlock(nn.Module):
         self.norm2 = _norm(norm_name, out_channels)
 
     def forward(self, inp: torch.Tensor) -> torch.Tensor:
+        if use_fused(inp):
+            out = ops.instance_norm_act(self.conv1(inp), "leakyrelu", 0.01, eps=self.norm1.eps)
+            return ops.instance_norm_act(self.conv2(out), "leakyrelu", 0.01, eps=self.norm2.eps)
         out = self.lrelu(self.norm1(self.conv1(inp)))
         return self.lrelu(self.norm2(self.conv2(out)))
 

@@ -9,7 +9,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .blocks import UnetOutBlock, UnetrBasicBlock, UnetrUpBlock
+from .. import ops
+from .blocks import UnetOutBlock, UnetrBasicBlock, UnetrUpBlock, use_fused
 from .idwt_upsample import UnetrIDWTBlock
 from .legacy import ProjectionHead  # noqa: F401  (re-exported like the reference)
 from .wave_helper import ProjectionUpsample
@@ -37,9 +38,14 @@ class ChannelCalibration(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         identity = self.residual(x)
-        t = self.relu(self.norm_reduce(self.reduce(x)))
-        t = self.relu(self.norm_conv(self.conv(t)))
-        t = self.norm_expand(self.expand(t))
+        if use_fused(x) and isinstance(self.norm_reduce, nn.InstanceNorm3d) and not self.norm_reduce.affine:
+            t = ops.instance_norm_act(self.reduce(x), "relu", eps=self.norm_reduce.eps)
+            t = ops.instance_norm_act(self.conv(t), "relu", eps=self.norm_conv.eps)
+            t = ops.instance_norm_act(self.expand(t), "none", eps=self.norm_expand.eps)
+        else:
+            t = self.relu(self.norm_reduce(self.reduce(x)))
+            t = self.relu(self.norm_conv(self.conv(t)))
+            t = self.norm_expand(self.expand(t))
         se = t.mean(dim=(2, 3, 4))
         se = self.sigmoid(self.fc2(F.relu(self.fc1(se))))
         return self.relu(t * se[:, :, None, None, None] + identity)

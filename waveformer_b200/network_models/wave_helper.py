@@ -141,9 +141,22 @@ class CCF_FFN(nn.Module):
         # the 1^3 convolution is a per-voxel linear map: run it on the channels-last tensor directly
         t = F.linear(x, self.pwconv.weight.view(self.C_hid, C), self.pwconv.bias)
         t = self.act(self.norm1(t))
-        t = self.dwconv(t.permute(0, 4, 1, 2, 3))          # NCDHW view of channels-last memory (no copy)
-        t = self.act(self.norm2(t.permute(0, 2, 3, 4, 1)))
+        if x.is_cuda and not torch.is_grad_enabled():
+            t = ops.dwconv3d_channels_last(t, *self._packed_dwconv())      # hand-written stencil, channels-last
+        else:
+            t = self.dwconv(t.permute(0, 4, 1, 2, 3)).permute(0, 2, 3, 4, 1)
+        t = self.act(self.norm2(t))
         return x + self.fc(t)
+
+    def _packed_dwconv(self):
+        w = self.dwconv.weight
+        key = (w._version, w.data_ptr(), w.device)
+        cache = getattr(self, "_dw_cache", None)
+        if cache is None or cache[0] != key:
+            b = self.dwconv.bias
+            cache = (key, ops.repack_depthwise_weight(w), None if b is None else b.detach().float().contiguous())
+            self._dw_cache = cache
+        return cache[1], cache[2]
 
     def flops(self):
         return 0
@@ -314,9 +327,23 @@ class ProjectionUpsample(nn.Module):
                 nn.Conv3d(in_channels, out_channels, kernel_size=1, stride=1))
         self.act = nn.GELU()
 
+    def _packed_dwconv(self):
+        w = self.conv1[1].weight
+        key = (w._version, w.data_ptr(), w.device)
+        cache = getattr(self, "_dw_cache", None)
+        if cache is None or cache[0] != key:
+            b = self.conv1[1].bias
+            cache = (key, ops.repack_depthwise_weight(w), None if b is None else b.detach().float().contiguous())
+            self._dw_cache = cache
+        return cache[1], cache[2]
+
     def forward(self, x):
         up = self.conv1[0](x)          # one upsample shared by both branches (the reference computes it twice)
-        y = self.conv3(self.act(self.conv2(self.norm(self.conv1[1](up)))))
+        if x.is_cuda and not torch.is_grad_enabled():
+            dw = ops.dwconv3d_channels_last(up.permute(0, 2, 3, 4, 1), *self._packed_dwconv()).permute(0, 4, 1, 2, 3)
+        else:
+            dw = self.conv1[1](up)
+        y = self.conv3(self.act(self.conv2(self.norm(dw))))
         if self.do_res:
             y = y + self.res_conv[1](up)
         return y

@@ -339,6 +339,87 @@ def window_attention(x, qkv_w, qkv_b, proj_w, proj_b, table, index, bias_t, head
     return _WindowAttention.apply(x, qkv_w, qkv_b, proj_w, proj_b, table, index, bias_t, heads, ws, scale)
 
 
+
+# ================================================================================================ block glue ====
+def dwconv3d_channels_last(x: torch.Tensor, w27: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """Depthwise 3x3x3 conv (padding 1) on ``x[B, D, H, W, C]``; ``w27`` fp32 ``[27, C]``, ``bias`` fp32 ``[C]``."""
+    dev = _need_cuda(x, w27, bias)
+    if x.dim() != 5:
+        raise ValueError("expected [B, D, H, W, C]")
+    x = x.contiguous()
+    B, D, H, W, C = x.shape
+    if w27.dtype != torch.float32 or tuple(w27.shape) != (27, C) or not w27.is_contiguous():
+        raise ValueError("w27 must be contiguous fp32 [27, C]")
+    y = torch.empty_like(x)
+    with torch.cuda.device(dev):
+        st = _lib.lib().wf_dwconv3d_ndhwc(x.data_ptr(), w27.data_ptr(), _ptr(bias), y.data_ptr(), _dtype_code(x), B, D, H,
+                                          W, C, _stream(dev))
+    _lib.check(st, "wf_dwconv3d_ndhwc")
+    _count()
+    return y
+
+
+def repack_depthwise_weight(weight: torch.Tensor) -> torch.Tensor:
+    """[C, 1, 3, 3, 3] conv weight -> fp32 [27, C] (tap-major) for ``dwconv3d_channels_last``."""
+    c = weight.shape[0]
+    return weight.detach().reshape(c, 27).t().contiguous().float()
+
+
+_ACT = {"none": 0, None: 0, "relu": 1, "leakyrelu": 2, "lrelu": 2}
+
+
+def _ndhwc_view(x: torch.Tensor):
+    """[B, C, D, H, W] -> ([B, D, H, W, C] view, voxel stride); copies only if the tensor is not channels-last-dense."""
+    v = x.permute(0, 2, 3, 4, 1)
+    vs = _voxel_stride(v)
+    if vs is None:
+        v = v.contiguous()
+        vs = v.shape[-1]
+    return v, vs
+
+
+def _instnorm_stats(v: torch.Tensor, vs: int, eps: float) -> torch.Tensor:
+    dev = v.device
+    B, D, H, W, C = v.shape
+    sums = torch.empty(B * C * 2, dtype=torch.float64, device=dev)
+    mr = torch.empty(B * C * 2, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        st = _lib.lib().wf_instnorm_stats_ndhwc(v.data_ptr(), sums.data_ptr(), mr.data_ptr(), _dtype_code(v), B,
+                                                D * H * W, C, vs, float(eps), _stream(dev))
+    _lib.check(st, "wf_instnorm_stats_ndhwc")
+    _count(2)
+    return mr
+
+
+def instance_norm_act(x: torch.Tensor, act: str = "none", slope: float = 0.01, res: Optional[torch.Tensor] = None,
+                      res_norm: bool = False, eps: float = 1e-5, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``act(InstanceNorm(x) + R)`` for ``x[B, C, D, H, W]`` (any strides; channels-last-3d is copy-free), where ``R`` is
+    nothing, ``res`` or ``InstanceNorm(res)``.  Returns a [B, C, D, H, W] tensor with channels-last-3d strides; ``out``
+    (optional) is a [B, D, H, W, C] channels-last destination, e.g. a channel slice of a concat buffer."""
+    dev = _need_cuda(x, res, out)
+    v, vs = _ndhwc_view(x)
+    B, D, H, W, C = v.shape
+    mr = _instnorm_stats(v, vs, eps)
+    rv, rs, rmr = None, C, None
+    if res is not None:
+        if res.shape != x.shape or res.dtype != x.dtype:
+            raise ValueError("residual must match x")
+        rv, rs = _ndhwc_view(res)
+        if res_norm:
+            rmr = _instnorm_stats(rv, rs, eps)
+    if out is None:
+        out = torch.empty((B, D, H, W, C), dtype=x.dtype, device=dev)
+    ys = _voxel_stride(out)
+    if ys is None or tuple(out.shape) != (B, D, H, W, C) or out.dtype != x.dtype:
+        raise ValueError("out must be a voxel-dense [B, D, H, W, C] tensor of x's dtype")
+    with torch.cuda.device(dev):
+        st = _lib.lib().wf_instnorm_apply_ndhwc(v.data_ptr(), mr.data_ptr(), _ptr(rv), _ptr(rmr), out.data_ptr(),
+                                                _ACT[act], float(slope), _dtype_code(x), B, D * H * W, C, vs, rs, ys,
+                                                _stream(dev))
+    _lib.check(st, "wf_instnorm_apply_ndhwc")
+    _count()
+    return out.permute(0, 4, 1, 2, 3)
+
 # ============================================================================================ sliding window ====
 def sw_gather(vol: torch.Tensor, starts: torch.Tensor, roi, dtype: torch.dtype, channels_last: bool) -> torch.Tensor:
     dev = _need_cuda(vol, starts)
