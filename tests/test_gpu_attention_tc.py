@@ -1,0 +1,69 @@
+"""GPU: the tcgen05 / TMEM attention path (bf16) against the fp32 oracle, the reference golden outputs and the
+CUDA-core kernels run on the same inputs (WF_ATTN_IMPL=simt)."""
+import os
+
+import pytest
+import torch
+
+from oracle import model as om
+from oracle.state import ModelConfig, make_state_dict
+
+from helpers import load_npz, max_rel, seeded_randn, sub_state
+
+pytestmark = pytest.mark.gpu
+CFG = ModelConfig(img_size=(128,) * 3)
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return make_state_dict(CFG, seed=0)
+
+
+def _attn(sd, stage, c, h):
+    from waveformer_b200.network_models import Attention
+    m = Attention(c, num_heads=h, qkv_bias=True, window_size=8, img_size=(8, 8, 8)).eval()
+    m.load_state_dict(sub_state(sd, f"waveformer_encoder.block{stage + 1}.1.attn"), strict=True)
+    return m.cuda().to(torch.bfloat16)
+
+
+def _run(m, x, impl):
+    old = os.environ.get("WF_ATTN_IMPL")
+    os.environ["WF_ATTN_IMPL"] = impl
+    try:
+        with torch.no_grad():
+            y = m.forward_grid(x)
+        torch.cuda.synchronize()
+        return y
+    finally:
+        if old is None:
+            os.environ.pop("WF_ATTN_IMPL", None)
+        else:
+            os.environ["WF_ATTN_IMPL"] = old
+
+
+@pytest.mark.parametrize("stage,c,h,b_", [(0, 48, 3, 3), (1, 96, 6, 2), (2, 192, 12, 1), (3, 384, 24, 1)])
+def test_tensor_core_path_matches_reference_golden(sd, stage, c, h, b_):
+    g = load_npz("attention_ws8.npz")
+    x = seeded_randn((b_, 512, c), 100 + stage).cuda().bfloat16().reshape(b_, 8, 8, 8, c)
+    m = _attn(sd, stage, c, h)
+    tc = _run(m, x, "tc").float().cpu().reshape(b_, 512, c)
+    simt = _run(m, x, "simt").float().cpu().reshape(b_, 512, c)
+    assert torch.isfinite(tc).all()
+    assert max_rel(tc, g[f"out_{c}"]) < 2e-2          # bf16 gate vs the fp32 reference
+    assert max_rel(tc, simt) < 1.5e-2                  # two independent device implementations agree
+
+
+@pytest.mark.parametrize("grid,batch", [((16, 16, 16), 2), ((32, 32, 32), 2), ((8, 16, 24), 1), ((64, 64, 64), 1)])
+def test_tensor_core_path_many_windows(sd, grid, batch):
+    """Several windows per CTA (persistent loop, double-buffered bulk copies) and the reshape-only reverse."""
+    p = "waveformer_encoder.block1.0.attn"
+    m = _attn(sd, 0, 48, 3)
+    m.load_state_dict(sub_state(sd, p), strict=True)
+    m = m.cuda().to(torch.bfloat16)
+    x = seeded_randn((batch,) + grid + (48,), 35)
+    got = _run(m, x.cuda().bfloat16(), "tc").float().cpu()
+    if grid[0] * grid[1] * grid[2] <= 16 ** 3 * 2:
+        want = om.window_attention(sd, p, om.window_partition(x.bfloat16().float(), 8), 3).reshape(x.shape)
+        assert max_rel(got, want) < 2e-2
+    simt = _run(m, x.cuda().bfloat16(), "simt").float().cpu()
+    assert max_rel(got, simt) < 1.5e-2

@@ -1,4 +1,6 @@
 // C-ABI glue: version / errors and the window-attention dispatcher (see include/waveformer_b200.h).
+#include <stdlib.h>
+
 #include "wf_common.cuh"
 
 namespace wf {
@@ -8,6 +10,11 @@ template <typename T>
 int attn_simt_forward(const T *x, const T *qkv_w, const T *qkv_b, const T *proj_w, const T *proj_b,
                       const float *bias_t, T *out, void *workspace, int B, int D1, int H1, int W1, int C, int heads,
                       int ws, float scale, cudaStream_t st);
+bool attn_tc_supported(int D1, int H1, int W1, int C, int heads, int ws);
+int attn_tc_forward(const __nv_bfloat16 *x, const __nv_bfloat16 *qkv_w, const __nv_bfloat16 *qkv_b,
+                    const __nv_bfloat16 *proj_w, const __nv_bfloat16 *proj_b, const float *bias_t,
+                    __nv_bfloat16 *out, void *workspace, int B, int D1, int H1, int W1, int C, int heads, float scale,
+                    cudaStream_t st);
 }  // namespace wf
 
 extern "C" const char *wf_version(void) { return "waveformer_b200 0.1.0 (sm_100a)"; }
@@ -58,6 +65,14 @@ extern "C" int wf_window_attn_fwd(const void *x, const void *qkv_w, const void *
         return wf::attn_simt_forward<float>((const float *)x, (const float *)qkv_w, (const float *)qkv_b,
                                             (const float *)proj_w, (const float *)proj_b, bias_t, (float *)out,
                                             workspace, B, D1, H1, W1, C, heads, ws, scale, st);
+    // bf16: tcgen05 / TMEM path for the reference geometry (512-token windows, head_dim 16); WF_ATTN_IMPL=simt forces
+    // the CUDA-core kernels (used by the tests to cross-check the two implementations on the device)
+    const char *impl = getenv("WF_ATTN_IMPL");
+    const bool force_simt = impl != nullptr && impl[0] == 's';
+    if (!force_simt && qkv_b != nullptr && wf::attn_tc_supported(D1, H1, W1, C, heads, ws))
+        return wf::attn_tc_forward((const __nv_bfloat16 *)x, (const __nv_bfloat16 *)qkv_w, (const __nv_bfloat16 *)qkv_b,
+                                   (const __nv_bfloat16 *)proj_w, (const __nv_bfloat16 *)proj_b, bias_t,
+                                   (__nv_bfloat16 *)out, workspace, B, D1, H1, W1, C, heads, scale, st);
     return wf::attn_simt_forward<__nv_bfloat16>((const __nv_bfloat16 *)x, (const __nv_bfloat16 *)qkv_w,
                                                 (const __nv_bfloat16 *)qkv_b, (const __nv_bfloat16 *)proj_w,
                                                 (const __nv_bfloat16 *)proj_b, bias_t, (__nv_bfloat16 *)out, workspace,

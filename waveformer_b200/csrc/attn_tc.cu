@@ -1,0 +1,378 @@
+// Kernel group 2, bf16 tensor-core path (tcgen05 + TMEM, sm_100a): window partition + QKV projection, attention core,
+// output projection, for windows of 8^3 = 512 tokens and head_dim 16 (every stage of the reference configuration).
+//
+// Replaces Block.window_partition (reference network_models/wave_helper.py:450-461), Attention.forward
+// (network_models/attention.py:83-104) and the reshape-only window reverse (wave_helper.py:498-499).
+//
+// Three launches:
+//   1. linear_tc_kernel<QKV>   D[128 x NT] = X_tile[128 x C] * Wqkv_tile[NT x C]^T  (tcgen05.mma, fp32 accum in TMEM);
+//      the window-partition gather is folded into the A-tile load; the epilogue adds the bias, folds scale*log2(e)
+//      into q and writes q/k/v per (window, head) in the 16-byte-chunked image [2][512][8] that IS the canonical
+//      no-swizzle UMMA operand layout, so the core kernel fetches whole operands with one bulk copy each.
+//   2. attn_core_tc_kernel     per (head, 128-query tile), persistent over windows: S = Q K^T (2 x MMA 128x256x16) into
+//      all 512 TMEM columns; 8 softmax warps (one TMEM lane = one query row; two warps per row split the key halves)
+//      do an exact two-pass softmax against a bf16 relative-position-bias tile that stays resident in shared memory
+//      across windows; P (bf16) overwrites S in place in TMEM and feeds O = P V as the TMEM A operand (32 x MMA
+//      128x16x16); Q/K/V of the next window are prefetched by bulk copies behind an mbarrier.
+//   3. linear_tc_kernel<PROJ>  out = O * Wproj^T + b, written in window order (= the reference's reshape-only reverse).
+//
+// With head_dim 16 the core is bound by the 512x512 exponentials per (window, head), not by the tensor pipe: per
+// 128x512 tile the MMAs need ~512 cycles while 65536 ex2 need >= 4096 cycles of the SM's 16/clk MUFU pipe.
+#include "tc_common.cuh"
+#include "wf_common.cuh"
+
+namespace wf {
+
+using namespace tc;
+
+struct TcWindowMap {
+    int D1, H1, W1, nWy, nWx, nW;  // ws = 8, N = 512
+    __device__ inline int64_t voxel(int64_t m) const {
+        const int tok = (int)(m & 511);
+        const int64_t win = m >> 9;
+        const int widx = (int)(win % nW);
+        const int64_t b = win / nW;
+        const int xb = widx % nWx, yb = (widx / nWx) % nWy, zb = widx / (nWx * nWy);
+        const int dx = tok & 7, dy = (tok >> 3) & 7, dz = tok >> 6;
+        return ((b * D1 + zb * 8 + dz) * H1 + yb * 8 + dy) * (int64_t)W1 + xb * 8 + dx;
+    }
+};
+
+constexpr float kLog2e = 1.4426950408889634f;
+
+// ------------------------------------------------------------------------------------------------ projections ----
+// grid (M/128, Nout/NT), 128 threads.  smem: A image [K/8][128][8] bf16, B image [K/8][NT][8] bf16 (no-swizzle canonical)
+template <bool QKV>
+__global__ void __launch_bounds__(128) linear_tc_kernel(const __nv_bfloat16 *__restrict__ A,
+                                                        const __nv_bfloat16 *__restrict__ Wt,
+                                                        const __nv_bfloat16 *__restrict__ bias,
+                                                        __nv_bfloat16 *__restrict__ out, int K, int NT, int Nout,
+                                                        TcWindowMap map, int heads, int64_t B_, float qscale,
+                                                        uint32_t tmem_cols) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int kchunks = K >> 3;
+    uint8_t *sA = smem;
+    uint8_t *sB = smem + (size_t)kchunks * 2048;
+    const int64_t m0 = (int64_t)blockIdx.x * 128;
+    const int n0 = blockIdx.y * NT;
+
+    if (warp == 0) tmem_alloc(&tmem_slot, tmem_cols);
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    // A tile: row r = tid, every 16-byte K chunk.  A warp writes 32 consecutive rows of one chunk: conflict-free.
+    {
+        const int64_t src_row = QKV ? map.voxel(m0 + tid) : (m0 + tid);
+        const uint4 *src = reinterpret_cast<const uint4 *>(A + src_row * K);
+        for (int kc = 0; kc < kchunks; ++kc)
+            *reinterpret_cast<uint4 *>(sA + (size_t)kc * 2048 + tid * 16) = __ldg(src + kc);
+    }
+    // B tile: rows n0 .. n0+NT-1 of the [Nout, K] weight
+    for (int idx = tid; idx < NT * kchunks; idx += 128) {
+        const int r = idx % NT, kc = idx / NT;
+        *reinterpret_cast<uint4 *>(sB + ((size_t)kc * NT + r) * 16) =
+            __ldg(reinterpret_cast<const uint4 *>(Wt + (int64_t)(n0 + r) * K) + kc);
+    }
+    fence_proxy_async();  // st.shared above -> visible to the tensor core's async proxy
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (tid == 0) {
+        const uint32_t idesc = instr_desc_bf16(128, NT, false);
+        const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+        for (int ks = 0; ks < (K >> 4); ++ks) {
+            const uint64_t da = smem_desc(a0 + ks * 2 * 2048, 2048, 128);
+            const uint64_t db = smem_desc(b0 + ks * 2 * NT * 16, NT * 16, 128);
+            mma_ss(tmem, da, db, idesc, ks > 0 ? 1u : 0u);
+        }
+        mma_commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    tc_fence_after();
+    // epilogue: thread = output row; 16 columns (= one head's q, k or v slice when QKV) per step
+    const int64_t m = m0 + tid;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    for (int c = 0; c < NT; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem + lane_base + c, r);
+        tmem_wait_ld();
+        const int n = n0 + c;
+        float v[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]) + (bias ? __bfloat162float(bias[n + e]) : 0.f);
+        if (QKV) {
+            const int C = heads * 16;
+            const int which = n / C, hh = (n % C) >> 4;
+            if (which == 0) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[e] *= qscale;
+            }
+            const int64_t win = m >> 9;
+            const int tok = (int)(m & 511);
+            __nv_bfloat16 *dst = out + (((int64_t)which * B_ + win) * heads + hh) * 8192 + tok * 8;
+            uint4 lo, hi;
+            lo.x = pack_bf16(v[0], v[1]); lo.y = pack_bf16(v[2], v[3]); lo.z = pack_bf16(v[4], v[5]); lo.w = pack_bf16(v[6], v[7]);
+            hi.x = pack_bf16(v[8], v[9]); hi.y = pack_bf16(v[10], v[11]); hi.z = pack_bf16(v[12], v[13]); hi.w = pack_bf16(v[14], v[15]);
+            *reinterpret_cast<uint4 *>(dst) = lo;          // chunk 0: head dims 0..7
+            *reinterpret_cast<uint4 *>(dst + 4096) = hi;   // chunk 1: head dims 8..15
+        } else {
+            uint4 lo, hi;
+            lo.x = pack_bf16(v[0], v[1]); lo.y = pack_bf16(v[2], v[3]); lo.z = pack_bf16(v[4], v[5]); lo.w = pack_bf16(v[6], v[7]);
+            hi.x = pack_bf16(v[8], v[9]); hi.y = pack_bf16(v[10], v[11]); hi.z = pack_bf16(v[12], v[13]); hi.w = pack_bf16(v[14], v[15]);
+            uint4 *dst = reinterpret_cast<uint4 *>(out + m * Nout + n);
+            dst[0] = lo;
+            dst[1] = hi;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------------ core ------
+constexpr int kBiasPitch = 520;                       // bf16 elements per bias row (512 + 8 pad: conflict-free LDS.128)
+constexpr int kBiasBytes = 128 * kBiasPitch * 2;      // 133120
+constexpr int kStageBytes = 4096 + 16384 + 16384;     // Q tile [2][128][8] + K [2][512][8] + V [2][512][8]
+constexpr int kCoreSmem = kBiasBytes + 2 * kStageBytes + 2 * 2 * 128 * 4;  // + row max / row sum exchange
+
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ void unpack8(const uint4 &u, float (&f)[8]) {
+    f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
+    f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
+    f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
+    f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
+}
+
+// grid = combos * groups, combos = heads * 4 (head, 128-query tile); CTA (combo, g) walks windows g, g+groups, ...
+// 256 threads: warp w handles TMEM lanes 32*(w%4).. (query rows) and key half w/4.
+__global__ void __launch_bounds__(256, 1) attn_core_tc_kernel(const __nv_bfloat16 *__restrict__ qkv,
+                                                              const float *__restrict__ bias_t,
+                                                              __nv_bfloat16 *__restrict__ o, int heads, int64_t B_,
+                                                              int groups) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar_full[2];
+    __shared__ __align__(8) uint64_t bar_s, bar_o;
+    __shared__ uint32_t tmem_slot;
+    __nv_bfloat16 *sBias = reinterpret_cast<__nv_bfloat16 *>(smem);
+    uint8_t *sStage = smem + kBiasBytes;
+    float *sMax = reinterpret_cast<float *>(smem + kBiasBytes + 2 * kStageBytes);  // [2][128]
+    float *sSum = sMax + 256;                                                       // [2][128]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int combo = blockIdx.x % (heads * 4), g = blockIdx.x / (heads * 4);
+    const int hh = combo >> 2, qt = combo & 3;
+    const int half = warp >> 2;                    // key half handled by this warp
+    const int row = (warp & 3) * 32 + lane;        // query row inside the tile = TMEM lane
+    const int C = heads * 16;
+
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
+    if (tid == 0) {
+        mbar_init(&bar_full[0], 1);
+        mbar_init(&bar_full[1], 1);
+        mbar_init(&bar_s, 1);
+        mbar_init(&bar_o, 1);
+        mbar_fence_init();
+    }
+    // relative-position bias tile for (head, query tile), pre-multiplied by log2(e): sBias[i][j], i = query row
+    {
+        const float *src = bias_t + ((int64_t)hh * 512) * 512 + qt * 128;  // bias_t[h][j][i]
+        for (int idx = tid; idx < 512 * 128; idx += 256) {
+            const int i = idx & 127, j = idx >> 7;
+            sBias[i * kBiasPitch + j] = __float2bfloat16_rn(__ldg(src + (int64_t)j * 512 + i) * kLog2e);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+
+    const int64_t per_which = B_ * heads * 8192;  // elements between the q, k and v planes
+    auto issue_loads = [&](int64_t win, int stage) {
+        uint8_t *dst = sStage + stage * kStageBytes;
+        const __nv_bfloat16 *qb = qkv + (win * heads + hh) * 8192;
+        mbar_expect_tx(&bar_full[stage], kStageBytes);
+        bulk_g2s(dst, qb + qt * 128 * 8, 2048, &bar_full[stage]);                 // Q chunk 0 (head dims 0..7)
+        bulk_g2s(dst + 2048, qb + 4096 + qt * 128 * 8, 2048, &bar_full[stage]);   // Q chunk 1
+        bulk_g2s(dst + 4096, qb + per_which, 16384, &bar_full[stage]);            // K
+        bulk_g2s(dst + 4096 + 16384, qb + 2 * per_which, 16384, &bar_full[stage]);  // V
+    };
+
+    if (tid == 0 && g < B_) issue_loads(g, 0);
+    const uint32_t idesc_s = instr_desc_bf16(128, 256, false);
+    const uint32_t idesc_o = instr_desc_bf16(128, 16, true);
+
+    int it = 0;
+    for (int64_t win = g; win < B_; win += groups, ++it) {
+        const int stage = it & 1;
+        const uint32_t ph_full = (it >> 1) & 1, ph = it & 1;
+        const uint32_t sQ = smem_u32(sStage + stage * kStageBytes), sK = sQ + 4096, sV = sK + 16384;
+        if (tid == 0) {
+            if (win + groups < B_) issue_loads(win + groups, stage ^ 1);  // prefetch: lands during this window's softmax
+            mbar_wait(&bar_full[stage], ph_full);
+            tc_fence_after();
+            // S[128 x 512] = Q[128 x 16] K^T : two N = 256 halves, TMEM columns [0,256) and [256,512)
+            const uint64_t dq = smem_desc(sQ, 2048, 128);
+            mma_ss(tmem, dq, smem_desc(sK, 8192, 128), idesc_s, 0u);
+            mma_ss(tmem + 256, dq, smem_desc(sK + 256 * 16, 8192, 128), idesc_s, 0u);
+            mma_commit(&bar_s);
+        }
+        mbar_wait(&bar_s, ph);
+        tc_fence_after();
+
+        const uint32_t scol = tmem + lane_base + half * 256;
+        const __nv_bfloat16 *brow = sBias + row * kBiasPitch + half * 256;
+        // ---- pass 1: row maximum of s + bias over this warp's 256 keys ----
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+            uint32_t r[32];
+            tmem_ld32(scol + c * 32, r);
+            tmem_wait_ld();
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                float b[8];
+                unpack8(*reinterpret_cast<const uint4 *>(brow + c * 32 + q4 * 8), b);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) mx = fmaxf(mx, __uint_as_float(r[q4 * 8 + e]) + b[e]);
+            }
+        }
+        sMax[half * 128 + row] = mx;
+        __syncthreads();
+        mx = fmaxf(sMax[row], sMax[128 + row]);
+        // ---- pass 2: p = 2^(s + bias - max), row sum, P (bf16) written over S in place ----
+        float sum = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+            uint32_t r[32];
+            tmem_ld32(scol + c * 32, r);
+            tmem_wait_ld();
+            uint32_t pk[16];
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                float b[8];
+                unpack8(*reinterpret_cast<const uint4 *>(brow + c * 32 + q4 * 8), b);
+                float p[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    p[e] = fast_exp2(__uint_as_float(r[q4 * 8 + e]) + b[e] - mx);
+                    sum += p[e];
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) pk[q4 * 4 + e] = pack_bf16(p[2 * e], p[2 * e + 1]);
+            }
+            tmem_st16(scol + c * 16, pk);  // keys [32c, 32c+32) of this half -> 16 packed columns (already consumed S)
+        }
+        tmem_wait_st();
+        sSum[half * 128 + row] = sum;
+        tc_fence_before();
+        __syncthreads();
+        // ---- O[128 x 16] = P[128 x 512] V[512 x 16]: A = P from TMEM, B = V (MN-major), D = TMEM columns [128,144) ----
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll 1
+            for (int ks = 0; ks < 32; ++ks) {
+                const uint32_t pa = tmem + (ks < 16 ? ks * 8 : 256 + (ks - 16) * 8);
+                mma_ts(tmem + 128, pa, smem_desc(sV + ks * 256, 128, 8192), idesc_o, ks > 0 ? 1u : 0u);
+            }
+            mma_commit(&bar_o);
+        }
+        mbar_wait(&bar_o, ph);
+        tc_fence_after();
+        if (warp < 4) {
+            uint32_t r[16];
+            tmem_ld16(tmem + lane_base + 128, r);
+            tmem_wait_ld();
+            const float inv = 1.f / (sSum[row] + sSum[128 + row]);
+            uint4 lo, hi;
+            lo.x = pack_bf16(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
+            lo.y = pack_bf16(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
+            lo.z = pack_bf16(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
+            lo.w = pack_bf16(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
+            hi.x = pack_bf16(__uint_as_float(r[8]) * inv, __uint_as_float(r[9]) * inv);
+            hi.y = pack_bf16(__uint_as_float(r[10]) * inv, __uint_as_float(r[11]) * inv);
+            hi.z = pack_bf16(__uint_as_float(r[12]) * inv, __uint_as_float(r[13]) * inv);
+            hi.w = pack_bf16(__uint_as_float(r[14]) * inv, __uint_as_float(r[15]) * inv);
+            uint4 *dst = reinterpret_cast<uint4 *>(o + (win * 512 + qt * 128 + row) * (int64_t)C + hh * 16);
+            dst[0] = lo;
+            dst[1] = hi;
+        }
+        tc_fence_before();
+        __syncthreads();  // O and P consumed, sMax / sSum free: the next window's S may overwrite TMEM
+    }
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// -------------------------------------------------------------------------------------------------- launcher ------
+static int pick_ntile(int n) {
+    for (int nt = 128; nt >= 16; nt -= 16)
+        if (n % nt == 0) return nt;
+    return 0;
+}
+static uint32_t pow2_cols(int n) {
+    uint32_t c = 32;
+    while ((int)c < n) c <<= 1;
+    return c;
+}
+
+bool attn_tc_supported(int D1, int H1, int W1, int C, int heads, int ws) {
+    return ws == 8 && C == heads * 16 && C % 16 == 0 && C <= 384 && D1 % 8 == 0 && H1 % 8 == 0 && W1 % 8 == 0;
+}
+
+int attn_tc_forward(const __nv_bfloat16 *x, const __nv_bfloat16 *qkv_w, const __nv_bfloat16 *qkv_b,
+                    const __nv_bfloat16 *proj_w, const __nv_bfloat16 *proj_b, const float *bias_t,
+                    __nv_bfloat16 *out, void *workspace, int B, int D1, int H1, int W1, int C, int heads, float scale,
+                    cudaStream_t st) {
+    TcWindowMap map;
+    map.D1 = D1; map.H1 = H1; map.W1 = W1;
+    map.nWy = H1 / 8; map.nWx = W1 / 8; map.nW = (D1 / 8) * map.nWy * map.nWx;
+    const int64_t B_ = (int64_t)B * map.nW;
+    const int64_t M = B_ * 512;
+    __nv_bfloat16 *qkv = reinterpret_cast<__nv_bfloat16 *>(workspace);  // [3][B_][heads][2][512][8]
+    __nv_bfloat16 *obuf = qkv + 3 * M * C;                              // [M][C]
+    static bool attrs_done = false;
+    if (!attrs_done) {
+        WF_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(attn_core_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCoreSmem));
+        attrs_done = true;
+    }
+    const int kchunks = C / 8;
+    {
+        const int nt = pick_ntile(3 * C);
+        if (!nt) return WF_ERR_BAD_SHAPE;
+        const size_t smem = (size_t)kchunks * 2048 + (size_t)kchunks * nt * 16;
+        dim3 grid((unsigned)(M / 128), (unsigned)(3 * C / nt));
+        linear_tc_kernel<true><<<grid, 128, smem, st>>>(x, qkv_w, qkv_b, qkv, C, nt, 3 * C, map, heads, B_, scale * kLog2e, pow2_cols(nt));
+        WF_LAUNCH_CHECK();
+    }
+    {
+        const int combos = heads * 4;
+        int groups = kNumSMs / combos;
+        if (groups < 1) groups = 1;
+        if (groups > B_) groups = (int)B_;
+        attn_core_tc_kernel<<<combos * groups, 256, kCoreSmem, st>>>(qkv, bias_t, obuf, heads, B_, groups);
+        WF_LAUNCH_CHECK();
+    }
+    {
+        const int nt = pick_ntile(C);
+        if (!nt) return WF_ERR_BAD_SHAPE;
+        const size_t smem = (size_t)kchunks * 2048 + (size_t)kchunks * nt * 16;
+        dim3 grid((unsigned)(M / 128), (unsigned)(C / nt));
+        linear_tc_kernel<false><<<grid, 128, smem, st>>>(obuf, proj_w, proj_b, out, C, nt, C, map, heads, B_, 1.f, pow2_cols(nt));
+        WF_LAUNCH_CHECK();
+    }
+    return WF_OK;
+}
+
+}  // namespace wf

@@ -21,7 +21,9 @@ template <typename T, int VEC> struct NVec {
     }
 };
 
-// grid (chunks, B); each block reduces `vox_per_block` voxels of one batch element for all channels
+// grid (chunks, B); each block reduces `vox_per_block` voxels of one batch element for all channels.
+// Sums are taken of (x - pivot) with pivot = the channel's value at voxel 0 of the batch element, so that
+// E[d^2] - E[d]^2 stays well conditioned when |mean| >> std.
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) instnorm_stats_kernel(const T *__restrict__ x, double *__restrict__ sums,
                                                              int64_t S, int C, int cvecs, int64_t vox_per_block,
@@ -39,13 +41,16 @@ __global__ void __launch_bounds__(256) instnorm_stats_kernel(const T *__restrict
     for (int e = 0; e < VEC; ++e) s[e] = q[e] = 0.f;
     if (vg < group) {
         const T *base = x + (int64_t)b * S * xs + cv * VEC;
+        float piv[VEC];
+        NVec<T, VEC>::load(base, piv);
         for (int64_t v = v0 + vg; v < v1; v += group) {
             float f[VEC];
             NVec<T, VEC>::load(base + v * xs, f);
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
-                s[e] += f[e];
-                q[e] = fmaf(f[e], f[e], q[e]);
+                const float d = f[e] - piv[e];
+                s[e] += d;
+                q[e] = fmaf(d, d, q[e]);
             }
         }
     }
@@ -66,14 +71,18 @@ __global__ void __launch_bounds__(256) instnorm_stats_kernel(const T *__restrict
     }
 }
 
-__global__ void instnorm_finalize_kernel(const double *__restrict__ sums, float *__restrict__ mr, int n, double inv_s,
-                                         double eps) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+template <typename T>
+__global__ void instnorm_finalize_kernel(const T *__restrict__ x, const double *__restrict__ sums, float *__restrict__ mr,
+                                         int n, int C, int64_t S, int64_t xs, double eps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // b*C + c
     if (i >= n) return;
-    const double mean = sums[2 * i] * inv_s;
-    double var = sums[2 * i + 1] * inv_s - mean * mean;
+    const int b = i / C, c = i % C;
+    const double piv = (double)to_f32(x[(int64_t)b * S * xs + c]);
+    const double inv_s = 1.0 / (double)S;
+    const double md = sums[2 * i] * inv_s;  // mean of (x - pivot)
+    double var = sums[2 * i + 1] * inv_s - md * md;
     var = var < 0.0 ? 0.0 : var;
-    mr[2 * i] = (float)mean;
+    mr[2 * i] = (float)(piv + md);
     mr[2 * i + 1] = (float)(1.0 / sqrt(var + eps));
 }
 
@@ -131,7 +140,7 @@ static int stats_launch(const T *x, double *sums, float *mr, int B, int64_t S, i
     }
     WF_LAUNCH_CHECK();
     const int n = B * C;
-    instnorm_finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(sums, mr, n, 1.0 / (double)S, (double)eps);
+    instnorm_finalize_kernel<T><<<(n + 127) / 128, 128, 0, st>>>(x, sums, mr, n, C, S, xs, (double)eps);
     WF_LAUNCH_CHECK();
     return WF_OK;
 }
