@@ -83,6 +83,9 @@ int wf_idwt3d_ndhwc(const void *ll, const void *hf, const void *gate, void *x, i
  *       [B, D1, H1, W1, C] without an inverse permute, so `out` viewed with that shape IS the reference result.
  * bias: dense relative-position bias produced by wf_relpos_bias_expand, fp32 [heads, N, N] stored TRANSPOSED
  *       (bias_t[h][j][i] = table[index[i][j]][h]) so a warp of queries reads it coalesced.
+ * `dtype` is the compute / weight / output type: WF_BF16 runs the tcgen05 tensor-core kernels (512-token windows,
+ * head_dim 16; other geometries use the CUDA-core kernels), WF_F32 the fp32 CUDA-core kernels.  x may be stored as
+ * x_dtype = WF_F32 while dtype = WF_BF16 (fp32 residual stream, bf16 operands: converted while the tile is staged).
  * Weights are in `dtype`; qkv_w [3C, C], qkv_b [3C], proj_w [C, C], proj_b [C] (PyTorch Linear layout).
  * head_dim = C / heads must be 8, 16, 32 or 64; scale multiplies q after its bias (attention.py:88).
  * ---------------------------------------------------------------------------------------------------------- */
@@ -91,9 +94,9 @@ int wf_relpos_bias_expand(const void *table, int table_dtype, const int64_t *ind
 
 size_t wf_window_attn_workspace_bytes(int dtype, int B, int D1, int H1, int W1, int C, int heads, int ws);
 
-int wf_window_attn_fwd(const void *x, const void *qkv_w, const void *qkv_b, const void *proj_w, const void *proj_b,
-                       const float *bias_t, void *out, void *workspace, size_t workspace_bytes, int dtype, int B,
-                       int D1, int H1, int W1, int C, int heads, int ws, float scale, void *stream);
+int wf_window_attn_fwd(const void *x, int x_dtype, const void *qkv_w, const void *qkv_b, const void *proj_w,
+                       const void *proj_b, const float *bias_t, void *out, void *workspace, size_t workspace_bytes,
+                       int dtype, int B, int D1, int H1, int W1, int C, int heads, int ws, float scale, void *stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Block glue that dominated the step as library calls, channels-last, fp32 accumulate.
@@ -113,11 +116,31 @@ int wf_dwconv3d_ndhwc(const void *x, const float *w27, const float *bias, void *
 int wf_instnorm_stats_ndhwc(const void *x, double *sums, float *mean_rstd, int dtype, int B, int64_t S, int C,
                             int64_t x_vox_stride, float eps, void *stream);
 
-/* y = act((x - mean) * rstd + R) with R = 0 (res NULL), res (res_mean_rstd NULL) or (res - mean_r) * rstd_r.
- * act: 0 none, 1 ReLU, 2 LeakyReLU(slope).  Fuses norm + residual add + activation of dynunet_block.py:100-110. */
-int wf_instnorm_apply_ndhwc(const void *x, const float *mean_rstd, const void *res, const float *res_mean_rstd, void *y,
-                            int act, float slope, int dtype, int B, int64_t S, int C, int64_t x_vox_stride,
-                            int64_t res_vox_stride, int64_t y_vox_stride, void *stream);
+/* y = act(((x - mean) * rstd) * gamma + beta + R) with R = 0 (res NULL), res (res_mean_rstd NULL) or
+ * (res - mean_r) * rstd_r; gamma / beta (fp32 [C]) optional.  act: 0 none, 1 ReLU, 2 LeakyReLU(slope).
+ * Fuses norm + residual add + activation of dynunet_block.py:100-110; with gamma / beta it is GroupNorm(num_groups = C)
+ * of ProjectionUpsample.norm (reference network_models/wave_helper.py:59,74). */
+int wf_instnorm_apply_ndhwc(const void *x, const float *mean_rstd, const void *res, const float *res_mean_rstd,
+                            const float *gamma, const float *beta, void *y, int act, float slope, int dtype, int B,
+                            int64_t S, int C, int64_t x_vox_stride, int64_t res_vox_stride, int64_t y_vox_stride,
+                            void *stream);
+
+/* y[r, :] = LayerNorm(x[r, :C]) * gamma + beta (gamma / beta fp32 [C] or NULL), optionally followed by GELU(erf).
+ * Rows are voxels of a channels-last tensor (row strides in elements); input and output storage types are independent.
+ * Replaces Block.norm1 / norm2 (reference network_models/wave_helper.py:477,509), CCF_FFN.norm1 / norm2 + act
+ * (wave_helper.py:278,286), PatchMerging.norm (wave_helper.py:192) and proj_out (network_models/waveformer.py:193-204). */
+int wf_layernorm_ndhwc(const void *x, const float *gamma, const float *beta, void *y, int in_dtype, int out_dtype,
+                       int64_t rows, int C, int64_t x_row_stride, int64_t y_row_stride, float eps, int gelu, void *stream);
+
+/* y = base + sum_s trilinear_upsample(srcs[s]) (sources summed in order, then added to base; base may be NULL).
+ * srcs[s]: [B, d_s, h_s, w_s, C] dense channels-last of src_dtype, src_dims = int[3 * nsrc]; base / y: [B, D, H, W, C]
+ * of io_dtype with voxel strides.  align_corners = 0 reproduces F.interpolate(size=(D,H,W), mode='trilinear') + the
+ * level sum + the shortcut add of Block.multi_scale_forward (reference network_models/wave_helper.py:500-508);
+ * align_corners = 1 reproduces nn.Upsample(scale_factor, 'trilinear', align_corners=True) of ProjectionUpsample
+ * (wave_helper.py:42,63).  srcs and src_dims are HOST arrays (read during the call). */
+int wf_upsample_trilinear_add_ndhwc(const void *const *srcs, const int *src_dims, int nsrc, const void *base, void *y,
+                                    int src_dtype, int io_dtype, int align_corners, int B, int D, int H, int W, int C,
+                                    int64_t base_vox_stride, int64_t y_vox_stride, void *stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Sliding-window stitching (re-hosted MONAI inferer, reference monai/inferers/utils.py:216-299).

@@ -6,12 +6,12 @@
 namespace wf {
 int g_last_cuda_error = 0;
 
-template <typename T>
-int attn_simt_forward(const T *x, const T *qkv_w, const T *qkv_b, const T *proj_w, const T *proj_b,
+template <typename TA, typename T>
+int attn_simt_forward(const TA *x, const T *qkv_w, const T *qkv_b, const T *proj_w, const T *proj_b,
                       const float *bias_t, T *out, void *workspace, int B, int D1, int H1, int W1, int C, int heads,
                       int ws, float scale, cudaStream_t st);
 bool attn_tc_supported(int D1, int H1, int W1, int C, int heads, int ws);
-int attn_tc_forward(const __nv_bfloat16 *x, const __nv_bfloat16 *qkv_w, const __nv_bfloat16 *qkv_b,
+int attn_tc_forward(const void *x, int x_is_f32, const __nv_bfloat16 *qkv_w, const __nv_bfloat16 *qkv_b,
                     const __nv_bfloat16 *proj_w, const __nv_bfloat16 *proj_b, const float *bias_t,
                     __nv_bfloat16 *out, void *workspace, int B, int D1, int H1, int W1, int C, int heads, float scale,
                     cudaStream_t st);
@@ -51,30 +51,34 @@ extern "C" size_t wf_window_attn_workspace_bytes(int dtype, int B, int D1, int H
     return 4 * tokens * (size_t)C * e + 256;  // q, k, v (head-major) and the pre-projection output
 }
 
-extern "C" int wf_window_attn_fwd(const void *x, const void *qkv_w, const void *qkv_b, const void *proj_w,
+extern "C" int wf_window_attn_fwd(const void *x, int x_dtype, const void *qkv_w, const void *qkv_b, const void *proj_w,
                                   const void *proj_b, const float *bias_t, void *out, void *workspace,
                                   size_t workspace_bytes, int dtype, int B, int D1, int H1, int W1, int C, int heads,
                                   int ws, float scale, void *stream) {
     if (!x || !qkv_w || !proj_w || !proj_b || !bias_t || !out || !workspace) return WF_ERR_NULL_POINTER;
     const int rc = check_attn_shape(B, D1, H1, W1, C, heads, ws);
     if (rc != WF_OK) return rc;
-    if (dtype != WF_F32 && dtype != WF_BF16) return WF_ERR_BAD_DTYPE;
+    if ((dtype != WF_F32 && dtype != WF_BF16) || (x_dtype != WF_F32 && x_dtype != WF_BF16)) return WF_ERR_BAD_DTYPE;
+    if (dtype == WF_F32 && x_dtype != WF_F32) return WF_ERR_BAD_DTYPE;
     if (workspace_bytes < wf_window_attn_workspace_bytes(dtype, B, D1, H1, W1, C, heads, ws)) return WF_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
+    using bf = __nv_bfloat16;
     if (dtype == WF_F32)
-        return wf::attn_simt_forward<float>((const float *)x, (const float *)qkv_w, (const float *)qkv_b,
-                                            (const float *)proj_w, (const float *)proj_b, bias_t, (float *)out,
-                                            workspace, B, D1, H1, W1, C, heads, ws, scale, st);
+        return wf::attn_simt_forward<float, float>((const float *)x, (const float *)qkv_w, (const float *)qkv_b,
+                                                   (const float *)proj_w, (const float *)proj_b, bias_t, (float *)out,
+                                                   workspace, B, D1, H1, W1, C, heads, ws, scale, st);
     // bf16: tcgen05 / TMEM path for the reference geometry (512-token windows, head_dim 16); WF_ATTN_IMPL=simt forces
     // the CUDA-core kernels (used by the tests to cross-check the two implementations on the device)
     const char *impl = getenv("WF_ATTN_IMPL");
     const bool force_simt = impl != nullptr && impl[0] == 's';
     if (!force_simt && qkv_b != nullptr && wf::attn_tc_supported(D1, H1, W1, C, heads, ws))
-        return wf::attn_tc_forward((const __nv_bfloat16 *)x, (const __nv_bfloat16 *)qkv_w, (const __nv_bfloat16 *)qkv_b,
-                                   (const __nv_bfloat16 *)proj_w, (const __nv_bfloat16 *)proj_b, bias_t,
-                                   (__nv_bfloat16 *)out, workspace, B, D1, H1, W1, C, heads, scale, st);
-    return wf::attn_simt_forward<__nv_bfloat16>((const __nv_bfloat16 *)x, (const __nv_bfloat16 *)qkv_w,
-                                                (const __nv_bfloat16 *)qkv_b, (const __nv_bfloat16 *)proj_w,
-                                                (const __nv_bfloat16 *)proj_b, bias_t, (__nv_bfloat16 *)out, workspace,
-                                                B, D1, H1, W1, C, heads, ws, scale, st);
+        return wf::attn_tc_forward(x, x_dtype == WF_F32, (const bf *)qkv_w, (const bf *)qkv_b, (const bf *)proj_w,
+                                   (const bf *)proj_b, bias_t, (bf *)out, workspace, B, D1, H1, W1, C, heads, scale, st);
+    if (x_dtype == WF_F32)
+        return wf::attn_simt_forward<float, bf>((const float *)x, (const bf *)qkv_w, (const bf *)qkv_b, (const bf *)proj_w,
+                                                (const bf *)proj_b, bias_t, (bf *)out, workspace, B, D1, H1, W1, C, heads,
+                                                ws, scale, st);
+    return wf::attn_simt_forward<bf, bf>((const bf *)x, (const bf *)qkv_w, (const bf *)qkv_b, (const bf *)proj_w,
+                                         (const bf *)proj_b, bias_t, (bf *)out, workspace, B, D1, H1, W1, C, heads, ws,
+                                         scale, st);
 }

@@ -27,8 +27,8 @@ struct WindowMap {
 // QKV = true : rows gathered through the window map; result scattered to head-major q/k/v buffers
 //              [3][B_][heads][N][hd], q additionally multiplied by `scale`.
 // QKV = false: plain [M, Nout] output.
-template <typename T, bool QKV>
-__global__ void __launch_bounds__(256) linear_kernel(const T *__restrict__ A, const T *__restrict__ Wt,
+template <typename TA, typename T, bool QKV>
+__global__ void __launch_bounds__(256) linear_kernel(const TA *__restrict__ A, const T *__restrict__ Wt,
                                                      const T *__restrict__ bias, T *__restrict__ out, int64_t M,
                                                      int Nout, int K, WindowMap map, int heads, int hd, float scale,
                                                      int64_t B_) {
@@ -180,8 +180,8 @@ __global__ void relpos_bias_expand_kernel(const void *table, int table_dtype, co
     bias_t[idx] = val;
 }
 
-template <typename T>
-int attn_simt_forward(const T *x, const T *qkv_w, const T *qkv_b, const T *proj_w, const T *proj_b,
+template <typename TA, typename T>
+int attn_simt_forward(const TA *x, const T *qkv_w, const T *qkv_b, const T *proj_w, const T *proj_b,
                       const float *bias_t, T *out, void *workspace, int B, int D1, int H1, int W1, int C, int heads,
                       int ws, float scale, cudaStream_t st) {
     WindowMap map;
@@ -193,7 +193,7 @@ int attn_simt_forward(const T *x, const T *qkv_w, const T *qkv_b, const T *proj_
     T *qkv = reinterpret_cast<T *>(workspace);
     T *q = qkv, *k = qkv + M * C, *v = qkv + 2 * M * C, *o = qkv + 3 * M * C;
     dim3 g1((unsigned)((M + 63) / 64), (unsigned)((3 * C + 63) / 64));
-    linear_kernel<T, true><<<g1, 256, 0, st>>>(x, qkv_w, qkv_b, qkv, M, 3 * C, C, map, heads, hd, scale, B_);
+    linear_kernel<TA, T, true><<<g1, 256, 0, st>>>(x, qkv_w, qkv_b, qkv, M, 3 * C, C, map, heads, hd, scale, B_);
     WF_LAUNCH_CHECK();
     const int KC = map.N < 256 ? map.N : 256;
     const size_t smem = (size_t)2 * KC * hd * sizeof(float);
@@ -214,16 +214,19 @@ int attn_simt_forward(const T *x, const T *qkv_w, const T *qkv_b, const T *proj_
 #undef WF_CORE
     WF_LAUNCH_CHECK();
     dim3 g3((unsigned)((M + 63) / 64), (unsigned)((C + 63) / 64));
-    linear_kernel<T, false><<<g3, 256, 0, st>>>(o, proj_w, proj_b, out, M, C, C, map, heads, hd, 1.f, B_);
+    linear_kernel<T, T, false><<<g3, 256, 0, st>>>(o, proj_w, proj_b, out, M, C, C, map, heads, hd, 1.f, B_);
     WF_LAUNCH_CHECK();
     return WF_OK;
 }
 
-template int attn_simt_forward<float>(const float *, const float *, const float *, const float *, const float *,
-                                      const float *, float *, void *, int, int, int, int, int, int, int, float, cudaStream_t);
-template int attn_simt_forward<__nv_bfloat16>(const __nv_bfloat16 *, const __nv_bfloat16 *, const __nv_bfloat16 *,
-                                              const __nv_bfloat16 *, const __nv_bfloat16 *, const float *, __nv_bfloat16 *,
-                                              void *, int, int, int, int, int, int, int, float, cudaStream_t);
+template int attn_simt_forward<float, float>(const float *, const float *, const float *, const float *, const float *,
+                                             const float *, float *, void *, int, int, int, int, int, int, int, float, cudaStream_t);
+template int attn_simt_forward<__nv_bfloat16, __nv_bfloat16>(const __nv_bfloat16 *, const __nv_bfloat16 *, const __nv_bfloat16 *,
+                                                             const __nv_bfloat16 *, const __nv_bfloat16 *, const float *,
+                                                             __nv_bfloat16 *, void *, int, int, int, int, int, int, int, float, cudaStream_t);
+template int attn_simt_forward<float, __nv_bfloat16>(const float *, const __nv_bfloat16 *, const __nv_bfloat16 *,
+                                                     const __nv_bfloat16 *, const __nv_bfloat16 *, const float *,
+                                                     __nv_bfloat16 *, void *, int, int, int, int, int, int, int, float, cudaStream_t);
 
 }  // namespace wf
 

@@ -42,8 +42,8 @@ constexpr float kLog2e = 1.4426950408889634f;
 
 // ------------------------------------------------------------------------------------------------ projections ----
 // grid (M/128, Nout/NT), 128 threads.  smem: A image [K/8][128][8] bf16, B image [K/8][NT][8] bf16 (no-swizzle canonical)
-template <bool QKV>
-__global__ void __launch_bounds__(128) linear_tc_kernel(const __nv_bfloat16 *__restrict__ A,
+template <bool QKV, typename TA>
+__global__ void __launch_bounds__(128) linear_tc_kernel(const TA *__restrict__ A,
                                                         const __nv_bfloat16 *__restrict__ Wt,
                                                         const __nv_bfloat16 *__restrict__ bias,
                                                         __nv_bfloat16 *__restrict__ out, int K, int NT, int Nout,
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(128) linear_tc_kernel(const __nv_bfloat16 *__r
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_slot;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5;
     const int kchunks = K >> 3;
     uint8_t *sA = smem;
     uint8_t *sB = smem + (size_t)kchunks * 2048;
@@ -67,9 +67,19 @@ __global__ void __launch_bounds__(128) linear_tc_kernel(const __nv_bfloat16 *__r
     // A tile: row r = tid, every 16-byte K chunk.  A warp writes 32 consecutive rows of one chunk: conflict-free.
     {
         const int64_t src_row = QKV ? map.voxel(m0 + tid) : (m0 + tid);
-        const uint4 *src = reinterpret_cast<const uint4 *>(A + src_row * K);
-        for (int kc = 0; kc < kchunks; ++kc)
-            *reinterpret_cast<uint4 *>(sA + (size_t)kc * 2048 + tid * 16) = __ldg(src + kc);
+        if constexpr (sizeof(TA) == 2) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(A + src_row * K);
+            for (int kc = 0; kc < kchunks; ++kc)
+                *reinterpret_cast<uint4 *>(sA + (size_t)kc * 2048 + tid * 16) = __ldg(src + kc);
+        } else {  // fp32 activations (residual-stream precision): converted to the bf16 operand while staging
+            const float4 *src = reinterpret_cast<const float4 *>(A + src_row * K);
+            for (int kc = 0; kc < kchunks; ++kc) {
+                const float4 a = __ldg(src + 2 * kc), b = __ldg(src + 2 * kc + 1);
+                uint4 u;
+                u.x = pack_bf16(a.x, a.y); u.y = pack_bf16(a.z, a.w); u.z = pack_bf16(b.x, b.y); u.w = pack_bf16(b.z, b.w);
+                *reinterpret_cast<uint4 *>(sA + (size_t)kc * 2048 + tid * 16) = u;
+            }
+        }
     }
     // B tile: rows n0 .. n0+NT-1 of the [Nout, K] weight
     for (int idx = tid; idx < NT * kchunks; idx += 128) {
@@ -329,7 +339,7 @@ bool attn_tc_supported(int D1, int H1, int W1, int C, int heads, int ws) {
     return ws == 8 && C == heads * 16 && C % 16 == 0 && C <= 384 && D1 % 8 == 0 && H1 % 8 == 0 && W1 % 8 == 0;
 }
 
-int attn_tc_forward(const __nv_bfloat16 *x, const __nv_bfloat16 *qkv_w, const __nv_bfloat16 *qkv_b,
+int attn_tc_forward(const void *x, int x_is_f32, const __nv_bfloat16 *qkv_w, const __nv_bfloat16 *qkv_b,
                     const __nv_bfloat16 *proj_w, const __nv_bfloat16 *proj_b, const float *bias_t,
                     __nv_bfloat16 *out, void *workspace, int B, int D1, int H1, int W1, int C, int heads, float scale,
                     cudaStream_t st) {
@@ -342,8 +352,9 @@ int attn_tc_forward(const __nv_bfloat16 *x, const __nv_bfloat16 *qkv_w, const __
     __nv_bfloat16 *obuf = qkv + 3 * M * C;                              // [M][C]
     static bool attrs_done = false;
     if (!attrs_done) {
-        WF_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        WF_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel<true, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel<true, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel<false, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         WF_CUDA_CHECK(cudaFuncSetAttribute(attn_core_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCoreSmem));
         attrs_done = true;
     }
@@ -353,7 +364,10 @@ int attn_tc_forward(const __nv_bfloat16 *x, const __nv_bfloat16 *qkv_w, const __
         if (!nt) return WF_ERR_BAD_SHAPE;
         const size_t smem = (size_t)kchunks * 2048 + (size_t)kchunks * nt * 16;
         dim3 grid((unsigned)(M / 128), (unsigned)(3 * C / nt));
-        linear_tc_kernel<true><<<grid, 128, smem, st>>>(x, qkv_w, qkv_b, qkv, C, nt, 3 * C, map, heads, B_, scale * kLog2e, pow2_cols(nt));
+        if (x_is_f32)
+            linear_tc_kernel<true, float><<<grid, 128, smem, st>>>((const float *)x, qkv_w, qkv_b, qkv, C, nt, 3 * C, map, heads, B_, scale * kLog2e, pow2_cols(nt));
+        else
+            linear_tc_kernel<true, __nv_bfloat16><<<grid, 128, smem, st>>>((const __nv_bfloat16 *)x, qkv_w, qkv_b, qkv, C, nt, 3 * C, map, heads, B_, scale * kLog2e, pow2_cols(nt));
         WF_LAUNCH_CHECK();
     }
     {
@@ -369,7 +383,7 @@ int attn_tc_forward(const __nv_bfloat16 *x, const __nv_bfloat16 *qkv_w, const __
         if (!nt) return WF_ERR_BAD_SHAPE;
         const size_t smem = (size_t)kchunks * 2048 + (size_t)kchunks * nt * 16;
         dim3 grid((unsigned)(M / 128), (unsigned)(C / nt));
-        linear_tc_kernel<false><<<grid, 128, smem, st>>>(obuf, proj_w, proj_b, out, C, nt, C, map, heads, B_, 1.f, pow2_cols(nt));
+        linear_tc_kernel<false, __nv_bfloat16><<<grid, 128, smem, st>>>(obuf, proj_w, proj_b, out, C, nt, C, map, heads, B_, 1.f, pow2_cols(nt));
         WF_LAUNCH_CHECK();
     }
     return WF_OK;

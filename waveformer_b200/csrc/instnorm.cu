@@ -92,7 +92,8 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(const T *__restrict
                                                              const T *__restrict__ res, const float *__restrict__ res_mr,
                                                              T *__restrict__ y, int64_t total, int64_t S, int C,
                                                              int cvecs, int64_t xs, int64_t rs, int64_t ys, int act,
-                                                             float slope) {
+                                                             float slope, const float *__restrict__ gamma,
+                                                             const float *__restrict__ beta) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int cv = (int)(idx % cvecs);
@@ -104,6 +105,10 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(const T *__restrict
     const float *m = mr + ((int64_t)b * C + c0) * 2;
 #pragma unroll
     for (int e = 0; e < VEC; ++e) f[e] = (f[e] - __ldg(m + 2 * e)) * __ldg(m + 2 * e + 1);
+    if (gamma != nullptr) {  // GroupNorm(num_groups = C) = InstanceNorm + per-channel affine
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) f[e] = fmaf(f[e], __ldg(gamma + c0 + e), beta != nullptr ? __ldg(beta + c0 + e) : 0.f);
+    }
     if (res != nullptr) {
         float r[VEC];
         NVec<T, VEC>::load(res + vox * rs + c0, r);
@@ -147,17 +152,18 @@ static int stats_launch(const T *x, double *sums, float *mr, int B, int64_t S, i
 
 template <typename T>
 static int apply_launch(const T *x, const float *mr, const T *res, const float *res_mr, T *y, int B, int64_t S, int C,
-                        int64_t xs, int64_t rs, int64_t ys, int act, float slope, cudaStream_t st) {
+                        int64_t xs, int64_t rs, int64_t ys, int act, float slope, const float *gamma, const float *beta,
+                        cudaStream_t st) {
     constexpr int V = Pack<T>::VEC;
     const size_t e = sizeof(T);
     const bool vec = (C % V == 0) && aligned16(x) && aligned16(y) && (xs * e) % 16 == 0 && (ys * e) % 16 == 0 &&
                      (res == nullptr || (aligned16(res) && (rs * e) % 16 == 0));
     if (vec) {
         const int64_t total = (int64_t)B * S * (C / V);
-        instnorm_apply_kernel<T, V><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, mr, res, res_mr, y, total, S, C, C / V, xs, rs, ys, act, slope);
+        instnorm_apply_kernel<T, V><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, mr, res, res_mr, y, total, S, C, C / V, xs, rs, ys, act, slope, gamma, beta);
     } else {
         const int64_t total = (int64_t)B * S * C;
-        instnorm_apply_kernel<T, 1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, mr, res, res_mr, y, total, S, C, C, xs, rs, ys, act, slope);
+        instnorm_apply_kernel<T, 1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, mr, res, res_mr, y, total, S, C, C, xs, rs, ys, act, slope, gamma, beta);
     }
     WF_LAUNCH_CHECK();
     return WF_OK;
@@ -177,17 +183,18 @@ extern "C" int wf_instnorm_stats_ndhwc(const void *x, double *sums, float *mean_
 }
 
 extern "C" int wf_instnorm_apply_ndhwc(const void *x, const float *mean_rstd, const void *res, const float *res_mean_rstd,
-                                       void *y, int act, float slope, int dtype, int B, int64_t S, int C,
-                                       int64_t x_vox_stride, int64_t res_vox_stride, int64_t y_vox_stride, void *stream) {
+                                       const float *gamma, const float *beta, void *y, int act, float slope, int dtype,
+                                       int B, int64_t S, int C, int64_t x_vox_stride, int64_t res_vox_stride,
+                                       int64_t y_vox_stride, void *stream) {
     if (!x || !mean_rstd || !y) return WF_ERR_NULL_POINTER;
     if (B <= 0 || S <= 0 || C <= 0 || x_vox_stride < C || y_vox_stride < C || (res && res_vox_stride < C)) return WF_ERR_BAD_SHAPE;
     if (act < 0 || act > 2) return WF_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == WF_F32)
         return wf::apply_launch<float>((const float *)x, mean_rstd, (const float *)res, res_mean_rstd, (float *)y, B, S, C,
-                                       x_vox_stride, res_vox_stride, y_vox_stride, act, slope, st);
+                                       x_vox_stride, res_vox_stride, y_vox_stride, act, slope, gamma, beta, st);
     if (dtype == WF_BF16)
         return wf::apply_launch<__nv_bfloat16>((const __nv_bfloat16 *)x, mean_rstd, (const __nv_bfloat16 *)res, res_mean_rstd,
-                                               (__nv_bfloat16 *)y, B, S, C, x_vox_stride, res_vox_stride, y_vox_stride, act, slope, st);
+                                               (__nv_bfloat16 *)y, B, S, C, x_vox_stride, res_vox_stride, y_vox_stride, act, slope, gamma, beta, st);
     return WF_ERR_BAD_DTYPE;
 }

@@ -1,0 +1,149 @@
+// LayerNorm over the channel dimension of channels-last activations, optionally fused with GELU(erf) (sm_100a).
+//
+// Reference call sites: Block.norm1 / norm2 (network_models/wave_helper.py:477,509), CCF_FFN.norm1/norm2 followed by
+// GELU (wave_helper.py:278,286), PatchMerging.norm (wave_helper.py:192) and the affine-free proj_out LayerNorm
+// (network_models/waveformer.py:193-204).  One streaming pass: a row (C <= 2048 channels) is held in registers by
+// TPR = 8 / 16 / 32 cooperating lanes, mean and centred variance are exact two-pass fp32, and input / output storage
+// types are independent (fp32 residual stream in, bf16 GEMM operand out).
+#include "wf_common.cuh"
+
+namespace wf {
+
+template <typename T> struct Row16;  // 16-byte packets of T
+template <> struct Row16<float> {
+    static constexpr int V = 4;
+    __device__ static inline void load(const float *p, float (&v)[4]) {
+        const float4 t = *reinterpret_cast<const float4 *>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    __device__ static inline void store(float *p, const float (&v)[4]) {
+        *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <> struct Row16<__nv_bfloat16> {
+    static constexpr int V = 8;
+    __device__ static inline void load(const __nv_bfloat16 *p, float (&v)[8]) {
+        Pack<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4 *>(p), v);
+    }
+    __device__ static inline void store(__nv_bfloat16 *p, const float (&v)[8]) {
+        *reinterpret_cast<uint4 *>(p) = Pack<__nv_bfloat16>::pack(v);
+    }
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+
+// Each thread owns NV groups of 4 consecutive channels: channel index = (j * TPR + sub) * 4 + e.
+template <typename TI, typename TO, int TPR, int NV>
+__global__ void __launch_bounds__(256) layernorm_kernel(const TI *__restrict__ x, const float *__restrict__ gamma,
+                                                        const float *__restrict__ beta, TO *__restrict__ y,
+                                                        int64_t rows, int C, int64_t xs, int64_t ys, float eps,
+                                                        int gelu) {
+    constexpr int RPB = 256 / TPR;  // rows per block
+    const int sub = threadIdx.x % TPR;
+    const int64_t row = (int64_t)blockIdx.x * RPB + threadIdx.x / TPR;
+    const bool live = row < rows;
+    const int groups = C >> 2;  // groups of 4 channels
+    float v[NV][4];
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int g = j * TPR + sub;
+        if (live && g < groups) {
+            const TI *p = x + row * xs + g * 4;
+            if constexpr (sizeof(TI) == 4) {
+                const float4 t = *reinterpret_cast<const float4 *>(p);
+                v[j][0] = t.x; v[j][1] = t.y; v[j][2] = t.z; v[j][3] = t.w;
+            } else {
+                const uint2 t = *reinterpret_cast<const uint2 *>(p);
+                v[j][0] = __uint_as_float(t.x << 16); v[j][1] = __uint_as_float(t.x & 0xffff0000u);
+                v[j][2] = __uint_as_float(t.y << 16); v[j][3] = __uint_as_float(t.y & 0xffff0000u);
+            }
+            sum += (v[j][0] + v[j][1]) + (v[j][2] + v[j][3]);
+        } else {
+            v[j][0] = v[j][1] = v[j][2] = v[j][3] = 0.f;
+        }
+    }
+#pragma unroll
+    for (int o = TPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)C;
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int g = j * TPR + sub;
+        if (g < groups) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float d = v[j][e] - mean;
+                sq = fmaf(d, d, sq);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = TPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / (float)C + eps);
+    if (!live) return;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int g = j * TPR + sub;
+        if (g >= groups) continue;
+        float o4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float t = (v[j][e] - mean) * rstd;
+            if (gamma != nullptr) t = fmaf(t, __ldg(gamma + g * 4 + e), beta != nullptr ? __ldg(beta + g * 4 + e) : 0.f);
+            o4[e] = gelu ? gelu_erf(t) : t;
+        }
+        TO *q = y + row * ys + g * 4;
+        if constexpr (sizeof(TO) == 4) {
+            *reinterpret_cast<float4 *>(q) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+        } else {
+            __nv_bfloat162 a = __floats2bfloat162_rn(o4[0], o4[1]), b = __floats2bfloat162_rn(o4[2], o4[3]);
+            *reinterpret_cast<uint2 *>(q) = make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b));
+        }
+    }
+}
+
+template <typename TI, typename TO>
+static int layernorm_launch(const TI *x, const float *gamma, const float *beta, TO *y, int64_t rows, int C, int64_t xs,
+                            int64_t ys, float eps, int gelu, cudaStream_t st) {
+    if (C % 4 != 0 || C > 2048) return WF_ERR_UNSUPPORTED;
+    if ((xs * sizeof(TI)) % (sizeof(TI) == 4 ? 16 : 8) != 0 || (ys * sizeof(TO)) % (sizeof(TO) == 4 ? 16 : 8) != 0)
+        return WF_ERR_MISALIGNED;
+    const int groups = C / 4;
+#define WF_LN(TPR_, NV_)                                                                                         \
+    do {                                                                                                         \
+        const int rpb = 256 / TPR_;                                                                              \
+        layernorm_kernel<TI, TO, TPR_, NV_><<<(unsigned)((rows + rpb - 1) / rpb), 256, 0, st>>>(x, gamma, beta, y, rows, \
+                                                                                                C, xs, ys, eps, gelu); \
+    } while (0)
+    if (groups <= 8) WF_LN(8, 1);
+    else if (groups <= 16) WF_LN(16, 1);
+    else if (groups <= 32) WF_LN(32, 1);
+    else if (groups <= 64) WF_LN(32, 2);
+    else if (groups <= 128) WF_LN(32, 4);
+    else if (groups <= 256) WF_LN(32, 8);
+    else WF_LN(32, 16);
+#undef WF_LN
+    WF_LAUNCH_CHECK();
+    return WF_OK;
+}
+
+}  // namespace wf
+
+extern "C" int wf_layernorm_ndhwc(const void *x, const float *gamma, const float *beta, void *y, int in_dtype,
+                                  int out_dtype, int64_t rows, int C, int64_t x_row_stride, int64_t y_row_stride,
+                                  float eps, int gelu, void *stream) {
+    if (!x || !y) return WF_ERR_NULL_POINTER;
+    if (rows <= 0 || C <= 0 || x_row_stride < C || y_row_stride < C) return WF_ERR_BAD_SHAPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    using bf = __nv_bfloat16;
+    if (in_dtype == WF_F32 && out_dtype == WF_F32)
+        return wf::layernorm_launch<float, float>((const float *)x, gamma, beta, (float *)y, rows, C, x_row_stride, y_row_stride, eps, gelu, st);
+    if (in_dtype == WF_F32 && out_dtype == WF_BF16)
+        return wf::layernorm_launch<float, bf>((const float *)x, gamma, beta, (bf *)y, rows, C, x_row_stride, y_row_stride, eps, gelu, st);
+    if (in_dtype == WF_BF16 && out_dtype == WF_BF16)
+        return wf::layernorm_launch<bf, bf>((const bf *)x, gamma, beta, (bf *)y, rows, C, x_row_stride, y_row_stride, eps, gelu, st);
+    if (in_dtype == WF_BF16 && out_dtype == WF_F32)
+        return wf::layernorm_launch<bf, float>((const bf *)x, gamma, beta, (float *)y, rows, C, x_row_stride, y_row_stride, eps, gelu, st);
+    return WF_ERR_BAD_DTYPE;
+}

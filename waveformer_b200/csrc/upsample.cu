@@ -1,0 +1,178 @@
+// Trilinear upsampling of channels-last activations, fused with the multi-level sum and the shortcut add of
+// Block.multi_scale_forward (sm_100a).
+//
+// Reference: `attn_fused = attn_fused + F.interpolate(attn_windows, size=(D,H,W), mode='trilinear')` per level and
+// `attn_fused = shortcut + attn_fused` (network_models/wave_helper.py:500-508), i.e. up to three upsampled coarse maps
+// summed in level order and added to the block input; and nn.Upsample(scale_factor=s, mode='trilinear',
+// align_corners=True) in ProjectionUpsample (wave_helper.py:42,63).  Index arithmetic follows PyTorch's
+// upsample_trilinear3d (area_pixel_compute_source_index): align_corners=False: src = max(0, (dst+0.5)*in/out - 0.5);
+// align_corners=True: src = dst*(in-1)/(out-1); i0 = floor(src), i1 = min(i0+1, in-1).
+// The coarse sources are small (<= 1/8 of the output) and stay in L1/L2; the kernel streams `base` in and `y` out once.
+#include "wf_common.cuh"
+
+namespace wf {
+
+struct UpSrc {
+    const void *ptr;
+    int d, h, w;
+    float sz, sy, sx;  // source-coordinate scale per axis
+};
+struct UpArgs {
+    UpSrc src[3];
+    int nsrc;
+    int align;
+};
+
+template <typename T, int N> __device__ __forceinline__ void load_n(const T *p, float (&v)[N]) {
+    if constexpr (N == 1) {
+        v[0] = to_f32(*p);
+    } else if constexpr (sizeof(T) == 4) {
+#pragma unroll
+        for (int i = 0; i < N / 4; ++i) {
+            const float4 t = reinterpret_cast<const float4 *>(p)[i];
+            v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N / 4; ++i) {
+            const uint2 t = reinterpret_cast<const uint2 *>(p)[i];
+            v[4 * i] = __uint_as_float(t.x << 16); v[4 * i + 1] = __uint_as_float(t.x & 0xffff0000u);
+            v[4 * i + 2] = __uint_as_float(t.y << 16); v[4 * i + 3] = __uint_as_float(t.y & 0xffff0000u);
+        }
+    }
+}
+template <typename T, int N> __device__ __forceinline__ void store_n(T *p, const float (&v)[N]) {
+    if constexpr (N == 1) {
+        *p = from_f32<T>(v[0]);
+    } else if constexpr (sizeof(T) == 4) {
+#pragma unroll
+        for (int i = 0; i < N / 4; ++i)
+            reinterpret_cast<float4 *>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < N / 4; ++i) {
+            __nv_bfloat162 a = __floats2bfloat162_rn(v[4 * i], v[4 * i + 1]), b = __floats2bfloat162_rn(v[4 * i + 2], v[4 * i + 3]);
+            reinterpret_cast<uint2 *>(p)[i] = make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b));
+        }
+    }
+}
+
+__device__ __forceinline__ void src_index(int dst, float scale, int in, int align, int &i0, int &i1, float &l1) {
+    float s = align ? scale * dst : fmaxf(scale * (dst + 0.5f) - 0.5f, 0.f);
+    i0 = (int)s;
+    if (i0 > in - 1) i0 = in - 1;
+    i1 = i0 + (i0 < in - 1 ? 1 : 0);
+    l1 = s - (float)i0;
+    if (l1 < 0.f) l1 = 0.f;
+    if (l1 > 1.f) l1 = 1.f;
+}
+
+template <typename TS, typename TB, typename TO, int VEC>
+__global__ void __launch_bounds__(256) upsample_add_kernel(UpArgs a, const TB *__restrict__ base, TO *__restrict__ y,
+                                                           int64_t total, int D, int H, int W, int C, int cvecs,
+                                                           int64_t bs, int64_t ys) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int cv = (int)(idx % cvecs);
+    int64_t t = idx / cvecs;
+    const int xx = (int)(t % W); t /= W;
+    const int yy = (int)(t % H); t /= H;
+    const int zz = (int)(t % D);
+    const int64_t b = t / D;
+    const int c0 = cv * VEC;
+    float acc[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
+    for (int s = 0; s < a.nsrc; ++s) {
+        const UpSrc &u = a.src[s];
+        int z0, z1, y0, y1, x0, x1;
+        float lz, ly, lx;
+        src_index(zz, u.sz, u.d, a.align, z0, z1, lz);
+        src_index(yy, u.sy, u.h, a.align, y0, y1, ly);
+        src_index(xx, u.sx, u.w, a.align, x0, x1, lx);
+        const TS *p = reinterpret_cast<const TS *>(u.ptr) + (int64_t)b * u.d * u.h * u.w * C + c0;
+        float lvl[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) lvl[e] = 0.f;
+        // same association as PyTorch: sum over the 8 corners of w_z * w_y * w_x * value
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int zi = (k & 4) ? z1 : z0, yi = (k & 2) ? y1 : y0, xi = (k & 1) ? x1 : x0;
+            const float wgt = ((k & 4) ? lz : 1.f - lz) * ((k & 2) ? ly : 1.f - ly) * ((k & 1) ? lx : 1.f - lx);
+            float f[VEC];
+            const TS *q = p + (((int64_t)zi * u.h + yi) * u.w + xi) * C;
+            if constexpr (VEC == 1) {
+                f[0] = to_f32(__ldg(q));
+            } else {
+                Pack<TS>::unpack(__ldg(reinterpret_cast<const typename Pack<TS>::raw *>(q)), f);
+            }
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) lvl[e] = fmaf(wgt, f[e], lvl[e]);
+        }
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[e] += lvl[e];
+    }
+    const int64_t vox = ((b * D + zz) * H + yy) * (int64_t)W + xx;
+    if (base != nullptr) {
+        float bv[VEC];
+        load_n<TB, VEC>(base + vox * bs + c0, bv);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[e] = bv[e] + acc[e];
+    }
+    store_n<TO, VEC>(y + vox * ys + c0, acc);
+}
+
+template <typename TS, typename TB, typename TO>
+static int upsample_launch(const UpArgs &a, const TB *base, TO *y, int B, int D, int H, int W, int C, int64_t bs,
+                           int64_t ys, cudaStream_t st) {
+    constexpr int V = Pack<TS>::VEC;
+    bool vec = (C % V == 0) && aligned16(y) && (base == nullptr || aligned16(base)) && (bs * sizeof(TB)) % 16 == 0 &&
+               (ys * sizeof(TO)) % 16 == 0;
+    for (int s = 0; s < a.nsrc; ++s) vec = vec && aligned16(a.src[s].ptr);
+    if (vec) {
+        const int64_t total = (int64_t)B * D * H * W * (C / V);
+        upsample_add_kernel<TS, TB, TO, V><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, base, y, total, D, H, W, C, C / V, bs, ys);
+    } else {
+        const int64_t total = (int64_t)B * D * H * W * C;
+        upsample_add_kernel<TS, TB, TO, 1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, base, y, total, D, H, W, C, C, bs, ys);
+    }
+    WF_LAUNCH_CHECK();
+    return WF_OK;
+}
+
+}  // namespace wf
+
+extern "C" int wf_upsample_trilinear_add_ndhwc(const void *const *srcs, const int *src_dims, int nsrc, const void *base,
+                                               void *y, int src_dtype, int io_dtype, int align_corners, int B, int D,
+                                               int H, int W, int C, int64_t base_vox_stride, int64_t y_vox_stride,
+                                               void *stream) {
+    if (!srcs || !src_dims || !y) return WF_ERR_NULL_POINTER;
+    if (nsrc < 1 || nsrc > 3 || B <= 0 || D <= 0 || H <= 0 || W <= 0 || C <= 0) return WF_ERR_BAD_SHAPE;
+    wf::UpArgs a;
+    a.nsrc = nsrc;
+    a.align = align_corners ? 1 : 0;
+    const int out[3] = {D, H, W};
+    for (int s = 0; s < nsrc; ++s) {
+        if (!srcs[s]) return WF_ERR_NULL_POINTER;
+        a.src[s].ptr = srcs[s];
+        const int *dm = src_dims + 3 * s;
+        if (dm[0] <= 0 || dm[1] <= 0 || dm[2] <= 0) return WF_ERR_BAD_SHAPE;
+        a.src[s].d = dm[0]; a.src[s].h = dm[1]; a.src[s].w = dm[2];
+        float sc[3];
+        for (int k = 0; k < 3; ++k)
+            sc[k] = align_corners ? (out[k] > 1 ? (float)(dm[k] - 1) / (float)(out[k] - 1) : 0.f) : (float)dm[k] / (float)out[k];
+        a.src[s].sz = sc[0]; a.src[s].sy = sc[1]; a.src[s].sx = sc[2];
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    using bf = __nv_bfloat16;
+    // sources and base/output may differ in storage type (bf16 attention output, fp32 residual stream)
+    if (src_dtype == WF_F32 && io_dtype == WF_F32)
+        return wf::upsample_launch<float, float, float>(a, (const float *)base, (float *)y, B, D, H, W, C, base_vox_stride, y_vox_stride, st);
+    if (src_dtype == WF_BF16 && io_dtype == WF_BF16)
+        return wf::upsample_launch<bf, bf, bf>(a, (const bf *)base, (bf *)y, B, D, H, W, C, base_vox_stride, y_vox_stride, st);
+    if (src_dtype == WF_BF16 && io_dtype == WF_F32)
+        return wf::upsample_launch<bf, float, float>(a, (const float *)base, (float *)y, B, D, H, W, C, base_vox_stride, y_vox_stride, st);
+    if (src_dtype == WF_F32 && io_dtype == WF_BF16)
+        return wf::upsample_launch<float, bf, bf>(a, (const bf *)base, (bf *)y, B, D, H, W, C, base_vox_stride, y_vox_stride, st);
+    return WF_ERR_BAD_DTYPE;
+}

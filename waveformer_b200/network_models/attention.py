@@ -50,9 +50,11 @@ class Attention(nn.Module):
         (window partition and the reference's reshape-only reverse are part of the kernel's addressing)."""
         if self.training and (self.attn_drop.p > 0 or self.proj_drop.p > 0):
             raise NotImplementedError("attention dropout is not part of the fused kernel (the path uses p = 0)")
+        # compute_dtype (set by waveformer_b200.prepare_inference) = dtype of the GEMM operands; x may be an fp32 stream
+        cd = getattr(self, "compute_dtype", None) or x.dtype
         return ops.window_attention(x, self.qkv.weight, self.qkv.bias, self.proj.weight, self.proj.bias,
                                     self.relative_position_bias_table, self.relative_position_index,
-                                    self._dense_bias(), self.num_heads, self.window_size, self.scale)
+                                    self._dense_bias(), self.num_heads, self.window_size, self.scale, cd)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         b_, n, c = x.shape

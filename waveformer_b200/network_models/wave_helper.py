@@ -17,6 +17,15 @@ from .. import ops
 from .attention import Attention
 
 
+def fused_path(x: torch.Tensor) -> bool:
+    """Inference on CUDA runs the hand-written kernels; autograd (training) keeps differentiable torch ops."""
+    return x.is_cuda and not torch.is_grad_enabled()
+
+
+def _ln(norm: nn.LayerNorm, x: torch.Tensor, gelu: bool = False, out_dtype=None) -> torch.Tensor:
+    return ops.layer_norm_cl(x, norm.weight, norm.bias, norm.eps, gelu=gelu, out_dtype=out_dtype)
+
+
 class DropPath(nn.Module):
     """Per-sample stochastic depth (timm's ``DropPath``, imported by the reference at ``wave_helper.py:26``)."""
 
@@ -138,13 +147,19 @@ class CCF_FFN(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         B, D, H, W, C = x.shape
         assert D * H * W == self.D * self.H * self.W
+        if fused_path(x):
+            # x may be an fp32 stream; GEMM operands and the 4C-wide intermediates use the compute dtype
+            cd = getattr(self, "compute_dtype", None) or x.dtype
+            t = F.linear(x.to(cd), ops.cast_cached(self.pwconv.weight, cd).view(self.C_hid, C), ops.cast_cached(self.pwconv.bias, cd))
+            t = _ln(self.norm1, t, gelu=True)                                  # LayerNorm + GELU, one pass
+            t = ops.dwconv3d_channels_last(t, *self._packed_dwconv())          # hand-written stencil
+            t = _ln(self.norm2, t, gelu=True)
+            f = F.linear(t, ops.cast_cached(self.fc.weight, cd), ops.cast_cached(self.fc.bias, cd))
+            return x + f
         # the 1^3 convolution is a per-voxel linear map: run it on the channels-last tensor directly
         t = F.linear(x, self.pwconv.weight.view(self.C_hid, C), self.pwconv.bias)
         t = self.act(self.norm1(t))
-        if x.is_cuda and not torch.is_grad_enabled():
-            t = ops.dwconv3d_channels_last(t, *self._packed_dwconv())      # hand-written stencil, channels-last
-        else:
-            t = self.dwconv(t.permute(0, 4, 1, 2, 3)).permute(0, 2, 3, 4, 1)
+        t = self.dwconv(t.permute(0, 4, 1, 2, 3)).permute(0, 2, 3, 4, 1)
         t = self.act(self.norm2(t))
         return x + self.fc(t)
 
@@ -187,8 +202,16 @@ class PatchMergingV2(nn.Module):
             return torch.cat([x[:, j::2, i::2, :] for i, j in itertools.product(range(2), range(2))], -1)
         raise ValueError(f"expecting 4D or 5D x, got {x.shape}.")
 
+    def _merge(self, x):
+        g = self._gather(x)
+        if fused_path(x):
+            cd = getattr(self, "compute_dtype", None) or x.dtype
+            n = _ln(self.norm, g, out_dtype=cd)
+            return F.linear(n, ops.cast_cached(self.reduction.weight, cd)).to(x.dtype)
+        return self.reduction(self.norm(g))
+
     def forward(self, x):
-        return self.reduction(self.norm(self._gather(x)))
+        return self._merge(x)
 
 
 class PatchMerging(PatchMergingV2):
@@ -202,7 +225,7 @@ class PatchMerging(PatchMergingV2):
             return super().forward(x)
         if x.dim() != 5:
             raise ValueError(f"expecting 5D x, got {x.shape}.")
-        return self.reduction(self.norm(self._gather(x)))
+        return self._merge(x)
 
 
 class Block(nn.Module):
@@ -262,6 +285,8 @@ class Block(nn.Module):
         D, H, W = self.img_size
         B, _, _, _, C = x.shape
         assert D == x.shape[1] and H == x.shape[2] and W == x.shape[3]
+        if fused_path(x):
+            return self._multi_scale_fused(x)
         shortcut = x
         cur = self.norm1(x)
         fused = None
@@ -278,6 +303,28 @@ class Block(nn.Module):
                 fused = a if fused is None else fused + a
         y = shortcut + self.drop_path(fused)
         y = y + self.drop_path(self.mlp(self.norm2(y)))
+        if self.level > 0:
+            return y, tuple(reversed(hfs))
+        return y
+
+    def _multi_scale_fused(self, x):
+        """Inference: x is the residual stream (fp32 or bf16).  LN -> DWT chain stays in the stream's dtype (the detail
+        bands are differences of neighbouring values, so they are computed before any rounding to bf16); attention
+        outputs come back in the compute dtype and are upsampled, summed and added to the stream by one kernel."""
+        D, H, W = self.img_size
+        cur = _ln(self.norm1, x)
+        coarse, hfs = [], []
+        for _ in range(self.attn_computation_level):
+            if self.level > 0:
+                cur, hf = ops.dwt3d_channels_last(cur, need_hf=self.need_hf)
+                if self.need_hf:
+                    hfs.append(self._details_as_dict(hf))
+            coarse.append(self.attn.forward_grid(cur))
+        if self.level > 0:
+            y = ops.upsample_trilinear_add(coarse, (D, H, W), base=x, out_dtype=x.dtype)
+        else:
+            y = x + coarse[0] if len(coarse) == 1 else x + sum(coarse)
+        y = y + self.mlp(_ln(self.norm2, y))
         if self.level > 0:
             return y, tuple(reversed(hfs))
         return y
@@ -338,11 +385,20 @@ class ProjectionUpsample(nn.Module):
         return cache[1], cache[2]
 
     def forward(self, x):
+        if fused_path(x):
+            xv = x.permute(0, 2, 3, 4, 1)                                # channels-last view
+            size = tuple(int(v * self.stride) for v in x.shape[2:])
+            up = ops.upsample_trilinear_add([xv], size, align_corners=True)   # shared by both branches
+            dw = ops.dwconv3d_channels_last(up, *self._packed_dwconv())
+            # GroupNorm(num_groups = C) = InstanceNorm + affine
+            n = ops.instance_norm_act(dw.permute(0, 4, 1, 2, 3), "none", eps=self.norm.eps,
+                                      gamma=ops.f32_cached(self.norm.weight), beta=ops.f32_cached(self.norm.bias))
+            y = self.conv3(self.act(self.conv2(n)))
+            if self.do_res:
+                y = y + self.res_conv[1](up.permute(0, 4, 1, 2, 3))
+            return y
         up = self.conv1[0](x)          # one upsample shared by both branches (the reference computes it twice)
-        if x.is_cuda and not torch.is_grad_enabled():
-            dw = ops.dwconv3d_channels_last(up.permute(0, 2, 3, 4, 1), *self._packed_dwconv()).permute(0, 4, 1, 2, 3)
-        else:
-            dw = self.conv1[1](up)
+        dw = self.conv1[1](up)
         y = self.conv3(self.act(self.conv2(self.norm(dw))))
         if self.do_res:
             y = y + self.res_conv[1](up)

@@ -270,26 +270,34 @@ def relpos_bias_expand(table: torch.Tensor, index: torch.Tensor) -> torch.Tensor
     return out
 
 
-def _window_attention_raw(x, qkv_w, qkv_b, proj_w, proj_b, bias_t, heads: int, ws: int, scale: float) -> torch.Tensor:
+def _window_attention_raw(x, qkv_w, qkv_b, proj_w, proj_b, bias_t, heads: int, ws: int, scale: float,
+                          compute_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """``compute_dtype`` (default: x.dtype) selects the kernels: bf16 -> tcgen05 tensor-core path (x may be fp32 or
+    bf16, the result is bf16); fp32 -> CUDA-core fp32 path."""
     dev = _need_cuda(x, qkv_w, qkv_b, proj_w, proj_b, bias_t)
     if x.dim() != 5:
         raise ValueError("expected x [B, D1, H1, W1, C]")
     B, D1, H1, W1, C = x.shape
-    code = _dtype_code(x)
+    cdt = compute_dtype or x.dtype
+    if cdt not in (torch.float32, torch.bfloat16):
+        raise ValueError(f"waveformer_b200: dtype {cdt} not supported (float32 or bfloat16)")
+    _dtype_code(x)
     x = x.contiguous()
-    ws_args = (code, B, D1, H1, W1, C, heads, ws)
+    code = 1 if cdt == torch.bfloat16 else 0
+    if code == 0 and x.dtype != torch.float32:
+        x = x.float()
+    x_code = _dtype_code(x)
     L = _lib.lib()
-    nbytes = L.wf_window_attn_workspace_bytes(*ws_args)
+    nbytes = L.wf_window_attn_workspace_bytes(code, B, D1, H1, W1, C, heads, ws)
     if nbytes == 0:
         raise ValueError(f"window attention: unsupported geometry grid={(D1, H1, W1)} C={C} heads={heads} ws={ws}")
     work = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    out = torch.empty_like(x)
-    cast = lambda t: None if t is None else t.detach().to(x.dtype).contiguous()
-    qkv_w, qkv_b, proj_w, proj_b = cast(qkv_w), cast(qkv_b), cast(proj_w), cast(proj_b)
+    out = torch.empty(x.shape, dtype=cdt, device=dev)
+    qkv_w, qkv_b, proj_w, proj_b = (cast_cached(t, cdt) for t in (qkv_w, qkv_b, proj_w, proj_b))
     with torch.cuda.device(dev):
-        st = L.wf_window_attn_fwd(x.data_ptr(), qkv_w.data_ptr(), _ptr(qkv_b), proj_w.data_ptr(), proj_b.data_ptr(),
-                                  bias_t.data_ptr(), out.data_ptr(), work.data_ptr(), nbytes, code, B, D1, H1, W1, C,
-                                  heads, ws, float(scale), _stream(dev))
+        st = L.wf_window_attn_fwd(x.data_ptr(), x_code, qkv_w.data_ptr(), _ptr(qkv_b), proj_w.data_ptr(),
+                                  proj_b.data_ptr(), bias_t.data_ptr(), out.data_ptr(), work.data_ptr(), nbytes, code, B,
+                                  D1, H1, W1, C, heads, ws, float(scale), _stream(dev))
     _lib.check(st, "wf_window_attn_fwd")
     _count(3)
     return out
@@ -306,17 +314,18 @@ class _WindowAttention(torch.autograd.Function):
     recomputing the window attention with torch ops under autograd - a library path, listed as a gap in DESIGN.md."""
 
     @staticmethod
-    def forward(ctx, x, qkv_w, qkv_b, proj_w, proj_b, table, index, bias_t, heads, ws, scale):
+    def forward(ctx, x, qkv_w, qkv_b, proj_w, proj_b, table, index, bias_t, heads, ws, scale, compute_dtype):
         ctx.save_for_backward(x, qkv_w, qkv_b, proj_w, proj_b, table, index)
         ctx.cfg = (heads, ws, scale)
-        return _window_attention_raw(x, qkv_w, qkv_b, proj_w, proj_b, bias_t, heads, ws, scale)
+        return _window_attention_raw(x, qkv_w, qkv_b, proj_w, proj_b, bias_t, heads, ws, scale, compute_dtype)
 
     @staticmethod
     def backward(ctx, g):
         x, qkv_w, qkv_b, proj_w, proj_b, table, index = ctx.saved_tensors
         heads, ws, scale = ctx.cfg
         with torch.enable_grad():
-            leaves = [t.detach().float().requires_grad_(True) for t in (x, qkv_w, qkv_b, proj_w, proj_b, table)]
+            srcs = (x, qkv_w, qkv_b, proj_w, proj_b, table)
+            leaves = [None if t is None else t.detach().float().requires_grad_(True) for t in srcs]
             xx, wq, bq, wp, bp, tb = leaves
             win = _window_partition(xx, ws)
             b_, n, c = win.shape
@@ -325,18 +334,19 @@ class _WindowAttention(torch.autograd.Function):
             s = s + tb[index.reshape(-1)].reshape(n, n, heads).permute(2, 0, 1)[None]
             o = (torch.softmax(s, -1) @ qkv[2]).transpose(1, 2).reshape(b_, n, c)
             y = torch.nn.functional.linear(o, wp, bp).reshape(x.shape)
-            grads = torch.autograd.grad(y, leaves, g.float())
-        srcs = (x, qkv_w, qkv_b, proj_w, proj_b, table)
-        out = [gr.to(s_.dtype) for gr, s_ in zip(grads, srcs)]
-        return out[0], out[1], out[2], out[3], out[4], out[5], None, None, None, None, None
+            live = [t for t in leaves if t is not None]
+            grads = list(torch.autograd.grad(y, live, g.float()))
+        out = [None if s_ is None else grads.pop(0).to(s_.dtype) for s_ in srcs]
+        return out[0], out[1], out[2], out[3], out[4], out[5], None, None, None, None, None, None
 
 
-def window_attention(x, qkv_w, qkv_b, proj_w, proj_b, table, index, bias_t, heads: int, ws: int, scale: float):
+def window_attention(x, qkv_w, qkv_b, proj_w, proj_b, table, index, bias_t, heads: int, ws: int, scale: float,
+                     compute_dtype: Optional[torch.dtype] = None):
     """Window partition + attention + reshape-only reverse on channels-last ``x[B, D1, H1, W1, C]``.
 
     Returns the window-major result buffer viewed as ``[B, D1, H1, W1, C]`` - exactly what the reference produces at
     ``wave_helper.py:497-499`` (it never applies the inverse permute)."""
-    return _WindowAttention.apply(x, qkv_w, qkv_b, proj_w, proj_b, table, index, bias_t, heads, ws, scale)
+    return _WindowAttention.apply(x, qkv_w, qkv_b, proj_w, proj_b, table, index, bias_t, heads, ws, scale, compute_dtype)
 
 
 
@@ -392,7 +402,8 @@ def _instnorm_stats(v: torch.Tensor, vs: int, eps: float) -> torch.Tensor:
 
 
 def instance_norm_act(x: torch.Tensor, act: str = "none", slope: float = 0.01, res: Optional[torch.Tensor] = None,
-                      res_norm: bool = False, eps: float = 1e-5, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                      res_norm: bool = False, eps: float = 1e-5, out: Optional[torch.Tensor] = None,
+                      gamma: Optional[torch.Tensor] = None, beta: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``act(InstanceNorm(x) + R)`` for ``x[B, C, D, H, W]`` (any strides; channels-last-3d is copy-free), where ``R`` is
     nothing, ``res`` or ``InstanceNorm(res)``.  Returns a [B, C, D, H, W] tensor with channels-last-3d strides; ``out``
     (optional) is a [B, D, H, W, C] channels-last destination, e.g. a channel slice of a concat buffer."""
@@ -413,12 +424,101 @@ def instance_norm_act(x: torch.Tensor, act: str = "none", slope: float = 0.01, r
     if ys is None or tuple(out.shape) != (B, D, H, W, C) or out.dtype != x.dtype:
         raise ValueError("out must be a voxel-dense [B, D, H, W, C] tensor of x's dtype")
     with torch.cuda.device(dev):
-        st = _lib.lib().wf_instnorm_apply_ndhwc(v.data_ptr(), mr.data_ptr(), _ptr(rv), _ptr(rmr), out.data_ptr(),
-                                                _ACT[act], float(slope), _dtype_code(x), B, D * H * W, C, vs, rs, ys,
-                                                _stream(dev))
+        st = _lib.lib().wf_instnorm_apply_ndhwc(v.data_ptr(), mr.data_ptr(), _ptr(rv), _ptr(rmr), _ptr(gamma), _ptr(beta),
+                                                out.data_ptr(), _ACT[act], float(slope), _dtype_code(x), B, D * H * W, C,
+                                                vs, rs, ys, _stream(dev))
     _lib.check(st, "wf_instnorm_apply_ndhwc")
     _count()
     return out.permute(0, 4, 1, 2, 3)
+
+
+_F32_CACHE = {}
+
+
+def f32_cached(p: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """fp32 contiguous copy of a (small) parameter, cached until the parameter is modified or moved."""
+    if p is None:
+        return None
+    key = id(p)
+    tag = (p._version, p.data_ptr(), p.device, p.dtype)
+    hit = _F32_CACHE.get(key)
+    if hit is None or hit[0] != tag:
+        hit = (tag, p.detach().float().contiguous())
+        _F32_CACHE[key] = hit
+    return hit[1]
+
+
+_CAST_CACHE = {}
+
+
+def cast_cached(p: Optional[torch.Tensor], dtype: torch.dtype) -> Optional[torch.Tensor]:
+    """``p`` in ``dtype`` (contiguous, detached); the converted copy is cached until ``p`` is modified or moved."""
+    if p is None:
+        return None
+    if p.dtype == dtype and p.is_contiguous():
+        return p.detach()
+    key = (id(p), dtype)
+    tag = (p._version, p.data_ptr(), p.device, p.dtype)
+    hit = _CAST_CACHE.get(key)
+    if hit is None or hit[0] != tag:
+        hit = (tag, p.detach().to(dtype).contiguous())
+        _CAST_CACHE[key] = hit
+    return hit[1]
+
+
+def layer_norm_cl(x: torch.Tensor, weight: Optional[torch.Tensor], bias: Optional[torch.Tensor], eps: float,
+                  gelu: bool = False, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """LayerNorm over the last dim of a channels-last tensor (any leading dims, last-dim stride 1), optional GELU;
+    ``out_dtype`` may differ from the input's (fp32 stream -> bf16 operand)."""
+    dev = _need_cuda(x, weight, bias)
+    C = x.shape[-1]
+    if x.stride(-1) != 1:
+        x = x.contiguous()
+    x2 = x.reshape(-1, C) if x.is_contiguous() else x.contiguous().reshape(-1, C)
+    rows = x2.shape[0]
+    out_dtype = out_dtype or x.dtype
+    y = torch.empty(x.shape, dtype=out_dtype, device=dev)
+    with torch.cuda.device(dev):
+        st = _lib.lib().wf_layernorm_ndhwc(x2.data_ptr(), _ptr(f32_cached(weight)), _ptr(f32_cached(bias)), y.data_ptr(),
+                                           _dtype_code(x2), _dtype_code(y), rows, C, x2.stride(0), C, float(eps),
+                                           int(gelu), _stream(dev))
+    _lib.check(st, "wf_layernorm_ndhwc")
+    _count()
+    return y
+
+
+def upsample_trilinear_add(srcs, size, base: Optional[torch.Tensor] = None, align_corners: bool = False,
+                           out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """``base + sum_s trilinear(srcs[s] -> size)`` for channels-last ``[B, d, h, w, C]`` sources (1..3 of them)."""
+    import ctypes
+
+    srcs = [s.contiguous() for s in srcs]
+    dev = _need_cuda(*srcs, base)
+    B, C = srcs[0].shape[0], srcs[0].shape[-1]
+    D, H, W = size
+    for s in srcs:
+        if s.dim() != 5 or s.shape[0] != B or s.shape[-1] != C or s.dtype != srcs[0].dtype:
+            raise ValueError("sources must be [B, d, h, w, C] with one dtype")
+    io_dtype = out_dtype or (base.dtype if base is not None else srcs[0].dtype)
+    bs = C
+    if base is not None:
+        if tuple(base.shape) != (B, D, H, W, C) or base.dtype != io_dtype:
+            raise ValueError("base must be [B, D, H, W, C] of the output dtype")
+        bs = _voxel_stride(base)
+        if bs is None:
+            base = base.contiguous()
+            bs = C
+    y = torch.empty((B, D, H, W, C), dtype=io_dtype, device=dev)
+    n = len(srcs)
+    ptrs = (ctypes.c_void_p * n)(*[s.data_ptr() for s in srcs])
+    dims = (ctypes.c_int * (3 * n))(*[v for s in srcs for v in s.shape[1:4]])
+    with torch.cuda.device(dev):
+        st = _lib.lib().wf_upsample_trilinear_add_ndhwc(ptrs, dims, n, _ptr(base), y.data_ptr(), _dtype_code(srcs[0]),
+                                                        _dtype_code(y), int(align_corners), B, D, H, W, C, bs, C,
+                                                        _stream(dev))
+    _lib.check(st, "wf_upsample_trilinear_add_ndhwc")
+    _count()
+    return y
 
 # ============================================================================================ sliding window ====
 def sw_gather(vol: torch.Tensor, starts: torch.Tensor, roi, dtype: torch.dtype, channels_last: bool) -> torch.Tensor:
