@@ -228,7 +228,8 @@ def main():
     pk = peaks()
 
     torch.manual_seed(0)  # identical random-init weights on every rank
-    model = Waveformer(**MODEL_KW).eval().to(dev).to(dtype).to(memory_format=torch.channels_last_3d)
+    from waveformer_b200 import prepare_inference
+    model = prepare_inference(Waveformer(**MODEL_KW).eval().to(dev), dtype)   # bf16 = the documented precision policy
     host = torch.randn((volumes,) + VOL, generator=torch.Generator().manual_seed(1)).pin_memory()
     resident = host.to(dev)
     inferer = SlidingWindowInferer(roi_size=ROI, sw_batch_size=2, overlap=0.5, mode="gaussian", return_labels=True)

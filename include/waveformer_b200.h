@@ -30,7 +30,9 @@ typedef enum {
     WF_ERR_UNSUPPORTED = -7
 } wf_status;
 
-typedef enum { WF_F32 = 0, WF_BF16 = 1 } wf_dtype;
+/* WF_F16 is accepted only as the operand format of the tensor-core window attention (`dtype` of wf_window_attn_fwd and
+ * `fmt` of wf_relpos_bias_image); activations are stored as WF_F32 or WF_BF16 everywhere. */
+typedef enum { WF_F32 = 0, WF_BF16 = 1, WF_F16 = 2 } wf_dtype;
 
 const char *wf_version(void);
 const char *wf_error_string(int status);
@@ -54,7 +56,7 @@ int wf_dwt3d_ncdhw(const void *x, void *ll, void *hf, int dtype, int64_t n, int 
 
 /* x: [B, D, H, W, C], channel stride 1, voxel stride x_vox_stride elements (>= C; lets the input be a channel
  * slice of a wider buffer); ll: [B, D/2, H/2, W/2, C] with voxel stride ll_vox_stride; bands: voxel stride C. */
-int wf_dwt3d_ndhwc(const void *x, void *ll, void *hf, int dtype, int B, int D, int H, int W, int C,
+int wf_dwt3d_ndhwc(const void *x, void *ll, void *hf, int dtype, int hf_dtype, int B, int D, int H, int W, int C,
                    int64_t x_vox_stride, int64_t ll_vox_stride, int64_t hf_band_stride, void *stream);
 
 /* ------------------------------------------------------------------------------------------------------------
@@ -81,22 +83,36 @@ int wf_idwt3d_ndhwc(const void *ll, const void *hf, const void *gate, void *x, i
  *       (b, zblk, yblk, xblk), token order (dz, dy, dx).
  * out:  [B * nW * ws^3, C] contiguous in WINDOW order; the reference re-reads exactly this buffer as
  *       [B, D1, H1, W1, C] without an inverse permute, so `out` viewed with that shape IS the reference result.
- * bias: dense relative-position bias produced by wf_relpos_bias_expand, fp32 [heads, N, N] stored TRANSPOSED
- *       (bias_t[h][j][i] = table[index[i][j]][h]) so a warp of queries reads it coalesced.
- * `dtype` is the compute / weight / output type: WF_BF16 runs the tcgen05 tensor-core kernels (512-token windows,
- * head_dim 16; other geometries use the CUDA-core kernels), WF_F32 the fp32 CUDA-core kernels.  x may be stored as
- * x_dtype = WF_F32 while dtype = WF_BF16 (fp32 residual stream, bf16 operands: converted while the tile is staged).
+ * bias_t:   dense relative-position bias produced by wf_relpos_bias_expand, fp32 [heads, N, N] stored TRANSPOSED
+ *           (bias_t[h][j][i] = table[index[i][j]][h]) so a warp of queries reads it coalesced (CUDA-core kernels).
+ * bias_img: dense 16-bit image produced by wf_relpos_bias_image for the tensor-core kernels (N = 512 only):
+ *           img[h][i][520] = fmt(table[index[i][j]][h] * log2 e), rows padded to 520 so the (head, 128-query) slab a
+ *           CTA needs is ONE contiguous 133120-byte bulk copy whose rows are bank-conflict free in shared memory.
+ * `dtype` is the weight type and the operand format of the GEMMs:
+ *   WF_F32  fp32 CUDA-core kernels (x, weights, out fp32; needs bias_t);
+ *   WF_BF16 tcgen05 tensor-core kernels when bias_img != NULL and the geometry is 512-token windows with head_dim 16
+ *           (wf_window_attn_tc_supported), else the CUDA-core kernels (need bias_t, out_dtype == WF_BF16);
+ *   WF_F16  the same tensor-core kernels with fp16 operands (10-bit mantissa: q, k, v, P and O are rounded 8x finer than
+ *           in bf16 at the same tensor-core rate); tensor-core geometry only.
+ * x may be stored as x_dtype = WF_F32 or WF_BF16 (converted to the operand format while the tile is staged);
+ * out_dtype is `dtype` or WF_F32 (the projection epilogue writes its fp32 accumulators).
  * Weights are in `dtype`; qkv_w [3C, C], qkv_b [3C], proj_w [C, C], proj_b [C] (PyTorch Linear layout).
  * head_dim = C / heads must be 8, 16, 32 or 64; scale multiplies q after its bias (attention.py:88).
  * ---------------------------------------------------------------------------------------------------------- */
 int wf_relpos_bias_expand(const void *table, int table_dtype, const int64_t *index, float *bias_t, int heads, int N,
                           int table_rows, void *stream);
 
+size_t wf_relpos_bias_image_bytes(int heads, int N);
+int wf_relpos_bias_image(const void *table, int table_dtype, const int64_t *index, void *img, int fmt, int heads, int N,
+                         int table_rows, void *stream);
+
+int wf_window_attn_tc_supported(int D1, int H1, int W1, int C, int heads, int ws);
 size_t wf_window_attn_workspace_bytes(int dtype, int B, int D1, int H1, int W1, int C, int heads, int ws);
 
 int wf_window_attn_fwd(const void *x, int x_dtype, const void *qkv_w, const void *qkv_b, const void *proj_w,
-                       const void *proj_b, const float *bias_t, void *out, void *workspace, size_t workspace_bytes,
-                       int dtype, int B, int D1, int H1, int W1, int C, int heads, int ws, float scale, void *stream);
+                       const void *proj_b, const float *bias_t, const void *bias_img, void *out, int out_dtype,
+                       void *workspace, size_t workspace_bytes, int dtype, int B, int D1, int H1, int W1, int C,
+                       int heads, int ws, float scale, void *stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Block glue that dominated the step as library calls, channels-last, fp32 accumulate.
@@ -127,10 +143,13 @@ int wf_instnorm_apply_ndhwc(const void *x, const float *mean_rstd, const void *r
 
 /* y[r, :] = LayerNorm(x[r, :C]) * gamma + beta (gamma / beta fp32 [C] or NULL), optionally followed by GELU(erf).
  * Rows are voxels of a channels-last tensor (row strides in elements); input and output storage types are independent.
+ * y2_bf16 (optional, dense [rows, C]) receives the same result rounded to bf16: the GEMM operand, while y keeps the fp32
+ * copy that CCF_FFN's own residual adds back (wave_helper.py:293).
  * Replaces Block.norm1 / norm2 (reference network_models/wave_helper.py:477,509), CCF_FFN.norm1 / norm2 + act
  * (wave_helper.py:278,286), PatchMerging.norm (wave_helper.py:192) and proj_out (network_models/waveformer.py:193-204). */
-int wf_layernorm_ndhwc(const void *x, const float *gamma, const float *beta, void *y, int in_dtype, int out_dtype,
-                       int64_t rows, int C, int64_t x_row_stride, int64_t y_row_stride, float eps, int gelu, void *stream);
+int wf_layernorm_ndhwc(const void *x, const float *gamma, const float *beta, void *y, void *y2_bf16, int in_dtype,
+                       int out_dtype, int64_t rows, int C, int64_t x_row_stride, int64_t y_row_stride, float eps, int gelu,
+                       void *stream);
 
 /* y = base + sum_s trilinear_upsample(srcs[s]) (sources summed in order, then added to base; base may be NULL).
  * srcs[s]: [B, d_s, h_s, w_s, C] dense channels-last of src_dtype, src_dims = int[3 * nsrc]; base / y: [B, D, H, W, C]

@@ -1,56 +1,73 @@
 #!/usr/bin/env python
-"""bf16 accuracy of the product forward against the fp32 reference fixture (tests/golden/waveformer_128.npz):
-max-relative error, relative L2 error and argmax agreement, plus where the error enters (per-stage)."""
+"""bf16 accuracy of the product forward on one 1x4x128^3 window, per precision policy and per weight set:
+max-relative error, relative L2 error, argmax agreement, and argmax agreement restricted to voxels whose fp32 decision
+margin (top-1 minus top-2 logit) exceeds the 2e-2 * max|logit| error tolerance.
+
+Weight sets: "unit-gain" = oracle.state.make_state_dict (every layer ~unit gain: the stress case the parity tests use;
+reference = CPU oracle); "ctor-init" = the constructor's own initialisation (what the reference calls random init:
+trunc-normal 0.02 linears; reference = the fp32 product path, itself <= 1e-6 from the oracle)."""
 import os
 import sys
 
-import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from helpers import load_npz, seeded_randn  # noqa: E402
+from helpers import seeded_randn  # noqa: E402
 from oracle.model import waveformer_forward  # noqa: E402
 from oracle.state import ModelConfig, make_state_dict  # noqa: E402
+from waveformer_b200 import prepare_inference  # noqa: E402
 from waveformer_b200.network_models import Waveformer  # noqa: E402
 
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 cfg = ModelConfig(img_size=(128,) * 3)
-sd = make_state_dict(cfg, seed=0)
 x = seeded_randn((1, 4, 128, 128, 128), 1)
-with torch.no_grad():
-    ref, mid = waveformer_forward(sd, x, cfg, return_intermediates=True)
 
 
-def report(tag, y):
+def report(tag, y, ref):
     y = y.float().cpu()
-    err = (y - ref)
-    print(f"{tag:34s} max-rel {float(err.abs().max() / ref.abs().max()):.4f}  rel-L2 {float(err.norm() / ref.norm()):.4f}  "
-          f"argmax-agree {float((y.argmax(1) == ref.argmax(1)).float().mean()):.5f}")
+    err = y - ref
+    tol = 2e-2 * float(ref.abs().max())
+    top = ref.topk(2, dim=1).values
+    clear = (top[:, 0] - top[:, 1]) > tol
+    same = y.argmax(1) == ref.argmax(1)
+    print(f"{tag:46s} max-rel {float(err.abs().max() / ref.abs().max()):.4f}  rel-L2 {float(err.norm() / ref.norm()):.4f}  "
+          f"argmax {float(same.float().mean()):.5f}  argmax|margin>tol {float(same[clear].float().mean()):.5f} "
+          f"({float(clear.float().mean()):.3f} of voxels)", flush=True)
 
 
-def build(dtype):
+def build(sd, **policy):
     m = Waveformer(**cfg.kwargs()).eval()
-    m.load_state_dict(sd, strict=True)
-    return m.cuda().to(dtype).to(memory_format=torch.channels_last_3d)
+    if sd is not None:
+        m.load_state_dict(sd, strict=True)
+    return m
 
+
+POLICIES = [("pure bf16 (model.to(bf16))", dict(fp32_stream=False)),
+            ("policy, attention bf16 operands", dict(attention="bf16")),
+            ("policy, attention fp16 operands (default)", dict(attention="fp16")),
+            ("policy, attention fp32 CUDA cores", dict(attention="fp32"))]
 
 with torch.no_grad():
-    m32 = build(torch.float32)
-    report("fp32 product", m32(x.cuda()))
-    m16 = build(torch.bfloat16)
-    report("bf16 product (pure bf16)", m16(x.cuda()))
-    # where does it enter?  feed fp32 encoder outputs into the bf16 decoder and vice versa
-    outs32, hf32 = m32.waveformer_encoder(x.cuda().contiguous(memory_format=torch.channels_last_3d))
-    outs16, hf16 = m16.waveformer_encoder(x.cuda().bfloat16().contiguous(memory_format=torch.channels_last_3d))
-    for i, (a, b) in enumerate(zip(outs16, outs32)):
-        e = (a.float() - b)
-        print(f"  encoder out{i}: max-rel {float(e.abs().max() / b.abs().max()):.4f} rel-L2 {float(e.norm() / b.norm()):.4f}")
-    # autocast-style: fp32 weights + autocast(bf16)
-    with torch.autocast("cuda", dtype=torch.bfloat16):
-        try:
-            report("fp32 model under autocast(bf16)", m32(x.cuda()))
-        except Exception as exc:  # noqa: BLE001
-            print("autocast run failed:", repr(exc)[:300])
+    for name in ("unit-gain", "ctor-init"):
+        if name == "unit-gain":
+            sd = make_state_dict(cfg, seed=0)
+            ref = waveformer_forward(sd, x, cfg)
+        else:
+            torch.manual_seed(0)
+            sd = {k: v.clone() for k, v in Waveformer(**cfg.kwargs()).state_dict().items()}
+            ref = None
+        m32 = prepare_inference(build(sd).cuda(), torch.float32)
+        y32 = m32(x.cuda()).float().cpu()
+        if ref is None:
+            ref = y32
+        print(f"== weights: {name}")
+        report("fp32 product", y32, ref)
+        del m32
+        for tag, kw in POLICIES:
+            m = prepare_inference(build(sd).cuda(), torch.bfloat16, **kw)
+            report(tag, m(x.cuda()), ref)
+            del m
+            torch.cuda.empty_cache()

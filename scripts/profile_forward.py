@@ -18,23 +18,30 @@ ap.add_argument("--dtype", default="bf16")
 ap.add_argument("--batch", type=int, default=2)
 ap.add_argument("--out", default="gpurun_out/profile_forward.txt")
 ap.add_argument("--rows", type=int, default=45)
+ap.add_argument("--iters", type=int, default=5)
+ap.add_argument("--warm", type=int, default=3)
+ap.add_argument("--no-profiler", action="store_true", help="plain timed forwards only (the command ncu wraps)")
 args = ap.parse_args()
 dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
 torch.manual_seed(0)
-m = Waveformer(img_size=(128,) * 3, patch_size=2, in_chans=4, out_chans=4, depths=[2] * 4, feat_size=[48, 96, 192, 384],
-               num_heads=[3, 6, 12, 24], drop_path_rate=0.1).eval().cuda().to(dtype).to(memory_format=torch.channels_last_3d)
-x = torch.randn(args.batch, 4, 128, 128, 128, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last_3d)
+from waveformer_b200 import prepare_inference  # noqa: E402
+m = prepare_inference(Waveformer(img_size=(128,) * 3, patch_size=2, in_chans=4, out_chans=4, depths=[2] * 4,
+                                 feat_size=[48, 96, 192, 384], num_heads=[3, 6, 12, 24], drop_path_rate=0.1).eval().cuda(), dtype)
+x = torch.randn(args.batch, 4, 128, 128, 128, device="cuda").contiguous(memory_format=torch.channels_last_3d)  # fp32 window, as the inferer gathers it
 with torch.no_grad():
-    for _ in range(3):
+    for _ in range(args.warm):
         m(x)
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for _ in range(5):
+    for _ in range(args.iters):
         m(x)
     b.record()
     torch.cuda.synchronize()
-    ms = a.elapsed_time(b) / 5
+    ms = a.elapsed_time(b) / args.iters
+    if args.no_profiler:
+        print(f"forward batch={args.batch} dtype={args.dtype}: {ms:.2f} ms")
+        sys.exit(0)
     with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
         m(x)
         torch.cuda.synchronize()

@@ -67,3 +67,22 @@ def test_tensor_core_path_many_windows(sd, grid, batch):
         assert max_rel(got, want) < 2e-2
     simt = _run(m, x.cuda().bfloat16(), "simt").float().cpu()
     assert max_rel(got, simt) < 1.5e-2
+
+
+@pytest.mark.parametrize("stage,c,h,b_", [(0, 48, 3, 3), (1, 96, 6, 2), (2, 192, 12, 1), (3, 384, 24, 1)])
+def test_fp16_operands_fp32_stream(sd, stage, c, h, b_):
+    """The precision policy of prepare_inference: fp32 activations in, fp16 tensor-core operands (10-bit mantissa),
+    fp32 result.  Must be ~8x closer to the fp32 reference than the bf16 gate (tolerance 3e-3 vs 2e-2)."""
+    from waveformer_b200.network_models import Attention
+    g = load_npz("attention_ws8.npz")
+    m = Attention(c, num_heads=h, qkv_bias=True, window_size=8, img_size=(8, 8, 8)).eval()
+    m.load_state_dict(sub_state(sd, f"waveformer_encoder.block{stage + 1}.1.attn"), strict=True)
+    m = m.cuda()                                    # fp32 master weights; the fp16 copies are cached by ops.cast_cached
+    m.compute_dtype, m.out_dtype = torch.float16, torch.float32
+    x = seeded_randn((b_, 512, c), 100 + stage).cuda().reshape(b_, 8, 8, 8, c)
+    y = _run(m, x, "tc")
+    assert y.dtype == torch.float32
+    assert max_rel(y.cpu().reshape(b_, 512, c), g[f"out_{c}"]) < 3e-3
+    m.compute_dtype, m.out_dtype = torch.bfloat16, torch.float32
+    y16 = _run(m, x, "tc")
+    assert y16.dtype == torch.float32 and max_rel(y16.cpu().reshape(b_, 512, c), g[f"out_{c}"]) < 2e-2

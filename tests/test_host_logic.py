@@ -178,3 +178,21 @@ def test_sharded_inferer_two_ranks_gloo(tmp_path, world):
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
     assert "OK" in res.stdout
+
+
+def test_cast_cache_never_serves_a_dead_tensors_copy():
+    """id() values are recycled by CPython: the operand-copy cache must key on object identity (weakref), not on id."""
+    from waveformer_b200 import ops
+    seen = set()
+    for i in range(200):
+        p = torch.full((4, 4), float(i))
+        q = ops.cast_cached(p, torch.bfloat16)
+        assert float(q[0, 0]) == float(torch.tensor(float(i)).bfloat16())
+        assert ops.cast_cached(p, torch.bfloat16) is q          # second call: cached
+        seen.add(id(p))
+        del p, q
+    assert len(seen) < 200 or True                               # ids usually repeat; correctness is asserted above
+    p = torch.ones(3)
+    q = ops.cast_cached(p, torch.bfloat16)
+    p.mul_(2)                                                    # in-place update bumps _version -> new copy
+    assert float(ops.cast_cached(p, torch.bfloat16)[0]) == 2.0 and float(q[0]) == 1.0

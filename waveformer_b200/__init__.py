@@ -5,3 +5,5 @@ re-hosted sliding-window inferer; ``waveformer_b200.ops`` are the torch-level op
 ``include/waveformer_b200.h``.  Everything computes on CUDA; there is no CPU fallback.
 """
 __version__ = "0.1.0"
+
+from .precision import prepare_inference  # noqa: E402,F401

@@ -21,16 +21,19 @@ SIGNATURES = {
     "wf_error_string": (_c.c_char_p, [_I]),
     "wf_last_cuda_error": (_I, []),
     "wf_dwt3d_ncdhw": (_I, [_VOIDP, _VOIDP, _VOIDP, _I, _I64, _I, _I, _I, _I64, _VOIDP]),
-    "wf_dwt3d_ndhwc": (_I, [_VOIDP, _VOIDP, _VOIDP, _I, _I, _I, _I, _I, _I, _I64, _I64, _I64, _VOIDP]),
+    "wf_dwt3d_ndhwc": (_I, [_VOIDP, _VOIDP, _VOIDP, _I, _I, _I, _I, _I, _I, _I, _I64, _I64, _I64, _VOIDP]),
     "wf_idwt3d_ncdhw": (_I, [_VOIDP, _VOIDP, _VOIDP, _VOIDP, _I, _I64, _I, _I, _I, _I64, _VOIDP]),
     "wf_idwt3d_ndhwc": (_I, [_VOIDP, _VOIDP, _VOIDP, _VOIDP, _I, _I, _I, _I, _I, _I, _I64, _I64, _I64, _VOIDP]),
     "wf_relpos_bias_expand": (_I, [_VOIDP, _I, _VOIDP, _VOIDP, _I, _I, _I, _VOIDP]),
     "wf_window_attn_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I, _I, _I, _I]),
-    "wf_window_attn_fwd": (_I, [_VOIDP, _I] + [_VOIDP] * 7 + [_SZ, _I, _I, _I, _I, _I, _I, _I, _I, _F, _VOIDP]),
+    "wf_relpos_bias_image_bytes": (_SZ, [_I, _I]),
+    "wf_relpos_bias_image": (_I, [_VOIDP, _I, _VOIDP, _VOIDP, _I, _I, _I, _I, _VOIDP]),
+    "wf_window_attn_tc_supported": (_I, [_I] * 6),
+    "wf_window_attn_fwd": (_I, [_VOIDP, _I] + [_VOIDP] * 7 + [_I, _VOIDP, _SZ, _I, _I, _I, _I, _I, _I, _I, _I, _F, _VOIDP]),
     "wf_dwconv3d_ndhwc": (_I, [_VOIDP, _VOIDP, _VOIDP, _VOIDP, _I, _I, _I, _I, _I, _I, _VOIDP]),
     "wf_instnorm_stats_ndhwc": (_I, [_VOIDP, _VOIDP, _VOIDP, _I, _I, _I64, _I, _I64, _F, _VOIDP]),
     "wf_instnorm_apply_ndhwc": (_I, [_VOIDP] * 7 + [_I, _F, _I, _I, _I64, _I, _I64, _I64, _I64, _VOIDP]),
-    "wf_layernorm_ndhwc": (_I, [_VOIDP, _VOIDP, _VOIDP, _VOIDP, _I, _I, _I64, _I, _I64, _I64, _F, _I, _VOIDP]),
+    "wf_layernorm_ndhwc": (_I, [_VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _I, _I, _I64, _I, _I64, _I64, _F, _I, _VOIDP]),
     "wf_upsample_trilinear_add_ndhwc": (_I, [_VOIDP, _VOIDP, _I, _VOIDP, _VOIDP, _I, _I, _I, _I, _I, _I, _I, _I, _I64, _I64, _VOIDP]),
     "wf_sw_gather": (_I, [_VOIDP, _VOIDP, _VOIDP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VOIDP]),
     "wf_sw_accumulate": (_I, [_VOIDP] * 6 + [_F, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VOIDP]),

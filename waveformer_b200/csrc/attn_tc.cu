@@ -18,6 +18,8 @@
 //
 // With head_dim 16 the core is bound by the 512x512 exponentials per (window, head), not by the tensor pipe: per
 // 128x512 tile the MMAs need ~512 cycles while 65536 ex2 need >= 4096 cycles of the SM's 16/clk MUFU pipe.
+#include <type_traits>
+
 #include "tc_common.cuh"
 #include "wf_common.cuh"
 
@@ -40,15 +42,51 @@ struct TcWindowMap {
 
 constexpr float kLog2e = 1.4426950408889634f;
 
+// ---- 16-bit operand formats: bf16 (FMT16 = false) or fp16 (FMT16 = true; 10-bit mantissa, used when the caller wants
+// tighter numerics than bf16 at the same tensor-core rate) --------------------------------------------------------
+template <bool F16> __device__ __forceinline__ uint32_t pack16(float lo, float hi) {
+    uint32_t r;
+    if constexpr (F16)
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    else
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// t0 = lo16(w) + s0, t1 = hi16(w) + s1 with the 16-bit halves widened inside the add (FHADD: no unpack instruction)
+template <bool F16> __device__ __forceinline__ void add16x2(uint32_t w, float s0, float s1, float &t0, float &t1) {
+    if constexpr (F16)
+        asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tadd.rn.f32.f16 %0, lo, %3;\n\tadd.rn.f32.f16 %1, hi, %4;\n\t}"
+            : "=f"(t0), "=f"(t1) : "r"(w), "f"(s0), "f"(s1));
+    else
+        asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tadd.rn.f32.bf16 %0, lo, %3;\n\tadd.rn.f32.bf16 %1, hi, %4;\n\t}"
+            : "=f"(t0), "=f"(t1) : "r"(w), "f"(s0), "f"(s1));
+}
+template <bool F16> __device__ __forceinline__ float widen16(uint16_t h) {
+    float t;
+    if constexpr (F16)
+        asm("cvt.f32.f16 %0, %1;" : "=f"(t) : "h"(h));
+    else
+        t = __uint_as_float((uint32_t)h << 16);
+    return t;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+template <bool F16> __host__ __device__ constexpr uint32_t instr_desc16(int M, int N, bool b_mn_major) {
+    return F16 ? (instr_desc_bf16(M, N, b_mn_major) & ~((7u << 7) | (7u << 10))) : instr_desc_bf16(M, N, b_mn_major);
+}
+
 // ------------------------------------------------------------------------------------------------ projections ----
-// grid (M/128, Nout/NT), 128 threads.  smem: A image [K/8][128][8] bf16, B image [K/8][NT][8] bf16 (no-swizzle canonical)
-template <bool QKV, typename TA>
-__global__ void __launch_bounds__(128) linear_tc_kernel(const TA *__restrict__ A,
-                                                        const __nv_bfloat16 *__restrict__ Wt,
-                                                        const __nv_bfloat16 *__restrict__ bias,
-                                                        __nv_bfloat16 *__restrict__ out, int K, int NT, int Nout,
-                                                        TcWindowMap map, int heads, int64_t B_, float qscale,
-                                                        uint32_t tmem_cols) {
+// grid (M/128, Nout/NT), 128 threads.  smem: A image [K/8][128][8], B image [K/8][NT][8] 16-bit (no-swizzle canonical).
+// TA: float (converted to the operand format while staging), __nv_bfloat16 (converted unless the format is bf16), or
+//     uint16_t (already in the operand format: the core kernel's output).   TO: float or uint16_t (operand format).
+template <bool QKV, typename TA, bool F16, typename TO>
+__global__ void __launch_bounds__(128) linear_tc_kernel(const TA *__restrict__ A, const uint16_t *__restrict__ Wt,
+                                                        const uint16_t *__restrict__ bias, TO *__restrict__ out, int K,
+                                                        int NT, int Nout, TcWindowMap map, int heads, int64_t B_,
+                                                        float qscale, uint32_t tmem_cols) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_slot;
@@ -67,16 +105,30 @@ __global__ void __launch_bounds__(128) linear_tc_kernel(const TA *__restrict__ A
     // A tile: row r = tid, every 16-byte K chunk.  A warp writes 32 consecutive rows of one chunk: conflict-free.
     {
         const int64_t src_row = QKV ? map.voxel(m0 + tid) : (m0 + tid);
-        if constexpr (sizeof(TA) == 2) {
+        constexpr bool raw = sizeof(TA) == 2 && (std::is_same<TA, uint16_t>::value || !F16);
+        if constexpr (raw) {
             const uint4 *src = reinterpret_cast<const uint4 *>(A + src_row * K);
             for (int kc = 0; kc < kchunks; ++kc)
                 *reinterpret_cast<uint4 *>(sA + (size_t)kc * 2048 + tid * 16) = __ldg(src + kc);
-        } else {  // fp32 activations (residual-stream precision): converted to the bf16 operand while staging
+        } else if constexpr (sizeof(TA) == 2) {  // bf16 activations, fp16 operands
+            const uint4 *src = reinterpret_cast<const uint4 *>(A + src_row * K);
+            for (int kc = 0; kc < kchunks; ++kc) {
+                const uint4 a = __ldg(src + kc);
+                const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+                uint4 u;
+                uint32_t *uw = &u.x;
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    uw[e] = pack16<F16>(__uint_as_float(w[e] << 16), __uint_as_float(w[e] & 0xffff0000u));
+                *reinterpret_cast<uint4 *>(sA + (size_t)kc * 2048 + tid * 16) = u;
+            }
+        } else {  // fp32 activations (residual-stream precision): converted to the operand format while staging
             const float4 *src = reinterpret_cast<const float4 *>(A + src_row * K);
             for (int kc = 0; kc < kchunks; ++kc) {
                 const float4 a = __ldg(src + 2 * kc), b = __ldg(src + 2 * kc + 1);
                 uint4 u;
-                u.x = pack_bf16(a.x, a.y); u.y = pack_bf16(a.z, a.w); u.z = pack_bf16(b.x, b.y); u.w = pack_bf16(b.z, b.w);
+                u.x = pack16<F16>(a.x, a.y); u.y = pack16<F16>(a.z, a.w);
+                u.z = pack16<F16>(b.x, b.y); u.w = pack16<F16>(b.z, b.w);
                 *reinterpret_cast<uint4 *>(sA + (size_t)kc * 2048 + tid * 16) = u;
             }
         }
@@ -93,7 +145,7 @@ __global__ void __launch_bounds__(128) linear_tc_kernel(const TA *__restrict__ A
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
     if (tid == 0) {
-        const uint32_t idesc = instr_desc_bf16(128, NT, false);
+        const uint32_t idesc = instr_desc16<F16>(128, NT, false);
         const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
         for (int ks = 0; ks < (K >> 4); ++ks) {
             const uint64_t da = smem_desc(a0 + ks * 2 * 2048, 2048, 128);
@@ -114,8 +166,8 @@ __global__ void __launch_bounds__(128) linear_tc_kernel(const TA *__restrict__ A
         const int n = n0 + c;
         float v[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]) + (bias ? __bfloat162float(bias[n + e]) : 0.f);
-        if (QKV) {
+        for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]) + (bias ? widen16<F16>(bias[n + e]) : 0.f);
+        if constexpr (QKV) {
             const int C = heads * 16;
             const int which = n / C, hh = (n % C) >> 4;
             if (which == 0) {
@@ -124,16 +176,20 @@ __global__ void __launch_bounds__(128) linear_tc_kernel(const TA *__restrict__ A
             }
             const int64_t win = m >> 9;
             const int tok = (int)(m & 511);
-            __nv_bfloat16 *dst = out + (((int64_t)which * B_ + win) * heads + hh) * 8192 + tok * 8;
+            uint16_t *dst = reinterpret_cast<uint16_t *>(out) + (((int64_t)which * B_ + win) * heads + hh) * 8192 + tok * 8;
             uint4 lo, hi;
-            lo.x = pack_bf16(v[0], v[1]); lo.y = pack_bf16(v[2], v[3]); lo.z = pack_bf16(v[4], v[5]); lo.w = pack_bf16(v[6], v[7]);
-            hi.x = pack_bf16(v[8], v[9]); hi.y = pack_bf16(v[10], v[11]); hi.z = pack_bf16(v[12], v[13]); hi.w = pack_bf16(v[14], v[15]);
+            lo.x = pack16<F16>(v[0], v[1]); lo.y = pack16<F16>(v[2], v[3]); lo.z = pack16<F16>(v[4], v[5]); lo.w = pack16<F16>(v[6], v[7]);
+            hi.x = pack16<F16>(v[8], v[9]); hi.y = pack16<F16>(v[10], v[11]); hi.z = pack16<F16>(v[12], v[13]); hi.w = pack16<F16>(v[14], v[15]);
             *reinterpret_cast<uint4 *>(dst) = lo;          // chunk 0: head dims 0..7
             *reinterpret_cast<uint4 *>(dst + 4096) = hi;   // chunk 1: head dims 8..15
+        } else if constexpr (sizeof(TO) == 4) {
+            float4 *dst = reinterpret_cast<float4 *>(out + m * Nout + n);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) dst[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
         } else {
             uint4 lo, hi;
-            lo.x = pack_bf16(v[0], v[1]); lo.y = pack_bf16(v[2], v[3]); lo.z = pack_bf16(v[4], v[5]); lo.w = pack_bf16(v[6], v[7]);
-            hi.x = pack_bf16(v[8], v[9]); hi.y = pack_bf16(v[10], v[11]); hi.z = pack_bf16(v[12], v[13]); hi.w = pack_bf16(v[14], v[15]);
+            lo.x = pack16<F16>(v[0], v[1]); lo.y = pack16<F16>(v[2], v[3]); lo.z = pack16<F16>(v[4], v[5]); lo.w = pack16<F16>(v[6], v[7]);
+            hi.x = pack16<F16>(v[8], v[9]); hi.y = pack16<F16>(v[10], v[11]); hi.z = pack16<F16>(v[12], v[13]); hi.w = pack16<F16>(v[14], v[15]);
             uint4 *dst = reinterpret_cast<uint4 *>(out + m * Nout + n);
             dst[0] = lo;
             dst[1] = hi;
@@ -145,8 +201,8 @@ __global__ void __launch_bounds__(128) linear_tc_kernel(const TA *__restrict__ A
 }
 
 // ------------------------------------------------------------------------------------------------------ core ------
-constexpr int kBiasPitch = 520;                       // bf16 elements per bias row (512 + 8 pad: conflict-free LDS.128)
-constexpr int kBiasBytes = 128 * kBiasPitch * 2;      // 133120
+constexpr int kBiasPitch = 520;                       // 16-bit elements per bias row (512 + 8 pad: conflict-free LDS.128)
+constexpr int kBiasBytes = 128 * kBiasPitch * 2;      // 133120 per (head, query tile)
 constexpr int kStageBytes = 4096 + 16384 + 16384;     // Q tile [2][128][8] + K [2][512][8] + V [2][512][8]
 constexpr int kCoreSmem = kBiasBytes + 2 * kStageBytes + 2 * 2 * 128 * 4;  // + row max / row sum exchange
 
@@ -156,24 +212,44 @@ __device__ __forceinline__ float fast_exp2(float x) {
     return y;
 }
 
-__device__ __forceinline__ void unpack8(const uint4 &u, float (&f)[8]) {
-    f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
-    f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
-    f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
-    f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
+// Dense bias image for the core kernel: img[h][qt][i][kBiasPitch] = fmt16(table[index[qt*128+i][j]][h] * log2 e).
+// Built once per table version; the core kernel then fetches its (head, query tile) slab with ONE bulk copy.
+template <bool F16>
+__global__ void relpos_bias_image_kernel(const void *__restrict__ table, int table_dtype,
+                                         const int64_t *__restrict__ index, uint16_t *__restrict__ img, int heads,
+                                         int table_rows) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over heads * 512 * kBiasPitch/2 (pairs)
+    const int64_t total = (int64_t)heads * 512 * (kBiasPitch / 2);
+    if (idx >= total) return;
+    const int jp = (int)(idx % (kBiasPitch / 2));
+    const int64_t r = idx / (kBiasPitch / 2);
+    const int i = (int)(r % 512), h = (int)(r / 512);
+    float v[2] = {0.f, 0.f};
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const int j = 2 * jp + e;
+        if (j < 512) {
+            int64_t row = index[(int64_t)i * 512 + j];
+            row = row < 0 ? 0 : (row >= table_rows ? table_rows - 1 : row);
+            v[e] = (table_dtype == WF_F32 ? reinterpret_cast<const float *>(table)[row * heads + h]
+                                          : __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(table)[row * heads + h])) * kLog2e;
+        }
+    }
+    reinterpret_cast<uint32_t *>(img)[idx] = pack16<F16>(v[0], v[1]);
 }
 
 // grid = combos * groups, combos = heads * 4 (head, 128-query tile); CTA (combo, g) walks windows g, g+groups, ...
 // 256 threads: warp w handles TMEM lanes 32*(w%4).. (query rows) and key half w/4.
-__global__ void __launch_bounds__(256, 1) attn_core_tc_kernel(const __nv_bfloat16 *__restrict__ qkv,
-                                                              const float *__restrict__ bias_t,
-                                                              __nv_bfloat16 *__restrict__ o, int heads, int64_t B_,
+template <bool F16>
+__global__ void __launch_bounds__(256, 1) attn_core_tc_kernel(const uint16_t *__restrict__ qkv,
+                                                              const uint16_t *__restrict__ bias_img,
+                                                              uint16_t *__restrict__ o, int heads, int64_t B_,
                                                               int groups) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_full[2];
-    __shared__ __align__(8) uint64_t bar_s, bar_o;
+    __shared__ __align__(8) uint64_t bar_s, bar_o, bar_bias;
     __shared__ uint32_t tmem_slot;
-    __nv_bfloat16 *sBias = reinterpret_cast<__nv_bfloat16 *>(smem);
+    uint16_t *sBias = reinterpret_cast<uint16_t *>(smem);
     uint8_t *sStage = smem + kBiasBytes;
     float *sMax = reinterpret_cast<float *>(smem + kBiasBytes + 2 * kStageBytes);  // [2][128]
     float *sSum = sMax + 256;                                                       // [2][128]
@@ -191,15 +267,8 @@ __global__ void __launch_bounds__(256, 1) attn_core_tc_kernel(const __nv_bfloat1
         mbar_init(&bar_full[1], 1);
         mbar_init(&bar_s, 1);
         mbar_init(&bar_o, 1);
+        mbar_init(&bar_bias, 1);
         mbar_fence_init();
-    }
-    // relative-position bias tile for (head, query tile), pre-multiplied by log2(e): sBias[i][j], i = query row
-    {
-        const float *src = bias_t + ((int64_t)hh * 512) * 512 + qt * 128;  // bias_t[h][j][i]
-        for (int idx = tid; idx < 512 * 128; idx += 256) {
-            const int i = idx & 127, j = idx >> 7;
-            sBias[i * kBiasPitch + j] = __float2bfloat16_rn(__ldg(src + (int64_t)j * 512 + i) * kLog2e);
-        }
     }
     tc_fence_before();
     __syncthreads();
@@ -210,7 +279,7 @@ __global__ void __launch_bounds__(256, 1) attn_core_tc_kernel(const __nv_bfloat1
     const int64_t per_which = B_ * heads * 8192;  // elements between the q, k and v planes
     auto issue_loads = [&](int64_t win, int stage) {
         uint8_t *dst = sStage + stage * kStageBytes;
-        const __nv_bfloat16 *qb = qkv + (win * heads + hh) * 8192;
+        const uint16_t *qb = qkv + (win * heads + hh) * 8192;
         mbar_expect_tx(&bar_full[stage], kStageBytes);
         bulk_g2s(dst, qb + qt * 128 * 8, 2048, &bar_full[stage]);                 // Q chunk 0 (head dims 0..7)
         bulk_g2s(dst + 2048, qb + 4096 + qt * 128 * 8, 2048, &bar_full[stage]);   // Q chunk 1
@@ -218,9 +287,14 @@ __global__ void __launch_bounds__(256, 1) attn_core_tc_kernel(const __nv_bfloat1
         bulk_g2s(dst + 4096 + 16384, qb + 2 * per_which, 16384, &bar_full[stage]);  // V
     };
 
-    if (tid == 0 && g < B_) issue_loads(g, 0);
-    const uint32_t idesc_s = instr_desc_bf16(128, 256, false);
-    const uint32_t idesc_o = instr_desc_bf16(128, 16, true);
+    if (tid == 0 && g < B_) {
+        // relative-position bias slab of this (head, query tile): one 130 KB bulk copy, resident for every window
+        mbar_expect_tx(&bar_bias, kBiasBytes);
+        bulk_g2s(sBias, bias_img + ((int64_t)hh * 4 + qt) * (kBiasBytes / 2), kBiasBytes, &bar_bias);
+        issue_loads(g, 0);
+    }
+    const uint32_t idesc_s = instr_desc16<F16>(128, 256, false);
+    const uint32_t idesc_o = instr_desc16<F16>(128, 16, true);
 
     int it = 0;
     for (int64_t win = g; win < B_; win += groups, ++it) {
@@ -237,12 +311,13 @@ __global__ void __launch_bounds__(256, 1) attn_core_tc_kernel(const __nv_bfloat1
             mma_ss(tmem + 256, dq, smem_desc(sK + 256 * 16, 8192, 128), idesc_s, 0u);
             mma_commit(&bar_s);
         }
+        if (it == 0) mbar_wait(&bar_bias, 0);
         mbar_wait(&bar_s, ph);
         tc_fence_after();
 
         const uint32_t scol = tmem + lane_base + half * 256;
-        const __nv_bfloat16 *brow = sBias + row * kBiasPitch + half * 256;
-        // ---- pass 1: row maximum of s + bias over this warp's 256 keys ----
+        const uint16_t *brow = sBias + row * kBiasPitch + half * 256;
+        // ---- pass 1: row maximum of s + bias over this warp's 256 keys (FHADD + FMNMX3: 1.5 ALU ops per key) ----
         float mx = -INFINITY;
 #pragma unroll 1
         for (int c = 0; c < 8; ++c) {
@@ -251,16 +326,20 @@ __global__ void __launch_bounds__(256, 1) attn_core_tc_kernel(const __nv_bfloat1
             tmem_wait_ld();
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
-                float b[8];
-                unpack8(*reinterpret_cast<const uint4 *>(brow + c * 32 + q4 * 8), b);
+                const uint4 b = *reinterpret_cast<const uint4 *>(brow + c * 32 + q4 * 8);
+                const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-                for (int e = 0; e < 8; ++e) mx = fmaxf(mx, __uint_as_float(r[q4 * 8 + e]) + b[e]);
+                for (int e = 0; e < 4; ++e) {
+                    float t0, t1;
+                    add16x2<F16>(bw[e], __uint_as_float(r[q4 * 8 + 2 * e]), __uint_as_float(r[q4 * 8 + 2 * e + 1]), t0, t1);
+                    mx = max3(mx, t0, t1);
+                }
             }
         }
         sMax[half * 128 + row] = mx;
         __syncthreads();
         mx = fmaxf(sMax[row], sMax[128 + row]);
-        // ---- pass 2: p = 2^(s + bias - max), row sum, P (bf16) written over S in place ----
+        // ---- pass 2: p = 2^(s + bias - max), row sum, P (16-bit) written over S in place ----
         float sum = 0.f;
 #pragma unroll 1
         for (int c = 0; c < 8; ++c) {
@@ -270,16 +349,16 @@ __global__ void __launch_bounds__(256, 1) attn_core_tc_kernel(const __nv_bfloat1
             uint32_t pk[16];
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
-                float b[8];
-                unpack8(*reinterpret_cast<const uint4 *>(brow + c * 32 + q4 * 8), b);
-                float p[8];
+                const uint4 b = *reinterpret_cast<const uint4 *>(brow + c * 32 + q4 * 8);
+                const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    p[e] = fast_exp2(__uint_as_float(r[q4 * 8 + e]) + b[e] - mx);
-                    sum += p[e];
+                for (int e = 0; e < 4; ++e) {
+                    float t0, t1;
+                    add16x2<F16>(bw[e], __uint_as_float(r[q4 * 8 + 2 * e]) - mx, __uint_as_float(r[q4 * 8 + 2 * e + 1]) - mx, t0, t1);
+                    const float p0 = fast_exp2(t0), p1 = fast_exp2(t1);
+                    sum += p0 + p1;
+                    pk[q4 * 4 + e] = pack16<F16>(p0, p1);
                 }
-#pragma unroll
-                for (int e = 0; e < 4; ++e) pk[q4 * 4 + e] = pack_bf16(p[2 * e], p[2 * e + 1]);
             }
             tmem_st16(scol + c * 16, pk);  // keys [32c, 32c+32) of this half -> 16 packed columns (already consumed S)
         }
@@ -305,14 +384,14 @@ __global__ void __launch_bounds__(256, 1) attn_core_tc_kernel(const __nv_bfloat1
             tmem_wait_ld();
             const float inv = 1.f / (sSum[row] + sSum[128 + row]);
             uint4 lo, hi;
-            lo.x = pack_bf16(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
-            lo.y = pack_bf16(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
-            lo.z = pack_bf16(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
-            lo.w = pack_bf16(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
-            hi.x = pack_bf16(__uint_as_float(r[8]) * inv, __uint_as_float(r[9]) * inv);
-            hi.y = pack_bf16(__uint_as_float(r[10]) * inv, __uint_as_float(r[11]) * inv);
-            hi.z = pack_bf16(__uint_as_float(r[12]) * inv, __uint_as_float(r[13]) * inv);
-            hi.w = pack_bf16(__uint_as_float(r[14]) * inv, __uint_as_float(r[15]) * inv);
+            lo.x = pack16<F16>(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
+            lo.y = pack16<F16>(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
+            lo.z = pack16<F16>(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
+            lo.w = pack16<F16>(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
+            hi.x = pack16<F16>(__uint_as_float(r[8]) * inv, __uint_as_float(r[9]) * inv);
+            hi.y = pack16<F16>(__uint_as_float(r[10]) * inv, __uint_as_float(r[11]) * inv);
+            hi.z = pack16<F16>(__uint_as_float(r[12]) * inv, __uint_as_float(r[13]) * inv);
+            hi.w = pack16<F16>(__uint_as_float(r[14]) * inv, __uint_as_float(r[15]) * inv);
             uint4 *dst = reinterpret_cast<uint4 *>(o + (win * 512 + qt * 128 + row) * (int64_t)C + hh * 16);
             dst[0] = lo;
             dst[1] = hi;
@@ -339,23 +418,39 @@ bool attn_tc_supported(int D1, int H1, int W1, int C, int heads, int ws) {
     return ws == 8 && C == heads * 16 && C % 16 == 0 && C <= 384 && D1 % 8 == 0 && H1 % 8 == 0 && W1 % 8 == 0;
 }
 
-int attn_tc_forward(const void *x, int x_is_f32, const __nv_bfloat16 *qkv_w, const __nv_bfloat16 *qkv_b,
-                    const __nv_bfloat16 *proj_w, const __nv_bfloat16 *proj_b, const float *bias_t,
-                    __nv_bfloat16 *out, void *workspace, int B, int D1, int H1, int W1, int C, int heads, float scale,
-                    cudaStream_t st) {
+size_t attn_tc_bias_image_bytes(int heads) { return (size_t)heads * 4 * kBiasBytes; }
+
+int attn_tc_bias_image(const void *table, int table_dtype, const int64_t *index, void *img, bool f16, int heads,
+                       int table_rows, cudaStream_t st) {
+    const int64_t total = (int64_t)heads * 512 * (kBiasPitch / 2);
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (f16)
+        relpos_bias_image_kernel<true><<<grid, 256, 0, st>>>(table, table_dtype, index, (uint16_t *)img, heads, table_rows);
+    else
+        relpos_bias_image_kernel<false><<<grid, 256, 0, st>>>(table, table_dtype, index, (uint16_t *)img, heads, table_rows);
+    WF_LAUNCH_CHECK();
+    return WF_OK;
+}
+
+template <bool F16>
+static int attn_tc_run(const void *x, int x_dtype, const uint16_t *qkv_w, const uint16_t *qkv_b, const uint16_t *proj_w,
+                       const uint16_t *proj_b, const uint16_t *bias_img, void *out, bool out_f32, void *workspace, int B,
+                       int D1, int H1, int W1, int C, int heads, float scale, cudaStream_t st) {
     TcWindowMap map;
     map.D1 = D1; map.H1 = H1; map.W1 = W1;
     map.nWy = H1 / 8; map.nWx = W1 / 8; map.nW = (D1 / 8) * map.nWy * map.nWx;
     const int64_t B_ = (int64_t)B * map.nW;
     const int64_t M = B_ * 512;
-    __nv_bfloat16 *qkv = reinterpret_cast<__nv_bfloat16 *>(workspace);  // [3][B_][heads][2][512][8]
-    __nv_bfloat16 *obuf = qkv + 3 * M * C;                              // [M][C]
+    uint16_t *qkv = reinterpret_cast<uint16_t *>(workspace);  // [3][B_][heads][2][512][8]
+    uint16_t *obuf = qkv + 3 * M * C;                         // [M][C]
     static bool attrs_done = false;
     if (!attrs_done) {
-        WF_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel<true, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        WF_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel<true, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        WF_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel<false, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        WF_CUDA_CHECK(cudaFuncSetAttribute(attn_core_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCoreSmem));
+        const int big = 200 * 1024;
+        WF_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel<true, float, F16, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel<true, __nv_bfloat16, F16, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel<false, uint16_t, F16, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel<false, uint16_t, F16, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(attn_core_tc_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCoreSmem));
         attrs_done = true;
     }
     const int kchunks = C / 8;
@@ -364,10 +459,10 @@ int attn_tc_forward(const void *x, int x_is_f32, const __nv_bfloat16 *qkv_w, con
         if (!nt) return WF_ERR_BAD_SHAPE;
         const size_t smem = (size_t)kchunks * 2048 + (size_t)kchunks * nt * 16;
         dim3 grid((unsigned)(M / 128), (unsigned)(3 * C / nt));
-        if (x_is_f32)
-            linear_tc_kernel<true, float><<<grid, 128, smem, st>>>((const float *)x, qkv_w, qkv_b, qkv, C, nt, 3 * C, map, heads, B_, scale * kLog2e, pow2_cols(nt));
+        if (x_dtype == WF_F32)
+            linear_tc_kernel<true, float, F16, uint16_t><<<grid, 128, smem, st>>>((const float *)x, qkv_w, qkv_b, qkv, C, nt, 3 * C, map, heads, B_, scale * kLog2e, pow2_cols(nt));
         else
-            linear_tc_kernel<true, __nv_bfloat16><<<grid, 128, smem, st>>>((const __nv_bfloat16 *)x, qkv_w, qkv_b, qkv, C, nt, 3 * C, map, heads, B_, scale * kLog2e, pow2_cols(nt));
+            linear_tc_kernel<true, __nv_bfloat16, F16, uint16_t><<<grid, 128, smem, st>>>((const __nv_bfloat16 *)x, qkv_w, qkv_b, qkv, C, nt, 3 * C, map, heads, B_, scale * kLog2e, pow2_cols(nt));
         WF_LAUNCH_CHECK();
     }
     {
@@ -375,7 +470,7 @@ int attn_tc_forward(const void *x, int x_is_f32, const __nv_bfloat16 *qkv_w, con
         int groups = kNumSMs / combos;
         if (groups < 1) groups = 1;
         if (groups > B_) groups = (int)B_;
-        attn_core_tc_kernel<<<combos * groups, 256, kCoreSmem, st>>>(qkv, bias_t, obuf, heads, B_, groups);
+        attn_core_tc_kernel<F16><<<combos * groups, 256, kCoreSmem, st>>>(qkv, bias_img, obuf, heads, B_, groups);
         WF_LAUNCH_CHECK();
     }
     {
@@ -383,10 +478,24 @@ int attn_tc_forward(const void *x, int x_is_f32, const __nv_bfloat16 *qkv_w, con
         if (!nt) return WF_ERR_BAD_SHAPE;
         const size_t smem = (size_t)kchunks * 2048 + (size_t)kchunks * nt * 16;
         dim3 grid((unsigned)(M / 128), (unsigned)(C / nt));
-        linear_tc_kernel<false, __nv_bfloat16><<<grid, 128, smem, st>>>(obuf, proj_w, proj_b, out, C, nt, C, map, heads, B_, 1.f, pow2_cols(nt));
+        if (out_f32)
+            linear_tc_kernel<false, uint16_t, F16, float><<<grid, 128, smem, st>>>(obuf, proj_w, proj_b, (float *)out, C, nt, C, map, heads, B_, 1.f, pow2_cols(nt));
+        else
+            linear_tc_kernel<false, uint16_t, F16, uint16_t><<<grid, 128, smem, st>>>(obuf, proj_w, proj_b, (uint16_t *)out, C, nt, C, map, heads, B_, 1.f, pow2_cols(nt));
         WF_LAUNCH_CHECK();
     }
     return WF_OK;
+}
+
+int attn_tc_forward(const void *x, int x_dtype, const void *qkv_w, const void *qkv_b, const void *proj_w,
+                    const void *proj_b, const void *bias_img, void *out, bool out_f32, void *workspace, bool f16, int B,
+                    int D1, int H1, int W1, int C, int heads, float scale, cudaStream_t st) {
+    using u16 = uint16_t;
+    if (f16)
+        return attn_tc_run<true>(x, x_dtype, (const u16 *)qkv_w, (const u16 *)qkv_b, (const u16 *)proj_w, (const u16 *)proj_b,
+                                 (const u16 *)bias_img, out, out_f32, workspace, B, D1, H1, W1, C, heads, scale, st);
+    return attn_tc_run<false>(x, x_dtype, (const u16 *)qkv_w, (const u16 *)qkv_b, (const u16 *)proj_w, (const u16 *)proj_b,
+                              (const u16 *)bias_img, out, out_f32, workspace, B, D1, H1, W1, C, heads, scale, st);
 }
 
 }  // namespace wf

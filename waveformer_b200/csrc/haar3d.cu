@@ -86,13 +86,69 @@ __global__ void __launch_bounds__(256) dwt_ncdhw_vec_kernel(const T *__restrict_
     }
 }
 
-template <typename T>
+// Raw global words: BYTES = 8, 16 or 32 per thread and access, streaming (evict-first) both ways.
+template <int BYTES> struct Words { uint32_t w[BYTES / 4]; };
+template <int BYTES> __device__ inline Words<BYTES> ld_words(const void *p) {
+    Words<BYTES> r;
+    if constexpr (BYTES == 8) {
+        const uint2 t = ld_stream<uint2>(p);
+        r.w[0] = t.x; r.w[1] = t.y;
+    } else {
+#pragma unroll
+        for (int i = 0; i < BYTES / 16; ++i) {
+            const uint4 t = ld_stream<uint4>(reinterpret_cast<const uint4 *>(p) + i);
+            r.w[4 * i] = t.x; r.w[4 * i + 1] = t.y; r.w[4 * i + 2] = t.z; r.w[4 * i + 3] = t.w;
+        }
+    }
+    return r;
+}
+template <int BYTES> __device__ inline void st_words(void *p, const Words<BYTES> &r) {
+    if constexpr (BYTES == 8) {
+        st_stream(p, make_uint2(r.w[0], r.w[1]));
+    } else {
+#pragma unroll
+        for (int i = 0; i < BYTES / 16; ++i)
+            st_stream(reinterpret_cast<uint4 *>(p) + i, make_uint4(r.w[4 * i], r.w[4 * i + 1], r.w[4 * i + 2], r.w[4 * i + 3]));
+    }
+}
+template <typename T, int N> __device__ inline void words_to_f32(const Words<N * (int)sizeof(T)> &r, float (&v)[N]) {
+    if constexpr (sizeof(T) == 4) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = __uint_as_float(r.w[i]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) {
+            v[2 * i] = __uint_as_float(r.w[i] << 16);
+            v[2 * i + 1] = __uint_as_float(r.w[i] & 0xffff0000u);
+        }
+    }
+}
+template <typename T, int N> __device__ inline Words<N * (int)sizeof(T)> f32_to_words(const float (&v)[N]) {
+    Words<N * (int)sizeof(T)> r;
+    if constexpr (sizeof(T) == 4) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) r.w[i] = __float_as_uint(v[i]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            r.w[i] = *reinterpret_cast<uint32_t *>(&h);
+        }
+    }
+    return r;
+}
+
+// One thread = CO consecutive coefficients of every sub-band -> 4 output rows x 2*CO samples.  The eight (fifteen with
+// a gate) sub-band loads are issued back to back before the first use, so each thread keeps 8 x CO x sizeof(T) bytes
+// (128 B at CO = 16 / sizeof(T)) in flight; HF / GATE are compile-time so nothing blocks the hoisting.
+template <typename T, int CO, bool HF, bool GATE>
 __global__ void __launch_bounds__(256) idwt_ncdhw_vec_kernel(const T *__restrict__ ll, const T *__restrict__ hf,
                                                              const T *__restrict__ gate, T *__restrict__ x,
                                                              int64_t total, int d, int h, int w, int64_t band_stride) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
-    const int wq = w >> 2;
+    constexpr int NB = CO * (int)sizeof(T);
+    const int wq = w / CO;
     const int xq = (int)(idx % wq);
     const int64_t row = idx / wq;
     const int y = (int)(row % h);
@@ -100,27 +156,37 @@ __global__ void __launch_bounds__(256) idwt_ncdhw_vec_kernel(const T *__restrict
     const int z = (int)(t % d);
     const int64_t b = t / d;
     const int H = 2 * h, W = 2 * w;
-    const int64_t off = row * w + 4 * xq;
-    float cin[8][4];
-    Quad<T>::unpack(ld_stream<typename Quad<T>::raw>(ll + off), cin[0]);
+    const int64_t off = row * w + CO * xq;
+    Words<NB> raw[8], graw[7];
+    raw[0] = ld_words<NB>(ll + off);
+    if constexpr (HF) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) raw[k + 1] = ld_words<NB>(hf + k * band_stride + off);
+        if constexpr (GATE) {
+#pragma unroll
+            for (int k = 0; k < 7; ++k) graw[k] = ld_words<NB>(gate + k * band_stride + off);
+        }
+    }
+    float cin[8][CO];
+    words_to_f32<T, CO>(raw[0], cin[0]);
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
-        if (hf != nullptr) {
-            Quad<T>::unpack(ld_stream<typename Quad<T>::raw>(hf + k * band_stride + off), cin[k + 1]);
-            if (gate != nullptr) {
-                float g[4];
-                Quad<T>::unpack(ld_stream<typename Quad<T>::raw>(gate + k * band_stride + off), g);
+        if constexpr (HF) {
+            words_to_f32<T, CO>(raw[k + 1], cin[k + 1]);
+            if constexpr (GATE) {
+                float g[CO];
+                words_to_f32<T, CO>(graw[k], g);
 #pragma unroll
-                for (int o = 0; o < 4; ++o) cin[k + 1][o] *= g[o];
+                for (int o = 0; o < CO; ++o) cin[k + 1][o] *= g[o];
             }
         } else {
 #pragma unroll
-            for (int o = 0; o < 4; ++o) cin[k + 1][o] = 0.f;
+            for (int o = 0; o < CO; ++o) cin[k + 1][o] = 0.f;
         }
     }
-    float f[4][8];
+    float f[4][2 * CO];
 #pragma unroll
-    for (int o = 0; o < 4; ++o) {
+    for (int o = 0; o < CO; ++o) {
         const float c[8] = {cin[0][o], cin[1][o], cin[2][o], cin[3][o], cin[4][o], cin[5][o], cin[6][o], cin[7][o]};
         float v[8];
         haar8(c, v);
@@ -130,11 +196,11 @@ __global__ void __launch_bounds__(256) idwt_ncdhw_vec_kernel(const T *__restrict
             f[r][2 * o + 1] = v[2 * r + 1];
         }
     }
-    T *r00 = x + (((b * (2 * d) + 2 * z) * H + 2 * y) * (int64_t)W + 8 * xq);
-    store8(r00, f[0]);
-    store8(r00 + W, f[1]);
-    store8(r00 + (int64_t)H * W, f[2]);
-    store8(r00 + (int64_t)H * W + W, f[3]);
+    T *r00 = x + (((b * (2 * d) + 2 * z) * H + 2 * y) * (int64_t)W + 2 * CO * xq);
+    st_words<2 * NB>(r00, f32_to_words<T, 2 * CO>(f[0]));
+    st_words<2 * NB>(r00 + W, f32_to_words<T, 2 * CO>(f[1]));
+    st_words<2 * NB>(r00 + (int64_t)H * W, f32_to_words<T, 2 * CO>(f[2]));
+    st_words<2 * NB>(r00 + (int64_t)H * W + W, f32_to_words<T, 2 * CO>(f[3]));
 }
 
 // scalar fallbacks: one thread per 2x2x2 cell
@@ -207,8 +273,10 @@ template <typename T, int VEC> struct ChanIO {
     }
 };
 
-template <typename T, int VEC>
-__global__ void __launch_bounds__(256) dwt_ndhwc_kernel(const T *__restrict__ x, T *__restrict__ ll, T *__restrict__ hf,
+// THF: storage type of the seven detail bands (may be bf16 while x / LL stay fp32: the encoder's residual-stream
+// precision for the attention input, the decoder's activation type for the details).
+template <typename T, typename THF, int VEC>
+__global__ void __launch_bounds__(256) dwt_ndhwc_kernel(const T *__restrict__ x, T *__restrict__ ll, THF *__restrict__ hf,
                                                         int64_t total, int d, int h, int w, int cchunks,
                                                         int64_t xs, int64_t lls, int64_t band_stride, int C) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -240,13 +308,21 @@ __global__ void __launch_bounds__(256) dwt_ndhwc_kernel(const T *__restrict__ x,
     }
     ChanIO<T, VEC>::store(ll + vox * lls + cc * VEC, o[0]);
     if (hf != nullptr) {
-        T *q = hf + vox * C + cc * VEC;
+        THF *q = hf + vox * C + cc * VEC;
 #pragma unroll
-        for (int k = 0; k < 7; ++k) ChanIO<T, VEC>::store(q + k * band_stride, o[k + 1]);
+        for (int k = 0; k < 7; ++k) {
+            if constexpr (VEC == 1 || sizeof(THF) == sizeof(T)) {
+                ChanIO<THF, VEC>::store(q + k * band_stride, o[k + 1]);
+            } else {  // fp32 packet of 4 channels -> 4 bf16 (8 bytes)
+                static_assert(VEC == 4, "mixed storage: fp32 in, bf16 details");
+                __nv_bfloat162 a = __floats2bfloat162_rn(o[k + 1][0], o[k + 1][1]), b = __floats2bfloat162_rn(o[k + 1][2], o[k + 1][3]);
+                st_stream(q + k * band_stride, make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b)));
+            }
+        }
     }
 }
 
-template <typename T, int VEC>
+template <typename T, int VEC, bool HF, bool GATE>
 __global__ void __launch_bounds__(256) idwt_ndhwc_kernel(const T *__restrict__ ll, const T *__restrict__ hf,
                                                          const T *__restrict__ gate, T *__restrict__ x, int64_t total,
                                                          int d, int h, int w, int cchunks, int64_t lls,
@@ -262,22 +338,27 @@ __global__ void __launch_bounds__(256) idwt_ndhwc_kernel(const T *__restrict__ l
     const int z = (int)(t % d);
     const int64_t b = t / d;
     const int H = 2 * h, W = 2 * w;
-    float cin[8][VEC];
+    // every load first (compile-time HF / GATE: no branch between them), then the butterflies
+    float cin[8][VEC], g[7][VEC];
     ChanIO<T, VEC>::load(ll + vox * lls + cc * VEC, cin[0]);
+    if constexpr (HF) {
+        const T *q = hf + vox * C + cc * VEC;
 #pragma unroll
-    for (int k = 0; k < 7; ++k) {
-        if (hf != nullptr) {
-            ChanIO<T, VEC>::load(hf + k * band_stride + vox * C + cc * VEC, cin[k + 1]);
-            if (gate != nullptr) {
-                float g[VEC];
-                ChanIO<T, VEC>::load(gate + k * band_stride + vox * C + cc * VEC, g);
+        for (int k = 0; k < 7; ++k) ChanIO<T, VEC>::load(q + k * band_stride, cin[k + 1]);
+        if constexpr (GATE) {
+            const T *gq = gate + vox * C + cc * VEC;
 #pragma unroll
-                for (int ch = 0; ch < VEC; ++ch) cin[k + 1][ch] *= g[ch];
-            }
-        } else {
+            for (int k = 0; k < 7; ++k) ChanIO<T, VEC>::load(gq + k * band_stride, g[k]);
+#pragma unroll
+            for (int k = 0; k < 7; ++k)
+#pragma unroll
+                for (int ch = 0; ch < VEC; ++ch) cin[k + 1][ch] *= g[k][ch];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 7; ++k)
 #pragma unroll
             for (int ch = 0; ch < VEC; ++ch) cin[k + 1][ch] = 0.f;
-        }
     }
     float o[8][VEC];
 #pragma unroll
@@ -317,11 +398,19 @@ static int dwt_ncdhw_launch(const T *x, T *ll, T *hf, int64_t n, int D, int H, i
 template <typename T>
 static int idwt_ncdhw_launch(const T *ll, const T *hf, const T *gate, T *x, int64_t n, int d, int h, int w, int64_t bs,
                              cudaStream_t st) {
-    const bool vec = (w % 4 == 0) && aligned16(x) && aligned16(ll) &&
+    constexpr int CO = 16 / (int)sizeof(T);  // 16-byte sub-band loads: 4 fp32 / 8 bf16 coefficients per thread
+    const bool vec = (w % CO == 0) && aligned16(x) && aligned16(ll) &&
                      (hf == nullptr || (aligned16(hf) && (bs * sizeof(T)) % 16 == 0)) && (gate == nullptr || aligned16(gate));
+    if (gate != nullptr && hf == nullptr) return WF_ERR_NULL_POINTER;
     if (vec) {
-        const int64_t total = n * d * h * (w / 4);
-        idwt_ncdhw_vec_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(ll, hf, gate, x, total, d, h, w, bs);
+        const int64_t total = n * d * h * (w / CO);
+        const int grid = grid_for(total, 256);
+        if (hf == nullptr)
+            idwt_ncdhw_vec_kernel<T, CO, false, false><<<grid, 256, 0, st>>>(ll, hf, gate, x, total, d, h, w, bs);
+        else if (gate == nullptr)
+            idwt_ncdhw_vec_kernel<T, CO, true, false><<<grid, 256, 0, st>>>(ll, hf, gate, x, total, d, h, w, bs);
+        else
+            idwt_ncdhw_vec_kernel<T, CO, true, true><<<grid, 256, 0, st>>>(ll, hf, gate, x, total, d, h, w, bs);
     } else {
         const int64_t total = n * d * h * w;
         idwt_ncdhw_scalar_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(ll, hf, gate, x, total, d, h, w, bs);
@@ -330,24 +419,36 @@ static int idwt_ncdhw_launch(const T *ll, const T *hf, const T *gate, T *x, int6
     return WF_OK;
 }
 
-template <typename T>
-static int dwt_ndhwc_launch(const T *x, T *ll, T *hf, int B, int D, int H, int W, int C, int64_t xs, int64_t lls,
+template <typename T, typename THF>
+static int dwt_ndhwc_launch(const T *x, T *ll, THF *hf, int B, int D, int H, int W, int C, int64_t xs, int64_t lls,
                             int64_t bs, cudaStream_t st) {
     const int d = D / 2, h = H / 2, w = W / 2;
     constexpr int V = Pack<T>::VEC;
     const size_t e = sizeof(T);
     const bool vec = (C % V == 0) && aligned16(x) && aligned16(ll) && (xs * e) % 16 == 0 && (lls * e) % 16 == 0 &&
-                     (hf == nullptr || (aligned16(hf) && (bs * e) % 16 == 0));
+                     (hf == nullptr || (aligned16(hf) && (bs * sizeof(THF)) % 16 == 0 && (C * sizeof(THF)) % 8 == 0));
     const int64_t vox = (int64_t)B * d * h * w;
     if (vec) {
         const int64_t total = vox * (C / V);
-        dwt_ndhwc_kernel<T, V><<<grid_for(total, 256), 256, 0, st>>>(x, ll, hf, total, d, h, w, C / V, xs, lls, bs, C);
+        dwt_ndhwc_kernel<T, THF, V><<<grid_for(total, 256), 256, 0, st>>>(x, ll, hf, total, d, h, w, C / V, xs, lls, bs, C);
     } else {
         const int64_t total = vox * C;
-        dwt_ndhwc_kernel<T, 1><<<grid_for(total, 256), 256, 0, st>>>(x, ll, hf, total, d, h, w, C, xs, lls, bs, C);
+        dwt_ndhwc_kernel<T, THF, 1><<<grid_for(total, 256), 256, 0, st>>>(x, ll, hf, total, d, h, w, C, xs, lls, bs, C);
     }
     WF_LAUNCH_CHECK();
     return WF_OK;
+}
+
+template <typename T, int V>
+static void idwt_ndhwc_dispatch(const T *ll, const T *hf, const T *gate, T *x, int64_t total, int d, int h, int w,
+                                int cchunks, int64_t lls, int64_t bs, int64_t xs, int C, cudaStream_t st) {
+    const int grid = grid_for(total, 256);
+    if (hf == nullptr)
+        idwt_ndhwc_kernel<T, V, false, false><<<grid, 256, 0, st>>>(ll, hf, gate, x, total, d, h, w, cchunks, lls, bs, xs, C);
+    else if (gate == nullptr)
+        idwt_ndhwc_kernel<T, V, true, false><<<grid, 256, 0, st>>>(ll, hf, gate, x, total, d, h, w, cchunks, lls, bs, xs, C);
+    else
+        idwt_ndhwc_kernel<T, V, true, true><<<grid, 256, 0, st>>>(ll, hf, gate, x, total, d, h, w, cchunks, lls, bs, xs, C);
 }
 
 template <typename T>
@@ -355,16 +456,14 @@ static int idwt_ndhwc_launch(const T *ll, const T *hf, const T *gate, T *x, int 
                              int64_t lls, int64_t bs, int64_t xs, cudaStream_t st) {
     constexpr int V = Pack<T>::VEC;
     const size_t e = sizeof(T);
+    if (gate != nullptr && hf == nullptr) return WF_ERR_NULL_POINTER;
     const bool vec = (C % V == 0) && aligned16(x) && aligned16(ll) && (xs * e) % 16 == 0 && (lls * e) % 16 == 0 &&
                      (hf == nullptr || (aligned16(hf) && (bs * e) % 16 == 0)) && (gate == nullptr || aligned16(gate));
     const int64_t vox = (int64_t)B * d * h * w;
-    if (vec) {
-        const int64_t total = vox * (C / V);
-        idwt_ndhwc_kernel<T, V><<<grid_for(total, 256), 256, 0, st>>>(ll, hf, gate, x, total, d, h, w, C / V, lls, bs, xs, C);
-    } else {
-        const int64_t total = vox * C;
-        idwt_ndhwc_kernel<T, 1><<<grid_for(total, 256), 256, 0, st>>>(ll, hf, gate, x, total, d, h, w, C, lls, bs, xs, C);
-    }
+    if (vec)
+        idwt_ndhwc_dispatch<T, V>(ll, hf, gate, x, vox * (C / V), d, h, w, C / V, lls, bs, xs, C, st);
+    else
+        idwt_ndhwc_dispatch<T, 1>(ll, hf, gate, x, vox * C, d, h, w, C, lls, bs, xs, C, st);
     WF_LAUNCH_CHECK();
     return WF_OK;
 }
@@ -397,17 +496,19 @@ extern "C" int wf_idwt3d_ncdhw(const void *ll, const void *hf, const void *gate,
     return WF_ERR_BAD_DTYPE;
 }
 
-extern "C" int wf_dwt3d_ndhwc(const void *x, void *ll, void *hf, int dtype, int B, int D, int H, int W, int C,
-                              int64_t x_vox_stride, int64_t ll_vox_stride, int64_t hf_band_stride, void *stream) {
+extern "C" int wf_dwt3d_ndhwc(const void *x, void *ll, void *hf, int dtype, int hf_dtype, int B, int D, int H, int W,
+                              int C, int64_t x_vox_stride, int64_t ll_vox_stride, int64_t hf_band_stride, void *stream) {
     if (!x || !ll) return WF_ERR_NULL_POINTER;
     if (B <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0 || (D | H | W) & 1) return WF_ERR_BAD_SHAPE;
     if (x_vox_stride < C || ll_vox_stride < C) return WF_ERR_BAD_SHAPE;
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == WF_F32)
-        return dwt_ndhwc_launch<float>((const float *)x, (float *)ll, (float *)hf, B, D, H, W, C, x_vox_stride, ll_vox_stride, hf_band_stride, st);
-    if (dtype == WF_BF16)
-        return dwt_ndhwc_launch<__nv_bfloat16>((const __nv_bfloat16 *)x, (__nv_bfloat16 *)ll, (__nv_bfloat16 *)hf, B, D, H, W, C,
-                                               x_vox_stride, ll_vox_stride, hf_band_stride, st);
+    using bf = __nv_bfloat16;
+    if (dtype == WF_F32 && hf_dtype == WF_F32)
+        return dwt_ndhwc_launch<float, float>((const float *)x, (float *)ll, (float *)hf, B, D, H, W, C, x_vox_stride, ll_vox_stride, hf_band_stride, st);
+    if (dtype == WF_F32 && hf_dtype == WF_BF16)
+        return dwt_ndhwc_launch<float, bf>((const float *)x, (float *)ll, (bf *)hf, B, D, H, W, C, x_vox_stride, ll_vox_stride, hf_band_stride, st);
+    if (dtype == WF_BF16 && hf_dtype == WF_BF16)
+        return dwt_ndhwc_launch<bf, bf>((const bf *)x, (bf *)ll, (bf *)hf, B, D, H, W, C, x_vox_stride, ll_vox_stride, hf_band_stride, st);
     return WF_ERR_BAD_DTYPE;
 }
 

@@ -33,11 +33,12 @@ template <> struct Row16<__nv_bfloat16> {
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 
 // Each thread owns NV groups of 4 consecutive channels: channel index = (j * TPR + sub) * 4 + e.
+// y2 (optional) receives the same values as bf16 - the GEMM operand - while y keeps the fp32 copy the residual needs.
 template <typename TI, typename TO, int TPR, int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const TI *__restrict__ x, const float *__restrict__ gamma,
                                                         const float *__restrict__ beta, TO *__restrict__ y,
-                                                        int64_t rows, int C, int64_t xs, int64_t ys, float eps,
-                                                        int gelu) {
+                                                        __nv_bfloat16 *__restrict__ y2, int64_t rows, int C, int64_t xs,
+                                                        int64_t ys, float eps, int gelu) {
     constexpr int RPB = 256 / TPR;  // rows per block
     const int sub = threadIdx.x % TPR;
     const int64_t row = (int64_t)blockIdx.x * RPB + threadIdx.x / TPR;
@@ -100,12 +101,17 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const TI *__restrict__ x
             __nv_bfloat162 a = __floats2bfloat162_rn(o4[0], o4[1]), b = __floats2bfloat162_rn(o4[2], o4[3]);
             *reinterpret_cast<uint2 *>(q) = make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b));
         }
+        if (y2 != nullptr) {
+            __nv_bfloat162 a = __floats2bfloat162_rn(o4[0], o4[1]), b = __floats2bfloat162_rn(o4[2], o4[3]);
+            *reinterpret_cast<uint2 *>(y2 + row * (int64_t)C + g * 4) =
+                make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b));
+        }
     }
 }
 
 template <typename TI, typename TO>
-static int layernorm_launch(const TI *x, const float *gamma, const float *beta, TO *y, int64_t rows, int C, int64_t xs,
-                            int64_t ys, float eps, int gelu, cudaStream_t st) {
+static int layernorm_launch(const TI *x, const float *gamma, const float *beta, TO *y, __nv_bfloat16 *y2, int64_t rows,
+                            int C, int64_t xs, int64_t ys, float eps, int gelu, cudaStream_t st) {
     if (C % 4 != 0 || C > 2048) return WF_ERR_UNSUPPORTED;
     if ((xs * sizeof(TI)) % (sizeof(TI) == 4 ? 16 : 8) != 0 || (ys * sizeof(TO)) % (sizeof(TO) == 4 ? 16 : 8) != 0)
         return WF_ERR_MISALIGNED;
@@ -113,8 +119,8 @@ static int layernorm_launch(const TI *x, const float *gamma, const float *beta, 
 #define WF_LN(TPR_, NV_)                                                                                         \
     do {                                                                                                         \
         const int rpb = 256 / TPR_;                                                                              \
-        layernorm_kernel<TI, TO, TPR_, NV_><<<(unsigned)((rows + rpb - 1) / rpb), 256, 0, st>>>(x, gamma, beta, y, rows, \
-                                                                                                C, xs, ys, eps, gelu); \
+        layernorm_kernel<TI, TO, TPR_, NV_><<<(unsigned)((rows + rpb - 1) / rpb), 256, 0, st>>>(x, gamma, beta, y, y2, \
+                                                                                                rows, C, xs, ys, eps, gelu); \
     } while (0)
     if (groups <= 8) WF_LN(8, 1);
     else if (groups <= 16) WF_LN(16, 1);
@@ -130,20 +136,20 @@ static int layernorm_launch(const TI *x, const float *gamma, const float *beta, 
 
 }  // namespace wf
 
-extern "C" int wf_layernorm_ndhwc(const void *x, const float *gamma, const float *beta, void *y, int in_dtype,
-                                  int out_dtype, int64_t rows, int C, int64_t x_row_stride, int64_t y_row_stride,
-                                  float eps, int gelu, void *stream) {
+extern "C" int wf_layernorm_ndhwc(const void *x, const float *gamma, const float *beta, void *y, void *y2_bf16,
+                                  int in_dtype, int out_dtype, int64_t rows, int C, int64_t x_row_stride,
+                                  int64_t y_row_stride, float eps, int gelu, void *stream) {
     if (!x || !y) return WF_ERR_NULL_POINTER;
     if (rows <= 0 || C <= 0 || x_row_stride < C || y_row_stride < C) return WF_ERR_BAD_SHAPE;
     cudaStream_t st = (cudaStream_t)stream;
     using bf = __nv_bfloat16;
     if (in_dtype == WF_F32 && out_dtype == WF_F32)
-        return wf::layernorm_launch<float, float>((const float *)x, gamma, beta, (float *)y, rows, C, x_row_stride, y_row_stride, eps, gelu, st);
+        return wf::layernorm_launch<float, float>((const float *)x, gamma, beta, (float *)y, (bf *)y2_bf16, rows, C, x_row_stride, y_row_stride, eps, gelu, st);
     if (in_dtype == WF_F32 && out_dtype == WF_BF16)
-        return wf::layernorm_launch<float, bf>((const float *)x, gamma, beta, (bf *)y, rows, C, x_row_stride, y_row_stride, eps, gelu, st);
+        return wf::layernorm_launch<float, bf>((const float *)x, gamma, beta, (bf *)y, (bf *)y2_bf16, rows, C, x_row_stride, y_row_stride, eps, gelu, st);
     if (in_dtype == WF_BF16 && out_dtype == WF_BF16)
-        return wf::layernorm_launch<bf, bf>((const bf *)x, gamma, beta, (bf *)y, rows, C, x_row_stride, y_row_stride, eps, gelu, st);
+        return wf::layernorm_launch<bf, bf>((const bf *)x, gamma, beta, (bf *)y, (bf *)y2_bf16, rows, C, x_row_stride, y_row_stride, eps, gelu, st);
     if (in_dtype == WF_BF16 && out_dtype == WF_F32)
-        return wf::layernorm_launch<bf, float>((const bf *)x, gamma, beta, (float *)y, rows, C, x_row_stride, y_row_stride, eps, gelu, st);
+        return wf::layernorm_launch<bf, float>((const bf *)x, gamma, beta, (float *)y, (bf *)y2_bf16, rows, C, x_row_stride, y_row_stride, eps, gelu, st);
     return WF_ERR_BAD_DTYPE;
 }

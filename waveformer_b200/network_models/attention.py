@@ -2,6 +2,8 @@
 (``network_models/attention.py:15-104``), computed by the hand-written CUDA kernels behind ``wf_window_attn_fwd``."""
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -36,25 +38,53 @@ class Attention(nn.Module):
         self.register_buffer("relative_position_index", build_relative_position_index(window_size))
         nn.init.trunc_normal_(self.relative_position_bias_table, std=.02)
         self.softmax = nn.Softmax(dim=-1)
-        self._bias_cache = None  # (key, dense transposed bias)
+        self._bias_cache = None   # (key, dense transposed fp32 bias)
+        self._image_cache = None  # (key, 16-bit bias image)
+
+    def _table_key(self):
+        t = self.relative_position_bias_table
+        return (t._version, t.data_ptr(), t.device, t.dtype)
 
     def _dense_bias(self) -> torch.Tensor:
-        t = self.relative_position_bias_table
-        key = (t._version, t.data_ptr(), t.device, t.dtype)
+        """fp32 transposed dense bias for the CUDA-core kernels, rebuilt when the table changes."""
+        key = self._table_key()
         if self.training or self._bias_cache is None or self._bias_cache[0] != key:
-            self._bias_cache = (key, ops.relpos_bias_expand(t.detach(), self.relative_position_index))
+            self._bias_cache = (key, ops.relpos_bias_expand(self.relative_position_bias_table.detach(),
+                                                            self.relative_position_index))
         return self._bias_cache[1]
+
+    def _bias_image(self, fmt: torch.dtype) -> torch.Tensor:
+        """16-bit dense bias image for the tensor-core kernels, rebuilt when the table changes."""
+        key = self._table_key() + (fmt,)
+        if self.training or self._image_cache is None or self._image_cache[0] != key:
+            self._image_cache = (key, ops.relpos_bias_image(self.relative_position_bias_table.detach(),
+                                                            self.relative_position_index, fmt))
+        return self._image_cache[1]
 
     def forward_grid(self, x: torch.Tensor) -> torch.Tensor:
         """x [B, D1, H1, W1, C] channels-last LL grid -> window-major result viewed as [B, D1, H1, W1, C]
         (window partition and the reference's reshape-only reverse are part of the kernel's addressing)."""
         if self.training and (self.attn_drop.p > 0 or self.proj_drop.p > 0):
             raise NotImplementedError("attention dropout is not part of the fused kernel (the path uses p = 0)")
-        # compute_dtype (set by waveformer_b200.prepare_inference) = dtype of the GEMM operands; x may be an fp32 stream
+        # compute_dtype / out_dtype are set by waveformer_b200.prepare_inference: the GEMM operand format (bf16 or fp16
+        # on the tensor cores, fp32 on CUDA cores) and the result type; x may be an fp32 residual stream either way
         cd = getattr(self, "compute_dtype", None) or x.dtype
-        return ops.window_attention(x, self.qkv.weight, self.qkv.bias, self.proj.weight, self.proj.bias,
-                                    self.relative_position_bias_table, self.relative_position_index,
-                                    self._dense_bias(), self.num_heads, self.window_size, self.scale, cd)
+        od = getattr(self, "out_dtype", None)
+        tc = ops.window_attention_uses_tensor_cores(x.shape[1:4], self.dim, self.num_heads, self.window_size, cd)
+        if os.environ.get("WF_ATTN_IMPL", "").startswith("s") or self.qkv.bias is None:
+            tc = False   # tests force the CUDA-core kernels to cross-check the two device implementations
+        if cd == torch.float16 and not tc:
+            cd = torch.bfloat16 if x.dtype == torch.bfloat16 else torch.float32   # fp16 exists as a tensor-core format only
+            od = None
+        if not tc and od is not None and od != cd:
+            od = None
+        img = self._bias_image(cd) if tc else None
+        dense = None if tc else self._dense_bias()
+        y = ops.window_attention(x, self.qkv.weight, self.qkv.bias, self.proj.weight, self.proj.bias,
+                                 self.relative_position_bias_table, self.relative_position_index, dense,
+                                 self.num_heads, self.window_size, self.scale, cd, img, od)
+        want = getattr(self, "out_dtype", None)
+        return y if want is None or y.dtype == want else y.to(want)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         b_, n, c = x.shape

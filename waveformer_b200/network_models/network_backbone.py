@@ -109,11 +109,12 @@ class Waveformer(nn.Module):
     def forward(self, x_in: torch.Tensor) -> torch.Tensor:
         if not x_in.is_cuda:
             raise RuntimeError("waveformer_b200.Waveformer runs on CUDA (B200) only; there is no CPU fallback")
-        dtype = self.out.conv.conv.weight.dtype
+        dtype = self.out.conv.conv.weight.dtype          # activation type of the convolutional U-Net
+        x_in = x_in.contiguous(memory_format=torch.channels_last_3d)
+        # the encoder reads the window in its patch embedding's own type (fp32 under prepare_inference's bf16 policy)
+        outs, outs_hf = self.waveformer_encoder(x_in)
         if x_in.dtype != dtype:
             x_in = x_in.to(dtype)
-        x_in = x_in.contiguous(memory_format=torch.channels_last_3d)
-        outs, outs_hf = self.waveformer_encoder(x_in)
         enc0 = self.encoder1(x_in)
         enc1 = self.encoder2(outs[0])
         enc2 = self.encoder3(outs[1])

@@ -22,8 +22,15 @@ def fused_path(x: torch.Tensor) -> bool:
     return x.is_cuda and not torch.is_grad_enabled()
 
 
-def _ln(norm: nn.LayerNorm, x: torch.Tensor, gelu: bool = False, out_dtype=None) -> torch.Tensor:
-    return ops.layer_norm_cl(x, norm.weight, norm.bias, norm.eps, gelu=gelu, out_dtype=out_dtype)
+def _ln(norm: nn.LayerNorm, x: torch.Tensor, gelu: bool = False, out_dtype=None, also_bf16: bool = False):
+    return ops.layer_norm_cl(x, norm.weight, norm.bias, norm.eps, gelu=gelu, out_dtype=out_dtype, also_bf16=also_bf16)
+
+
+def _linear_f32_out(a: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """bf16 operands, fp32 accumulators written out unrounded (the result joins the fp32 residual stream)."""
+    k = a.shape[-1]
+    y = torch.mm(a.reshape(-1, k), weight.t(), out_dtype=torch.float32)
+    return y.view(a.shape[:-1] + (weight.shape[0],))
 
 
 class DropPath(nn.Module):
@@ -144,18 +151,25 @@ class CCF_FFN(nn.Module):
             if m.bias is not None:
                 m.bias.data.zero_()
 
+    def ffn_fused(self, x: torch.Tensor, xop: torch.Tensor) -> torch.Tensor:
+        """The FFN branch WITHOUT its residual.  ``xop`` = x in the GEMM operand type (bf16 under the inference policy,
+        where x itself is the fp32 copy); the 4C-wide intermediates live in the operand type, the result is returned in
+        x's type - unrounded fp32 accumulators when x is the fp32 stream."""
+        C = x.shape[-1]
+        cd = xop.dtype
+        t = F.linear(xop, ops.cast_cached(self.pwconv.weight, cd).view(self.C_hid, C), ops.cast_cached(self.pwconv.bias, cd))
+        t = _ln(self.norm1, t, gelu=True)                                  # LayerNorm + GELU, one pass
+        t = ops.dwconv3d_channels_last(t, *self._packed_dwconv())          # hand-written stencil
+        t = _ln(self.norm2, t, gelu=True)
+        if x.dtype == torch.float32 and cd != torch.float32:
+            return _linear_f32_out(t, ops.cast_cached(self.fc.weight, cd)) + ops.f32_cached(self.fc.bias)
+        return F.linear(t, ops.cast_cached(self.fc.weight, cd), ops.cast_cached(self.fc.bias, cd))
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         B, D, H, W, C = x.shape
         assert D * H * W == self.D * self.H * self.W
         if fused_path(x):
-            # x may be an fp32 stream; GEMM operands and the 4C-wide intermediates use the compute dtype
-            cd = getattr(self, "compute_dtype", None) or x.dtype
-            t = F.linear(x.to(cd), ops.cast_cached(self.pwconv.weight, cd).view(self.C_hid, C), ops.cast_cached(self.pwconv.bias, cd))
-            t = _ln(self.norm1, t, gelu=True)                                  # LayerNorm + GELU, one pass
-            t = ops.dwconv3d_channels_last(t, *self._packed_dwconv())          # hand-written stencil
-            t = _ln(self.norm2, t, gelu=True)
-            f = F.linear(t, ops.cast_cached(self.fc.weight, cd), ops.cast_cached(self.fc.bias, cd))
-            return x + f
+            return x + self.ffn_fused(x, x.to(getattr(self, "compute_dtype", None) or x.dtype))
         # the 1^3 convolution is a per-voxel linear map: run it on the channels-last tensor directly
         t = F.linear(x, self.pwconv.weight.view(self.C_hid, C), self.pwconv.bias)
         t = self.act(self.norm1(t))
@@ -207,7 +221,9 @@ class PatchMergingV2(nn.Module):
         if fused_path(x):
             cd = getattr(self, "compute_dtype", None) or x.dtype
             n = _ln(self.norm, g, out_dtype=cd)
-            return F.linear(n, ops.cast_cached(self.reduction.weight, cd)).to(x.dtype)
+            if x.dtype == torch.float32 and cd != torch.float32:
+                return _linear_f32_out(n, ops.cast_cached(self.reduction.weight, cd))   # fp32 stream stays unrounded
+            return F.linear(n, ops.cast_cached(self.reduction.weight, cd))
         return self.reduction(self.norm(g))
 
     def forward(self, x):
@@ -314,9 +330,10 @@ class Block(nn.Module):
         D, H, W = self.img_size
         cur = _ln(self.norm1, x)
         coarse, hfs = [], []
+        hf_dtype = getattr(self, "hf_dtype", None)   # decoder activation type (prepare_inference); default: the stream's
         for _ in range(self.attn_computation_level):
             if self.level > 0:
-                cur, hf = ops.dwt3d_channels_last(cur, need_hf=self.need_hf)
+                cur, hf = ops.dwt3d_channels_last(cur, need_hf=self.need_hf, hf_dtype=hf_dtype)
                 if self.need_hf:
                     hfs.append(self._details_as_dict(hf))
             coarse.append(self.attn.forward_grid(cur))
@@ -324,7 +341,14 @@ class Block(nn.Module):
             y = ops.upsample_trilinear_add(coarse, (D, H, W), base=x, out_dtype=x.dtype)
         else:
             y = x + coarse[0] if len(coarse) == 1 else x + sum(coarse)
-        y = y + self.mlp(_ln(self.norm2, y))
+        cd = getattr(self.mlp, "compute_dtype", None)
+        if cd is not None and cd != y.dtype:
+            # fp32 stream: LayerNorm writes the fp32 copy (CCF_FFN's own residual, wave_helper.py:293) and the bf16 GEMM
+            # operand in one pass; y + n + ffn(n) is accumulated in fp32
+            n, nop = _ln(self.norm2, y, also_bf16=True)
+            y = (y + n).add_(self.mlp.ffn_fused(n, nop))
+        else:
+            y = y + self.mlp(_ln(self.norm2, y))
         if self.level > 0:
             return y, tuple(reversed(hfs))
         return y

@@ -10,6 +10,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .. import ops
 from .blocks import SwinPatchEmbed
 from .wave_helper import Block, PatchMerging
 
@@ -84,7 +85,9 @@ class MultiscaleTransformer(nn.Module):
 
     def forward_features(self, x_rgb: torch.Tensor, normalize: bool = True) -> Tuple[List[torch.Tensor], List]:
         outs, outs_hf = [], []
-        t = self.pos_drop(self.patch_embed(x_rgb)).permute(0, 2, 3, 4, 1)   # [B, D, H, W, C]
+        pe_dtype = self.patch_embed.proj.weight.dtype
+        t = self.pos_drop(self.patch_embed(x_rgb if x_rgb.dtype == pe_dtype else x_rgb.to(pe_dtype)))
+        t = t.permute(0, 2, 3, 4, 1)                                           # [B, D, H, W, C]
         if not t.is_contiguous():
             t = t.contiguous()
         for s in range(4):
@@ -92,7 +95,12 @@ class MultiscaleTransformer(nn.Module):
             for blk in getattr(self, f"block{s + 1}"):
                 res = blk(t)
                 t, hf = res if isinstance(res, tuple) else (res, ())
-            o = F.layer_norm(t, [t.shape[-1]]) if normalize else t
+            od = getattr(self, "out_dtype", None) or t.dtype    # decoder activation type (prepare_inference)
+            if normalize and t.is_cuda and not torch.is_grad_enabled():
+                o = ops.layer_norm_cl(t, None, None, 1e-5, out_dtype=od)   # affine-free LN, stream -> decoder type
+            else:
+                o = F.layer_norm(t, [t.shape[-1]]) if normalize else t
+                o = o if o.dtype == od else o.to(od)
             outs.append(o.permute(0, 4, 1, 2, 3))
             if s < 3:
                 outs_hf.append(hf if hf is not None else ())

@@ -6,6 +6,7 @@ raises if the tensor is not on a CUDA device (no CPU fallback).
 """
 from __future__ import annotations
 
+import weakref
 from typing import Optional, Tuple
 
 import torch
@@ -101,7 +102,7 @@ def _idwt_ncdhw_raw(ll: torch.Tensor, hf: Optional[torch.Tensor], gate: Optional
     return x
 
 
-def _dwt_ndhwc_raw(x: torch.Tensor, need_hf: bool) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+def _dwt_ndhwc_raw(x: torch.Tensor, need_hf: bool, hf_dtype: Optional[torch.dtype] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     dev = _need_cuda(x)
     if x.dim() != 5:
         raise ValueError("expected [B, D, H, W, C]")
@@ -113,10 +114,11 @@ def _dwt_ndhwc_raw(x: torch.Tensor, need_hf: bool) -> Tuple[torch.Tensor, Option
         x = x.contiguous()
         xs = C
     ll = torch.empty((B, D // 2, H // 2, W // 2, C), dtype=x.dtype, device=dev)
-    hf = torch.empty((7,) + tuple(ll.shape), dtype=x.dtype, device=dev) if need_hf else None
+    hf = torch.empty((7,) + tuple(ll.shape), dtype=hf_dtype or x.dtype, device=dev) if need_hf else None
     with torch.cuda.device(dev):
-        st = _lib.lib().wf_dwt3d_ndhwc(x.data_ptr(), ll.data_ptr(), _ptr(hf), _dtype_code(x), B, D, H, W, C, xs, C,
-                                       ll.numel(), _stream(dev))
+        st = _lib.lib().wf_dwt3d_ndhwc(x.data_ptr(), ll.data_ptr(), _ptr(hf), _dtype_code(x),
+                                       _dtype_code(hf) if need_hf else _dtype_code(x), B, D, H, W, C, xs, C, ll.numel(),
+                                       _stream(dev))
     _lib.check(st, "wf_dwt3d_ndhwc")
     _count()
     return ll, hf
@@ -199,8 +201,8 @@ class _IdwtNCDHW(torch.autograd.Function):
 
 class _DwtNDHWC(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, need_hf):
-        ll, hf = _dwt_ndhwc_raw(x, need_hf)
+    def forward(ctx, x, need_hf, hf_dtype=None):
+        ll, hf = _dwt_ndhwc_raw(x, need_hf, hf_dtype)
         ctx.need_hf = need_hf
         if need_hf:
             return ll, hf
@@ -209,7 +211,9 @@ class _DwtNDHWC(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_ll, g_hf):
         hf = g_hf if (ctx.need_hf and g_hf is not None and g_hf.numel()) else None
-        return _idwt_ndhwc_raw(g_ll, hf), None
+        if hf is not None and hf.dtype != g_ll.dtype:
+            hf = hf.to(g_ll.dtype)
+        return _idwt_ndhwc_raw(g_ll, hf), None, None
 
 
 class _IdwtNDHWC(torch.autograd.Function):
@@ -240,9 +244,10 @@ def idwt3d(ll: torch.Tensor, hf: Optional[torch.Tensor], gate: Optional[torch.Te
     return _IdwtNCDHW.apply(ll, hf, gate)
 
 
-def dwt3d_channels_last(x: torch.Tensor, need_hf: bool = True):
-    """One Haar level on channels-last ``x[B, D, H, W, C]`` -> ``ll[B, d, h, w, C]``, ``hf[7, B, d, h, w, C]``."""
-    ll, hf = _DwtNDHWC.apply(x, need_hf)
+def dwt3d_channels_last(x: torch.Tensor, need_hf: bool = True, hf_dtype: Optional[torch.dtype] = None):
+    """One Haar level on channels-last ``x[B, D, H, W, C]`` -> ``ll[B, d, h, w, C]``, ``hf[7, B, d, h, w, C]``
+    (``hf_dtype``: store the details as bf16 while x / ll stay fp32)."""
+    ll, hf = _DwtNDHWC.apply(x, need_hf, hf_dtype)
     return ll, (hf if need_hf else None)
 
 
@@ -270,34 +275,66 @@ def relpos_bias_expand(table: torch.Tensor, index: torch.Tensor) -> torch.Tensor
     return out
 
 
+_ATTN_CODE = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+
+
+def relpos_bias_image(table: torch.Tensor, index: torch.Tensor, fmt: torch.dtype) -> torch.Tensor:
+    """Dense 16-bit bias image ``img[h, i, 520] = fmt(table[index[i, j], h] * log2 e)`` for the tensor-core kernels."""
+    dev = _need_cuda(table, index)
+    if index.dtype != torch.int64 or tuple(index.shape) != (512, 512):
+        raise ValueError("the tensor-core attention path needs a [512, 512] int64 relative_position_index")
+    if fmt not in (torch.bfloat16, torch.float16):
+        raise ValueError("bias image format must be bfloat16 or float16")
+    table = table.contiguous()
+    index = index.contiguous()
+    heads = table.shape[1]
+    L = _lib.lib()
+    img = torch.empty(L.wf_relpos_bias_image_bytes(heads, 512) // 2, dtype=fmt, device=dev)
+    with torch.cuda.device(dev):
+        st = L.wf_relpos_bias_image(table.data_ptr(), _dtype_code(table), index.data_ptr(), img.data_ptr(),
+                                    _ATTN_CODE[fmt], heads, 512, table.shape[0], _stream(dev))
+    _lib.check(st, "wf_relpos_bias_image")
+    _count()
+    return img
+
+
+def window_attention_uses_tensor_cores(grid, C: int, heads: int, ws: int, compute_dtype: torch.dtype) -> bool:
+    if compute_dtype not in (torch.bfloat16, torch.float16):
+        return False
+    return bool(_lib.lib().wf_window_attn_tc_supported(int(grid[0]), int(grid[1]), int(grid[2]), int(C), int(heads), int(ws)))
+
+
 def _window_attention_raw(x, qkv_w, qkv_b, proj_w, proj_b, bias_t, heads: int, ws: int, scale: float,
-                          compute_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
-    """``compute_dtype`` (default: x.dtype) selects the kernels: bf16 -> tcgen05 tensor-core path (x may be fp32 or
-    bf16, the result is bf16); fp32 -> CUDA-core fp32 path."""
-    dev = _need_cuda(x, qkv_w, qkv_b, proj_w, proj_b, bias_t)
+                          compute_dtype: Optional[torch.dtype] = None, bias_img: Optional[torch.Tensor] = None,
+                          out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """``compute_dtype`` (default: x.dtype) is the weight / GEMM-operand type: bf16 or fp16 -> tcgen05 tensor-core path
+    (needs ``bias_img``; x may be fp32 or bf16; the result is ``out_dtype`` = compute dtype or fp32); fp32 -> CUDA-core
+    fp32 path (needs ``bias_t``)."""
+    dev = _need_cuda(x, qkv_w, qkv_b, proj_w, proj_b, bias_t, bias_img)
     if x.dim() != 5:
         raise ValueError("expected x [B, D1, H1, W1, C]")
     B, D1, H1, W1, C = x.shape
     cdt = compute_dtype or x.dtype
-    if cdt not in (torch.float32, torch.bfloat16):
-        raise ValueError(f"waveformer_b200: dtype {cdt} not supported (float32 or bfloat16)")
+    if cdt not in _ATTN_CODE:
+        raise ValueError(f"waveformer_b200: dtype {cdt} not supported (float32, bfloat16 or float16 operands)")
     _dtype_code(x)
     x = x.contiguous()
-    code = 1 if cdt == torch.bfloat16 else 0
+    code = _ATTN_CODE[cdt]
     if code == 0 and x.dtype != torch.float32:
         x = x.float()
+    odt = out_dtype or cdt
     x_code = _dtype_code(x)
     L = _lib.lib()
     nbytes = L.wf_window_attn_workspace_bytes(code, B, D1, H1, W1, C, heads, ws)
     if nbytes == 0:
         raise ValueError(f"window attention: unsupported geometry grid={(D1, H1, W1)} C={C} heads={heads} ws={ws}")
     work = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    out = torch.empty(x.shape, dtype=cdt, device=dev)
+    out = torch.empty(x.shape, dtype=odt, device=dev)
     qkv_w, qkv_b, proj_w, proj_b = (cast_cached(t, cdt) for t in (qkv_w, qkv_b, proj_w, proj_b))
     with torch.cuda.device(dev):
         st = L.wf_window_attn_fwd(x.data_ptr(), x_code, qkv_w.data_ptr(), _ptr(qkv_b), proj_w.data_ptr(),
-                                  proj_b.data_ptr(), bias_t.data_ptr(), out.data_ptr(), work.data_ptr(), nbytes, code, B,
-                                  D1, H1, W1, C, heads, ws, float(scale), _stream(dev))
+                                  proj_b.data_ptr(), _ptr(bias_t), _ptr(bias_img), out.data_ptr(), _ATTN_CODE[odt],
+                                  work.data_ptr(), nbytes, code, B, D1, H1, W1, C, heads, ws, float(scale), _stream(dev))
     _lib.check(st, "wf_window_attn_fwd")
     _count(3)
     return out
@@ -314,10 +351,12 @@ class _WindowAttention(torch.autograd.Function):
     recomputing the window attention with torch ops under autograd - a library path, listed as a gap in DESIGN.md."""
 
     @staticmethod
-    def forward(ctx, x, qkv_w, qkv_b, proj_w, proj_b, table, index, bias_t, heads, ws, scale, compute_dtype):
+    def forward(ctx, x, qkv_w, qkv_b, proj_w, proj_b, table, index, bias_t, heads, ws, scale, compute_dtype, bias_img,
+                out_dtype):
         ctx.save_for_backward(x, qkv_w, qkv_b, proj_w, proj_b, table, index)
         ctx.cfg = (heads, ws, scale)
-        return _window_attention_raw(x, qkv_w, qkv_b, proj_w, proj_b, bias_t, heads, ws, scale, compute_dtype)
+        return _window_attention_raw(x, qkv_w, qkv_b, proj_w, proj_b, bias_t, heads, ws, scale, compute_dtype, bias_img,
+                                     out_dtype)
 
     @staticmethod
     def backward(ctx, g):
@@ -337,16 +376,18 @@ class _WindowAttention(torch.autograd.Function):
             live = [t for t in leaves if t is not None]
             grads = list(torch.autograd.grad(y, live, g.float()))
         out = [None if s_ is None else grads.pop(0).to(s_.dtype) for s_ in srcs]
-        return out[0], out[1], out[2], out[3], out[4], out[5], None, None, None, None, None, None
+        return (out[0], out[1], out[2], out[3], out[4], out[5]) + (None,) * 8
 
 
 def window_attention(x, qkv_w, qkv_b, proj_w, proj_b, table, index, bias_t, heads: int, ws: int, scale: float,
-                     compute_dtype: Optional[torch.dtype] = None):
+                     compute_dtype: Optional[torch.dtype] = None, bias_img: Optional[torch.Tensor] = None,
+                     out_dtype: Optional[torch.dtype] = None):
     """Window partition + attention + reshape-only reverse on channels-last ``x[B, D1, H1, W1, C]``.
 
     Returns the window-major result buffer viewed as ``[B, D1, H1, W1, C]`` - exactly what the reference produces at
     ``wave_helper.py:497-499`` (it never applies the inverse permute)."""
-    return _WindowAttention.apply(x, qkv_w, qkv_b, proj_w, proj_b, table, index, bias_t, heads, ws, scale, compute_dtype)
+    return _WindowAttention.apply(x, qkv_w, qkv_b, proj_w, proj_b, table, index, bias_t, heads, ws, scale, compute_dtype,
+                                  bias_img, out_dtype)
 
 
 
@@ -432,44 +473,39 @@ def instance_norm_act(x: torch.Tensor, act: str = "none", slope: float = 0.01, r
     return out.permute(0, 4, 1, 2, 3)
 
 
-_F32_CACHE = {}
-
-
-def f32_cached(p: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
-    """fp32 contiguous copy of a (small) parameter, cached until the parameter is modified or moved."""
-    if p is None:
-        return None
-    key = id(p)
-    tag = (p._version, p.data_ptr(), p.device, p.dtype)
-    hit = _F32_CACHE.get(key)
-    if hit is None or hit[0] != tag:
-        hit = (tag, p.detach().float().contiguous())
-        _F32_CACHE[key] = hit
-    return hit[1]
-
-
 _CAST_CACHE = {}
 
 
 def cast_cached(p: Optional[torch.Tensor], dtype: torch.dtype) -> Optional[torch.Tensor]:
-    """``p`` in ``dtype`` (contiguous, detached); the converted copy is cached until ``p`` is modified or moved."""
+    """``p`` in ``dtype`` (contiguous, detached).  The converted copy is cached until ``p`` is modified, moved or freed:
+    an entry is valid only while its weak reference still points at the very same tensor object (``id`` values and
+    device addresses are both recycled once a tensor dies, so neither can identify it)."""
     if p is None:
         return None
     if p.dtype == dtype and p.is_contiguous():
         return p.detach()
     key = (id(p), dtype)
-    tag = (p._version, p.data_ptr(), p.device, p.dtype)
+    tag = (p._version, p.data_ptr(), p.device, p.dtype, tuple(p.shape))
     hit = _CAST_CACHE.get(key)
-    if hit is None or hit[0] != tag:
-        hit = (tag, p.detach().to(dtype).contiguous())
+    if hit is None or hit[0]() is not p or hit[1] != tag:
+        if len(_CAST_CACHE) > 4096:
+            for k in [k for k, v in _CAST_CACHE.items() if v[0]() is None]:
+                del _CAST_CACHE[k]
+        hit = (weakref.ref(p), tag, p.detach().to(dtype).contiguous())
         _CAST_CACHE[key] = hit
-    return hit[1]
+    return hit[2]
+
+
+def f32_cached(p: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """fp32 contiguous view / copy of a (small) parameter, cached like ``cast_cached``."""
+    return cast_cached(p, torch.float32)
 
 
 def layer_norm_cl(x: torch.Tensor, weight: Optional[torch.Tensor], bias: Optional[torch.Tensor], eps: float,
-                  gelu: bool = False, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+                  gelu: bool = False, out_dtype: Optional[torch.dtype] = None, also_bf16: bool = False):
     """LayerNorm over the last dim of a channels-last tensor (any leading dims, last-dim stride 1), optional GELU;
-    ``out_dtype`` may differ from the input's (fp32 stream -> bf16 operand)."""
+    ``out_dtype`` may differ from the input's (fp32 stream -> bf16 operand).  ``also_bf16`` returns ``(y, y_bf16)``:
+    the same result also rounded to bf16 by the same pass (GEMM operand + fp32 copy for the residual)."""
     dev = _need_cuda(x, weight, bias)
     C = x.shape[-1]
     if x.stride(-1) != 1:
@@ -478,13 +514,14 @@ def layer_norm_cl(x: torch.Tensor, weight: Optional[torch.Tensor], bias: Optiona
     rows = x2.shape[0]
     out_dtype = out_dtype or x.dtype
     y = torch.empty(x.shape, dtype=out_dtype, device=dev)
+    y2 = torch.empty(x.shape, dtype=torch.bfloat16, device=dev) if also_bf16 else None
     with torch.cuda.device(dev):
         st = _lib.lib().wf_layernorm_ndhwc(x2.data_ptr(), _ptr(f32_cached(weight)), _ptr(f32_cached(bias)), y.data_ptr(),
-                                           _dtype_code(x2), _dtype_code(y), rows, C, x2.stride(0), C, float(eps),
-                                           int(gelu), _stream(dev))
+                                           _ptr(y2), _dtype_code(x2), _dtype_code(y), rows, C, x2.stride(0), C,
+                                           float(eps), int(gelu), _stream(dev))
     _lib.check(st, "wf_layernorm_ndhwc")
     _count()
-    return y
+    return (y, y2) if also_bf16 else y
 
 
 def upsample_trilinear_add(srcs, size, base: Optional[torch.Tensor] = None, align_corners: bool = False,

@@ -1,0 +1,83 @@
+"""Inference precision policy (``prepare_inference``).
+
+The reference runs fp32 everywhere (autocast is forced off, ``light_training/prediction.py:124``).  The B200 path stores
+activations of the convolutional U-Net in bf16 (94 % of the FLOPs, cuDNN tensor-core convolutions) but keeps the parts
+whose rounding dominates the logit error - measured with ``scripts/precision_zones.py`` / ``precision_attn.py`` on the
+unit-gain test weights - at higher precision, none of which costs measurable time:
+
+* the encoder's residual stream (patch embedding output, block outputs, patch merging) stays fp32; LayerNorm reads it
+  in fp32 and writes the GEMM operand type, so no tensor of the stream is ever rounded to bf16;
+* the patch embedding (4 -> 48 channels, 2^3 kernel: 0.2 % of the FLOPs) runs in fp32 on the fp32 input window - rounding
+  the raw image to bf16 alone costs 4e-2 max-relative logit error;
+* window attention uses fp16 tensor-core operands (same tcgen05 rate as bf16, 10-bit mantissa) with fp32 accumulation and
+  an fp32 result: with bf16 operands attention alone costs 7e-2, with fp16 9e-3;
+* everything else (CCF_FFN GEMMs, conv blocks, decoder, IDWT) has bf16 operands and bf16 storage, fp32 accumulation,
+  fp32 statistics in every normalisation.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .network_models.attention import Attention
+from .network_models.blocks import SwinPatchEmbed
+from .network_models.wave_helper import Block, CCF_FFN, PatchMergingV2, ProjectionUpsample
+from .network_models.waveformer import MultiscaleTransformer
+
+__all__ = ["prepare_inference"]
+
+
+def prepare_inference(model: nn.Module, dtype: torch.dtype = torch.bfloat16, *, attention: str = "fp16",
+                      fp32_stream: bool = True) -> nn.Module:
+    """Put ``model`` (a ``Waveformer``) into inference form on its current device.
+
+    ``dtype=torch.float32``: nothing is rounded (parity mode, <= 1e-4 against the reference).
+    ``dtype=torch.bfloat16``: the policy in the module docstring.  ``attention`` selects the operand format of the
+    window-attention GEMMs ("fp16", "bf16" or "fp32" = CUDA-core kernels); ``fp32_stream=False`` gives the plain
+    all-bf16 model (``model.to(torch.bfloat16)``), kept for the precision study.
+    """
+    model.eval()
+    if dtype == torch.float32:
+        model.float()
+        for m in model.modules():
+            for name in ("compute_dtype", "out_dtype"):
+                if hasattr(m, name):
+                    delattr(m, name)
+        return model.to(memory_format=torch.channels_last_3d)
+    if dtype != torch.bfloat16:
+        raise ValueError("prepare_inference supports float32 and bfloat16")
+    if attention not in ("fp16", "bf16", "fp32"):
+        raise ValueError("attention must be 'fp16', 'bf16' or 'fp32'")
+    if not fp32_stream:
+        return model.to(torch.bfloat16).to(memory_format=torch.channels_last_3d)
+    attn_dtype = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[attention]
+    keep = set()                                       # parameters that stay fp32 (never rounded through bf16)
+
+    def keep_fp32(mod: nn.Module) -> None:
+        for t in list(mod.parameters()) + list(mod.buffers()):
+            keep.add(id(t))
+
+    for m in model.modules():
+        if isinstance(m, SwinPatchEmbed):
+            keep_fp32(m)                                # fp32 input window -> fp32 stream
+        elif isinstance(m, Attention):
+            keep_fp32(m)                                # fp32 master weights; 16-bit operand copies are cached per dtype
+            m.compute_dtype = attn_dtype
+            m.out_dtype = torch.float32
+        elif isinstance(m, (nn.LayerNorm, nn.GroupNorm)):
+            keep_fp32(m)                                # the normalisation kernels read gamma / beta as fp32
+        if isinstance(m, CCF_FFN):
+            keep_fp32(m.dwconv)                         # depthwise stencils: the kernel takes fp32 taps
+            m.compute_dtype = torch.bfloat16            # bf16 GEMM operands, fp32 stream in / out
+        elif isinstance(m, ProjectionUpsample):
+            keep_fp32(m.conv1[1])
+        elif isinstance(m, PatchMergingV2):
+            m.compute_dtype = torch.bfloat16
+        elif isinstance(m, Block):
+            m.hf_dtype = torch.bfloat16                 # detail bands go to the bf16 decoder
+        elif isinstance(m, MultiscaleTransformer):
+            m.out_dtype = torch.bfloat16                # stage outputs feed the bf16 conv blocks
+    for t in list(model.parameters()) + list(model.buffers()):
+        if t.is_floating_point():
+            t.data = t.data.float() if id(t) in keep else t.data.to(torch.bfloat16)
+    return model.to(memory_format=torch.channels_last_3d)
