@@ -161,6 +161,19 @@ int wf_upsample_trilinear_add_ndhwc(const void *const *srcs, const int *src_dims
                                     int src_dtype, int io_dtype, int align_corners, int B, int D, int H, int W, int C,
                                     int64_t base_vox_stride, int64_t y_vox_stride, void *stream);
 
+/* 3x3x3 convolution (padding 1, no bias) of a 4-channel channels-last volume x [B, D, H, W, 4] (x_dtype WF_F32 or
+ * WF_BF16; bf16 tensor-core operands, fp32 accumulation), fused with an optional 1x1x1 convolution of the same input and
+ * with the InstanceNorm statistics of both bf16 results.  Replaces conv1 + norm1's statistics and conv3 + norm3's
+ * statistics of the first residual block, Waveformer.encoder1 (reference network_models/network_backbone.py:247-255 ->
+ * monai/networks/blocks/dynunet_block.py:98-111).
+ * wpack: bf16 [n0 + n1][112], k = tap * 4 + channel with tap = (dz+1)*9 + (dy+1)*3 + (dx+1), zero padded to 112; rows
+ *        >= n0 carry the 1x1x1 weights in the centre tap (k = 52..55).
+ * y0 / y1: bf16 [B, D, H, W, n0 / n1] with voxel strides (channel slices of wider buffers allowed); n1 may be 0.
+ * sums0 / sums1: fp64 scratch [B * n * 2]; mean_rstd0 / mean_rstd1: fp32 [B * n * 2] = (mean, 1/sqrt(var + eps)). */
+int wf_conv3d_c4_in_stats(const void *x, int x_dtype, const void *wpack, void *y0, int64_t y0_vox_stride, int n0,
+                          void *y1, int64_t y1_vox_stride, int n1, double *sums0, double *sums1, float *mean_rstd0,
+                          float *mean_rstd1, float eps, int B, int D, int H, int W, void *stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Sliding-window stitching (re-hosted MONAI inferer, reference monai/inferers/utils.py:216-299).
  * ---------------------------------------------------------------------------------------------------------- */

@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+(timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest.log)
+timeout 300 python scripts/module_times.py > gpurun_out/module_times.log 2>&1
+timeout 300 python scripts/profile_forward.py --dtype bf16 --batch 2 --rows 60 > gpurun_out/prof_bf16.log 2>&1
+tail -12 gpurun_out/pytest.log; cat gpurun_out/module_times.log

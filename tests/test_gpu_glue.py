@@ -64,3 +64,31 @@ def test_instance_norm_writes_into_concat_slice():
     assert torch.equal(y.permute(0, 2, 3, 4, 1), buf[..., 8:24])
     assert bool((buf[..., :8] == 5).all()) and bool((buf[..., 24:] == 5).all())
     assert max_rel(y.cpu(), F.relu(F.instance_norm(x.cpu()))) < 5e-6
+
+
+@pytest.mark.parametrize("shape", [(2, 4, 16, 24, 32), (2, 4, 6, 10, 12), (1, 4, 8, 8, 8), (3, 4, 5, 7, 9)])
+@pytest.mark.parametrize("in_dtype", [torch.float32, torch.bfloat16])
+def test_conv3d_c4_with_fused_shortcut_and_statistics(shape, in_dtype):
+    """tcgen05 implicit-GEMM first-block convolution: conv1 (3^3) + conv3 (1^3) + both InstanceNorm statistics vs
+    torch's convolutions on the same bf16-rounded operands (ragged tiles, tiles straddling two batch elements)."""
+    from waveformer_b200 import ops
+    x = seeded_randn(shape, 70).cuda().to(in_dtype).contiguous(memory_format=torch.channels_last_3d)
+    w1 = (seeded_randn((48, 4, 3, 3, 3), 71) / 108 ** 0.5).cuda().bfloat16()
+    w3 = (seeded_randn((48, 4, 1, 1, 1), 72) / 2.0).cuda().bfloat16()
+    y0, s0, y1, s1 = ops.conv3d_c4_in_stats(x, w1, w3, eps=1e-5)
+    xr = x.bfloat16().float()
+    want0 = F.conv3d(xr, w1.float(), padding=1)
+    want1 = F.conv3d(xr, w3.float())
+    assert y0.dtype == torch.bfloat16 and tuple(y0.shape) == tuple(want0.shape)
+    assert max_rel(y0.float().cpu(), want0.cpu()) < 6e-3
+    assert max_rel(y1.float().cpu(), want1.cpu()) < 6e-3
+    for y, s in ((y0, s0), (y1, s1)):
+        f = y.float()
+        mean = f.mean(dim=(2, 3, 4)).reshape(-1)
+        rstd = (f.var(dim=(2, 3, 4), unbiased=False) + 1e-5).rsqrt().reshape(-1)
+        got = s.reshape(-1, 2)
+        assert float((got[:, 0] - mean).abs().max()) < 2e-5 * max(1.0, float(mean.abs().max()))
+        assert max_rel(got[:, 1].cpu(), rstd.cpu()) < 1e-4
+    # conv only (no shortcut)
+    y0b, s0b, y1b, s1b = ops.conv3d_c4_in_stats(x, w1, None)
+    assert y1b is None and s1b is None and torch.equal(y0b, y0)

@@ -6,4 +6,9 @@ re-hosted sliding-window inferer; ``waveformer_b200.ops`` are the torch-level op
 """
 __version__ = "0.1.0"
 
-from .precision import prepare_inference  # noqa: E402,F401
+
+def __getattr__(name):  # lazy: importing the package must not import torch-heavy modules (python -m waveformer_b200.build)
+    if name == "prepare_inference":
+        from .precision import prepare_inference
+        return prepare_inference
+    raise AttributeError(name)

@@ -1,0 +1,265 @@
+// 3x3x3 convolution (padding 1, stride 1, no bias) of a 4-channel channels-last volume, fused with the block's 1x1x1
+// shortcut convolution and with the InstanceNorm statistics of both results (tcgen05 / TMEM, sm_100a).
+//
+// Reference: the first residual block of the U-Net, Waveformer.encoder1 = UnetrBasicBlock(in_chans -> 48, res_block)
+// (network_models/network_backbone.py:247-255,386) -> MONAI UnetResBlock.forward
+// (monai/networks/blocks/dynunet_block.py:98-111): conv1 (3^3, in -> out), norm1, lrelu, conv2, norm2, and the shortcut
+// conv3 (1^3, in -> out), norm3.  With in_chans = 4 the library convolution runs at 13 TFLOP/s (3.3 ms per batch-2
+// window, 15 % of the forward): K = 27 * 4 is too thin for its tiling.  Here it is an implicit GEMM whose im2col rows
+// are gathered by the threads themselves:
+//   tile = 128 consecutive voxels (one TMEM lane each); thread = voxel: 27 neighbour loads of 8 bytes (4 x bf16; fp32
+//   input is converted on the fly), written as the K-major no-swizzle UMMA A image [14 chunks][128 rows][8];
+//   B = packed weights [N][112] (k = tap * 4 + channel, zero padded; rows >= n0 hold the 1^3 shortcut's weights in the
+//   centre tap), resident in shared memory for the CTA's lifetime; 7 x tcgen05.mma 128 x N x 16 into TMEM;
+//   epilogue: TMEM -> bf16 -> shared staging tile -> coalesced 16-byte stores to the two outputs, and per-channel
+//   sum / sum of squares of the ROUNDED outputs (thread t < N owns channel t; fp32 per tile, fp64 per CTA, one fp64
+//   atomicAdd per CTA and channel at the end), so InstanceNorm needs no separate statistics pass.
+// Persistent CTAs (grid = min(tiles, 4 per SM)); traffic = one read of the input (L2-resident) + one write of the output.
+#include "tc_common.cuh"
+#include "wf_common.cuh"
+
+namespace wf {
+
+using namespace tc;
+
+constexpr int kC4K = 112;        // 27 taps * 4 channels, padded to 7 k-steps of 16
+constexpr int kC4Chunks = 14;    // 16-byte K chunks per row
+
+struct C4Geom {
+    int B, D, H, W;
+    int64_t total;  // B * D * H * W
+};
+
+template <typename TIN> __device__ __forceinline__ uint2 load_vox4(const TIN *p) {
+    if constexpr (sizeof(TIN) == 2) {
+        return __ldg(reinterpret_cast<const uint2 *>(p));
+    } else {
+        const float4 f = __ldg(reinterpret_cast<const float4 *>(p));
+        return make_uint2(pack_bf16(f.x, f.y), pack_bf16(f.z, f.w));
+    }
+}
+
+// dynamic smem: [A image 14 * 2048][B image 14 * N * 16][staging 128 * (N + 8) * 2]
+template <typename TIN>
+__global__ void __launch_bounds__(128, 4) conv3d_c4_kernel(const TIN *__restrict__ x, const uint16_t *__restrict__ wpack,
+                                                           __nv_bfloat16 *__restrict__ y0, int64_t ys0, int n0,
+                                                           __nv_bfloat16 *__restrict__ y1, int64_t ys1, int n1,
+                                                           double *__restrict__ sums0, double *__restrict__ sums1,
+                                                           C4Geom g, int64_t ntiles, uint32_t tmem_cols) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int N = n0 + n1;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    uint8_t *sA = smem;
+    uint8_t *sB = smem + kC4Chunks * 2048;
+    const int pitch = N + 8;  // staging row pitch in elements (16-byte aligned rows, conflict-free 16-byte writes)
+    __nv_bfloat16 *sOut = reinterpret_cast<__nv_bfloat16 *>(sB + (size_t)kC4Chunks * N * 16);
+
+    if (warp == 0) tmem_alloc(&tmem_slot, tmem_cols);
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    // weights: [N][112] bf16 row-major in global -> canonical K-major image [chunk][row][8]
+    for (int idx = tid; idx < N * kC4Chunks; idx += 128) {
+        const int r = idx % N, kc = idx / N;
+        *reinterpret_cast<uint4 *>(sB + ((size_t)kc * N + r) * 16) =
+            __ldg(reinterpret_cast<const uint4 *>(wpack + (int64_t)r * kC4K) + kc);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t idesc = instr_desc_bf16(128, N, false);
+    const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const int64_t S = (int64_t)g.D * g.H * g.W;
+
+    double acc_s = 0.0, acc_q = 0.0;   // this thread's channel (tid < N), one batch element at a time
+    int64_t acc_b = -1;
+    auto flush = [&]() {
+        if (tid < N && acc_b >= 0) {
+            double *dst = tid < n0 ? sums0 + (acc_b * n0 + tid) * 2 : sums1 + (acc_b * n1 + (tid - n0)) * 2;
+            atomicAdd(dst, acc_s);
+            atomicAdd(dst + 1, acc_q);
+        }
+        acc_s = acc_q = 0.0;
+    };
+
+    uint32_t phase = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t v = tile * 128 + tid;
+        const bool live = v < g.total;
+        // ---- gather this voxel's 27 x 4 neighbourhood into the A image ----
+        {
+            int xx = 0, yy = 0, zz = 0;
+            int64_t b = 0;
+            if (live) {
+                xx = (int)(v % g.W);
+                int64_t t = v / g.W;
+                yy = (int)(t % g.H); t /= g.H;
+                zz = (int)(t % g.D);
+                b = t / g.D;
+            }
+            const TIN *base = x + (b * S) * 4;
+            uint2 tap[28];
+#pragma unroll
+            for (int dz = -1; dz <= 1; ++dz)
+#pragma unroll
+                for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        const int z2 = zz + dz, y2 = yy + dy, x2 = xx + dx;
+                        const bool in = live && (unsigned)z2 < (unsigned)g.D && (unsigned)y2 < (unsigned)g.H &&
+                                        (unsigned)x2 < (unsigned)g.W;
+                        const int t = (dz + 1) * 9 + (dy + 1) * 3 + (dx + 1);
+                        tap[t] = in ? load_vox4<TIN>(base + (((int64_t)z2 * g.H + y2) * g.W + x2) * 4) : make_uint2(0u, 0u);
+                    }
+            tap[27] = make_uint2(0u, 0u);
+#pragma unroll
+            for (int kc = 0; kc < kC4Chunks; ++kc)
+                *reinterpret_cast<uint4 *>(sA + kc * 2048 + tid * 16) =
+                    make_uint4(tap[2 * kc].x, tap[2 * kc].y, tap[2 * kc + 1].x, tap[2 * kc + 1].y);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();   // A image complete; previous tile's staging fully consumed
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < kC4K / 16; ++ks)
+                mma_ss(tmem, smem_desc(a0 + ks * 2 * 2048, 2048, 128), smem_desc(b0 + ks * 2 * N * 16, N * 16, 128), idesc,
+                       ks > 0 ? 1u : 0u);
+            mma_commit(&bar);
+        }
+        mbar_wait(&bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        // ---- epilogue: TMEM lane -> bf16 -> staging row ----
+        for (int c = 0; c < N; c += 16) {
+            uint32_t r[16];
+            tmem_ld16(tmem + lane_base + c, r);
+            tmem_wait_ld();
+            uint4 lo, hi;
+            lo.x = pack_bf16(__uint_as_float(r[0]), __uint_as_float(r[1]));   lo.y = pack_bf16(__uint_as_float(r[2]), __uint_as_float(r[3]));
+            lo.z = pack_bf16(__uint_as_float(r[4]), __uint_as_float(r[5]));   lo.w = pack_bf16(__uint_as_float(r[6]), __uint_as_float(r[7]));
+            hi.x = pack_bf16(__uint_as_float(r[8]), __uint_as_float(r[9]));   hi.y = pack_bf16(__uint_as_float(r[10]), __uint_as_float(r[11]));
+            hi.z = pack_bf16(__uint_as_float(r[12]), __uint_as_float(r[13])); hi.w = pack_bf16(__uint_as_float(r[14]), __uint_as_float(r[15]));
+            uint4 *dst = reinterpret_cast<uint4 *>(sOut + (size_t)tid * pitch + c);
+            dst[0] = lo;
+            dst[1] = hi;
+        }
+        tc_fence_before();
+        __syncthreads();   // staging complete; TMEM and the A image are free for the next tile
+        // ---- coalesced stores: voxel rows of n0 (y0) and n1 (y1) channels ----
+        const int64_t v0 = tile * 128;
+        const int rows = (int)min((int64_t)128, g.total - v0);
+        {
+            const int per0 = n0 >> 3;
+            for (int i = tid; i < rows * per0; i += 128) {
+                const int r = i / per0, p = i % per0;
+                *reinterpret_cast<uint4 *>(y0 + (v0 + r) * ys0 + p * 8) = *reinterpret_cast<const uint4 *>(sOut + (size_t)r * pitch + p * 8);
+            }
+            const int per1 = n1 >> 3;
+            for (int i = tid; i < rows * per1; i += 128) {
+                const int r = i / per1, p = i % per1;
+                *reinterpret_cast<uint4 *>(y1 + (v0 + r) * ys1 + p * 8) = *reinterpret_cast<const uint4 *>(sOut + (size_t)r * pitch + n0 + p * 8);
+            }
+        }
+        // ---- statistics of the rounded outputs: thread t owns channel t ----
+        if (tid < N) {
+            // a tile may straddle two batch elements only if S % 128 != 0; handle row by row in that (rare) case
+            const int64_t b_first = v0 / S, b_last = (v0 + rows - 1) / S;
+            if (b_first == b_last) {
+                if (b_first != acc_b) { flush(); acc_b = b_first; }
+                float s = 0.f, q = 0.f;
+                for (int r = 0; r < rows; ++r) {
+                    const float f = __bfloat162float(sOut[(size_t)r * pitch + tid]);
+                    s += f;
+                    q = fmaf(f, f, q);
+                }
+                acc_s += (double)s;
+                acc_q += (double)q;
+            } else {
+                for (int r = 0; r < rows; ++r) {
+                    const int64_t bb = (v0 + r) / S;
+                    if (bb != acc_b) { flush(); acc_b = bb; }
+                    const float f = __bfloat162float(sOut[(size_t)r * pitch + tid]);
+                    acc_s += (double)f;
+                    acc_q += (double)f * f;
+                }
+            }
+        }
+        // the next iteration's first __syncthreads orders these staging reads before the next epilogue's writes
+    }
+    flush();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, tmem_cols);
+}
+
+// mean / rstd from raw (unshifted) fp64 sums: mr[2i] = mean, mr[2i+1] = 1 / sqrt(var + eps)
+__global__ void stats_finalize_raw_kernel(const double *__restrict__ sums, float *__restrict__ mr, int n, double inv_s,
+                                          double eps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double m = sums[2 * i] * inv_s;
+    double var = sums[2 * i + 1] * inv_s - m * m;
+    var = var < 0.0 ? 0.0 : var;
+    mr[2 * i] = (float)m;
+    mr[2 * i + 1] = (float)(1.0 / sqrt(var + eps));
+}
+
+}  // namespace wf
+
+using namespace wf;
+
+extern "C" int wf_conv3d_c4_in_stats(const void *x, int x_dtype, const void *wpack, void *y0, int64_t y0_vox_stride,
+                                     int n0, void *y1, int64_t y1_vox_stride, int n1, double *sums0, double *sums1,
+                                     float *mean_rstd0, float *mean_rstd1, float eps, int B, int D, int H, int W,
+                                     void *stream) {
+    if (!x || !wpack || !y0 || !sums0 || !mean_rstd0) return WF_ERR_NULL_POINTER;
+    if (n1 > 0 && (!y1 || !sums1 || !mean_rstd1)) return WF_ERR_NULL_POINTER;
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return WF_ERR_BAD_SHAPE;
+    const int N = n0 + n1;
+    if (n0 <= 0 || n1 < 0 || n0 % 8 || n1 % 8 || N % 16 || N > 128) return WF_ERR_BAD_SHAPE;
+    if (y0_vox_stride < n0 || (n1 > 0 && y1_vox_stride < n1) || y0_vox_stride % 8 || (n1 > 0 && y1_vox_stride % 8)) return WF_ERR_BAD_SHAPE;
+    if (x_dtype != WF_F32 && x_dtype != WF_BF16) return WF_ERR_BAD_DTYPE;
+    if (!aligned16(x) || !aligned16(wpack) || !aligned16(y0) || (n1 > 0 && !aligned16(y1))) return WF_ERR_MISALIGNED;
+    cudaStream_t st = (cudaStream_t)stream;
+    C4Geom g;
+    g.B = B; g.D = D; g.H = H; g.W = W;
+    g.total = (int64_t)B * D * H * W;
+    const int64_t ntiles = (g.total + 127) / 128;
+    const size_t smem = (size_t)kC4Chunks * 2048 + (size_t)kC4Chunks * N * 16 + (size_t)128 * (N + 8) * 2;
+    uint32_t cols = 32;
+    while ((int)cols < N) cols <<= 1;
+    static bool attrs_done = false;
+    if (!attrs_done) {
+        WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_c4_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_c4_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attrs_done = true;
+    }
+    WF_CUDA_CHECK(cudaMemsetAsync(sums0, 0, sizeof(double) * 2 * (size_t)B * n0, st));
+    if (n1 > 0) WF_CUDA_CHECK(cudaMemsetAsync(sums1, 0, sizeof(double) * 2 * (size_t)B * n1, st));
+    const int per_sm = (int)min((size_t)4, (size_t)(200 * 1024) / smem);
+    const int grid = (int)min(ntiles, (int64_t)kNumSMs * (per_sm < 1 ? 1 : per_sm));
+    if (x_dtype == WF_F32)
+        conv3d_c4_kernel<float><<<grid, 128, smem, st>>>((const float *)x, (const uint16_t *)wpack, (__nv_bfloat16 *)y0, y0_vox_stride, n0,
+                                                         (__nv_bfloat16 *)y1, y1_vox_stride, n1, sums0, sums1, g, ntiles, cols);
+    else
+        conv3d_c4_kernel<__nv_bfloat16><<<grid, 128, smem, st>>>((const __nv_bfloat16 *)x, (const uint16_t *)wpack, (__nv_bfloat16 *)y0,
+                                                                 y0_vox_stride, n0, (__nv_bfloat16 *)y1, y1_vox_stride, n1, sums0, sums1, g,
+                                                                 ntiles, cols);
+    WF_LAUNCH_CHECK();
+    const double inv_s = 1.0 / ((double)D * H * W);
+    stats_finalize_raw_kernel<<<(B * n0 + 127) / 128, 128, 0, st>>>(sums0, mean_rstd0, B * n0, inv_s, (double)eps);
+    WF_LAUNCH_CHECK();
+    if (n1 > 0) {
+        stats_finalize_raw_kernel<<<(B * n1 + 127) / 128, 128, 0, st>>>(sums1, mean_rstd1, B * n1, inv_s, (double)eps);
+        WF_LAUNCH_CHECK();
+    }
+    return WF_OK;
+}

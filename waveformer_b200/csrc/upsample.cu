@@ -67,18 +67,18 @@ __device__ __forceinline__ void src_index(int dst, float scale, int in, int alig
     if (l1 > 1.f) l1 = 1.f;
 }
 
+// grid: x = ceil(W * cvecs / 256) (threads flat over (x, channel packet) of one row), y = H, z = B * D: the z / y source
+// indices and weights depend on blockIdx only (uniform datapath); a thread pays one division and the x-axis arithmetic.
 template <typename TS, typename TB, typename TO, int VEC>
 __global__ void __launch_bounds__(256) upsample_add_kernel(UpArgs a, const TB *__restrict__ base, TO *__restrict__ y,
                                                            int64_t total, int D, int H, int W, int C, int cvecs,
                                                            int64_t bs, int64_t ys) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int cv = (int)(idx % cvecs);
-    int64_t t = idx / cvecs;
-    const int xx = (int)(t % W); t /= W;
-    const int yy = (int)(t % H); t /= H;
-    const int zz = (int)(t % D);
-    const int64_t b = t / D;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= W * cvecs) return;
+    const int xx = i / cvecs, cv = i - xx * cvecs;
+    const int yy = blockIdx.y;
+    const int zz = blockIdx.z % D;
+    const int64_t b = blockIdx.z / D;
     const int c0 = cv * VEC;
     float acc[VEC];
 #pragma unroll
@@ -131,10 +131,12 @@ static int upsample_launch(const UpArgs &a, const TB *base, TO *y, int B, int D,
     for (int s = 0; s < a.nsrc; ++s) vec = vec && aligned16(a.src[s].ptr);
     if (vec) {
         const int64_t total = (int64_t)B * D * H * W * (C / V);
-        upsample_add_kernel<TS, TB, TO, V><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, base, y, total, D, H, W, C, C / V, bs, ys);
+        dim3 grid((unsigned)((W * (C / V) + 255) / 256), (unsigned)H, (unsigned)(B * D));
+        upsample_add_kernel<TS, TB, TO, V><<<grid, 256, 0, st>>>(a, base, y, total, D, H, W, C, C / V, bs, ys);
     } else {
         const int64_t total = (int64_t)B * D * H * W * C;
-        upsample_add_kernel<TS, TB, TO, 1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, base, y, total, D, H, W, C, C, bs, ys);
+        dim3 grid((unsigned)((W * C + 255) / 256), (unsigned)H, (unsigned)(B * D));
+        upsample_add_kernel<TS, TB, TO, 1><<<grid, 256, 0, st>>>(a, base, y, total, D, H, W, C, C, bs, ys);
     }
     WF_LAUNCH_CHECK();
     return WF_OK;
@@ -148,6 +150,7 @@ extern "C" int wf_upsample_trilinear_add_ndhwc(const void *const *srcs, const in
                                                void *stream) {
     if (!srcs || !src_dims || !y) return WF_ERR_NULL_POINTER;
     if (nsrc < 1 || nsrc > 3 || B <= 0 || D <= 0 || H <= 0 || W <= 0 || C <= 0) return WF_ERR_BAD_SHAPE;
+    if (H > 65535 || (int64_t)B * D > 65535) return WF_ERR_UNSUPPORTED;
     wf::UpArgs a;
     a.nsrc = nsrc;
     a.align = align_corners ? 1 : 0;

@@ -78,14 +78,32 @@ class UnetResBlock(nn.Module):
             self.conv3 = get_conv_layer(spatial_dims, in_channels, out_channels, 1, stride, dropout=dropout)
             self.norm3 = _norm(norm_name, out_channels)
 
-    def forward(self, inp: torch.Tensor) -> torch.Tensor:
+    def _c4_fused(self, inp: torch.Tensor) -> bool:
+        c1 = self.conv1.conv
+        return (self.downsample and c1.in_channels == 4 and c1.kernel_size == (3, 3, 3) and c1.stride == (1, 1, 1)
+                and c1.weight.dtype == torch.bfloat16 and c1.out_channels % 8 == 0 and 2 * c1.out_channels <= 128
+                and self.conv3.conv.stride == (1, 1, 1) and self.norm1.eps == self.norm3.eps
+                and inp.dtype in (torch.float32, torch.bfloat16))
+
+    def forward(self, inp: torch.Tensor, out_buf: torch.Tensor = None) -> torch.Tensor:
+        """``out_buf`` (inference only): a [B, D, H, W, C] channels-last destination - typically the skip half of a
+        decoder's concatenation buffer - the block's last kernel writes into (the torch.cat copy disappears)."""
+        if use_fused(inp) and self._c4_fused(inp):
+            # 4-channel input (the network's first block): conv1, the 1^3 shortcut conv3 and both InstanceNorm statistics
+            # in one tcgen05 kernel (the library convolution needs 3.3 ms for this K = 108 problem)
+            c1, s1, c3, s3 = ops.conv3d_c4_in_stats(inp, self.conv1.conv.weight, self.conv3.conv.weight, eps=self.norm1.eps)
+            out = ops.instance_norm_act(c1, "leakyrelu", 0.01, eps=self.norm1.eps, stats=s1)
+            out = self.conv2(out)
+            return ops.instance_norm_act(out, "leakyrelu", 0.01, res=c3, res_norm=True, eps=self.norm2.eps, res_stats=s3,
+                                         out=out_buf)
         if use_fused(inp):
             # InstanceNorm + LeakyReLU, and InstanceNorm (+ InstanceNorm'd shortcut) + add + LeakyReLU: one kernel each
             out = ops.instance_norm_act(self.conv1(inp), "leakyrelu", 0.01, eps=self.norm1.eps)
             out = self.conv2(out)
             if self.downsample:
-                return ops.instance_norm_act(out, "leakyrelu", 0.01, res=self.conv3(inp), res_norm=True, eps=self.norm2.eps)
-            return ops.instance_norm_act(out, "leakyrelu", 0.01, res=inp, eps=self.norm2.eps)
+                return ops.instance_norm_act(out, "leakyrelu", 0.01, res=self.conv3(inp), res_norm=True, eps=self.norm2.eps,
+                                             out=out_buf)
+            return ops.instance_norm_act(out, "leakyrelu", 0.01, res=inp, eps=self.norm2.eps, out=out_buf)
         out = self.lrelu(self.norm1(self.conv1(inp)))
         out = self.norm2(self.conv2(out))
         res = self.norm3(self.conv3(inp)) if self.downsample else inp
@@ -102,10 +120,10 @@ class UnetBasicBlock(nn.Module):
         self.norm1 = _norm(norm_name, out_channels)
         self.norm2 = _norm(norm_name, out_channels)
 
-    def forward(self, inp: torch.Tensor) -> torch.Tensor:
+    def forward(self, inp: torch.Tensor, out_buf: torch.Tensor = None) -> torch.Tensor:
         if use_fused(inp):
             out = ops.instance_norm_act(self.conv1(inp), "leakyrelu", 0.01, eps=self.norm1.eps)
-            return ops.instance_norm_act(self.conv2(out), "leakyrelu", 0.01, eps=self.norm2.eps)
+            return ops.instance_norm_act(self.conv2(out), "leakyrelu", 0.01, eps=self.norm2.eps, out=out_buf)
         out = self.lrelu(self.norm1(self.conv1(inp)))
         return self.lrelu(self.norm2(self.conv2(out)))
 
@@ -117,8 +135,8 @@ class UnetrBasicBlock(nn.Module):
         cls = UnetResBlock if res_block else UnetBasicBlock
         self.layer = cls(spatial_dims, in_channels, out_channels, kernel_size, stride, norm_name)
 
-    def forward(self, inp: torch.Tensor) -> torch.Tensor:
-        return self.layer(inp)
+    def forward(self, inp: torch.Tensor, out_buf: torch.Tensor = None) -> torch.Tensor:
+        return self.layer(inp) if out_buf is None else self.layer(inp, out_buf)
 
 
 class UnetrUpBlock(nn.Module):
@@ -130,8 +148,15 @@ class UnetrUpBlock(nn.Module):
         cls = UnetResBlock if res_block else UnetBasicBlock
         self.conv_block = cls(spatial_dims, 2 * out_channels, out_channels, kernel_size, 1, norm_name)
 
-    def forward(self, inp: torch.Tensor, skip: torch.Tensor) -> torch.Tensor:
-        return self.conv_block(torch.cat((self.transp_conv(inp), skip), dim=1))
+    def forward(self, inp: torch.Tensor, skip: torch.Tensor, cat_buf: torch.Tensor = None) -> torch.Tensor:
+        """``cat_buf`` (inference only): [B, D, H, W, 2C] channels-last buffer whose channels [C, 2C) already hold
+        ``skip`` (written there by its producer); only the upsampled half is copied in."""
+        up = self.transp_conv(inp)
+        if cat_buf is not None:
+            c = up.shape[1]
+            cat_buf[..., :c].copy_(up.permute(0, 2, 3, 4, 1))
+            return self.conv_block(cat_buf.permute(0, 4, 1, 2, 3))
+        return self.conv_block(torch.cat((up, skip), dim=1))
 
 
 class UnetOutBlock(nn.Module):

@@ -76,7 +76,9 @@ class UnetrIDWTBlock(nn.Module):
             return base
         return torch.stack(cl, 0).contiguous()
 
-    def forward(self, inp, skip, hf_coeffs):
+    def forward(self, inp, skip, hf_coeffs, cat_buf=None, out_buf=None):
+        """``cat_buf`` (inference only): [B, D, H, W, 2C] channels-last buffer whose channels [C, 2C) already hold ``skip``;
+        ``out_buf``: channels-last destination of the block's result (a slice of the next concatenation buffer)."""
         low = self.conv_lf_block(inp)                                   # [B, C, d, h, w]
         B, C = low.shape[:2]
         cur = low.permute(0, 2, 3, 4, 1)                                # channels-last view (copy only if NCDHW-contiguous)
@@ -92,12 +94,14 @@ class UnetrIDWTBlock(nn.Module):
             out = None
             if fuse_cat and i == n_levels - 1:
                 _, d, h, w, _ = cur.shape
-                cat = torch.empty((B, 2 * d, 2 * h, 2 * w, 2 * C), dtype=cur.dtype, device=cur.device)
+                cat = cat_buf if cat_buf is not None else torch.empty((B, 2 * d, 2 * h, 2 * w, 2 * C), dtype=cur.dtype,
+                                                                      device=cur.device)
                 out = cat[..., :C]
             cur = ops.idwt3d_channels_last(cur, stack, gate, out)
         if fuse_cat and n_levels > 0:
-            cat[..., C:] = skip.permute(0, 2, 3, 4, 1)
+            if cat_buf is None:
+                cat[..., C:] = skip.permute(0, 2, 3, 4, 1)
             merged = cat.permute(0, 4, 1, 2, 3)                         # [B, 2C, D, H, W], channels-last-3d strides
         else:
             merged = torch.cat((cur.permute(0, 4, 1, 2, 3), skip), dim=1)
-        return self.conv_block(merged)
+        return self.conv_block(merged) if out_buf is None else self.conv_block(merged, out_buf)

@@ -113,8 +113,11 @@ class Waveformer(nn.Module):
         x_in = x_in.contiguous(memory_format=torch.channels_last_3d)
         # the encoder reads the window in its patch embedding's own type (fp32 under prepare_inference's bf16 policy)
         outs, outs_hf = self.waveformer_encoder(x_in)
-        if x_in.dtype != dtype:
-            x_in = x_in.to(dtype)
+        layer1 = getattr(self.encoder1, "layer", None)
+        if x_in.dtype != dtype and not (hasattr(layer1, "_c4_fused") and not torch.is_grad_enabled() and layer1._c4_fused(x_in)):
+            x_in = x_in.to(dtype)      # the fused 4-channel first block converts the fp32 window while it gathers
+        if use_fused(x_in):
+            return self._forward_fused(x_in, outs, outs_hf, dtype)
         enc0 = self.encoder1(x_in)
         enc1 = self.encoder2(outs[0])
         enc2 = self.encoder3(outs[1])
@@ -125,6 +128,33 @@ class Waveformer(nn.Module):
         dec2 = self.decoder2(dec5, enc1, outs_hf[-3])
         combined = torch.cat([self.learnable_up4(dec4), self.learnable_up3(dec3), dec2], dim=1)
         return self.out(self.decoder1(combined, enc0))
+
+    def _forward_fused(self, x_in, outs, outs_hf, dtype):
+        """Inference wiring: every concatenation buffer is allocated up front and its producers write their channel
+        slice directly (skip halves by the encoder blocks' last kernel, IDWT halves by the synthesis kernel, the three
+        inputs of decoder1 by their producers), so no torch.cat copy of a full activation remains."""
+        f = self.feat_size
+        dev = x_in.device
+
+        def cat_for(skip_src: torch.Tensor, c: int) -> torch.Tensor:
+            b, _, d, h, w = skip_src.shape
+            return torch.empty((b, d, h, w, 2 * c), dtype=dtype, device=dev)
+
+        cat1 = cat_for(x_in, f[0])
+        cat2, cat3, cat4 = cat_for(outs[0], f[0]), cat_for(outs[1], f[1]), cat_for(outs[2], f[2])
+        enc0 = self.encoder1(x_in, cat1[..., f[0]:])
+        enc1 = self.encoder2(outs[0], cat2[..., f[0]:])
+        enc2 = self.encoder3(outs[1], cat3[..., f[1]:])
+        enc3 = self.encoder4(outs[2], cat4[..., f[2]:])
+        dec5 = self.encoder10(outs[3])
+        b, _, d, h, w = outs[0].shape
+        comb = torch.empty((b, d, h, w, 3 * f[0]), dtype=dtype, device=dev)       # [up4 | up3 | dec2]
+        dec4 = self.decoder4(dec5, enc3, outs_hf[-1], cat_buf=cat4)
+        dec3 = self.decoder3(dec5, enc2, outs_hf[-2], cat_buf=cat3)
+        self.decoder2(dec5, enc1, outs_hf[-3], cat_buf=cat2, out_buf=comb[..., 2 * f[0]:])
+        self.learnable_up4(dec4, out_buf=comb[..., :f[0]])
+        self.learnable_up3(dec3, out_buf=comb[..., f[0]:2 * f[0]])
+        return self.out(self.decoder1(comb.permute(0, 4, 1, 2, 3), enc0, cat_buf=cat1))
 
 
 def create_waveformer(network_config: dict) -> Waveformer:

@@ -408,7 +408,8 @@ class ProjectionUpsample(nn.Module):
             self._dw_cache = cache
         return cache[1], cache[2]
 
-    def forward(self, x):
+    def forward(self, x, out_buf=None):
+        """``out_buf`` (inference only): channels-last [B, D, H, W, C_out] destination (a slice of decoder1's input)."""
         if fused_path(x):
             xv = x.permute(0, 2, 3, 4, 1)                                # channels-last view
             size = tuple(int(v * self.stride) for v in x.shape[2:])
@@ -418,6 +419,11 @@ class ProjectionUpsample(nn.Module):
             n = ops.instance_norm_act(dw.permute(0, 4, 1, 2, 3), "none", eps=self.norm.eps,
                                       gamma=ops.f32_cached(self.norm.weight), beta=ops.f32_cached(self.norm.bias))
             y = self.conv3(self.act(self.conv2(n)))
+            if out_buf is not None:
+                dst = out_buf.permute(0, 4, 1, 2, 3)
+                if self.do_res:
+                    return torch.add(y, self.res_conv[1](up.permute(0, 4, 1, 2, 3)), out=dst)
+                return dst.copy_(y)
             if self.do_res:
                 y = y + self.res_conv[1](up.permute(0, 4, 1, 2, 3))
             return y

@@ -444,21 +444,23 @@ def _instnorm_stats(v: torch.Tensor, vs: int, eps: float) -> torch.Tensor:
 
 def instance_norm_act(x: torch.Tensor, act: str = "none", slope: float = 0.01, res: Optional[torch.Tensor] = None,
                       res_norm: bool = False, eps: float = 1e-5, out: Optional[torch.Tensor] = None,
-                      gamma: Optional[torch.Tensor] = None, beta: Optional[torch.Tensor] = None) -> torch.Tensor:
+                      gamma: Optional[torch.Tensor] = None, beta: Optional[torch.Tensor] = None,
+                      stats: Optional[torch.Tensor] = None, res_stats: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``act(InstanceNorm(x) + R)`` for ``x[B, C, D, H, W]`` (any strides; channels-last-3d is copy-free), where ``R`` is
     nothing, ``res`` or ``InstanceNorm(res)``.  Returns a [B, C, D, H, W] tensor with channels-last-3d strides; ``out``
     (optional) is a [B, D, H, W, C] channels-last destination, e.g. a channel slice of a concat buffer."""
     dev = _need_cuda(x, res, out)
     v, vs = _ndhwc_view(x)
     B, D, H, W, C = v.shape
-    mr = _instnorm_stats(v, vs, eps)
+    # stats / res_stats: (mean, rstd) pairs already produced by the kernel that wrote x / res (fused statistics)
+    mr = stats if stats is not None else _instnorm_stats(v, vs, eps)
     rv, rs, rmr = None, C, None
     if res is not None:
         if res.shape != x.shape or res.dtype != x.dtype:
             raise ValueError("residual must match x")
         rv, rs = _ndhwc_view(res)
         if res_norm:
-            rmr = _instnorm_stats(rv, rs, eps)
+            rmr = res_stats if res_stats is not None else _instnorm_stats(rv, rs, eps)
     if out is None:
         out = torch.empty((B, D, H, W, C), dtype=x.dtype, device=dev)
     ys = _voxel_stride(out)
@@ -471,6 +473,55 @@ def instance_norm_act(x: torch.Tensor, act: str = "none", slope: float = 0.01, r
     _lib.check(st, "wf_instnorm_apply_ndhwc")
     _count()
     return out.permute(0, 4, 1, 2, 3)
+
+
+_C4_PACK = {}
+
+
+def _pack_c4_weights(w3x3: torch.Tensor, w1x1: Optional[torch.Tensor]) -> torch.Tensor:
+    """[n0, 4, 3, 3, 3] (+ [n1, 4, 1, 1, 1]) -> bf16 [n0 + n1, 112] for wf_conv3d_c4_in_stats; cached per weight version."""
+    key = (id(w3x3), None if w1x1 is None else id(w1x1))
+    tag = (w3x3._version, w3x3.data_ptr(), None if w1x1 is None else (w1x1._version, w1x1.data_ptr()))
+    hit = _C4_PACK.get(key)
+    if hit is not None and hit[0]() is w3x3 and hit[1] == tag:
+        return hit[2]
+    n0 = w3x3.shape[0]
+    n1 = 0 if w1x1 is None else w1x1.shape[0]
+    pack = torch.zeros((n0 + n1, 112), dtype=torch.float32, device=w3x3.device)
+    pack[:n0, :108] = w3x3.detach().float().permute(0, 2, 3, 4, 1).reshape(n0, 108)
+    if n1:
+        pack[n0:, 52:56] = w1x1.detach().float().reshape(n1, 4)
+    pack = pack.to(torch.bfloat16).contiguous()
+    _C4_PACK[key] = (weakref.ref(w3x3), tag, pack)
+    return pack
+
+
+def conv3d_c4_in_stats(x: torch.Tensor, w3x3: torch.Tensor, w1x1: Optional[torch.Tensor] = None, eps: float = 1e-5):
+    """3^3 conv (+ optional 1^3 conv) of a 4-channel volume with fused InstanceNorm statistics.  ``x``: [B, 4, D, H, W]
+    with channels-last-3d strides (fp32 or bf16).  Returns ``(y0, stats0, y1, stats1)``; ``y*`` are bf16 [B, n, D, H, W]
+    channels-last-3d, ``stats*`` the (mean, rstd) tensors ``instance_norm_act(stats=...)`` takes."""
+    dev = _need_cuda(x, w3x3, w1x1)
+    v, vs = _ndhwc_view(x)
+    B, D, H, W, C = v.shape
+    if C != 4 or vs != 4:
+        raise ValueError("conv3d_c4_in_stats needs a dense 4-channel channels-last volume")
+    if tuple(w3x3.shape[1:]) != (4, 3, 3, 3) or (w1x1 is not None and tuple(w1x1.shape[1:]) != (4, 1, 1, 1)):
+        raise ValueError("weights must be [n0, 4, 3, 3, 3] and [n1, 4, 1, 1, 1]")
+    n0 = w3x3.shape[0]
+    n1 = 0 if w1x1 is None else w1x1.shape[0]
+    pack = _pack_c4_weights(w3x3, w1x1)
+    y0 = torch.empty((B, D, H, W, n0), dtype=torch.bfloat16, device=dev)
+    y1 = torch.empty((B, D, H, W, n1), dtype=torch.bfloat16, device=dev) if n1 else None
+    sums = torch.empty(2 * B * (n0 + n1), dtype=torch.float64, device=dev)
+    mr0 = torch.empty(2 * B * n0, dtype=torch.float32, device=dev)
+    mr1 = torch.empty(2 * B * n1, dtype=torch.float32, device=dev) if n1 else None
+    with torch.cuda.device(dev):
+        st = _lib.lib().wf_conv3d_c4_in_stats(v.data_ptr(), _dtype_code(v), pack.data_ptr(), y0.data_ptr(), n0, n0, _ptr(y1),
+                                              n1, n1, sums.data_ptr(), sums.data_ptr() + 16 * B * n0, mr0.data_ptr(),
+                                              _ptr(mr1), float(eps), B, D, H, W, _stream(dev))
+    _lib.check(st, "wf_conv3d_c4_in_stats")
+    _count(3 if n1 else 2)
+    return (y0.permute(0, 4, 1, 2, 3), mr0, None if y1 is None else y1.permute(0, 4, 1, 2, 3), mr1)
 
 
 _CAST_CACHE = {}
