@@ -92,3 +92,70 @@ def test_conv3d_c4_with_fused_shortcut_and_statistics(shape, in_dtype):
     # conv only (no shortcut)
     y0b, s0b, y1b, s1b = ops.conv3d_c4_in_stats(x, w1, None)
     assert y1b is None and s1b is None and torch.equal(y0b, y0)
+
+
+@pytest.mark.parametrize("rows,c", [(1000, 48), (513, 96), (300, 192), (77, 384), (40, 768), (9, 1536), (64, 20), (50, 8)])
+@pytest.mark.parametrize("in_dtype,out_dtype", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16),
+                                                (torch.bfloat16, torch.bfloat16)])
+@pytest.mark.parametrize("gelu", [False, True])
+def test_layer_norm_channels_last_matches_torch(rows, c, in_dtype, out_dtype, gelu):
+    """LayerNorm (+ GELU erf) over channels: every lane-per-row configuration of the wide kernel, the narrow fallback
+    (C % 8 != 0), mixed storage types and the dual fp32 + bf16 output."""
+    from waveformer_b200 import ops
+    x = (seeded_randn((rows, c), 80) * 1.7 + 0.3).cuda().to(in_dtype)
+    g = (1.0 + 0.1 * seeded_randn((c,), 81)).cuda()
+    b = (0.05 * seeded_randn((c,), 82)).cuda()
+    want = F.layer_norm(x.float(), (c,), g, b, 1e-6)
+    if gelu:
+        want = F.gelu(want)
+    got = ops.layer_norm_cl(x, g, b, 1e-6, gelu=gelu, out_dtype=out_dtype)
+    tol = 2e-6 if out_dtype == torch.float32 and in_dtype == torch.float32 else 5e-3
+    assert got.dtype == out_dtype and max_rel(got.float().cpu(), want.cpu()) < tol
+    if out_dtype == torch.float32:
+        y, y2 = ops.layer_norm_cl(x, g, b, 1e-6, gelu=gelu, out_dtype=out_dtype, also_bf16=True)
+        assert torch.equal(y, got) and torch.equal(y2, got.bfloat16())
+    # affine-free (proj_out)
+    got0 = ops.layer_norm_cl(x, None, None, 1e-5, out_dtype=out_dtype)
+    assert max_rel(got0.float().cpu(), F.layer_norm(x.float(), (c,)).cpu()) < tol
+
+
+@pytest.mark.parametrize("align", [False, True])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 3e-6), (torch.bfloat16, 8e-3)])
+def test_trilinear_upsample_sum_matches_torch(align, dtype, tol):
+    """base + sum of trilinear upsamples of 1..3 coarse maps (Block.multi_scale_forward / ProjectionUpsample)."""
+    from waveformer_b200 import ops
+    size = (16, 24, 32)
+    srcs = [seeded_randn((2, 8, 12, 16, 48), 90), seeded_randn((2, 4, 6, 8, 48), 91), seeded_randn((2, 2, 3, 4, 48), 92)]
+    base = seeded_randn((2,) + size + (48,), 93)
+    for n in (1, 3):
+        want = base.clone() if not align else torch.zeros_like(base)
+        for s in srcs[:n]:
+            s_r = s.to(dtype).float()
+            want = want + F.interpolate(s_r.permute(0, 4, 1, 2, 3), size=size, mode="trilinear",
+                                        align_corners=align).permute(0, 2, 3, 4, 1)
+        got = ops.upsample_trilinear_add([s.cuda().to(dtype) for s in srcs[:n]], size,
+                                         base=None if align else base.cuda(), align_corners=align,
+                                         out_dtype=torch.float32 if not align else dtype)
+        assert max_rel(got.float().cpu(), want) < tol
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 32, 192), (1, 9, 10, 23, 96), (1, 8, 8, 8, 1536), (1, 4, 6, 40, 72)])
+def test_depthwise_conv_tile_kernel_matches_register_kernel(shape):
+    """The shared-memory FHFMA kernel (bf16) against torch and against the register-tiled kernel (WF_DWCONV_IMPL=reg):
+    ragged tiles in every axis, partial channel groups (C % 64 != 0), more than one channel group."""
+    import os
+    from waveformer_b200 import ops
+    c = shape[-1]
+    x = seeded_randn(shape, 95).cuda().bfloat16()
+    w = (seeded_randn((c, 1, 3, 3, 3), 96) / 27 ** 0.5)
+    bias = (0.05 * seeded_randn((c,), 97)).cuda()
+    w27 = ops.repack_depthwise_weight(w.cuda())
+    got = ops.dwconv3d_channels_last(x, w27, bias)
+    os.environ["WF_DWCONV_IMPL"] = "reg"
+    try:
+        old = ops.dwconv3d_channels_last(x, w27, bias)
+    finally:
+        os.environ.pop("WF_DWCONV_IMPL", None)
+    want = F.conv3d(x.float().permute(0, 4, 1, 2, 3), w.cuda().bfloat16().float(), bias, padding=1, groups=c).permute(0, 2, 3, 4, 1)
+    assert max_rel(got.float().cpu(), want.cpu()) < 6e-3          # bf16 taps, fp32 accumulation, bf16 result
+    assert max_rel(got.float().cpu(), old.float().cpu()) < 8e-3   # register kernel keeps fp32 taps

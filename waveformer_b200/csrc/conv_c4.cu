@@ -39,7 +39,8 @@ template <typename TIN> __device__ __forceinline__ uint2 load_vox4(const TIN *p)
     }
 }
 
-// dynamic smem: [A image 14 * 2048][B image 14 * N * 16][staging 128 * (N + 8) * 2]
+// dynamic smem: [B image 14 * N * 16][A image 14 * 2048, re-used as the bf16 staging tile 128 * (N + 8) * 2 once the MMAs
+// of the tile have completed]
 template <typename TIN>
 __global__ void __launch_bounds__(128, 4) conv3d_c4_kernel(const TIN *__restrict__ x, const uint16_t *__restrict__ wpack,
                                                            __nv_bfloat16 *__restrict__ y0, int64_t ys0, int n0,
@@ -51,10 +52,10 @@ __global__ void __launch_bounds__(128, 4) conv3d_c4_kernel(const TIN *__restrict
     __shared__ uint32_t tmem_slot;
     const int N = n0 + n1;
     const int tid = threadIdx.x, warp = tid >> 5;
-    uint8_t *sA = smem;
-    uint8_t *sB = smem + kC4Chunks * 2048;
+    uint8_t *sB = smem;
+    uint8_t *sA = smem + (size_t)kC4Chunks * N * 16;
     const int pitch = N + 8;  // staging row pitch in elements (16-byte aligned rows, conflict-free 16-byte writes)
-    __nv_bfloat16 *sOut = reinterpret_cast<__nv_bfloat16 *>(sB + (size_t)kC4Chunks * N * 16);
+    __nv_bfloat16 *sOut = reinterpret_cast<__nv_bfloat16 *>(sA);
 
     if (warp == 0) tmem_alloc(&tmem_slot, tmem_cols);
     if (tid == 0) {
@@ -77,15 +78,23 @@ __global__ void __launch_bounds__(128, 4) conv3d_c4_kernel(const TIN *__restrict
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     const int64_t S = (int64_t)g.D * g.H * g.W;
 
-    double acc_s = 0.0, acc_q = 0.0;   // this thread's channel (tid < N), one batch element at a time
+    // statistics: thread t < N owns channel pair (t % (N/2)) for the rows of half (t / (N/2)) of every tile; fp32 per
+    // tile, fp64 across this CTA's tiles, one batch element at a time
+    const int half_n = N >> 1;
+    const int cpair = tid % half_n, rhalf = tid / half_n;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};   // sum c, sum c+1, sumsq c, sumsq c+1
     int64_t acc_b = -1;
     auto flush = [&]() {
         if (tid < N && acc_b >= 0) {
-            double *dst = tid < n0 ? sums0 + (acc_b * n0 + tid) * 2 : sums1 + (acc_b * n1 + (tid - n0)) * 2;
-            atomicAdd(dst, acc_s);
-            atomicAdd(dst + 1, acc_q);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int c = 2 * cpair + e;
+                double *dst = c < n0 ? sums0 + (acc_b * n0 + c) * 2 : sums1 + (acc_b * n1 + (c - n0)) * 2;
+                atomicAdd(dst, acc[e]);
+                atomicAdd(dst + 1, acc[2 + e]);
+            }
         }
-        acc_s = acc_q = 0.0;
+        acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
     };
 
     uint32_t phase = 0;
@@ -118,6 +127,7 @@ __global__ void __launch_bounds__(128, 4) conv3d_c4_kernel(const TIN *__restrict
                         tap[t] = in ? load_vox4<TIN>(base + (((int64_t)z2 * g.H + y2) * g.W + x2) * 4) : make_uint2(0u, 0u);
                     }
             tap[27] = make_uint2(0u, 0u);
+            __syncthreads();   // the previous tile's staging tile (same shared memory) has been stored and summed
 #pragma unroll
             for (int kc = 0; kc < kC4Chunks; ++kc)
                 *reinterpret_cast<uint4 *>(sA + kc * 2048 + tid * 16) =
@@ -125,7 +135,7 @@ __global__ void __launch_bounds__(128, 4) conv3d_c4_kernel(const TIN *__restrict
         }
         fence_proxy_async();
         tc_fence_before();
-        __syncthreads();   // A image complete; previous tile's staging fully consumed
+        __syncthreads();   // A image complete
         if (tid == 0) {
             tc_fence_after();
 #pragma unroll
@@ -152,7 +162,7 @@ __global__ void __launch_bounds__(128, 4) conv3d_c4_kernel(const TIN *__restrict
             dst[1] = hi;
         }
         tc_fence_before();
-        __syncthreads();   // staging complete; TMEM and the A image are free for the next tile
+        __syncthreads();   // staging complete; TMEM is free for the next tile
         // ---- coalesced stores: voxel rows of n0 (y0) and n1 (y1) channels ----
         const int64_t v0 = tile * 128;
         const int rows = (int)min((int64_t)128, g.total - v0);
@@ -168,31 +178,35 @@ __global__ void __launch_bounds__(128, 4) conv3d_c4_kernel(const TIN *__restrict
                 *reinterpret_cast<uint4 *>(y1 + (v0 + r) * ys1 + p * 8) = *reinterpret_cast<const uint4 *>(sOut + (size_t)r * pitch + n0 + p * 8);
             }
         }
-        // ---- statistics of the rounded outputs: thread t owns channel t ----
+        // ---- statistics of the rounded outputs ----
         if (tid < N) {
-            // a tile may straddle two batch elements only if S % 128 != 0; handle row by row in that (rare) case
+            // a tile may straddle two batch elements only if S % 128 != 0; handled row by row in that (rare) case
             const int64_t b_first = v0 / S, b_last = (v0 + rows - 1) / S;
+            const uint32_t *col = reinterpret_cast<const uint32_t *>(sOut) + cpair;
+            const int wpitch = pitch >> 1;
+            const int r0 = rhalf * 64, r1 = min(rows, r0 + 64);
             if (b_first == b_last) {
                 if (b_first != acc_b) { flush(); acc_b = b_first; }
-                float s = 0.f, q = 0.f;
-                for (int r = 0; r < rows; ++r) {
-                    const float f = __bfloat162float(sOut[(size_t)r * pitch + tid]);
-                    s += f;
-                    q = fmaf(f, f, q);
+                float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+                for (int r = r0; r < r1; ++r) {
+                    const uint32_t w = col[(size_t)r * wpitch];
+                    const float f0 = __uint_as_float(w << 16), f1 = __uint_as_float(w & 0xffff0000u);
+                    s0 += f0; s1 += f1;
+                    q0 = fmaf(f0, f0, q0); q1 = fmaf(f1, f1, q1);
                 }
-                acc_s += (double)s;
-                acc_q += (double)q;
+                acc[0] += (double)s0; acc[1] += (double)s1; acc[2] += (double)q0; acc[3] += (double)q1;
             } else {
-                for (int r = 0; r < rows; ++r) {
+                for (int r = r0; r < r1; ++r) {
                     const int64_t bb = (v0 + r) / S;
                     if (bb != acc_b) { flush(); acc_b = bb; }
-                    const float f = __bfloat162float(sOut[(size_t)r * pitch + tid]);
-                    acc_s += (double)f;
-                    acc_q += (double)f * f;
+                    const uint32_t w = col[(size_t)r * wpitch];
+                    const double f0 = (double)__uint_as_float(w << 16), f1 = (double)__uint_as_float(w & 0xffff0000u);
+                    acc[0] += f0; acc[1] += f1; acc[2] += f0 * f0; acc[3] += f1 * f1;
                 }
             }
         }
-        // the next iteration's first __syncthreads orders these staging reads before the next epilogue's writes
+        // the next iteration's first __syncthreads orders these staging reads before the next gather overwrites them
     }
     flush();
     tc_fence_before();
@@ -233,7 +247,8 @@ extern "C" int wf_conv3d_c4_in_stats(const void *x, int x_dtype, const void *wpa
     g.B = B; g.D = D; g.H = H; g.W = W;
     g.total = (int64_t)B * D * H * W;
     const int64_t ntiles = (g.total + 127) / 128;
-    const size_t smem = (size_t)kC4Chunks * 2048 + (size_t)kC4Chunks * N * 16 + (size_t)128 * (N + 8) * 2;
+    const size_t stage = (size_t)128 * (N + 8) * 2, aimg = (size_t)kC4Chunks * 2048;
+    const size_t smem = (size_t)kC4Chunks * N * 16 + (stage > aimg ? stage : aimg);
     uint32_t cols = 32;
     while ((int)cols < N) cols <<= 1;
     static bool attrs_done = false;

@@ -9,6 +9,8 @@
 //
 // x, y: [B, D, H, W, C] channels-last, dense; w27: fp32 [27][C] (tap-major repack of the [C,1,3,3,3] weight);
 // bias: fp32 [C] or NULL.  Accumulation in fp32.
+#include <stdlib.h>
+
 #include "wf_common.cuh"
 
 namespace wf {
@@ -105,6 +107,138 @@ __global__ void __launch_bounds__(256) dwconv3d_ndhwc_kernel(const T *__restrict
         if (x0 + o < W) CVec<T, VEC>::store(orow + (int64_t)(x0 + o) * C, acc[o]);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// bf16 fast path: shared-memory tile + mixed-precision FMA.
+//   CTA = output tile of TZ x TY x TX = 4 x 4 x 16 voxels x 64 channels; the 6 x 6 x 18 x 64 haloed input tile (81 KB,
+//   zero padded at the volume border) is staged once with cp.async; lane = one bf16x2 channel pair (a warp's 32 lanes
+//   read 128 contiguous bytes: conflict-free LDS.32), warp = one pair of adjacent output rows (z, y..y+1) walking along
+//   x with a 12-row x 3-column register window: 12 LDS.32 per 2 output voxels instead of 54 LDG.128 per 4.
+//   Taps are kept as 27 packed bf16x2 registers and applied with FHFMA (fma.rn.f32.bf16: both 16-bit operands are
+//   widened inside the fp32 FMA, no unpack instructions); accumulation is fp32.
+constexpr int kDwTZ = 4, kDwTY = 4, kDwTX = 16, kDwCG = 64;
+constexpr int kDwHZ = kDwTZ + 2, kDwHY = kDwTY + 2, kDwHX = kDwTX + 2;
+constexpr int kDwSmem = kDwHZ * kDwHY * kDwHX * kDwCG * 2;  // 82944
+
+__device__ __forceinline__ void fhfma2(float &a0, float &a1, uint32_t v, uint32_t w) {
+    // a0 += lo(v) * lo(w); a1 += hi(v) * hi(w)   (bf16 x bf16 + fp32, FHFMA.BF16)
+    asm("{\n\t.reg .b16 vl, vh, wl, wh;\n\tmov.b32 {vl, vh}, %2;\n\tmov.b32 {wl, wh}, %3;\n\t"
+        "fma.rn.f32.bf16 %0, vl, wl, %0;\n\tfma.rn.f32.bf16 %1, vh, wh, %1;\n\t}"
+        : "+f"(a0), "+f"(a1)
+        : "r"(v), "r"(w));
+}
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 2) dwconv3d_bf16_tile_kernel(const __nv_bfloat16 *__restrict__ x,
+                                                                    const float *__restrict__ w27,
+                                                                    const float *__restrict__ bias,
+                                                                    __nv_bfloat16 *__restrict__ y, int D, int H, int W,
+                                                                    int C, int tiles_x, int tiles_y, int tiles_z) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int t = blockIdx.x;
+    const int tx = t % tiles_x; t /= tiles_x;
+    const int ty = t % tiles_y; t /= tiles_y;
+    const int tz = t % tiles_z;
+    const int64_t b = t / tiles_z;
+    const int c0 = blockIdx.y * kDwCG;
+    const int x0 = tx * kDwTX, y0 = ty * kDwTY, z0 = tz * kDwTZ;
+    const int cchunks = min(8, (C - c0) >> 3);  // live 16-byte channel chunks of this group
+
+    // ---- stage the haloed tile: 6 * 6 * 18 voxels x 8 chunks of 16 bytes ----
+    const __nv_bfloat16 *xb = x + (int64_t)b * D * H * W * C + c0;
+    for (int i = tid; i < kDwHZ * kDwHY * kDwHX * 8; i += 256) {
+        const int ch = i & 7, v = i >> 3;
+        const int xi = v % kDwHX, yi = (v / kDwHX) % kDwHY, zi = v / (kDwHX * kDwHY);
+        const int gx = x0 - 1 + xi, gy = y0 - 1 + yi, gz = z0 - 1 + zi;
+        uint8_t *dst = smem + (size_t)v * 128 + ch * 16;
+        if (ch < cchunks && (unsigned)gx < (unsigned)W && (unsigned)gy < (unsigned)H && (unsigned)gz < (unsigned)D)
+            cp_async16(dst, xb + (((int64_t)gz * H + gy) * W + gx) * C + ch * 8);
+        else
+            *reinterpret_cast<uint4 *>(dst) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    // ---- this lane's taps (two channels) while the copies are in flight ----
+    const int c = c0 + 2 * lane;
+    const bool live_c = c < C;
+    uint32_t wt[27];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+        const float2 f = live_c ? __ldg(reinterpret_cast<const float2 *>(w27 + (int64_t)k * C + c)) : make_float2(0.f, 0.f);
+        __nv_bfloat162 h = __floats2bfloat162_rn(f.x, f.y);
+        wt[k] = *reinterpret_cast<uint32_t *>(&h);
+    }
+    float b0 = 0.f, b1 = 0.f;
+    if (bias != nullptr && live_c) {
+        const float2 f = __ldg(reinterpret_cast<const float2 *>(bias + c));
+        b0 = f.x; b1 = f.y;
+    }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    // ---- warp = output rows (z0 + zl, y0 + 2*yp) and (.., y0 + 2*yp + 1) ----
+    const int zl = warp >> 1, yp = warp & 1;
+    const uint32_t *tile = reinterpret_cast<const uint32_t *>(smem) + lane;
+    // input row r of the window: zi = zl + r / 4, yi = 2 * yp + r % 4   (halo coordinates)
+    auto ld = [&](int r, int xi) -> uint32_t {
+        const int zi = zl + (r >> 2), yi = 2 * yp + (r & 3);
+        return tile[((zi * kDwHY + yi) * kDwHX + xi) * 32];
+    };
+    uint32_t win[12][3];
+#pragma unroll
+    for (int r = 0; r < 12; ++r) {
+        win[r][0] = ld(r, 0);
+        win[r][1] = ld(r, 1);
+    }
+    const int gz = z0 + zl, gy = y0 + 2 * yp;
+    __nv_bfloat16 *yrow = y + ((((int64_t)b * D + gz) * H + gy) * W + x0) * C + c;
+    const bool row0 = gz < D && gy < H && live_c, row1 = gz < D && gy + 1 < H && live_c;
+#pragma unroll
+    for (int j = 0; j < kDwTX; ++j) {
+#pragma unroll
+        for (int r = 0; r < 12; ++r) win[r][(j + 2) % 3] = ld(r, j + 2);
+        float a00 = b0, a01 = b1, a10 = b0, a11 = b1;   // output row 0 / 1, channel 0 / 1
+#pragma unroll
+        for (int dz = 0; dz < 3; ++dz)
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    const uint32_t wv = wt[dz * 9 + dy * 3 + dx];
+                    fhfma2(a00, a01, win[dz * 4 + dy][(j + dx) % 3], wv);       // output row 0 reads window rows dy
+                    fhfma2(a10, a11, win[dz * 4 + dy + 1][(j + dx) % 3], wv);   // output row 1 reads window rows dy + 1
+                }
+        if (x0 + j < W) {
+            if (row0) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(a00, a01);
+                *reinterpret_cast<__nv_bfloat162 *>(yrow + (int64_t)j * C) = h;
+            }
+            if (row1) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(a10, a11);
+                *reinterpret_cast<__nv_bfloat162 *>(yrow + ((int64_t)W + j) * C) = h;
+            }
+        }
+    }
+}
+
+static int dwconv_bf16_tile_launch(const __nv_bfloat16 *x, const float *w27, const float *bias, __nv_bfloat16 *y, int B,
+                                   int D, int H, int W, int C, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        WF_CUDA_CHECK(cudaFuncSetAttribute(dwconv3d_bf16_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmem));
+        attr_done = true;
+    }
+    const int tiles_x = (W + kDwTX - 1) / kDwTX, tiles_y = (H + kDwTY - 1) / kDwTY, tiles_z = (D + kDwTZ - 1) / kDwTZ;
+    const int64_t tiles = (int64_t)B * tiles_x * tiles_y * tiles_z;
+    if (tiles > 0x7fffffff) return WF_ERR_UNSUPPORTED;
+    dim3 grid((unsigned)tiles, (unsigned)((C + kDwCG - 1) / kDwCG));
+    dwconv3d_bf16_tile_kernel<<<grid, 256, kDwSmem, st>>>(x, w27, bias, y, D, H, W, C, tiles_x, tiles_y, tiles_z);
+    WF_LAUNCH_CHECK();
+    return WF_OK;
+}
+
 template <typename T>
 static int dwconv_launch(const T *x, const float *w27, const float *bias, T *y, int B, int D, int H, int W, int C,
                          cudaStream_t st) {
@@ -132,7 +266,13 @@ extern "C" int wf_dwconv3d_ndhwc(const void *x, const float *w27, const float *b
     if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || C <= 0) return WF_ERR_BAD_SHAPE;
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == WF_F32) return wf::dwconv_launch<float>((const float *)x, w27, bias, (float *)y, B, D, H, W, C, st);
-    if (dtype == WF_BF16)
+    if (dtype == WF_BF16) {
+        // shared-memory tile kernel when the geometry gives it enough work; the register-tiled kernel otherwise
+        const char *impl = getenv("WF_DWCONV_IMPL");
+        const bool force_old = impl != nullptr && impl[0] == 'r';
+        if (!force_old && C % 8 == 0 && W >= 8 && wf::aligned16(x) && wf::aligned16(w27) && (bias == nullptr || wf::aligned16(bias)))
+            return wf::dwconv_bf16_tile_launch((const __nv_bfloat16 *)x, w27, bias, (__nv_bfloat16 *)y, B, D, H, W, C, st);
         return wf::dwconv_launch<__nv_bfloat16>((const __nv_bfloat16 *)x, w27, bias, (__nv_bfloat16 *)y, B, D, H, W, C, st);
+    }
     return WF_ERR_BAD_DTYPE;
 }

@@ -109,9 +109,122 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const TI *__restrict__ x
     }
 }
 
+// Wide variant (C % 8 == 0): a row is split into chunks of 8 channels; LPR lanes cooperate on a row and each lane owns
+// NCH chunks (chunk index = j * LPR + lane-in-row), i.e. 16-byte (bf16) / 2 x 16-byte (fp32) accesses, NCH * 8 values of
+// independent work per thread and log2(LPR) shuffle steps per statistic.  A warp covers 32 / LPR rows.
+template <typename TI, typename TO, int LPR, int NCH>
+__global__ void __launch_bounds__(256) layernorm_wide_kernel(const TI *__restrict__ x, const float *__restrict__ gamma,
+                                                             const float *__restrict__ beta, TO *__restrict__ y,
+                                                             __nv_bfloat16 *__restrict__ y2, int64_t rows, int C,
+                                                             int64_t xs, int64_t ys, float eps, int gelu) {
+    constexpr int RPB = 256 / LPR;
+    const int sub = threadIdx.x % LPR;
+    const int64_t row = (int64_t)blockIdx.x * RPB + threadIdx.x / LPR;
+    const bool live = row < rows;
+    const int chunks = C >> 3;
+    float v[NCH][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+        const int ch = j * LPR + sub;
+        if (live && ch < chunks) {
+            const TI *p = x + row * xs + ch * 8;
+            if constexpr (sizeof(TI) == 4) {
+                const float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + 4);
+                v[j][0] = a.x; v[j][1] = a.y; v[j][2] = a.z; v[j][3] = a.w; v[j][4] = b.x; v[j][5] = b.y; v[j][6] = b.z; v[j][7] = b.w;
+            } else {
+                Pack<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4 *>(p), v[j]);
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sum += v[j][e];
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[j][e] = 0.f;
+        }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)C;
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+        if (j * LPR + sub < chunks) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float d = v[j][e] - mean;
+                sq = fmaf(d, d, sq);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / (float)C + eps);
+    if (!live) return;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+        const int ch = j * LPR + sub;
+        if (ch >= chunks) continue;
+        float o8[8];
+        float g8[8], b8[8];
+        if (gamma != nullptr) {
+            const float4 ga = __ldg(reinterpret_cast<const float4 *>(gamma + ch * 8)), gb = __ldg(reinterpret_cast<const float4 *>(gamma + ch * 8 + 4));
+            g8[0] = ga.x; g8[1] = ga.y; g8[2] = ga.z; g8[3] = ga.w; g8[4] = gb.x; g8[5] = gb.y; g8[6] = gb.z; g8[7] = gb.w;
+            if (beta != nullptr) {
+                const float4 ba = __ldg(reinterpret_cast<const float4 *>(beta + ch * 8)), bb = __ldg(reinterpret_cast<const float4 *>(beta + ch * 8 + 4));
+                b8[0] = ba.x; b8[1] = ba.y; b8[2] = ba.z; b8[3] = ba.w; b8[4] = bb.x; b8[5] = bb.y; b8[6] = bb.z; b8[7] = bb.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) b8[e] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float t = (v[j][e] - mean) * rstd;
+            if (gamma != nullptr) t = fmaf(t, g8[e], b8[e]);
+            o8[e] = gelu ? gelu_erf(t) : t;
+        }
+        TO *q = y + row * ys + ch * 8;
+        if constexpr (sizeof(TO) == 4) {
+            reinterpret_cast<float4 *>(q)[0] = make_float4(o8[0], o8[1], o8[2], o8[3]);
+            reinterpret_cast<float4 *>(q)[1] = make_float4(o8[4], o8[5], o8[6], o8[7]);
+        } else {
+            *reinterpret_cast<uint4 *>(q) = Pack<__nv_bfloat16>::pack(o8);
+        }
+        if (y2 != nullptr) *reinterpret_cast<uint4 *>(y2 + row * (int64_t)C + ch * 8) = Pack<__nv_bfloat16>::pack(o8);
+    }
+}
+
+template <typename TI, typename TO>
+static bool layernorm_wide_launch(const TI *x, const float *gamma, const float *beta, TO *y, __nv_bfloat16 *y2, int64_t rows,
+                                  int C, int64_t xs, int64_t ys, float eps, int gelu, cudaStream_t st) {
+    if (C % 8 != 0 || (xs * sizeof(TI)) % 16 != 0 || (ys * sizeof(TO)) % 16 != 0 || !aligned16(x) || !aligned16(y) ||
+        (y2 != nullptr && !aligned16(y2)) || (gamma != nullptr && !aligned16(gamma)) || (beta != nullptr && !aligned16(beta)))
+        return false;
+    const int chunks = C / 8;
+#define WF_LNW(LPR_, NCH_)                                                                                            \
+    do {                                                                                                              \
+        const int rpb = 256 / LPR_;                                                                                   \
+        layernorm_wide_kernel<TI, TO, LPR_, NCH_><<<(unsigned)((rows + rpb - 1) / rpb), 256, 0, st>>>(                \
+            x, gamma, beta, y, y2, rows, C, xs, ys, eps, gelu);                                                       \
+        return true;                                                                                                  \
+    } while (0)
+    if (chunks <= 6) WF_LNW(2, 3);
+    if (chunks <= 12) WF_LNW(4, 3);
+    if (chunks <= 24) WF_LNW(8, 3);
+    if (chunks <= 48) WF_LNW(16, 3);
+    if (chunks <= 96) WF_LNW(32, 3);
+    if (chunks <= 192) WF_LNW(32, 6);
+#undef WF_LNW
+    return false;
+}
+
 template <typename TI, typename TO>
 static int layernorm_launch(const TI *x, const float *gamma, const float *beta, TO *y, __nv_bfloat16 *y2, int64_t rows,
                             int C, int64_t xs, int64_t ys, float eps, int gelu, cudaStream_t st) {
+    if (layernorm_wide_launch<TI, TO>(x, gamma, beta, y, y2, rows, C, xs, ys, eps, gelu, st)) {
+        WF_LAUNCH_CHECK();
+        return WF_OK;
+    }
     if (C % 4 != 0 || C > 2048) return WF_ERR_UNSUPPORTED;
     if ((xs * sizeof(TI)) % (sizeof(TI) == 4 ? 16 : 8) != 0 || (ys * sizeof(TO)) % (sizeof(TO) == 4 ? 16 : 8) != 0)
         return WF_ERR_MISALIGNED;

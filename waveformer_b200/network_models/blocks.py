@@ -101,7 +101,13 @@ class UnetResBlock(nn.Module):
             out = ops.instance_norm_act(self.conv1(inp), "leakyrelu", 0.01, eps=self.norm1.eps)
             out = self.conv2(out)
             if self.downsample:
-                return ops.instance_norm_act(out, "leakyrelu", 0.01, res=self.conv3(inp), res_norm=True, eps=self.norm2.eps,
+                c3 = self.conv3.conv
+                if c3.kernel_size == (1, 1, 1) and c3.stride == (1, 1, 1) and inp.stride(1) == 1:
+                    # the 1^3 shortcut is a per-voxel linear map: one GEMM on the channels-last view
+                    res = F.linear(inp.permute(0, 2, 3, 4, 1), c3.weight.view(c3.out_channels, c3.in_channels)).permute(0, 4, 1, 2, 3)
+                else:
+                    res = self.conv3(inp)
+                return ops.instance_norm_act(out, "leakyrelu", 0.01, res=res, res_norm=True, eps=self.norm2.eps,
                                              out=out_buf)
             return ops.instance_norm_act(out, "leakyrelu", 0.01, res=inp, eps=self.norm2.eps, out=out_buf)
         out = self.lrelu(self.norm1(self.conv1(inp)))

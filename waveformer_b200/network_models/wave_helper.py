@@ -408,25 +408,47 @@ class ProjectionUpsample(nn.Module):
             self._dw_cache = cache
         return cache[1], cache[2]
 
+    @staticmethod
+    def _pointwise(t: torch.Tensor, conv: nn.Conv3d, weight: torch.Tensor = None, bias: torch.Tensor = None):
+        """1^3 convolution of a channels-last tensor as one GEMM with the bias in its epilogue (the library's channels-
+        last convolution adds the bias in a second full pass)."""
+        w = conv.weight.view(conv.out_channels, conv.in_channels) if weight is None else weight
+        return F.linear(t, w, conv.bias if bias is None else bias)
+
+    def _forward_fused(self, x, out_buf):
+        xv = x.permute(0, 2, 3, 4, 1)                                    # channels-last view [B, d, h, w, C]
+        B = xv.shape[0]
+        size = tuple(int(v * self.stride) for v in x.shape[2:])
+        up = ops.upsample_trilinear_add([xv], size, align_corners=True)      # shared by both branches
+        dw = ops.dwconv3d_channels_last(up, *self._packed_dwconv())
+        # GroupNorm(num_groups = C) is a per-(sample, channel) affine map a * x + d of the depthwise result; it is folded
+        # into conv2 (W' = W diag(a), b' = b + W d) instead of being applied in a pass of its own
+        mr = ops.instance_norm_stats(dw.permute(0, 4, 1, 2, 3), eps=self.norm.eps).view(B, -1, 2)      # (mean, rstd)
+        a = mr[..., 1] * ops.f32_cached(self.norm.weight)                                      # [B, C]
+        d = ops.f32_cached(self.norm.bias) - mr[..., 0] * a
+        w2 = self.conv2.weight.view(self.conv2.out_channels, -1).float()
+        c_in, c_mid = dw.shape[-1], self.conv2.out_channels
+        h = torch.empty(dw.shape[:-1] + (c_mid,), dtype=dw.dtype, device=dw.device)
+        for i in range(B):
+            wi = (w2 * a[i][None, :]).to(dw.dtype)
+            bi = (self.conv2.bias.float() + w2 @ d[i]).to(dw.dtype)
+            torch.addmm(bi, dw[i].reshape(-1, c_in), wi.t(), out=h[i].view(-1, c_mid))
+        h = self.act(h)
+        if self.use_double_conv:
+            h = self._pointwise(self.conv3[1](self._pointwise(h, self.conv3[0])), self.conv3[2])
+        else:
+            h = self._pointwise(h, self.conv3)
+        dst = out_buf if out_buf is not None else torch.empty_like(h)
+        if self.do_res:
+            torch.add(h, self._pointwise(up, self.res_conv[1]), out=dst)
+        else:
+            dst.copy_(h)
+        return dst.permute(0, 4, 1, 2, 3)
+
     def forward(self, x, out_buf=None):
         """``out_buf`` (inference only): channels-last [B, D, H, W, C_out] destination (a slice of decoder1's input)."""
         if fused_path(x):
-            xv = x.permute(0, 2, 3, 4, 1)                                # channels-last view
-            size = tuple(int(v * self.stride) for v in x.shape[2:])
-            up = ops.upsample_trilinear_add([xv], size, align_corners=True)   # shared by both branches
-            dw = ops.dwconv3d_channels_last(up, *self._packed_dwconv())
-            # GroupNorm(num_groups = C) = InstanceNorm + affine
-            n = ops.instance_norm_act(dw.permute(0, 4, 1, 2, 3), "none", eps=self.norm.eps,
-                                      gamma=ops.f32_cached(self.norm.weight), beta=ops.f32_cached(self.norm.bias))
-            y = self.conv3(self.act(self.conv2(n)))
-            if out_buf is not None:
-                dst = out_buf.permute(0, 4, 1, 2, 3)
-                if self.do_res:
-                    return torch.add(y, self.res_conv[1](up.permute(0, 4, 1, 2, 3)), out=dst)
-                return dst.copy_(y)
-            if self.do_res:
-                y = y + self.res_conv[1](up.permute(0, 4, 1, 2, 3))
-            return y
+            return self._forward_fused(x, out_buf)
         up = self.conv1[0](x)          # one upsample shared by both branches (the reference computes it twice)
         dw = self.conv1[1](up)
         y = self.conv3(self.act(self.conv2(self.norm(dw))))

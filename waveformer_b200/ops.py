@@ -442,6 +442,13 @@ def _instnorm_stats(v: torch.Tensor, vs: int, eps: float) -> torch.Tensor:
     return mr
 
 
+def instance_norm_stats(x: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """(mean, rstd) per (sample, channel) of ``x[B, C, D, H, W]`` as a flat fp32 tensor [B * C * 2]."""
+    _need_cuda(x)
+    v, vs = _ndhwc_view(x)
+    return _instnorm_stats(v, vs, eps)
+
+
 def instance_norm_act(x: torch.Tensor, act: str = "none", slope: float = 0.01, res: Optional[torch.Tensor] = None,
                       res_norm: bool = False, eps: float = 1e-5, out: Optional[torch.Tensor] = None,
                       gamma: Optional[torch.Tensor] = None, beta: Optional[torch.Tensor] = None,
