@@ -141,6 +141,15 @@ int wf_instnorm_apply_ndhwc(const void *x, const float *mean_rstd, const void *r
                             int64_t S, int C, int64_t x_vox_stride, int64_t res_vox_stride, int64_t y_vox_stride,
                             void *stream);
 
+/* out[b, v, k] = head_b[k] + sum_c head_w[k, c] * act(norm(x)[b, v, c] + R): wf_instnorm_apply_ndhwc fused with the 1x1x1
+ * output convolution that is its only consumer (Waveformer.out, reference network_models/network_backbone.py:407;
+ * UnetOutBlock, monai/networks/blocks/dynunet_block.py:266), so the last C-channel activation is never written.
+ * head_w fp32 [K, C], head_b fp32 [K] or NULL, out [B, S, K] dense (out_dtype WF_F32, or WF_BF16 with dtype WF_BF16). */
+int wf_instnorm_apply_head_ndhwc(const void *x, const float *mean_rstd, const void *res, const float *res_mean_rstd,
+                                 const float *head_w, const float *head_b, void *out, int act, float slope, int dtype,
+                                 int out_dtype, int B, int64_t S, int C, int K, int64_t x_vox_stride,
+                                 int64_t res_vox_stride, void *stream);
+
 /* y[r, :] = LayerNorm(x[r, :C]) * gamma + beta (gamma / beta fp32 [C] or NULL), optionally followed by GELU(erf).
  * Rows are voxels of a channels-last tensor (row strides in elements); input and output storage types are independent.
  * y2_bf16 (optional, dense [rows, C]) receives the same result rounded to bf16: the GEMM operand, while y keeps the fp32
@@ -173,6 +182,15 @@ int wf_upsample_trilinear_add_ndhwc(const void *const *srcs, const int *src_dims
 int wf_conv3d_c4_in_stats(const void *x, int x_dtype, const void *wpack, void *y0, int64_t y0_vox_stride, int n0,
                           void *y1, int64_t y1_vox_stride, int n1, double *sums0, double *sums1, float *mean_rstd0,
                           float *mean_rstd1, float eps, int B, int D, int H, int W, void *stream);
+
+/* ConvTranspose3d(kernel 2, stride 2, no bias) on channels-last bf16 activations as one tensor-core GEMM whose epilogue
+ * writes every output voxel in place, e.g. into channels [0, Cout) of a concatenation buffer (y_vox_stride = 2 * Cout).
+ * Replaces UnetrUpBlock.transp_conv and the torch.cat that follows it (reference monai/networks/blocks/unetr_block.py:57-86,
+ * Waveformer.decoder1, network_models/network_backbone.py:405).
+ * x: [B, D, H, W, Cin] (voxel stride x_vox_stride); wpack: bf16 [8 * Cout, Cin], row (dz*4 + dy*2 + dx) * Cout + co holds
+ * w[:, co, dz, dy, dx]; y: [B, 2D, 2H, 2W, Cout] with voxel stride y_vox_stride.  Cin, Cout multiples of 16. */
+int wf_convtranspose3d_k2s2_ndhwc(const void *x, const void *wpack, void *y, int dtype, int B, int D, int H, int W, int Cin,
+                                  int Cout, int64_t x_vox_stride, int64_t y_vox_stride, void *stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Sliding-window stitching (re-hosted MONAI inferer, reference monai/inferers/utils.py:216-299).

@@ -159,3 +159,36 @@ def test_depthwise_conv_tile_kernel_matches_register_kernel(shape):
     want = F.conv3d(x.float().permute(0, 4, 1, 2, 3), w.cuda().bfloat16().float(), bias, padding=1, groups=c).permute(0, 2, 3, 4, 1)
     assert max_rel(got.float().cpu(), want.cpu()) < 6e-3          # bf16 taps, fp32 accumulation, bf16 result
     assert max_rel(got.float().cpu(), old.float().cpu()) < 8e-3   # register kernel keeps fp32 taps
+
+
+@pytest.mark.parametrize("shape,k", [((2, 48, 8, 12, 16), 4), ((1, 96, 5, 6, 7), 13), ((3, 16, 4, 4, 4), 2)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 8e-3)])
+@pytest.mark.parametrize("res_norm", [True, False])
+def test_instance_norm_act_with_fused_output_head(shape, k, dtype, tol, res_norm):
+    """act(IN(x) + IN(res) | res) -> 1^3 conv (+ bias) in one kernel vs the two-step torch computation."""
+    from waveformer_b200 import ops
+    x = seeded_randn(shape, 110).cuda().to(dtype).contiguous(memory_format=torch.channels_last_3d)
+    r = seeded_randn(shape, 111).cuda().to(dtype).contiguous(memory_format=torch.channels_last_3d)
+    w = (seeded_randn((k, shape[1], 1, 1, 1), 112) / shape[1] ** 0.5).cuda()
+    b = (0.1 * seeded_randn((k,), 113)).cuda()
+    got = ops.instance_norm_act_head(x, w, b, "leakyrelu", 0.01, res=r, res_norm=res_norm, out_dtype=torch.float32)
+    xc, rc = x.double().cpu(), r.double().cpu()                     # reference on the host in fp64 (no TF32 anywhere)
+    t = F.instance_norm(xc) + (F.instance_norm(rc) if res_norm else rc)
+    want = F.conv3d(F.leaky_relu(t, 0.01), w.double().cpu(), b.double().cpu())
+    assert got.dtype == torch.float32 and tuple(got.shape) == tuple(want.shape)
+    assert max_rel(got.cpu(), want) < tol
+
+
+@pytest.mark.parametrize("shape,cout", [((2, 8, 8, 16, 144), 48), ((1, 3, 5, 7, 32), 16), ((1, 4, 4, 4, 64), 64)])
+def test_conv_transpose_k2s2_scatters_into_concat_buffer(shape, cout):
+    """ConvTranspose3d(k=2, s=2) as one tcgen05 GEMM writing channels [0, Cout) of a wider channels-last buffer."""
+    from waveformer_b200 import ops
+    cin = shape[-1]
+    x = seeded_randn(shape, 120).cuda().bfloat16()
+    w = (seeded_randn((cin, cout, 2, 2, 2), 121) / cin ** 0.5).cuda().bfloat16()
+    B, D, H, W, _ = shape
+    cat = torch.full((B, 2 * D, 2 * H, 2 * W, 2 * cout), 7.0, dtype=torch.bfloat16, device="cuda")
+    ops.conv_transpose3d_k2s2(x, w, out=cat[..., :cout])
+    want = F.conv_transpose3d(x.float().permute(0, 4, 1, 2, 3), w.float(), stride=2).permute(0, 2, 3, 4, 1)
+    assert max_rel(cat[..., :cout].float().cpu(), want.cpu()) < 6e-3
+    assert bool((cat[..., cout:] == 7.0).all())                      # the skip half is untouched

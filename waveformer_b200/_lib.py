@@ -33,9 +33,11 @@ SIGNATURES = {
     "wf_dwconv3d_ndhwc": (_I, [_VOIDP, _VOIDP, _VOIDP, _VOIDP, _I, _I, _I, _I, _I, _I, _VOIDP]),
     "wf_instnorm_stats_ndhwc": (_I, [_VOIDP, _VOIDP, _VOIDP, _I, _I, _I64, _I, _I64, _F, _VOIDP]),
     "wf_instnorm_apply_ndhwc": (_I, [_VOIDP] * 7 + [_I, _F, _I, _I, _I64, _I, _I64, _I64, _I64, _VOIDP]),
+    "wf_instnorm_apply_head_ndhwc": (_I, [_VOIDP] * 7 + [_I, _F, _I, _I, _I, _I64, _I, _I, _I64, _I64, _VOIDP]),
     "wf_layernorm_ndhwc": (_I, [_VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _I, _I, _I64, _I, _I64, _I64, _F, _I, _VOIDP]),
     "wf_upsample_trilinear_add_ndhwc": (_I, [_VOIDP, _VOIDP, _I, _VOIDP, _VOIDP, _I, _I, _I, _I, _I, _I, _I, _I, _I64, _I64, _VOIDP]),
     "wf_conv3d_c4_in_stats": (_I, [_VOIDP, _I, _VOIDP, _VOIDP, _I64, _I, _VOIDP, _I64, _I, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _F, _I, _I, _I, _I, _VOIDP]),
+    "wf_convtranspose3d_k2s2_ndhwc": (_I, [_VOIDP, _VOIDP, _VOIDP, _I, _I, _I, _I, _I, _I, _I, _I64, _I64, _VOIDP]),
     "wf_sw_gather": (_I, [_VOIDP, _VOIDP, _VOIDP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VOIDP]),
     "wf_sw_accumulate": (_I, [_VOIDP] * 6 + [_F, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VOIDP]),
     "wf_sw_finalize": (_I, [_VOIDP, _VOIDP, _VOIDP, _I, _VOIDP, _VOIDP, _VOIDP, _F] + [_I] * 8 + [_VOIDP]),

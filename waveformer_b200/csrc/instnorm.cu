@@ -130,6 +130,103 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(const T *__restrict
     NVec<T, VEC>::store(y + vox * ys + c0, f);
 }
 
+// Last block of the network: y = act((x - mean) * rstd + [(r - mean_r) * rstd_r | r]) is consumed only by the 1x1x1
+// output convolution (Waveformer.out, reference network_models/network_backbone.py:407 -> UnetOutBlock,
+// monai/networks/blocks/dynunet_block.py:266), so the C-channel activation is never written: each lane normalises one
+// 16-byte channel packet, multiplies it with its slice of the [K, C] head weight, the packets of a voxel are summed
+// through shared memory and one thread per voxel stores the K logits.
+//   block = 32 voxels x cpv packets (cpv = C / VEC), persistent over voxel groups; KP = padded K (4, 8 or 16).
+template <typename T, typename TO, int KP>
+__global__ void __launch_bounds__(1024) instnorm_apply_head_kernel(const T *__restrict__ x, const float *__restrict__ mr,
+                                                                   const T *__restrict__ res, const float *__restrict__ res_mr,
+                                                                   const float *__restrict__ hw, const float *__restrict__ hb,
+                                                                   TO *__restrict__ out, int64_t S, int64_t total_vox, int C,
+                                                                   int K, int cpv, int64_t xs, int64_t rs, int act, float slope) {
+    constexpr int VEC = Pack<T>::VEC;
+    extern __shared__ float part[];  // [32 * cpv][KP]
+    const int tid = threadIdx.x;
+    const int vl = tid / cpv, cv = tid - vl * cpv;   // voxel in the group, channel packet
+    const int c0 = cv * VEC;
+    float w[KP][VEC];
+#pragma unroll
+    for (int k = 0; k < KP; ++k)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) w[k][e] = k < K ? __ldg(hw + (int64_t)k * C + c0 + e) : 0.f;
+    const int64_t groups = (total_vox + 31) / 32;
+    for (int64_t g = blockIdx.x; g < groups; g += gridDim.x) {
+        const int64_t vox = g * 32 + vl;
+        float p[KP];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) p[k] = 0.f;
+        if (vox < total_vox) {
+            const int64_t b = vox / S;
+            float f[VEC];
+            NVec<T, VEC>::load(x + vox * xs + c0, f);
+            const float *m = mr + ((int64_t)b * C + c0) * 2;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) f[e] = (f[e] - __ldg(m + 2 * e)) * __ldg(m + 2 * e + 1);
+            if (res != nullptr) {
+                float r[VEC];
+                NVec<T, VEC>::load(res + vox * rs + c0, r);
+                if (res_mr != nullptr) {
+                    const float *m2 = res_mr + ((int64_t)b * C + c0) * 2;
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) r[e] = (r[e] - __ldg(m2 + 2 * e)) * __ldg(m2 + 2 * e + 1);
+                }
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) f[e] += r[e];
+            }
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                if (act == 1) f[e] = fmaxf(f[e], 0.f);
+                else if (act == 2) f[e] = f[e] > 0.f ? f[e] : f[e] * slope;
+            }
+#pragma unroll
+            for (int k = 0; k < KP; ++k)
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) p[k] = fmaf(f[e], w[k][e], p[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < KP; ++k) part[(size_t)tid * KP + k] = p[k];
+        __syncthreads();
+        if (tid < 32 && g * 32 + tid < total_vox) {
+            float o[KP];
+#pragma unroll
+            for (int k = 0; k < KP; ++k) o[k] = (hb != nullptr && k < K) ? __ldg(hb + k) : 0.f;
+            for (int j = 0; j < cpv; ++j)
+#pragma unroll
+                for (int k = 0; k < KP; ++k) o[k] += part[((size_t)tid * cpv + j) * KP + k];
+            TO *dst = out + (g * 32 + tid) * (int64_t)K;
+            for (int k = 0; k < K; ++k) dst[k] = from_f32<TO>(o[k]);
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T, typename TO>
+static int apply_head_launch(const T *x, const float *mr, const T *res, const float *res_mr, const float *hw, const float *hb,
+                             TO *out, int B, int64_t S, int C, int K, int64_t xs, int64_t rs, int act, float slope,
+                             cudaStream_t st) {
+    constexpr int V = Pack<T>::VEC;
+    const size_t e = sizeof(T);
+    if (C % V != 0 || C / V > 32 || K < 1 || K > 16) return WF_ERR_UNSUPPORTED;
+    if (!aligned16(x) || (xs * e) % 16 != 0 || (res != nullptr && (!aligned16(res) || (rs * e) % 16 != 0))) return WF_ERR_MISALIGNED;
+    const int cpv = C / V;
+    const int threads = 32 * cpv;
+    const int64_t total = (int64_t)B * S;
+    const int64_t groups = (total + 31) / 32;
+    const int per_sm = 2048 / threads > 0 ? 2048 / threads : 1;
+    const unsigned grid = (unsigned)min(groups, (int64_t)kNumSMs * per_sm);
+#define WF_HEAD(KP_) instnorm_apply_head_kernel<T, TO, KP_><<<grid, threads, (size_t)threads * KP_ * sizeof(float), st>>>( \
+        x, mr, res, res_mr, hw, hb, out, S, total, C, K, cpv, xs, rs, act, slope)
+    if (K <= 4) WF_HEAD(4);
+    else if (K <= 8) WF_HEAD(8);
+    else WF_HEAD(16);
+#undef WF_HEAD
+    WF_LAUNCH_CHECK();
+    return WF_OK;
+}
+
 template <typename T>
 static int stats_launch(const T *x, double *sums, float *mr, int B, int64_t S, int C, int64_t xs, float eps, cudaStream_t st) {
     constexpr int V = Pack<T>::VEC;
@@ -196,5 +293,26 @@ extern "C" int wf_instnorm_apply_ndhwc(const void *x, const float *mean_rstd, co
     if (dtype == WF_BF16)
         return wf::apply_launch<__nv_bfloat16>((const __nv_bfloat16 *)x, mean_rstd, (const __nv_bfloat16 *)res, res_mean_rstd,
                                                (__nv_bfloat16 *)y, B, S, C, x_vox_stride, res_vox_stride, y_vox_stride, act, slope, gamma, beta, st);
+    return WF_ERR_BAD_DTYPE;
+}
+
+extern "C" int wf_instnorm_apply_head_ndhwc(const void *x, const float *mean_rstd, const void *res, const float *res_mean_rstd,
+                                            const float *head_w, const float *head_b, void *out, int act, float slope,
+                                            int dtype, int out_dtype, int B, int64_t S, int C, int K, int64_t x_vox_stride,
+                                            int64_t res_vox_stride, void *stream) {
+    if (!x || !mean_rstd || !head_w || !out) return WF_ERR_NULL_POINTER;
+    if (B <= 0 || S <= 0 || C <= 0 || x_vox_stride < C || (res && res_vox_stride < C)) return WF_ERR_BAD_SHAPE;
+    if (act < 0 || act > 2) return WF_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    using bf = __nv_bfloat16;
+    if (dtype == WF_F32 && out_dtype == WF_F32)
+        return wf::apply_head_launch<float, float>((const float *)x, mean_rstd, (const float *)res, res_mean_rstd, head_w, head_b,
+                                                   (float *)out, B, S, C, K, x_vox_stride, res_vox_stride, act, slope, st);
+    if (dtype == WF_BF16 && out_dtype == WF_F32)
+        return wf::apply_head_launch<bf, float>((const bf *)x, mean_rstd, (const bf *)res, res_mean_rstd, head_w, head_b,
+                                                (float *)out, B, S, C, K, x_vox_stride, res_vox_stride, act, slope, st);
+    if (dtype == WF_BF16 && out_dtype == WF_BF16)
+        return wf::apply_head_launch<bf, bf>((const bf *)x, mean_rstd, (const bf *)res, res_mean_rstd, head_w, head_b,
+                                             (bf *)out, B, S, C, K, x_vox_stride, res_vox_stride, act, slope, st);
     return WF_ERR_BAD_DTYPE;
 }

@@ -85,9 +85,11 @@ class UnetResBlock(nn.Module):
                 and self.conv3.conv.stride == (1, 1, 1) and self.norm1.eps == self.norm3.eps
                 and inp.dtype in (torch.float32, torch.bfloat16))
 
-    def forward(self, inp: torch.Tensor, out_buf: torch.Tensor = None) -> torch.Tensor:
+    def forward(self, inp: torch.Tensor, out_buf: torch.Tensor = None, head=None) -> torch.Tensor:
         """``out_buf`` (inference only): a [B, D, H, W, C] channels-last destination - typically the skip half of a
-        decoder's concatenation buffer - the block's last kernel writes into (the torch.cat copy disappears)."""
+        decoder's concatenation buffer - the block's last kernel writes into (the torch.cat copy disappears).
+        ``head`` (inference only) = (weight [K, C, 1, 1, 1], bias, out_dtype) of a 1^3 convolution that is the block's only
+        consumer: the last kernel then emits the K-channel result and the block's own output is never stored."""
         if use_fused(inp) and self._c4_fused(inp):
             # 4-channel input (the network's first block): conv1, the 1^3 shortcut conv3 and both InstanceNorm statistics
             # in one tcgen05 kernel (the library convolution needs 3.3 ms for this K = 108 problem)
@@ -107,8 +109,14 @@ class UnetResBlock(nn.Module):
                     res = F.linear(inp.permute(0, 2, 3, 4, 1), c3.weight.view(c3.out_channels, c3.in_channels)).permute(0, 4, 1, 2, 3)
                 else:
                     res = self.conv3(inp)
+                if head is not None:
+                    return ops.instance_norm_act_head(out, head[0], head[1], "leakyrelu", 0.01, res=res, res_norm=True,
+                                                      eps=self.norm2.eps, out_dtype=head[2])
                 return ops.instance_norm_act(out, "leakyrelu", 0.01, res=res, res_norm=True, eps=self.norm2.eps,
                                              out=out_buf)
+            if head is not None:
+                return ops.instance_norm_act_head(out, head[0], head[1], "leakyrelu", 0.01, res=inp, eps=self.norm2.eps,
+                                                  out_dtype=head[2])
             return ops.instance_norm_act(out, "leakyrelu", 0.01, res=inp, eps=self.norm2.eps, out=out_buf)
         out = self.lrelu(self.norm1(self.conv1(inp)))
         out = self.norm2(self.conv2(out))
@@ -154,15 +162,24 @@ class UnetrUpBlock(nn.Module):
         cls = UnetResBlock if res_block else UnetBasicBlock
         self.conv_block = cls(spatial_dims, 2 * out_channels, out_channels, kernel_size, 1, norm_name)
 
-    def forward(self, inp: torch.Tensor, skip: torch.Tensor, cat_buf: torch.Tensor = None) -> torch.Tensor:
+    def forward(self, inp: torch.Tensor, skip: torch.Tensor, cat_buf: torch.Tensor = None, head=None) -> torch.Tensor:
         """``cat_buf`` (inference only): [B, D, H, W, 2C] channels-last buffer whose channels [C, 2C) already hold
         ``skip`` (written there by its producer); only the upsampled half is copied in."""
-        up = self.transp_conv(inp)
+        tc = self.transp_conv.conv
         if cat_buf is not None:
-            c = up.shape[1]
-            cat_buf[..., :c].copy_(up.permute(0, 2, 3, 4, 1))
-            return self.conv_block(cat_buf.permute(0, 4, 1, 2, 3))
-        return self.conv_block(torch.cat((up, skip), dim=1))
+            c = tc.out_channels
+            if (inp.dtype == torch.bfloat16 and tc.kernel_size == (2, 2, 2) and tc.stride == (2, 2, 2) and tc.bias is None
+                    and tc.in_channels % 16 == 0 and c % 16 == 0 and tc.in_channels <= 512 and inp.stride(1) == 1):
+                # kernel == stride: one tensor-core GEMM that scatters its result into the concat buffer in place
+                ops.conv_transpose3d_k2s2(inp.permute(0, 2, 3, 4, 1), tc.weight, out=cat_buf[..., :c])
+            else:
+                cat_buf[..., :c].copy_(self.transp_conv(inp).permute(0, 2, 3, 4, 1))
+            merged = cat_buf.permute(0, 4, 1, 2, 3)
+            if head is not None and isinstance(self.conv_block, UnetResBlock):
+                return self.conv_block(merged, None, head)
+            y = self.conv_block(merged)
+            return y if head is None else F.conv3d(y, head[0], head[1]).to(head[2] or y.dtype)
+        return self.conv_block(torch.cat((self.transp_conv(inp), skip), dim=1))
 
 
 class UnetOutBlock(nn.Module):

@@ -154,7 +154,9 @@ class Waveformer(nn.Module):
         self.decoder2(dec5, enc1, outs_hf[-3], cat_buf=cat2, out_buf=comb[..., 2 * f[0]:])
         self.learnable_up4(dec4, out_buf=comb[..., :f[0]])
         self.learnable_up3(dec3, out_buf=comb[..., f[0]:2 * f[0]])
-        return self.out(self.decoder1(comb.permute(0, 4, 1, 2, 3), enc0, cat_buf=cat1))
+        oc = self.out.conv.conv
+        head = (oc.weight, oc.bias, getattr(self, "logits_dtype", None) or dtype)    # the 1^3 output conv rides the last kernel
+        return self.decoder1(comb.permute(0, 4, 1, 2, 3), enc0, cat_buf=cat1, head=head)
 
 
 def create_waveformer(network_config: dict) -> Waveformer:

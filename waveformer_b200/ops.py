@@ -482,6 +482,75 @@ def instance_norm_act(x: torch.Tensor, act: str = "none", slope: float = 0.01, r
     return out.permute(0, 4, 1, 2, 3)
 
 
+def instance_norm_act_head(x: torch.Tensor, head_w: torch.Tensor, head_b: Optional[torch.Tensor], act: str = "none",
+                           slope: float = 0.01, res: Optional[torch.Tensor] = None, res_norm: bool = False,
+                           eps: float = 1e-5, stats: Optional[torch.Tensor] = None,
+                           res_stats: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """``conv1x1(act(InstanceNorm(x) + R))`` for ``x[B, C, D, H, W]``: the normalised activation is consumed in registers
+    and only the ``K`` logits are stored.  ``head_w``: the [K, C, 1, 1, 1] weight.  Returns [B, K, D, H, W] with
+    channels-last-3d strides, ``out_dtype`` (default fp32)."""
+    dev = _need_cuda(x, res, head_w, head_b)
+    v, vs = _ndhwc_view(x)
+    B, D, H, W, C = v.shape
+    K = head_w.shape[0]
+    mr = stats if stats is not None else _instnorm_stats(v, vs, eps)
+    rv, rs, rmr = None, C, None
+    if res is not None:
+        if res.shape != x.shape or res.dtype != x.dtype:
+            raise ValueError("residual must match x")
+        rv, rs = _ndhwc_view(res)
+        if res_norm:
+            rmr = res_stats if res_stats is not None else _instnorm_stats(rv, rs, eps)
+    odt = out_dtype or torch.float32
+    out = torch.empty((B, D, H, W, K), dtype=odt, device=dev)
+    hw = f32_cached(head_w).reshape(K, C)
+    with torch.cuda.device(dev):
+        st = _lib.lib().wf_instnorm_apply_head_ndhwc(v.data_ptr(), mr.data_ptr(), _ptr(rv), _ptr(rmr), hw.data_ptr(),
+                                                     _ptr(f32_cached(head_b)), out.data_ptr(), _ACT[act], float(slope),
+                                                     _dtype_code(x), _dtype_code(out), B, D * H * W, C, K, vs, rs,
+                                                     _stream(dev))
+    _lib.check(st, "wf_instnorm_apply_head_ndhwc")
+    _count()
+    return out.permute(0, 4, 1, 2, 3)
+
+
+_CT_PACK = {}
+
+
+def conv_transpose3d_k2s2(x: torch.Tensor, weight: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """ConvTranspose3d(k=2, s=2, bias=False) of channels-last bf16 ``x[B, D, H, W, Cin]`` with ``weight[Cin, Cout, 2, 2, 2]``
+    into ``out[B, 2D, 2H, 2W, Cout]`` (may be a channel slice of a wider channels-last buffer)."""
+    dev = _need_cuda(x, weight, out)
+    if x.dtype != torch.bfloat16 or x.dim() != 5:
+        raise ValueError("conv_transpose3d_k2s2 takes channels-last bf16 [B, D, H, W, Cin]")
+    xs = _voxel_stride(x)
+    if xs is None:
+        x = x.contiguous()
+        xs = x.shape[-1]
+    B, D, H, W, Cin = x.shape
+    if tuple(weight.shape[2:]) != (2, 2, 2) or weight.shape[0] != Cin:
+        raise ValueError("weight must be [Cin, Cout, 2, 2, 2]")
+    Cout = weight.shape[1]
+    key = id(weight)
+    tag = (weight._version, weight.data_ptr(), weight.dtype)
+    hit = _CT_PACK.get(key)
+    if hit is None or hit[0]() is not weight or hit[1] != tag:
+        pack = weight.detach().permute(2, 3, 4, 1, 0).reshape(8 * Cout, Cin).to(torch.bfloat16).contiguous()
+        hit = (weakref.ref(weight), tag, pack)
+        _CT_PACK[key] = hit
+    if out is None:
+        out = torch.empty((B, 2 * D, 2 * H, 2 * W, Cout), dtype=x.dtype, device=dev)
+    ys = _voxel_stride(out)
+    if ys is None or tuple(out.shape) != (B, 2 * D, 2 * H, 2 * W, Cout) or out.dtype != x.dtype:
+        raise ValueError("out must be a voxel-dense [B, 2D, 2H, 2W, Cout] bf16 tensor")
+    with torch.cuda.device(dev):
+        st = _lib.lib().wf_convtranspose3d_k2s2_ndhwc(x.data_ptr(), hit[2].data_ptr(), out.data_ptr(), 1, B, D, H, W, Cin,
+                                                      Cout, xs, ys, _stream(dev))
+    _lib.check(st, "wf_convtranspose3d_k2s2_ndhwc")
+    _count()
+    return out
+
+
 _C4_PACK = {}
 
 

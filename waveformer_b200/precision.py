@@ -77,6 +77,7 @@ def prepare_inference(model: nn.Module, dtype: torch.dtype = torch.bfloat16, *, 
             m.hf_dtype = torch.bfloat16                 # detail bands go to the bf16 decoder
         elif isinstance(m, MultiscaleTransformer):
             m.out_dtype = torch.bfloat16                # stage outputs feed the bf16 conv blocks
+    model.logits_dtype = torch.float32                  # the fused output head stores its fp32 accumulators
     for t in list(model.parameters()) + list(model.buffers()):
         if t.is_floating_point():
             t.data = t.data.float() if id(t) in keep else t.data.to(torch.bfloat16)
