@@ -154,8 +154,19 @@ def kernel_rooflines(pk):
     return out
 
 
+def host_threads() -> int:
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which would cripple the CPU arm)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def cpu_patch_seconds(steps: int, warmup: int):
     """The reference algorithm (oracle port, fp32) on the host cores: one 128^3 window forward per step."""
+    host_threads()
     from oracle.model import waveformer_forward
     from oracle.state import ModelConfig, make_state_dict
     cfg = ModelConfig(img_size=ROI)
@@ -177,7 +188,7 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = torch.get_num_threads()
+    cores = host_threads()
     sec = cpu_patch_seconds(args.steps, args.warmup)
     value = VOXELS / (WINDOWS_PER_VOLUME * sec)
     sample = "1 of 18 windows per step: one 1x4x128^3 fp32 forward of the oracle port; volume time = 18 x patch time"
@@ -320,7 +331,7 @@ def main():
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         sec = cpu_patch_seconds(1, 1)
-        cpu = dict(value=VOXELS / (WINDOWS_PER_VOLUME * sec), unit="voxels/s", cores=torch.get_num_threads(), kind="port",
+        cpu = dict(value=VOXELS / (WINDOWS_PER_VOLUME * sec), unit="voxels/s", cores=host_threads(), kind="port",
                    sample="1 of 18 windows: one 1x4x128^3 fp32 forward of the oracle port (1 warm-up + 1 timed), "
                           "volume time = 18 x patch time", patch_seconds=sec)
     line = dict(metric="sliding_window_voxels_per_s", value=value, unit="voxels/s", n_gpus=world, steps=args.steps,

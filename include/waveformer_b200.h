@@ -135,10 +135,11 @@ int wf_instnorm_stats_ndhwc(const void *x, double *sums, float *mean_rstd, int d
 /* y = act(((x - mean) * rstd) * gamma + beta + R) with R = 0 (res NULL), res (res_mean_rstd NULL) or
  * (res - mean_r) * rstd_r; gamma / beta (fp32 [C]) optional.  act: 0 none, 1 ReLU, 2 LeakyReLU(slope).
  * Fuses norm + residual add + activation of dynunet_block.py:100-110; with gamma / beta it is GroupNorm(num_groups = C)
- * of ProjectionUpsample.norm (reference network_models/wave_helper.py:59,74). */
+ * of ProjectionUpsample.norm (reference network_models/wave_helper.py:59,74).  x and res share `dtype`; y_dtype is `dtype`, or
+ * WF_BF16 with dtype WF_F32 (a block kept in fp32 / TF32 by the precision policy writing into a bf16 concat buffer). */
 int wf_instnorm_apply_ndhwc(const void *x, const float *mean_rstd, const void *res, const float *res_mean_rstd,
-                            const float *gamma, const float *beta, void *y, int act, float slope, int dtype, int B,
-                            int64_t S, int C, int64_t x_vox_stride, int64_t res_vox_stride, int64_t y_vox_stride,
+                            const float *gamma, const float *beta, void *y, int act, float slope, int dtype, int y_dtype,
+                            int B, int64_t S, int C, int64_t x_vox_stride, int64_t res_vox_stride, int64_t y_vox_stride,
                             void *stream);
 
 /* out[b, v, k] = head_b[k] + sum_c head_w[k, c] * act(norm(x)[b, v, c] + R): wf_instnorm_apply_ndhwc fused with the 1x1x1

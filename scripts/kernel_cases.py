@@ -1,0 +1,69 @@
+#!/usr/bin/env python
+"""Run ONE hand-written kernel on its production geometry a few times (the command `ncu --set full` wraps).
+
+    python scripts/kernel_cases.py --case haar|c4|dwconv|attn|layernorm|convt|head [--iters 3]
+Prints the CUDA-event time per call (a number printed under ncu is not a bench value).
+"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from waveformer_b200 import ops  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--case", required=True)
+ap.add_argument("--iters", type=int, default=3)
+args = ap.parse_args()
+g = torch.Generator("cuda").manual_seed(0)
+rn = lambda *s: torch.randn(*s, device="cuda", generator=g)  # noqa: E731
+
+if args.case == "haar":      # BASELINE configs[1]
+    x = rn(2, 48, 128, 128, 128).bfloat16()
+    ll, hf = ops._dwt_ncdhw_raw(x, True)
+    fns = {"dwt3d_ncdhw_bf16": lambda: ops._dwt_ncdhw_raw(x, True), "idwt3d_ncdhw_bf16": lambda: ops._idwt_ncdhw_raw(ll, hf)}
+elif args.case == "c4":      # encoder1: 2 x 4 x 128^3 fp32 window -> conv1 + conv3 + statistics
+    x = rn(2, 4, 128, 128, 128).contiguous(memory_format=torch.channels_last_3d)
+    w1, w3 = (rn(48, 4, 3, 3, 3) * 0.1).bfloat16(), (rn(48, 4, 1, 1, 1) * 0.5).bfloat16()
+    fns = {"conv3d_c4_in_stats": lambda: ops.conv3d_c4_in_stats(x, w1, w3)}
+elif args.case == "dwconv":  # CCF_FFN stage 1: 2 x 64^3 x 192
+    x = rn(2, 64, 64, 64, 192).bfloat16()
+    w27, b = rn(27, 192) * 0.2, rn(192) * 0.05
+    fns = {"dwconv3d_bf16_tile": lambda: ops.dwconv3d_channels_last(x, w27, b)}
+elif args.case == "layernorm":
+    x = rn(2 * 64 ** 3, 192).bfloat16()
+    gam, bet = 1 + 0.1 * rn(192), 0.1 * rn(192)
+    fns = {"layernorm_gelu_192_bf16": lambda: ops.layer_norm_cl(x, gam, bet, 1e-5, gelu=True)}
+elif args.case == "convt":   # decoder1.transp_conv: 144 -> 48, 64^3 -> 128^3 into the 96-channel concat buffer
+    x = rn(2, 64, 64, 64, 144).bfloat16()
+    w = (rn(144, 48, 2, 2, 2) / 12).bfloat16()
+    cat = torch.empty(2, 128, 128, 128, 96, device="cuda", dtype=torch.bfloat16)
+    fns = {"convtranspose_k2s2": lambda: ops.conv_transpose3d_k2s2(x, w, out=cat[..., :48])}
+elif args.case == "head":    # decoder1's last kernel: IN + IN(res) + lrelu + 1x1 head, 2 x 128^3 x 48 -> 4
+    x = rn(2, 128, 128, 128, 48).bfloat16().permute(0, 4, 1, 2, 3)
+    r = rn(2, 128, 128, 128, 48).bfloat16().permute(0, 4, 1, 2, 3)
+    w, b = rn(4, 48, 1, 1, 1) / 7, rn(4) * 0.1
+    fns = {"instnorm_apply_head": lambda: ops.instance_norm_act_head(x, w, b, "leakyrelu", 0.01, res=r, res_norm=True)}
+elif args.case == "attn":    # stage-1 level-1 attention at sw_batch 2
+    from waveformer_b200.network_models import Attention
+    att = Attention(48, num_heads=3, qkv_bias=True, window_size=8).cuda().eval()
+    att.compute_dtype, att.out_dtype = torch.float16, torch.float32
+    x = rn(2, 32, 32, 32, 48)
+    fns = {"window_attention_s1L1": lambda: att.forward_grid(x)}
+else:
+    raise SystemExit("unknown case")
+
+with torch.no_grad():
+    for name, fn in fns.items():
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.iters):
+            fn()
+        b_.record()
+        torch.cuda.synchronize()
+        print(f"{name}: {a.elapsed_time(b_) / args.iters * 1e3:.1f} us per call")

@@ -18,34 +18,66 @@ namespace wf {
 
 using namespace tc;
 
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+
 __global__ void __launch_bounds__(128) convT_k2s2_kernel(const __nv_bfloat16 *__restrict__ x, const uint16_t *__restrict__ wp,
                                                          __nv_bfloat16 *__restrict__ y, int64_t M, int K, int NT, int Cout,
                                                          int D, int H, int W, int64_t xs, int64_t ys, uint32_t tmem_cols) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_slot;
+    __shared__ int64_t s_ov[128];   // output voxel index of position (0, 0, 0) for each input voxel of the tile; -1 = none
     const int tid = threadIdx.x, warp = tid >> 5;
     const int kchunks = K >> 3;
+    {
+        const int64_t mm = (int64_t)blockIdx.x * 128 + tid;
+        int64_t ov = -1;
+        if (mm < M) {   // M < 2^31 (host check): 32-bit divisions
+            const uint32_t v32 = (uint32_t)mm;
+            const uint32_t t = v32 / (uint32_t)W, xx = v32 - t * (uint32_t)W;
+            const uint32_t t2 = t / (uint32_t)H, yy = t - t2 * (uint32_t)H;
+            const uint32_t b = t2 / (uint32_t)D, zz = t2 - b * (uint32_t)D;
+            ov = (((int64_t)b * (2 * D) + 2 * zz) * (2 * H) + 2 * yy) * (int64_t)(2 * W) + 2 * xx;
+        }
+        s_ov[tid] = ov;
+    }
     uint8_t *sA = smem;
     uint8_t *sB = smem + (size_t)kchunks * 2048;
-    const int64_t m = (int64_t)blockIdx.x * 128 + tid;
     const int n0 = blockIdx.y * NT;
-    const bool live = m < M;
 
     if (warp == 0) tmem_alloc(&tmem_slot, tmem_cols);
     if (tid == 0) {
         mbar_init(&bar, 1);
         mbar_fence_init();
     }
+    // Operand staging.  Global reads want a warp to touch few 128-byte lines, the K-major image wants the 8 lanes of a
+    // quarter warp on 8 different rows (16-byte bank groups): lane = (row % 8) + 8 * (chunk % 4), i.e. one instruction
+    // reads 64 contiguous bytes of 8 rows and writes conflict-free.
     {
-        const uint4 *src = reinterpret_cast<const uint4 *>(x + (live ? m : 0) * xs);
-        for (int kc = 0; kc < kchunks; ++kc)
-            *reinterpret_cast<uint4 *>(sA + (size_t)kc * 2048 + tid * 16) = live ? __ldg(src + kc) : make_uint4(0u, 0u, 0u, 0u);
-    }
-    for (int idx = tid; idx < NT * kchunks; idx += 128) {
-        const int r = idx % NT, kc = idx / NT;
-        *reinterpret_cast<uint4 *>(sB + ((size_t)kc * NT + r) * 16) =
-            __ldg(reinterpret_cast<const uint4 *>(wp + (int64_t)(n0 + r) * K) + kc);
+        const int64_t m_base = (int64_t)blockIdx.x * 128;
+        const int kq = (kchunks + 3) >> 2;                      // groups of 4 chunks
+        for (int idx = tid; idx < 16 * kq * 32; idx += 128) {   // 16 row groups x kq chunk groups x 32 lanes
+            const int l = idx & 31, grp = idx >> 5;
+            const int rg = grp % 16, cg = grp / 16;
+            const int r = rg * 8 + (l & 7), kc = cg * 4 + (l >> 3);
+            if (kc < kchunks) {
+                const int64_t mm = m_base + r;
+                uint8_t *dst = sA + (size_t)kc * 2048 + r * 16;
+                if (mm < M) cp_async16(dst, reinterpret_cast<const uint4 *>(x + mm * xs) + kc);   // all copies in flight at once
+                else *reinterpret_cast<uint4 *>(dst) = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+        const int ngr = NT >> 3;
+        for (int idx = tid; idx < ngr * kq * 32; idx += 128) {
+            const int l = idx & 31, grp = idx >> 5;
+            const int rg = grp % ngr, cg = grp / ngr;
+            const int r = rg * 8 + (l & 7), kc = cg * 4 + (l >> 3);
+            if (kc < kchunks)
+                cp_async16(sB + ((size_t)kc * NT + r) * 16, reinterpret_cast<const uint4 *>(wp + (int64_t)(n0 + r) * K) + kc);
+        }
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
     }
     fence_proxy_async();
     tc_fence_before();
@@ -62,35 +94,56 @@ __global__ void __launch_bounds__(128) convT_k2s2_kernel(const __nv_bfloat16 *__
     }
     mbar_wait(&bar, 0);
     tc_fence_after();
-    // input voxel -> (b, z, y, x)
-    int xx = 0, yy = 0, zz = 0;
-    int64_t b = 0;
-    if (live) {
-        xx = (int)(m % W);
-        int64_t t = m / W;
-        yy = (int)(t % H); t /= H;
-        zz = (int)(t % D);
-        b = t / D;
-    }
+    // ---- epilogue: TMEM lane -> bf16 -> staging tile [128 rows][NT + 8] (aliases the operand images, which the MMAs
+    // have finished reading) -> cooperative stores: 16-byte pieces of the Cout-channel run of each output voxel ----
+    __nv_bfloat16 *sOut = reinterpret_cast<__nv_bfloat16 *>(smem);
+    const int pitch = NT + 8;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    const int H2 = 2 * H, W2 = 2 * W;
     for (int c = 0; c < NT; c += 16) {
         uint32_t r[16];
         tmem_ld16(tmem + lane_base + c, r);
         tmem_wait_ld();
-        if (!live) continue;
-        const int n = n0 + c;
-        const int pos = n / Cout, co = n - pos * Cout;
-        const int dz = pos >> 2, dy = (pos >> 1) & 1, dx = pos & 1;
-        const int64_t ov = ((b * (2 * D) + 2 * zz + dz) * H2 + 2 * yy + dy) * (int64_t)W2 + 2 * xx + dx;
         uint4 lo, hi;
         lo.x = pack_bf16(__uint_as_float(r[0]), __uint_as_float(r[1]));   lo.y = pack_bf16(__uint_as_float(r[2]), __uint_as_float(r[3]));
         lo.z = pack_bf16(__uint_as_float(r[4]), __uint_as_float(r[5]));   lo.w = pack_bf16(__uint_as_float(r[6]), __uint_as_float(r[7]));
         hi.x = pack_bf16(__uint_as_float(r[8]), __uint_as_float(r[9]));   hi.y = pack_bf16(__uint_as_float(r[10]), __uint_as_float(r[11]));
         hi.z = pack_bf16(__uint_as_float(r[12]), __uint_as_float(r[13])); hi.w = pack_bf16(__uint_as_float(r[14]), __uint_as_float(r[15]));
-        uint4 *dst = reinterpret_cast<uint4 *>(y + ov * ys + co);
+        uint4 *dst = reinterpret_cast<uint4 *>(sOut + (size_t)tid * pitch + c);
         dst[0] = lo;
         dst[1] = hi;
+    }
+    __syncthreads();
+    {
+        // a (row, position) pair owns `per` = gcd-free run of 16-byte pieces: positions inside this N tile are
+        // n0 / Cout ... ; piece p of (row, pos) -> channels [8p, 8p + 8) of that output voxel
+        const int per = Cout >> 3;                       // 16-byte pieces per output voxel
+        const int pos_in_tile = NT / Cout > 0 ? NT / Cout : 1;
+        const int H2 = 2 * H, W2 = 2 * W;
+        if (NT % Cout == 0) {
+            const int total = 128 * pos_in_tile * per;
+            for (int i = tid; i < total; i += 128) {
+                const int p = i % per;
+                const int t2 = i / per;
+                const int row = t2 % 128, pl = t2 / 128;     // consecutive lanes: pieces of one voxel, then the next input x
+                if (s_ov[row] < 0) continue;
+                const int pos = n0 / Cout + pl;
+                const int dz = pos >> 2, dy = (pos >> 1) & 1, dx = pos & 1;
+                const int64_t ov = s_ov[row] + ((int64_t)dz * H2 + dy) * W2 + dx;
+                *reinterpret_cast<uint4 *>(y + ov * ys + p * 8) =
+                    *reinterpret_cast<const uint4 *>(sOut + (size_t)row * pitch + pl * Cout + p * 8);
+            }
+        } else {   // the N tile covers part of one position's channels (Cout > NT)
+            const int pos = n0 / Cout, co0 = n0 - pos * Cout;
+            const int pieces = NT >> 3;
+            const int dz = pos >> 2, dy = (pos >> 1) & 1, dx = pos & 1;
+            for (int i = tid; i < 128 * pieces; i += 128) {
+                const int p = i % pieces, row = i / pieces;
+                if (s_ov[row] < 0) continue;
+                const int64_t ov = s_ov[row] + ((int64_t)dz * H2 + dy) * W2 + dx;
+                *reinterpret_cast<uint4 *>(y + ov * ys + co0 + p * 8) =
+                    *reinterpret_cast<const uint4 *>(sOut + (size_t)row * pitch + p * 8);
+            }
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -111,14 +164,15 @@ extern "C" int wf_convtranspose3d_k2s2_ndhwc(const void *x, const void *wpack, v
         return WF_ERR_BAD_SHAPE;
     if (!aligned16(x) || !aligned16(wpack) || !aligned16(y)) return WF_ERR_MISALIGNED;
     const int N = 8 * Cout;
-    // N tile: the largest multiple of 16 (<= 128) that divides N; Cout % 16 == 0 keeps every 16-channel store group
-    // inside one output position
+    // N tile: the largest multiple of 16 (<= 128) that divides N and is a multiple or a divisor of Cout (an N tile then
+    // covers whole output positions, or a slice of one)
     int NT = 0;
     for (int nt = 128; nt >= 16; nt -= 16)
-        if (N % nt == 0) { NT = nt; break; }
+        if (N % nt == 0 && (nt % Cout == 0 || Cout % nt == 0)) { NT = nt; break; }
     if (!NT) return WF_ERR_UNSUPPORTED;
     const int kchunks = Cin / 8;
-    const size_t smem = (size_t)kchunks * 2048 + (size_t)kchunks * NT * 16;
+    const size_t images = (size_t)kchunks * 2048 + (size_t)kchunks * NT * 16, stage = (size_t)128 * (NT + 8) * 2;
+    const size_t smem = images > stage ? images : stage;
     if (smem > 200 * 1024) return WF_ERR_UNSUPPORTED;
     static bool attr_done = false;
     if (!attr_done) {
@@ -128,6 +182,7 @@ extern "C" int wf_convtranspose3d_k2s2_ndhwc(const void *x, const void *wpack, v
     uint32_t cols = 32;
     while ((int)cols < NT) cols <<= 1;
     const int64_t M = (int64_t)B * D * H * W;
+    if (M >= 0x7fffffffLL) return WF_ERR_UNSUPPORTED;
     dim3 grid((unsigned)((M + 127) / 128), (unsigned)(N / NT));
     convT_k2s2_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>((const __nv_bfloat16 *)x, (const uint16_t *)wpack,
                                                                 (__nv_bfloat16 *)y, M, Cin, NT, Cout, D, H, W, x_vox_stride,

@@ -15,6 +15,8 @@
 //   sum / sum of squares of the ROUNDED outputs (thread t < N owns channel t; fp32 per tile, fp64 per CTA, one fp64
 //   atomicAdd per CTA and channel at the end), so InstanceNorm needs no separate statistics pass.
 // Persistent CTAs (grid = min(tiles, 4 per SM)); traffic = one read of the input (L2-resident) + one write of the output.
+#include <type_traits>
+
 #include "tc_common.cuh"
 #include "wf_common.cuh"
 
@@ -105,27 +107,49 @@ __global__ void __launch_bounds__(128, 4) conv3d_c4_kernel(const TIN *__restrict
         {
             int xx = 0, yy = 0, zz = 0;
             int64_t b = 0;
-            if (live) {
-                xx = (int)(v % g.W);
-                int64_t t = v / g.W;
-                yy = (int)(t % g.H); t /= g.H;
-                zz = (int)(t % g.D);
-                b = t / g.D;
+            if (live) {   // total < 2^31 (checked by the host wrapper): 32-bit divisions, ~5x cheaper than 64-bit ones
+                const uint32_t v32 = (uint32_t)v;
+                uint32_t t = v32 / (uint32_t)g.W;
+                xx = (int)(v32 - t * (uint32_t)g.W);
+                uint32_t t2 = t / (uint32_t)g.H;
+                yy = (int)(t - t2 * (uint32_t)g.H);
+                const uint32_t t3 = t2 / (uint32_t)g.D;
+                zz = (int)(t2 - t3 * (uint32_t)g.D);
+                b = t3;
             }
             const TIN *base = x + (b * S) * 4;
             uint2 tap[28];
+            // nine unconditional loads per z plane (coordinates clamped into the volume, result masked afterwards), so
+            // the loads of a plane are in flight together instead of one predicated load at a time
 #pragma unroll
-            for (int dz = -1; dz <= 1; ++dz)
+            for (int dz = -1; dz <= 1; ++dz) {
+                typename std::conditional<sizeof(TIN) == 2, uint2, float4>::type raw[9];
+                bool in[9];
+                const int z2 = zz + dz;
+                const int zc = min(max(z2, 0), g.D - 1);
 #pragma unroll
-                for (int dy = -1; dy <= 1; ++dy)
+                for (int dy = -1; dy <= 1; ++dy) {
+                    const int y2 = yy + dy;
+                    const int yc = min(max(y2, 0), g.H - 1);
 #pragma unroll
                     for (int dx = -1; dx <= 1; ++dx) {
-                        const int z2 = zz + dz, y2 = yy + dy, x2 = xx + dx;
-                        const bool in = live && (unsigned)z2 < (unsigned)g.D && (unsigned)y2 < (unsigned)g.H &&
-                                        (unsigned)x2 < (unsigned)g.W;
-                        const int t = (dz + 1) * 9 + (dy + 1) * 3 + (dx + 1);
-                        tap[t] = in ? load_vox4<TIN>(base + (((int64_t)z2 * g.H + y2) * g.W + x2) * 4) : make_uint2(0u, 0u);
+                        const int x2 = xx + dx;
+                        const int xc = min(max(x2, 0), g.W - 1);
+                        const int i = (dy + 1) * 3 + (dx + 1);
+                        in[i] = live && z2 == zc && y2 == yc && x2 == xc;
+                        const TIN *p = base + (((int64_t)zc * g.H + yc) * g.W + xc) * 4;
+                        if constexpr (sizeof(TIN) == 2) raw[i] = __ldg(reinterpret_cast<const uint2 *>(p));
+                        else raw[i] = __ldg(reinterpret_cast<const float4 *>(p));
                     }
+                }
+#pragma unroll
+                for (int i = 0; i < 9; ++i) {
+                    uint2 v;
+                    if constexpr (sizeof(TIN) == 2) v = raw[i];
+                    else v = make_uint2(pack_bf16(raw[i].x, raw[i].y), pack_bf16(raw[i].z, raw[i].w));
+                    tap[(dz + 1) * 9 + i] = in[i] ? v : make_uint2(0u, 0u);
+                }
+            }
             tap[27] = make_uint2(0u, 0u);
             __syncthreads();   // the previous tile's staging tile (same shared memory) has been stored and summed
 #pragma unroll
@@ -181,7 +205,7 @@ __global__ void __launch_bounds__(128, 4) conv3d_c4_kernel(const TIN *__restrict
         // ---- statistics of the rounded outputs ----
         if (tid < N) {
             // a tile may straddle two batch elements only if S % 128 != 0; handled row by row in that (rare) case
-            const int64_t b_first = v0 / S, b_last = (v0 + rows - 1) / S;
+            const int64_t b_first = (uint32_t)v0 / (uint32_t)S, b_last = (uint32_t)(v0 + rows - 1) / (uint32_t)S;
             const uint32_t *col = reinterpret_cast<const uint32_t *>(sOut) + cpair;
             const int wpitch = pitch >> 1;
             const int r0 = rhalf * 64, r1 = min(rows, r0 + 64);
@@ -198,7 +222,7 @@ __global__ void __launch_bounds__(128, 4) conv3d_c4_kernel(const TIN *__restrict
                 acc[0] += (double)s0; acc[1] += (double)s1; acc[2] += (double)q0; acc[3] += (double)q1;
             } else {
                 for (int r = r0; r < r1; ++r) {
-                    const int64_t bb = (v0 + r) / S;
+                    const int64_t bb = (uint32_t)(v0 + r) / (uint32_t)S;
                     if (bb != acc_b) { flush(); acc_b = bb; }
                     const uint32_t w = col[(size_t)r * wpitch];
                     const double f0 = (double)__uint_as_float(w << 16), f1 = (double)__uint_as_float(w & 0xffff0000u);
@@ -246,6 +270,7 @@ extern "C" int wf_conv3d_c4_in_stats(const void *x, int x_dtype, const void *wpa
     C4Geom g;
     g.B = B; g.D = D; g.H = H; g.W = W;
     g.total = (int64_t)B * D * H * W;
+    if (g.total >= 0x7fffffffLL) return WF_ERR_UNSUPPORTED;   // the kernel uses 32-bit voxel arithmetic
     const int64_t ntiles = (g.total + 127) / 128;
     const size_t stage = (size_t)128 * (N + 8) * 2, aimg = (size_t)kC4Chunks * 2048;
     const size_t smem = (size_t)kC4Chunks * N * 16 + (stage > aimg ? stage : aimg);

@@ -87,18 +87,27 @@ __global__ void instnorm_finalize_kernel(const T *__restrict__ x, const double *
 }
 
 // act: 0 none, 1 relu, 2 leaky relu (slope)
-template <typename T, int VEC>
+template <typename T, typename TO, int VEC>
 __global__ void __launch_bounds__(256) instnorm_apply_kernel(const T *__restrict__ x, const float *__restrict__ mr,
                                                              const T *__restrict__ res, const float *__restrict__ res_mr,
-                                                             T *__restrict__ y, int64_t total, int64_t S, int C,
+                                                             TO *__restrict__ y, int64_t total, int64_t S, int C,
                                                              int cvecs, int64_t xs, int64_t rs, int64_t ys, int act,
                                                              float slope, const float *__restrict__ gamma,
                                                              const float *__restrict__ beta) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
-    const int cv = (int)(idx % cvecs);
-    const int64_t vox = idx / cvecs;  // b*S + v
-    const int64_t b = vox / S;
+    int cv;
+    int64_t vox, b;   // vox = b*S + v
+    if (total < 0x7fffffffLL) {   // 32-bit divisions (a thread only moves one 16-byte packet: index math must stay cheap)
+        const uint32_t i32 = (uint32_t)idx, q = i32 / (uint32_t)cvecs;
+        cv = (int)(i32 - q * (uint32_t)cvecs);
+        vox = q;
+        b = q / (uint32_t)S;
+    } else {
+        cv = (int)(idx % cvecs);
+        vox = idx / cvecs;
+        b = vox / S;
+    }
     const int c0 = cv * VEC;
     float f[VEC];
     NVec<T, VEC>::load(x + vox * xs + c0, f);
@@ -127,79 +136,141 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(const T *__restrict
 #pragma unroll
         for (int e = 0; e < VEC; ++e) f[e] = f[e] > 0.f ? f[e] : f[e] * slope;
     }
-    NVec<T, VEC>::store(y + vox * ys + c0, f);
+    if constexpr (sizeof(TO) == sizeof(T)) {
+        NVec<TO, VEC>::store(y + vox * ys + c0, f);
+    } else {  // fp32 in, bf16 out: 4 channels -> 8 bytes
+        if constexpr (VEC == 1) {
+            y[vox * ys + c0] = from_f32<TO>(f[0]);
+        } else {
+            __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]), b2 = __floats2bfloat162_rn(f[2], f[3]);
+            *reinterpret_cast<uint2 *>(y + vox * ys + c0) = make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b2));
+        }
+    }
 }
 
 // Last block of the network: y = act((x - mean) * rstd + [(r - mean_r) * rstd_r | r]) is consumed only by the 1x1x1
 // output convolution (Waveformer.out, reference network_models/network_backbone.py:407 -> UnetOutBlock,
 // monai/networks/blocks/dynunet_block.py:266), so the C-channel activation is never written: each lane normalises one
-// 16-byte channel packet, multiplies it with its slice of the [K, C] head weight, the packets of a voxel are summed
-// through shared memory and one thread per voxel stores the K logits.
-//   block = 32 voxels x cpv packets (cpv = C / VEC), persistent over voxel groups; KP = padded K (4, 8 or 16).
+// 16-byte channel packet and multiplies it with its slice of the [K, C] head weight; the cpv = C / VEC packets of a voxel
+// sit in consecutive lanes of one warp (floor(32 / cpv) voxels per warp) and are summed with a segmented shuffle tree;
+// lane 0 of each voxel stores the K logits.  No shared memory, no block barrier; two voxel groups per iteration keep
+// four 16-byte loads in flight per lane; mean / rstd and the head weights live in registers.
 template <typename T, typename TO, int KP>
-__global__ void __launch_bounds__(1024) instnorm_apply_head_kernel(const T *__restrict__ x, const float *__restrict__ mr,
-                                                                   const T *__restrict__ res, const float *__restrict__ res_mr,
-                                                                   const float *__restrict__ hw, const float *__restrict__ hb,
-                                                                   TO *__restrict__ out, int64_t S, int64_t total_vox, int C,
-                                                                   int K, int cpv, int64_t xs, int64_t rs, int act, float slope) {
+__global__ void __launch_bounds__(256, KP <= 4 ? 2 : 1) instnorm_apply_head_kernel(const T *__restrict__ x, const float *__restrict__ mr,
+                                                                  const T *__restrict__ res, const float *__restrict__ res_mr,
+                                                                  const float *__restrict__ hw, const float *__restrict__ hb,
+                                                                  TO *__restrict__ out, int64_t S, int64_t total_vox, int C,
+                                                                  int K, int cpv, int64_t xs, int64_t rs, int act, float slope) {
     constexpr int VEC = Pack<T>::VEC;
-    extern __shared__ float part[];  // [32 * cpv][KP]
-    const int tid = threadIdx.x;
-    const int vl = tid / cpv, cv = tid - vl * cpv;   // voxel in the group, channel packet
+    const int lane = threadIdx.x & 31;
+    const int vpw = 32 / cpv;                       // voxels per warp
+    const int vl = lane / cpv, cv = lane - vl * cpv;
+    const bool lane_live = vl < vpw;
     const int c0 = cv * VEC;
+    const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     float w[KP][VEC];
 #pragma unroll
     for (int k = 0; k < KP; ++k)
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) w[k][e] = k < K ? __ldg(hw + (int64_t)k * C + c0 + e) : 0.f;
-    const int64_t groups = (total_vox + 31) / 32;
-    for (int64_t g = blockIdx.x; g < groups; g += gridDim.x) {
-        const int64_t vox = g * 32 + vl;
-        float p[KP];
+        for (int e = 0; e < VEC; ++e) w[k][e] = (k < K && lane_live) ? __ldg(hw + (int64_t)k * C + c0 + e) : 0.f;
+    float bias_k[KP];
 #pragma unroll
-        for (int k = 0; k < KP; ++k) p[k] = 0.f;
-        if (vox < total_vox) {
-            const int64_t b = vox / S;
-            float f[VEC];
-            NVec<T, VEC>::load(x + vox * xs + c0, f);
-            const float *m = mr + ((int64_t)b * C + c0) * 2;
+    for (int k = 0; k < KP; ++k) bias_k[k] = (hb != nullptr && k < K) ? __ldg(hb + k) : 0.f;
+    // folded normalisation: t = x * sx + r * sr + sh   (sx = rstd, sr = rstd_r or 1, sh = -mean * rstd - mean_r * rstd_r)
+    float sx[VEC], sr[VEC], sh[VEC];
+    int64_t cur_b = -1;
+    auto load_stats = [&](int64_t b) {
+        const float *m = mr + (b * C + c0) * 2;
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) f[e] = (f[e] - __ldg(m + 2 * e)) * __ldg(m + 2 * e + 1);
-            if (res != nullptr) {
-                float r[VEC];
-                NVec<T, VEC>::load(res + vox * rs + c0, r);
-                if (res_mr != nullptr) {
-                    const float *m2 = res_mr + ((int64_t)b * C + c0) * 2;
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) r[e] = (r[e] - __ldg(m2 + 2 * e)) * __ldg(m2 + 2 * e + 1);
-                }
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) f[e] += r[e];
-            }
+        for (int e = 0; e < VEC; ++e) {
+            sx[e] = __ldg(m + 2 * e + 1);
+            sh[e] = -__ldg(m + 2 * e) * sx[e];
+            sr[e] = 1.f;
+        }
+        if (res != nullptr && res_mr != nullptr) {
+            const float *m2 = res_mr + (b * C + c0) * 2;
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
-                if (act == 1) f[e] = fmaxf(f[e], 0.f);
-                else if (act == 2) f[e] = f[e] > 0.f ? f[e] : f[e] * slope;
+                sr[e] = __ldg(m2 + 2 * e + 1);
+                sh[e] = fmaf(-__ldg(m2 + 2 * e), sr[e], sh[e]);
             }
+        }
+        cur_b = b;
+    };
+    const int64_t groups = (total_vox + vpw - 1) / vpw;          // one group = the voxels one warp covers at once
+    const bool small = total_vox < 0x7fffffffLL;                  // 32-bit batch-index division
+    using Raw = typename Pack<T>::raw;
+    Raw xr[2], rr[2], xn[2], rn[2];                               // current / prefetched packets of two voxel groups
+    auto fetch = [&](int64_t g0, Raw (&xd)[2], Raw (&rd)[2]) {
 #pragma unroll
-            for (int k = 0; k < KP; ++k)
+        for (int u = 0; u < 2; ++u) {
+            const int64_t vx = (g0 + u) * vpw + vl;
+            if (lane_live && (g0 + u) < groups && vx < total_vox) {
+                xd[u] = *reinterpret_cast<const Raw *>(x + vx * xs + c0);
+                if (res != nullptr) rd[u] = *reinterpret_cast<const Raw *>(res + vx * rs + c0);
+            }
+        }
+    };
+    int64_t g0 = warp_id * 2;
+    if (g0 < groups) fetch(g0, xr, rr);
+    for (; g0 < groups; g0 += nwarps * 2) {
+        const int64_t gn = g0 + nwarps * 2;
+        if (gn < groups) fetch(gn, xn, rn);                       // next iteration's loads fly while this one computes
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) p[k] = fmaf(f[e], w[k][e], p[k]);
+        for (int u = 0; u < 2; ++u) {
+            const int64_t vx = (g0 + u) * vpw + vl;
+            const bool ok = lane_live && (g0 + u) < groups && vx < total_vox;
+            float p[KP];
+#pragma unroll
+            for (int k = 0; k < KP; ++k) p[k] = 0.f;
+            if (ok) {
+                const int64_t b = small ? (int64_t)((uint32_t)vx / (uint32_t)S) : vx / S;
+                if (b != cur_b) load_stats(b);
+                float f[VEC];
+                Pack<T>::unpack(xr[u], f);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) f[e] = fmaf(f[e], sx[e], sh[e]);
+                if (res != nullptr) {
+                    float r[VEC];
+                    Pack<T>::unpack(rr[u], r);
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) f[e] = fmaf(r[e], sr[e], f[e]);
+                }
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    if (act == 1) f[e] = fmaxf(f[e], 0.f);
+                    else if (act == 2) f[e] = f[e] > 0.f ? f[e] : f[e] * slope;
+                }
+#pragma unroll
+                for (int k = 0; k < KP; ++k)
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) p[k] = fmaf(f[e], w[k][e], p[k]);
+            }
+            // segmented tree over the cpv lanes of a voxel (all 32 lanes take part in the shuffles)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                if (o < 2 * cpv) {
+#pragma unroll
+                    for (int k = 0; k < KP; ++k) {
+                        const float t = __shfl_down_sync(0xffffffffu, p[k], o);
+                        if (cv + o < cpv) p[k] += t;
+                    }
+                }
+            }
+            if (ok && cv == 0) {
+                TO *dst = out + vx * (int64_t)K;
+                if constexpr (KP == 4 && sizeof(TO) == 4) {
+                    if (K == 4) {
+                        *reinterpret_cast<float4 *>(dst) = make_float4(p[0] + bias_k[0], p[1] + bias_k[1], p[2] + bias_k[2], p[3] + bias_k[3]);
+                        continue;
+                    }
+                }
+                for (int k = 0; k < K; ++k) dst[k] = from_f32<TO>(p[k] + bias_k[k]);
+            }
         }
 #pragma unroll
-        for (int k = 0; k < KP; ++k) part[(size_t)tid * KP + k] = p[k];
-        __syncthreads();
-        if (tid < 32 && g * 32 + tid < total_vox) {
-            float o[KP];
-#pragma unroll
-            for (int k = 0; k < KP; ++k) o[k] = (hb != nullptr && k < K) ? __ldg(hb + k) : 0.f;
-            for (int j = 0; j < cpv; ++j)
-#pragma unroll
-                for (int k = 0; k < KP; ++k) o[k] += part[((size_t)tid * cpv + j) * KP + k];
-            TO *dst = out + (g * 32 + tid) * (int64_t)K;
-            for (int k = 0; k < K; ++k) dst[k] = from_f32<TO>(o[k]);
-        }
-        __syncthreads();
+        for (int u = 0; u < 2; ++u) { xr[u] = xn[u]; rr[u] = rn[u]; }
     }
 }
 
@@ -212,12 +283,12 @@ static int apply_head_launch(const T *x, const float *mr, const T *res, const fl
     if (C % V != 0 || C / V > 32 || K < 1 || K > 16) return WF_ERR_UNSUPPORTED;
     if (!aligned16(x) || (xs * e) % 16 != 0 || (res != nullptr && (!aligned16(res) || (rs * e) % 16 != 0))) return WF_ERR_MISALIGNED;
     const int cpv = C / V;
-    const int threads = 32 * cpv;
     const int64_t total = (int64_t)B * S;
-    const int64_t groups = (total + 31) / 32;
-    const int per_sm = 2048 / threads > 0 ? 2048 / threads : 1;
-    const unsigned grid = (unsigned)min(groups, (int64_t)kNumSMs * per_sm);
-#define WF_HEAD(KP_) instnorm_apply_head_kernel<T, TO, KP_><<<grid, threads, (size_t)threads * KP_ * sizeof(float), st>>>( \
+    const int vpw = 32 / cpv;
+    const int64_t groups = (total + vpw - 1) / vpw;
+    const int64_t want_blocks = (groups / 2 + 7) / 8 + 1;                    // 8 warps per block, 2 groups per iteration
+    const unsigned grid = (unsigned)min(want_blocks, (int64_t)kNumSMs * 8);
+#define WF_HEAD(KP_) instnorm_apply_head_kernel<T, TO, KP_><<<grid, 256, 0, st>>>( \
         x, mr, res, res_mr, hw, hb, out, S, total, C, K, cpv, xs, rs, act, slope)
     if (K <= 4) WF_HEAD(4);
     else if (K <= 8) WF_HEAD(8);
@@ -247,20 +318,23 @@ static int stats_launch(const T *x, double *sums, float *mr, int B, int64_t S, i
     return WF_OK;
 }
 
-template <typename T>
-static int apply_launch(const T *x, const float *mr, const T *res, const float *res_mr, T *y, int B, int64_t S, int C,
+template <typename T, typename TO>
+static int apply_launch(const T *x, const float *mr, const T *res, const float *res_mr, TO *y, int B, int64_t S, int C,
                         int64_t xs, int64_t rs, int64_t ys, int act, float slope, const float *gamma, const float *beta,
                         cudaStream_t st) {
     constexpr int V = Pack<T>::VEC;
     const size_t e = sizeof(T);
-    const bool vec = (C % V == 0) && aligned16(x) && aligned16(y) && (xs * e) % 16 == 0 && (ys * e) % 16 == 0 &&
+    // a packet is V elements: 16 bytes of T on the input side, V * sizeof(TO) bytes (16, or 8 for fp32 -> bf16) on the output
+    const size_t out_packet = V * sizeof(TO);
+    const bool vec = (C % V == 0) && aligned16(x) && (xs * e) % 16 == 0 &&
+                     (reinterpret_cast<uintptr_t>(y) % out_packet) == 0 && (ys * sizeof(TO)) % out_packet == 0 &&
                      (res == nullptr || (aligned16(res) && (rs * e) % 16 == 0));
     if (vec) {
         const int64_t total = (int64_t)B * S * (C / V);
-        instnorm_apply_kernel<T, V><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, mr, res, res_mr, y, total, S, C, C / V, xs, rs, ys, act, slope, gamma, beta);
+        instnorm_apply_kernel<T, TO, V><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, mr, res, res_mr, y, total, S, C, C / V, xs, rs, ys, act, slope, gamma, beta);
     } else {
         const int64_t total = (int64_t)B * S * C;
-        instnorm_apply_kernel<T, 1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, mr, res, res_mr, y, total, S, C, C, xs, rs, ys, act, slope, gamma, beta);
+        instnorm_apply_kernel<T, TO, 1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, mr, res, res_mr, y, total, S, C, C, xs, rs, ys, act, slope, gamma, beta);
     }
     WF_LAUNCH_CHECK();
     return WF_OK;
@@ -281,18 +355,22 @@ extern "C" int wf_instnorm_stats_ndhwc(const void *x, double *sums, float *mean_
 
 extern "C" int wf_instnorm_apply_ndhwc(const void *x, const float *mean_rstd, const void *res, const float *res_mean_rstd,
                                        const float *gamma, const float *beta, void *y, int act, float slope, int dtype,
-                                       int B, int64_t S, int C, int64_t x_vox_stride, int64_t res_vox_stride,
+                                       int y_dtype, int B, int64_t S, int C, int64_t x_vox_stride, int64_t res_vox_stride,
                                        int64_t y_vox_stride, void *stream) {
     if (!x || !mean_rstd || !y) return WF_ERR_NULL_POINTER;
     if (B <= 0 || S <= 0 || C <= 0 || x_vox_stride < C || y_vox_stride < C || (res && res_vox_stride < C)) return WF_ERR_BAD_SHAPE;
     if (act < 0 || act > 2) return WF_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == WF_F32)
-        return wf::apply_launch<float>((const float *)x, mean_rstd, (const float *)res, res_mean_rstd, (float *)y, B, S, C,
-                                       x_vox_stride, res_vox_stride, y_vox_stride, act, slope, gamma, beta, st);
-    if (dtype == WF_BF16)
-        return wf::apply_launch<__nv_bfloat16>((const __nv_bfloat16 *)x, mean_rstd, (const __nv_bfloat16 *)res, res_mean_rstd,
-                                               (__nv_bfloat16 *)y, B, S, C, x_vox_stride, res_vox_stride, y_vox_stride, act, slope, gamma, beta, st);
+    using bf = __nv_bfloat16;
+    if (dtype == WF_F32 && y_dtype == WF_F32)
+        return wf::apply_launch<float, float>((const float *)x, mean_rstd, (const float *)res, res_mean_rstd, (float *)y, B, S, C,
+                                              x_vox_stride, res_vox_stride, y_vox_stride, act, slope, gamma, beta, st);
+    if (dtype == WF_F32 && y_dtype == WF_BF16)   // fp32 block (TF32 convolutions) writing a bf16 concat slice
+        return wf::apply_launch<float, bf>((const float *)x, mean_rstd, (const float *)res, res_mean_rstd, (bf *)y, B, S, C,
+                                           x_vox_stride, res_vox_stride, y_vox_stride, act, slope, gamma, beta, st);
+    if (dtype == WF_BF16 && y_dtype == WF_BF16)
+        return wf::apply_launch<bf, bf>((const bf *)x, mean_rstd, (const bf *)res, res_mean_rstd, (bf *)y, B, S, C, x_vox_stride,
+                                        res_vox_stride, y_vox_stride, act, slope, gamma, beta, st);
     return WF_ERR_BAD_DTYPE;
 }
 

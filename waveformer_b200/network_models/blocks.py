@@ -150,6 +150,13 @@ class UnetrBasicBlock(nn.Module):
         self.layer = cls(spatial_dims, in_channels, out_channels, kernel_size, stride, norm_name)
 
     def forward(self, inp: torch.Tensor, out_buf: torch.Tensor = None) -> torch.Tensor:
+        if getattr(self, "tf32", False) and use_fused(inp):
+            # precision policy: this block is kept in fp32 storage with TF32 tensor-core convolutions
+            w = self.layer.conv1.conv.weight
+            if inp.dtype != w.dtype:
+                inp = inp.to(w.dtype)
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=True):
+                return self.layer(inp) if out_buf is None else self.layer(inp, out_buf)
         return self.layer(inp) if out_buf is None else self.layer(inp, out_buf)
 
 

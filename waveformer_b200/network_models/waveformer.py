@@ -95,7 +95,9 @@ class MultiscaleTransformer(nn.Module):
             for blk in getattr(self, f"block{s + 1}"):
                 res = blk(t)
                 t, hf = res if isinstance(res, tuple) else (res, ())
-            od = getattr(self, "out_dtype", None) or t.dtype    # decoder activation type (prepare_inference)
+            od = getattr(self, "out_dtype", None) or t.dtype    # activation type of this output's consumer (prepare_inference)
+            if isinstance(od, (list, tuple)):
+                od = od[s]
             if normalize and t.is_cuda and not torch.is_grad_enabled():
                 o = ops.layer_norm_cl(t, None, None, 1e-5, out_dtype=od)   # affine-free LN, stream -> decoder type
             else:

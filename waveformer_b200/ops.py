@@ -471,12 +471,13 @@ def instance_norm_act(x: torch.Tensor, act: str = "none", slope: float = 0.01, r
     if out is None:
         out = torch.empty((B, D, H, W, C), dtype=x.dtype, device=dev)
     ys = _voxel_stride(out)
-    if ys is None or tuple(out.shape) != (B, D, H, W, C) or out.dtype != x.dtype:
-        raise ValueError("out must be a voxel-dense [B, D, H, W, C] tensor of x's dtype")
+    if ys is None or tuple(out.shape) != (B, D, H, W, C) or not (out.dtype == x.dtype or
+                                                                  (x.dtype == torch.float32 and out.dtype == torch.bfloat16)):
+        raise ValueError("out must be a voxel-dense [B, D, H, W, C] tensor of x's dtype (or bf16 for fp32 x)")
     with torch.cuda.device(dev):
         st = _lib.lib().wf_instnorm_apply_ndhwc(v.data_ptr(), mr.data_ptr(), _ptr(rv), _ptr(rmr), _ptr(gamma), _ptr(beta),
-                                                out.data_ptr(), _ACT[act], float(slope), _dtype_code(x), B, D * H * W, C,
-                                                vs, rs, ys, _stream(dev))
+                                                out.data_ptr(), _ACT[act], float(slope), _dtype_code(x), _dtype_code(out),
+                                                B, D * H * W, C, vs, rs, ys, _stream(dev))
     _lib.check(st, "wf_instnorm_apply_ndhwc")
     _count()
     return out.permute(0, 4, 1, 2, 3)

@@ -11,8 +11,10 @@ unit-gain test weights - at higher precision, none of which costs measurable tim
   the raw image to bf16 alone costs 4e-2 max-relative logit error;
 * window attention uses fp16 tensor-core operands (same tcgen05 rate as bf16, 10-bit mantissa) with fp32 accumulation and
   an fp32 result: with bf16 operands attention alone costs 7e-2, with fp16 9e-3;
-* everything else (CCF_FFN GEMMs, conv blocks, decoder, IDWT) has bf16 operands and bf16 storage, fp32 accumulation,
-  fp32 statistics in every normalisation.
+* the three skip blocks encoder2..4 (residual blocks with an identity shortcut on the stage outputs) run fp32 storage /
+  TF32 tensor-core convolutions: together they are half of the remaining logit error and 5 % of the step;
+* everything else (CCF_FFN GEMMs, the 128^3 conv blocks, decoder, IDWT) has bf16 operands and bf16 storage, fp32
+  accumulation, fp32 statistics in every normalisation.
 """
 from __future__ import annotations
 
@@ -76,7 +78,18 @@ def prepare_inference(model: nn.Module, dtype: torch.dtype = torch.bfloat16, *, 
         elif isinstance(m, Block):
             m.hf_dtype = torch.bfloat16                 # detail bands go to the bf16 decoder
         elif isinstance(m, MultiscaleTransformer):
-            m.out_dtype = torch.bfloat16                # stage outputs feed the bf16 conv blocks
+            # stage outputs 0..2 feed the fp32 skip blocks below, the last one the bf16 bottleneck
+            m.out_dtype = [torch.float32, torch.float32, torch.float32, torch.bfloat16]
+    # The residual blocks that turn the encoder's stage outputs into the decoder's skip connections (encoder2..4: identity
+    # shortcut, 48 / 96 / 192 channels at 64^3 / 32^3 / 16^3, 5 % of the step) stay fp32 with TF32 tensor-core
+    # convolutions: rounding their input and activations to bf16 alone accounts for half of the bf16 logit error
+    # (scripts/precision_zones.py: max-rel 1.7e-2 -> 0.9e-2 with these blocks lifted), because their identity shortcut
+    # carries the stage output straight into every decoder level.  Their last kernel writes the bf16 concat slice.
+    for name in ("encoder2", "encoder3", "encoder4"):
+        blk = getattr(model, name, None)
+        if blk is not None:
+            keep_fp32(blk)
+            blk.tf32 = True
     model.logits_dtype = torch.float32                  # the fused output head stores its fp32 accumulators
     for t in list(model.parameters()) + list(model.buffers()):
         if t.is_floating_point():
