@@ -25,7 +25,7 @@ if args.case == "haar":      # BASELINE configs[1]
     ll, hf = ops._dwt_ncdhw_raw(x, True)
     fns = {"dwt3d_ncdhw_bf16": lambda: ops._dwt_ncdhw_raw(x, True), "idwt3d_ncdhw_bf16": lambda: ops._idwt_ncdhw_raw(ll, hf)}
 elif args.case == "c4":      # encoder1: 2 x 4 x 128^3 fp32 window -> conv1 + conv3 + statistics
-    x = rn(2, 4, 128, 128, 128).contiguous(memory_format=torch.channels_last_3d)
+    x = rn(2, 4, 128, 128, 128).bfloat16().contiguous(memory_format=torch.channels_last_3d)
     w1, w3 = (rn(48, 4, 3, 3, 3) * 0.1).bfloat16(), (rn(48, 4, 1, 1, 1) * 0.5).bfloat16()
     fns = {"conv3d_c4_in_stats": lambda: ops.conv3d_c4_in_stats(x, w1, w3)}
 elif args.case == "dwconv":  # CCF_FFN stage 1: 2 x 64^3 x 192

@@ -22,16 +22,23 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 
-__global__ void __launch_bounds__(128) convT_k2s2_kernel(const __nv_bfloat16 *__restrict__ x, const uint16_t *__restrict__ wp,
-                                                         __nv_bfloat16 *__restrict__ y, int64_t M, int K, int NT, int Cout,
-                                                         int D, int H, int W, int64_t xs, int64_t ys, uint32_t tmem_cols) {
+// One CTA = 128 input voxels x ALL 8 * Cout output columns: the A tile is staged once, the whole packed weight matrix is
+// staged next to it (L2-resident), all N / NT accumulator tiles live in TMEM at once (N <= 512 columns), one commit covers
+// every MMA, then the eight warps drain TMEM (warp w: lane quadrant w % 4, tiles of parity w / 4) through a bf16 staging
+// area that aliases the operand images, and the block writes the output voxels with coalesced 16-byte stores.
+__global__ void __launch_bounds__(256) convT_k2s2_kernel(const __nv_bfloat16 *__restrict__ x, const uint16_t *__restrict__ wp,
+                                                         __nv_bfloat16 *__restrict__ y, int64_t M, int K, int NT, int ntiles,
+                                                         int Cout, int D, int H, int W, int64_t xs, int64_t ys) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_slot;
     __shared__ int64_t s_ov[128];   // output voxel index of position (0, 0, 0) for each input voxel of the tile; -1 = none
     const int tid = threadIdx.x, warp = tid >> 5;
     const int kchunks = K >> 3;
-    {
+    const int N = NT * ntiles;
+    uint8_t *sA = smem;
+    uint8_t *sB = smem + (size_t)kchunks * 2048;   // [ntiles][kchunks][NT][16 bytes]
+    if (tid < 128) {
         const int64_t mm = (int64_t)blockIdx.x * 128 + tid;
         int64_t ov = -1;
         if (mm < M) {   // M < 2^31 (host check): 32-bit divisions
@@ -43,39 +50,35 @@ __global__ void __launch_bounds__(128) convT_k2s2_kernel(const __nv_bfloat16 *__
         }
         s_ov[tid] = ov;
     }
-    uint8_t *sA = smem;
-    uint8_t *sB = smem + (size_t)kchunks * 2048;
-    const int n0 = blockIdx.y * NT;
-
-    if (warp == 0) tmem_alloc(&tmem_slot, tmem_cols);
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
     if (tid == 0) {
         mbar_init(&bar, 1);
         mbar_fence_init();
     }
-    // Operand staging.  Global reads want a warp to touch few 128-byte lines, the K-major image wants the 8 lanes of a
-    // quarter warp on 8 different rows (16-byte bank groups): lane = (row % 8) + 8 * (chunk % 4), i.e. one instruction
-    // reads 64 contiguous bytes of 8 rows and writes conflict-free.
+    // Operand staging with cp.async (every copy in flight at once).  Global reads want a warp to touch few 128-byte lines,
+    // the K-major image wants the 8 lanes of a quarter warp on 8 different rows (16-byte bank groups):
+    // lane = (row % 8) + 8 * (chunk % 4), i.e. one instruction reads 64 contiguous bytes of 8 rows, conflict-free writes.
     {
         const int64_t m_base = (int64_t)blockIdx.x * 128;
         const int kq = (kchunks + 3) >> 2;                      // groups of 4 chunks
-        for (int idx = tid; idx < 16 * kq * 32; idx += 128) {   // 16 row groups x kq chunk groups x 32 lanes
-            const int l = idx & 31, grp = idx >> 5;
-            const int rg = grp % 16, cg = grp / 16;
-            const int r = rg * 8 + (l & 7), kc = cg * 4 + (l >> 3);
-            if (kc < kchunks) {
+        const int l = tid & 31, lr = l & 7, lc = l >> 3;        // lane -> (row within the 8-row group, chunk within the group)
+        for (int cg = 0; cg < kq; ++cg) {
+            const int kc = cg * 4 + lc;
+            if (kc >= kchunks) continue;
+            for (int rg = warp; rg < 16; rg += 8) {             // A: 16 row groups
+                const int r = rg * 8 + lr;
                 const int64_t mm = m_base + r;
                 uint8_t *dst = sA + (size_t)kc * 2048 + r * 16;
-                if (mm < M) cp_async16(dst, reinterpret_cast<const uint4 *>(x + mm * xs) + kc);   // all copies in flight at once
+                if (mm < M) cp_async16(dst, reinterpret_cast<const uint4 *>(x + mm * xs) + kc);
                 else *reinterpret_cast<uint4 *>(dst) = make_uint4(0u, 0u, 0u, 0u);
             }
-        }
-        const int ngr = NT >> 3;
-        for (int idx = tid; idx < ngr * kq * 32; idx += 128) {
-            const int l = idx & 31, grp = idx >> 5;
-            const int rg = grp % ngr, cg = grp / ngr;
-            const int r = rg * 8 + (l & 7), kc = cg * 4 + (l >> 3);
-            if (kc < kchunks)
-                cp_async16(sB + ((size_t)kc * NT + r) * 16, reinterpret_cast<const uint4 *>(wp + (int64_t)(n0 + r) * K) + kc);
+            const int rg_per_tile = NT >> 3;
+            for (int t = 0; t < ntiles; ++t)                    // B: N / 8 row groups, tile by tile
+                for (int rg = warp; rg < rg_per_tile; rg += 8) {
+                    const int r = rg * 8 + lr;
+                    cp_async16(sB + (((size_t)t * kchunks + kc) * NT + r) * 16,
+                               reinterpret_cast<const uint4 *>(wp + (int64_t)(t * NT + r) * K) + kc);
+                }
         }
         asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
     }
@@ -87,67 +90,59 @@ __global__ void __launch_bounds__(128) convT_k2s2_kernel(const __nv_bfloat16 *__
     if (tid == 0) {
         const uint32_t idesc = instr_desc_bf16(128, NT, false);
         const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
-        for (int ks = 0; ks < (K >> 4); ++ks)
-            mma_ss(tmem, smem_desc(a0 + ks * 2 * 2048, 2048, 128), smem_desc(b0 + ks * 2 * NT * 16, NT * 16, 128), idesc,
-                   ks > 0 ? 1u : 0u);
+        for (int t = 0; t < ntiles; ++t)
+            for (int ks = 0; ks < (K >> 4); ++ks)
+                mma_ss(tmem + t * NT, smem_desc(a0 + ks * 2 * 2048, 2048, 128),
+                       smem_desc(b0 + (t * kchunks + ks * 2) * NT * 16, NT * 16, 128), idesc, ks > 0 ? 1u : 0u);
         mma_commit(&bar);
     }
     mbar_wait(&bar, 0);
     tc_fence_after();
-    // ---- epilogue: TMEM lane -> bf16 -> staging tile [128 rows][NT + 8] (aliases the operand images, which the MMAs
-    // have finished reading) -> cooperative stores: 16-byte pieces of the Cout-channel run of each output voxel ----
+    __syncthreads();   // every thread has seen the MMAs complete: the operand images may be overwritten
+    // ---- TMEM -> bf16 staging [128 rows][N + 8] ----
     __nv_bfloat16 *sOut = reinterpret_cast<__nv_bfloat16 *>(smem);
-    const int pitch = NT + 8;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    for (int c = 0; c < NT; c += 16) {
-        uint32_t r[16];
-        tmem_ld16(tmem + lane_base + c, r);
-        tmem_wait_ld();
-        uint4 lo, hi;
-        lo.x = pack_bf16(__uint_as_float(r[0]), __uint_as_float(r[1]));   lo.y = pack_bf16(__uint_as_float(r[2]), __uint_as_float(r[3]));
-        lo.z = pack_bf16(__uint_as_float(r[4]), __uint_as_float(r[5]));   lo.w = pack_bf16(__uint_as_float(r[6]), __uint_as_float(r[7]));
-        hi.x = pack_bf16(__uint_as_float(r[8]), __uint_as_float(r[9]));   hi.y = pack_bf16(__uint_as_float(r[10]), __uint_as_float(r[11]));
-        hi.z = pack_bf16(__uint_as_float(r[12]), __uint_as_float(r[13])); hi.w = pack_bf16(__uint_as_float(r[14]), __uint_as_float(r[15]));
-        uint4 *dst = reinterpret_cast<uint4 *>(sOut + (size_t)tid * pitch + c);
-        dst[0] = lo;
-        dst[1] = hi;
-    }
-    __syncthreads();
+    const int pitch = N + 8;
     {
-        // a (row, position) pair owns `per` = gcd-free run of 16-byte pieces: positions inside this N tile are
-        // n0 / Cout ... ; piece p of (row, pos) -> channels [8p, 8p + 8) of that output voxel
-        const int per = Cout >> 3;                       // 16-byte pieces per output voxel
-        const int pos_in_tile = NT / Cout > 0 ? NT / Cout : 1;
-        const int H2 = 2 * H, W2 = 2 * W;
-        if (NT % Cout == 0) {
-            const int total = 128 * pos_in_tile * per;
-            for (int i = tid; i < total; i += 128) {
-                const int p = i % per;
-                const int t2 = i / per;
-                const int row = t2 % 128, pl = t2 / 128;     // consecutive lanes: pieces of one voxel, then the next input x
-                if (s_ov[row] < 0) continue;
-                const int pos = n0 / Cout + pl;
-                const int dz = pos >> 2, dy = (pos >> 1) & 1, dx = pos & 1;
-                const int64_t ov = s_ov[row] + ((int64_t)dz * H2 + dy) * W2 + dx;
-                *reinterpret_cast<uint4 *>(y + ov * ys + p * 8) =
-                    *reinterpret_cast<const uint4 *>(sOut + (size_t)row * pitch + pl * Cout + p * 8);
-            }
-        } else {   // the N tile covers part of one position's channels (Cout > NT)
-            const int pos = n0 / Cout, co0 = n0 - pos * Cout;
-            const int pieces = NT >> 3;
-            const int dz = pos >> 2, dy = (pos >> 1) & 1, dx = pos & 1;
-            for (int i = tid; i < 128 * pieces; i += 128) {
-                const int p = i % pieces, row = i / pieces;
-                if (s_ov[row] < 0) continue;
-                const int64_t ov = s_ov[row] + ((int64_t)dz * H2 + dy) * W2 + dx;
-                *reinterpret_cast<uint4 *>(y + ov * ys + co0 + p * 8) =
-                    *reinterpret_cast<const uint4 *>(sOut + (size_t)row * pitch + p * 8);
+        const int row = (warp & 3) * 32 + (tid & 31);
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        for (int t = warp >> 2; t < ntiles; t += 2) {
+            for (int c = 0; c < NT; c += 16) {
+                uint32_t r[16];
+                tmem_ld16(tmem + lane_base + t * NT + c, r);
+                tmem_wait_ld();
+                uint4 lo, hi;
+                lo.x = pack_bf16(__uint_as_float(r[0]), __uint_as_float(r[1]));   lo.y = pack_bf16(__uint_as_float(r[2]), __uint_as_float(r[3]));
+                lo.z = pack_bf16(__uint_as_float(r[4]), __uint_as_float(r[5]));   lo.w = pack_bf16(__uint_as_float(r[6]), __uint_as_float(r[7]));
+                hi.x = pack_bf16(__uint_as_float(r[8]), __uint_as_float(r[9]));   hi.y = pack_bf16(__uint_as_float(r[10]), __uint_as_float(r[11]));
+                hi.z = pack_bf16(__uint_as_float(r[12]), __uint_as_float(r[13])); hi.w = pack_bf16(__uint_as_float(r[14]), __uint_as_float(r[15]));
+                uint4 *dst = reinterpret_cast<uint4 *>(sOut + (size_t)row * pitch + t * NT + c);
+                dst[0] = lo;
+                dst[1] = hi;
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, tmem_cols);
+    // ---- coalesced stores: piece p (16 bytes = 8 channels) of output position pos of input voxel `row`; a thread keeps
+    // its (row, piece) pairs for all eight positions, so the index arithmetic is done once ----
+    {
+        const int per = Cout >> 3;
+        const int64_t sz = (int64_t)(2 * H) * (2 * W), sy = 2 * W;
+        for (int q = tid; q < 128 * per; q += 256) {   // consecutive lanes: pieces of one voxel, then the next input x
+            const int row = q / per, p = q - row * per;
+            const int64_t base = s_ov[row];
+            if (base < 0) continue;
+            const __nv_bfloat16 *src = sOut + (size_t)row * pitch + p * 8;
+            __nv_bfloat16 *dst = y + base * ys + p * 8;
+#pragma unroll
+            for (int pos = 0; pos < 8; ++pos) {
+                const int64_t off = (pos >> 2) * sz + ((pos >> 1) & 1) * sy + (pos & 1);
+                *reinterpret_cast<uint4 *>(dst + off * ys) = *reinterpret_cast<const uint4 *>(src + pos * Cout);
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace wf
@@ -164,29 +159,26 @@ extern "C" int wf_convtranspose3d_k2s2_ndhwc(const void *x, const void *wpack, v
         return WF_ERR_BAD_SHAPE;
     if (!aligned16(x) || !aligned16(wpack) || !aligned16(y)) return WF_ERR_MISALIGNED;
     const int N = 8 * Cout;
-    // N tile: the largest multiple of 16 (<= 128) that divides N and is a multiple or a divisor of Cout (an N tile then
-    // covers whole output positions, or a slice of one)
+    if (N > 512) return WF_ERR_UNSUPPORTED;                     // all accumulator tiles live in TMEM at once
+    // N tile: the largest multiple of 16 (<= 256) that divides N
     int NT = 0;
-    for (int nt = 128; nt >= 16; nt -= 16)
-        if (N % nt == 0 && (nt % Cout == 0 || Cout % nt == 0)) { NT = nt; break; }
+    for (int nt = 256; nt >= 16; nt -= 16)
+        if (N % nt == 0) { NT = nt; break; }
     if (!NT) return WF_ERR_UNSUPPORTED;
     const int kchunks = Cin / 8;
-    const size_t images = (size_t)kchunks * 2048 + (size_t)kchunks * NT * 16, stage = (size_t)128 * (NT + 8) * 2;
+    const size_t images = (size_t)kchunks * 2048 + (size_t)kchunks * N * 16, stage = (size_t)128 * (N + 8) * 2;
     const size_t smem = images > stage ? images : stage;
-    if (smem > 200 * 1024) return WF_ERR_UNSUPPORTED;
+    if (smem > 220 * 1024) return WF_ERR_UNSUPPORTED;
     static bool attr_done = false;
     if (!attr_done) {
-        WF_CUDA_CHECK(cudaFuncSetAttribute(convT_k2s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(convT_k2s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_done = true;
     }
-    uint32_t cols = 32;
-    while ((int)cols < NT) cols <<= 1;
     const int64_t M = (int64_t)B * D * H * W;
     if (M >= 0x7fffffffLL) return WF_ERR_UNSUPPORTED;
-    dim3 grid((unsigned)((M + 127) / 128), (unsigned)(N / NT));
-    convT_k2s2_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>((const __nv_bfloat16 *)x, (const uint16_t *)wpack,
-                                                                (__nv_bfloat16 *)y, M, Cin, NT, Cout, D, H, W, x_vox_stride,
-                                                                y_vox_stride, cols);
+    convT_k2s2_kernel<<<(unsigned)((M + 127) / 128), 256, smem, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16 *)x, (const uint16_t *)wpack, (__nv_bfloat16 *)y, M, Cin, NT, N / NT, Cout, D, H, W, x_vox_stride,
+        y_vox_stride);
     WF_LAUNCH_CHECK();
     return WF_OK;
 }

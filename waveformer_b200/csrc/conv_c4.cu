@@ -56,8 +56,9 @@ __global__ void __launch_bounds__(128, 4) conv3d_c4_kernel(const TIN *__restrict
     const int tid = threadIdx.x, warp = tid >> 5;
     uint8_t *sB = smem;
     uint8_t *sA = smem + (size_t)kC4Chunks * N * 16;
-    const int pitch = N + 8;  // staging row pitch in elements (16-byte aligned rows, conflict-free 16-byte writes)
-    __nv_bfloat16 *sOut = reinterpret_cast<__nv_bfloat16 *>(sA);
+    // staging: two DENSE sub-tiles [128][n0] and [128][n1] (so that, for dense outputs, tile -> global is a linear copy)
+    __nv_bfloat16 *sOut0 = reinterpret_cast<__nv_bfloat16 *>(sA);
+    __nv_bfloat16 *sOut1 = sOut0 + 128 * n0;
 
     if (warp == 0) tmem_alloc(&tmem_slot, tmem_cols);
     if (tid == 0) {
@@ -119,35 +120,55 @@ __global__ void __launch_bounds__(128, 4) conv3d_c4_kernel(const TIN *__restrict
             }
             const TIN *base = x + (b * S) * 4;
             uint2 tap[28];
-            // nine unconditional loads per z plane (coordinates clamped into the volume, result masked afterwards), so
-            // the loads of a plane are in flight together instead of one predicated load at a time
+            // unconditional loads (coordinates clamped into the volume, result masked afterwards) so that they are in
+            // flight together instead of one predicated load at a time: all 27 for bf16 input (54 registers), nine per z
+            // plane for fp32 input (36 registers)
+            if constexpr (sizeof(TIN) == 2) {
+                // per-axis clamped coordinates and validity, then 32-bit voxel offsets (total < 2^31): one IMAD.WIDE per load
+                int zo[3], yo[3], xo[3];
+                bool zok[3], yok[3], xok[3];
 #pragma unroll
-            for (int dz = -1; dz <= 1; ++dz) {
-                typename std::conditional<sizeof(TIN) == 2, uint2, float4>::type raw[9];
-                bool in[9];
-                const int z2 = zz + dz;
-                const int zc = min(max(z2, 0), g.D - 1);
+                for (int d = 0; d < 3; ++d) {
+                    const int z2 = zz + d - 1, y2 = yy + d - 1, x2 = xx + d - 1;
+                    zok[d] = (unsigned)z2 < (unsigned)g.D; yok[d] = (unsigned)y2 < (unsigned)g.H; xok[d] = (unsigned)x2 < (unsigned)g.W;
+                    zo[d] = (zok[d] ? z2 : zz) * g.H; yo[d] = yok[d] ? y2 : yy; xo[d] = xok[d] ? x2 : xx;
+                }
+                const uint2 *vb = reinterpret_cast<const uint2 *>(base);
+                uint2 raw[27];
 #pragma unroll
-                for (int dy = -1; dy <= 1; ++dy) {
-                    const int y2 = yy + dy;
-                    const int yc = min(max(y2, 0), g.H - 1);
-#pragma unroll
-                    for (int dx = -1; dx <= 1; ++dx) {
-                        const int x2 = xx + dx;
-                        const int xc = min(max(x2, 0), g.W - 1);
-                        const int i = (dy + 1) * 3 + (dx + 1);
-                        in[i] = live && z2 == zc && y2 == yc && x2 == xc;
-                        const TIN *p = base + (((int64_t)zc * g.H + yc) * g.W + xc) * 4;
-                        if constexpr (sizeof(TIN) == 2) raw[i] = __ldg(reinterpret_cast<const uint2 *>(p));
-                        else raw[i] = __ldg(reinterpret_cast<const float4 *>(p));
-                    }
+                for (int t = 0; t < 27; ++t) {
+                    const int dz = t / 9, dy = (t / 3) % 3, dx = t % 3;
+                    raw[t] = __ldg(vb + (uint32_t)((zo[dz] + yo[dy]) * g.W + xo[dx]));
                 }
 #pragma unroll
-                for (int i = 0; i < 9; ++i) {
-                    uint2 v;
-                    if constexpr (sizeof(TIN) == 2) v = raw[i];
-                    else v = make_uint2(pack_bf16(raw[i].x, raw[i].y), pack_bf16(raw[i].z, raw[i].w));
-                    tap[(dz + 1) * 9 + i] = in[i] ? v : make_uint2(0u, 0u);
+                for (int t = 0; t < 27; ++t) {
+                    const int dz = t / 9, dy = (t / 3) % 3, dx = t % 3;
+                    tap[t] = (live && zok[dz] && yok[dy] && xok[dx]) ? raw[t] : make_uint2(0u, 0u);
+                }
+            } else {
+#pragma unroll
+                for (int dz = -1; dz <= 1; ++dz) {
+                    float4 raw[9];
+                    bool in[9];
+                    const int z2 = zz + dz;
+                    const int zc = min(max(z2, 0), g.D - 1);
+#pragma unroll
+                    for (int dy = -1; dy <= 1; ++dy) {
+                        const int y2 = yy + dy;
+                        const int yc = min(max(y2, 0), g.H - 1);
+#pragma unroll
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            const int x2 = xx + dx;
+                            const int xc = min(max(x2, 0), g.W - 1);
+                            const int i = (dy + 1) * 3 + (dx + 1);
+                            in[i] = live && z2 == zc && y2 == yc && x2 == xc;
+                            raw[i] = __ldg(reinterpret_cast<const float4 *>(base + (((int64_t)zc * g.H + yc) * g.W + xc) * 4));
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 9; ++i)
+                        tap[(dz + 1) * 9 + i] = in[i] ? make_uint2(pack_bf16(raw[i].x, raw[i].y), pack_bf16(raw[i].z, raw[i].w))
+                                                      : make_uint2(0u, 0u);
                 }
             }
             tap[27] = make_uint2(0u, 0u);
@@ -181,7 +202,8 @@ __global__ void __launch_bounds__(128, 4) conv3d_c4_kernel(const TIN *__restrict
             lo.z = pack_bf16(__uint_as_float(r[4]), __uint_as_float(r[5]));   lo.w = pack_bf16(__uint_as_float(r[6]), __uint_as_float(r[7]));
             hi.x = pack_bf16(__uint_as_float(r[8]), __uint_as_float(r[9]));   hi.y = pack_bf16(__uint_as_float(r[10]), __uint_as_float(r[11]));
             hi.z = pack_bf16(__uint_as_float(r[12]), __uint_as_float(r[13])); hi.w = pack_bf16(__uint_as_float(r[14]), __uint_as_float(r[15]));
-            uint4 *dst = reinterpret_cast<uint4 *>(sOut + (size_t)tid * pitch + c);
+            // 16 columns never straddle the two outputs (n0 % 16 == 0 is required by the host wrapper when n1 > 0)
+            uint4 *dst = reinterpret_cast<uint4 *>(c < n0 ? sOut0 + (size_t)tid * n0 + c : sOut1 + (size_t)tid * n1 + (c - n0));
             dst[0] = lo;
             dst[1] = hi;
         }
@@ -190,24 +212,35 @@ __global__ void __launch_bounds__(128, 4) conv3d_c4_kernel(const TIN *__restrict
         // ---- coalesced stores: voxel rows of n0 (y0) and n1 (y1) channels ----
         const int64_t v0 = tile * 128;
         const int rows = (int)min((int64_t)128, g.total - v0);
-        {
+        if (ys0 == n0 && (n1 == 0 || ys1 == n1)) {   // dense outputs: the tile is contiguous in global memory too
+            const uint4 *s0 = reinterpret_cast<const uint4 *>(sOut0);
+            uint4 *d0 = reinterpret_cast<uint4 *>(y0 + v0 * n0);
+            for (int i = tid; i < rows * (n0 >> 3); i += 128) d0[i] = s0[i];
+            if (n1 > 0) {
+                const uint4 *s1 = reinterpret_cast<const uint4 *>(sOut1);
+                uint4 *d1 = reinterpret_cast<uint4 *>(y1 + v0 * n1);
+                for (int i = tid; i < rows * (n1 >> 3); i += 128) d1[i] = s1[i];
+            }
+        } else {
             const int per0 = n0 >> 3;
             for (int i = tid; i < rows * per0; i += 128) {
                 const int r = i / per0, p = i % per0;
-                *reinterpret_cast<uint4 *>(y0 + (v0 + r) * ys0 + p * 8) = *reinterpret_cast<const uint4 *>(sOut + (size_t)r * pitch + p * 8);
+                *reinterpret_cast<uint4 *>(y0 + (v0 + r) * ys0 + p * 8) = *reinterpret_cast<const uint4 *>(sOut0 + (size_t)r * n0 + p * 8);
             }
             const int per1 = n1 >> 3;
             for (int i = tid; i < rows * per1; i += 128) {
                 const int r = i / per1, p = i % per1;
-                *reinterpret_cast<uint4 *>(y1 + (v0 + r) * ys1 + p * 8) = *reinterpret_cast<const uint4 *>(sOut + (size_t)r * pitch + n0 + p * 8);
+                *reinterpret_cast<uint4 *>(y1 + (v0 + r) * ys1 + p * 8) = *reinterpret_cast<const uint4 *>(sOut1 + (size_t)r * n1 + p * 8);
             }
         }
-        // ---- statistics of the rounded outputs ----
+        // ---- statistics of the rounded outputs: FHADD / FHFMA consume the bf16 halves directly ----
         if (tid < N) {
             // a tile may straddle two batch elements only if S % 128 != 0; handled row by row in that (rare) case
             const int64_t b_first = (uint32_t)v0 / (uint32_t)S, b_last = (uint32_t)(v0 + rows - 1) / (uint32_t)S;
-            const uint32_t *col = reinterpret_cast<const uint32_t *>(sOut) + cpair;
-            const int wpitch = pitch >> 1;
+            const int c2 = 2 * cpair;                                  // first channel of this thread's pair
+            const uint32_t *col = c2 < n0 ? reinterpret_cast<const uint32_t *>(sOut0) + (c2 >> 1)
+                                          : reinterpret_cast<const uint32_t *>(sOut1) + ((c2 - n0) >> 1);
+            const int wpitch = (c2 < n0 ? n0 : n1) >> 1;
             const int r0 = rhalf * 64, r1 = min(rows, r0 + 64);
             if (b_first == b_last) {
                 if (b_first != acc_b) { flush(); acc_b = b_first; }
@@ -215,9 +248,10 @@ __global__ void __launch_bounds__(128, 4) conv3d_c4_kernel(const TIN *__restrict
 #pragma unroll 8
                 for (int r = r0; r < r1; ++r) {
                     const uint32_t w = col[(size_t)r * wpitch];
-                    const float f0 = __uint_as_float(w << 16), f1 = __uint_as_float(w & 0xffff0000u);
-                    s0 += f0; s1 += f1;
-                    q0 = fmaf(f0, f0, q0); q1 = fmaf(f1, f1, q1);
+                    asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %4;\n\t"
+                        "add.rn.f32.bf16 %0, lo, %0;\n\tadd.rn.f32.bf16 %1, hi, %1;\n\t"
+                        "fma.rn.f32.bf16 %2, lo, lo, %2;\n\tfma.rn.f32.bf16 %3, hi, hi, %3;\n\t}"
+                        : "+f"(s0), "+f"(s1), "+f"(q0), "+f"(q1) : "r"(w));
                 }
                 acc[0] += (double)s0; acc[1] += (double)s1; acc[2] += (double)q0; acc[3] += (double)q1;
             } else {
@@ -262,7 +296,7 @@ extern "C" int wf_conv3d_c4_in_stats(const void *x, int x_dtype, const void *wpa
     if (n1 > 0 && (!y1 || !sums1 || !mean_rstd1)) return WF_ERR_NULL_POINTER;
     if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return WF_ERR_BAD_SHAPE;
     const int N = n0 + n1;
-    if (n0 <= 0 || n1 < 0 || n0 % 8 || n1 % 8 || N % 16 || N > 128) return WF_ERR_BAD_SHAPE;
+    if (n0 <= 0 || n1 < 0 || n0 % 8 || n1 % 8 || N % 16 || N > 128 || (n1 > 0 && n0 % 16)) return WF_ERR_BAD_SHAPE;
     if (y0_vox_stride < n0 || (n1 > 0 && y1_vox_stride < n1) || y0_vox_stride % 8 || (n1 > 0 && y1_vox_stride % 8)) return WF_ERR_BAD_SHAPE;
     if (x_dtype != WF_F32 && x_dtype != WF_BF16) return WF_ERR_BAD_DTYPE;
     if (!aligned16(x) || !aligned16(wpack) || !aligned16(y0) || (n1 > 0 && !aligned16(y1))) return WF_ERR_MISALIGNED;
@@ -272,7 +306,7 @@ extern "C" int wf_conv3d_c4_in_stats(const void *x, int x_dtype, const void *wpa
     g.total = (int64_t)B * D * H * W;
     if (g.total >= 0x7fffffffLL) return WF_ERR_UNSUPPORTED;   // the kernel uses 32-bit voxel arithmetic
     const int64_t ntiles = (g.total + 127) / 128;
-    const size_t stage = (size_t)128 * (N + 8) * 2, aimg = (size_t)kC4Chunks * 2048;
+    const size_t stage = (size_t)128 * N * 2, aimg = (size_t)kC4Chunks * 2048;
     const size_t smem = (size_t)kC4Chunks * N * 16 + (stage > aimg ? stage : aimg);
     uint32_t cols = 32;
     while ((int)cols < N) cols <<= 1;

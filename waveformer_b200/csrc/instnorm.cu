@@ -274,6 +274,94 @@ __global__ void __launch_bounds__(256, KP <= 4 ? 2 : 1) instnorm_apply_head_kern
     }
 }
 
+// bf16 fast path of the fused head: one thread = one voxel.  All CPV 16-byte packets of x and of the residual are loaded
+// up front (2 * CPV independent loads in flight per thread), everything else is thread-local: no shuffles, no barriers in
+// the loop.  Per-channel constants live in shared memory as two float4 per channel - (scale_x, scale_r, shift, 0) and the
+// K <= 4 head weights - read as warp-wide broadcasts.  grid = (blocks, B): a block stays inside one batch element.
+template <typename TO, int CPV>
+__global__ void __launch_bounds__(256) instnorm_apply_head_voxel_kernel(
+    const __nv_bfloat16 *__restrict__ x, const float *__restrict__ mr, const __nv_bfloat16 *__restrict__ res,
+    const float *__restrict__ res_mr, const float *__restrict__ hw, const float *__restrict__ hb, TO *__restrict__ out,
+    int64_t S, int K, int64_t xs, int64_t rs, int act, float slope) {
+    constexpr int C = CPV * 8;
+    __shared__ float4 s_norm[C], s_w[C];
+    const int b = blockIdx.y;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float m = mr[((int64_t)b * C + c) * 2], r = mr[((int64_t)b * C + c) * 2 + 1];
+        float sr = 0.f, sh = -m * r;
+        if (res != nullptr) {
+            sr = 1.f;
+            if (res_mr != nullptr) {
+                sr = res_mr[((int64_t)b * C + c) * 2 + 1];
+                sh = fmaf(-res_mr[((int64_t)b * C + c) * 2], sr, sh);
+            }
+        }
+        s_norm[c] = make_float4(r, sr, sh, 0.f);
+        s_w[c] = make_float4(hw[c], K > 1 ? hw[C + c] : 0.f, K > 2 ? hw[2 * C + c] : 0.f, K > 3 ? hw[3 * C + c] : 0.f);
+    }
+    __syncthreads();
+    const float4 bias = make_float4(hb ? hb[0] : 0.f, (hb && K > 1) ? hb[1] : 0.f, (hb && K > 2) ? hb[2] : 0.f,
+                                    (hb && K > 3) ? hb[3] : 0.f);
+    const __nv_bfloat16 *xb = x + (int64_t)b * S * xs;
+    const __nv_bfloat16 *rb = res != nullptr ? res + (int64_t)b * S * rs : nullptr;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < S; v += (int64_t)gridDim.x * blockDim.x) {
+        uint4 xr[CPV], rr[CPV];
+#pragma unroll
+        for (int j = 0; j < CPV; ++j) xr[j] = __ldg(reinterpret_cast<const uint4 *>(xb + v * xs) + j);
+        if (rb != nullptr) {
+#pragma unroll
+            for (int j = 0; j < CPV; ++j) rr[j] = __ldg(reinterpret_cast<const uint4 *>(rb + v * rs) + j);
+        }
+        float a0 = bias.x, a1 = bias.y, a2 = bias.z, a3 = bias.w;
+#pragma unroll
+        for (int j = 0; j < CPV; ++j) {
+            float f[8], r[8];
+            Pack<__nv_bfloat16>::unpack(xr[j], f);
+            if (rb != nullptr) Pack<__nv_bfloat16>::unpack(rr[j], r);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float4 n = s_norm[j * 8 + e], w = s_w[j * 8 + e];
+                float t = fmaf(f[e], n.x, n.z);
+                if (rb != nullptr) t = fmaf(r[e], n.y, t);
+                if (act == 1) t = fmaxf(t, 0.f);
+                else if (act == 2) t = fmaxf(t, t * slope);   // LeakyReLU for 0 <= slope <= 1
+                a0 = fmaf(t, w.x, a0); a1 = fmaf(t, w.y, a1); a2 = fmaf(t, w.z, a2); a3 = fmaf(t, w.w, a3);
+            }
+        }
+        TO *dst = out + ((int64_t)b * S + v) * K;
+        if constexpr (sizeof(TO) == 4) {
+            if (K == 4) {
+                *reinterpret_cast<float4 *>(dst) = make_float4(a0, a1, a2, a3);
+                continue;
+            }
+        }
+        dst[0] = from_f32<TO>(a0);
+        if (K > 1) dst[1] = from_f32<TO>(a1);
+        if (K > 2) dst[2] = from_f32<TO>(a2);
+        if (K > 3) dst[3] = from_f32<TO>(a3);
+    }
+}
+
+template <typename TO>
+static bool apply_head_voxel_launch(const __nv_bfloat16 *x, const float *mr, const __nv_bfloat16 *res, const float *res_mr,
+                                    const float *hw, const float *hb, TO *out, int B, int64_t S, int C, int K, int64_t xs,
+                                    int64_t rs, int act, float slope, cudaStream_t st) {
+    if (K > 4 || C % 8 != 0 || B > 65535 || (act == 2 && (slope < 0.f || slope > 1.f))) return false;
+    const int64_t want = (S + 255) / 256;
+    dim3 grid((unsigned)min(want, (int64_t)kNumSMs * 6), (unsigned)B);
+#define WF_HV(CPV_) instnorm_apply_head_voxel_kernel<TO, CPV_><<<grid, 256, 0, st>>>(x, mr, res, res_mr, hw, hb, out, S, K, xs, rs, act, slope)
+    switch (C / 8) {
+        case 2: WF_HV(2); break;
+        case 4: WF_HV(4); break;
+        case 6: WF_HV(6); break;
+        case 8: WF_HV(8); break;
+        case 12: WF_HV(12); break;
+        default: return false;
+    }
+#undef WF_HV
+    return true;
+}
+
 template <typename T, typename TO>
 static int apply_head_launch(const T *x, const float *mr, const T *res, const float *res_mr, const float *hw, const float *hb,
                              TO *out, int B, int64_t S, int C, int K, int64_t xs, int64_t rs, int act, float slope,
@@ -282,6 +370,12 @@ static int apply_head_launch(const T *x, const float *mr, const T *res, const fl
     const size_t e = sizeof(T);
     if (C % V != 0 || C / V > 32 || K < 1 || K > 16) return WF_ERR_UNSUPPORTED;
     if (!aligned16(x) || (xs * e) % 16 != 0 || (res != nullptr && (!aligned16(res) || (rs * e) % 16 != 0))) return WF_ERR_MISALIGNED;
+    if constexpr (sizeof(T) == 2) {
+        if (apply_head_voxel_launch<TO>(x, mr, res, res_mr, hw, hb, out, B, S, C, K, xs, rs, act, slope, st)) {
+            WF_LAUNCH_CHECK();
+            return WF_OK;
+        }
+    }
     const int cpv = C / V;
     const int64_t total = (int64_t)B * S;
     const int vpw = 32 / cpv;
