@@ -161,6 +161,12 @@ int wf_layernorm_ndhwc(const void *x, const float *gamma, const float *beta, voi
                        int out_dtype, int64_t rows, int C, int64_t x_row_stride, int64_t y_row_stride, float eps, int gelu,
                        void *stream);
 
+/* out = a + b + c + bias[channel]: the tail of a transformer block, x + LN(x) + ffn(LN(x)) (+ the fc bias) in ONE fp32 pass
+ * (reference network_models/wave_helper.py:293 and :509).  a, b, out fp32 [rows, C]; c fp32 or bf16 [rows, C]; bias fp32 [C]
+ * or NULL; C % 4 == 0. */
+int wf_residual_sum(const float *a, const float *b, const void *c, int c_dtype, const float *bias, float *out, int64_t rows,
+                    int C, void *stream);
+
 /* y = base + sum_s trilinear_upsample(srcs[s]) (sources summed in order, then added to base; base may be NULL).
  * srcs[s]: [B, d_s, h_s, w_s, C] dense channels-last of src_dtype, src_dims = int[3 * nsrc]; base / y: [B, D, H, W, C]
  * of io_dtype with voxel strides.  align_corners = 0 reproduces F.interpolate(size=(D,H,W), mode='trilinear') + the

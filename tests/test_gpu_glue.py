@@ -192,3 +192,25 @@ def test_conv_transpose_k2s2_scatters_into_concat_buffer(shape, cout):
     want = F.conv_transpose3d(x.float().permute(0, 4, 1, 2, 3), w.float(), stride=2).permute(0, 2, 3, 4, 1)
     assert max_rel(cat[..., :cout].float().cpu(), want.cpu()) < 6e-3
     assert bool((cat[..., cout:] == 7.0).all())                      # the skip half is untouched
+
+
+def test_trilinear_upsample_generic_ratio_uses_point_kernel():
+    """Scale factors below 2 fall back to the one-output-per-thread kernel (the 2x2x2-cell kernel needs >= 2)."""
+    from waveformer_b200 import ops
+    src = seeded_randn((1, 8, 12, 16, 24), 130)
+    size = (12, 18, 24)
+    want = F.interpolate(src.permute(0, 4, 1, 2, 3), size=size, mode="trilinear", align_corners=False).permute(0, 2, 3, 4, 1)
+    got = ops.upsample_trilinear_add([src.cuda()], size)
+    assert max_rel(got.cpu(), want) < 3e-6
+
+
+@pytest.mark.parametrize("c_dtype", [torch.float32, torch.bfloat16])
+def test_residual_sum_matches_torch(c_dtype):
+    from waveformer_b200 import ops
+    a, b = seeded_randn((3, 5, 7, 9, 48), 140).cuda(), seeded_randn((3, 5, 7, 9, 48), 141).cuda()
+    c = seeded_randn((3, 5, 7, 9, 48), 142).cuda().to(c_dtype)
+    bias = seeded_randn((48,), 143).cuda()
+    got = ops.residual_sum(a, b, c, bias)
+    want = a + b + c.float() + bias
+    assert got.dtype == torch.float32 and float((got - want).abs().max()) < 1e-6
+    assert float((ops.residual_sum(a, b, c) - (a + b + c.float())).abs().max()) < 1e-6

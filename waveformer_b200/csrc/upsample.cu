@@ -122,6 +122,130 @@ __global__ void __launch_bounds__(256) upsample_add_kernel(UpArgs a, const TB *_
     store_n<TO, VEC>(y + vox * ys + c0, acc);
 }
 
+// ---- cell variant: one thread = a 2 x 2 x 2 block of output voxels x 4 channels -------------------------------------
+// For upscaling by >= 2 (source step per output voxel <= 0.5) the two outputs of an aligned pair read at most three
+// distinct source points per axis, so the cell needs 3 x 3 x 3 source loads per level instead of 8 x 8, and the index
+// arithmetic is paid once per 8 outputs.  Interpolation is separable: x pass (3 -> 2), y pass (3 -> 2), z pass (3 -> 2).
+struct AxisPair {
+    int p[3];        // source points
+    float wa[3];     // weights of output 2k on the points
+    float wb[3];     // weights of output 2k + 1
+};
+
+__device__ __forceinline__ AxisPair axis_pair(int o, float scale, int in, int align) {
+    int i0a, i1a, i0b, i1b;
+    float la, lb;
+    src_index(o, scale, in, align, i0a, i1a, la);
+    src_index(o + 1, scale, in, align, i0b, i1b, lb);
+    AxisPair r;
+    r.p[0] = i0a; r.p[1] = i1a; r.p[2] = i1b;
+    // weights land on the FIRST slot holding the same source index (clamped borders repeat indices); static indexing only
+    const bool a_same = i1a == i0a;
+    r.wa[0] = (1.f - la) + (a_same ? la : 0.f);
+    r.wa[1] = a_same ? 0.f : la;
+    r.wa[2] = 0.f;
+    const int s0 = i0b == r.p[0] ? 0 : (i0b == r.p[1] ? 1 : 2);
+    const int s1 = i1b == r.p[0] ? 0 : (i1b == r.p[1] ? 1 : 2);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) r.wb[k] = (s0 == k ? 1.f - lb : 0.f) + (s1 == k ? lb : 0.f);
+    return r;
+}
+
+template <typename T> __device__ __forceinline__ void load4(const T *p, float (&v)[4]) { load_n<T, 4>(p, v); }
+
+// grid: x = ceil((W / 2) * (C / 4) / 128), y = H / 2, z = B * D / 2; 128 threads (~148 registers each)
+template <typename TS, typename TB, typename TO>
+__global__ void __launch_bounds__(128) upsample_cell_kernel(UpArgs a, const TB *__restrict__ base, TO *__restrict__ y, int D,
+                                                            int H, int W, int C, int c4s, int64_t bs, int64_t ys) {
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= (W >> 1) * c4s) return;
+    const int xc = i / c4s, cv = i - xc * c4s;
+    const int yc = blockIdx.y;
+    const int zc = blockIdx.z % (D >> 1);
+    const int64_t b = blockIdx.z / (D >> 1);
+    const int c0 = cv * 4;
+    float out[2][2][2][4];
+#pragma unroll
+    for (int zo = 0; zo < 2; ++zo)
+#pragma unroll
+        for (int yo = 0; yo < 2; ++yo)
+#pragma unroll
+            for (int xo = 0; xo < 2; ++xo)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) out[zo][yo][xo][e] = 0.f;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {   // static index into the by-value argument struct (a dynamic one would copy it to local memory)
+        if (s >= a.nsrc) break;
+        const UpSrc &u = a.src[s];
+        const AxisPair az = axis_pair(2 * zc, u.sz, u.d, a.align);
+        const AxisPair ay = axis_pair(2 * yc, u.sy, u.h, a.align);
+        const AxisPair ax = axis_pair(2 * xc, u.sx, u.w, a.align);
+        const TS *p = reinterpret_cast<const TS *>(u.ptr) + (int64_t)b * u.d * u.h * u.w * C + c0;
+#pragma unroll
+        for (int iz = 0; iz < 3; ++iz) {
+            float ty[2][2][4];   // [y output][x output][channel] for this z point
+#pragma unroll
+            for (int yo = 0; yo < 2; ++yo)
+#pragma unroll
+                for (int xo = 0; xo < 2; ++xo)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) ty[yo][xo][e] = 0.f;
+#pragma unroll
+            for (int iy = 0; iy < 3; ++iy) {
+                const TS *row = p + ((int64_t)az.p[iz] * u.h + ay.p[iy]) * u.w * C;
+                float v[3][4];
+#pragma unroll
+                for (int ix = 0; ix < 3; ++ix) load4<TS>(row + (int64_t)ax.p[ix] * C, v[ix]);
+                float tx[2][4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    tx[0][e] = fmaf(ax.wa[2], v[2][e], fmaf(ax.wa[1], v[1][e], ax.wa[0] * v[0][e]));
+                    tx[1][e] = fmaf(ax.wb[2], v[2][e], fmaf(ax.wb[1], v[1][e], ax.wb[0] * v[0][e]));
+                }
+#pragma unroll
+                for (int xo = 0; xo < 2; ++xo)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        ty[0][xo][e] = fmaf(ay.wa[iy], tx[xo][e], ty[0][xo][e]);
+                        ty[1][xo][e] = fmaf(ay.wb[iy], tx[xo][e], ty[1][xo][e]);
+                    }
+            }
+#pragma unroll
+            for (int yo = 0; yo < 2; ++yo)
+#pragma unroll
+                for (int xo = 0; xo < 2; ++xo)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        out[0][yo][xo][e] = fmaf(az.wa[iz], ty[yo][xo][e], out[0][yo][xo][e]);
+                        out[1][yo][xo][e] = fmaf(az.wb[iz], ty[yo][xo][e], out[1][yo][xo][e]);
+                    }
+        }
+    }
+#pragma unroll
+    for (int zo = 0; zo < 2; ++zo)
+#pragma unroll
+        for (int yo = 0; yo < 2; ++yo)
+#pragma unroll
+            for (int xo = 0; xo < 2; ++xo) {
+                const int64_t vox = ((b * D + 2 * zc + zo) * H + 2 * yc + yo) * (int64_t)W + 2 * xc + xo;
+                if (base != nullptr) {
+                    float bv[4];
+                    load_n<TB, 4>(base + vox * bs + c0, bv);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) out[zo][yo][xo][e] = bv[e] + out[zo][yo][xo][e];
+                }
+                store_n<TO, 4>(y + vox * ys + c0, out[zo][yo][xo]);
+            }
+}
+
+// the cell kernel applies when every axis of every source is upscaled by at least 2 and the output extents are even
+static bool cell_ok(const UpArgs &a, int D, int H, int W, int C) {
+    if ((D | H | W) & 1 || C % 4 != 0 || (D >> 1) > 65535 || (H >> 1) > 65535) return false;
+    for (int s = 0; s < a.nsrc; ++s)
+        if (a.src[s].sz > 0.5f || a.src[s].sy > 0.5f || a.src[s].sx > 0.5f) return false;
+    return true;
+}
+
 template <typename TS, typename TB, typename TO>
 static int upsample_launch(const UpArgs &a, const TB *base, TO *y, int B, int D, int H, int W, int C, int64_t bs,
                            int64_t ys, cudaStream_t st) {
@@ -129,6 +253,12 @@ static int upsample_launch(const UpArgs &a, const TB *base, TO *y, int B, int D,
     bool vec = (C % V == 0) && aligned16(y) && (base == nullptr || aligned16(base)) && (bs * sizeof(TB)) % 16 == 0 &&
                (ys * sizeof(TO)) % 16 == 0;
     for (int s = 0; s < a.nsrc; ++s) vec = vec && aligned16(a.src[s].ptr);
+    if (vec && cell_ok(a, D, H, W, C) && (int64_t)B * (D >> 1) <= 65535) {
+        dim3 grid((unsigned)(((W >> 1) * (C / 4) + 127) / 128), (unsigned)(H >> 1), (unsigned)(B * (D >> 1)));
+        upsample_cell_kernel<TS, TB, TO><<<grid, 128, 0, st>>>(a, base, y, D, H, W, C, C / 4, bs, ys);
+        WF_LAUNCH_CHECK();
+        return WF_OK;
+    }
     if (vec) {
         const int64_t total = (int64_t)B * D * H * W * (C / V);
         dim3 grid((unsigned)((W * (C / V) + 255) / 256), (unsigned)H, (unsigned)(B * D));

@@ -151,7 +151,7 @@ class CCF_FFN(nn.Module):
             if m.bias is not None:
                 m.bias.data.zero_()
 
-    def ffn_fused(self, x: torch.Tensor, xop: torch.Tensor) -> torch.Tensor:
+    def ffn_fused(self, x: torch.Tensor, xop: torch.Tensor, defer_bias: bool = False):
         """The FFN branch WITHOUT its residual.  ``xop`` = x in the GEMM operand type (bf16 under the inference policy,
         where x itself is the fp32 copy); the 4C-wide intermediates live in the operand type, the result is returned in
         x's type - unrounded fp32 accumulators when x is the fp32 stream."""
@@ -162,7 +162,10 @@ class CCF_FFN(nn.Module):
         t = ops.dwconv3d_channels_last(t, *self._packed_dwconv())          # hand-written stencil
         t = _ln(self.norm2, t, gelu=True)
         if x.dtype == torch.float32 and cd != torch.float32:
-            return _linear_f32_out(t, ops.cast_cached(self.fc.weight, cd)) + ops.f32_cached(self.fc.bias)
+            f = _linear_f32_out(t, ops.cast_cached(self.fc.weight, cd))
+            if defer_bias:
+                return f, self.fc.bias       # the caller adds the bias in its fused residual pass
+            return f + ops.f32_cached(self.fc.bias)
         return F.linear(t, ops.cast_cached(self.fc.weight, cd), ops.cast_cached(self.fc.bias, cd))
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -346,7 +349,8 @@ class Block(nn.Module):
             # fp32 stream: LayerNorm writes the fp32 copy (CCF_FFN's own residual, wave_helper.py:293) and the bf16 GEMM
             # operand in one pass; y + n + ffn(n) is accumulated in fp32
             n, nop = _ln(self.norm2, y, also_bf16=True)
-            y = (y + n).add_(self.mlp.ffn_fused(n, nop))
+            f, fb = self.mlp.ffn_fused(n, nop, defer_bias=True)
+            y = ops.residual_sum(y, n, f, fb)          # y + n + ffn(n) + fc bias: one pass
         else:
             y = y + self.mlp(_ln(self.norm2, y))
         if self.level > 0:

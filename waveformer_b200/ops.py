@@ -652,6 +652,22 @@ def layer_norm_cl(x: torch.Tensor, weight: Optional[torch.Tensor], bias: Optiona
     return (y, y2) if also_bf16 else y
 
 
+def residual_sum(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``a + b + c + bias`` over the last (channel) dim in one pass; a, b fp32 contiguous, c fp32 or bf16."""
+    dev = _need_cuda(a, b, c, bias)
+    if a.dtype != torch.float32 or b.dtype != torch.float32 or a.shape != b.shape or a.shape != c.shape:
+        raise ValueError("residual_sum: a, b fp32 and all three of one shape")
+    a, b, c = a.contiguous(), b.contiguous(), c.contiguous()
+    C = a.shape[-1]
+    out = torch.empty_like(a)
+    with torch.cuda.device(dev):
+        st = _lib.lib().wf_residual_sum(a.data_ptr(), b.data_ptr(), c.data_ptr(), _dtype_code(c), _ptr(f32_cached(bias)),
+                                        out.data_ptr(), a.numel() // C, C, _stream(dev))
+    _lib.check(st, "wf_residual_sum")
+    _count()
+    return out
+
+
 def upsample_trilinear_add(srcs, size, base: Optional[torch.Tensor] = None, align_corners: bool = False,
                            out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
     """``base + sum_s trilinear(srcs[s] -> size)`` for channels-last ``[B, d, h, w, C]`` sources (1..3 of them)."""
