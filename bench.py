@@ -205,7 +205,8 @@ def workload_config(volumes: int):
                          "gaussian blending, sw_batch_size 2 (BASELINE configs[2]; configs[3] at N>1)",
                 volumes_per_step=volumes, windows_per_volume=WINDOWS_PER_VOLUME, roi=list(ROI), overlap=0.5,
                 blend="gaussian", sw_batch_size=2, parallelism="windows sharded over one process per GPU",
-                l2_policy="inputs and activations (>= 143 MB per volume) exceed the 126 MB L2; no explicit flush")
+                l2_policy="inputs and activations (>= 143 MB per volume) exceed the 126 MB L2; no explicit flush",
+                launch="window forward replayed as a CUDA graph (waveformer_b200.graphs.GraphedForward)")
 
 
 def main():
@@ -217,6 +218,7 @@ def main():
     ap.add_argument("--volumes", type=int, default=0, help="volumes per step (default: one per GPU)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cuda-graph", action="store_true", help="launch every kernel of the window forward eagerly")
     ap.add_argument("--no-kernel-rooflines", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -244,6 +246,9 @@ def main():
     torch.manual_seed(0)  # identical random-init weights on every rank
     from waveformer_b200 import prepare_inference
     model = prepare_inference(Waveformer(**MODEL_KW).eval().to(dev), dtype)   # bf16 = the documented precision policy
+    if not args.no_cuda_graph:
+        from waveformer_b200.graphs import GraphedForward
+        model = GraphedForward(model)      # the window forward (~450 launches) is replayed as one CUDA graph
     host = torch.randn((volumes,) + VOL, generator=torch.Generator().manual_seed(1)).pin_memory()
     resident = host.to(dev)
     inferer = SlidingWindowInferer(roi_size=ROI, sw_batch_size=2, overlap=0.5, mode="gaussian", return_labels=True)

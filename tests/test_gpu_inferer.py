@@ -87,3 +87,29 @@ def test_volume_240x240x155_bf16_matches_reference():
     # the class populations must still agree to 1 %
     hist = np.bincount(inf.labels.reshape(-1).cpu().numpy(), minlength=4)
     assert np.abs(hist - g["label_hist"]).sum() <= 1e-2 * hist.sum()
+
+
+def test_cuda_graph_replay_matches_eager():
+    """GraphedForward (the bench's launch mode): captured replay of the window forward = the eager forward, bit for bit,
+    including through the sliding-window inferer (static output buffer consumed before the next replay)."""
+    from waveformer_b200 import prepare_inference
+    from waveformer_b200.graphs import GraphedForward
+    from waveformer_b200.inferers import SlidingWindowInferer
+    from waveformer_b200.network_models import Waveformer
+    cfg = ModelConfig(img_size=(64,) * 3)
+    m = Waveformer(**cfg.kwargs()).eval()
+    m.load_state_dict(make_state_dict(cfg, seed=0), strict=True)
+    m = prepare_inference(m.cuda(), torch.bfloat16)
+    g = GraphedForward(m)
+    x = seeded_randn((2, 4, 64, 64, 64), 77).cuda().contiguous(memory_format=torch.channels_last_3d)
+    with torch.no_grad():
+        want = m(x).clone()
+        got1 = g(x).clone()
+        got2 = g(x * 1.0).clone()        # a different input tensor with the same signature -> replay with a copy-in
+    assert torch.equal(got1, want) and torch.equal(got2, want)
+    vol = seeded_randn((1, 4, 96, 80, 70), 78).cuda()
+    inf = SlidingWindowInferer(roi_size=(64,) * 3, sw_batch_size=2, overlap=0.5, mode="gaussian")
+    with torch.no_grad():
+        a = inf(vol, m).clone()
+        b = inf(vol, g)
+    assert float((a - b).abs().max()) <= 1e-6 * float(a.abs().max())    # atomics: summation order may differ
