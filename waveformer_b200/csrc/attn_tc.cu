@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(128) linear_tc_kernel(const TA *__restrict__ A
 constexpr int kBiasPitch = 520;                       // 16-bit elements per bias row (512 + 8 pad: conflict-free LDS.128)
 constexpr int kBiasBytes = 128 * kBiasPitch * 2;      // 133120 per (head, query tile)
 constexpr int kStageBytes = 4096 + 16384 + 16384;     // Q tile [2][128][8] + K [2][512][8] + V [2][512][8]
-constexpr int kCoreSmem = kBiasBytes + 2 * kStageBytes + 2 * 2 * 128 * 4;  // + row max / row sum exchange
+constexpr int kCoreSmem = kBiasBytes + 2 * kStageBytes + 2 * 4 * 128 * 4;  // + row max / row sum exchange (4 key quarters)
 
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
@@ -239,9 +239,13 @@ __global__ void relpos_bias_image_kernel(const void *__restrict__ table, int tab
 }
 
 // grid = combos * groups, combos = heads * 4 (head, 128-query tile); CTA (combo, g) walks windows g, g+groups, ...
-// 256 threads: warp w handles TMEM lanes 32*(w%4).. (query rows) and key half w/4.
+// 512 threads: warp w handles TMEM lanes 32*(w%4).. (query rows) and key quarter w/4 (128 keys).  Sixteen warps instead
+// of eight double the latency hiding of the TMEM-load -> FHADD / ex2 chains (the softmax passes were issue-latency bound
+// at 2 warps per scheduler, profiles/r01_stalls_attention_s1L1.txt).
+// TMEM columns: S = [0, 512) fp32; quarter q packs its P (16-bit) in place into [128q, 128q + 64); O accumulates in
+// [64, 80), which quarter 0 has consumed by then.
 template <bool F16>
-__global__ void __launch_bounds__(256, 1) attn_core_tc_kernel(const uint16_t *__restrict__ qkv,
+__global__ void __launch_bounds__(512, 1) attn_core_tc_kernel(const uint16_t *__restrict__ qkv,
                                                               const uint16_t *__restrict__ bias_img,
                                                               uint16_t *__restrict__ o, int heads, int64_t B_,
                                                               int groups) {
@@ -251,13 +255,13 @@ __global__ void __launch_bounds__(256, 1) attn_core_tc_kernel(const uint16_t *__
     __shared__ uint32_t tmem_slot;
     uint16_t *sBias = reinterpret_cast<uint16_t *>(smem);
     uint8_t *sStage = smem + kBiasBytes;
-    float *sMax = reinterpret_cast<float *>(smem + kBiasBytes + 2 * kStageBytes);  // [2][128]
-    float *sSum = sMax + 256;                                                       // [2][128]
+    float *sMax = reinterpret_cast<float *>(smem + kBiasBytes + 2 * kStageBytes);  // [4][128]
+    float *sSum = sMax + 512;                                                       // [4][128]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int combo = blockIdx.x % (heads * 4), g = blockIdx.x / (heads * 4);
     const int hh = combo >> 2, qt = combo & 3;
-    const int half = warp >> 2;                    // key half handled by this warp
+    const int quarter = warp >> 2;                 // key quarter (128 keys) handled by this warp
     const int row = (warp & 3) * 32 + lane;        // query row inside the tile = TMEM lane
     const int C = heads * 16;
 
@@ -315,12 +319,12 @@ __global__ void __launch_bounds__(256, 1) attn_core_tc_kernel(const uint16_t *__
         mbar_wait(&bar_s, ph);
         tc_fence_after();
 
-        const uint32_t scol = tmem + lane_base + half * 256;
-        const uint16_t *brow = sBias + row * kBiasPitch + half * 256;
-        // ---- pass 1: row maximum of s + bias over this warp's 256 keys (FHADD + FMNMX3: 1.5 ALU ops per key) ----
+        const uint32_t scol = tmem + lane_base + quarter * 128;
+        const uint16_t *brow = sBias + row * kBiasPitch + quarter * 128;
+        // ---- pass 1: row maximum of s + bias over this warp's 128 keys (FHADD + FMNMX3: 1.5 ALU ops per key) ----
         float mx = -INFINITY;
 #pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < 4; ++c) {
             uint32_t r[32];
             tmem_ld32(scol + c * 32, r);
             tmem_wait_ld();
@@ -336,13 +340,13 @@ __global__ void __launch_bounds__(256, 1) attn_core_tc_kernel(const uint16_t *__
                 }
             }
         }
-        sMax[half * 128 + row] = mx;
+        sMax[quarter * 128 + row] = mx;
         __syncthreads();
-        mx = fmaxf(sMax[row], sMax[128 + row]);
+        mx = fmaxf(fmaxf(sMax[row], sMax[128 + row]), fmaxf(sMax[256 + row], sMax[384 + row]));
         // ---- pass 2: p = 2^(s + bias - max), row sum, P (16-bit) written over S in place ----
         float sum = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < 4; ++c) {
             uint32_t r[32];
             tmem_ld32(scol + c * 32, r);
             tmem_wait_ld();
@@ -363,16 +367,17 @@ __global__ void __launch_bounds__(256, 1) attn_core_tc_kernel(const uint16_t *__
             tmem_st16(scol + c * 16, pk);  // keys [32c, 32c+32) of this half -> 16 packed columns (already consumed S)
         }
         tmem_wait_st();
-        sSum[half * 128 + row] = sum;
+        sSum[quarter * 128 + row] = sum;
         tc_fence_before();
         __syncthreads();
-        // ---- O[128 x 16] = P[128 x 512] V[512 x 16]: A = P from TMEM, B = V (MN-major), D = TMEM columns [128,144) ----
+        // ---- O[128 x 16] = P[128 x 512] V[512 x 16]: A = P from TMEM (k-step ks = keys [16 ks, 16 ks + 16) = 8 packed
+        // columns at 128 * (ks / 8) + 8 * (ks % 8)), B = V (MN-major), D = TMEM columns [64, 80) ----
         if (tid == 0) {
             tc_fence_after();
 #pragma unroll 1
             for (int ks = 0; ks < 32; ++ks) {
-                const uint32_t pa = tmem + (ks < 16 ? ks * 8 : 256 + (ks - 16) * 8);
-                mma_ts(tmem + 128, pa, smem_desc(sV + ks * 256, 128, 8192), idesc_o, ks > 0 ? 1u : 0u);
+                const uint32_t pa = tmem + (ks >> 3) * 128 + (ks & 7) * 8;
+                mma_ts(tmem + 64, pa, smem_desc(sV + ks * 256, 128, 8192), idesc_o, ks > 0 ? 1u : 0u);
             }
             mma_commit(&bar_o);
         }
@@ -380,9 +385,9 @@ __global__ void __launch_bounds__(256, 1) attn_core_tc_kernel(const uint16_t *__
         tc_fence_after();
         if (warp < 4) {
             uint32_t r[16];
-            tmem_ld16(tmem + lane_base + 128, r);
+            tmem_ld16(tmem + lane_base + 64, r);
             tmem_wait_ld();
-            const float inv = 1.f / (sSum[row] + sSum[128 + row]);
+            const float inv = 1.f / ((sSum[row] + sSum[128 + row]) + (sSum[256 + row] + sSum[384 + row]));
             uint4 lo, hi;
             lo.x = pack16<F16>(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
             lo.y = pack16<F16>(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
@@ -470,7 +475,7 @@ static int attn_tc_run(const void *x, int x_dtype, const uint16_t *qkv_w, const 
         int groups = kNumSMs / combos;
         if (groups < 1) groups = 1;
         if (groups > B_) groups = (int)B_;
-        attn_core_tc_kernel<F16><<<combos * groups, 256, kCoreSmem, st>>>(qkv, bias_img, obuf, heads, B_, groups);
+        attn_core_tc_kernel<F16><<<combos * groups, 512, kCoreSmem, st>>>(qkv, bias_img, obuf, heads, B_, groups);
         WF_LAUNCH_CHECK();
     }
     {
