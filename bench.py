@@ -200,11 +200,11 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
-def workload_config(volumes: int):
+def workload_config(volumes: int, sw_batch: int = 2):
     return dict(workload="WaveFormer sliding-window inference, synthetic 4x240x240x155 volume(s), ROI 128^3, overlap 0.5, "
-                         "gaussian blending, sw_batch_size 2 (BASELINE configs[2]; configs[3] at N>1)",
+                         f"gaussian blending, sw_batch_size {sw_batch} (BASELINE configs[2]; configs[3] at N>1)",
                 volumes_per_step=volumes, windows_per_volume=WINDOWS_PER_VOLUME, roi=list(ROI), overlap=0.5,
-                blend="gaussian", sw_batch_size=2, parallelism="windows sharded over one process per GPU",
+                blend="gaussian", sw_batch_size=sw_batch, parallelism="windows sharded over one process per GPU",
                 l2_policy="inputs and activations (>= 143 MB per volume) exceed the 126 MB L2; no explicit flush",
                 launch="window forward replayed as a CUDA graph (waveformer_b200.graphs.GraphedForward)")
 
@@ -219,6 +219,7 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true", help="launch every kernel of the window forward eagerly")
+    ap.add_argument("--sw-batch", type=int, default=2, help="windows per forward (the reference's 4_predict.py uses 2)")
     ap.add_argument("--no-kernel-rooflines", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -251,7 +252,7 @@ def main():
         model = GraphedForward(model)      # the window forward (~450 launches) is replayed as one CUDA graph
     host = torch.randn((volumes,) + VOL, generator=torch.Generator().manual_seed(1)).pin_memory()
     resident = host.to(dev)
-    inferer = SlidingWindowInferer(roi_size=ROI, sw_batch_size=2, overlap=0.5, mode="gaussian", return_labels=True)
+    inferer = SlidingWindowInferer(roi_size=ROI, sw_batch_size=args.sw_batch, overlap=0.5, mode="gaussian", return_labels=True)
 
     def barrier():
         if world > 1:
@@ -349,7 +350,7 @@ def main():
                           "volume time = 18 x patch time", patch_seconds=sec)
     line = dict(metric="sliding_window_voxels_per_s", value=value, unit="voxels/s", n_gpus=world, steps=args.steps,
                 warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype=args.dtype, data="synthetic", config=workload_config(volumes), clocks=clocks, e2e=e2e,
+                dtype=args.dtype, data="synthetic", config=workload_config(volumes, args.sw_batch), clocks=clocks, e2e=e2e,
                 gpu_launches=launches, roofline=roof, roofline_kernels=kernels, cpu_baseline=cpu)
     print(json.dumps(line))
     if world > 1:

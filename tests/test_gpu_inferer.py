@@ -113,3 +113,44 @@ def test_cuda_graph_replay_matches_eager():
         a = inf(vol, m).clone()
         b = inf(vol, g)
     assert float((a - b).abs().max()) <= 1e-6 * float(a.abs().max())    # atomics: summation order may differ
+
+
+def test_predictor_mirror_tta_matches_reference_loop():
+    """Re-hosted Predictor (mirror TTA on the device, one D2H copy) vs the oracle's restatement of the reference loop
+    (light_training/prediction.py:110-160) around the oracle's MONAI inferer, with a network that is NOT flip-equivariant."""
+    from oracle import prediction as op
+    from oracle import sliding_window as osw
+    from waveformer_b200.inferers import SlidingWindowInferer
+    from waveformer_b200.prediction import Predictor
+    roi = (16, 16, 16)
+    ramp = torch.linspace(0.5, 1.5, 16)[None, None, :, None, None] * torch.linspace(1.0, 2.0, 16)[None, None, None, None, :]
+
+    def net_cpu(p):
+        return torch.cat([p[:, :1] * ramp, p[:, 1:2] + 0.25 * ramp], 1)
+
+    def net_gpu(p):
+        r = ramp.to(p.device)
+        return torch.cat([p[:, :1] * r, p[:, 1:2] + 0.25 * r], 1)
+
+    x = seeded_randn((1, 2, 40, 24, 30), 90)
+    want = op.mirror_and_predict(x, lambda v: osw.sliding_window_inference(v, roi, 2, net_cpu, overlap=0.5, mode="gaussian"),
+                                 [0, 1, 2])
+    inf = SlidingWindowInferer(roi_size=roi, sw_batch_size=2, overlap=0.5, mode="gaussian", compute_dtype=torch.float32,
+                               channels_last=False)
+
+    class _M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.p = torch.nn.Parameter(torch.zeros(1))
+
+        def forward(self, v):
+            return net_gpu(v)
+
+    got = Predictor(inf, mirror_axes=[0, 1, 2]).maybe_mirror_and_predict(x, _M().cuda(), torch.device("cuda"))
+    assert not got.is_cuda and tuple(got.shape) == tuple(want.shape)
+    assert max_rel(got, want) < 2e-6
+    props = {"shape_after_cropping_before_resample": (50, 30, 33)}
+    res = Predictor.predict_raw_probability(got.cuda(), props)
+    assert res.dtype == torch.half and max_rel(res.float().cpu(), op.predict_raw_probability(want, (50, 30, 33)).float()) < 2e-3
+    labels, regions = Predictor.labels_and_regions(res)
+    assert labels.dtype == torch.uint8 and tuple(regions.shape) == (3, 50, 30, 33)

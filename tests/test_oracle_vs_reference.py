@@ -47,3 +47,33 @@ def test_sliding_window_with_model(ref):
         want = Inferer(roi_size=(64, 64, 64), sw_batch_size=2, overlap=0.5, mode="gaussian")(x, m)
         got = osw.sliding_window_inference(x, (64, 64, 64), 2, lambda p: om.waveformer_forward(sd, p, cfg), 0.5, "gaussian")
     assert max_rel(got, want) < 5e-5
+
+
+def test_mirror_tta_restatement_matches_reference_predictor():
+    """oracle/prediction.py vs the live ``light_training.prediction.Predictor`` (its heavy optional imports stubbed)."""
+    import importlib
+    import sys
+    import types
+    for name in ("SimpleITK", "skimage", "skimage.measure", "light_training.preprocessing.resampling.default_resampling"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["light_training.preprocessing.resampling.default_resampling"].resample_data_or_seg_to_shape = lambda *a, **k: None
+    sys.modules["skimage"].measure = sys.modules["skimage.measure"]
+    if "/root/reference" not in sys.path:
+        sys.path.insert(0, "/root/reference")
+    pred = importlib.import_module("light_training.prediction")
+    from oracle import prediction as op
+    x = torch.randn(1, 2, 12, 10, 8, generator=torch.Generator().manual_seed(3))
+
+    def net(v):
+        return v * torch.arange(8.0)[None, None, None, None, :] + 0.1 * v.flip(2)
+
+    class _Id(torch.nn.Module):
+        def forward(self, v):
+            return v
+
+    for axes in ([0, 1, 2], [1], None):
+        ref = pred.Predictor(lambda v, model, **k: net(v), mirror_axes=axes).maybe_mirror_and_predict(x, _Id(), torch.device("cpu"))
+        assert float((ref - op.mirror_and_predict(x, net, axes)).abs().max()) == 0.0
+    props = {"shape_after_cropping_before_resample": (15, 9, 11)}
+    want = pred.Predictor.predict_raw_probability(x.clone(), props)
+    assert float((want.float() - op.predict_raw_probability(x, (15, 9, 11)).float()).abs().max()) == 0.0
