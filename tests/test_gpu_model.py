@@ -189,3 +189,23 @@ def test_training_step_gradients_match_oracle():
         assert float(cos) > 0.999, (name, float(cos))
         checked += 1
     assert checked > 120
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+def test_reference_default_constructor_geometry(dtype, tol):
+    """The reference's own default arguments (network_backbone.py:134-152): img 96^3, in_chans 1, out_chans 13 -> window
+    size 6 (216 tokens: CUDA-core attention, not the 512-token tensor-core path), cuDNN first convolution (the fused
+    kernel needs 4 input channels) and a 13-channel output head.  Every fast path must hand over to its fallback."""
+    from waveformer_b200 import prepare_inference
+    from waveformer_b200.network_models import Waveformer
+    cfg = ModelConfig(img_size=(96,) * 3, in_chans=1, out_chans=13)
+    sd = make_state_dict(cfg, seed=7)
+    x = seeded_randn((1, 1, 96, 96, 96), 8)
+    m = Waveformer(**cfg.kwargs()).eval()
+    m.load_state_dict(sd, strict=True)
+    m = prepare_inference(m.cuda(), dtype)
+    with torch.no_grad():
+        y = m(x.cuda()).float().cpu()
+        ref = om.waveformer_forward(sd, x, cfg)
+    assert tuple(y.shape) == (1, 13, 96, 96, 96)
+    assert max_rel(y, ref) <= tol
