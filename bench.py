@@ -244,6 +244,7 @@ def main():
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     pk = peaks()
 
+    torch.backends.cudnn.benchmark = True   # let cuDNN time its algorithms for the (fixed) window shapes during warm-up
     torch.manual_seed(0)  # identical random-init weights on every rank
     from waveformer_b200 import prepare_inference
     model = prepare_inference(Waveformer(**MODEL_KW).eval().to(dev), dtype)   # bf16 = the documented precision policy

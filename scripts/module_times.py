@@ -10,6 +10,8 @@ from waveformer_b200 import prepare_inference  # noqa: E402
 from waveformer_b200.network_models import Waveformer  # noqa: E402
 
 torch.manual_seed(0)
+if os.environ.get("WF_CUDNN_BENCHMARK"):
+    torch.backends.cudnn.benchmark = True
 m = prepare_inference(Waveformer(img_size=(128,) * 3, patch_size=2, in_chans=4, out_chans=4, depths=[2] * 4,
                                  feat_size=[48, 96, 192, 384], num_heads=[3, 6, 12, 24]).eval().cuda(), torch.bfloat16)
 x = torch.randn(2, 4, 128, 128, 128, device="cuda").contiguous(memory_format=torch.channels_last_3d)

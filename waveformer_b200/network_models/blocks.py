@@ -155,7 +155,7 @@ class UnetrBasicBlock(nn.Module):
             w = self.layer.conv1.conv.weight
             if inp.dtype != w.dtype:
                 inp = inp.to(w.dtype)
-            with torch.backends.cudnn.flags(enabled=True, allow_tf32=True):
+            with torch.backends.cudnn.flags(enabled=True, benchmark=torch.backends.cudnn.benchmark, allow_tf32=True):
                 return self.layer(inp) if out_buf is None else self.layer(inp, out_buf)
         return self.layer(inp) if out_buf is None else self.layer(inp, out_buf)
 
