@@ -238,20 +238,32 @@ __global__ void relpos_bias_image_kernel(const void *__restrict__ table, int tab
     reinterpret_cast<uint32_t *>(img)[idx] = pack16<F16>(v[0], v[1]);
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void softmax_warps_sync() {   // named barrier 1: the 16 softmax warps only
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+}
+
 // grid = combos * groups, combos = heads * 4 (head, 128-query tile); CTA (combo, g) walks windows g, g+groups, ...
-// 512 threads: warp w handles TMEM lanes 32*(w%4).. (query rows) and key quarter w/4 (128 keys).  Sixteen warps instead
-// of eight double the latency hiding of the TMEM-load -> FHADD / ex2 chains (the softmax passes were issue-latency bound
-// at 2 warps per scheduler, profiles/r01_stalls_attention_s1L1.txt).
-// TMEM columns: S = [0, 512) fp32; quarter q packs its P (16-bit) in place into [128q, 128q + 64); O accumulates in
-// [64, 80), which quarter 0 has consumed by then.
+// 544 threads = 16 softmax warps + 1 issuer warp (warp specialisation):
+//   softmax warp w: TMEM lanes 32*(w%4).. (query rows), key quarter w/4 (128 keys); pass 1 row max, pass 2 exponentials;
+//   every finished 32-key chunk of P (16 packed TMEM columns, written over the first half of its own S chunk) is
+//   announced on an mbarrier (one arrive per warp, four warps per chunk);
+//   issuer (one thread): bulk loads of the next window, S = Q K^T (2 x tcgen05.mma 128x256x16), and - as each P chunk is
+//   announced - its two O += P V k-steps (tcgen05.mma 128x16x16, A from TMEM), so the 32 small PV instructions run
+//   underneath the exponentials instead of after them (they were 24 % of the kernel as a serial phase, profiles/).
+// TMEM columns: S = [0, 512) fp32; P chunk (q, c) = [128q + 32c, 128q + 32c + 16); O = [16, 32) (the second half of
+// chunk (0, 0), free once that chunk's P is written - the first PV instruction waits for exactly that chunk).
 template <bool F16>
-__global__ void __launch_bounds__(512, 1) attn_core_tc_kernel(const uint16_t *__restrict__ qkv,
+__global__ void __launch_bounds__(544, 1) attn_core_tc_kernel(const uint16_t *__restrict__ qkv,
                                                               const uint16_t *__restrict__ bias_img,
                                                               uint16_t *__restrict__ o, int heads, int64_t B_,
                                                               int groups) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_full[2];
-    __shared__ __align__(8) uint64_t bar_s, bar_o, bar_bias;
+    __shared__ __align__(8) uint64_t bar_s, bar_o, bar_bias, bar_epi;
+    __shared__ __align__(8) uint64_t bar_p[16];   // [quarter][chunk]
     __shared__ uint32_t tmem_slot;
     uint16_t *sBias = reinterpret_cast<uint16_t *>(smem);
     uint8_t *sStage = smem + kBiasBytes;
@@ -261,8 +273,6 @@ __global__ void __launch_bounds__(512, 1) attn_core_tc_kernel(const uint16_t *__
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int combo = blockIdx.x % (heads * 4), g = blockIdx.x / (heads * 4);
     const int hh = combo >> 2, qt = combo & 3;
-    const int quarter = warp >> 2;                 // key quarter (128 keys) handled by this warp
-    const int row = (warp & 3) * 32 + lane;        // query row inside the tile = TMEM lane
     const int C = heads * 16;
 
     if (warp == 0) tmem_alloc(&tmem_slot, 512);
@@ -272,138 +282,162 @@ __global__ void __launch_bounds__(512, 1) attn_core_tc_kernel(const uint16_t *__
         mbar_init(&bar_s, 1);
         mbar_init(&bar_o, 1);
         mbar_init(&bar_bias, 1);
+        mbar_init(&bar_epi, 4);
+        for (int i = 0; i < 16; ++i) mbar_init(&bar_p[i], 4);
         mbar_fence_init();
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-
     const int64_t per_which = B_ * heads * 8192;  // elements between the q, k and v planes
-    auto issue_loads = [&](int64_t win, int stage) {
-        uint8_t *dst = sStage + stage * kStageBytes;
-        const uint16_t *qb = qkv + (win * heads + hh) * 8192;
-        mbar_expect_tx(&bar_full[stage], kStageBytes);
-        bulk_g2s(dst, qb + qt * 128 * 8, 2048, &bar_full[stage]);                 // Q chunk 0 (head dims 0..7)
-        bulk_g2s(dst + 2048, qb + 4096 + qt * 128 * 8, 2048, &bar_full[stage]);   // Q chunk 1
-        bulk_g2s(dst + 4096, qb + per_which, 16384, &bar_full[stage]);            // K
-        bulk_g2s(dst + 4096 + 16384, qb + 2 * per_which, 16384, &bar_full[stage]);  // V
-    };
 
-    if (tid == 0 && g < B_) {
-        // relative-position bias slab of this (head, query tile): one 130 KB bulk copy, resident for every window
-        mbar_expect_tx(&bar_bias, kBiasBytes);
-        bulk_g2s(sBias, bias_img + ((int64_t)hh * 4 + qt) * (kBiasBytes / 2), kBiasBytes, &bar_bias);
-        issue_loads(g, 0);
-    }
-    const uint32_t idesc_s = instr_desc16<F16>(128, 256, false);
-    const uint32_t idesc_o = instr_desc16<F16>(128, 16, true);
-
-    int it = 0;
-    for (int64_t win = g; win < B_; win += groups, ++it) {
-        const int stage = it & 1;
-        const uint32_t ph_full = (it >> 1) & 1, ph = it & 1;
-        const uint32_t sQ = smem_u32(sStage + stage * kStageBytes), sK = sQ + 4096, sV = sK + 16384;
-        if (tid == 0) {
-            if (win + groups < B_) issue_loads(win + groups, stage ^ 1);  // prefetch: lands during this window's softmax
-            mbar_wait(&bar_full[stage], ph_full);
-            tc_fence_after();
-            // S[128 x 512] = Q[128 x 16] K^T : two N = 256 halves, TMEM columns [0,256) and [256,512)
-            const uint64_t dq = smem_desc(sQ, 2048, 128);
-            mma_ss(tmem, dq, smem_desc(sK, 8192, 128), idesc_s, 0u);
-            mma_ss(tmem + 256, dq, smem_desc(sK + 256 * 16, 8192, 128), idesc_s, 0u);
-            mma_commit(&bar_s);
+    if (warp == 16) {
+        // ================================================= issuer ====================================================
+        if (lane == 0 && g < B_) {
+            auto issue_loads = [&](int64_t win, int stage) {
+                uint8_t *dst = sStage + stage * kStageBytes;
+                const uint16_t *qb = qkv + (win * heads + hh) * 8192;
+                mbar_expect_tx(&bar_full[stage], kStageBytes);
+                bulk_g2s(dst, qb + qt * 128 * 8, 2048, &bar_full[stage]);                 // Q chunk 0 (head dims 0..7)
+                bulk_g2s(dst + 2048, qb + 4096 + qt * 128 * 8, 2048, &bar_full[stage]);   // Q chunk 1
+                bulk_g2s(dst + 4096, qb + per_which, 16384, &bar_full[stage]);            // K
+                bulk_g2s(dst + 4096 + 16384, qb + 2 * per_which, 16384, &bar_full[stage]);  // V
+            };
+            // relative-position bias slab of this (head, query tile): one 130 KB bulk copy, resident for every window
+            mbar_expect_tx(&bar_bias, kBiasBytes);
+            bulk_g2s(sBias, bias_img + ((int64_t)hh * 4 + qt) * (kBiasBytes / 2), kBiasBytes, &bar_bias);
+            issue_loads(g, 0);
+            const uint32_t idesc_s = instr_desc16<F16>(128, 256, false);
+            const uint32_t idesc_o = instr_desc16<F16>(128, 16, true);
+            int it = 0;
+            for (int64_t win = g; win < B_; win += groups, ++it) {
+                const int stage = it & 1;
+                const uint32_t ph_full = (it >> 1) & 1, ph = it & 1;
+                const uint32_t sQ = smem_u32(sStage + stage * kStageBytes), sK = sQ + 4096, sV = sK + 16384;
+                if (it > 0) {   // previous tile: O read back and its V / P consumed -> TMEM and the other stage are free
+                    mbar_wait(&bar_epi, (it - 1) & 1);
+                    tc_fence_after();
+                }
+                if (win + groups < B_) issue_loads(win + groups, stage ^ 1);
+                mbar_wait(&bar_full[stage], ph_full);
+                tc_fence_after();
+                // S[128 x 512] = Q[128 x 16] K^T : two N = 256 halves, TMEM columns [0,256) and [256,512)
+                const uint64_t dq = smem_desc(sQ, 2048, 128);
+                mma_ss(tmem, dq, smem_desc(sK, 8192, 128), idesc_s, 0u);
+                mma_ss(tmem + 256, dq, smem_desc(sK + 256 * 16, 8192, 128), idesc_s, 0u);
+                mma_commit(&bar_s);
+                // O[128 x 16] += P_chunk[128 x 32] V_chunk[32 x 16] as the chunks arrive (chunk index fastest over quarters)
+                uint32_t first = 1;
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c)
+#pragma unroll 1
+                    for (int q = 0; q < 4; ++q) {
+                        mbar_wait(&bar_p[q * 4 + c], ph);
+                        tc_fence_after();
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const int ks = q * 8 + c * 2 + j;   // k-step = keys [16 ks, 16 ks + 16)
+                            mma_ts(tmem + 16, tmem + q * 128 + c * 32 + j * 8, smem_desc(sV + ks * 256, 128, 8192), idesc_o,
+                                   first ? 0u : 1u);
+                            first = 0;
+                        }
+                    }
+                mma_commit(&bar_o);
+            }
         }
-        if (it == 0) mbar_wait(&bar_bias, 0);
-        mbar_wait(&bar_s, ph);
-        tc_fence_after();
-
+    } else {
+        // ============================================== softmax warps ================================================
+        const int quarter = warp >> 2;                 // key quarter (128 keys) handled by this warp
+        const int row = (warp & 3) * 32 + lane;        // query row inside the tile = TMEM lane
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const uint32_t scol = tmem + lane_base + quarter * 128;
         const uint16_t *brow = sBias + row * kBiasPitch + quarter * 128;
-        // ---- pass 1: row maximum of s + bias over this warp's 128 keys (FHADD + FMNMX3: 1.5 ALU ops per key) ----
-        float mx = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-            uint32_t r[32];
-            tmem_ld32(scol + c * 32, r);
-            tmem_wait_ld();
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-                const uint4 b = *reinterpret_cast<const uint4 *>(brow + c * 32 + q4 * 8);
-                const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    float t0, t1;
-                    add16x2<F16>(bw[e], __uint_as_float(r[q4 * 8 + 2 * e]), __uint_as_float(r[q4 * 8 + 2 * e + 1]), t0, t1);
-                    mx = max3(mx, t0, t1);
-                }
-            }
-        }
-        sMax[quarter * 128 + row] = mx;
-        __syncthreads();
-        mx = fmaxf(fmaxf(sMax[row], sMax[128 + row]), fmaxf(sMax[256 + row], sMax[384 + row]));
-        // ---- pass 2: p = 2^(s + bias - max), row sum, P (16-bit) written over S in place ----
-        float sum = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-            uint32_t r[32];
-            tmem_ld32(scol + c * 32, r);
-            tmem_wait_ld();
-            uint32_t pk[16];
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-                const uint4 b = *reinterpret_cast<const uint4 *>(brow + c * 32 + q4 * 8);
-                const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    float t0, t1;
-                    add16x2<F16>(bw[e], __uint_as_float(r[q4 * 8 + 2 * e]) - mx, __uint_as_float(r[q4 * 8 + 2 * e + 1]) - mx, t0, t1);
-                    const float p0 = fast_exp2(t0), p1 = fast_exp2(t1);
-                    sum += p0 + p1;
-                    pk[q4 * 4 + e] = pack16<F16>(p0, p1);
-                }
-            }
-            tmem_st16(scol + c * 16, pk);  // keys [32c, 32c+32) of this half -> 16 packed columns (already consumed S)
-        }
-        tmem_wait_st();
-        sSum[quarter * 128 + row] = sum;
-        tc_fence_before();
-        __syncthreads();
-        // ---- O[128 x 16] = P[128 x 512] V[512 x 16]: A = P from TMEM (k-step ks = keys [16 ks, 16 ks + 16) = 8 packed
-        // columns at 128 * (ks / 8) + 8 * (ks % 8)), B = V (MN-major), D = TMEM columns [64, 80) ----
-        if (tid == 0) {
+        int it = 0;
+        for (int64_t win = g; win < B_; win += groups, ++it) {
+            const uint32_t ph = it & 1;
+            if (it == 0) mbar_wait(&bar_bias, 0);
+            mbar_wait(&bar_s, ph);
             tc_fence_after();
+            // ---- pass 1: row maximum of s + bias over this warp's 128 keys (FHADD + FMNMX3: 1.5 ALU ops per key) ----
+            float mx = -INFINITY;
 #pragma unroll 1
-            for (int ks = 0; ks < 32; ++ks) {
-                const uint32_t pa = tmem + (ks >> 3) * 128 + (ks & 7) * 8;
-                mma_ts(tmem + 64, pa, smem_desc(sV + ks * 256, 128, 8192), idesc_o, ks > 0 ? 1u : 0u);
+            for (int c = 0; c < 4; ++c) {
+                uint32_t r[32];
+                tmem_ld32(scol + c * 32, r);
+                tmem_wait_ld();
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const uint4 b = *reinterpret_cast<const uint4 *>(brow + c * 32 + q4 * 8);
+                    const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float t0, t1;
+                        add16x2<F16>(bw[e], __uint_as_float(r[q4 * 8 + 2 * e]), __uint_as_float(r[q4 * 8 + 2 * e + 1]), t0, t1);
+                        mx = max3(mx, t0, t1);
+                    }
+                }
             }
-            mma_commit(&bar_o);
+            sMax[quarter * 128 + row] = mx;
+            softmax_warps_sync();
+            mx = fmaxf(fmaxf(sMax[row], sMax[128 + row]), fmaxf(sMax[256 + row], sMax[384 + row]));
+            // ---- pass 2: p = 2^(s + bias - max), row sum; each 32-key chunk of P is packed over the first half of its
+            // own S chunk and announced to the issuer ----
+            float sum = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t r[32];
+                tmem_ld32(scol + c * 32, r);
+                tmem_wait_ld();
+                uint32_t pk[16];
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const uint4 b = *reinterpret_cast<const uint4 *>(brow + c * 32 + q4 * 8);
+                    const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float t0, t1;
+                        add16x2<F16>(bw[e], __uint_as_float(r[q4 * 8 + 2 * e]) - mx, __uint_as_float(r[q4 * 8 + 2 * e + 1]) - mx, t0, t1);
+                        const float p0 = fast_exp2(t0), p1 = fast_exp2(t1);
+                        sum += p0 + p1;
+                        pk[q4 * 4 + e] = pack16<F16>(p0, p1);
+                    }
+                }
+                tmem_st16(scol + c * 32, pk);
+                tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_p[quarter * 4 + c]);
+            }
+            sSum[quarter * 128 + row] = sum;
+            softmax_warps_sync();   // every row sum is visible; also orders this tile's sMax reads before the next tile's writes
+            if (warp < 4) {
+                mbar_wait(&bar_o, ph);
+                tc_fence_after();
+                uint32_t r[16];
+                tmem_ld16(tmem + lane_base + 16, r);
+                tmem_wait_ld();
+                const float inv = 1.f / ((sSum[row] + sSum[128 + row]) + (sSum[256 + row] + sSum[384 + row]));
+                uint4 lo, hi;
+                lo.x = pack16<F16>(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
+                lo.y = pack16<F16>(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
+                lo.z = pack16<F16>(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
+                lo.w = pack16<F16>(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
+                hi.x = pack16<F16>(__uint_as_float(r[8]) * inv, __uint_as_float(r[9]) * inv);
+                hi.y = pack16<F16>(__uint_as_float(r[10]) * inv, __uint_as_float(r[11]) * inv);
+                hi.z = pack16<F16>(__uint_as_float(r[12]) * inv, __uint_as_float(r[13]) * inv);
+                hi.w = pack16<F16>(__uint_as_float(r[14]) * inv, __uint_as_float(r[15]) * inv);
+                uint4 *dst = reinterpret_cast<uint4 *>(o + (win * 512 + qt * 128 + row) * (int64_t)C + hh * 16);
+                dst[0] = lo;
+                dst[1] = hi;
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_epi);   // O consumed: the issuer may overwrite TMEM with the next S
+            }
         }
-        mbar_wait(&bar_o, ph);
-        tc_fence_after();
-        if (warp < 4) {
-            uint32_t r[16];
-            tmem_ld16(tmem + lane_base + 64, r);
-            tmem_wait_ld();
-            const float inv = 1.f / ((sSum[row] + sSum[128 + row]) + (sSum[256 + row] + sSum[384 + row]));
-            uint4 lo, hi;
-            lo.x = pack16<F16>(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
-            lo.y = pack16<F16>(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
-            lo.z = pack16<F16>(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
-            lo.w = pack16<F16>(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
-            hi.x = pack16<F16>(__uint_as_float(r[8]) * inv, __uint_as_float(r[9]) * inv);
-            hi.y = pack16<F16>(__uint_as_float(r[10]) * inv, __uint_as_float(r[11]) * inv);
-            hi.z = pack16<F16>(__uint_as_float(r[12]) * inv, __uint_as_float(r[13]) * inv);
-            hi.w = pack16<F16>(__uint_as_float(r[14]) * inv, __uint_as_float(r[15]) * inv);
-            uint4 *dst = reinterpret_cast<uint4 *>(o + (win * 512 + qt * 128 + row) * (int64_t)C + hh * 16);
-            dst[0] = lo;
-            dst[1] = hi;
-        }
-        tc_fence_before();
-        __syncthreads();  // O and P consumed, sMax / sSum free: the next window's S may overwrite TMEM
     }
+    tc_fence_before();
+    __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
@@ -475,7 +509,7 @@ static int attn_tc_run(const void *x, int x_dtype, const uint16_t *qkv_w, const 
         int groups = kNumSMs / combos;
         if (groups < 1) groups = 1;
         if (groups > B_) groups = (int)B_;
-        attn_core_tc_kernel<F16><<<combos * groups, 512, kCoreSmem, st>>>(qkv, bias_img, obuf, heads, B_, groups);
+        attn_core_tc_kernel<F16><<<combos * groups, 544, kCoreSmem, st>>>(qkv, bias_img, obuf, heads, B_, groups);
         WF_LAUNCH_CHECK();
     }
     {
