@@ -167,6 +167,10 @@ int wf_layernorm_ndhwc(const void *x, const float *gamma, const float *beta, voi
 int wf_residual_sum(const float *a, const float *b, const void *c, int c_dtype, const float *bias, float *out, int64_t rows,
                     int C, void *stream);
 
+/* x = GELU(x) (exact erf form) in place on n elements (n % 8 == 0 for bf16, % 4 for fp32): the activation between the
+ * 1x1x1 convolutions of ProjectionUpsample (reference network_models/wave_helper.py:47-63). */
+int wf_gelu_inplace(void *x, int dtype, int64_t n, void *stream);
+
 /* y = base + sum_s trilinear_upsample(srcs[s]) (sources summed in order, then added to base; base may be NULL).
  * srcs[s]: [B, d_s, h_s, w_s, C] dense channels-last of src_dtype, src_dims = int[3 * nsrc]; base / y: [B, D, H, W, C]
  * of io_dtype with voxel strides.  align_corners = 0 reproduces F.interpolate(size=(D,H,W), mode='trilinear') + the

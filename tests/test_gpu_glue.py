@@ -214,3 +214,12 @@ def test_residual_sum_matches_torch(c_dtype):
     want = a + b + c.float() + bias
     assert got.dtype == torch.float32 and float((got - want).abs().max()) < 1e-6
     assert float((ops.residual_sum(a, b, c) - (a + b + c.float())).abs().max()) < 1e-6
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-6), (torch.bfloat16, 5e-3)])
+def test_gelu_inplace_matches_torch(dtype, tol):
+    from waveformer_b200 import ops
+    x = (seeded_randn((3, 7, 16, 8), 150) * 2.5).cuda().to(dtype)
+    want = F.gelu(x.float())
+    got = ops.gelu_(x.clone())
+    assert got.dtype == dtype and max_rel(got.float().cpu(), want.cpu()) < tol

@@ -419,6 +419,11 @@ class ProjectionUpsample(nn.Module):
         w = conv.weight.view(conv.out_channels, conv.in_channels) if weight is None else weight
         return F.linear(t, w, conv.bias if bias is None else bias)
 
+    def _gelu(self, t: torch.Tensor) -> torch.Tensor:
+        ok = isinstance(self.act, nn.GELU) and getattr(self.act, "approximate", "none") == "none" and t.is_contiguous() \
+            and t.numel() % 8 == 0
+        return ops.gelu_(t) if ok else self.act(t)
+
     def _forward_fused(self, x, out_buf):
         xv = x.permute(0, 2, 3, 4, 1)                                    # channels-last view [B, d, h, w, C]
         B = xv.shape[0]
@@ -437,9 +442,9 @@ class ProjectionUpsample(nn.Module):
             wi = (w2 * a[i][None, :]).to(dw.dtype)
             bi = (self.conv2.bias.float() + w2 @ d[i]).to(dw.dtype)
             torch.addmm(bi, dw[i].reshape(-1, c_in), wi.t(), out=h[i].view(-1, c_mid))
-        h = self.act(h)
+        h = self._gelu(h)
         if self.use_double_conv:
-            h = self._pointwise(self.conv3[1](self._pointwise(h, self.conv3[0])), self.conv3[2])
+            h = self._pointwise(self._gelu(self._pointwise(h, self.conv3[0])), self.conv3[2])
         else:
             h = self._pointwise(h, self.conv3)
         dst = out_buf if out_buf is not None else torch.empty_like(h)

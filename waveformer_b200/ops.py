@@ -652,6 +652,18 @@ def layer_norm_cl(x: torch.Tensor, weight: Optional[torch.Tensor], bias: Optiona
     return (y, y2) if also_bf16 else y
 
 
+def gelu_(x: torch.Tensor) -> torch.Tensor:
+    """In-place exact (erf) GELU of a contiguous bf16 / fp32 tensor."""
+    dev = _need_cuda(x)
+    if not x.is_contiguous():
+        raise ValueError("gelu_ works in place on a contiguous tensor")
+    with torch.cuda.device(dev):
+        st = _lib.lib().wf_gelu_inplace(x.data_ptr(), _dtype_code(x), x.numel(), _stream(dev))
+    _lib.check(st, "wf_gelu_inplace")
+    _count()
+    return x
+
+
 def residual_sum(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``a + b + c + bias`` over the last (channel) dim in one pass; a, b fp32 contiguous, c fp32 or bf16."""
     dev = _need_cuda(a, b, c, bias)
