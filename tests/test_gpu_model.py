@@ -209,3 +209,37 @@ def test_reference_default_constructor_geometry(dtype, tol):
         ref = om.waveformer_forward(sd, x, cfg)
     assert tuple(y.shape) == (1, 13, 96, 96, 96)
     assert max_rel(y, ref) <= tol
+
+
+def test_idwt_block_with_hf_refinement_gate_fp32():
+    """The gated decoder path (hf_refinement=True, off by default): per-band sigmoid gates computed by HFRefinementRes and
+    multiplied inside the synthesis kernel, vs the unmodified reference (tests/golden/idwt_block_hf_gate.npz,
+    scripts/make_golden_hf_gate.py).  Same state_dict keys, strict load."""
+    from waveformer_b200.network_models import IDWTBlock
+    g = load_npz("idwt_block_hf_gate.npz")
+    dec = IDWTBlock(spatial_dims=3, in_channels=64, out_channels=16, stage=2, hf_refinement=True, wavelet="db1",
+                    kernel_size=3, norm_name="instance", res_block=True).eval()
+    assert list(dec.state_dict().keys()) == [str(k) for k in g["keys"]]
+    sd = {}
+    for i, (k, v) in enumerate(dec.state_dict().items()):       # the generator script's seeded weights
+        t = seeded_randn(tuple(v.shape), 9000 + 100 + i)
+        if v.dim() > 1:
+            fan = 1
+            for d in v.shape[1:]:
+                fan *= d
+            t = t / fan ** 0.5
+        elif k.endswith("weight"):
+            t = 1.0 + 0.1 * t
+        else:
+            t = 0.05 * t
+        sd[k] = t
+    dec.load_state_dict(sd, strict=True)
+    dec = dec.cuda()
+    keys = ("aad", "ada", "add", "daa", "dad", "dda", "ddd")
+    inp = seeded_randn((2, 64, 4, 4, 4), 600).cuda()
+    skip = seeded_randn((2, 16, 16, 16, 16), 601).cuda()
+    hf = ({k: seeded_randn((2, 16, 4, 4, 4), 610 + i).cuda() for i, k in enumerate(keys)},
+          {k: seeded_randn((2, 16, 8, 8, 8), 620 + i).cuda() for i, k in enumerate(keys)})
+    with torch.no_grad():
+        y = dec(inp, skip, hf)
+    assert max_rel(y.cpu(), g["out"]) < 5e-5

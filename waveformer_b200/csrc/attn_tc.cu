@@ -482,15 +482,14 @@ static int attn_tc_run(const void *x, int x_dtype, const uint16_t *qkv_w, const 
     const int64_t M = B_ * 512;
     uint16_t *qkv = reinterpret_cast<uint16_t *>(workspace);  // [3][B_][heads][2][512][8]
     uint16_t *obuf = qkv + 3 * M * C;                         // [M][C]
-    static bool attrs_done = false;
-    if (!attrs_done) {
+    static unsigned long long attrs_done = 0;   // per-device opt-in bits
+    if (first_use_on_current_device(attrs_done)) {
         const int big = 200 * 1024;
         WF_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel<true, float, F16, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
         WF_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel<true, __nv_bfloat16, F16, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
         WF_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel<false, uint16_t, F16, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
         WF_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel<false, uint16_t, F16, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
         WF_CUDA_CHECK(cudaFuncSetAttribute(attn_core_tc_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCoreSmem));
-        attrs_done = true;
     }
     const int kchunks = C / 8;
     {

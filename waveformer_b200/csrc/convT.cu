@@ -169,10 +169,9 @@ extern "C" int wf_convtranspose3d_k2s2_ndhwc(const void *x, const void *wpack, v
     const size_t images = (size_t)kchunks * 2048 + (size_t)kchunks * N * 16, stage = (size_t)128 * (N + 8) * 2;
     const size_t smem = images > stage ? images : stage;
     if (smem > 220 * 1024) return WF_ERR_UNSUPPORTED;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static unsigned long long attr_done = 0;   // per-device opt-in bits
+    if (first_use_on_current_device(attr_done)) {
         WF_CUDA_CHECK(cudaFuncSetAttribute(convT_k2s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        attr_done = true;
     }
     const int64_t M = (int64_t)B * D * H * W;
     if (M >= 0x7fffffffLL) return WF_ERR_UNSUPPORTED;

@@ -310,11 +310,10 @@ extern "C" int wf_conv3d_c4_in_stats(const void *x, int x_dtype, const void *wpa
     const size_t smem = (size_t)kC4Chunks * N * 16 + (stage > aimg ? stage : aimg);
     uint32_t cols = 32;
     while ((int)cols < N) cols <<= 1;
-    static bool attrs_done = false;
-    if (!attrs_done) {
+    static unsigned long long attrs_done = 0;   // per-device opt-in bits
+    if (first_use_on_current_device(attrs_done)) {
         WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_c4_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_c4_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        attrs_done = true;
     }
     WF_CUDA_CHECK(cudaMemsetAsync(sums0, 0, sizeof(double) * 2 * (size_t)B * n0, st));
     if (n1 > 0) WF_CUDA_CHECK(cudaMemsetAsync(sums1, 0, sizeof(double) * 2 * (size_t)B * n1, st));

@@ -225,10 +225,9 @@ __global__ void __launch_bounds__(256, 2) dwconv3d_bf16_tile_kernel(const __nv_b
 
 static int dwconv_bf16_tile_launch(const __nv_bfloat16 *x, const float *w27, const float *bias, __nv_bfloat16 *y, int B,
                                    int D, int H, int W, int C, cudaStream_t st) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static unsigned long long attr_done = 0;   // per-device opt-in bits
+    if (first_use_on_current_device(attr_done)) {
         WF_CUDA_CHECK(cudaFuncSetAttribute(dwconv3d_bf16_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmem));
-        attr_done = true;
     }
     const int tiles_x = (W + kDwTX - 1) / kDwTX, tiles_y = (H + kDwTY - 1) / kDwTY, tiles_z = (D + kDwTZ - 1) / kDwTZ;
     const int64_t tiles = (int64_t)B * tiles_x * tiles_y * tiles_z;

@@ -28,6 +28,18 @@ inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 constexpr int kNumSMs = 148;  // B200
 
+// Function attributes (the > 48 KB dynamic shared-memory opt-in) are per DEVICE: one flag word per call site, one bit per
+// device ordinal, so a process that drives several GPUs opts in on each of them.  Returns true the first time the calling
+// site runs on the current device.
+inline bool first_use_on_current_device(unsigned long long &mask) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return true;   // unknown ordinal: just opt in again
+    const unsigned long long bit = 1ull << dev;
+    if (mask & bit) return false;
+    mask |= bit;
+    return true;
+}
+
 // ---- 16-byte packets of activations ---------------------------------------------------------------------------
 template <typename T> struct Pack;  // VEC elements of T in one 16-byte global transaction
 template <> struct Pack<float> {
