@@ -194,6 +194,19 @@ int wf_conv3d_c4_in_stats(const void *x, int x_dtype, const void *wpack, void *y
                           void *y1, int64_t y1_vox_stride, int n1, double *sums0, double *sums1, float *mean_rstd0,
                           float *mean_rstd1, float eps, int B, int D, int H, int W, void *stream);
 
+/* 3x3x3 convolution (padding 1, no bias) 48 -> 48 channels on channels-last bf16 rows of W = 128 voxels: a producer /
+ * consumer tcgen05 implicit GEMM (input rows streamed through a shared-memory ring, weights resident, double-buffered TMEM
+ * accumulators) that also (i) applies InstanceNorm + LeakyReLU(slope) to its INPUT while staging it when in_mean_rstd is
+ * given, and (ii) returns the InstanceNorm statistics of its bf16 OUTPUT.  Replaces `conv2(lrelu(norm1(.)))` + norm2's
+ * statistics in the 128^3 residual blocks (reference monai/networks/blocks/dynunet_block.py:98-111, used by
+ * Waveformer.encoder1 / decoder1, network_models/network_backbone.py:386,405).
+ * wpack: bf16 [3 dz][3 dx][3 k-steps][2 chunks][144 = 3 dy x 48 out][8], element = w[out, 16 ks + 8 chunk + e, dz, dy, dx]
+ * (the three dy taps of a (dz, dx, k-step) are adjacent along N so that one tcgen05.mma feeds up to three output rows).  sums: fp64 scratch [B * 48 * 2]; mean_rstd (out) / in_mean_rstd (in, optional): fp32
+ * [B * 48 * 2] = (mean, 1/sqrt(var + eps)) pairs. */
+int wf_conv3d_k3_c48_in_stats(const void *x, const void *wpack, void *y, double *sums, float *mean_rstd,
+                              const float *in_mean_rstd, float slope, float eps, int B, int D, int H, int W,
+                              int64_t x_vox_stride, int64_t y_vox_stride, void *stream);
+
 /* ConvTranspose3d(kernel 2, stride 2, no bias) on channels-last bf16 activations as one tensor-core GEMM whose epilogue
  * writes every output voxel in place, e.g. into channels [0, Cout) of a concatenation buffer (y_vox_stride = 2 * Cout).
  * Replaces UnetrUpBlock.transp_conv and the torch.cat that follows it (reference monai/networks/blocks/unetr_block.py:57-86,

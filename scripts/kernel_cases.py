@@ -28,6 +28,13 @@ elif args.case == "c4":      # encoder1: 2 x 4 x 128^3 fp32 window -> conv1 + co
     x = rn(2, 4, 128, 128, 128).bfloat16().contiguous(memory_format=torch.channels_last_3d)
     w1, w3 = (rn(48, 4, 3, 3, 3) * 0.1).bfloat16(), (rn(48, 4, 1, 1, 1) * 0.5).bfloat16()
     fns = {"conv3d_c4_in_stats": lambda: ops.conv3d_c4_in_stats(x, w1, w3)}
+elif args.case == "k3":      # encoder1 / decoder1 conv2: 48 -> 48 at 2 x 128^3, fused input IN + lrelu and output statistics
+    x = rn(2, 128, 128, 128, 48).bfloat16().permute(0, 4, 1, 2, 3)
+    w = (rn(48, 48, 3, 3, 3) / 36).bfloat16()
+    st = ops.instance_norm_stats(x)
+    fns = {"conv3d_k3_c48 (fused in-norm + stats)": lambda: ops.conv3d_k3_c48(x, w, in_stats=st),
+           "conv3d_k3_c48 (plain + stats)": lambda: ops.conv3d_k3_c48(x, w),
+           "cudnn conv3d 48->48 (library, for comparison)": lambda: torch.nn.functional.conv3d(x, w, padding=1)}
 elif args.case == "dwconv":  # CCF_FFN stage 1: 2 x 64^3 x 192
     x = rn(2, 64, 64, 64, 192).bfloat16()
     w27, b = rn(27, 192) * 0.2, rn(192) * 0.05

@@ -223,3 +223,31 @@ def test_gelu_inplace_matches_torch(dtype, tol):
     want = F.gelu(x.float())
     got = ops.gelu_(x.clone())
     assert got.dtype == dtype and max_rel(got.float().cpu(), want.cpu()) < tol
+
+
+@pytest.mark.parametrize("shape", [(1, 2, 4, 128), (2, 3, 6, 128), (1, 5, 9, 128)])
+@pytest.mark.parametrize("fused_input_norm", [False, True])
+def test_conv3d_k3_c48_producer_consumer_kernel(shape, fused_input_norm):
+    """tcgen05 3^3 convolution 48 -> 48 on rows of 128 voxels (ring-staged input rows, shifted-descriptor dx taps, double-
+    buffered TMEM accumulators): vs torch's convolution on the same bf16-rounded operands; fused InstanceNorm + LeakyReLU of
+    the input; fused output statistics; partial row blocks (H % 4 != 0) and volume borders in z / y / x."""
+    from waveformer_b200 import ops
+    B, D, H, W = shape
+    x = (seeded_randn((B, 48, D, H, W), 160) * 1.3 + 0.2).cuda().bfloat16().contiguous(memory_format=torch.channels_last_3d)
+    w = (seeded_randn((48, 48, 3, 3, 3), 161) / (27 * 48) ** 0.5).cuda().bfloat16()
+    xin = x.float()
+    stats = None
+    if fused_input_norm:
+        stats = ops.instance_norm_stats(x, eps=1e-5)
+        t = F.leaky_relu(F.instance_norm(xin, eps=1e-5), 0.01)
+        xin = t.bfloat16().float()                      # the kernel rounds the normalised operand to bf16 as well
+    want = F.conv3d(xin, w.float(), padding=1)
+    y, st = ops.conv3d_k3_c48(x, w, in_stats=stats, slope=0.01)
+    assert y.dtype == torch.bfloat16 and tuple(y.shape) == tuple(want.shape)
+    assert max_rel(y.float().cpu(), want.cpu()) < 8e-3
+    f = y.float()
+    mean = f.mean(dim=(2, 3, 4)).reshape(-1)
+    rstd = (f.var(dim=(2, 3, 4), unbiased=False) + 1e-5).rsqrt().reshape(-1)
+    got = st.reshape(-1, 2)
+    assert float((got[:, 0] - mean).abs().max()) < 2e-5 * max(1.0, float(mean.abs().max()))
+    assert max_rel(got[:, 1].cpu(), rstd.cpu()) < 1e-4

@@ -39,6 +39,7 @@ SIGNATURES = {
     "wf_layernorm_ndhwc": (_I, [_VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _I, _I, _I64, _I, _I64, _I64, _F, _I, _VOIDP]),
     "wf_upsample_trilinear_add_ndhwc": (_I, [_VOIDP, _VOIDP, _I, _VOIDP, _VOIDP, _I, _I, _I, _I, _I, _I, _I, _I, _I64, _I64, _VOIDP]),
     "wf_conv3d_c4_in_stats": (_I, [_VOIDP, _I, _VOIDP, _VOIDP, _I64, _I, _VOIDP, _I64, _I, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _F, _I, _I, _I, _I, _VOIDP]),
+    "wf_conv3d_k3_c48_in_stats": (_I, [_VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _F, _F, _I, _I, _I, _I, _I64, _I64, _VOIDP]),
     "wf_convtranspose3d_k2s2_ndhwc": (_I, [_VOIDP, _VOIDP, _VOIDP, _I, _I, _I, _I, _I, _I, _I, _I64, _I64, _VOIDP]),
     "wf_sw_gather": (_I, [_VOIDP, _VOIDP, _VOIDP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VOIDP]),
     "wf_sw_accumulate": (_I, [_VOIDP] * 6 + [_F, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VOIDP]),

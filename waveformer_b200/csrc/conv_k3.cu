@@ -1,0 +1,365 @@
+// 3x3x3 convolution (padding 1, stride 1, no bias), 48 -> 48 channels, channels-last bf16, rows of W = 128 voxels:
+// a producer / consumer tcgen05 implicit GEMM with the InstanceNorm statistics of the result fused into the epilogue and,
+// optionally, the InstanceNorm + LeakyReLU of the INPUT applied on the fly to the staged rows.
+//
+// Reference: conv2 of the two 128^3 residual blocks, Waveformer.encoder1 / decoder1.conv_block (MONAI UnetResBlock.forward,
+// monai/networks/blocks/dynunet_block.py:98-111: `out = self.conv2(self.lrelu(self.norm1(self.conv1(inp))))`, then norm2).
+// The library runs this convolution at 0.77 ms per batch-2 window and needs one more pass for norm1 + lrelu (0.18 ms) and
+// one for norm2's statistics (0.08 ms).
+//
+// Work decomposition.  One CTA owns a block of 4 output rows (y0 .. y0+3) of one (b, z) plane; a row is 128 voxels = the
+// M dimension (one TMEM lane per voxel), the 48 output channels are N, and K runs over 27 taps x 48 input channels.
+//   * An INPUT row (z', y') is staged once as a K-major no-swizzle image [6 chunks][132 rows][16 B]: row r holds voxel
+//     x = r - 1, rows 0 and 129 are the zero halo.  Because rows are 16 bytes apart, the operand for tap dx is the same
+//     image with its start address advanced by dx rows - no im2col copy.  The row feeds up to 3 output rows (dy); their
+//     accumulators are adjacent in TMEM and their weight tiles adjacent along N, so each (dx, k-step) is ONE
+//     tcgen05.mma 128 x 144 x 16: 9 instructions per input row instead of 27 (the A operand streams at the same ~100 clk
+//     per instruction whatever N is).
+//   * The 18 input rows of a block (3 planes x 6 rows) stream through a 4-slot ring (cp.async -> mbarrier), out-of-volume
+//     rows are skipped (zero contribution).  All 27 weight tiles [144 x 16] (124 KB) stay resident in shared memory.
+//   * Accumulators: 4 output rows x 48 columns, double buffered in TMEM (2 x 192 columns), so the epilogue of a block
+//     (TMEM -> bf16 -> staging -> coalesced stores + per-channel sum / sum of squares) overlaps the MMAs of the next one.
+// Warp roles (288 threads): warps 0-3 loaders (+ optional input normalisation), warp 4 MMA issuer, warps 5-8 epilogue.
+#include "tc_common.cuh"
+#include "wf_common.cuh"
+
+namespace wf {
+
+using namespace tc;
+
+constexpr int kK3C = 48;                       // channels in = channels out
+constexpr int kK3Chunks = kK3C / 8;            // 6 sixteen-byte K chunks per voxel
+constexpr int kK3Rows = 132;                   // image rows: 1 halo + 128 voxels + 1 halo + 2 pad
+constexpr int kK3RowImg = kK3Chunks * kK3Rows * 16;        // 12672 bytes per staged input row
+constexpr int kK3Ring = 5;
+constexpr int kK3Lag = 3;                       // rows of cp.async copies in flight per loader thread
+constexpr int kK3WTile3 = 2 * 3 * kK3C * 16;               // one [144 = 3 dy x 48 out][16] weight tile: 4608 bytes
+constexpr int kK3WBytes = 27 * kK3WTile3;                  // 3 dz x 3 dx x 3 k-steps tiles = 124416
+constexpr int kK3StageBytes = 256 * (kK3C + 8) * 2;        // epilogue staging: 2 output rows at a time, 28672
+constexpr int kK3Smem = kK3WBytes + kK3Ring * kK3RowImg + kK3StageBytes;   // 203776
+
+__device__ __forceinline__ void cp_async16_k3(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_k3(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct K3Args {
+    const __nv_bfloat16 *x;     // [B, D, H, W = 128, 48], voxel stride xs
+    const uint16_t *wpack;      // [3 dz][3 dx][3 ks][2 chunks][144 = 3 dy x 48 out][8] bf16
+    __nv_bfloat16 *y;           // [B, D, H, 128, 48], voxel stride ys
+    double *sums;               // [B][48][2] (sum, sum of squares of the rounded outputs); zeroed by the host wrapper
+    const float *in_mr;         // optional (mean, rstd) [B][48][2] of the input: x is normalised + LeakyReLU'd while staged
+    float slope;
+    int64_t xs, ys;
+    int B, D, H;
+};
+
+__global__ void __launch_bounds__(288, 1) conv3d_k3_c48_kernel(K3Args a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar_full[kK3Ring], bar_empty[kK3Ring], bar_acc_full[2], bar_acc_empty[2];
+    __shared__ uint32_t tmem_slot;
+    uint8_t *sW = smem;
+    uint8_t *sRing = smem + kK3WBytes;
+    __nv_bfloat16 *sStage = reinterpret_cast<__nv_bfloat16 *>(smem + kK3WBytes + kK3Ring * kK3RowImg);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int W = 128;
+    const int yblocks = (a.H + 3) >> 2;
+    const int64_t nblocks = (int64_t)a.B * a.D * yblocks;
+
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
+    if (tid == 0) {
+        for (int i = 0; i < kK3Ring; ++i) {
+            mbar_init(&bar_full[i], 128);    // one deferred arrival per loader thread
+            mbar_init(&bar_empty[i], 1);     // tcgen05.commit
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_acc_full[i], 1);  // tcgen05.commit
+            mbar_init(&bar_acc_empty[i], 4); // one per epilogue warp
+        }
+        mbar_fence_init();
+    }
+    // resident weights (every thread helps) and the zero halo rows of the ring images
+    for (int i = tid; i < kK3WBytes / 16; i += 288)
+        reinterpret_cast<uint4 *>(sW)[i] = __ldg(reinterpret_cast<const uint4 *>(a.wpack) + i);
+    for (int i = tid; i < kK3Ring * kK3Chunks * 4; i += 288) {
+        const int slot = i / (kK3Chunks * 4), r = i % (kK3Chunks * 4);
+        const int ch = r >> 2, which = r & 3;                       // rows 0, 129, 130, 131 of every chunk
+        const int row = which == 0 ? 0 : 128 + which;
+        *reinterpret_cast<uint4 *>(sRing + slot * kK3RowImg + (ch * kK3Rows + row) * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp < 4) {
+        // ================================================= loaders ====================================================
+        // thread t stages voxel x = t of each input row: 6 chunks of 16 bytes, written to rows t + 1 of the chunk planes
+        uint32_t n_loaded = 0;   // rows staged so far by this CTA (ring position)
+        uint32_t n_arrived = 0;  // rows whose copies have landed and been announced (cp.async path lags by <= 2 rows)
+        int64_t pend_b[kK3Lag + 1];   // batch element of each in-flight row (selects the normalisation constants)
+        float sc[kK3C], sh[kK3C];     // input normalisation as x * sc + sh (only used with in_mr)
+        int64_t norm_b = -1;
+        auto announce_upto = [&](uint32_t upto) {
+            // the copies of rows [n_arrived, upto) have completed (cp.async.wait_group).  Optionally normalise + LeakyReLU
+            // this thread's own voxel (the 6 chunks it copied itself: no cross-thread dependency), make the row visible to
+            // the tensor core's async proxy, then arrive on the slot's barrier.
+            for (; n_arrived < upto; ++n_arrived) {
+                if (a.in_mr != nullptr) {
+                    uint8_t *img = sRing + (n_arrived % kK3Ring) * kK3RowImg;
+                    const int64_t rb = pend_b[n_arrived % (kK3Lag + 1)];
+                    if (rb != norm_b) {      // (scale, shift) of the 48 channels live in registers; reloaded per batch element
+                        const float2 *mr = reinterpret_cast<const float2 *>(a.in_mr) + rb * kK3C;
+#pragma unroll
+                        for (int c = 0; c < kK3C; ++c) {
+                            const float2 m = __ldg(mr + c);
+                            sc[c] = m.y;
+                            sh[c] = -m.x * m.y;
+                        }
+                        norm_b = rb;
+                    }
+#pragma unroll
+                    for (int ch = 0; ch < kK3Chunks; ++ch) {
+                        uint4 *cell = reinterpret_cast<uint4 *>(img + (ch * kK3Rows + tid + 1) * 16);
+                        float f[8];
+                        Pack<__nv_bfloat16>::unpack(*cell, f);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float t = fmaf(f[e], sc[ch * 8 + e], sh[ch * 8 + e]);
+                            f[e] = fmaxf(t, t * a.slope);
+                        }
+                        *cell = Pack<__nv_bfloat16>::pack(f);
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive_k3(&bar_full[n_arrived % kK3Ring]);
+            }
+        };
+        for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+            const int yb = (int)(blk % yblocks);
+            const int64_t t2 = blk / yblocks;
+            const int z = (int)(t2 % a.D);
+            const int64_t b = t2 / a.D;
+            const int y0 = yb * 4;
+            for (int dz = -1; dz <= 1; ++dz) {
+                const int zz = z + dz;
+                if ((unsigned)zz >= (unsigned)a.D) continue;
+                for (int iy = -1; iy <= 4; ++iy) {
+                    const int yy = y0 + iy;
+                    if ((unsigned)yy >= (unsigned)a.H) continue;
+                    const int slot = n_loaded % kK3Ring;
+                    const uint32_t use = n_loaded / kK3Ring;
+                    if (use > 0) mbar_wait(&bar_empty[slot], (use - 1) & 1);   // the MMAs that read this slot are done
+                    uint8_t *img = sRing + slot * kK3RowImg;
+                    const __nv_bfloat16 *src = a.x + ((((int64_t)b * a.D + zz) * a.H + yy) * W + tid) * a.xs;
+#pragma unroll
+                    for (int ch = 0; ch < kK3Chunks; ++ch)
+                        cp_async16_k3(img + (ch * kK3Rows + tid + 1) * 16, src + ch * 8);
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                    pend_b[n_loaded % (kK3Lag + 1)] = b;
+                    if (n_loaded + 1 - n_arrived > kK3Lag) {      // keep at most kK3Lag rows in flight per thread
+                        asm volatile("cp.async.wait_group %0;" ::"n"(kK3Lag) : "memory");
+                        announce_upto(n_loaded + 1 - kK3Lag);
+                    }
+                    ++n_loaded;
+                }
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        announce_upto(n_loaded);
+    } else if (warp == 4) {
+        // ================================================= issuer =====================================================
+        if (lane == 0) {
+            const uint32_t idesc1 = instr_desc_bf16(128, kK3C, false), idesc2 = instr_desc_bf16(128, 2 * kK3C, false),
+                           idesc3 = instr_desc_bf16(128, 3 * kK3C, false);
+            const uint64_t desc_a0 = smem_desc(smem_u32(sRing), kK3Rows * 16, 128);   // slot 0, chunk 0, row 0
+            const uint64_t desc_w0 = smem_desc(smem_u32(sW), 3 * kK3C * 16, 128);      // tile (dz, dx, ks) = [2][144 = dy x out][8]
+            uint32_t n_used = 0, nblk = 0;
+            for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x, ++nblk) {
+                const int yb = (int)(blk % yblocks);
+                const int z = (int)((blk / yblocks) % a.D);
+                const int y0 = yb * 4;
+                const int buf = nblk & 1;
+                // the epilogue has zeroed (first use) or drained and re-zeroed (later uses) this accumulator buffer
+                mbar_wait(&bar_acc_empty[buf], (nblk >> 1) & 1);
+                tc_fence_after();
+                for (int dz = -1; dz <= 1; ++dz) {
+                    if ((unsigned)(z + dz) >= (unsigned)a.D) continue;
+                    for (int iy = -1; iy <= 4; ++iy) {
+                        const int yy = y0 + iy;
+                        if ((unsigned)yy >= (unsigned)a.H) continue;
+                        const int slot = n_used % kK3Ring;
+                        mbar_wait(&bar_full[slot], (n_used / kK3Ring) & 1);
+                        tc_fence_after();
+                        // descriptors: a base per ring slot / for the weights, plus compile-time offsets in 16-byte
+                        // units (the address field holds addr >> 4; all shared-memory addresses fit its 14 bits) - the single
+                        // issuing thread must spend only a few instructions per MMA or it, not the tensor pipe, is the limit
+                        const uint64_t da0 = desc_a0 + (uint64_t)(slot * (kK3RowImg / 16));
+                        // One MMA per (dx, k-step) covers EVERY output row this input row feeds: the rows' accumulators are
+                        // adjacent in TMEM (descending row order) and their dy weight tiles are adjacent along N, so
+                        // N = 48 x (rows fed) = up to 144.  A [128 x 16] operand streamed from shared memory costs the
+                        // same ~100 clk whatever N is (measured), so merging the three dy taps cuts the MMA time 3x.
+                        // Every MMA accumulates: the epilogue warps zero an accumulator buffer before handing it back.
+                        const int r_hi = min(3, min(iy + 1, a.H - 1 - y0)), r_lo = max(0, iy - 1);
+                        if (r_hi >= r_lo) {
+                            const int nrows = r_hi - r_lo + 1;
+                            const uint32_t idesc = nrows == 3 ? idesc3 : (nrows == 2 ? idesc2 : idesc1);
+                            const uint32_t acc = tmem + buf * 256 + (3 - r_hi) * kK3C;
+                            // first weight row: dy of r_hi = iy - r_hi (in -1..1) -> N offset (dy + 1) * 48
+                            const uint64_t dbz = desc_w0 + (uint64_t)((dz + 1) * 9 * (kK3WTile3 / 16) + (iy - r_hi + 1) * kK3C);
+#pragma unroll
+                            for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+                                for (int ks = 0; ks < 3; ++ks)
+                                    mma_ss(acc, da0 + (uint64_t)(ks * 2 * kK3Rows + dx),
+                                           dbz + (uint64_t)((dx * 3 + ks) * (kK3WTile3 / 16)), idesc, 1u);
+                        }
+                        mma_commit(&bar_empty[slot]);   // slot reusable once these MMAs have read it
+                        ++n_used;
+                    }
+                }
+                mma_commit(&bar_acc_full[buf]);
+            }
+        }
+    } else {
+        // ================================================ epilogue ====================================================
+        const int quad = warp & 3;                          // a warp may touch TMEM lanes 32 * (warp id % 4) .. + 31 only
+        const int et = quad * 32 + lane;                    // 0..127 = voxel x of this thread's TMEM lane (warps 5..8 -> 1,2,3,0)
+        const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+        constexpr int pitch = kK3C + 8;
+        double acc_s[2] = {0.0, 0.0}, acc_q[2] = {0.0, 0.0};   // threads et < 96: channel pair et % 24, row quarter et / 24
+        int64_t acc_b = -1;
+        const int cpair = et % 24, rq = et / 24;
+        auto flush = [&]() {
+            if (et < 96 && acc_b >= 0) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    double *dst = a.sums + (acc_b * kK3C + 2 * cpair + e) * 2;
+                    atomicAdd(dst, acc_s[e]);
+                    atomicAdd(dst + 1, acc_q[e]);
+                }
+            }
+            acc_s[0] = acc_s[1] = acc_q[0] = acc_q[1] = 0.0;
+        };
+        auto zero_and_release = [&](int buf) {
+            // every MMA accumulates, so an accumulator buffer is handed to the issuer zeroed
+            uint32_t zeros[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) zeros[i] = 0u;
+#pragma unroll
+            for (int c = 0; c < 4 * kK3C; c += 16) tmem_st16(tmem + lane_base + buf * 256 + c, zeros);
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_k3(&bar_acc_empty[buf]);
+        };
+        zero_and_release(0);
+        zero_and_release(1);
+        uint32_t nblk = 0;
+        for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x, ++nblk) {
+            const int yb = (int)(blk % yblocks);
+            const int64_t t2 = blk / yblocks;
+            const int z = (int)(t2 % a.D);
+            const int64_t b = t2 / a.D;
+            const int y0 = yb * 4;
+            const int buf = nblk & 1;
+            if (b != acc_b) { flush(); acc_b = b; }
+            mbar_wait(&bar_acc_full[buf], (nblk >> 1) & 1);
+            tc_fence_after();
+            for (int half = 0; half < 2; ++half) {          // two output rows at a time through the staging tile
+                const int rows_here = min(2, a.H - (y0 + 2 * half));
+                if (rows_here <= 0) break;
+                for (int rr = 0; rr < rows_here; ++rr) {
+                    const uint32_t acc = tmem + lane_base + buf * 256 + (3 - (2 * half + rr)) * kK3C;   // descending row order
+#pragma unroll
+                    for (int c = 0; c < kK3C; c += 16) {
+                        uint32_t r[16];
+                        tmem_ld16(acc + c, r);
+                        tmem_wait_ld();
+                        uint4 lo, hi;
+                        lo.x = pack_bf16(__uint_as_float(r[0]), __uint_as_float(r[1]));   lo.y = pack_bf16(__uint_as_float(r[2]), __uint_as_float(r[3]));
+                        lo.z = pack_bf16(__uint_as_float(r[4]), __uint_as_float(r[5]));   lo.w = pack_bf16(__uint_as_float(r[6]), __uint_as_float(r[7]));
+                        hi.x = pack_bf16(__uint_as_float(r[8]), __uint_as_float(r[9]));   hi.y = pack_bf16(__uint_as_float(r[10]), __uint_as_float(r[11]));
+                        hi.z = pack_bf16(__uint_as_float(r[12]), __uint_as_float(r[13])); hi.w = pack_bf16(__uint_as_float(r[14]), __uint_as_float(r[15]));
+                        uint4 *dst = reinterpret_cast<uint4 *>(sStage + (size_t)(rr * 128 + et) * pitch + c);
+                        dst[0] = lo;
+                        dst[1] = hi;
+                    }
+                }
+                if (half == 1 || a.H - (y0 + 2) <= 0) zero_and_release(buf);   // accumulators fully read
+                asm volatile("bar.sync 2, 128;" ::: "memory");      // staging complete (epilogue warps only)
+                // coalesced stores: rows y0 + 2*half (+1) are contiguous voxels in global memory
+                const int nvox = rows_here * 128;
+                const int64_t v0 = (((int64_t)b * a.D + z) * a.H + y0 + 2 * half) * W;
+                for (int i = et; i < nvox * kK3Chunks; i += 128) {
+                    const int vx = i / kK3Chunks, p = i - vx * kK3Chunks;
+                    *reinterpret_cast<uint4 *>(a.y + (v0 + vx) * a.ys + p * 8) =
+                        *reinterpret_cast<const uint4 *>(sStage + (size_t)vx * pitch + p * 8);
+                }
+                // statistics of the rounded outputs: 24 channel pairs x 4 row quarters
+                if (et < 96) {
+                    const uint32_t *col = reinterpret_cast<const uint32_t *>(sStage) + cpair;
+                    constexpr int wpitch = pitch / 2;
+                    const int q0 = rq * (nvox / 4), q1 = q0 + nvox / 4;
+                    float s0 = 0.f, s1 = 0.f, qq0 = 0.f, qq1 = 0.f;
+#pragma unroll 8
+                    for (int r = q0; r < q1; ++r) {
+                        const uint32_t w = col[(size_t)r * wpitch];
+                        asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %4;\n\t"
+                            "add.rn.f32.bf16 %0, lo, %0;\n\tadd.rn.f32.bf16 %1, hi, %1;\n\t"
+                            "fma.rn.f32.bf16 %2, lo, lo, %2;\n\tfma.rn.f32.bf16 %3, hi, hi, %3;\n\t}"
+                            : "+f"(s0), "+f"(s1), "+f"(qq0), "+f"(qq1) : "r"(w));
+                    }
+                    acc_s[0] += (double)s0; acc_s[1] += (double)s1; acc_q[0] += (double)qq0; acc_q[1] += (double)qq1;
+                }
+                asm volatile("bar.sync 2, 128;" ::: "memory");      // staging consumed before the next half overwrites it
+            }
+        }
+        flush();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+__global__ void k3_finalize_kernel(const double *__restrict__ sums, float *__restrict__ mr, int n, double inv_s, double eps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double m = sums[2 * i] * inv_s;
+    double var = sums[2 * i + 1] * inv_s - m * m;
+    var = var < 0.0 ? 0.0 : var;
+    mr[2 * i] = (float)m;
+    mr[2 * i + 1] = (float)(1.0 / sqrt(var + eps));
+}
+
+}  // namespace wf
+
+using namespace wf;
+
+extern "C" int wf_conv3d_k3_c48_in_stats(const void *x, const void *wpack, void *y, double *sums, float *mean_rstd,
+                                         const float *in_mean_rstd, float slope, float eps, int B, int D, int H, int W,
+                                         int64_t x_vox_stride, int64_t y_vox_stride, void *stream) {
+    if (!x || !wpack || !y || !sums || !mean_rstd) return WF_ERR_NULL_POINTER;
+    if (B <= 0 || D <= 0 || H <= 0 || W != 128) return WF_ERR_BAD_SHAPE;
+    if (x_vox_stride < kK3C || y_vox_stride < kK3C || x_vox_stride % 8 || y_vox_stride % 8) return WF_ERR_BAD_SHAPE;
+    if (!aligned16(x) || !aligned16(wpack) || !aligned16(y)) return WF_ERR_MISALIGNED;
+    cudaStream_t st = (cudaStream_t)stream;
+    static unsigned long long attr_done = 0;   // per-device opt-in bits
+    if (first_use_on_current_device(attr_done))
+        WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_k3_c48_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kK3Smem));
+    WF_CUDA_CHECK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)B * kK3C, st));
+    K3Args a;
+    a.x = (const __nv_bfloat16 *)x; a.wpack = (const uint16_t *)wpack; a.y = (__nv_bfloat16 *)y; a.sums = sums;
+    a.in_mr = in_mean_rstd; a.slope = slope; a.xs = x_vox_stride; a.ys = y_vox_stride; a.B = B; a.D = D; a.H = H;
+    const int64_t nblocks = (int64_t)B * D * ((H + 3) / 4);
+    const int grid = (int)(nblocks < kNumSMs ? nblocks : kNumSMs);
+    conv3d_k3_c48_kernel<<<grid, 288, kK3Smem, st>>>(a);
+    WF_LAUNCH_CHECK();
+    const int n = B * kK3C;
+    k3_finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(sums, mean_rstd, n, 1.0 / ((double)D * H * W), (double)eps);
+    WF_LAUNCH_CHECK();
+    return WF_OK;
+}

@@ -78,6 +78,20 @@ class UnetResBlock(nn.Module):
             self.conv3 = get_conv_layer(spatial_dims, in_channels, out_channels, 1, stride, dropout=dropout)
             self.norm3 = _norm(norm_name, out_channels)
 
+    def _conv2_after_norm(self, c1: torch.Tensor, s1):
+        """``conv2(lrelu(norm1(c1)))`` and, when the tensor-core kernel applies, norm2's statistics of the result.
+        48 -> 48 channels on rows of 128 voxels (the two 128^3 blocks): one producer / consumer tcgen05 kernel that
+        normalises its input while staging it and reduces the statistics of its output in its epilogue."""
+        c2 = self.conv2.conv
+        if (c1.dtype == torch.bfloat16 and c2.weight.dtype == torch.bfloat16 and c2.in_channels == 48 and c2.out_channels == 48
+                and c2.kernel_size == (3, 3, 3) and c2.stride == (1, 1, 1) and c2.bias is None and c1.shape[-1] == 128
+                and c1.stride(1) == 1 and self.norm1.eps == self.norm2.eps):
+            if s1 is None:
+                s1 = ops.instance_norm_stats(c1, eps=self.norm1.eps)
+            return ops.conv3d_k3_c48(c1, c2.weight, in_stats=s1, slope=0.01, eps=self.norm2.eps)
+        out = ops.instance_norm_act(c1, "leakyrelu", 0.01, eps=self.norm1.eps, stats=s1)
+        return self.conv2(out), None
+
     def _c4_fused(self, inp: torch.Tensor) -> bool:
         c1 = self.conv1.conv
         return (self.downsample and c1.in_channels == 4 and c1.kernel_size == (3, 3, 3) and c1.stride == (1, 1, 1)
@@ -94,14 +108,12 @@ class UnetResBlock(nn.Module):
             # 4-channel input (the network's first block): conv1, the 1^3 shortcut conv3 and both InstanceNorm statistics
             # in one tcgen05 kernel (the library convolution needs 3.3 ms for this K = 108 problem)
             c1, s1, c3, s3 = ops.conv3d_c4_in_stats(inp, self.conv1.conv.weight, self.conv3.conv.weight, eps=self.norm1.eps)
-            out = ops.instance_norm_act(c1, "leakyrelu", 0.01, eps=self.norm1.eps, stats=s1)
-            out = self.conv2(out)
+            out, s2 = self._conv2_after_norm(c1, s1)
             return ops.instance_norm_act(out, "leakyrelu", 0.01, res=c3, res_norm=True, eps=self.norm2.eps, res_stats=s3,
-                                         out=out_buf)
+                                         out=out_buf, stats=s2)
         if use_fused(inp):
             # InstanceNorm + LeakyReLU, and InstanceNorm (+ InstanceNorm'd shortcut) + add + LeakyReLU: one kernel each
-            out = ops.instance_norm_act(self.conv1(inp), "leakyrelu", 0.01, eps=self.norm1.eps)
-            out = self.conv2(out)
+            out, s2 = self._conv2_after_norm(self.conv1(inp), None)
             if self.downsample:
                 c3 = self.conv3.conv
                 if c3.kernel_size == (1, 1, 1) and c3.stride == (1, 1, 1) and inp.stride(1) == 1:
@@ -111,13 +123,13 @@ class UnetResBlock(nn.Module):
                     res = self.conv3(inp)
                 if head is not None:
                     return ops.instance_norm_act_head(out, head[0], head[1], "leakyrelu", 0.01, res=res, res_norm=True,
-                                                      eps=self.norm2.eps, out_dtype=head[2])
+                                                      eps=self.norm2.eps, out_dtype=head[2], stats=s2)
                 return ops.instance_norm_act(out, "leakyrelu", 0.01, res=res, res_norm=True, eps=self.norm2.eps,
-                                             out=out_buf)
+                                             out=out_buf, stats=s2)
             if head is not None:
                 return ops.instance_norm_act_head(out, head[0], head[1], "leakyrelu", 0.01, res=inp, eps=self.norm2.eps,
-                                                  out_dtype=head[2])
-            return ops.instance_norm_act(out, "leakyrelu", 0.01, res=inp, eps=self.norm2.eps, out=out_buf)
+                                                  out_dtype=head[2], stats=s2)
+            return ops.instance_norm_act(out, "leakyrelu", 0.01, res=inp, eps=self.norm2.eps, out=out_buf, stats=s2)
         out = self.lrelu(self.norm1(self.conv1(inp)))
         out = self.norm2(self.conv2(out))
         res = self.norm3(self.conv3(inp)) if self.downsample else inp

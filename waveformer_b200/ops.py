@@ -515,6 +515,44 @@ def instance_norm_act_head(x: torch.Tensor, head_w: torch.Tensor, head_b: Option
     return out.permute(0, 4, 1, 2, 3)
 
 
+_K3_PACK = {}
+
+
+def conv3d_k3_c48(x: torch.Tensor, weight: torch.Tensor, in_stats: Optional[torch.Tensor] = None, slope: float = 0.01,
+                  eps: float = 1e-5, out: Optional[torch.Tensor] = None):
+    """3^3 convolution 48 -> 48 (padding 1, no bias) of ``x[B, 48, D, H, 128]`` (bf16, channels-last-3d strides) on the
+    tensor cores.  With ``in_stats`` (the (mean, rstd) tensor of x) the input is InstanceNorm'd + LeakyReLU'd while it is
+    staged, i.e. the call computes ``conv(lrelu(IN(x)))``.  Returns ``(y, stats)``: y bf16 [B, 48, D, H, 128] channels-last
+    and the (mean, rstd) statistics of y for the following ``instance_norm_act(stats=...)``."""
+    dev = _need_cuda(x, weight, in_stats, out)
+    v, vs = _ndhwc_view(x)
+    B, D, H, W, C = v.shape
+    if v.dtype != torch.bfloat16 or C != 48 or W != 128 or tuple(weight.shape) != (48, 48, 3, 3, 3):
+        raise ValueError("conv3d_k3_c48: bf16 [B, 48, D, H, 128] input and a [48, 48, 3, 3, 3] weight")
+    key = id(weight)
+    tag = (weight._version, weight.data_ptr(), weight.dtype)
+    hit = _K3_PACK.get(key)
+    if hit is None or hit[0]() is not weight or hit[1] != tag:
+        w = weight.detach().float().permute(2, 3, 4, 0, 1).reshape(3, 3, 3, 48, 3, 2, 8)   # [dz, dy, dx, n, ks, chunk, e]
+        pack = w.permute(0, 2, 4, 5, 1, 3, 6).contiguous().to(torch.bfloat16)              # [dz, dx, ks, chunk, dy, n, e]
+        hit = (weakref.ref(weight), tag, pack)
+        _K3_PACK[key] = hit
+    if out is None:
+        out = torch.empty((B, D, H, W, 48), dtype=torch.bfloat16, device=dev)
+    ys = _voxel_stride(out)
+    if ys is None or tuple(out.shape) != (B, D, H, W, 48) or out.dtype != torch.bfloat16:
+        raise ValueError("out must be a voxel-dense bf16 [B, D, H, 128, 48] tensor")
+    sums = torch.empty(2 * B * 48, dtype=torch.float64, device=dev)
+    mr = torch.empty(2 * B * 48, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        st = _lib.lib().wf_conv3d_k3_c48_in_stats(v.data_ptr(), hit[2].data_ptr(), out.data_ptr(), sums.data_ptr(),
+                                                  mr.data_ptr(), _ptr(in_stats), float(slope), float(eps), B, D, H, W, vs,
+                                                  ys, _stream(dev))
+    _lib.check(st, "wf_conv3d_k3_c48_in_stats")
+    _count(2)
+    return out.permute(0, 4, 1, 2, 3), mr
+
+
 _CT_PACK = {}
 
 
