@@ -114,6 +114,21 @@ int wf_window_attn_fwd(const void *x, int x_dtype, const void *qkv_w, const void
                        void *workspace, size_t workspace_bytes, int dtype, int B, int D1, int H1, int W1, int C,
                        int heads, int ws, float scale, void *stream);
 
+/* Gradient of the attention core between the two Linear layers (training; reference network_models/attention.py:87-101,
+ * differentiated): S = (scale q) k^T + table[index], P = softmax(S), O = P v.
+ * workspace : the fp32 workspace wf_window_attn_fwd(dtype = WF_F32) left behind (q pre-scaled, k, v head-major
+ *             [windows][heads][N][hd], then O [windows * N, C]);
+ * d_o       : gradient wrt O, [windows * N, C] (= grad_out @ proj_w, a library GEMM done by the caller);
+ * d_qkv     : receives the gradient wrt the qkv Linear's output, [windows * N, 3C] (q part already multiplied by scale);
+ * d_table   : [table_rows, heads], ACCUMULATED into (the caller zeroes it);
+ * stats     : scratch of wf_window_attn_bwd_stats_bytes (log-sum-exp and delta of every score row).
+ * Probabilities are recomputed, never stored.  The gradients of the two Linear layers themselves are plain GEMMs on
+ * d_qkv / d_o and stay with the caller. */
+size_t wf_window_attn_bwd_stats_bytes(int64_t windows, int N, int heads);
+int wf_window_attn_bwd(const float *workspace, const float *bias_t, const float *table, const int64_t *index,
+                       const float *d_o, float *d_qkv, float *d_table, float *stats, int64_t windows, int N, int C,
+                       int heads, int table_rows, float scale, void *stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Block glue that dominated the step as library calls, channels-last, fp32 accumulate.
  * ---------------------------------------------------------------------------------------------------------- */

@@ -81,3 +81,41 @@ def test_zero_qkv_weight_known_answer(sd):
         y = m(seeded_randn((1, 512, 48), 34).cuda())
         want = torch.nn.functional.linear(m.qkv.bias[96:], m.proj.weight, m.proj.bias)
     assert float((y - want).abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("grid,ws,c,h", [((16, 16, 16), 8, 48, 3), ((8, 16, 8), 8, 96, 6), ((8, 8, 8), 4, 48, 3),
+                                        ((8, 8, 8), 8, 64, 2)])
+def test_attention_gradients_match_oracle_autograd(sd, grid, ws, c, h):
+    """wf_window_attn_bwd (attention core) + the Linear gradients vs fp64 autograd through the oracle restatement,
+    including the relative-position table gradient and the reshape-only reverse on the way back."""
+    from oracle.state import relative_position_index
+    from waveformer_b200.network_models import Attention
+    p = "attn"
+    hd = c // h
+    ref = {f"{p}.qkv.weight": seeded_randn((3 * c, c), 41) * c ** -0.5, f"{p}.qkv.bias": seeded_randn((3 * c,), 42) * 0.1,
+           f"{p}.proj.weight": seeded_randn((c, c), 43) * c ** -0.5, f"{p}.proj.bias": seeded_randn((c,), 44) * 0.1,
+           f"{p}.relative_position_bias_table": seeded_randn(((2 * ws - 1) ** 3, h), 45) * 0.5,
+           f"{p}.relative_position_index": relative_position_index(ws)}
+    m = Attention(c, num_heads=h, qkv_bias=True, window_size=ws).train()
+    m.load_state_dict(sub_state(ref, p), strict=True)
+    m = m.cuda()
+    x = seeded_randn((2,) + grid + (c,), 46)
+    gout = seeded_randn((2,) + grid + (c,), 47)
+
+    xg = x.cuda().requires_grad_(True)
+    y = m.forward_grid(xg)
+    y.backward(gout.cuda())
+    got = {"x": xg.grad, "qkv.weight": m.qkv.weight.grad, "qkv.bias": m.qkv.bias.grad, "proj.weight": m.proj.weight.grad,
+           "proj.bias": m.proj.bias.grad, "relative_position_bias_table": m.relative_position_bias_table.grad}
+
+    ref64 = {k: (v.double().requires_grad_(True) if v.is_floating_point() else v) for k, v in ref.items()}
+    x64 = x.double().requires_grad_(True)
+    y64 = om.window_attention(ref64, p, om.window_partition(x64, ws), h).reshape(x.shape)
+    assert max_rel(y.detach().cpu(), y64.detach().float()) < 2e-5
+    y64.backward(gout.double())
+    want = {"x": x64.grad}
+    want.update({k: ref64[f"{p}.{k}"].grad for k in got if k != "x"})
+    for k, g in got.items():
+        assert g is not None, k
+        assert max_rel(g.cpu(), want[k].float()) < 1e-4, k
+    assert hd in (16, 32)

@@ -306,7 +306,7 @@ def window_attention_uses_tensor_cores(grid, C: int, heads: int, ws: int, comput
 
 def _window_attention_raw(x, qkv_w, qkv_b, proj_w, proj_b, bias_t, heads: int, ws: int, scale: float,
                           compute_dtype: Optional[torch.dtype] = None, bias_img: Optional[torch.Tensor] = None,
-                          out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+                          out_dtype: Optional[torch.dtype] = None, return_workspace: bool = False):
     """``compute_dtype`` (default: x.dtype) is the weight / GEMM-operand type: bf16 or fp16 -> tcgen05 tensor-core path
     (needs ``bias_img``; x may be fp32 or bf16; the result is ``out_dtype`` = compute dtype or fp32); fp32 -> CUDA-core
     fp32 path (needs ``bias_t``)."""
@@ -337,7 +337,7 @@ def _window_attention_raw(x, qkv_w, qkv_b, proj_w, proj_b, bias_t, heads: int, w
                                   work.data_ptr(), nbytes, code, B, D1, H1, W1, C, heads, ws, float(scale), _stream(dev))
     _lib.check(st, "wf_window_attn_fwd")
     _count(3)
-    return out
+    return (out, work) if return_workspace else out
 
 
 def _window_partition(x: torch.Tensor, ws: int) -> torch.Tensor:
@@ -346,9 +346,54 @@ def _window_partition(x: torch.Tensor, ws: int) -> torch.Tensor:
     return x.permute(0, 1, 3, 5, 2, 4, 6, 7).reshape(-1, ws * ws * ws, c)
 
 
+def _window_unpartition(rows: torch.Tensor, shape, ws: int) -> torch.Tensor:
+    """Inverse of _window_partition: window-major rows ``[B * nW * ws^3, C]`` -> ``[B, D, H, W, C]``."""
+    b, d, h, w, c = shape
+    t = rows.reshape(b, d // ws, h // ws, w // ws, ws, ws, ws, c)
+    return t.permute(0, 1, 4, 2, 5, 3, 6, 7).reshape(b, d, h, w, c)
+
+
+def _window_attention_backward(g, x, qkv_w, qkv_b, proj_w, proj_b, table, index, heads: int, ws: int, scale: float):
+    """Gradients of window_attention in fp32.  q, k, v and O are recomputed by the fp32 forward kernels (nothing but the
+    layer input is kept between forward and backward), the attention core is differentiated by wf_window_attn_bwd, and the
+    gradients of the two Linear layers are library GEMMs on its d_qkv / on grad_out."""
+    dev = x.device
+    f32 = lambda t: None if t is None else t.detach().float().contiguous()
+    xf, wq, bq, wp, bp, tb = (f32(t) for t in (x, qkv_w, qkv_b, proj_w, proj_b, table))
+    index = index.contiguous()
+    B, D1, H1, W1, C = xf.shape
+    n = ws * ws * ws
+    windows = B * (D1 // ws) * (H1 // ws) * (W1 // ws)
+    M = windows * n
+    bias_t = relpos_bias_expand(tb, index)
+    _, work = _window_attention_raw(xf, wq, bq, wp, bp, bias_t, heads, ws, scale, torch.float32, None, torch.float32,
+                                    return_workspace=True)
+    wsf = work[: 4 * M * C * 4].view(torch.float32)
+    o = wsf[3 * M * C:].view(M, C)
+    g2 = g.detach().float().contiguous().view(M, C)       # the output buffer is window-major (reshape-only reverse)
+    d_proj_w = g2.t() @ o
+    d_proj_b = g2.sum(0)
+    d_o = g2 @ wp
+    d_qkv = torch.empty((M, 3 * C), dtype=torch.float32, device=dev)
+    d_table = torch.zeros_like(tb)
+    L = _lib.lib()
+    stats = torch.empty(L.wf_window_attn_bwd_stats_bytes(windows, n, heads) // 4, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        st = L.wf_window_attn_bwd(wsf.data_ptr(), bias_t.data_ptr(), tb.data_ptr(), index.data_ptr(), d_o.data_ptr(),
+                                  d_qkv.data_ptr(), d_table.data_ptr(), stats.data_ptr(), windows, n, C, heads,
+                                  tb.shape[0], float(scale), _stream(dev))
+    _lib.check(st, "wf_window_attn_bwd")
+    _count(2)
+    xw = _window_partition(xf, ws).reshape(M, C)
+    d_qkv_w = d_qkv.t() @ xw
+    d_qkv_b = d_qkv.sum(0) if qkv_b is not None else None
+    d_x = _window_unpartition(d_qkv @ wq, xf.shape, ws)
+    return d_x, d_qkv_w, d_qkv_b, d_proj_w, d_proj_b, d_table
+
+
 class _WindowAttention(torch.autograd.Function):
-    """Forward = the CUDA kernels.  Backward (training, BASELINE config 5) currently re-derives the gradient by
-    recomputing the window attention with torch ops under autograd - a library path, listed as a gap in DESIGN.md."""
+    """Forward = the CUDA kernels (any operand format).  Backward (training, BASELINE config 5) = fp32 recompute of
+    q / k / v / O with the forward kernels + wf_window_attn_bwd; see _window_attention_backward."""
 
     @staticmethod
     def forward(ctx, x, qkv_w, qkv_b, proj_w, proj_b, table, index, bias_t, heads, ws, scale, compute_dtype, bias_img,
@@ -362,21 +407,10 @@ class _WindowAttention(torch.autograd.Function):
     def backward(ctx, g):
         x, qkv_w, qkv_b, proj_w, proj_b, table, index = ctx.saved_tensors
         heads, ws, scale = ctx.cfg
-        with torch.enable_grad():
-            srcs = (x, qkv_w, qkv_b, proj_w, proj_b, table)
-            leaves = [None if t is None else t.detach().float().requires_grad_(True) for t in srcs]
-            xx, wq, bq, wp, bp, tb = leaves
-            win = _window_partition(xx, ws)
-            b_, n, c = win.shape
-            qkv = torch.nn.functional.linear(win, wq, bq).reshape(b_, n, 3, heads, c // heads).permute(2, 0, 3, 1, 4)
-            s = (qkv[0] * scale) @ qkv[1].transpose(-2, -1)
-            s = s + tb[index.reshape(-1)].reshape(n, n, heads).permute(2, 0, 1)[None]
-            o = (torch.softmax(s, -1) @ qkv[2]).transpose(1, 2).reshape(b_, n, c)
-            y = torch.nn.functional.linear(o, wp, bp).reshape(x.shape)
-            live = [t for t in leaves if t is not None]
-            grads = list(torch.autograd.grad(y, live, g.float()))
-        out = [None if s_ is None else grads.pop(0).to(s_.dtype) for s_ in srcs]
-        return (out[0], out[1], out[2], out[3], out[4], out[5]) + (None,) * 8
+        srcs = (x, qkv_w, qkv_b, proj_w, proj_b, table)
+        grads = _window_attention_backward(g, x, qkv_w, qkv_b, proj_w, proj_b, table, index, heads, ws, scale)
+        out = tuple(None if (s_ is None or g_ is None) else g_.to(s_.dtype) for s_, g_ in zip(srcs, grads))
+        return out + (None,) * 8
 
 
 def window_attention(x, qkv_w, qkv_b, proj_w, proj_b, table, index, bias_t, heads: int, ws: int, scale: float,
