@@ -151,6 +151,18 @@ def kernel_rooflines(pk):
     out["window_attention_c48_tc"] = dict(bound="tensor", achieved=round(tf, 2), peak=pk["bf16_tflops"], unit="TFLOP/s",
                                           frac=round(tf / pk["bf16_tflops"], 5), ms=round(t, 4), algorithmic_flops=flops,
                                           note="head_dim 16: exponent-bound (65536 ex2 per 128x512 tile vs 512 tensor clk), DESIGN.md 5")
+    # 3x3x3 convolution 48 -> 48 on 2 x 128^3 (conv2 of encoder1 / decoder1): the largest single kernel of the window forward
+    xk = torch.randn((2, 128, 128, 128, 48), device="cuda").bfloat16().permute(0, 4, 1, 2, 3)
+    wk = (torch.randn((48, 48, 3, 3, 3), device="cuda") / 36).bfloat16()
+    with torch.no_grad():
+        t = event_ms(lambda: ops.conv3d_k3_c48(xk, wk), 10)
+    flops = 2 * xk.numel() * 48 * 27
+    tf = flops / (t * 1e-3) / 1e12
+    out["conv3d_k3_c48_tc"] = dict(bound="tensor", achieved=round(tf, 2), peak=pk["bf16_tflops"], unit="TFLOP/s",
+                                   frac=round(tf / pk["bf16_tflops"], 5), ms=round(t, 4), algorithmic_flops=flops,
+                                   note="N = 48 output channels: one tcgen05.mma per 128 x 16 activation operand, DESIGN.md 4")
+    del xk, wk
+    torch.cuda.empty_cache()
     return out
 
 
