@@ -252,10 +252,12 @@ int wf_sw_accumulate(const void *seg, float *acc, const int32_t *starts, const f
 /* acc[b, k, z, y, x] /= sum over every window w of `all_starts` (int32 [nall][4], the FULL window list of the
  * volume batch, not just this rank's) covering the voxel of max(gz*gy*gx, floor).  The count map is geometry only,
  * so it is recomputed here instead of being stored and reduced (inferers/utils.py:265-276, :298-299).
- * labels (optional, uint8 [Bv, D, H, W]) receives argmax over k (4_predict.py:241). */
+ * labels (optional, uint8 [Bv, D, H, W]) receives argmax over k (4_predict.py:241).
+ * Only planes z in [z_begin, z_end) of every volume are normalised, so a slab whose windows are all accumulated can be
+ * finished (and copied to the host) while later windows still run; (0, D) = the whole volume. */
 int wf_sw_finalize(float *acc, uint8_t *labels, const int32_t *all_starts, int nall, const float *gz, const float *gy,
                    const float *gx, float floor_w, int Bv, int K, int D, int H, int W, int r0, int r1, int r2,
-                   void *stream);
+                   int z_begin, int z_end, void *stream);
 
 #ifdef __cplusplus
 }

@@ -154,3 +154,27 @@ def test_predictor_mirror_tta_matches_reference_loop():
     assert res.dtype == torch.half and max_rel(res.float().cpu(), op.predict_raw_probability(want, (50, 30, 33)).float()) < 2e-3
     labels, regions = Predictor.labels_and_regions(res)
     assert labels.dtype == torch.uint8 and tuple(regions.shape) == (3, 50, 30, 33)
+
+
+@pytest.mark.parametrize("shape,roi,ov,bs", [((1, 2, 40, 36, 30), (16, 16, 16), 0.5, 2),
+                                             ((3, 2, 24, 33, 17), (16, 16, 16), 0.25, 3),
+                                             ((1, 2, 12, 40, 16), (16, 16, 16), 0.5, 4)])   # last: padded (12 < 16)
+def test_streamed_host_io_equals_device_resident(shape, roi, ov, bs):
+    """Pinned host input (z-slab H2D on the copy stream) + device='cpu' (z-slab normalise + D2H while later windows run)
+    must give the all-resident call's logits and labels (up to the order of the float atomic adds of overlapping windows,
+    which differs from run to run in either mode)."""
+    from waveformer_b200.inferers import SlidingWindowInferer
+    wconv = (seeded_randn((3, 2, 3, 3, 3), 600) * 0.2).cuda()
+    net = lambda p: torch.nn.functional.conv3d(p, wconv, padding=1)
+    x = seeded_randn(shape, 77)
+    kw = dict(roi_size=roi, sw_batch_size=bs, overlap=ov, mode="gaussian", compute_dtype=torch.float32, return_labels=True)
+    ref_inf = SlidingWindowInferer(**kw)
+    want = ref_inf(x.cuda(), net)
+    inf = SlidingWindowInferer(device="cpu", **kw)
+    for _ in range(2):                       # second call reuses the pinned buffer and the cached plans
+        got = inf(x.pin_memory(), net)
+        assert not got.is_cuda and got.is_pinned()
+        assert got.shape == want.shape and max_rel(got, want.cpu()) < 1e-6
+        assert float((inf.labels.cpu() != ref_inf.labels.cpu()).float().mean()) < 1e-4
+    mid = SlidingWindowInferer(**kw)(x.pin_memory(), net)      # host in, device out
+    assert mid.is_cuda and max_rel(mid.cpu(), want.cpu()) < 1e-6

@@ -196,3 +196,24 @@ def test_cast_cache_never_serves_a_dead_tensors_copy():
     q = ops.cast_cached(p, torch.bfloat16)
     p.mul_(2)                                                    # in-place update bumps _version -> new copy
     assert float(ops.cast_cached(p, torch.bfloat16)[0]) == 2.0 and float(q[0]) == 1.0
+
+
+def test_output_schedule_tiles_every_volume():
+    """Streamed output: slabs become final in order, never before their last window, and tile [0, D) exactly."""
+    from waveformer_b200.inferers import output_schedule, scan_interval, window_starts
+    size, roi = (240, 240, 155), (128, 128, 128)
+    starts = window_starts(size, roi, scan_interval(size, roi, (0.5,) * 3))
+    wins = [(v, s[0]) for v in range(2) for s in starts]
+    batches = [wins[i:i + 4] for i in range(0, len(wins), 4)]
+    sched = output_schedule(batches, size[0])
+    assert len(sched) == len(batches)
+    cover = {0: [], 1: []}
+    for j, out in enumerate(sched):
+        later = [w for b in batches[j + 1:] for w in b]
+        for v, za, zb in out:
+            cover[v].append((za, zb))
+            assert all(not (lv == v and lz < zb) for lv, lz in later)       # nothing still to come overlaps the slab
+    for v in cover:
+        assert cover[v][0][0] == 0 and cover[v][-1][1] == size[0]
+        assert all(a[1] == b[0] for a, b in zip(cover[v], cover[v][1:]))
+    assert cover[0] == [(0, 64), (64, 112), (112, 240)]

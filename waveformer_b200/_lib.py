@@ -45,7 +45,7 @@ SIGNATURES = {
     "wf_convtranspose3d_k2s2_ndhwc": (_I, [_VOIDP, _VOIDP, _VOIDP, _I, _I, _I, _I, _I, _I, _I, _I64, _I64, _VOIDP]),
     "wf_sw_gather": (_I, [_VOIDP, _VOIDP, _VOIDP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VOIDP]),
     "wf_sw_accumulate": (_I, [_VOIDP] * 6 + [_F, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VOIDP]),
-    "wf_sw_finalize": (_I, [_VOIDP, _VOIDP, _VOIDP, _I, _VOIDP, _VOIDP, _VOIDP, _F] + [_I] * 8 + [_VOIDP]),
+    "wf_sw_finalize": (_I, [_VOIDP, _VOIDP, _VOIDP, _I, _VOIDP, _VOIDP, _VOIDP, _F] + [_I] * 10 + [_VOIDP]),
 }
 
 _LIB: Optional[ctypes.CDLL] = None

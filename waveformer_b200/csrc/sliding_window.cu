@@ -64,7 +64,8 @@ __global__ void __launch_bounds__(256) sw_finalize_kernel(float *__restrict__ ac
                                                           const int32_t *__restrict__ all_starts, int nall,
                                                           const float *__restrict__ gz, const float *__restrict__ gy,
                                                           const float *__restrict__ gx, float floor_w, int64_t total,
-                                                          int K, int D, int H, int W, int r0, int r1, int r2) {
+                                                          int K, int D, int H, int W, int r0, int r1, int r2, int z_begin,
+                                                          int z_end) {
     extern __shared__ int32_t s_starts[];
     for (int i = threadIdx.x; i < 4 * nall; i += blockDim.x) s_starts[i] = all_starts[i];
     __syncthreads();
@@ -73,7 +74,8 @@ __global__ void __launch_bounds__(256) sw_finalize_kernel(float *__restrict__ ac
     int64_t t = idx;
     const int x = (int)(t % W); t /= W;
     const int y = (int)(t % H); t /= H;
-    const int z = (int)(t % D); t /= D;
+    const int nz = z_end - z_begin;                 // only planes [z_begin, z_end) of every volume (streamed output)
+    const int z = z_begin + (int)(t % nz); t /= nz;
     const int b = (int)t;
     float count = 0.f;
     for (int n = 0; n < nall; ++n) {  // same order as the reference's `for __s in slices: count_map[__s] += w`
@@ -92,7 +94,7 @@ __global__ void __launch_bounds__(256) sw_finalize_kernel(float *__restrict__ ac
         *p = v;
         if (v > best) { best = v; arg = k; }
     }
-    if (labels) labels[idx] = (uint8_t)arg;
+    if (labels) labels[(int64_t)b * plane + sp] = (uint8_t)arg;
 }
 
 }  // namespace wf
@@ -134,12 +136,13 @@ extern "C" int wf_sw_accumulate(const void *seg, float *acc, const int32_t *star
 
 extern "C" int wf_sw_finalize(float *acc, uint8_t *labels, const int32_t *all_starts, int nall, const float *gz,
                               const float *gy, const float *gx, float floor_w, int Bv, int K, int D, int H, int W,
-                              int r0, int r1, int r2, void *stream) {
+                              int r0, int r1, int r2, int z_begin, int z_end, void *stream) {
     if (!acc || !all_starts || !gz || !gy || !gx) return WF_ERR_NULL_POINTER;
     if (nall <= 0 || nall > 8192 || Bv <= 0 || K <= 0) return WF_ERR_BAD_SHAPE;
-    const int64_t total = (int64_t)Bv * D * H * W;
+    if (z_begin < 0 || z_end > D || z_begin >= z_end) return WF_ERR_BAD_SHAPE;
+    const int64_t total = (int64_t)Bv * (z_end - z_begin) * H * W;
     sw_finalize_kernel<<<blocks_for(total), 256, (size_t)nall * 16, (cudaStream_t)stream>>>(
-        acc, labels, all_starts, nall, gz, gy, gx, floor_w, total, K, D, H, W, r0, r1, r2);
+        acc, labels, all_starts, nall, gz, gy, gx, floor_w, total, K, D, H, W, r0, r1, r2, z_begin, z_end);
     WF_LAUNCH_CHECK();
     return WF_OK;
 }

@@ -14,9 +14,14 @@ What changes relative to the reference's loop (same results):
   gets ONE ``reduce(SUM)`` (NCCL over NVLink) to its owner rank, which normalises it.  One volume on N GPUs is the
   north star's case (a single reduce of the stitched logit volume to rank 0); with at least N volumes no volume is
   split and the path has no collective at all.  Windows are independent, so nothing else is ever exchanged.
+* host input / host output are STREAMED: a volume handed over in (pinned) host memory is copied in z-slabs on a copy
+  stream and a window batch only waits for the slabs it reads; with ``device="cpu"`` (MONAI's name for "where the
+  stitched output lives") a z-slab of the output is normalised and copied back as soon as no remaining window touches
+  it, so most of both transfers hides behind the window forwards.
 """
 from __future__ import annotations
 
+import bisect
 import itertools
 import math
 from typing import Callable, List, Optional, Sequence, Tuple
@@ -97,12 +102,61 @@ def volume_plan(num_volumes: int, windows_per_volume: int, sw_batch_size: int, w
 
 
 # ------------------------------------------------------------------------------------------------------ inferer
+def output_schedule(batches: Sequence[Sequence[Tuple[int, int]]], depth: int):
+    """When is a z-slab of a volume final?  ``batches[j]`` lists ``(volume, z_start)`` of the windows of batch j, in
+    processing order.  Returns ``sched[j] = [(volume, z_a, z_b), ...]``: after batch j no remaining window of `volume`
+    starts below z_b, so planes [z_a, z_b) can be normalised and shipped.  The slabs of a volume tile [0, depth)."""
+    remaining = {}
+    for b in batches:
+        for v, z in b:
+            remaining.setdefault(v, []).append(z)
+    done = {v: 0 for v in remaining}
+    sched = []
+    for b in batches:
+        for v, z in b:
+            remaining[v].remove(z)
+        out = []
+        for v in sorted({v for v, _ in b}):
+            z_final = min(remaining[v]) if remaining[v] else depth
+            if z_final > done[v]:
+                out.append((v, done[v], z_final))
+                done[v] = z_final
+        sched.append(out)
+    return sched
+
+
+_COPY_STREAMS = {}
+_PINNED = {}
+
+
+def _copy_stream(dev: torch.device) -> torch.cuda.Stream:
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _COPY_STREAMS[key]
+
+
+def _pinned_out(shape, cache) -> torch.Tensor:
+    """Page-locked result buffer, reused while the shape stays the same (pinning 143 MB costs more than the transfer):
+    the tensor a host-output call returns is valid until the next call on the same inferer."""
+    shape = tuple(shape)
+    buf = cache.get("host_out")
+    if buf is None or tuple(buf.shape) != shape:
+        buf = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+        cache["host_out"] = buf
+    return buf
+
+
 class SlidingWindowInferer:
     """Callable ``inferer(inputs, network)`` with MONAI's constructor arguments for the path the reference uses.
 
     Extra (keyword-only) arguments: ``process_group`` / ``shard`` (patch sharding over one process per GPU),
     ``compute_dtype`` (dtype the windows are handed to the network in; default: the network's parameter dtype),
     ``channels_last`` (hand the network channels-last-3d windows), ``return_labels`` (also produce the argmax map).
+
+    ``device``: ``None`` keeps the stitched volume in HBM (a CUDA tensor is returned whatever the input's device);
+    ``"cpu"`` returns it in page-locked host memory, streamed back slab by slab while later windows still run (the
+    buffer is reused by the next call of this inferer).  ``sw_device`` is implied: windows always run on the GPU.
     """
 
     def __init__(self, roi_size, sw_batch_size: int = 1, overlap=0.25, mode="constant", sigma_scale=0.125,
@@ -127,6 +181,9 @@ class SlidingWindowInferer:
         self.compute_dtype = compute_dtype
         self.channels_last = channels_last
         self.return_labels = return_labels
+        self.device = None if device is None else torch.device(device)
+        if self.device is not None and self.device.type not in ("cpu", "cuda"):
+            raise ValueError(f"device must be a cpu or cuda device, got {device}")
         self.labels: Optional[torch.Tensor] = None
         self.owned_volumes: List[int] = []
         self._geom_cache = {}
@@ -135,7 +192,7 @@ class SlidingWindowInferer:
         out, labels, owned = _run(inputs, self.roi_size, self.sw_batch_size, network, self.overlap, self.mode,
                                   self.sigma_scale, self.padding_mode, self.cval, self.process_group, self.shard,
                                   self.compute_dtype, self.channels_last, self.return_labels, False, self._geom_cache,
-                                  args, kwargs)
+                                  args, kwargs, host_out=self.device is not None and self.device.type == "cpu")
         self.labels = labels
         self.owned_volumes = owned      # indices (into the input batch) of the volumes returned on THIS rank
         return out
@@ -151,7 +208,7 @@ def sliding_window_inference(inputs, roi_size, sw_batch_size, predictor, overlap
     roi = tuple(roi_size) if isinstance(roi_size, (tuple, list)) else (roi_size,) * 3
     out, _, _ = _run(inputs, roi, int(sw_batch_size), predictor, overlap, getattr(mode, "value", mode), sigma_scale,
                      getattr(padding_mode, "value", padding_mode), cval, process_group, True, None, True, False, False,
-                     {}, args, kwargs)
+                     _PINNED, args, kwargs, host_out=device is not None and torch.device(device).type == "cpu")
     return out
 
 
@@ -165,7 +222,7 @@ def _network_dtype(network, fallback: torch.dtype) -> torch.dtype:
 
 
 def _run(inputs, roi_size, sw_batch_size, network, overlap, mode, sigma_scale, padding_mode, cval, group, shard,
-         compute_dtype, channels_last, return_labels, gather_result, cache, args, kwargs):
+         compute_dtype, channels_last, return_labels, gather_result, cache, args, kwargs, host_out: bool = False):
     """Returns ``(logits, labels, owned)``: ``logits[i]`` is the stitched fp32 volume ``owned[i]`` (indices into the
     input batch).  Single process: ``owned`` is every volume, i.e. exactly the reference's return value."""
     if inputs.dim() != 5:
@@ -200,8 +257,8 @@ def _run(inputs, roi_size, sw_batch_size, network, overlap, mode, sigma_scale, p
         touch = volume_plan(batch, nwin, sw_batch_size, world)
         local_vols = [v for v in range(batch) if rank in touch[v]]          # volumes this rank stitches into
         slot = {v: i for i, v in enumerate(local_vols)}
-        my_tables = [torch.tensor([(slot[i // nwin],) + tuple(starts[i % nwin]) for i in b], dtype=torch.int32, device=dev)
-                     for b in mine]
+        host_tables = [[(slot[i // nwin],) + tuple(starts[i % nwin]) for i in b] for b in mine]
+        my_tables = [torch.tensor(t, dtype=torch.int32, device=dev) for t in host_tables]
         # contiguous runs => at most the FIRST local volume is finalised by an earlier rank; the rest are ours
         owned = [v for v in local_vols if touch[v][0] == rank]
         own_off = len(local_vols) - len(owned)
@@ -210,14 +267,38 @@ def _run(inputs, roi_size, sw_batch_size, network, overlap, mode, sigma_scale, p
                                  dtype=torch.int32, device=dev)
         shared = [v for v in range(batch) if len(touch[v]) > 1]
         fac, floor = gaussian_factors(roi, mode, sg)
-        cache[key] = (my_tables, local_vols, slot, owned, own_off, fin_table, shared, touch, [f.to(dev) for f in fac], floor)
-    my_tables, local_vols, slot, owned, own_off, fin_table, shared, touch, (gz, gy, gx), floor = cache[key]
+        # streaming plans (host side): z-slabs of the input in the order windows need them, and when output slabs are final
+        slab_ends = sorted({s_[0] + roi[0] for s_ in starts})
+        need = [max((t[0], bisect.bisect_left(slab_ends, t[1] + roi[0])) for t in tb) for tb in host_tables]
+        sched = output_schedule([[(t[0], t[1]) for t in tb] for tb in host_tables], size[0])
+        fin_one = torch.tensor([(0,) + tuple(s_) for s_ in starts], dtype=torch.int32, device=dev)
+        cache[key] = (my_tables, local_vols, slot, owned, own_off, fin_table, shared, touch, [f.to(dev) for f in fac], floor,
+                      slab_ends, need, sched, fin_one)
+    (my_tables, local_vols, slot, owned, own_off, fin_table, shared, touch, (gz, gy, gx), floor, slab_ends, need, sched,
+     fin_one) = cache[key]
 
     # bring in only the volumes this rank touches (host input: this is the H2D copy of the end-to-end path)
     if local_vols:
         lo, hi = local_vols[0], local_vols[-1] + 1                          # contiguous by construction
         vol = inputs[lo:hi]
-        if not vol.is_cuda:
+        in_events = None
+        if not vol.is_cuda and vol.dtype == torch.float32 and not any(pad) and my_tables:
+            # streamed H2D: z-slabs in the order the windows need them, one contiguous copy per (volume, channel, slab)
+            src = vol.contiguous()
+            vol = torch.empty(src.shape, dtype=torch.float32, device=dev)
+            cs = _copy_stream(dev)
+            cs.wait_stream(torch.cuda.current_stream(dev))
+            in_events = {}
+            with torch.cuda.stream(cs):
+                for v in range(src.shape[0]):
+                    a = 0
+                    for si, b in enumerate(slab_ends):
+                        for c in range(src.shape[1]):
+                            vol[v, c, a:b].copy_(src[v, c, a:b], non_blocking=True)
+                        in_events[(v, si)] = cs.record_event()
+                        a = b
+            vol.record_stream(cs)
+        elif not vol.is_cuda:
             vol = vol.to(dev, non_blocking=True)
         if vol.dtype != torch.float32:
             vol = vol.float()
@@ -227,7 +308,14 @@ def _run(inputs, roi_size, sw_batch_size, network, overlap, mode, sigma_scale, p
     dtype = compute_dtype or _network_dtype(network, torch.float32)
 
     acc = None
-    for st in my_tables:
+    labels_buf = None
+    # output slabs of volumes that are stitched by this rank alone can leave while later windows run
+    stream_out = host_out and not any(pad)
+    streamable = {slot[v] for v in owned if v not in shared} if stream_out else set()
+    out_host, out_stream = None, None
+    for j, st in enumerate(my_tables):
+        if in_events is not None:
+            torch.cuda.current_stream(dev).wait_event(in_events[need[j]])   # copies are in order: the last slab suffices
         win = ops.sw_gather(vol, st, roi, dtype, channels_last)
         if channels_last:
             win = win.permute(0, 4, 1, 2, 3)  # [n, C, r, r, r] with channels-last-3d strides, zero copy
@@ -242,6 +330,22 @@ def _run(inputs, roi_size, sw_batch_size, network, overlap, mode, sigma_scale, p
             ops.sw_accumulate(seg.permute(0, 2, 3, 4, 1), acc, st, gz, gy, gx, floor, True)
         else:
             ops.sw_accumulate(seg, acc, st, gz, gy, gx, floor, False)
+        for (sl, za, zb) in sched[j]:
+            if sl not in streamable:
+                continue
+            if out_host is None:
+                out_host = _pinned_out((len(owned), acc.shape[1]) + size, cache)
+                out_stream = _copy_stream(dev)
+                acc.record_stream(out_stream)
+                if return_labels and labels_buf is None:
+                    labels_buf = torch.empty((len(owned),) + size, dtype=torch.uint8, device=dev)
+            i = sl - own_off
+            ops.sw_finalize(acc[sl:sl + 1], fin_one, gz, gy, gx, floor, roi,
+                            None if labels_buf is None else labels_buf[i:i + 1], z_range=(za, zb))
+            out_stream.wait_event(torch.cuda.current_stream(dev).record_event())
+            with torch.cuda.stream(out_stream):
+                for k in range(acc.shape[1]):
+                    out_host[i, k, za:zb].copy_(acc[sl, k, za:zb], non_blocking=True)
 
     if world > 1 and shared:
         k = _agree_channels(acc, network, dist, group, dev)
@@ -262,8 +366,14 @@ def _run(inputs, roi_size, sw_batch_size, network, overlap, mode, sigma_scale, p
     if owned:
         acc_owned, fin = acc[own_off:], fin_table
         if return_labels:
-            labels = torch.empty((len(owned),) + size, dtype=torch.uint8, device=dev)
-        ops.sw_finalize(acc_owned, fin, gz, gy, gx, floor, roi, labels)
+            labels = labels_buf if labels_buf is not None else torch.empty((len(owned),) + size, dtype=torch.uint8, device=dev)
+        rest = [v for v in owned if slot[v] not in streamable]        # everything, unless the output is streamed
+        if len(rest) == len(owned):
+            ops.sw_finalize(acc_owned, fin, gz, gy, gx, floor, roi, labels)
+        else:
+            for v in rest:
+                i = slot[v] - own_off
+                ops.sw_finalize(acc_owned[i:i + 1], fin_one, gz, gy, gx, floor, roi, None if labels is None else labels[i:i + 1])
         out = acc_owned
     else:
         out = None
@@ -275,6 +385,17 @@ def _run(inputs, roi_size, sw_batch_size, network, overlap, mode, sigma_scale, p
         out = out[tuple(crop)]
         if labels is not None:
             labels = labels[tuple(crop[1:])]
+    if host_out and out is not None:
+        if out_host is None or any(pad):
+            out_host = _pinned_out(out.shape, cache)
+            out_host.copy_(out, non_blocking=True)
+        else:
+            for v in owned:                          # volumes that could not be streamed (finished by a reduce)
+                if slot[v] not in streamable:
+                    out_host[slot[v] - own_off].copy_(out[slot[v] - own_off], non_blocking=True)
+            out_stream.synchronize()
+        torch.cuda.current_stream(dev).synchronize()
+        out = out_host
     return out, labels, owned
 
 

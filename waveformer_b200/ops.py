@@ -825,13 +825,15 @@ def sw_accumulate(seg: torch.Tensor, acc: torch.Tensor, starts: torch.Tensor, gz
 
 
 def sw_finalize(acc: torch.Tensor, all_starts: torch.Tensor, gz, gy, gx, floor_w: float, roi,
-                labels: Optional[torch.Tensor] = None) -> None:
+                labels: Optional[torch.Tensor] = None, z_range: Optional[Tuple[int, int]] = None) -> None:
+    """Divide the accumulated volume(s) by the recomputed count map, in place; ``z_range`` limits it to planes [a, b)."""
     dev = _need_cuda(acc, all_starts, gz, gy, gx, labels)
     Bv, K, D, H, W = acc.shape
     r0, r1, r2 = roi
+    za, zb = (0, D) if z_range is None else (int(z_range[0]), int(z_range[1]))
     with torch.cuda.device(dev):
         st = _lib.lib().wf_sw_finalize(acc.data_ptr(), _ptr(labels), all_starts.data_ptr(), all_starts.shape[0],
                                        gz.data_ptr(), gy.data_ptr(), gx.data_ptr(), float(floor_w), Bv, K, D, H, W, r0,
-                                       r1, r2, _stream(dev))
+                                       r1, r2, za, zb, _stream(dev))
     _lib.check(st, "wf_sw_finalize")
     _count()
