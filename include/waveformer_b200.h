@@ -30,8 +30,9 @@ typedef enum {
     WF_ERR_UNSUPPORTED = -7
 } wf_status;
 
-/* WF_F16 is accepted only as the operand format of the tensor-core window attention (`dtype` of wf_window_attn_fwd and
- * `fmt` of wf_relpos_bias_image); activations are stored as WF_F32 or WF_BF16 everywhere. */
+/* WF_F16 is accepted as the operand format of the tensor-core window attention (`dtype` of wf_window_attn_fwd and
+ * `fmt` of wf_relpos_bias_image) and as the activation type of the two InstanceNorm entry points (fp16 skip blocks of the
+ * precision policy); everything else stores activations as WF_F32 or WF_BF16. */
 typedef enum { WF_F32 = 0, WF_BF16 = 1, WF_F16 = 2 } wf_dtype;
 
 const char *wf_version(void);
@@ -133,6 +134,14 @@ int wf_window_attn_bwd(const float *workspace, const float *bias_t, const float 
  * Block glue that dominated the step as library calls, channels-last, fp32 accumulate.
  * ---------------------------------------------------------------------------------------------------------- */
 
+/* PatchMerging front half: y[b, z, y, x, s*C + c] = LayerNorm_{8C}(x[b, 2z+i_s, 2y+j_s, 2x+k_s, c]) for the 8 octants
+ * s = 0..7, (i_s, j_s, k_s) = bits 2, 1, 0 of ((octants >> 3s) & 7).  Replaces the eight strided slices + torch.cat + self.norm
+ * of PatchMerging.forward (reference network_models/wave_helper.py:170-194; MONAI 0.9's order repeats two octants, which
+ * is why the order is an argument) - the [.., 8C] concatenation is never stored.  x: fp32 [B, D, H, W, C] dense, D/H/W even,
+ * C % 16 == 0 and C <= 192; gamma / beta: fp32 [8C]; y: [B, D/2, H/2, W/2, 8C] dense, out_dtype WF_F32 or WF_BF16. */
+int wf_patch_merge_layernorm(const float *x, const float *gamma, const float *beta, void *y, int out_dtype, int B, int D,
+                             int H, int W, int C, uint32_t octants, float eps, void *stream);
+
 /* Depthwise 3x3x3 convolution, zero padding 1: y[b,z,y,x,c] = bias[c] + sum_taps w27[tap][c] * x[b,z+dz,y+dy,x+dx,c].
  * Replaces CCF_FFN.dwconv (reference network_models/wave_helper.py:231-232,283) and ProjectionUpsample.conv1[1]
  * (wave_helper.py:44).  x, y: [B, D, H, W, C] dense channels-last; w27: fp32 [27][C], tap = (dz+1)*9+(dy+1)*3+(dx+1),
@@ -151,7 +160,8 @@ int wf_instnorm_stats_ndhwc(const void *x, double *sums, float *mean_rstd, int d
  * (res - mean_r) * rstd_r; gamma / beta (fp32 [C]) optional.  act: 0 none, 1 ReLU, 2 LeakyReLU(slope).
  * Fuses norm + residual add + activation of dynunet_block.py:100-110; with gamma / beta it is GroupNorm(num_groups = C)
  * of ProjectionUpsample.norm (reference network_models/wave_helper.py:59,74).  x and res share `dtype`; y_dtype is `dtype`, or
- * WF_BF16 with dtype WF_F32 (a block kept in fp32 / TF32 by the precision policy writing into a bf16 concat buffer). */
+ * WF_BF16 with dtype WF_F32 / WF_F16 (a block kept in fp32-TF32 or fp16 by the precision policy writing into a bf16 concat
+ * buffer).  WF_F16 activations are accepted by these two InstanceNorm entry points (stats and apply) only. */
 int wf_instnorm_apply_ndhwc(const void *x, const float *mean_rstd, const void *res, const float *res_mean_rstd,
                             const float *gamma, const float *beta, void *y, int act, float slope, int dtype, int y_dtype,
                             int B, int64_t S, int C, int64_t x_vox_stride, int64_t res_vox_stride, int64_t y_vox_stride,

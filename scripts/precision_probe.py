@@ -48,6 +48,8 @@ def build(sd, **policy):
 POLICIES = [("pure bf16 (model.to(bf16))", dict(fp32_stream=False)),
             ("policy, attention bf16 operands", dict(attention="bf16")),
             ("policy, attention fp16 operands (default)", dict(attention="fp16")),
+            ("policy, skip blocks fp16", dict(attention="fp16", skip_blocks="fp16")),
+            ("policy, skip blocks bf16", dict(attention="fp16", skip_blocks="bf16")),
             ("policy, attention fp32 CUDA cores", dict(attention="fp32"))]
 
 with torch.no_grad():

@@ -20,13 +20,15 @@ ap.add_argument("--out", default="gpurun_out/profile_forward.txt")
 ap.add_argument("--rows", type=int, default=45)
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--warm", type=int, default=3)
+ap.add_argument("--skip-blocks", default="tf32")
 ap.add_argument("--no-profiler", action="store_true", help="plain timed forwards only (the command ncu wraps)")
 args = ap.parse_args()
 dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
 torch.manual_seed(0)
 from waveformer_b200 import prepare_inference  # noqa: E402
 m = prepare_inference(Waveformer(img_size=(128,) * 3, patch_size=2, in_chans=4, out_chans=4, depths=[2] * 4,
-                                 feat_size=[48, 96, 192, 384], num_heads=[3, 6, 12, 24], drop_path_rate=0.1).eval().cuda(), dtype)
+                                 feat_size=[48, 96, 192, 384], num_heads=[3, 6, 12, 24], drop_path_rate=0.1).eval().cuda(), dtype,
+                      **({"skip_blocks": args.skip_blocks} if dtype == torch.bfloat16 else {}))
 x = torch.randn(args.batch, 4, 128, 128, 128, device="cuda").contiguous(memory_format=torch.channels_last_3d)  # fp32 window, as the inferer gathers it
 with torch.no_grad():
     for _ in range(args.warm):

@@ -26,7 +26,7 @@ def test_depthwise_conv_matches_torch(shape, dtype, tol):
 
 
 @pytest.mark.parametrize("shape", [(2, 48, 16, 16, 16), (1, 96, 6, 10, 4), (2, 20, 4, 4, 4), (1, 384, 8, 8, 8)])
-@pytest.mark.parametrize("dtype,tol", [(torch.float32, 5e-6), (torch.bfloat16, 8e-3)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 5e-6), (torch.bfloat16, 8e-3), (torch.float16, 1e-3)])
 @pytest.mark.parametrize("channels_last", [True, False])
 def test_instance_norm_act_matches_torch(shape, dtype, tol, channels_last):
     from waveformer_b200 import ops
@@ -46,6 +46,18 @@ def test_instance_norm_act_matches_torch(shape, dtype, tol, channels_last):
         got = ops.instance_norm_act(xc, **kw)
         assert got.shape == x.shape and got.dtype == dtype
         assert max_rel(got.float().cpu(), want) < tol, kw
+
+
+def test_instance_norm_fp16_block_writes_bf16_slice():
+    """fp16 skip block (precision policy): fp16 input + fp16 identity shortcut, bf16 result into a concat slice."""
+    from waveformer_b200 import ops
+    x = seeded_randn((2, 48, 8, 8, 8), 54).half().cuda().contiguous(memory_format=torch.channels_last_3d)
+    r = seeded_randn((2, 48, 8, 8, 8), 55).half().cuda().contiguous(memory_format=torch.channels_last_3d)
+    buf = torch.zeros((2, 8, 8, 8, 96), device="cuda", dtype=torch.bfloat16)
+    y = ops.instance_norm_act(x, "leakyrelu", 0.01, res=r, out=buf[..., 48:])
+    want = F.leaky_relu(F.instance_norm(x.float().cpu()) + r.float().cpu(), 0.01)
+    assert y.dtype == torch.bfloat16 and max_rel(y.float().cpu(), want) < 8e-3
+    assert bool((buf[..., :48] == 0).all())
 
 
 def test_instance_norm_large_offset_is_stable():
@@ -251,3 +263,24 @@ def test_conv3d_k3_c48_producer_consumer_kernel(shape, fused_input_norm):
     got = st.reshape(-1, 2)
     assert float((got[:, 0] - mean).abs().max()) < 2e-5 * max(1.0, float(mean.abs().max()))
     assert max_rel(got[:, 1].cpu(), rstd.cpu()) < 1e-4
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 12, 16, 48), (1, 4, 4, 8, 96), (1, 4, 4, 4, 192), (2, 2, 6, 4, 16)])
+@pytest.mark.parametrize("out_dtype,tol", [(torch.float32, 5e-6), (torch.bfloat16, 8e-3)])
+@pytest.mark.parametrize("v2", [False, True])
+def test_patch_merge_gather_layernorm_fused(shape, out_dtype, tol, v2):
+    """Octant gather + LayerNorm(8C) in one kernel vs torch.cat + F.layer_norm, for MONAI 0.9's order (two octants
+    repeated, reference wave_helper.py:170-194) and the itertools.product order of PatchMergingV2."""
+    import itertools
+    from waveformer_b200 import ops
+    monai09 = ((0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (0, 1, 0), (0, 0, 1), (1, 1, 1))
+    octs = tuple(itertools.product(range(2), range(2), range(2))) if v2 else monai09
+    x = seeded_randn(shape, 140) * 2 + 0.5
+    c8 = 8 * shape[-1]
+    gam, bet = 1 + 0.1 * seeded_randn((c8,), 141), 0.1 * seeded_randn((c8,), 142)
+    cat = torch.cat([x[:, i::2, j::2, k::2, :] for i, j, k in octs], -1)
+    want = F.layer_norm(cat, (c8,), gam, bet, 1e-5)
+    got = ops.patch_merge_layer_norm(x.cuda(), gam.cuda(), bet.cuda(), 1e-5, octs, out_dtype)
+    assert got is not None and got.dtype == out_dtype and tuple(got.shape) == tuple(want.shape)
+    assert max_rel(got.float().cpu(), want) < tol
+    assert ops.patch_merge_layer_norm(x[:, :, :, :-1].contiguous().cuda(), gam.cuda(), bet.cuda(), 1e-5, octs, out_dtype) is None

@@ -447,6 +447,8 @@ extern "C" int wf_instnorm_stats_ndhwc(const void *x, double *sums, float *mean_
     if (dtype == WF_F32) return wf::stats_launch<float>((const float *)x, sums, mean_rstd, B, S, C, x_vox_stride, eps, st);
     if (dtype == WF_BF16)
         return wf::stats_launch<__nv_bfloat16>((const __nv_bfloat16 *)x, sums, mean_rstd, B, S, C, x_vox_stride, eps, st);
+    if (dtype == WF_F16)
+        return wf::stats_launch<__half>((const __half *)x, sums, mean_rstd, B, S, C, x_vox_stride, eps, st);
     return WF_ERR_BAD_DTYPE;
 }
 
@@ -468,6 +470,12 @@ extern "C" int wf_instnorm_apply_ndhwc(const void *x, const float *mean_rstd, co
     if (dtype == WF_BF16 && y_dtype == WF_BF16)
         return wf::apply_launch<bf, bf>((const bf *)x, mean_rstd, (const bf *)res, res_mean_rstd, (bf *)y, B, S, C, x_vox_stride,
                                         res_vox_stride, y_vox_stride, act, slope, gamma, beta, st);
+    if (dtype == WF_F16 && y_dtype == WF_F16)    // fp16 skip block, intermediate activation
+        return wf::apply_launch<__half, __half>((const __half *)x, mean_rstd, (const __half *)res, res_mean_rstd, (__half *)y, B,
+                                                S, C, x_vox_stride, res_vox_stride, y_vox_stride, act, slope, gamma, beta, st);
+    if (dtype == WF_F16 && y_dtype == WF_BF16)   // fp16 skip block writing its bf16 concat slice
+        return wf::apply_launch<__half, bf>((const __half *)x, mean_rstd, (const __half *)res, res_mean_rstd, (bf *)y, B, S, C,
+                                            x_vox_stride, res_vox_stride, y_vox_stride, act, slope, gamma, beta, st);
     return WF_ERR_BAD_DTYPE;
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -70,6 +71,29 @@ template <> struct Pack<__nv_bfloat16> {
     }
 };
 
+template <> struct Pack<__half> {   // fp16 activations of the skip blocks (precision policy: 10-bit mantissa at bf16 cost)
+    static constexpr int VEC = 8;
+    using raw = uint4;
+    __device__ static inline void unpack(const raw &r, float (&v)[8]) {
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&w[i]));
+            v[2 * i] = f.x;
+            v[2 * i + 1] = f.y;
+        }
+    }
+    __device__ static inline raw pack(const float (&v)[8]) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t *>(&h);
+        }
+        return make_uint4(w[0], w[1], w[2], w[3]);
+    }
+};
+
 // streaming (evict-first) 16-byte global accesses: every byte of the Haar kernels is touched exactly once
 template <typename R> __device__ inline R ld_stream(const void *p) { return __ldcs(reinterpret_cast<const R *>(p)); }
 template <typename R> __device__ inline void st_stream(void *p, const R &v) { __stcs(reinterpret_cast<R *>(p), v); }
@@ -77,7 +101,9 @@ template <typename R> __device__ inline void st_stream(void *p, const R &v) { __
 template <typename T> __device__ inline float to_f32(T v);
 template <> __device__ inline float to_f32<float>(float v) { return v; }
 template <> __device__ inline float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ inline float to_f32<__half>(__half v) { return __half2float(v); }
 template <typename T> __device__ inline T from_f32(float v);
+template <> __device__ inline __half from_f32<__half>(float v) { return __float2half_rn(v); }
 template <> __device__ inline float from_f32<float>(float v) { return v; }
 template <> __device__ inline __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 

@@ -169,6 +169,13 @@ class UnetrBasicBlock(nn.Module):
                 inp = inp.to(w.dtype)
             with torch.backends.cudnn.flags(enabled=True, benchmark=torch.backends.cudnn.benchmark, allow_tf32=True):
                 return self.layer(inp) if out_buf is None else self.layer(inp, out_buf)
+        sd = getattr(self, "skip_dtype", None)
+        if sd is not None and use_fused(inp):
+            # precision policy, fp16 variant: fp16 storage / operands (10-bit mantissa like TF32) at the cost of the bf16 path
+            if inp.dtype != sd:
+                inp = inp.to(sd)
+            y = self.layer(inp) if out_buf is None else self.layer(inp, out_buf)
+            return y if out_buf is not None or y.dtype == torch.bfloat16 else y.to(torch.bfloat16)
         return self.layer(inp) if out_buf is None else self.layer(inp, out_buf)
 
 

@@ -220,14 +220,18 @@ class PatchMergingV2(nn.Module):
         raise ValueError(f"expecting 4D or 5D x, got {x.shape}.")
 
     def _merge(self, x):
-        g = self._gather(x)
         if fused_path(x):
             cd = getattr(self, "compute_dtype", None) or x.dtype
-            n = _ln(self.norm, g, out_dtype=cd)
+            n = None
+            if x.dim() == 5 and isinstance(self.norm, nn.LayerNorm):
+                # octant gather + LayerNorm in one kernel: the [.., 8C] concatenation is never stored
+                n = ops.patch_merge_layer_norm(x, self.norm.weight, self.norm.bias, self.norm.eps, self._octants, cd)
+            if n is None:
+                n = _ln(self.norm, self._gather(x), out_dtype=cd)
             if x.dtype == torch.float32 and cd != torch.float32:
                 return _linear_f32_out(n, ops.cast_cached(self.reduction.weight, cd))   # fp32 stream stays unrounded
             return F.linear(n, ops.cast_cached(self.reduction.weight, cd))
-        return self.reduction(self.norm(g))
+        return self.reduction(self.norm(self._gather(x)))
 
     def forward(self, x):
         return self._merge(x)

@@ -23,11 +23,13 @@ def _count(n: int = 1) -> None:
     LAUNCHES += n
 
 
-def _dtype_code(t: torch.Tensor) -> int:
+def _dtype_code(t: torch.Tensor, allow_f16: bool = False) -> int:
     if t.dtype == torch.float32:
         return 0
     if t.dtype == torch.bfloat16:
         return 1
+    if allow_f16 and t.dtype == torch.float16:      # InstanceNorm kernels only (fp16 skip blocks of the precision policy)
+        return 2
     # same convention as ptwt, which raises ValueError for dtypes it does not support
     raise ValueError(f"waveformer_b200: dtype {t.dtype} not supported (float32 or bfloat16)")
 
@@ -469,7 +471,7 @@ def _instnorm_stats(v: torch.Tensor, vs: int, eps: float) -> torch.Tensor:
     sums = torch.empty(B * C * 2, dtype=torch.float64, device=dev)
     mr = torch.empty(B * C * 2, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        st = _lib.lib().wf_instnorm_stats_ndhwc(v.data_ptr(), sums.data_ptr(), mr.data_ptr(), _dtype_code(v), B,
+        st = _lib.lib().wf_instnorm_stats_ndhwc(v.data_ptr(), sums.data_ptr(), mr.data_ptr(), _dtype_code(v, True), B,
                                                 D * H * W, C, vs, float(eps), _stream(dev))
     _lib.check(st, "wf_instnorm_stats_ndhwc")
     _count(2)
@@ -505,13 +507,13 @@ def instance_norm_act(x: torch.Tensor, act: str = "none", slope: float = 0.01, r
     if out is None:
         out = torch.empty((B, D, H, W, C), dtype=x.dtype, device=dev)
     ys = _voxel_stride(out)
-    if ys is None or tuple(out.shape) != (B, D, H, W, C) or not (out.dtype == x.dtype or
-                                                                  (x.dtype == torch.float32 and out.dtype == torch.bfloat16)):
-        raise ValueError("out must be a voxel-dense [B, D, H, W, C] tensor of x's dtype (or bf16 for fp32 x)")
+    if ys is None or tuple(out.shape) != (B, D, H, W, C) or not (
+            out.dtype == x.dtype or (x.dtype in (torch.float32, torch.float16) and out.dtype == torch.bfloat16)):
+        raise ValueError("out must be a voxel-dense [B, D, H, W, C] tensor of x's dtype (or bf16 for fp32 / fp16 x)")
     with torch.cuda.device(dev):
         st = _lib.lib().wf_instnorm_apply_ndhwc(v.data_ptr(), mr.data_ptr(), _ptr(rv), _ptr(rmr), _ptr(gamma), _ptr(beta),
-                                                out.data_ptr(), _ACT[act], float(slope), _dtype_code(x), _dtype_code(out),
-                                                B, D * H * W, C, vs, rs, ys, _stream(dev))
+                                                out.data_ptr(), _ACT[act], float(slope), _dtype_code(x, True),
+                                                _dtype_code(out, True), B, D * H * W, C, vs, rs, ys, _stream(dev))
     _lib.check(st, "wf_instnorm_apply_ndhwc")
     _count()
     return out.permute(0, 4, 1, 2, 3)
@@ -750,6 +752,29 @@ def residual_sum(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, bias: Option
     _lib.check(st, "wf_residual_sum")
     _count()
     return out
+
+
+def patch_merge_layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, octants,
+                           out_dtype: torch.dtype) -> Optional[torch.Tensor]:
+    """Octant gather + LayerNorm over the 8C concatenation in one kernel: ``x[B, D, H, W, C]`` fp32 ->
+    ``[B, D/2, H/2, W/2, 8C]``.  Returns None when the geometry is outside the kernel (the caller keeps torch.cat + LN)."""
+    if (x.dtype != torch.float32 or not x.is_contiguous() or x.dim() != 5 or out_dtype not in (torch.float32, torch.bfloat16)
+            or gamma is None or beta is None or gamma.dtype != torch.float32 or beta.dtype != torch.float32):
+        return None
+    B, D, H, W, C = x.shape
+    if (D | H | W) & 1 or C % 16 or C > 192 or (8 * C // 128) not in (1, 2, 3, 4, 6, 8, 12) or len(octants) != 8:
+        return None
+    dev = _need_cuda(x, gamma, beta)
+    code = 0
+    for s, (i, j, k) in enumerate(octants):
+        code |= ((i << 2) | (j << 1) | k) << (3 * s)
+    y = torch.empty((B, D // 2, H // 2, W // 2, 8 * C), dtype=out_dtype, device=dev)
+    with torch.cuda.device(dev):
+        st = _lib.lib().wf_patch_merge_layernorm(x.data_ptr(), gamma.contiguous().data_ptr(), beta.contiguous().data_ptr(),
+                                                 y.data_ptr(), _dtype_code(y), B, D, H, W, C, code, float(eps), _stream(dev))
+    _lib.check(st, "wf_patch_merge_layernorm")
+    _count()
+    return y
 
 
 def upsample_trilinear_add(srcs, size, base: Optional[torch.Tensor] = None, align_corners: bool = False,

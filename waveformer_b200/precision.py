@@ -11,8 +11,10 @@ unit-gain test weights - at higher precision, none of which costs measurable tim
   the raw image to bf16 alone costs 4e-2 max-relative logit error;
 * window attention uses fp16 tensor-core operands (same tcgen05 rate as bf16, 10-bit mantissa) with fp32 accumulation and
   an fp32 result: with bf16 operands attention alone costs 7e-2, with fp16 9e-3;
-* the three skip blocks encoder2..4 (residual blocks with an identity shortcut on the stage outputs) run fp32 storage /
-  TF32 tensor-core convolutions: together they are half of the remaining logit error and 5 % of the step;
+* the three skip blocks encoder2..4 (residual blocks with an identity shortcut on the stage outputs) run in fp16 storage
+  with fp16 tensor-core convolutions (InstanceNorm'd activations are O(1): no range problem; 10-bit mantissa like TF32,
+  at the cost of the bf16 kernels): in bf16 they are half of the remaining logit error.  ``skip_blocks="tf32"`` keeps
+  them in fp32 storage with TF32 convolutions instead (same error, +0.4 ms per batch-2 forward);
 * everything else (CCF_FFN GEMMs, the 128^3 conv blocks, decoder, IDWT) has bf16 operands and bf16 storage, fp32
   accumulation, fp32 statistics in every normalisation.
 """
@@ -30,13 +32,15 @@ __all__ = ["prepare_inference"]
 
 
 def prepare_inference(model: nn.Module, dtype: torch.dtype = torch.bfloat16, *, attention: str = "fp16",
-                      fp32_stream: bool = True) -> nn.Module:
+                      fp32_stream: bool = True, skip_blocks: str = "fp16") -> nn.Module:
     """Put ``model`` (a ``Waveformer``) into inference form on its current device.
 
     ``dtype=torch.float32``: nothing is rounded (parity mode, <= 1e-4 against the reference).
     ``dtype=torch.bfloat16``: the policy in the module docstring.  ``attention`` selects the operand format of the
     window-attention GEMMs ("fp16", "bf16" or "fp32" = CUDA-core kernels); ``fp32_stream=False`` gives the plain
-    all-bf16 model (``model.to(torch.bfloat16)``), kept for the precision study.
+    all-bf16 model (``model.to(torch.bfloat16)``), kept for the precision study.  ``skip_blocks`` is the format of the
+    residual blocks encoder2..4: "tf32" (fp32 storage, TF32 tensor-core convolutions), "fp16" (fp16 storage and operands:
+    the same 10-bit mantissa at the cost of the bf16 kernels) or "bf16" (no special treatment).
     """
     model.eval()
     if dtype == torch.float32:
@@ -50,10 +54,13 @@ def prepare_inference(model: nn.Module, dtype: torch.dtype = torch.bfloat16, *, 
         raise ValueError("prepare_inference supports float32 and bfloat16")
     if attention not in ("fp16", "bf16", "fp32"):
         raise ValueError("attention must be 'fp16', 'bf16' or 'fp32'")
+    if skip_blocks not in ("tf32", "fp16", "bf16"):
+        raise ValueError("skip_blocks must be 'tf32', 'fp16' or 'bf16'")
     if not fp32_stream:
         return model.to(torch.bfloat16).to(memory_format=torch.channels_last_3d)
     attn_dtype = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[attention]
     keep = set()                                       # parameters that stay fp32 (never rounded through bf16)
+    half = set()                                       # parameters stored as fp16 (skip blocks, skip_blocks="fp16")
 
     def keep_fp32(mod: nn.Module) -> None:
         for t in list(mod.parameters()) + list(mod.buffers()):
@@ -81,17 +88,26 @@ def prepare_inference(model: nn.Module, dtype: torch.dtype = torch.bfloat16, *, 
             # stage outputs 0..2 feed the fp32 skip blocks below, the last one the bf16 bottleneck
             m.out_dtype = [torch.float32, torch.float32, torch.float32, torch.bfloat16]
     # The residual blocks that turn the encoder's stage outputs into the decoder's skip connections (encoder2..4: identity
-    # shortcut, 48 / 96 / 192 channels at 64^3 / 32^3 / 16^3, 5 % of the step) stay fp32 with TF32 tensor-core
-    # convolutions: rounding their input and activations to bf16 alone accounts for half of the bf16 logit error
-    # (scripts/precision_zones.py: max-rel 1.7e-2 -> 0.9e-2 with these blocks lifted), because their identity shortcut
-    # carries the stage output straight into every decoder level.  Their last kernel writes the bf16 concat slice.
+    # shortcut, 48 / 96 / 192 channels at 64^3 / 32^3 / 16^3, 5 % of the step) keep a 10-bit mantissa: rounding their input
+    # and activations to bf16 alone accounts for half of the bf16 logit error (scripts/precision_zones.py: max-rel 1.7e-2
+    # -> 0.9e-2 with these blocks lifted), because their identity shortcut carries the stage output straight into every
+    # decoder level.  fp16 storage + fp16 tensor-core convolutions (default) or fp32 storage + TF32 convolutions measure
+    # the same error (0.97e-2 vs 1.02e-2); fp16 runs at the bf16 kernels' speed.  Their last kernel writes the bf16 concat slice.
     for name in ("encoder2", "encoder3", "encoder4"):
         blk = getattr(model, name, None)
-        if blk is not None:
+        if blk is None:
+            continue
+        if skip_blocks == "bf16":
+            blk.skip_dtype = torch.bfloat16             # only the fp32 stage output is cast on the way in
+        elif skip_blocks == "tf32":
             keep_fp32(blk)
             blk.tf32 = True
+        else:
+            for t in list(blk.parameters()) + list(blk.buffers()):
+                half.add(id(t))
+            blk.skip_dtype = torch.float16
     model.logits_dtype = torch.float32                  # the fused output head stores its fp32 accumulators
     for t in list(model.parameters()) + list(model.buffers()):
         if t.is_floating_point():
-            t.data = t.data.float() if id(t) in keep else t.data.to(torch.bfloat16)
+            t.data = t.data.float() if id(t) in keep else t.data.to(torch.float16 if id(t) in half else torch.bfloat16)
     return model.to(memory_format=torch.channels_last_3d)
