@@ -192,6 +192,13 @@ int wf_layernorm_ndhwc(const void *x, const float *gamma, const float *beta, voi
 int wf_residual_sum(const float *a, const float *b, const void *c, int c_dtype, const float *bias, float *out, int64_t rows,
                     int C, void *stream);
 
+/* GroupNorm(num_groups = C) + 1x1x1 convolution folded into one per-sample linear map (ProjectionUpsample.norm -> conv2,
+ * reference network_models/wave_helper.py:59-60,74-75): with (mean, rstd) = mean_rstd[b][c] of the normalised tensor,
+ * a = rstd * gamma, d = beta - mean * a:  w_folded[b][n][c] = w[n][c] * a[b][c],  b_folded[b][n] = bias[n] + sum_c w[n][c] d[b][c].
+ * w [N, C] and bias [N] (or NULL) in w_dtype, outputs in out_dtype (same, or WF_BF16 from WF_F32); gamma / beta fp32 or NULL. */
+int wf_groupnorm_fold_linear(const float *mean_rstd, const float *gamma, const float *beta, const void *w, const void *bias,
+                             void *w_folded, void *b_folded, int w_dtype, int out_dtype, int B, int C, int N, void *stream);
+
 /* x = GELU(x) (exact erf form) in place on n elements (n % 8 == 0 for bf16, % 4 for fp32): the activation between the
  * 1x1x1 convolutions of ProjectionUpsample (reference network_models/wave_helper.py:47-63). */
 int wf_gelu_inplace(void *x, int dtype, int64_t n, void *stream);

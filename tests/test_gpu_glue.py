@@ -284,3 +284,43 @@ def test_patch_merge_gather_layernorm_fused(shape, out_dtype, tol, v2):
     assert got is not None and got.dtype == out_dtype and tuple(got.shape) == tuple(want.shape)
     assert max_rel(got.float().cpu(), want) < tol
     assert ops.patch_merge_layer_norm(x[:, :, :, :-1].contiguous().cuda(), gam.cuda(), bet.cuda(), 1e-5, octs, out_dtype) is None
+
+
+@pytest.mark.parametrize("cin,cout,stride,double", [(96, 48, 2, False), (192, 48, 4, True), (16, 8, 2, False)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 1.5e-2)])
+def test_projection_upsample_fused_matches_module_math(cin, cout, stride, double, dtype, tol):
+    """ProjectionUpsample inference path (cell upsample, depthwise stencil, GroupNorm folded into conv2 by
+    wf_groupnorm_fold_linear, GELU kernel, last conv + residual projection accumulated into a concat slice) vs the
+    module's own torch ops (= the reference's wave_helper.py:33-81) in fp64 on the host."""
+    from waveformer_b200.network_models.wave_helper import ProjectionUpsample
+    torch.manual_seed(5)
+    m = ProjectionUpsample(cin, cout, stride=stride, residual=True, use_double_conv=double).eval()
+    with torch.no_grad():
+        m.norm.weight.copy_(1 + 0.2 * seeded_randn((cin,), 150))
+        m.norm.bias.copy_(0.2 * seeded_randn((cin,), 151))
+    x = seeded_randn((2, cin, 4, 4, 4), 152)
+    with torch.no_grad():
+        want = m.double()(x.double()).float()
+    m = m.float().cuda()
+    if dtype == torch.bfloat16:
+        keep = {id(p) for p in list(m.norm.parameters()) + list(m.conv1[1].parameters())}
+        for p in m.parameters():
+            if id(p) not in keep:
+                p.data = p.data.bfloat16()
+    xc = x.cuda().to(dtype).contiguous(memory_format=torch.channels_last_3d)
+    buf = torch.zeros((2,) + tuple(want.shape[2:]) + (cout + 8,), device="cuda", dtype=dtype)
+    with torch.no_grad():
+        got = m(xc, out_buf=buf[..., 8:])
+    assert tuple(got.shape) == tuple(want.shape)
+    assert max_rel(got.float().cpu(), want) < tol
+    assert bool((buf[..., :8] == 0).all())
+    gamma, beta = m.norm.weight, m.norm.bias
+    mr = torch.stack([seeded_randn((2 * cin,), 153), seeded_randn((2 * cin,), 154).abs() + 0.5], -1).reshape(-1).cuda()
+    from waveformer_b200 import ops
+    w = seeded_randn((2 * cin, cin), 155).cuda()
+    b = seeded_randn((2 * cin,), 156).cuda()
+    wf_, bf_ = ops.groupnorm_fold_linear(mr, gamma, beta, w, b, 2, torch.float32)
+    a = mr.view(2, cin, 2)[..., 1] * gamma
+    d = beta - mr.view(2, cin, 2)[..., 0] * a
+    assert max_rel(wf_.cpu(), (w[None] * a[:, None, :]).cpu()) < 1e-6
+    assert max_rel(bf_.cpu(), (b[None] + d @ w.t()).cpu()) < 1e-5

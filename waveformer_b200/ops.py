@@ -754,6 +754,24 @@ def residual_sum(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, bias: Option
     return out
 
 
+def groupnorm_fold_linear(mean_rstd: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor],
+                          weight: torch.Tensor, bias: Optional[torch.Tensor], batch: int, out_dtype: torch.dtype):
+    """GroupNorm(groups = C) followed by a linear map ``weight[N, C]``, folded per sample: returns ``(W'[B, N, C], b'[B, N])``
+    in ``out_dtype`` with ``W' x + b' == weight @ GroupNorm(x) + bias`` for the statistics ``mean_rstd[B * C * 2]``."""
+    dev = _need_cuda(mean_rstd, gamma, beta, weight, bias)
+    N, C = weight.shape
+    weight = weight.contiguous()
+    wf_ = torch.empty((batch, N, C), dtype=out_dtype, device=dev)
+    bf_ = torch.empty((batch, N), dtype=out_dtype, device=dev)
+    with torch.cuda.device(dev):
+        st = _lib.lib().wf_groupnorm_fold_linear(mean_rstd.data_ptr(), _ptr(gamma), _ptr(beta), weight.data_ptr(), _ptr(bias),
+                                                 wf_.data_ptr(), bf_.data_ptr(), _dtype_code(weight), _dtype_code(wf_),
+                                                 batch, C, N, _stream(dev))
+    _lib.check(st, "wf_groupnorm_fold_linear")
+    _count()
+    return wf_, bf_
+
+
 def patch_merge_layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, octants,
                            out_dtype: torch.dtype) -> Optional[torch.Tensor]:
     """Octant gather + LayerNorm over the 8C concatenation in one kernel: ``x[B, D, H, W, C]`` fp32 ->
