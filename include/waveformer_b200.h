@@ -149,6 +149,13 @@ int wf_patch_merge_layernorm(const float *x, const float *gamma, const float *be
 int wf_dwconv3d_ndhwc(const void *x, const float *w27, const float *bias, void *y, int dtype, int B, int D, int H, int W,
                       int C, void *stream);
 
+/* The same convolution (bf16, C % 8 == 0, W >= 8) that also reduces the statistics of the normalisation that follows it
+ * (ProjectionUpsample.norm, reference network_models/wave_helper.py:59,74): mean_rstd receives fp32 [B][C][2] = (mean,
+ * 1/sqrt(var + eps)) of the ROUNDED result, sums is fp64 scratch [B][C][2].  Other geometries: WF_ERR_UNSUPPORTED (call
+ * wf_dwconv3d_ndhwc + wf_instnorm_stats_ndhwc). */
+int wf_dwconv3d_ndhwc_stats(const void *x, const float *w27, const float *bias, void *y, double *sums, float *mean_rstd,
+                            float eps, int dtype, int B, int D, int H, int W, int C, void *stream);
+
 /* Affine-free InstanceNorm3d statistics of x [B, S voxels, C] (voxel stride x_vox_stride): sums is scratch
  * (fp64 [B][C][2]), mean_rstd receives fp32 [B][C][2] = (mean, 1/sqrt(var + eps)), biased variance.
  * Replaces the statistics half of nn.InstanceNorm3d in MONAI UnetResBlock (monai/networks/blocks/dynunet_block.py:

@@ -324,3 +324,20 @@ def test_projection_upsample_fused_matches_module_math(cin, cout, stride, double
     d = beta - mr.view(2, cin, 2)[..., 0] * a
     assert max_rel(wf_.cpu(), (w[None] * a[:, None, :]).cpu()) < 1e-6
     assert max_rel(bf_.cpu(), (b[None] + d @ w.t()).cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 8, 16, 192), (1, 5, 7, 9, 48), (2, 4, 4, 8, 24)])
+def test_depthwise_conv_with_fused_statistics(shape):
+    """bf16 tile kernel with the following normalisation's statistics reduced in its epilogue: same output as the plain
+    kernel, (mean, rstd) equal to the separate statistics pass over that output (ragged tiles, partial channel groups)."""
+    from waveformer_b200 import ops
+    C = shape[-1]
+    x = (seeded_randn(shape, 160) + 0.3).bfloat16().cuda()
+    w = ops.repack_depthwise_weight((seeded_randn((C, 1, 3, 3, 3), 161) * 0.3).cuda())
+    b = (seeded_randn((C,), 162) * 0.1).cuda()
+    y, mr = ops.dwconv3d_channels_last_stats(x, w, b, 1e-5)
+    want_y = ops.dwconv3d_channels_last(x, w, b)
+    assert torch.equal(y, want_y)
+    want = ops.instance_norm_stats(want_y.permute(0, 4, 1, 2, 3), eps=1e-5)
+    assert max_rel(mr.view(-1, 2)[:, 0].cpu(), want.view(-1, 2)[:, 0].cpu()) < 1e-4
+    assert max_rel(mr.view(-1, 2)[:, 1].cpu(), want.view(-1, 2)[:, 1].cpu()) < 1e-4

@@ -34,6 +34,7 @@ SIGNATURES = {
     "wf_window_attn_bwd": (_I, [_VOIDP] * 8 + [_I64, _I, _I, _I, _I, _F, _VOIDP]),
     "wf_patch_merge_layernorm": (_I, [_VOIDP, _VOIDP, _VOIDP, _VOIDP, _I, _I, _I, _I, _I, _I, _c.c_uint32, _F, _VOIDP]),
     "wf_dwconv3d_ndhwc": (_I, [_VOIDP, _VOIDP, _VOIDP, _VOIDP, _I, _I, _I, _I, _I, _I, _VOIDP]),
+    "wf_dwconv3d_ndhwc_stats": (_I, [_VOIDP] * 6 + [_F, _I, _I, _I, _I, _I, _I, _VOIDP]),
     "wf_instnorm_stats_ndhwc": (_I, [_VOIDP, _VOIDP, _VOIDP, _I, _I, _I64, _I, _I64, _F, _VOIDP]),
     "wf_instnorm_apply_ndhwc": (_I, [_VOIDP] * 7 + [_I, _F, _I, _I, _I, _I64, _I, _I64, _I64, _I64, _VOIDP]),
     "wf_instnorm_apply_head_ndhwc": (_I, [_VOIDP] * 7 + [_I, _F, _I, _I, _I, _I64, _I, _I, _I64, _I64, _VOIDP]),

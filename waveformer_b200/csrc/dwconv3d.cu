@@ -132,12 +132,18 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
 
+// STATS: additionally reduce per-(sample, channel) sum / sum of squares of the ROUNDED outputs into `sums` (fp64 [B][C][2],
+// zeroed by the launcher) - the statistics of the GroupNorm / InstanceNorm that follows (ProjectionUpsample.norm), so the
+// separate statistics pass over the result disappears.
+template <bool STATS>
 __global__ void __launch_bounds__(256, 2) dwconv3d_bf16_tile_kernel(const __nv_bfloat16 *__restrict__ x,
                                                                     const float *__restrict__ w27,
                                                                     const float *__restrict__ bias,
                                                                     __nv_bfloat16 *__restrict__ y, int D, int H, int W,
-                                                                    int C, int tiles_x, int tiles_y, int tiles_z) {
+                                                                    int C, int tiles_x, int tiles_y, int tiles_z,
+                                                                    double *__restrict__ sums) {
     extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ float s_red[STATS ? 8 * 32 * 4 : 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int t = blockIdx.x;
     const int tx = t % tiles_x; t /= tiles_x;
@@ -195,6 +201,7 @@ __global__ void __launch_bounds__(256, 2) dwconv3d_bf16_tile_kernel(const __nv_b
     const int gz = z0 + zl, gy = y0 + 2 * yp;
     __nv_bfloat16 *yrow = y + ((((int64_t)b * D + gz) * H + gy) * W + x0) * C + c;
     const bool row0 = gz < D && gy < H && live_c, row1 = gz < D && gy + 1 < H && live_c;
+    float st_s0 = 0.f, st_s1 = 0.f, st_q0 = 0.f, st_q1 = 0.f;   // STATS: this lane's two channels over its outputs
 #pragma unroll
     for (int j = 0; j < kDwTX; ++j) {
 #pragma unroll
@@ -214,26 +221,58 @@ __global__ void __launch_bounds__(256, 2) dwconv3d_bf16_tile_kernel(const __nv_b
             if (row0) {
                 __nv_bfloat162 h = __floats2bfloat162_rn(a00, a01);
                 *reinterpret_cast<__nv_bfloat162 *>(yrow + (int64_t)j * C) = h;
+                if constexpr (STATS) {
+                    const float2 f = __bfloat1622float2(h);
+                    st_s0 += f.x; st_s1 += f.y; st_q0 = fmaf(f.x, f.x, st_q0); st_q1 = fmaf(f.y, f.y, st_q1);
+                }
             }
             if (row1) {
                 __nv_bfloat162 h = __floats2bfloat162_rn(a10, a11);
                 *reinterpret_cast<__nv_bfloat162 *>(yrow + ((int64_t)W + j) * C) = h;
+                if constexpr (STATS) {
+                    const float2 f = __bfloat1622float2(h);
+                    st_s0 += f.x; st_s1 += f.y; st_q0 = fmaf(f.x, f.x, st_q0); st_q1 = fmaf(f.y, f.y, st_q1);
+                }
             }
+        }
+    }
+    if constexpr (STATS) {
+        float *r = s_red + (warp * 32 + lane) * 4;
+        r[0] = st_s0; r[1] = st_s1; r[2] = st_q0; r[3] = st_q1;
+        __syncthreads();
+        if (tid < 2 * kDwCG) {              // thread = (channel of the group, sum | sum of squares)
+            const int ch = tid >> 1, which = tid & 1;
+            float a = 0.f;
+#pragma unroll
+            for (int wv = 0; wv < 8; ++wv) a += s_red[(wv * 32 + (ch >> 1)) * 4 + which * 2 + (ch & 1)];
+            if (c0 + ch < C) atomicAdd(sums + ((int64_t)b * C + c0 + ch) * 2 + which, (double)a);
         }
     }
 }
 
+__global__ void dwconv_stats_finalize_kernel(const double *__restrict__ sums, float *__restrict__ mr, int n, double inv_s,
+                                             double eps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double m = sums[2 * i] * inv_s;
+    double var = sums[2 * i + 1] * inv_s - m * m;
+    var = var < 0.0 ? 0.0 : var;
+    mr[2 * i] = (float)m;
+    mr[2 * i + 1] = (float)(1.0 / sqrt(var + eps));
+}
+
+template <bool STATS>
 static int dwconv_bf16_tile_launch(const __nv_bfloat16 *x, const float *w27, const float *bias, __nv_bfloat16 *y, int B,
-                                   int D, int H, int W, int C, cudaStream_t st) {
+                                   int D, int H, int W, int C, cudaStream_t st, double *sums = nullptr) {
     static unsigned long long attr_done = 0;   // per-device opt-in bits
     if (first_use_on_current_device(attr_done)) {
-        WF_CUDA_CHECK(cudaFuncSetAttribute(dwconv3d_bf16_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmem));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(dwconv3d_bf16_tile_kernel<STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmem));
     }
     const int tiles_x = (W + kDwTX - 1) / kDwTX, tiles_y = (H + kDwTY - 1) / kDwTY, tiles_z = (D + kDwTZ - 1) / kDwTZ;
     const int64_t tiles = (int64_t)B * tiles_x * tiles_y * tiles_z;
     if (tiles > 0x7fffffff) return WF_ERR_UNSUPPORTED;
     dim3 grid((unsigned)tiles, (unsigned)((C + kDwCG - 1) / kDwCG));
-    dwconv3d_bf16_tile_kernel<<<grid, 256, kDwSmem, st>>>(x, w27, bias, y, D, H, W, C, tiles_x, tiles_y, tiles_z);
+    dwconv3d_bf16_tile_kernel<STATS><<<grid, 256, kDwSmem, st>>>(x, w27, bias, y, D, H, W, C, tiles_x, tiles_y, tiles_z, sums);
     WF_LAUNCH_CHECK();
     return WF_OK;
 }
@@ -270,8 +309,26 @@ extern "C" int wf_dwconv3d_ndhwc(const void *x, const float *w27, const float *b
         const char *impl = getenv("WF_DWCONV_IMPL");
         const bool force_old = impl != nullptr && impl[0] == 'r';
         if (!force_old && C % 8 == 0 && W >= 8 && wf::aligned16(x) && wf::aligned16(w27) && (bias == nullptr || wf::aligned16(bias)))
-            return wf::dwconv_bf16_tile_launch((const __nv_bfloat16 *)x, w27, bias, (__nv_bfloat16 *)y, B, D, H, W, C, st);
+            return wf::dwconv_bf16_tile_launch<false>((const __nv_bfloat16 *)x, w27, bias, (__nv_bfloat16 *)y, B, D, H, W, C, st);
         return wf::dwconv_launch<__nv_bfloat16>((const __nv_bfloat16 *)x, w27, bias, (__nv_bfloat16 *)y, B, D, H, W, C, st);
     }
     return WF_ERR_BAD_DTYPE;
+}
+
+extern "C" int wf_dwconv3d_ndhwc_stats(const void *x, const float *w27, const float *bias, void *y, double *sums,
+                                       float *mean_rstd, float eps, int dtype, int B, int D, int H, int W, int C,
+                                       void *stream) {
+    if (!x || !w27 || !y || !sums || !mean_rstd) return WF_ERR_NULL_POINTER;
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || C <= 0) return WF_ERR_BAD_SHAPE;
+    if (dtype != WF_BF16) return WF_ERR_UNSUPPORTED;
+    if (C % 8 != 0 || W < 8) return WF_ERR_UNSUPPORTED;
+    if (!wf::aligned16(x) || !wf::aligned16(w27) || (bias != nullptr && !wf::aligned16(bias))) return WF_ERR_MISALIGNED;
+    cudaStream_t st = (cudaStream_t)stream;
+    WF_CUDA_CHECK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)B * C, st));
+    const int rc = wf::dwconv_bf16_tile_launch<true>((const __nv_bfloat16 *)x, w27, bias, (__nv_bfloat16 *)y, B, D, H, W, C, st, sums);
+    if (rc != WF_OK) return rc;
+    const int n = B * C;
+    wf::dwconv_stats_finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(sums, mean_rstd, n, 1.0 / ((double)D * H * W), (double)eps);
+    WF_LAUNCH_CHECK();
+    return WF_OK;
 }

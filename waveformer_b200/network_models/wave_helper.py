@@ -433,10 +433,10 @@ class ProjectionUpsample(nn.Module):
         B = xv.shape[0]
         size = tuple(int(v * self.stride) for v in x.shape[2:])
         up = ops.upsample_trilinear_add([xv], size, align_corners=True)      # shared by both branches
-        dw = ops.dwconv3d_channels_last(up, *self._packed_dwconv())
         # GroupNorm(num_groups = C) is a per-(sample, channel) affine map a * x + d of the depthwise result; it is folded
-        # into conv2 (W' = W diag(a), b' = b + W d) instead of being applied in a pass of its own
-        mr = ops.instance_norm_stats(dw.permute(0, 4, 1, 2, 3), eps=self.norm.eps)             # (mean, rstd) per (b, c)
+        # into conv2 (W' = W diag(a), b' = b + W d) instead of being applied in a pass of its own, and its statistics
+        # (mean, rstd per (b, c)) come out of the depthwise kernel's epilogue
+        dw, mr = ops.dwconv3d_channels_last_stats(up, *self._packed_dwconv(), eps=self.norm.eps)
         c_in, c_mid = dw.shape[-1], self.conv2.out_channels
         w2 = self.conv2.weight.view(c_mid, c_in)
         b2 = self.conv2.bias

@@ -446,6 +446,31 @@ def dwconv3d_channels_last(x: torch.Tensor, w27: torch.Tensor, bias: Optional[to
     return y
 
 
+def dwconv3d_channels_last_stats(x: torch.Tensor, w27: torch.Tensor, bias: Optional[torch.Tensor], eps: float):
+    """Depthwise conv + the (mean, rstd) of its result per (sample, channel) - one kernel when the bf16 tile kernel covers
+    the geometry, else the convolution followed by the statistics pass.  Returns ``(y, mean_rstd[B * C * 2])``."""
+    dev = _need_cuda(x, w27, bias)
+    if x.dim() != 5:
+        raise ValueError("expected [B, D, H, W, C]")
+    x = x.contiguous()
+    B, D, H, W, C = x.shape
+    if x.dtype == torch.bfloat16 and C % 8 == 0 and W >= 8 and w27.dtype == torch.float32 and tuple(w27.shape) == (27, C) \
+            and w27.is_contiguous():
+        y = torch.empty_like(x)
+        sums = torch.empty(B * C * 2, dtype=torch.float64, device=dev)
+        mr = torch.empty(B * C * 2, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            st = _lib.lib().wf_dwconv3d_ndhwc_stats(x.data_ptr(), w27.data_ptr(), _ptr(bias), y.data_ptr(), sums.data_ptr(),
+                                                    mr.data_ptr(), float(eps), _dtype_code(x), B, D, H, W, C, _stream(dev))
+        if st == 0:
+            _count(2)
+            return y, mr
+        if st != -7:        # WF_ERR_UNSUPPORTED falls through to the two-kernel form
+            _lib.check(st, "wf_dwconv3d_ndhwc_stats")
+    y = dwconv3d_channels_last(x, w27, bias)
+    return y, _instnorm_stats(y, C, eps)
+
+
 def repack_depthwise_weight(weight: torch.Tensor) -> torch.Tensor:
     """[C, 1, 3, 3, 3] conv weight -> fp32 [27, C] (tap-major) for ``dwconv3d_channels_last``."""
     c = weight.shape[0]
