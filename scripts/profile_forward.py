@@ -20,7 +20,7 @@ ap.add_argument("--out", default="gpurun_out/profile_forward.txt")
 ap.add_argument("--rows", type=int, default=45)
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--warm", type=int, default=3)
-ap.add_argument("--skip-blocks", default="tf32")
+ap.add_argument("--skip-blocks", default="fp16")
 ap.add_argument("--no-profiler", action="store_true", help="plain timed forwards only (the command ncu wraps)")
 args = ap.parse_args()
 dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
