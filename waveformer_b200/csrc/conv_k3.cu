@@ -31,12 +31,22 @@ constexpr int kK3C = 48;                       // channels in = channels out
 constexpr int kK3Chunks = kK3C / 8;            // 6 sixteen-byte K chunks per voxel
 constexpr int kK3Rows = 132;                   // image rows: 1 halo + 128 voxels + 1 halo + 2 pad
 constexpr int kK3RowImg = kK3Chunks * kK3Rows * 16;        // 12672 bytes per staged input row
-constexpr int kK3Ring = 5;
-constexpr int kK3Lag = 3;                       // rows of cp.async copies in flight per loader thread
+#ifndef WF_K3_RING
+#define WF_K3_RING 7
+#endif
+#ifndef WF_K3_LAG
+#define WF_K3_LAG 3
+#endif
+#ifndef WF_K3_SR
+#define WF_K3_SR 1
+#endif
+constexpr int kK3Ring = WF_K3_RING;           // staged input rows (measured: 7 slots / 1-row epilogue staging 645 us, 5 / 2 rows 686 us)
+constexpr int kK3Lag = WF_K3_LAG;                       // rows of cp.async copies in flight per loader thread
 constexpr int kK3WTile3 = 2 * 3 * kK3C * 16;               // one [144 = 3 dy x 48 out][16] weight tile: 4608 bytes
 constexpr int kK3WBytes = 27 * kK3WTile3;                  // 3 dz x 3 dx x 3 k-steps tiles = 124416
-constexpr int kK3StageBytes = 256 * (kK3C + 8) * 2;        // epilogue staging: 2 output rows at a time, 28672
-constexpr int kK3Smem = kK3WBytes + kK3Ring * kK3RowImg + kK3StageBytes;   // 203776
+constexpr int kK3StageRows = WF_K3_SR;                      // output rows per epilogue staging pass
+constexpr int kK3StageBytes = kK3StageRows * 128 * (kK3C + 8) * 2;   // 14336 per row
+constexpr int kK3Smem = kK3WBytes + kK3Ring * kK3RowImg + kK3StageBytes;   // 227456 with 7 slots
 
 __device__ __forceinline__ void cp_async16_k3(void *smem_dst, const void *gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
@@ -269,11 +279,11 @@ __global__ void __launch_bounds__(288, 1) conv3d_k3_c48_kernel(K3Args a) {
             if (b != acc_b) { flush(); acc_b = b; }
             mbar_wait(&bar_acc_full[buf], (nblk >> 1) & 1);
             tc_fence_after();
-            for (int half = 0; half < 2; ++half) {          // two output rows at a time through the staging tile
-                const int rows_here = min(2, a.H - (y0 + 2 * half));
+            for (int half = 0; half < 4 / kK3StageRows; ++half) {   // kK3StageRows output rows at a time through the staging tile
+                const int rows_here = min(kK3StageRows, a.H - (y0 + kK3StageRows * half));
                 if (rows_here <= 0) break;
                 for (int rr = 0; rr < rows_here; ++rr) {
-                    const uint32_t acc = tmem + lane_base + buf * 256 + (3 - (2 * half + rr)) * kK3C;   // descending row order
+                    const uint32_t acc = tmem + lane_base + buf * 256 + (3 - (kK3StageRows * half + rr)) * kK3C;   // descending row order
 #pragma unroll
                     for (int c = 0; c < kK3C; c += 16) {
                         uint32_t r[16];
@@ -289,11 +299,12 @@ __global__ void __launch_bounds__(288, 1) conv3d_k3_c48_kernel(K3Args a) {
                         dst[1] = hi;
                     }
                 }
-                if (half == 1 || a.H - (y0 + 2) <= 0) zero_and_release(buf);   // accumulators fully read
+                if (half == 4 / kK3StageRows - 1 || a.H - (y0 + kK3StageRows * (half + 1)) <= 0)
+                    zero_and_release(buf);                          // accumulators fully read
                 asm volatile("bar.sync 2, 128;" ::: "memory");      // staging complete (epilogue warps only)
-                // coalesced stores: rows y0 + 2*half (+1) are contiguous voxels in global memory
+                // coalesced stores: the rows of one pass are contiguous voxels in global memory
                 const int nvox = rows_here * 128;
-                const int64_t v0 = (((int64_t)b * a.D + z) * a.H + y0 + 2 * half) * W;
+                const int64_t v0 = (((int64_t)b * a.D + z) * a.H + y0 + kK3StageRows * half) * W;
                 for (int i = et; i < nvox * kK3Chunks; i += 128) {
                     const int vx = i / kK3Chunks, p = i - vx * kK3Chunks;
                     *reinterpret_cast<uint4 *>(a.y + (v0 + vx) * a.ys + p * 8) =
