@@ -353,6 +353,14 @@ def main():
             tr = json.load(f)
         roof["traffic"] = tr["dwt3d_ncdhw_bf16"]["dram_traffic_bytes"] + tr["idwt3d_ncdhw_bf16"]["dram_traffic_bytes"]
         roof["traffic_source"] = "profiles/r01_kernel_traffic.json (ncu --set full; the last ~50 MB of each launch's writes are still in L2)"
+    # the kernel that takes the largest share of the window forward (profiles/r01_launch_summary.txt): the 3^3 tensor-core
+    # convolution, two launches per forward (one with the fused input normalisation), tensor-pipe bound
+    dominant = None
+    if "conv3d_k3_c48_tc" in kernels:
+        dominant = dict(kernels["conv3d_k3_c48_tc"])
+        dominant["kernel"] = "conv3d_k3_c48_kernel on 2x48x128^3 (conv2 of encoder1 / decoder1)"
+        dominant["share_of_forward"] = "2 launches, ~15 % of the window forward's device time (ncu launch list)"
+        dominant["traffic"] = 770605000      # dram bytes per launch, profiles/r01_ncu_k3.json (algorithmic 805.3 MB)
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         sec = cpu_patch_seconds(1, 1)
@@ -362,7 +370,8 @@ def main():
     line = dict(metric="sliding_window_voxels_per_s", value=value, unit="voxels/s", n_gpus=world, steps=args.steps,
                 warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype=args.dtype, data="synthetic", config=workload_config(volumes, args.sw_batch), clocks=clocks, e2e=e2e,
-                gpu_launches=launches, roofline=roof, roofline_kernels=kernels, cpu_baseline=cpu)
+                gpu_launches=launches, roofline=roof, roofline_dominant_by_time=dominant, roofline_kernels=kernels,
+                cpu_baseline=cpu)
     print(json.dumps(line))
     if world > 1:
         dist.barrier()
