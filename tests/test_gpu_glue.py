@@ -237,12 +237,14 @@ def test_gelu_inplace_matches_torch(dtype, tol):
     assert got.dtype == dtype and max_rel(got.float().cpu(), want.cpu()) < tol
 
 
-@pytest.mark.parametrize("shape", [(1, 2, 4, 128), (2, 3, 6, 128), (1, 5, 9, 128)])
+@pytest.mark.parametrize("shape", [(1, 2, 4, 128), (2, 3, 6, 128), (1, 5, 9, 128), (2, 24, 40, 128), (2, 128, 128, 128)])
 @pytest.mark.parametrize("fused_input_norm", [False, True])
 def test_conv3d_k3_c48_producer_consumer_kernel(shape, fused_input_norm):
     """tcgen05 3^3 convolution 48 -> 48 on rows of 128 voxels (ring-staged input rows, shifted-descriptor dx taps, double-
     buffered TMEM accumulators): vs torch's convolution on the same bf16-rounded operands; fused InstanceNorm + LeakyReLU of
-    the input; fused output statistics; partial row blocks (H % 4 != 0) and volume borders in z / y / x."""
+    the input; fused output statistics; partial row blocks (H % 4 != 0) and volume borders in z / y / x.  The last two
+    shapes make every persistent CTA walk several / 56 row blocks (ring wrap-around, both TMEM accumulator buffers many
+    times over); the last one is BASELINE's full size."""
     from waveformer_b200 import ops
     B, D, H, W = shape
     x = (seeded_randn((B, 48, D, H, W), 160) * 1.3 + 0.2).cuda().bfloat16().contiguous(memory_format=torch.channels_last_3d)
