@@ -5,6 +5,8 @@ from __future__ import annotations
 from functools import partial
 from typing import Tuple, Union
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -111,6 +113,8 @@ class Waveformer(nn.Module):
             raise RuntimeError("waveformer_b200.Waveformer runs on CUDA (B200) only; there is no CPU fallback")
         dtype = self.out.conv.conv.weight.dtype          # activation type of the convolutional U-Net
         x_in = x_in.contiguous(memory_format=torch.channels_last_3d)
+        if use_fused(x_in) and os.environ.get("WF_FORK", "1") != "0":
+            return self._forward_forked(x_in, dtype)
         # the encoder reads the window in its patch embedding's own type (fp32 under prepare_inference's bf16 policy)
         outs, outs_hf = self.waveformer_encoder(x_in)
         if x_in.dtype != dtype:
@@ -128,10 +132,85 @@ class Waveformer(nn.Module):
         combined = torch.cat([self.learnable_up4(dec4), self.learnable_up3(dec3), dec2], dim=1)
         return self.out(self.decoder1(combined, enc0))
 
+    def _streams(self, dev):
+        st = getattr(self, "_side_streams", None)
+        if st is None or st[0].device != dev:
+            st = self._side_streams = tuple(torch.cuda.Stream(device=dev) for _ in range(3))
+        return st
+
+    def _forward_forked(self, x_in, dtype):
+        """Inference wiring as a fork / join graph over four streams (capturable; GraphedForward records the edges).
+
+        The convolutional blocks hang off the transformer encoder like branches: encoder1 needs only the raw window,
+        encoder2..4 / encoder10 need one stage output each, and behind the shared bottleneck dec5 the chains
+        [decoder4 -> learnable_up4], [decoder3 -> learnable_up3] and [decoder2] are independent (reference
+        network_backbone.py:380-407).  The encoder's 16^3 / 8^3 stages and the small decoder blocks launch kernels that fill
+        a fraction of the 148 SMs; run side by side with the large 128^3 / 64^3 kernels they disappear behind them
+        (-3 % of the step measured with the decoder chains forked alone).
+            s0: encoder1, encoder2                  (after the window / stage-1 output)
+            s1: encoder4, encoder10 -> dec5, decoder4, learnable_up4
+            s2: encoder3, decoder3, learnable_up3
+            current stream: transformer encoder, decoder2, join, decoder1 (+ fused head)
+        Buffers shared across streams are allocated on the current stream before the fork or marked with record_stream."""
+        f = self.feat_size
+        dev = x_in.device
+        cur = torch.cuda.current_stream(dev)
+        s0, s1, s2 = self._streams(dev)
+        xb = x_in if x_in.dtype == dtype else x_in.to(dtype)
+        b, _, d, h, w = x_in.shape
+        cat1 = torch.empty((b, d, h, w, 2 * f[0]), dtype=dtype, device=dev)
+        s0.wait_stream(cur)
+        with torch.cuda.stream(s0):
+            enc0 = self.encoder1(xb, cat1[..., f[0]:])
+        skips, cats = {}, {}
+        plan = {0: (self.encoder2, s0, f[0]), 1: (self.encoder3, s2, f[1]), 2: (self.encoder4, s1, f[2])}
+
+        def on_stage(i, out):          # called by the encoder on the current stream right after stage i's output exists
+            if i not in plan:
+                return
+            block, st, c = plan[i]
+            bb, _, dd, hh, ww = out.shape
+            cats[i] = torch.empty((bb, dd, hh, ww, 2 * c), dtype=dtype, device=dev)
+            st.wait_stream(cur)
+            out.record_stream(st)
+            with torch.cuda.stream(st):
+                skips[i] = block(out, cats[i][..., c:])
+
+        enc = self.waveformer_encoder
+        enc._stage_hook = on_stage
+        try:
+            outs, outs_hf = enc(x_in)
+        finally:
+            enc._stage_hook = None
+        bb, _, dd, hh, ww = outs[0].shape
+        comb = torch.empty((bb, dd, hh, ww, 3 * f[0]), dtype=dtype, device=dev)       # [up4 | up3 | dec2]
+        s1.wait_stream(cur)
+        outs[3].record_stream(s1)
+        with torch.cuda.stream(s1):
+            dec5 = self.encoder10(outs[3])
+            ready = s1.record_event()
+            dec4 = self.decoder4(dec5, skips[2], outs_hf[-1], cat_buf=cats[2])
+            self.learnable_up4(dec4, out_buf=comb[..., :f[0]])
+        s2.wait_stream(cur)
+        with torch.cuda.stream(s2):
+            s2.wait_event(ready)
+            dec5.record_stream(s2)
+            dec3 = self.decoder3(dec5, skips[1], outs_hf[-2], cat_buf=cats[1])
+            self.learnable_up3(dec3, out_buf=comb[..., f[0]:2 * f[0]])
+        cur.wait_stream(s0)
+        cur.wait_event(ready)
+        dec5.record_stream(cur)
+        self.decoder2(dec5, skips[0], outs_hf[-3], cat_buf=cats[0], out_buf=comb[..., 2 * f[0]:])
+        cur.wait_stream(s1)
+        cur.wait_stream(s2)
+        oc = self.out.conv.conv
+        head = (oc.weight, oc.bias, getattr(self, "logits_dtype", None) or dtype)
+        return self.decoder1(comb.permute(0, 4, 1, 2, 3), enc0, cat_buf=cat1, head=head)
+
     def _forward_fused(self, x_in, outs, outs_hf, dtype):
-        """Inference wiring: every concatenation buffer is allocated up front and its producers write their channel
-        slice directly (skip halves by the encoder blocks' last kernel, IDWT halves by the synthesis kernel, the three
-        inputs of decoder1 by their producers), so no torch.cat copy of a full activation remains."""
+        """Inference wiring on ONE stream (WF_FORK=0): every concatenation buffer is allocated up front and its producers
+        write their channel slice directly (skip halves by the encoder blocks' last kernel, IDWT halves by the synthesis
+        kernel, the three inputs of decoder1 by their producers), so no torch.cat copy of a full activation remains."""
         f = self.feat_size
         dev = x_in.device
 

@@ -104,6 +104,9 @@ class MultiscaleTransformer(nn.Module):
                 o = F.layer_norm(t, [t.shape[-1]]) if normalize else t
                 o = o if o.dtype == od else o.to(od)
             outs.append(o.permute(0, 4, 1, 2, 3))
+            hook = getattr(self, "_stage_hook", None)      # Waveformer's forked inference wiring starts the stage's skip
+            if hook is not None:                           # block on a side stream as soon as the output exists
+                hook(s, outs[-1])
             if s < 3:
                 outs_hf.append(hf if hf is not None else ())
                 t = getattr(self, f"downsample_{s + 1}")(t)
