@@ -185,13 +185,13 @@ int wf_instnorm_apply_head_ndhwc(const void *x, const float *mean_rstd, const vo
 
 /* y[r, :] = LayerNorm(x[r, :C]) * gamma + beta (gamma / beta fp32 [C] or NULL), optionally followed by GELU(erf).
  * Rows are voxels of a channels-last tensor (row strides in elements); input and output storage types are independent.
- * y2_bf16 (optional, dense [rows, C]) receives the same result rounded to bf16: the GEMM operand, while y keeps the fp32
- * copy that CCF_FFN's own residual adds back (wave_helper.py:293).
+ * y2 (optional, dense [rows, C], y2_dtype WF_BF16 or WF_F16) receives the same result rounded to 16 bits: the GEMM
+ * operand, while y keeps the fp32 copy that CCF_FFN's own residual adds back (wave_helper.py:293).
  * Replaces Block.norm1 / norm2 (reference network_models/wave_helper.py:477,509), CCF_FFN.norm1 / norm2 + act
  * (wave_helper.py:278,286), PatchMerging.norm (wave_helper.py:192) and proj_out (network_models/waveformer.py:193-204). */
-int wf_layernorm_ndhwc(const void *x, const float *gamma, const float *beta, void *y, void *y2_bf16, int in_dtype,
-                       int out_dtype, int64_t rows, int C, int64_t x_row_stride, int64_t y_row_stride, float eps, int gelu,
-                       void *stream);
+int wf_layernorm_ndhwc(const void *x, const float *gamma, const float *beta, void *y, void *y2, int y2_dtype, int in_dtype,
+                       int out_dtype, int64_t rows, int C, int64_t x_row_stride, int64_t y_row_stride, float eps,
+                       int gelu, void *stream);
 
 /* out = a + b + c + bias[channel]: the tail of a transformer block, x + LN(x) + ffn(LN(x)) (+ the fc bias) in ONE fp32 pass
  * (reference network_models/wave_helper.py:293 and :509).  a, b, out fp32 [rows, C]; c fp32 or bf16 [rows, C]; bias fp32 [C]
@@ -220,16 +220,17 @@ int wf_upsample_trilinear_add_ndhwc(const void *const *srcs, const int *src_dims
                                     int src_dtype, int io_dtype, int align_corners, int B, int D, int H, int W, int C,
                                     int64_t base_vox_stride, int64_t y_vox_stride, void *stream);
 
-/* 3x3x3 convolution (padding 1, no bias) of a 4-channel channels-last volume x [B, D, H, W, 4] (x_dtype WF_F32 or
- * WF_BF16; bf16 tensor-core operands, fp32 accumulation), fused with an optional 1x1x1 convolution of the same input and
- * with the InstanceNorm statistics of both bf16 results.  Replaces conv1 + norm1's statistics and conv3 + norm3's
+/* 3x3x3 convolution (padding 1, no bias) of a 4-channel channels-last volume x [B, D, H, W, 4] (op_dtype WF_BF16 or
+ * WF_F16 = format of the tensor-core operands, of wpack and of both results; x_dtype = WF_F32 - converted while gathered -
+ * or op_dtype; fp32 accumulation), fused with an optional 1x1x1 convolution of the same input and with the InstanceNorm
+ * statistics of both 16-bit results.  Replaces conv1 + norm1's statistics and conv3 + norm3's
  * statistics of the first residual block, Waveformer.encoder1 (reference network_models/network_backbone.py:247-255 ->
  * monai/networks/blocks/dynunet_block.py:98-111).
  * wpack: bf16 [n0 + n1][112], k = tap * 4 + channel with tap = (dz+1)*9 + (dy+1)*3 + (dx+1), zero padded to 112; rows
  *        >= n0 carry the 1x1x1 weights in the centre tap (k = 52..55).
  * y0 / y1: bf16 [B, D, H, W, n0 / n1] with voxel strides (channel slices of wider buffers allowed); n1 may be 0.
  * sums0 / sums1: fp64 scratch [B * n * 2]; mean_rstd0 / mean_rstd1: fp32 [B * n * 2] = (mean, 1/sqrt(var + eps)). */
-int wf_conv3d_c4_in_stats(const void *x, int x_dtype, const void *wpack, void *y0, int64_t y0_vox_stride, int n0,
+int wf_conv3d_c4_in_stats(const void *x, int x_dtype, int op_dtype, const void *wpack, void *y0, int64_t y0_vox_stride, int n0,
                           void *y1, int64_t y1_vox_stride, int n1, double *sums0, double *sums1, float *mean_rstd0,
                           float *mean_rstd1, float eps, int B, int D, int H, int W, void *stream);
 
@@ -240,13 +241,15 @@ int wf_conv3d_c4_in_stats(const void *x, int x_dtype, const void *wpack, void *y
  * statistics in the 128^3 residual blocks (reference monai/networks/blocks/dynunet_block.py:98-111, used by
  * Waveformer.encoder1 / decoder1, network_models/network_backbone.py:386,405).
  * wpack: bf16 [3 dz][3 dx][3 k-steps][2 chunks][144 = 3 dy x 48 out][8], element = w[out, 16 ks + 8 chunk + e, dz, dy, dx]
- * (the three dy taps of a (dz, dx, k-step) are adjacent along N so that one tcgen05.mma feeds up to three output rows).  sums: fp64 scratch [B * 48 * 2]; mean_rstd (out) / in_mean_rstd (in, optional): fp32
- * [B * 48 * 2] = (mean, 1/sqrt(var + eps)) pairs. */
-int wf_conv3d_k3_c48_in_stats(const void *x, const void *wpack, void *y, double *sums, float *mean_rstd,
+ * (the three dy taps of a (dz, dx, k-step) are adjacent along N so that one tcgen05.mma feeds up to three output rows).
+ * dtype: WF_BF16 or WF_F16 - the one 16-bit format of x, wpack and y.  sums: fp64 scratch [B * 48 * 2]; mean_rstd (out) /
+ * in_mean_rstd (in, optional): fp32 [B * 48 * 2] = (mean, 1/sqrt(var + eps)) pairs. */
+int wf_conv3d_k3_c48_in_stats(const void *x, int dtype, const void *wpack, void *y, double *sums, float *mean_rstd,
                               const float *in_mean_rstd, float slope, float eps, int B, int D, int H, int W,
                               int64_t x_vox_stride, int64_t y_vox_stride, void *stream);
 
-/* ConvTranspose3d(kernel 2, stride 2, no bias) on channels-last bf16 activations as one tensor-core GEMM whose epilogue
+/* ConvTranspose3d(kernel 2, stride 2, no bias) on channels-last 16-bit activations (dtype WF_BF16 or WF_F16: x, wpack
+ * and y share it) as one tensor-core GEMM whose epilogue
  * writes every output voxel in place, e.g. into channels [0, Cout) of a concatenation buffer (y_vox_stride = 2 * Cout).
  * Replaces UnetrUpBlock.transp_conv and the torch.cat that follows it (reference monai/networks/blocks/unetr_block.py:57-86,
  * Waveformer.decoder1, network_models/network_backbone.py:405).
@@ -261,27 +264,36 @@ int wf_convtranspose3d_k2s2_ndhwc(const void *x, const void *wpack, void *y, int
 
 /* Gather `nwin` windows (roi r0 x r1 x r2, starts in `starts` = int32 [nwin][4] = {batch index, z0, y0, x0}, device
  * memory) from vol [Bv, C, D, H, W] fp32 into win [nwin, C, r0, r1, r2] (dtype, NCDHW contiguous) or, when
- * channels_last != 0, [nwin, r0, r1, r2, C].  Replaces torch.cat([inputs[s] ...]) at inferers/utils.py:223. */
+ * channels_last != 0, [nwin, r0, r1, r2, C].  Replaces torch.cat([inputs[s] ...]) at inferers/utils.py:223.
+ * flip (bit 0 / 1 / 2 = mirror z / y / x): the window is cut from the MIRRORED volume V'(p) = V(flip(p)) without that
+ * copy ever being built - the mirror test-time augmentation of light_training/prediction.py:129-156
+ * (`torch.flip(x, dims)` in front of the inferer) as an index transform.  0 = plain gather. */
 int wf_sw_gather(const float *vol, void *win, const int32_t *starts, int nwin, int dtype, int channels_last, int C,
-                 int D, int H, int W, int r0, int r1, int r2, void *stream);
+                 int D, int H, int W, int r0, int r1, int r2, int flip, void *stream);
 
 /* acc[b, k, z0+z, y0+y, x0+x] += max(gz[z]*gy[y]*gx[x], floor) * seg[n, k, z, y, x] for every window n (atomic
  * adds: windows of one call may overlap).  seg: [nwin, K, r0, r1, r2] NCDHW or NDHWC (channels_last).  gz/gy/gx are
  * the 1-D gaussian factors of compute_importance_map (monai/data/utils.py:1121-1138).  Replaces
- * `seg *= w; out[slice] += seg` at inferers/utils.py:287-289 / :351-360. */
+ * `seg *= w; out[slice] += seg` at inferers/utils.py:287-289 / :351-360.
+ * flip != 0: `starts` are positions in the mirrored volume (see wf_sw_gather); the contribution lands at flip(p), i.e.
+ * the `torch.flip(..., dims)` of the stitched result at prediction.py:135-155 is part of the scatter. */
 int wf_sw_accumulate(const void *seg, float *acc, const int32_t *starts, const float *gz, const float *gy,
                      const float *gx, float floor_w, int nwin, int dtype, int channels_last, int K, int D, int H,
-                     int W, int r0, int r1, int r2, void *stream);
+                     int W, int r0, int r1, int r2, int flip, void *stream);
 
-/* acc[b, k, z, y, x] /= sum over every window w of `all_starts` (int32 [nall][4], the FULL window list of the
- * volume batch, not just this rank's) covering the voxel of max(gz*gy*gx, floor).  The count map is geometry only,
+/* acc[b, k, z, y, x] /= sum over every window w of `all_starts` (int32 [nall][4], the FULL window list, not just this
+ * rank's; an entry whose volume slot is < 0 applies to EVERY volume of the call - volumes of one call share their
+ * geometry, so nall is normally one volume's window count; nall <= 3072) covering the voxel of max(gz*gy*gx, floor).  The count map is geometry only,
  * so it is recomputed here instead of being stored and reduced (inferers/utils.py:265-276, :298-299).
  * labels (optional, uint8 [Bv, D, H, W]) receives argmax over k (4_predict.py:241).
  * Only planes z in [z_begin, z_end) of every volume are normalised, so a slab whose windows are all accumulated can be
- * finished (and copied to the host) while later windows still run; (0, D) = the whole volume. */
+ * finished (and copied to the host) while later windows still run; (0, D) = the whole volume.
+ * flip: the volume was stitched from a mirrored pass (its count map is the plain one read at flip(q)).
+ * dst (optional, same shape as acc): dst = (dst_add ? dst : 0) + dst_scale * normalised acc - the running mean over the
+ * 2^k mirrored passes of prediction.py:129-157 without a pass of its own. */
 int wf_sw_finalize(float *acc, uint8_t *labels, const int32_t *all_starts, int nall, const float *gz, const float *gy,
                    const float *gx, float floor_w, int Bv, int K, int D, int H, int W, int r0, int r1, int r2,
-                   int z_begin, int z_end, void *stream);
+                   int z_begin, int z_end, int flip, float *dst, float dst_scale, int dst_add, void *stream);
 
 #ifdef __cplusplus
 }

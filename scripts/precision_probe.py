@@ -46,11 +46,12 @@ def build(sd, **policy):
 
 
 POLICIES = [("pure bf16 (model.to(bf16))", dict(fp32_stream=False)),
-            ("policy, attention bf16 operands", dict(attention="bf16")),
-            ("policy, attention fp16 operands (default)", dict(attention="fp16")),
-            ("policy, skip blocks fp16", dict(attention="fp16", skip_blocks="fp16")),
-            ("policy, skip blocks bf16", dict(attention="fp16", skip_blocks="bf16")),
-            ("policy, attention fp32 CUDA cores", dict(attention="fp32"))]
+            ("r01 policy: bf16 storage, attn fp16", dict(storage="bf16")),
+            ("r02 policy: fp16 storage, attn fp16 (default)", dict()),
+            ("fp16 storage, attention fp32 CUDA cores", dict(attention="fp32")),
+            ("bf16 storage, attention fp32 CUDA cores", dict(storage="bf16", attention="fp32"))]
+if len(sys.argv) > 1:
+    POLICIES = [p for p in POLICIES if any(a in p[0] for a in sys.argv[1:])]
 
 with torch.no_grad():
     for name in ("unit-gain", "ctor-init"):

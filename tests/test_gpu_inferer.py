@@ -178,3 +178,64 @@ def test_streamed_host_io_equals_device_resident(shape, roi, ov, bs):
         assert float((inf.labels.cpu() != ref_inf.labels.cpu()).float().mean()) < 1e-4
     mid = SlidingWindowInferer(**kw)(x.pin_memory(), net)      # host in, device out
     assert mid.is_cuda and max_rel(mid.cpu(), want.cpu()) < 1e-6
+
+
+@pytest.mark.parametrize("axes", [(0,), (2,), (0, 1), (0, 1, 2)])
+def test_mirrored_pass_is_flip_infer_flip(axes):
+    """`inferer(x, net, flip=axes)` == flip(inferer(flip(x), net)) (one TTA pass of light_training/prediction.py:134-155)
+    although no mirrored copy of the input or of the result is built: gather / scatter / count map are index-mirrored."""
+    from waveformer_b200.inferers import SlidingWindowInferer
+    wconv = (seeded_randn((3, 2, 3, 3, 3), 601) * 0.2).cuda()
+    net = lambda p: torch.nn.functional.conv3d(p, wconv, padding=1)        # not flip-equivariant
+    x = seeded_randn((2, 2, 40, 24, 30), 91).cuda()
+    kw = dict(roi_size=(16, 16, 16), sw_batch_size=3, overlap=0.5, mode="gaussian", compute_dtype=torch.float32,
+              channels_last=False, return_labels=True)
+    dims = tuple(a + 2 for a in axes)
+    plain = SlidingWindowInferer(**kw)
+    want = torch.flip(plain(torch.flip(x, dims), net), dims)
+    want_labels = torch.flip(plain.labels, tuple(a + 1 for a in axes))
+    inf = SlidingWindowInferer(**kw)
+    got = inf(x, net, flip=axes)
+    assert max_rel(got.cpu(), want.cpu()) < 1e-6
+    assert float((inf.labels != want_labels).float().mean()) < 1e-4
+    # running mean folded into the normalisation kernel
+    mean = torch.full_like(want, 2.0)
+    inf(x, net, flip=axes, into=(mean, 0.25, True))
+    assert max_rel(mean.cpu(), (2.0 + 0.25 * want).cpu()) < 1e-6
+
+
+def test_host_output_is_fresh_unless_reuse_is_requested():
+    """MONAI returns a new tensor per call; the pinned result buffer is only recycled with reuse_output=True."""
+    from waveformer_b200.inferers import SlidingWindowInferer, sliding_window_inference
+    net = lambda p: p[:, :1] * 2.0
+    kw = dict(roi_size=(16, 16, 16), sw_batch_size=2, overlap=0.5, mode="gaussian", compute_dtype=torch.float32,
+              channels_last=False)
+    a_in, b_in = seeded_randn((1, 2, 24, 20, 18), 1).cuda(), seeded_randn((1, 2, 24, 20, 18), 2).cuda()
+    inf = SlidingWindowInferer(device="cpu", **kw)
+    a = inf(a_in, net)
+    keep = a.clone()
+    b = inf(b_in, net)
+    assert a.data_ptr() != b.data_ptr() and torch.equal(a, keep) and not torch.equal(a, b)
+    fa = sliding_window_inference(a_in, (16, 16, 16), 2, net, 0.5, "gaussian", device="cpu")
+    fb = sliding_window_inference(b_in, (16, 16, 16), 2, net, 0.5, "gaussian", device="cpu")
+    assert fa.data_ptr() != fb.data_ptr() and max_rel(fa, keep) < 1e-6
+    re = SlidingWindowInferer(device="cpu", reuse_output=True, **kw)
+    assert re(a_in, net).data_ptr() == re(b_in, net).data_ptr()
+    # the plan cache is bounded whatever the stream of crop shapes
+    for d in range(20, 34):
+        inf(seeded_randn((1, 2, d, 20, 18), d).cuda(), net)
+    assert len(inf._geom_cache) <= 8
+
+
+def test_many_volumes_in_one_call_share_one_window_table():
+    """wf_sw_finalize takes ONE volume's window list (slot -1) for all volumes of a call: 300 volumes x 8 windows used to
+    need a 2400-entry table per voxel and more than 48 KB of shared memory."""
+    from oracle import sliding_window as osw
+    from waveformer_b200.inferers import SlidingWindowInferer
+    net = lambda p: p * 0.5 + 1.0
+    x = seeded_randn((300, 1, 12, 12, 12), 5)
+    inf = SlidingWindowInferer(roi_size=(8, 8, 8), sw_batch_size=64, overlap=0.5, mode="gaussian",
+                               compute_dtype=torch.float32, channels_last=False)
+    got = inf(x.cuda(), net).cpu()
+    want = osw.sliding_window_inference(x, (8, 8, 8), 64, net, 0.5, "gaussian")
+    assert max_rel(got, want) < 1e-5

@@ -112,7 +112,24 @@ def test_shard_batches_cover_each_window_once(n, bs, world):
         sizes.append(len(mine))
         seen += mine
     assert sorted(seen) == list(range(n))
-    assert max(sizes) - min(sizes) <= bs
+    assert max(sizes) - min(sizes) <= 1               # window granularity: 18 windows on 8 ranks = 2 or 3 each
+
+
+@pytest.mark.parametrize("vols,nwin,world", [(1, 18, 8), (64, 18, 8), (8, 18, 4), (3, 8, 2), (5, 18, 3)])
+def test_interleaved_sharding_splits_every_volume_and_spreads_the_owners(vols, nwin, world):
+    from waveformer_b200.inferers import shard_windows, volume_owner, volume_plan
+    n = vols * nwin
+    seen = [i for r in range(world) for i in shard_windows(n, r, world, "interleaved")]
+    assert sorted(seen) == list(range(n))
+    touch = volume_plan(vols, nwin, 2, world, "interleaved")
+    assert all(t == list(range(min(world, nwin))) for t in touch)       # every rank holds a share of every volume
+    owners = [volume_owner(v, touch, "interleaved") for v in range(vols)]
+    counts = [owners.count(r) for r in range(world)]
+    assert max(counts) - min(counts) <= 1
+    # contiguous runs: whole volumes when the rank count divides the volume count -> nothing is shared
+    touch_c = volume_plan(vols, nwin, 2, world, "contiguous")
+    if vols % world == 0:
+        assert all(len(t) == 1 for t in touch_c)
 
 
 _WORKER = r'''
@@ -124,20 +141,21 @@ from helpers import seeded_randn
 
 # The CUDA stitching kernels cannot run here; stand-ins with the same contracts (built on the oracle's arithmetic)
 # let the test exercise the ORCHESTRATION: sharding, the single reduce, finalisation on rank 0.
-def sw_gather(vol, starts, roi, dtype, channels_last):
+def sw_gather(vol, starts, roi, dtype, channels_last, flip=0):
     wins = [vol[b:b + 1, :, z:z + roi[0], y:y + roi[1], x:x + roi[2]] for b, z, y, x in starts.tolist()]
     w = torch.cat(wins, 0).to(dtype)
     return w.permute(0, 2, 3, 4, 1).contiguous() if channels_last else w
-def sw_accumulate(seg, acc, starts, gz, gy, gx, floor, channels_last):
+def sw_accumulate(seg, acc, starts, gz, gy, gx, floor, channels_last, flip=0):
     if channels_last: seg = seg.permute(0, 4, 1, 2, 3)
     w = torch.clamp((gz[:, None, None] * gy[None, :, None]) * gx[None, None, :], min=floor)
     for (b, z, y, x), s in zip(starts.tolist(), seg):
         acc[b, :, z:z + s.shape[1], y:y + s.shape[2], x:x + s.shape[3]] += s.float() * w
-def sw_finalize(acc, all_starts, gz, gy, gx, floor, roi, labels=None):
+def sw_finalize(acc, all_starts, gz, gy, gx, floor, roi, labels=None, z_range=None, flip=0, dst=None, dst_scale=1.0, dst_add=False):
     w = torch.clamp((gz[:, None, None] * gy[None, :, None]) * gx[None, None, :], min=floor)
     cnt = torch.zeros((acc.shape[0], 1) + tuple(acc.shape[2:]))
     for b, z, y, x in all_starts.tolist():
-        cnt[b, 0, z:z + roi[0], y:y + roi[1], x:x + roi[2]] += w
+        sel = slice(None) if b < 0 else slice(b, b + 1)          # slot -1: the window exists in every volume
+        cnt[sel, 0, z:z + roi[0], y:y + roi[1], x:x + roi[2]] += w
     acc /= cnt
 ops.sw_gather, ops.sw_accumulate, ops.sw_finalize = sw_gather, sw_accumulate, sw_finalize
 class _T(torch.Tensor): pass
@@ -147,15 +165,20 @@ dist.init_process_group("gloo", init_method="env://")
 rank, world = dist.get_rank(), dist.get_world_size()
 wconv = seeded_randn((3, 2, 3, 3, 3), 600) * 0.2
 net = lambda p: torch.nn.functional.conv3d(p.float(), wconv, padding=1)
-for case, shape in (("split-volume", (1, 2, 40, 36, 30)), ("three-volumes", (3, 2, 24, 36, 30)), ("whole-volumes", (2, 2, 24, 20, 30))):
+cases = (("split-volume", (1, 2, 40, 36, 30), True), ("three-volumes", (3, 2, 24, 36, 30), True),
+         ("whole-volumes", (world, 2, 24, 20, 30), True), ("one-window", (1, 2, 16, 16, 16), True),
+         ("interleaved", (3, 2, 24, 36, 30), "interleaved"), ("interleaved-one", (1, 2, 40, 36, 30), "interleaved"))
+for case, shape, shard in cases:
     x = seeded_randn(shape, 77)
     inf = inferers.SlidingWindowInferer(roi_size=(16, 16, 16), sw_batch_size=2, overlap=0.5, mode="gaussian",
-                                        compute_dtype=torch.float32, channels_last=False)
+                                        compute_dtype=torch.float32, channels_last=False, shard=shard)
     y = inf(x, net)
     want = osw.sliding_window_inference(x, (16, 16, 16), 2, net, 0.5, "gaussian")
     owned = inf.owned_volumes
-    if case == "split-volume":
+    if case in ("split-volume", "interleaved-one"):
         assert owned == ([0] if rank == 0 else []) and (y is None) == (rank != 0)
+    if case == "whole-volumes":
+        assert owned == [rank]                      # contiguous runs of whole volumes: no collective at all
     got_owned = [None] * world
     dist.all_gather_object(got_owned, owned)
     assert sorted(v for o in got_owned for v in o) == list(range(shape[0])), got_owned   # every volume exactly once
@@ -168,13 +191,14 @@ dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize("world", [2])
-def test_sharded_inferer_two_ranks_gloo(tmp_path, world):
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_inferer_gloo(tmp_path, world):
     script = tmp_path / "worker.py"
     script.write_text(_WORKER)
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", OMP_NUM_THREADS="2")
+    port = str(29533 + world)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=port, OMP_NUM_THREADS="2")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
-           "127.0.0.1", "--master-port", "29533", str(script), ROOT]
+           "127.0.0.1", "--master-port", port, str(script), ROOT]
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
     assert "OK" in res.stdout

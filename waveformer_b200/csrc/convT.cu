@@ -26,8 +26,9 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
 // staged next to it (L2-resident), all N / NT accumulator tiles live in TMEM at once (N <= 512 columns), one commit covers
 // every MMA, then the eight warps drain TMEM (warp w: lane quadrant w % 4, tiles of parity w / 4) through a bf16 staging
 // area that aliases the operand images, and the block writes the output voxels with coalesced 16-byte stores.
-__global__ void __launch_bounds__(256) convT_k2s2_kernel(const __nv_bfloat16 *__restrict__ x, const uint16_t *__restrict__ wp,
-                                                         __nv_bfloat16 *__restrict__ y, int64_t M, int K, int NT, int ntiles,
+template <bool F16>
+__global__ void __launch_bounds__(256) convT_k2s2_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict__ wp,
+                                                         uint16_t *__restrict__ y, int64_t M, int K, int NT, int ntiles,
                                                          int Cout, int D, int H, int W, int64_t xs, int64_t ys) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(256) convT_k2s2_kernel(const __nv_bfloat16 *__
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
     if (tid == 0) {
-        const uint32_t idesc = instr_desc_bf16(128, NT, false);
+        const uint32_t idesc = instr_desc_h16<F16>(128, NT, false);
         const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
         for (int t = 0; t < ntiles; ++t)
             for (int ks = 0; ks < (K >> 4); ++ks)
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(256) convT_k2s2_kernel(const __nv_bfloat16 *__
     tc_fence_after();
     __syncthreads();   // every thread has seen the MMAs complete: the operand images may be overwritten
     // ---- TMEM -> bf16 staging [128 rows][N + 8] ----
-    __nv_bfloat16 *sOut = reinterpret_cast<__nv_bfloat16 *>(smem);
+    uint16_t *sOut = reinterpret_cast<uint16_t *>(smem);
     const int pitch = N + 8;
     {
         const int row = (warp & 3) * 32 + (tid & 31);
@@ -111,10 +112,10 @@ __global__ void __launch_bounds__(256) convT_k2s2_kernel(const __nv_bfloat16 *__
                 tmem_ld16(tmem + lane_base + t * NT + c, r);
                 tmem_wait_ld();
                 uint4 lo, hi;
-                lo.x = pack_bf16(__uint_as_float(r[0]), __uint_as_float(r[1]));   lo.y = pack_bf16(__uint_as_float(r[2]), __uint_as_float(r[3]));
-                lo.z = pack_bf16(__uint_as_float(r[4]), __uint_as_float(r[5]));   lo.w = pack_bf16(__uint_as_float(r[6]), __uint_as_float(r[7]));
-                hi.x = pack_bf16(__uint_as_float(r[8]), __uint_as_float(r[9]));   hi.y = pack_bf16(__uint_as_float(r[10]), __uint_as_float(r[11]));
-                hi.z = pack_bf16(__uint_as_float(r[12]), __uint_as_float(r[13])); hi.w = pack_bf16(__uint_as_float(r[14]), __uint_as_float(r[15]));
+                lo.x = pack_h16<F16>(__uint_as_float(r[0]), __uint_as_float(r[1]));   lo.y = pack_h16<F16>(__uint_as_float(r[2]), __uint_as_float(r[3]));
+                lo.z = pack_h16<F16>(__uint_as_float(r[4]), __uint_as_float(r[5]));   lo.w = pack_h16<F16>(__uint_as_float(r[6]), __uint_as_float(r[7]));
+                hi.x = pack_h16<F16>(__uint_as_float(r[8]), __uint_as_float(r[9]));   hi.y = pack_h16<F16>(__uint_as_float(r[10]), __uint_as_float(r[11]));
+                hi.z = pack_h16<F16>(__uint_as_float(r[12]), __uint_as_float(r[13])); hi.w = pack_h16<F16>(__uint_as_float(r[14]), __uint_as_float(r[15]));
                 uint4 *dst = reinterpret_cast<uint4 *>(sOut + (size_t)row * pitch + t * NT + c);
                 dst[0] = lo;
                 dst[1] = hi;
@@ -132,8 +133,8 @@ __global__ void __launch_bounds__(256) convT_k2s2_kernel(const __nv_bfloat16 *__
             const int row = q / per, p = q - row * per;
             const int64_t base = s_ov[row];
             if (base < 0) continue;
-            const __nv_bfloat16 *src = sOut + (size_t)row * pitch + p * 8;
-            __nv_bfloat16 *dst = y + base * ys + p * 8;
+            const uint16_t *src = sOut + (size_t)row * pitch + p * 8;
+            uint16_t *dst = y + base * ys + p * 8;
 #pragma unroll
             for (int pos = 0; pos < 8; ++pos) {
                 const int64_t off = (pos >> 2) * sz + ((pos >> 1) & 1) * sy + (pos & 1);
@@ -153,7 +154,7 @@ extern "C" int wf_convtranspose3d_k2s2_ndhwc(const void *x, const void *wpack, v
                                              int W, int Cin, int Cout, int64_t x_vox_stride, int64_t y_vox_stride,
                                              void *stream) {
     if (!x || !wpack || !y) return WF_ERR_NULL_POINTER;
-    if (dtype != WF_BF16) return WF_ERR_BAD_DTYPE;
+    if (dtype != WF_BF16 && dtype != WF_F16) return WF_ERR_BAD_DTYPE;
     if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return WF_ERR_BAD_SHAPE;
     if (Cin % 16 || Cin > 512 || Cout % 16 || x_vox_stride < Cin || y_vox_stride < Cout || x_vox_stride % 8 || y_vox_stride % 8)
         return WF_ERR_BAD_SHAPE;
@@ -171,13 +172,18 @@ extern "C" int wf_convtranspose3d_k2s2_ndhwc(const void *x, const void *wpack, v
     if (smem > 220 * 1024) return WF_ERR_UNSUPPORTED;
     static unsigned long long attr_done = 0;   // per-device opt-in bits
     if (first_use_on_current_device(attr_done)) {
-        WF_CUDA_CHECK(cudaFuncSetAttribute(convT_k2s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(convT_k2s2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(convT_k2s2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     }
     const int64_t M = (int64_t)B * D * H * W;
     if (M >= 0x7fffffffLL) return WF_ERR_UNSUPPORTED;
-    convT_k2s2_kernel<<<(unsigned)((M + 127) / 128), 256, smem, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16 *)x, (const uint16_t *)wpack, (__nv_bfloat16 *)y, M, Cin, NT, N / NT, Cout, D, H, W, x_vox_stride,
-        y_vox_stride);
+    const unsigned grid = (unsigned)((M + 127) / 128);
+    if (dtype == WF_F16)
+        convT_k2s2_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(
+            (const uint16_t *)x, (const uint16_t *)wpack, (uint16_t *)y, M, Cin, NT, N / NT, Cout, D, H, W, x_vox_stride, y_vox_stride);
+    else
+        convT_k2s2_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>(
+            (const uint16_t *)x, (const uint16_t *)wpack, (uint16_t *)y, M, Cin, NT, N / NT, Cout, D, H, W, x_vox_stride, y_vox_stride);
     WF_LAUNCH_CHECK();
     return WF_OK;
 }

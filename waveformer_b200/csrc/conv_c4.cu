@@ -32,21 +32,15 @@ struct C4Geom {
     int64_t total;  // B * D * H * W
 };
 
-template <typename TIN> __device__ __forceinline__ uint2 load_vox4(const TIN *p) {
-    if constexpr (sizeof(TIN) == 2) {
-        return __ldg(reinterpret_cast<const uint2 *>(p));
-    } else {
-        const float4 f = __ldg(reinterpret_cast<const float4 *>(p));
-        return make_uint2(pack_bf16(f.x, f.y), pack_bf16(f.z, f.w));
-    }
-}
 
 // dynamic smem: [B image 14 * N * 16][A image 14 * 2048, re-used as the bf16 staging tile 128 * (N + 8) * 2 once the MMAs
 // of the tile have completed]
-template <typename TIN>
+// TIN: float (converted to the operand format while gathered) or uint16_t (already in the operand format);
+// F16: operand / output format fp16 instead of bf16.
+template <typename TIN, bool F16>
 __global__ void __launch_bounds__(128, 4) conv3d_c4_kernel(const TIN *__restrict__ x, const uint16_t *__restrict__ wpack,
-                                                           __nv_bfloat16 *__restrict__ y0, int64_t ys0, int n0,
-                                                           __nv_bfloat16 *__restrict__ y1, int64_t ys1, int n1,
+                                                           uint16_t *__restrict__ y0, int64_t ys0, int n0,
+                                                           uint16_t *__restrict__ y1, int64_t ys1, int n1,
                                                            double *__restrict__ sums0, double *__restrict__ sums1,
                                                            C4Geom g, int64_t ntiles, uint32_t tmem_cols) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -57,8 +51,8 @@ __global__ void __launch_bounds__(128, 4) conv3d_c4_kernel(const TIN *__restrict
     uint8_t *sB = smem;
     uint8_t *sA = smem + (size_t)kC4Chunks * N * 16;
     // staging: two DENSE sub-tiles [128][n0] and [128][n1] (so that, for dense outputs, tile -> global is a linear copy)
-    __nv_bfloat16 *sOut0 = reinterpret_cast<__nv_bfloat16 *>(sA);
-    __nv_bfloat16 *sOut1 = sOut0 + 128 * n0;
+    uint16_t *sOut0 = reinterpret_cast<uint16_t *>(sA);
+    uint16_t *sOut1 = sOut0 + 128 * n0;
 
     if (warp == 0) tmem_alloc(&tmem_slot, tmem_cols);
     if (tid == 0) {
@@ -76,7 +70,7 @@ __global__ void __launch_bounds__(128, 4) conv3d_c4_kernel(const TIN *__restrict
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
-    const uint32_t idesc = instr_desc_bf16(128, N, false);
+    const uint32_t idesc = instr_desc_h16<F16>(128, N, false);
     const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     const int64_t S = (int64_t)g.D * g.H * g.W;
@@ -167,7 +161,7 @@ __global__ void __launch_bounds__(128, 4) conv3d_c4_kernel(const TIN *__restrict
                     }
 #pragma unroll
                     for (int i = 0; i < 9; ++i)
-                        tap[(dz + 1) * 9 + i] = in[i] ? make_uint2(pack_bf16(raw[i].x, raw[i].y), pack_bf16(raw[i].z, raw[i].w))
+                        tap[(dz + 1) * 9 + i] = in[i] ? make_uint2(pack_h16<F16>(raw[i].x, raw[i].y), pack_h16<F16>(raw[i].z, raw[i].w))
                                                       : make_uint2(0u, 0u);
                 }
             }
@@ -198,10 +192,10 @@ __global__ void __launch_bounds__(128, 4) conv3d_c4_kernel(const TIN *__restrict
             tmem_ld16(tmem + lane_base + c, r);
             tmem_wait_ld();
             uint4 lo, hi;
-            lo.x = pack_bf16(__uint_as_float(r[0]), __uint_as_float(r[1]));   lo.y = pack_bf16(__uint_as_float(r[2]), __uint_as_float(r[3]));
-            lo.z = pack_bf16(__uint_as_float(r[4]), __uint_as_float(r[5]));   lo.w = pack_bf16(__uint_as_float(r[6]), __uint_as_float(r[7]));
-            hi.x = pack_bf16(__uint_as_float(r[8]), __uint_as_float(r[9]));   hi.y = pack_bf16(__uint_as_float(r[10]), __uint_as_float(r[11]));
-            hi.z = pack_bf16(__uint_as_float(r[12]), __uint_as_float(r[13])); hi.w = pack_bf16(__uint_as_float(r[14]), __uint_as_float(r[15]));
+            lo.x = pack_h16<F16>(__uint_as_float(r[0]), __uint_as_float(r[1]));   lo.y = pack_h16<F16>(__uint_as_float(r[2]), __uint_as_float(r[3]));
+            lo.z = pack_h16<F16>(__uint_as_float(r[4]), __uint_as_float(r[5]));   lo.w = pack_h16<F16>(__uint_as_float(r[6]), __uint_as_float(r[7]));
+            hi.x = pack_h16<F16>(__uint_as_float(r[8]), __uint_as_float(r[9]));   hi.y = pack_h16<F16>(__uint_as_float(r[10]), __uint_as_float(r[11]));
+            hi.z = pack_h16<F16>(__uint_as_float(r[12]), __uint_as_float(r[13])); hi.w = pack_h16<F16>(__uint_as_float(r[14]), __uint_as_float(r[15]));
             // 16 columns never straddle the two outputs (n0 % 16 == 0 is required by the host wrapper when n1 > 0)
             uint4 *dst = reinterpret_cast<uint4 *>(c < n0 ? sOut0 + (size_t)tid * n0 + c : sOut1 + (size_t)tid * n1 + (c - n0));
             dst[0] = lo;
@@ -248,10 +242,7 @@ __global__ void __launch_bounds__(128, 4) conv3d_c4_kernel(const TIN *__restrict
 #pragma unroll 8
                 for (int r = r0; r < r1; ++r) {
                     const uint32_t w = col[(size_t)r * wpitch];
-                    asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %4;\n\t"
-                        "add.rn.f32.bf16 %0, lo, %0;\n\tadd.rn.f32.bf16 %1, hi, %1;\n\t"
-                        "fma.rn.f32.bf16 %2, lo, lo, %2;\n\tfma.rn.f32.bf16 %3, hi, hi, %3;\n\t}"
-                        : "+f"(s0), "+f"(s1), "+f"(q0), "+f"(q1) : "r"(w));
+                    stat_h16x2<F16>(w, s0, s1, q0, q1);
                 }
                 acc[0] += (double)s0; acc[1] += (double)s1; acc[2] += (double)q0; acc[3] += (double)q1;
             } else {
@@ -259,7 +250,8 @@ __global__ void __launch_bounds__(128, 4) conv3d_c4_kernel(const TIN *__restrict
                     const int64_t bb = (uint32_t)(v0 + r) / (uint32_t)S;
                     if (bb != acc_b) { flush(); acc_b = bb; }
                     const uint32_t w = col[(size_t)r * wpitch];
-                    const double f0 = (double)__uint_as_float(w << 16), f1 = (double)__uint_as_float(w & 0xffff0000u);
+                    const float2 ff = unpack_h16<F16>(w);
+                    const double f0 = (double)ff.x, f1 = (double)ff.y;
                     acc[0] += f0; acc[1] += f1; acc[2] += f0 * f0; acc[3] += f1 * f1;
                 }
             }
@@ -288,7 +280,7 @@ __global__ void stats_finalize_raw_kernel(const double *__restrict__ sums, float
 
 using namespace wf;
 
-extern "C" int wf_conv3d_c4_in_stats(const void *x, int x_dtype, const void *wpack, void *y0, int64_t y0_vox_stride,
+extern "C" int wf_conv3d_c4_in_stats(const void *x, int x_dtype, int op_dtype, const void *wpack, void *y0, int64_t y0_vox_stride,
                                      int n0, void *y1, int64_t y1_vox_stride, int n1, double *sums0, double *sums1,
                                      float *mean_rstd0, float *mean_rstd1, float eps, int B, int D, int H, int W,
                                      void *stream) {
@@ -298,7 +290,8 @@ extern "C" int wf_conv3d_c4_in_stats(const void *x, int x_dtype, const void *wpa
     const int N = n0 + n1;
     if (n0 <= 0 || n1 < 0 || n0 % 8 || n1 % 8 || N % 16 || N > 128 || (n1 > 0 && n0 % 16)) return WF_ERR_BAD_SHAPE;
     if (y0_vox_stride < n0 || (n1 > 0 && y1_vox_stride < n1) || y0_vox_stride % 8 || (n1 > 0 && y1_vox_stride % 8)) return WF_ERR_BAD_SHAPE;
-    if (x_dtype != WF_F32 && x_dtype != WF_BF16) return WF_ERR_BAD_DTYPE;
+    if (op_dtype != WF_BF16 && op_dtype != WF_F16) return WF_ERR_BAD_DTYPE;
+    if (x_dtype != WF_F32 && x_dtype != op_dtype) return WF_ERR_BAD_DTYPE;
     if (!aligned16(x) || !aligned16(wpack) || !aligned16(y0) || (n1 > 0 && !aligned16(y1))) return WF_ERR_MISALIGNED;
     cudaStream_t st = (cudaStream_t)stream;
     C4Geom g;
@@ -312,20 +305,24 @@ extern "C" int wf_conv3d_c4_in_stats(const void *x, int x_dtype, const void *wpa
     while ((int)cols < N) cols <<= 1;
     static unsigned long long attrs_done = 0;   // per-device opt-in bits
     if (first_use_on_current_device(attrs_done)) {
-        WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_c4_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_c4_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_c4_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_c4_kernel<uint16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_c4_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_c4_kernel<uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     }
     WF_CUDA_CHECK(cudaMemsetAsync(sums0, 0, sizeof(double) * 2 * (size_t)B * n0, st));
     if (n1 > 0) WF_CUDA_CHECK(cudaMemsetAsync(sums1, 0, sizeof(double) * 2 * (size_t)B * n1, st));
     const int per_sm = (int)min((size_t)4, (size_t)(200 * 1024) / smem);
     const int grid = (int)min(ntiles, (int64_t)kNumSMs * (per_sm < 1 ? 1 : per_sm));
-    if (x_dtype == WF_F32)
-        conv3d_c4_kernel<float><<<grid, 128, smem, st>>>((const float *)x, (const uint16_t *)wpack, (__nv_bfloat16 *)y0, y0_vox_stride, n0,
-                                                         (__nv_bfloat16 *)y1, y1_vox_stride, n1, sums0, sums1, g, ntiles, cols);
-    else
-        conv3d_c4_kernel<__nv_bfloat16><<<grid, 128, smem, st>>>((const __nv_bfloat16 *)x, (const uint16_t *)wpack, (__nv_bfloat16 *)y0,
-                                                                 y0_vox_stride, n0, (__nv_bfloat16 *)y1, y1_vox_stride, n1, sums0, sums1, g,
-                                                                 ntiles, cols);
+#define WF_C4(TIN_, F16_)                                                                                              \
+    conv3d_c4_kernel<TIN_, F16_><<<grid, 128, smem, st>>>((const TIN_ *)x, (const uint16_t *)wpack, (uint16_t *)y0, y0_vox_stride, \
+                                                          n0, (uint16_t *)y1, y1_vox_stride, n1, sums0, sums1, g, ntiles, cols)
+    if (op_dtype == WF_F16) {
+        if (x_dtype == WF_F32) WF_C4(float, true); else WF_C4(uint16_t, true);
+    } else {
+        if (x_dtype == WF_F32) WF_C4(float, false); else WF_C4(uint16_t, false);
+    }
+#undef WF_C4
     WF_LAUNCH_CHECK();
     const double inv_s = 1.0 / ((double)D * H * W);
     stats_finalize_raw_kernel<<<(B * n0 + 127) / 128, 128, 0, st>>>(sums0, mean_rstd0, B * n0, inv_s, (double)eps);

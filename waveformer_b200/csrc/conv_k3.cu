@@ -20,6 +20,8 @@
 //   * Accumulators: 4 output rows x 48 columns, double buffered in TMEM (2 x 192 columns), so the epilogue of a block
 //     (TMEM -> bf16 -> staging -> coalesced stores + per-channel sum / sum of squares) overlaps the MMAs of the next one.
 // Warp roles (288 threads): warps 0-3 loaders (+ optional input normalisation), warp 4 MMA issuer, warps 5-8 epilogue.
+#include <type_traits>
+
 #include "tc_common.cuh"
 #include "wf_common.cuh"
 
@@ -56,9 +58,9 @@ __device__ __forceinline__ void mbar_arrive_k3(uint64_t *bar) {
 }
 
 struct K3Args {
-    const __nv_bfloat16 *x;     // [B, D, H, W = 128, 48], voxel stride xs
-    const uint16_t *wpack;      // [3 dz][3 dx][3 ks][2 chunks][144 = 3 dy x 48 out][8] bf16
-    __nv_bfloat16 *y;           // [B, D, H, 128, 48], voxel stride ys
+    const uint16_t *x;          // [B, D, H, W = 128, 48] bf16 or fp16, voxel stride xs
+    const uint16_t *wpack;      // [3 dz][3 dx][3 ks][2 chunks][144 = 3 dy x 48 out][8] in the same 16-bit format
+    uint16_t *y;                // [B, D, H, 128, 48], voxel stride ys
     double *sums;               // [B][48][2] (sum, sum of squares of the rounded outputs); zeroed by the host wrapper
     const float *in_mr;         // optional (mean, rstd) [B][48][2] of the input: x is normalised + LeakyReLU'd while staged
     float slope;
@@ -66,13 +68,16 @@ struct K3Args {
     int B, D, H;
 };
 
+// F16: activations / weights / result are fp16 instead of bf16 (same tensor-core rate, 10-bit mantissa)
+template <bool F16>
 __global__ void __launch_bounds__(288, 1) conv3d_k3_c48_kernel(K3Args a) {
+    using T16 = typename std::conditional<F16, __half, __nv_bfloat16>::type;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_full[kK3Ring], bar_empty[kK3Ring], bar_acc_full[2], bar_acc_empty[2];
     __shared__ uint32_t tmem_slot;
     uint8_t *sW = smem;
     uint8_t *sRing = smem + kK3WBytes;
-    __nv_bfloat16 *sStage = reinterpret_cast<__nv_bfloat16 *>(smem + kK3WBytes + kK3Ring * kK3RowImg);
+    uint16_t *sStage = reinterpret_cast<uint16_t *>(smem + kK3WBytes + kK3Ring * kK3RowImg);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int W = 128;
     const int yblocks = (a.H + 3) >> 2;
@@ -135,13 +140,13 @@ __global__ void __launch_bounds__(288, 1) conv3d_k3_c48_kernel(K3Args a) {
                     for (int ch = 0; ch < kK3Chunks; ++ch) {
                         uint4 *cell = reinterpret_cast<uint4 *>(img + (ch * kK3Rows + tid + 1) * 16);
                         float f[8];
-                        Pack<__nv_bfloat16>::unpack(*cell, f);
+                        Pack<T16>::unpack(*cell, f);
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
                             const float t = fmaf(f[e], sc[ch * 8 + e], sh[ch * 8 + e]);
                             f[e] = fmaxf(t, t * a.slope);
                         }
-                        *cell = Pack<__nv_bfloat16>::pack(f);
+                        *cell = Pack<T16>::pack(f);
                     }
                 }
                 fence_proxy_async();
@@ -164,7 +169,7 @@ __global__ void __launch_bounds__(288, 1) conv3d_k3_c48_kernel(K3Args a) {
                     const uint32_t use = n_loaded / kK3Ring;
                     if (use > 0) mbar_wait(&bar_empty[slot], (use - 1) & 1);   // the MMAs that read this slot are done
                     uint8_t *img = sRing + slot * kK3RowImg;
-                    const __nv_bfloat16 *src = a.x + ((((int64_t)b * a.D + zz) * a.H + yy) * W + tid) * a.xs;
+                    const uint16_t *src = a.x + ((((int64_t)b * a.D + zz) * a.H + yy) * W + tid) * a.xs;
 #pragma unroll
                     for (int ch = 0; ch < kK3Chunks; ++ch)
                         cp_async16_k3(img + (ch * kK3Rows + tid + 1) * 16, src + ch * 8);
@@ -183,8 +188,8 @@ __global__ void __launch_bounds__(288, 1) conv3d_k3_c48_kernel(K3Args a) {
     } else if (warp == 4) {
         // ================================================= issuer =====================================================
         if (lane == 0) {
-            const uint32_t idesc1 = instr_desc_bf16(128, kK3C, false), idesc2 = instr_desc_bf16(128, 2 * kK3C, false),
-                           idesc3 = instr_desc_bf16(128, 3 * kK3C, false);
+            const uint32_t idesc1 = instr_desc_h16<F16>(128, kK3C, false), idesc2 = instr_desc_h16<F16>(128, 2 * kK3C, false),
+                           idesc3 = instr_desc_h16<F16>(128, 3 * kK3C, false);
             const uint64_t desc_a0 = smem_desc(smem_u32(sRing), kK3Rows * 16, 128);   // slot 0, chunk 0, row 0
             const uint64_t desc_w0 = smem_desc(smem_u32(sW), 3 * kK3C * 16, 128);      // tile (dz, dx, ks) = [2][144 = dy x out][8]
             uint32_t n_used = 0, nblk = 0;
@@ -290,10 +295,10 @@ __global__ void __launch_bounds__(288, 1) conv3d_k3_c48_kernel(K3Args a) {
                         tmem_ld16(acc + c, r);
                         tmem_wait_ld();
                         uint4 lo, hi;
-                        lo.x = pack_bf16(__uint_as_float(r[0]), __uint_as_float(r[1]));   lo.y = pack_bf16(__uint_as_float(r[2]), __uint_as_float(r[3]));
-                        lo.z = pack_bf16(__uint_as_float(r[4]), __uint_as_float(r[5]));   lo.w = pack_bf16(__uint_as_float(r[6]), __uint_as_float(r[7]));
-                        hi.x = pack_bf16(__uint_as_float(r[8]), __uint_as_float(r[9]));   hi.y = pack_bf16(__uint_as_float(r[10]), __uint_as_float(r[11]));
-                        hi.z = pack_bf16(__uint_as_float(r[12]), __uint_as_float(r[13])); hi.w = pack_bf16(__uint_as_float(r[14]), __uint_as_float(r[15]));
+                        lo.x = pack_h16<F16>(__uint_as_float(r[0]), __uint_as_float(r[1]));   lo.y = pack_h16<F16>(__uint_as_float(r[2]), __uint_as_float(r[3]));
+                        lo.z = pack_h16<F16>(__uint_as_float(r[4]), __uint_as_float(r[5]));   lo.w = pack_h16<F16>(__uint_as_float(r[6]), __uint_as_float(r[7]));
+                        hi.x = pack_h16<F16>(__uint_as_float(r[8]), __uint_as_float(r[9]));   hi.y = pack_h16<F16>(__uint_as_float(r[10]), __uint_as_float(r[11]));
+                        hi.z = pack_h16<F16>(__uint_as_float(r[12]), __uint_as_float(r[13])); hi.w = pack_h16<F16>(__uint_as_float(r[14]), __uint_as_float(r[15]));
                         uint4 *dst = reinterpret_cast<uint4 *>(sStage + (size_t)(rr * 128 + et) * pitch + c);
                         dst[0] = lo;
                         dst[1] = hi;
@@ -319,10 +324,7 @@ __global__ void __launch_bounds__(288, 1) conv3d_k3_c48_kernel(K3Args a) {
 #pragma unroll 8
                     for (int r = q0; r < q1; ++r) {
                         const uint32_t w = col[(size_t)r * wpitch];
-                        asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %4;\n\t"
-                            "add.rn.f32.bf16 %0, lo, %0;\n\tadd.rn.f32.bf16 %1, hi, %1;\n\t"
-                            "fma.rn.f32.bf16 %2, lo, lo, %2;\n\tfma.rn.f32.bf16 %3, hi, hi, %3;\n\t}"
-                            : "+f"(s0), "+f"(s1), "+f"(qq0), "+f"(qq1) : "r"(w));
+                        stat_h16x2<F16>(w, s0, s1, qq0, qq1);
                     }
                     acc_s[0] += (double)s0; acc_s[1] += (double)s1; acc_q[0] += (double)qq0; acc_q[1] += (double)qq1;
                 }
@@ -350,24 +352,31 @@ __global__ void k3_finalize_kernel(const double *__restrict__ sums, float *__res
 
 using namespace wf;
 
-extern "C" int wf_conv3d_k3_c48_in_stats(const void *x, const void *wpack, void *y, double *sums, float *mean_rstd,
+extern "C" int wf_conv3d_k3_c48_in_stats(const void *x, int dtype, const void *wpack, void *y, double *sums, float *mean_rstd,
                                          const float *in_mean_rstd, float slope, float eps, int B, int D, int H, int W,
                                          int64_t x_vox_stride, int64_t y_vox_stride, void *stream) {
     if (!x || !wpack || !y || !sums || !mean_rstd) return WF_ERR_NULL_POINTER;
+    if (dtype != WF_BF16 && dtype != WF_F16) return WF_ERR_BAD_DTYPE;
     if (B <= 0 || D <= 0 || H <= 0 || W != 128) return WF_ERR_BAD_SHAPE;
     if (x_vox_stride < kK3C || y_vox_stride < kK3C || x_vox_stride % 8 || y_vox_stride % 8) return WF_ERR_BAD_SHAPE;
     if (!aligned16(x) || !aligned16(wpack) || !aligned16(y)) return WF_ERR_MISALIGNED;
     cudaStream_t st = (cudaStream_t)stream;
     static unsigned long long attr_done = 0;   // per-device opt-in bits
     if (first_use_on_current_device(attr_done))
-        WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_k3_c48_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kK3Smem));
+    {
+        WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_k3_c48_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kK3Smem));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_k3_c48_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kK3Smem));
+    }
     WF_CUDA_CHECK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)B * kK3C, st));
     K3Args a;
-    a.x = (const __nv_bfloat16 *)x; a.wpack = (const uint16_t *)wpack; a.y = (__nv_bfloat16 *)y; a.sums = sums;
+    a.x = (const uint16_t *)x; a.wpack = (const uint16_t *)wpack; a.y = (uint16_t *)y; a.sums = sums;
     a.in_mr = in_mean_rstd; a.slope = slope; a.xs = x_vox_stride; a.ys = y_vox_stride; a.B = B; a.D = D; a.H = H;
     const int64_t nblocks = (int64_t)B * D * ((H + 3) / 4);
     const int grid = (int)(nblocks < kNumSMs ? nblocks : kNumSMs);
-    conv3d_k3_c48_kernel<<<grid, 288, kK3Smem, st>>>(a);
+    if (dtype == WF_F16)
+        conv3d_k3_c48_kernel<true><<<grid, 288, kK3Smem, st>>>(a);
+    else
+        conv3d_k3_c48_kernel<false><<<grid, 288, kK3Smem, st>>>(a);
     WF_LAUNCH_CHECK();
     const int n = B * kK3C;
     k3_finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(sums, mean_rstd, n, 1.0 / ((double)D * H * W), (double)eps);

@@ -119,12 +119,32 @@ constexpr int kDwTZ = 4, kDwTY = 4, kDwTX = 16, kDwCG = 64;
 constexpr int kDwHZ = kDwTZ + 2, kDwHY = kDwTY + 2, kDwHX = kDwTX + 2;
 constexpr int kDwSmem = kDwHZ * kDwHY * kDwHX * kDwCG * 2;  // 82944
 
-__device__ __forceinline__ void fhfma2(float &a0, float &a1, uint32_t v, uint32_t w) {
-    // a0 += lo(v) * lo(w); a1 += hi(v) * hi(w)   (bf16 x bf16 + fp32, FHFMA.BF16)
-    asm("{\n\t.reg .b16 vl, vh, wl, wh;\n\tmov.b32 {vl, vh}, %2;\n\tmov.b32 {wl, wh}, %3;\n\t"
-        "fma.rn.f32.bf16 %0, vl, wl, %0;\n\tfma.rn.f32.bf16 %1, vh, wh, %1;\n\t}"
-        : "+f"(a0), "+f"(a1)
-        : "r"(v), "r"(w));
+template <bool F16> __device__ __forceinline__ void fhfma2(float &a0, float &a1, uint32_t v, uint32_t w) {
+    // a0 += lo(v) * lo(w); a1 += hi(v) * hi(w)   (16-bit x 16-bit + fp32: FHFMA.BF16 / FHFMA.F16)
+    if constexpr (F16)
+        asm("{\n\t.reg .b16 vl, vh, wl, wh;\n\tmov.b32 {vl, vh}, %2;\n\tmov.b32 {wl, wh}, %3;\n\t"
+            "fma.rn.f32.f16 %0, vl, wl, %0;\n\tfma.rn.f32.f16 %1, vh, wh, %1;\n\t}"
+            : "+f"(a0), "+f"(a1)
+            : "r"(v), "r"(w));
+    else
+        asm("{\n\t.reg .b16 vl, vh, wl, wh;\n\tmov.b32 {vl, vh}, %2;\n\tmov.b32 {wl, wh}, %3;\n\t"
+            "fma.rn.f32.bf16 %0, vl, wl, %0;\n\tfma.rn.f32.bf16 %1, vh, wh, %1;\n\t}"
+            : "+f"(a0), "+f"(a1)
+            : "r"(v), "r"(w));
+}
+// two fp32 -> one packed pair of the 16-bit storage type, and back
+template <bool F16> __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+    if constexpr (F16) {
+        __half2 h = __floats2half2_rn(lo, hi);
+        return *reinterpret_cast<uint32_t *>(&h);
+    } else {
+        __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+        return *reinterpret_cast<uint32_t *>(&h);
+    }
+}
+template <bool F16> __device__ __forceinline__ float2 unpack2(uint32_t w) {
+    if constexpr (F16) return __half22float2(*reinterpret_cast<const __half2 *>(&w));
+    else return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
 }
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
@@ -135,11 +155,11 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
 // STATS: additionally reduce per-(sample, channel) sum / sum of squares of the ROUNDED outputs into `sums` (fp64 [B][C][2],
 // zeroed by the launcher) - the statistics of the GroupNorm / InstanceNorm that follows (ProjectionUpsample.norm), so the
 // separate statistics pass over the result disappears.
-template <bool STATS>
-__global__ void __launch_bounds__(256, 2) dwconv3d_bf16_tile_kernel(const __nv_bfloat16 *__restrict__ x,
+template <bool STATS, bool F16>
+__global__ void __launch_bounds__(256, 2) dwconv3d_bf16_tile_kernel(const uint16_t *__restrict__ x,
                                                                     const float *__restrict__ w27,
                                                                     const float *__restrict__ bias,
-                                                                    __nv_bfloat16 *__restrict__ y, int D, int H, int W,
+                                                                    uint16_t *__restrict__ y, int D, int H, int W,
                                                                     int C, int tiles_x, int tiles_y, int tiles_z,
                                                                     double *__restrict__ sums) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -155,7 +175,7 @@ __global__ void __launch_bounds__(256, 2) dwconv3d_bf16_tile_kernel(const __nv_b
     const int cchunks = min(8, (C - c0) >> 3);  // live 16-byte channel chunks of this group
 
     // ---- stage the haloed tile: 6 * 6 * 18 voxels x 8 chunks of 16 bytes ----
-    const __nv_bfloat16 *xb = x + (int64_t)b * D * H * W * C + c0;
+    const uint16_t *xb = x + (int64_t)b * D * H * W * C + c0;
     for (int i = tid; i < kDwHZ * kDwHY * kDwHX * 8; i += 256) {
         const int ch = i & 7, v = i >> 3;
         const int xi = v % kDwHX, yi = (v / kDwHX) % kDwHY, zi = v / (kDwHX * kDwHY);
@@ -173,8 +193,7 @@ __global__ void __launch_bounds__(256, 2) dwconv3d_bf16_tile_kernel(const __nv_b
 #pragma unroll
     for (int k = 0; k < 27; ++k) {
         const float2 f = live_c ? __ldg(reinterpret_cast<const float2 *>(w27 + (int64_t)k * C + c)) : make_float2(0.f, 0.f);
-        __nv_bfloat162 h = __floats2bfloat162_rn(f.x, f.y);
-        wt[k] = *reinterpret_cast<uint32_t *>(&h);
+        wt[k] = pack2<F16>(f.x, f.y);
     }
     float b0 = 0.f, b1 = 0.f;
     if (bias != nullptr && live_c) {
@@ -199,7 +218,7 @@ __global__ void __launch_bounds__(256, 2) dwconv3d_bf16_tile_kernel(const __nv_b
         win[r][1] = ld(r, 1);
     }
     const int gz = z0 + zl, gy = y0 + 2 * yp;
-    __nv_bfloat16 *yrow = y + ((((int64_t)b * D + gz) * H + gy) * W + x0) * C + c;
+    uint16_t *yrow = y + ((((int64_t)b * D + gz) * H + gy) * W + x0) * C + c;
     const bool row0 = gz < D && gy < H && live_c, row1 = gz < D && gy + 1 < H && live_c;
     float st_s0 = 0.f, st_s1 = 0.f, st_q0 = 0.f, st_q1 = 0.f;   // STATS: this lane's two channels over its outputs
 #pragma unroll
@@ -214,23 +233,23 @@ __global__ void __launch_bounds__(256, 2) dwconv3d_bf16_tile_kernel(const __nv_b
 #pragma unroll
                 for (int dx = 0; dx < 3; ++dx) {
                     const uint32_t wv = wt[dz * 9 + dy * 3 + dx];
-                    fhfma2(a00, a01, win[dz * 4 + dy][(j + dx) % 3], wv);       // output row 0 reads window rows dy
-                    fhfma2(a10, a11, win[dz * 4 + dy + 1][(j + dx) % 3], wv);   // output row 1 reads window rows dy + 1
+                    fhfma2<F16>(a00, a01, win[dz * 4 + dy][(j + dx) % 3], wv);       // output row 0 reads window rows dy
+                    fhfma2<F16>(a10, a11, win[dz * 4 + dy + 1][(j + dx) % 3], wv);   // output row 1 reads window rows dy + 1
                 }
         if (x0 + j < W) {
             if (row0) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(a00, a01);
-                *reinterpret_cast<__nv_bfloat162 *>(yrow + (int64_t)j * C) = h;
+                const uint32_t h = pack2<F16>(a00, a01);
+                *reinterpret_cast<uint32_t *>(yrow + (int64_t)j * C) = h;
                 if constexpr (STATS) {
-                    const float2 f = __bfloat1622float2(h);
+                    const float2 f = unpack2<F16>(h);
                     st_s0 += f.x; st_s1 += f.y; st_q0 = fmaf(f.x, f.x, st_q0); st_q1 = fmaf(f.y, f.y, st_q1);
                 }
             }
             if (row1) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(a10, a11);
-                *reinterpret_cast<__nv_bfloat162 *>(yrow + ((int64_t)W + j) * C) = h;
+                const uint32_t h = pack2<F16>(a10, a11);
+                *reinterpret_cast<uint32_t *>(yrow + ((int64_t)W + j) * C) = h;
                 if constexpr (STATS) {
-                    const float2 f = __bfloat1622float2(h);
+                    const float2 f = unpack2<F16>(h);
                     st_s0 += f.x; st_s1 += f.y; st_q0 = fmaf(f.x, f.x, st_q0); st_q1 = fmaf(f.y, f.y, st_q1);
                 }
             }
@@ -261,18 +280,18 @@ __global__ void dwconv_stats_finalize_kernel(const double *__restrict__ sums, fl
     mr[2 * i + 1] = (float)(1.0 / sqrt(var + eps));
 }
 
-template <bool STATS>
-static int dwconv_bf16_tile_launch(const __nv_bfloat16 *x, const float *w27, const float *bias, __nv_bfloat16 *y, int B,
+template <bool STATS, bool F16>
+static int dwconv_bf16_tile_launch(const uint16_t *x, const float *w27, const float *bias, uint16_t *y, int B,
                                    int D, int H, int W, int C, cudaStream_t st, double *sums = nullptr) {
     static unsigned long long attr_done = 0;   // per-device opt-in bits
     if (first_use_on_current_device(attr_done)) {
-        WF_CUDA_CHECK(cudaFuncSetAttribute(dwconv3d_bf16_tile_kernel<STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmem));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(dwconv3d_bf16_tile_kernel<STATS, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmem));
     }
     const int tiles_x = (W + kDwTX - 1) / kDwTX, tiles_y = (H + kDwTY - 1) / kDwTY, tiles_z = (D + kDwTZ - 1) / kDwTZ;
     const int64_t tiles = (int64_t)B * tiles_x * tiles_y * tiles_z;
     if (tiles > 0x7fffffff) return WF_ERR_UNSUPPORTED;
     dim3 grid((unsigned)tiles, (unsigned)((C + kDwCG - 1) / kDwCG));
-    dwconv3d_bf16_tile_kernel<STATS><<<grid, 256, kDwSmem, st>>>(x, w27, bias, y, D, H, W, C, tiles_x, tiles_y, tiles_z, sums);
+    dwconv3d_bf16_tile_kernel<STATS, F16><<<grid, 256, kDwSmem, st>>>(x, w27, bias, y, D, H, W, C, tiles_x, tiles_y, tiles_z, sums);
     WF_LAUNCH_CHECK();
     return WF_OK;
 }
@@ -304,12 +323,17 @@ extern "C" int wf_dwconv3d_ndhwc(const void *x, const float *w27, const float *b
     if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || C <= 0) return WF_ERR_BAD_SHAPE;
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == WF_F32) return wf::dwconv_launch<float>((const float *)x, w27, bias, (float *)y, B, D, H, W, C, st);
-    if (dtype == WF_BF16) {
+    if (dtype == WF_BF16 || dtype == WF_F16) {
         // shared-memory tile kernel when the geometry gives it enough work; the register-tiled kernel otherwise
         const char *impl = getenv("WF_DWCONV_IMPL");
         const bool force_old = impl != nullptr && impl[0] == 'r';
-        if (!force_old && C % 8 == 0 && W >= 8 && wf::aligned16(x) && wf::aligned16(w27) && (bias == nullptr || wf::aligned16(bias)))
-            return wf::dwconv_bf16_tile_launch<false>((const __nv_bfloat16 *)x, w27, bias, (__nv_bfloat16 *)y, B, D, H, W, C, st);
+        if (!force_old && C % 8 == 0 && W >= 8 && wf::aligned16(x) && wf::aligned16(w27) && (bias == nullptr || wf::aligned16(bias))) {
+            if (dtype == WF_F16)
+                return wf::dwconv_bf16_tile_launch<false, true>((const uint16_t *)x, w27, bias, (uint16_t *)y, B, D, H, W, C, st);
+            return wf::dwconv_bf16_tile_launch<false, false>((const uint16_t *)x, w27, bias, (uint16_t *)y, B, D, H, W, C, st);
+        }
+        if (dtype == WF_F16)
+            return wf::dwconv_launch<__half>((const __half *)x, w27, bias, (__half *)y, B, D, H, W, C, st);
         return wf::dwconv_launch<__nv_bfloat16>((const __nv_bfloat16 *)x, w27, bias, (__nv_bfloat16 *)y, B, D, H, W, C, st);
     }
     return WF_ERR_BAD_DTYPE;
@@ -320,12 +344,14 @@ extern "C" int wf_dwconv3d_ndhwc_stats(const void *x, const float *w27, const fl
                                        void *stream) {
     if (!x || !w27 || !y || !sums || !mean_rstd) return WF_ERR_NULL_POINTER;
     if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || C <= 0) return WF_ERR_BAD_SHAPE;
-    if (dtype != WF_BF16) return WF_ERR_UNSUPPORTED;
+    if (dtype != WF_BF16 && dtype != WF_F16) return WF_ERR_UNSUPPORTED;
     if (C % 8 != 0 || W < 8) return WF_ERR_UNSUPPORTED;
     if (!wf::aligned16(x) || !wf::aligned16(w27) || (bias != nullptr && !wf::aligned16(bias))) return WF_ERR_MISALIGNED;
     cudaStream_t st = (cudaStream_t)stream;
     WF_CUDA_CHECK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)B * C, st));
-    const int rc = wf::dwconv_bf16_tile_launch<true>((const __nv_bfloat16 *)x, w27, bias, (__nv_bfloat16 *)y, B, D, H, W, C, st, sums);
+    const int rc = dtype == WF_F16
+        ? wf::dwconv_bf16_tile_launch<true, true>((const uint16_t *)x, w27, bias, (uint16_t *)y, B, D, H, W, C, st, sums)
+        : wf::dwconv_bf16_tile_launch<true, false>((const uint16_t *)x, w27, bias, (uint16_t *)y, B, D, H, W, C, st, sums);
     if (rc != WF_OK) return rc;
     const int n = B * C;
     wf::dwconv_stats_finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(sums, mean_rstd, n, 1.0 / ((double)D * H * W), (double)eps);

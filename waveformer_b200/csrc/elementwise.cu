@@ -17,8 +17,9 @@ __global__ void __launch_bounds__(256) residual_sum_kernel(const float *__restri
         vc = __ldcs(reinterpret_cast<const float4 *>(c) + i);
     } else {
         const uint2 t = __ldcs(reinterpret_cast<const uint2 *>(c) + i);
-        vc = make_float4(__uint_as_float(t.x << 16), __uint_as_float(t.x & 0xffff0000u), __uint_as_float(t.y << 16),
-                         __uint_as_float(t.y & 0xffff0000u));
+        float f[8];
+        Pack<TC>::unpack(make_uint4(t.x, t.y, 0u, 0u), f);
+        vc = make_float4(f[0], f[1], f[2], f[3]);
     }
     float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
     if (bias != nullptr) bb = __ldg(reinterpret_cast<const float4 *>(bias) + (int)(i % c4s));
@@ -103,6 +104,12 @@ extern "C" int wf_groupnorm_fold_linear(const float *mean_rstd, const float *gam
     else if (w_dtype == WF_F32 && out_dtype == WF_BF16)
         wf::groupnorm_fold_kernel<float, bf><<<grid, 128, 0, st>>>(mean_rstd, gamma, beta, (const float *)w, (const float *)bias,
                                                                    (bf *)w_folded, (bf *)b_folded, C, N);
+    else if (w_dtype == WF_F16 && out_dtype == WF_F16)
+        wf::groupnorm_fold_kernel<__half, __half><<<grid, 128, 0, st>>>(mean_rstd, gamma, beta, (const __half *)w, (const __half *)bias,
+                                                                        (__half *)w_folded, (__half *)b_folded, C, N);
+    else if (w_dtype == WF_F32 && out_dtype == WF_F16)
+        wf::groupnorm_fold_kernel<float, __half><<<grid, 128, 0, st>>>(mean_rstd, gamma, beta, (const float *)w, (const float *)bias,
+                                                                       (__half *)w_folded, (__half *)b_folded, C, N);
     else
         return WF_ERR_BAD_DTYPE;
     WF_LAUNCH_CHECK();
@@ -120,6 +127,9 @@ extern "C" int wf_gelu_inplace(void *x, int dtype, int64_t n, void *stream) {
     } else if (dtype == WF_BF16) {
         if (n % 8) return WF_ERR_BAD_SHAPE;
         wf::gelu_inplace_kernel<__nv_bfloat16><<<(unsigned)((n / 8 + 255) / 256), 256, 0, st>>>((__nv_bfloat16 *)x, n / 8);
+    } else if (dtype == WF_F16) {
+        if (n % 8) return WF_ERR_BAD_SHAPE;
+        wf::gelu_inplace_kernel<__half><<<(unsigned)((n / 8 + 255) / 256), 256, 0, st>>>((__half *)x, n / 8);
     } else {
         return WF_ERR_BAD_DTYPE;
     }
@@ -141,6 +151,8 @@ extern "C" int wf_residual_sum(const float *a, const float *b, const void *c, in
         wf::residual_sum_kernel<float><<<grid, 256, 0, st>>>(a, b, (const float *)c, bias, out, total4, C / 4);
     else if (c_dtype == WF_BF16)
         wf::residual_sum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a, b, (const __nv_bfloat16 *)c, bias, out, total4, C / 4);
+    else if (c_dtype == WF_F16)
+        wf::residual_sum_kernel<__half><<<grid, 256, 0, st>>>(a, b, (const __half *)c, bias, out, total4, C / 4);
     else
         return WF_ERR_BAD_DTYPE;
     WF_LAUNCH_CHECK();

@@ -8,6 +8,8 @@
 // Two layouts, each with a 16-byte vector kernel and a scalar fallback for shapes the vector path cannot take:
 //   NCDHW  : a thread turns 4 input rows x 8 samples into 4 coefficients of each of the 8 sub-bands.
 //   NDHWC  : a thread owns one 2x2x2 cell x one 16-byte channel packet (4 fp32 / 8 bf16 channels).
+#include <type_traits>
+
 #include "wf_common.cuh"
 
 namespace wf {
@@ -31,21 +33,33 @@ template <> struct Quad<__nv_bfloat16> {
         v[3] = __uint_as_float(r.y & 0xffff0000u);
     }
 };
+template <> struct Quad<__half> {
+    using raw = uint2;
+    __device__ static inline raw pack(const float (&v)[4]) {
+        __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+        return make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b));
+    }
+};
 
 // 8 consecutive elements of T -> fp32
-__device__ inline void load8(const float *p, float (&v)[8]) {
+__device__ inline void ld8s(const float *p, float (&v)[8]) {
     float4 a = ld_stream<float4>(p), b = ld_stream<float4>(p + 4);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
-__device__ inline void load8(const __nv_bfloat16 *p, float (&v)[8]) {
+__device__ inline void ld8s(const __nv_bfloat16 *p, float (&v)[8]) {
     uint4 a = ld_stream<uint4>(p);
     Pack<__nv_bfloat16>::unpack(a, v);
 }
-__device__ inline void store8(float *p, const float (&v)[8]) {
+__device__ inline void st8s(float *p, const float (&v)[8]) {
     st_stream(p, make_float4(v[0], v[1], v[2], v[3]));
     st_stream(p + 4, make_float4(v[4], v[5], v[6], v[7]));
 }
-__device__ inline void store8(__nv_bfloat16 *p, const float (&v)[8]) { st_stream(p, Pack<__nv_bfloat16>::pack(v)); }
+__device__ inline void st8s(__nv_bfloat16 *p, const float (&v)[8]) { st_stream(p, Pack<__nv_bfloat16>::pack(v)); }
+__device__ inline void ld8s(const __half *p, float (&v)[8]) {
+    uint4 a = ld_stream<uint4>(p);
+    Pack<__half>::unpack(a, v);
+}
+__device__ inline void st8s(__half *p, const float (&v)[8]) { st_stream(p, Pack<__half>::pack(v)); }
 
 // ------------------------------------------------------------------------------------------------ NCDHW -------
 template <typename T>
@@ -64,10 +78,10 @@ __global__ void __launch_bounds__(256) dwt_ncdhw_vec_kernel(const T *__restrict_
     const int H = 2 * h, W = 2 * w;
     const T *r00 = x + (((b * (2 * d) + 2 * z) * H + 2 * y) * (int64_t)W + 8 * xq);
     float f[4][8];
-    load8(r00, f[0]);
-    load8(r00 + W, f[1]);
-    load8(r00 + (int64_t)H * W, f[2]);
-    load8(r00 + (int64_t)H * W + W, f[3]);
+    ld8s(r00, f[0]);
+    ld8s(r00 + W, f[1]);
+    ld8s(r00 + (int64_t)H * W, f[2]);
+    ld8s(r00 + (int64_t)H * W + W, f[3]);
     float out[8][4];
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
@@ -115,6 +129,13 @@ template <typename T, int N> __device__ inline void words_to_f32(const Words<N *
     if constexpr (sizeof(T) == 4) {
 #pragma unroll
         for (int i = 0; i < N; ++i) v[i] = __uint_as_float(r.w[i]);
+    } else if constexpr (std::is_same<T, __half>::value) {
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&r.w[i]));
+            v[2 * i] = f.x;
+            v[2 * i + 1] = f.y;
+        }
     } else {
 #pragma unroll
         for (int i = 0; i < N / 2; ++i) {
@@ -128,6 +149,12 @@ template <typename T, int N> __device__ inline Words<N * (int)sizeof(T)> f32_to_
     if constexpr (sizeof(T) == 4) {
 #pragma unroll
         for (int i = 0; i < N; ++i) r.w[i] = __float_as_uint(v[i]);
+    } else if constexpr (std::is_same<T, __half>::value) {
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) {
+            __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+            r.w[i] = *reinterpret_cast<uint32_t *>(&h);
+        }
     } else {
 #pragma unroll
         for (int i = 0; i < N / 2; ++i) {
@@ -313,10 +340,9 @@ __global__ void __launch_bounds__(256) dwt_ndhwc_kernel(const T *__restrict__ x,
         for (int k = 0; k < 7; ++k) {
             if constexpr (VEC == 1 || sizeof(THF) == sizeof(T)) {
                 ChanIO<THF, VEC>::store(q + k * band_stride, o[k + 1]);
-            } else {  // fp32 packet of 4 channels -> 4 bf16 (8 bytes)
-                static_assert(VEC == 4, "mixed storage: fp32 in, bf16 details");
-                __nv_bfloat162 a = __floats2bfloat162_rn(o[k + 1][0], o[k + 1][1]), b = __floats2bfloat162_rn(o[k + 1][2], o[k + 1][3]);
-                st_stream(q + k * band_stride, make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b)));
+            } else {  // fp32 packet of 4 channels -> 4 sixteen-bit values (8 bytes)
+                static_assert(VEC == 4, "mixed storage: fp32 in, 16-bit details");
+                st_stream(q + k * band_stride, Quad<THF>::pack(o[k + 1]));
             }
         }
     }
@@ -480,6 +506,8 @@ extern "C" int wf_dwt3d_ncdhw(const void *x, void *ll, void *hf, int dtype, int6
     if (dtype == WF_F32) return dwt_ncdhw_launch<float>((const float *)x, (float *)ll, (float *)hf, n, D, H, W, hf_band_stride, st);
     if (dtype == WF_BF16)
         return dwt_ncdhw_launch<__nv_bfloat16>((const __nv_bfloat16 *)x, (__nv_bfloat16 *)ll, (__nv_bfloat16 *)hf, n, D, H, W, hf_band_stride, st);
+    if (dtype == WF_F16)
+        return dwt_ncdhw_launch<__half>((const __half *)x, (__half *)ll, (__half *)hf, n, D, H, W, hf_band_stride, st);
     return WF_ERR_BAD_DTYPE;
 }
 
@@ -493,6 +521,9 @@ extern "C" int wf_idwt3d_ncdhw(const void *ll, const void *hf, const void *gate,
     if (dtype == WF_BF16)
         return idwt_ncdhw_launch<__nv_bfloat16>((const __nv_bfloat16 *)ll, (const __nv_bfloat16 *)hf, (const __nv_bfloat16 *)gate,
                                                 (__nv_bfloat16 *)x, n, d, h, w, hf_band_stride, st);
+    if (dtype == WF_F16)
+        return idwt_ncdhw_launch<__half>((const __half *)ll, (const __half *)hf, (const __half *)gate, (__half *)x, n, d, h, w,
+                                         hf_band_stride, st);
     return WF_ERR_BAD_DTYPE;
 }
 
@@ -509,6 +540,10 @@ extern "C" int wf_dwt3d_ndhwc(const void *x, void *ll, void *hf, int dtype, int 
         return dwt_ndhwc_launch<float, bf>((const float *)x, (float *)ll, (bf *)hf, B, D, H, W, C, x_vox_stride, ll_vox_stride, hf_band_stride, st);
     if (dtype == WF_BF16 && hf_dtype == WF_BF16)
         return dwt_ndhwc_launch<bf, bf>((const bf *)x, (bf *)ll, (bf *)hf, B, D, H, W, C, x_vox_stride, ll_vox_stride, hf_band_stride, st);
+    if (dtype == WF_F32 && hf_dtype == WF_F16)
+        return dwt_ndhwc_launch<float, __half>((const float *)x, (float *)ll, (__half *)hf, B, D, H, W, C, x_vox_stride, ll_vox_stride, hf_band_stride, st);
+    if (dtype == WF_F16 && hf_dtype == WF_F16)
+        return dwt_ndhwc_launch<__half, __half>((const __half *)x, (__half *)ll, (__half *)hf, B, D, H, W, C, x_vox_stride, ll_vox_stride, hf_band_stride, st);
     return WF_ERR_BAD_DTYPE;
 }
 
@@ -525,5 +560,8 @@ extern "C" int wf_idwt3d_ndhwc(const void *ll, const void *hf, const void *gate,
     if (dtype == WF_BF16)
         return idwt_ndhwc_launch<__nv_bfloat16>((const __nv_bfloat16 *)ll, (const __nv_bfloat16 *)hf, (const __nv_bfloat16 *)gate,
                                                 (__nv_bfloat16 *)x, B, d, h, w, C, ll_vox_stride, hf_band_stride, x_vox_stride, st);
+    if (dtype == WF_F16)
+        return idwt_ndhwc_launch<__half>((const __half *)ll, (const __half *)hf, (const __half *)gate, (__half *)x, B, d, h, w, C,
+                                         ll_vox_stride, hf_band_stride, x_vox_stride, st);
     return WF_ERR_BAD_DTYPE;
 }

@@ -278,9 +278,9 @@ __global__ void __launch_bounds__(256, KP <= 4 ? 2 : 1) instnorm_apply_head_kern
 // up front (2 * CPV independent loads in flight per thread), everything else is thread-local: no shuffles, no barriers in
 // the loop.  Per-channel constants live in shared memory as two float4 per channel - (scale_x, scale_r, shift, 0) and the
 // K <= 4 head weights - read as warp-wide broadcasts.  grid = (blocks, B): a block stays inside one batch element.
-template <typename TO, int CPV>
+template <typename T, typename TO, int CPV>
 __global__ void __launch_bounds__(256) instnorm_apply_head_voxel_kernel(
-    const __nv_bfloat16 *__restrict__ x, const float *__restrict__ mr, const __nv_bfloat16 *__restrict__ res,
+    const T *__restrict__ x, const float *__restrict__ mr, const T *__restrict__ res,
     const float *__restrict__ res_mr, const float *__restrict__ hw, const float *__restrict__ hb, TO *__restrict__ out,
     int64_t S, int K, int64_t xs, int64_t rs, int act, float slope) {
     constexpr int C = CPV * 8;
@@ -302,8 +302,8 @@ __global__ void __launch_bounds__(256) instnorm_apply_head_voxel_kernel(
     __syncthreads();
     const float4 bias = make_float4(hb ? hb[0] : 0.f, (hb && K > 1) ? hb[1] : 0.f, (hb && K > 2) ? hb[2] : 0.f,
                                     (hb && K > 3) ? hb[3] : 0.f);
-    const __nv_bfloat16 *xb = x + (int64_t)b * S * xs;
-    const __nv_bfloat16 *rb = res != nullptr ? res + (int64_t)b * S * rs : nullptr;
+    const T *xb = x + (int64_t)b * S * xs;
+    const T *rb = res != nullptr ? res + (int64_t)b * S * rs : nullptr;
     for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < S; v += (int64_t)gridDim.x * blockDim.x) {
         uint4 xr[CPV], rr[CPV];
 #pragma unroll
@@ -316,8 +316,8 @@ __global__ void __launch_bounds__(256) instnorm_apply_head_voxel_kernel(
 #pragma unroll
         for (int j = 0; j < CPV; ++j) {
             float f[8], r[8];
-            Pack<__nv_bfloat16>::unpack(xr[j], f);
-            if (rb != nullptr) Pack<__nv_bfloat16>::unpack(rr[j], r);
+            Pack<T>::unpack(xr[j], f);
+            if (rb != nullptr) Pack<T>::unpack(rr[j], r);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const float4 n = s_norm[j * 8 + e], w = s_w[j * 8 + e];
@@ -342,14 +342,14 @@ __global__ void __launch_bounds__(256) instnorm_apply_head_voxel_kernel(
     }
 }
 
-template <typename TO>
-static bool apply_head_voxel_launch(const __nv_bfloat16 *x, const float *mr, const __nv_bfloat16 *res, const float *res_mr,
+template <typename T, typename TO>
+static bool apply_head_voxel_launch(const T *x, const float *mr, const T *res, const float *res_mr,
                                     const float *hw, const float *hb, TO *out, int B, int64_t S, int C, int K, int64_t xs,
                                     int64_t rs, int act, float slope, cudaStream_t st) {
     if (K > 4 || C % 8 != 0 || B > 65535 || (act == 2 && (slope < 0.f || slope > 1.f))) return false;
     const int64_t want = (S + 255) / 256;
     dim3 grid((unsigned)min(want, (int64_t)kNumSMs * 6), (unsigned)B);
-#define WF_HV(CPV_) instnorm_apply_head_voxel_kernel<TO, CPV_><<<grid, 256, 0, st>>>(x, mr, res, res_mr, hw, hb, out, S, K, xs, rs, act, slope)
+#define WF_HV(CPV_) instnorm_apply_head_voxel_kernel<T, TO, CPV_><<<grid, 256, 0, st>>>(x, mr, res, res_mr, hw, hb, out, S, K, xs, rs, act, slope)
     switch (C / 8) {
         case 2: WF_HV(2); break;
         case 4: WF_HV(4); break;
@@ -371,7 +371,7 @@ static int apply_head_launch(const T *x, const float *mr, const T *res, const fl
     if (C % V != 0 || C / V > 32 || K < 1 || K > 16) return WF_ERR_UNSUPPORTED;
     if (!aligned16(x) || (xs * e) % 16 != 0 || (res != nullptr && (!aligned16(res) || (rs * e) % 16 != 0))) return WF_ERR_MISALIGNED;
     if constexpr (sizeof(T) == 2) {
-        if (apply_head_voxel_launch<TO>(x, mr, res, res_mr, hw, hb, out, B, S, C, K, xs, rs, act, slope, st)) {
+        if (apply_head_voxel_launch<T, TO>(x, mr, res, res_mr, hw, hb, out, B, S, C, K, xs, rs, act, slope, st)) {
             WF_LAUNCH_CHECK();
             return WF_OK;
         }
@@ -476,6 +476,9 @@ extern "C" int wf_instnorm_apply_ndhwc(const void *x, const float *mean_rstd, co
     if (dtype == WF_F16 && y_dtype == WF_BF16)   // fp16 skip block writing its bf16 concat slice
         return wf::apply_launch<__half, bf>((const __half *)x, mean_rstd, (const __half *)res, res_mean_rstd, (bf *)y, B, S, C,
                                             x_vox_stride, res_vox_stride, y_vox_stride, act, slope, gamma, beta, st);
+    if (dtype == WF_F32 && y_dtype == WF_F16)    // fp32 block (TF32 convolutions) writing an fp16 concat slice
+        return wf::apply_launch<float, __half>((const float *)x, mean_rstd, (const float *)res, res_mean_rstd, (__half *)y, B, S,
+                                               C, x_vox_stride, res_vox_stride, y_vox_stride, act, slope, gamma, beta, st);
     return WF_ERR_BAD_DTYPE;
 }
 
@@ -497,5 +500,11 @@ extern "C" int wf_instnorm_apply_head_ndhwc(const void *x, const float *mean_rst
     if (dtype == WF_BF16 && out_dtype == WF_BF16)
         return wf::apply_head_launch<bf, bf>((const bf *)x, mean_rstd, (const bf *)res, res_mean_rstd, head_w, head_b,
                                              (bf *)out, B, S, C, K, x_vox_stride, res_vox_stride, act, slope, st);
+    if (dtype == WF_F16 && out_dtype == WF_F32)
+        return wf::apply_head_launch<__half, float>((const __half *)x, mean_rstd, (const __half *)res, res_mean_rstd, head_w,
+                                                    head_b, (float *)out, B, S, C, K, x_vox_stride, res_vox_stride, act, slope, st);
+    if (dtype == WF_F16 && out_dtype == WF_F16)
+        return wf::apply_head_launch<__half, __half>((const __half *)x, mean_rstd, (const __half *)res, res_mean_rstd, head_w,
+                                                     head_b, (__half *)out, B, S, C, K, x_vox_stride, res_vox_stride, act, slope, st);
     return WF_ERR_BAD_DTYPE;
 }

@@ -9,27 +9,6 @@
 
 namespace wf {
 
-template <typename T> struct Row16;  // 16-byte packets of T
-template <> struct Row16<float> {
-    static constexpr int V = 4;
-    __device__ static inline void load(const float *p, float (&v)[4]) {
-        const float4 t = *reinterpret_cast<const float4 *>(p);
-        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-    }
-    __device__ static inline void store(float *p, const float (&v)[4]) {
-        *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
-    }
-};
-template <> struct Row16<__nv_bfloat16> {
-    static constexpr int V = 8;
-    __device__ static inline void load(const __nv_bfloat16 *p, float (&v)[8]) {
-        Pack<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4 *>(p), v);
-    }
-    __device__ static inline void store(__nv_bfloat16 *p, const float (&v)[8]) {
-        *reinterpret_cast<uint4 *>(p) = Pack<__nv_bfloat16>::pack(v);
-    }
-};
-
 // GELU(x) = x * Phi(x) with the exact (erf) definition nn.GELU() uses.  erf by Abramowitz-Stegun 7.1.26 (|error| <=
 // 1.5e-7, i.e. fp32 round-off level): one reciprocal, one ex2 and six FMAs instead of erff's ~25 instructions - this
 // kernel is ALU-bound on the exact routine.
@@ -50,10 +29,10 @@ __device__ __forceinline__ float gelu_erf(float x) {
 
 // Each thread owns NV groups of 4 consecutive channels: channel index = (j * TPR + sub) * 4 + e.
 // y2 (optional) receives the same values as bf16 - the GEMM operand - while y keeps the fp32 copy the residual needs.
-template <typename TI, typename TO, int TPR, int NV>
+template <typename TI, typename TO, typename T2, int TPR, int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const TI *__restrict__ x, const float *__restrict__ gamma,
                                                         const float *__restrict__ beta, TO *__restrict__ y,
-                                                        __nv_bfloat16 *__restrict__ y2, int64_t rows, int C, int64_t xs,
+                                                        T2 *__restrict__ y2, int64_t rows, int C, int64_t xs,
                                                         int64_t ys, float eps, int gelu) {
     constexpr int RPB = 256 / TPR;  // rows per block
     const int sub = threadIdx.x % TPR;
@@ -66,15 +45,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const TI *__restrict__ x
     for (int j = 0; j < NV; ++j) {
         const int g = j * TPR + sub;
         if (live && g < groups) {
-            const TI *p = x + row * xs + g * 4;
-            if constexpr (sizeof(TI) == 4) {
-                const float4 t = *reinterpret_cast<const float4 *>(p);
-                v[j][0] = t.x; v[j][1] = t.y; v[j][2] = t.z; v[j][3] = t.w;
-            } else {
-                const uint2 t = *reinterpret_cast<const uint2 *>(p);
-                v[j][0] = __uint_as_float(t.x << 16); v[j][1] = __uint_as_float(t.x & 0xffff0000u);
-                v[j][2] = __uint_as_float(t.y << 16); v[j][3] = __uint_as_float(t.y & 0xffff0000u);
-            }
+            load4<TI>(x + row * xs + g * 4, v[j]);
             sum += (v[j][0] + v[j][1]) + (v[j][2] + v[j][3]);
         } else {
             v[j][0] = v[j][1] = v[j][2] = v[j][3] = 0.f;
@@ -110,28 +81,18 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const TI *__restrict__ x
             if (gamma != nullptr) t = fmaf(t, __ldg(gamma + g * 4 + e), beta != nullptr ? __ldg(beta + g * 4 + e) : 0.f);
             o4[e] = gelu ? gelu_erf(t) : t;
         }
-        TO *q = y + row * ys + g * 4;
-        if constexpr (sizeof(TO) == 4) {
-            *reinterpret_cast<float4 *>(q) = make_float4(o4[0], o4[1], o4[2], o4[3]);
-        } else {
-            __nv_bfloat162 a = __floats2bfloat162_rn(o4[0], o4[1]), b = __floats2bfloat162_rn(o4[2], o4[3]);
-            *reinterpret_cast<uint2 *>(q) = make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b));
-        }
-        if (y2 != nullptr) {
-            __nv_bfloat162 a = __floats2bfloat162_rn(o4[0], o4[1]), b = __floats2bfloat162_rn(o4[2], o4[3]);
-            *reinterpret_cast<uint2 *>(y2 + row * (int64_t)C + g * 4) =
-                make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b));
-        }
+        store4<TO>(y + row * ys + g * 4, o4);
+        if (y2 != nullptr) store4<T2>(y2 + row * (int64_t)C + g * 4, o4);
     }
 }
 
 // Wide variant (C % 8 == 0): a row is split into chunks of 8 channels; LPR lanes cooperate on a row and each lane owns
 // NCH chunks (chunk index = j * LPR + lane-in-row), i.e. 16-byte (bf16) / 2 x 16-byte (fp32) accesses, NCH * 8 values of
 // independent work per thread and log2(LPR) shuffle steps per statistic.  A warp covers 32 / LPR rows.
-template <typename TI, typename TO, int LPR, int NCH>
+template <typename TI, typename TO, typename T2, int LPR, int NCH>
 __global__ void __launch_bounds__(256) layernorm_wide_kernel(const TI *__restrict__ x, const float *__restrict__ gamma,
                                                              const float *__restrict__ beta, TO *__restrict__ y,
-                                                             __nv_bfloat16 *__restrict__ y2, int64_t rows, int C,
+                                                             T2 *__restrict__ y2, int64_t rows, int C,
                                                              int64_t xs, int64_t ys, float eps, int gelu) {
     constexpr int RPB = 256 / LPR;
     const int sub = threadIdx.x % LPR;
@@ -144,13 +105,7 @@ __global__ void __launch_bounds__(256) layernorm_wide_kernel(const TI *__restric
     for (int j = 0; j < NCH; ++j) {
         const int ch = j * LPR + sub;
         if (live && ch < chunks) {
-            const TI *p = x + row * xs + ch * 8;
-            if constexpr (sizeof(TI) == 4) {
-                const float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + 4);
-                v[j][0] = a.x; v[j][1] = a.y; v[j][2] = a.z; v[j][3] = a.w; v[j][4] = b.x; v[j][5] = b.y; v[j][6] = b.z; v[j][7] = b.w;
-            } else {
-                Pack<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4 *>(p), v[j]);
-            }
+            load8<TI>(x + row * xs + ch * 8, v[j]);
 #pragma unroll
             for (int e = 0; e < 8; ++e) sum += v[j][e];
         } else {
@@ -199,19 +154,13 @@ __global__ void __launch_bounds__(256) layernorm_wide_kernel(const TI *__restric
             if (gamma != nullptr) t = fmaf(t, g8[e], b8[e]);
             o8[e] = gelu ? gelu_erf(t) : t;
         }
-        TO *q = y + row * ys + ch * 8;
-        if constexpr (sizeof(TO) == 4) {
-            reinterpret_cast<float4 *>(q)[0] = make_float4(o8[0], o8[1], o8[2], o8[3]);
-            reinterpret_cast<float4 *>(q)[1] = make_float4(o8[4], o8[5], o8[6], o8[7]);
-        } else {
-            *reinterpret_cast<uint4 *>(q) = Pack<__nv_bfloat16>::pack(o8);
-        }
-        if (y2 != nullptr) *reinterpret_cast<uint4 *>(y2 + row * (int64_t)C + ch * 8) = Pack<__nv_bfloat16>::pack(o8);
+        store8<TO>(y + row * ys + ch * 8, o8);
+        if (y2 != nullptr) store8<T2>(y2 + row * (int64_t)C + ch * 8, o8);
     }
 }
 
-template <typename TI, typename TO>
-static bool layernorm_wide_launch(const TI *x, const float *gamma, const float *beta, TO *y, __nv_bfloat16 *y2, int64_t rows,
+template <typename TI, typename TO, typename T2>
+static bool layernorm_wide_launch(const TI *x, const float *gamma, const float *beta, TO *y, T2 *y2, int64_t rows,
                                   int C, int64_t xs, int64_t ys, float eps, int gelu, cudaStream_t st) {
     if (C % 8 != 0 || (xs * sizeof(TI)) % 16 != 0 || (ys * sizeof(TO)) % 16 != 0 || !aligned16(x) || !aligned16(y) ||
         (y2 != nullptr && !aligned16(y2)) || (gamma != nullptr && !aligned16(gamma)) || (beta != nullptr && !aligned16(beta)))
@@ -220,7 +169,7 @@ static bool layernorm_wide_launch(const TI *x, const float *gamma, const float *
 #define WF_LNW(LPR_, NCH_)                                                                                            \
     do {                                                                                                              \
         const int rpb = 256 / LPR_;                                                                                   \
-        layernorm_wide_kernel<TI, TO, LPR_, NCH_><<<(unsigned)((rows + rpb - 1) / rpb), 256, 0, st>>>(                \
+        layernorm_wide_kernel<TI, TO, T2, LPR_, NCH_><<<(unsigned)((rows + rpb - 1) / rpb), 256, 0, st>>>(                \
             x, gamma, beta, y, y2, rows, C, xs, ys, eps, gelu);                                                       \
         return true;                                                                                                  \
     } while (0)
@@ -234,10 +183,10 @@ static bool layernorm_wide_launch(const TI *x, const float *gamma, const float *
     return false;
 }
 
-template <typename TI, typename TO>
-static int layernorm_launch(const TI *x, const float *gamma, const float *beta, TO *y, __nv_bfloat16 *y2, int64_t rows,
+template <typename TI, typename TO, typename T2>
+static int layernorm_launch(const TI *x, const float *gamma, const float *beta, TO *y, T2 *y2, int64_t rows,
                             int C, int64_t xs, int64_t ys, float eps, int gelu, cudaStream_t st) {
-    if (layernorm_wide_launch<TI, TO>(x, gamma, beta, y, y2, rows, C, xs, ys, eps, gelu, st)) {
+    if (layernorm_wide_launch<TI, TO, T2>(x, gamma, beta, y, y2, rows, C, xs, ys, eps, gelu, st)) {
         WF_LAUNCH_CHECK();
         return WF_OK;
     }
@@ -248,7 +197,7 @@ static int layernorm_launch(const TI *x, const float *gamma, const float *beta, 
 #define WF_LN(TPR_, NV_)                                                                                         \
     do {                                                                                                         \
         const int rpb = 256 / TPR_;                                                                              \
-        layernorm_kernel<TI, TO, TPR_, NV_><<<(unsigned)((rows + rpb - 1) / rpb), 256, 0, st>>>(x, gamma, beta, y, y2, \
+        layernorm_kernel<TI, TO, T2, TPR_, NV_><<<(unsigned)((rows + rpb - 1) / rpb), 256, 0, st>>>(x, gamma, beta, y, y2, \
                                                                                                 rows, C, xs, ys, eps, gelu); \
     } while (0)
     if (groups <= 8) WF_LN(8, 1);
@@ -265,20 +214,30 @@ static int layernorm_launch(const TI *x, const float *gamma, const float *beta, 
 
 }  // namespace wf
 
-extern "C" int wf_layernorm_ndhwc(const void *x, const float *gamma, const float *beta, void *y, void *y2_bf16,
+extern "C" int wf_layernorm_ndhwc(const void *x, const float *gamma, const float *beta, void *y, void *y2, int y2_dtype,
                                   int in_dtype, int out_dtype, int64_t rows, int C, int64_t x_row_stride,
                                   int64_t y_row_stride, float eps, int gelu, void *stream) {
     if (!x || !y) return WF_ERR_NULL_POINTER;
     if (rows <= 0 || C <= 0 || x_row_stride < C || y_row_stride < C) return WF_ERR_BAD_SHAPE;
+    if (y2 != nullptr && y2_dtype != WF_BF16 && y2_dtype != WF_F16) return WF_ERR_BAD_DTYPE;
     cudaStream_t st = (cudaStream_t)stream;
     using bf = __nv_bfloat16;
-    if (in_dtype == WF_F32 && out_dtype == WF_F32)
-        return wf::layernorm_launch<float, float>((const float *)x, gamma, beta, (float *)y, (bf *)y2_bf16, rows, C, x_row_stride, y_row_stride, eps, gelu, st);
-    if (in_dtype == WF_F32 && out_dtype == WF_BF16)
-        return wf::layernorm_launch<float, bf>((const float *)x, gamma, beta, (bf *)y, (bf *)y2_bf16, rows, C, x_row_stride, y_row_stride, eps, gelu, st);
-    if (in_dtype == WF_BF16 && out_dtype == WF_BF16)
-        return wf::layernorm_launch<bf, bf>((const bf *)x, gamma, beta, (bf *)y, (bf *)y2_bf16, rows, C, x_row_stride, y_row_stride, eps, gelu, st);
-    if (in_dtype == WF_BF16 && out_dtype == WF_F32)
-        return wf::layernorm_launch<bf, float>((const bf *)x, gamma, beta, (float *)y, (bf *)y2_bf16, rows, C, x_row_stride, y_row_stride, eps, gelu, st);
+    using hf = __half;
+#define WF_LN_CASE(IC_, OC_, TI_, TO_)                                                                                      \
+    if (in_dtype == IC_ && out_dtype == OC_) {                                                                              \
+        if (y2 != nullptr && y2_dtype == WF_F16)                                                                            \
+            return wf::layernorm_launch<TI_, TO_, hf>((const TI_ *)x, gamma, beta, (TO_ *)y, (hf *)y2, rows, C, x_row_stride, \
+                                                      y_row_stride, eps, gelu, st);                                         \
+        return wf::layernorm_launch<TI_, TO_, bf>((const TI_ *)x, gamma, beta, (TO_ *)y, (bf *)y2, rows, C, x_row_stride,     \
+                                                  y_row_stride, eps, gelu, st);                                             \
+    }
+    WF_LN_CASE(WF_F32, WF_F32, float, float)
+    WF_LN_CASE(WF_F32, WF_BF16, float, bf)
+    WF_LN_CASE(WF_BF16, WF_BF16, bf, bf)
+    WF_LN_CASE(WF_BF16, WF_F32, bf, float)
+    WF_LN_CASE(WF_F32, WF_F16, float, hf)
+    WF_LN_CASE(WF_F16, WF_F16, hf, hf)
+    WF_LN_CASE(WF_F16, WF_F32, hf, float)
+#undef WF_LN_CASE
     return WF_ERR_BAD_DTYPE;
 }

@@ -61,12 +61,8 @@ __global__ void __launch_bounds__(256) patch_merge_ln_kernel(const float *__rest
         const float4 bt = __ldg(reinterpret_cast<const float4 *>(beta + c0));
         const float o0 = fmaf((v[i][0] - mean) * rstd, g.x, bt.x), o1 = fmaf((v[i][1] - mean) * rstd, g.y, bt.y);
         const float o2 = fmaf((v[i][2] - mean) * rstd, g.z, bt.z), o3 = fmaf((v[i][3] - mean) * rstd, g.w, bt.w);
-        if constexpr (sizeof(TO) == 4) {
-            *reinterpret_cast<float4 *>(yr + c0) = make_float4(o0, o1, o2, o3);
-        } else {
-            __nv_bfloat162 a = __floats2bfloat162_rn(o0, o1), c = __floats2bfloat162_rn(o2, o3);
-            *reinterpret_cast<uint2 *>(yr + c0) = make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&c));
-        }
+        const float o4[4] = {o0, o1, o2, o3};
+        store4<TO>(yr + c0, o4);
     }
 }
 
@@ -104,5 +100,7 @@ extern "C" int wf_patch_merge_layernorm(const float *x, const float *gamma, cons
         return wf::patch_merge_launch<float>(x, gamma, beta, (float *)y, B, D / 2, H / 2, W / 2, C, octants, eps, st);
     if (out_dtype == WF_BF16)
         return wf::patch_merge_launch<__nv_bfloat16>(x, gamma, beta, (__nv_bfloat16 *)y, B, D / 2, H / 2, W / 2, C, octants, eps, st);
+    if (out_dtype == WF_F16)
+        return wf::patch_merge_launch<__half>(x, gamma, beta, (__half *)y, B, D / 2, H / 2, W / 2, C, octants, eps, st);
     return WF_ERR_BAD_DTYPE;
 }

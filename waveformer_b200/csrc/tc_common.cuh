@@ -144,6 +144,42 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));  // first source -> upper half
     return r;
 }
+// 16-bit operand formats of kind::f16: bf16 (F16 = false) or fp16 (F16 = true: 10-bit mantissa at the same tensor rate)
+template <bool F16> __device__ __forceinline__ uint32_t pack_h16(float lo, float hi) {
+    uint32_t r;
+    if constexpr (F16)
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    else
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// per-channel-pair statistics straight from a packed 16-bit pair: s += v, q += v * v (the halves are widened inside the
+// fp32 add / FMA: FHADD / FHFMA, no unpack instructions)
+template <bool F16> __device__ __forceinline__ void stat_h16x2(uint32_t w, float &s0, float &s1, float &q0, float &q1) {
+    if constexpr (F16)
+        asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %4;\n\t"
+            "add.rn.f32.f16 %0, lo, %0;\n\tadd.rn.f32.f16 %1, hi, %1;\n\t"
+            "fma.rn.f32.f16 %2, lo, lo, %2;\n\tfma.rn.f32.f16 %3, hi, hi, %3;\n\t}"
+            : "+f"(s0), "+f"(s1), "+f"(q0), "+f"(q1) : "r"(w));
+    else
+        asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %4;\n\t"
+            "add.rn.f32.bf16 %0, lo, %0;\n\tadd.rn.f32.bf16 %1, hi, %1;\n\t"
+            "fma.rn.f32.bf16 %2, lo, lo, %2;\n\tfma.rn.f32.bf16 %3, hi, hi, %3;\n\t}"
+            : "+f"(s0), "+f"(s1), "+f"(q0), "+f"(q1) : "r"(w));
+}
+template <bool F16> __device__ __forceinline__ float2 unpack_h16(uint32_t w) {
+    if constexpr (F16) {
+        float a, b;
+        asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}" : "=f"(a), "=f"(b) : "r"(w));
+        return make_float2(a, b);
+    } else {
+        return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+    }
+}
+template <bool F16> __host__ __device__ constexpr uint32_t instr_desc_h16(int M, int N, bool b_mn_major) {
+    // A / B format fields [7,10) and [10,13): 0 = F16, 1 = BF16
+    return F16 ? (instr_desc_bf16(M, N, b_mn_major) & ~((7u << 7) | (7u << 10))) : instr_desc_bf16(M, N, b_mn_major);
+}
 
 }  // namespace tc
 }  // namespace wf

@@ -35,9 +35,9 @@ template <typename T, int N> __device__ __forceinline__ void load_n(const T *p, 
     } else {
 #pragma unroll
         for (int i = 0; i < N / 4; ++i) {
-            const uint2 t = reinterpret_cast<const uint2 *>(p)[i];
-            v[4 * i] = __uint_as_float(t.x << 16); v[4 * i + 1] = __uint_as_float(t.x & 0xffff0000u);
-            v[4 * i + 2] = __uint_as_float(t.y << 16); v[4 * i + 3] = __uint_as_float(t.y & 0xffff0000u);
+            float f[4];
+            load4<T>(p + 4 * i, f);
+            v[4 * i] = f[0]; v[4 * i + 1] = f[1]; v[4 * i + 2] = f[2]; v[4 * i + 3] = f[3];
         }
     }
 }
@@ -51,8 +51,8 @@ template <typename T, int N> __device__ __forceinline__ void store_n(T *p, const
     } else {
 #pragma unroll
         for (int i = 0; i < N / 4; ++i) {
-            __nv_bfloat162 a = __floats2bfloat162_rn(v[4 * i], v[4 * i + 1]), b = __floats2bfloat162_rn(v[4 * i + 2], v[4 * i + 3]);
-            reinterpret_cast<uint2 *>(p)[i] = make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b));
+            const float f[4] = {v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]};
+            store4<T>(p + 4 * i, f);
         }
     }
 }
@@ -151,7 +151,6 @@ __device__ __forceinline__ AxisPair axis_pair(int o, float scale, int in, int al
     return r;
 }
 
-template <typename T> __device__ __forceinline__ void load4(const T *p, float (&v)[4]) { load_n<T, 4>(p, v); }
 
 // grid: x = ceil((W / 2) * (C / 4) / 128), y = H / 2, z = B * D / 2; 128 threads (~148 registers each)
 template <typename TS, typename TB, typename TO>
@@ -307,5 +306,12 @@ extern "C" int wf_upsample_trilinear_add_ndhwc(const void *const *srcs, const in
         return wf::upsample_launch<bf, float, float>(a, (const float *)base, (float *)y, B, D, H, W, C, base_vox_stride, y_vox_stride, st);
     if (src_dtype == WF_F32 && io_dtype == WF_BF16)
         return wf::upsample_launch<float, bf, bf>(a, (const bf *)base, (bf *)y, B, D, H, W, C, base_vox_stride, y_vox_stride, st);
+    using hf = __half;
+    if (src_dtype == WF_F16 && io_dtype == WF_F16)
+        return wf::upsample_launch<hf, hf, hf>(a, (const hf *)base, (hf *)y, B, D, H, W, C, base_vox_stride, y_vox_stride, st);
+    if (src_dtype == WF_F16 && io_dtype == WF_F32)
+        return wf::upsample_launch<hf, float, float>(a, (const float *)base, (float *)y, B, D, H, W, C, base_vox_stride, y_vox_stride, st);
+    if (src_dtype == WF_F32 && io_dtype == WF_F16)
+        return wf::upsample_launch<float, hf, hf>(a, (const hf *)base, (hf *)y, B, D, H, W, C, base_vox_stride, y_vox_stride, st);
     return WF_ERR_BAD_DTYPE;
 }

@@ -23,7 +23,8 @@ inline int cuda_fail(cudaError_t e) {
         if (_e != cudaSuccess) return ::wf::cuda_fail(_e);       \
     } while (0)
 
-#define WF_LAUNCH_CHECK() WF_CUDA_CHECK(cudaPeekAtLastError())
+// cudaGetLastError (not Peek): a failed launch must not poison every later call of the library
+#define WF_LAUNCH_CHECK() WF_CUDA_CHECK(cudaGetLastError())
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -93,6 +94,45 @@ template <> struct Pack<__half> {   // fp16 activations of the skip blocks (prec
         return make_uint4(w[0], w[1], w[2], w[3]);
     }
 };
+
+// 4 / 8 consecutive elements of T <-> fp32 registers with plain (cached) vector accesses: fp32 16 / 2 x 16 bytes,
+// 16-bit types 8 / 16 bytes
+template <typename T> __device__ inline void load4(const T *p, float (&v)[4]) {
+    if constexpr (sizeof(T) == 4) {
+        const float4 t = *reinterpret_cast<const float4 *>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+        const uint2 t = *reinterpret_cast<const uint2 *>(p);
+        float f[8];
+        Pack<T>::unpack(make_uint4(t.x, t.y, 0u, 0u), f);
+        v[0] = f[0]; v[1] = f[1]; v[2] = f[2]; v[3] = f[3];
+    }
+}
+template <typename T> __device__ inline void store4(T *p, const float (&v)[4]) {
+    if constexpr (sizeof(T) == 4) {
+        *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+        const float f[8] = {v[0], v[1], v[2], v[3], 0.f, 0.f, 0.f, 0.f};
+        const uint4 t = Pack<T>::pack(f);
+        *reinterpret_cast<uint2 *>(p) = make_uint2(t.x, t.y);
+    }
+}
+template <typename T> __device__ inline void load8(const T *p, float (&v)[8]) {
+    if constexpr (sizeof(T) == 4) {
+        const float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+        Pack<T>::unpack(*reinterpret_cast<const uint4 *>(p), v);
+    }
+}
+template <typename T> __device__ inline void store8(T *p, const float (&v)[8]) {
+    if constexpr (sizeof(T) == 4) {
+        reinterpret_cast<float4 *>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4 *>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+        *reinterpret_cast<uint4 *>(p) = Pack<T>::pack(v);
+    }
+}
 
 // streaming (evict-first) 16-byte global accesses: every byte of the Haar kernels is touched exactly once
 template <typename R> __device__ inline R ld_stream(const void *p) { return __ldcs(reinterpret_cast<const R *>(p)); }

@@ -83,7 +83,7 @@ class UnetResBlock(nn.Module):
         48 -> 48 channels on rows of 128 voxels (the two 128^3 blocks): one producer / consumer tcgen05 kernel that
         normalises its input while staging it and reduces the statistics of its output in its epilogue."""
         c2 = self.conv2.conv
-        if (c1.dtype == torch.bfloat16 and c2.weight.dtype == torch.bfloat16 and c2.in_channels == 48 and c2.out_channels == 48
+        if (c1.dtype in ops.HALF_TYPES and c2.weight.dtype == c1.dtype and c2.in_channels == 48 and c2.out_channels == 48
                 and c2.kernel_size == (3, 3, 3) and c2.stride == (1, 1, 1) and c2.bias is None and c1.shape[-1] == 128
                 and c1.stride(1) == 1 and self.norm1.eps == self.norm2.eps):
             if s1 is None:
@@ -95,9 +95,27 @@ class UnetResBlock(nn.Module):
     def _c4_fused(self, inp: torch.Tensor) -> bool:
         c1 = self.conv1.conv
         return (self.downsample and c1.in_channels == 4 and c1.kernel_size == (3, 3, 3) and c1.stride == (1, 1, 1)
-                and c1.weight.dtype == torch.bfloat16 and c1.out_channels % 8 == 0 and 2 * c1.out_channels <= 128
+                and c1.weight.dtype in ops.HALF_TYPES and c1.out_channels % 8 == 0 and 2 * c1.out_channels <= 128
                 and self.conv3.conv.stride == (1, 1, 1) and self.norm1.eps == self.norm3.eps
-                and inp.dtype in (torch.float32, torch.bfloat16))
+                and inp.dtype in (torch.float32, c1.weight.dtype))
+
+    @staticmethod
+    def _head_fusable(x: torch.Tensor, head) -> bool:
+        """Limits of wf_instnorm_apply_head_ndhwc (instnorm.cu): at most 16 output channels, at most 32 sixteen-byte
+        packets per voxel, and the (activation, logits) type pairs it is instantiated for.  Anything else takes
+        InstanceNorm + activation followed by the library 1^3 convolution - same result, one more pass."""
+        k, c = head[0].shape[0], x.shape[1]
+        vec = 4 if x.dtype == torch.float32 else 8
+        od = head[2] or torch.float32
+        pairs = {(torch.float32, torch.float32), (torch.bfloat16, torch.float32), (torch.bfloat16, torch.bfloat16),
+                 (torch.float16, torch.float32), (torch.float16, torch.float16)}
+        return k <= 16 and c % vec == 0 and c // vec <= 32 and (x.dtype, od) in pairs
+
+    @staticmethod
+    def _head_unfused(y: torch.Tensor, head) -> torch.Tensor:
+        w, b, od = head
+        out = F.conv3d(y, w.to(y.dtype), None if b is None else b.to(y.dtype))
+        return out if od is None or out.dtype == od else out.to(od)
 
     def forward(self, inp: torch.Tensor, out_buf: torch.Tensor = None, head=None) -> torch.Tensor:
         """``out_buf`` (inference only): a [B, D, H, W, C] channels-last destination - typically the skip half of a
@@ -121,15 +139,17 @@ class UnetResBlock(nn.Module):
                     res = F.linear(inp.permute(0, 2, 3, 4, 1), c3.weight.view(c3.out_channels, c3.in_channels)).permute(0, 4, 1, 2, 3)
                 else:
                     res = self.conv3(inp)
-                if head is not None:
+                if head is not None and self._head_fusable(out, head):
                     return ops.instance_norm_act_head(out, head[0], head[1], "leakyrelu", 0.01, res=res, res_norm=True,
                                                       eps=self.norm2.eps, out_dtype=head[2], stats=s2)
-                return ops.instance_norm_act(out, "leakyrelu", 0.01, res=res, res_norm=True, eps=self.norm2.eps,
-                                             out=out_buf, stats=s2)
-            if head is not None:
+                y = ops.instance_norm_act(out, "leakyrelu", 0.01, res=res, res_norm=True, eps=self.norm2.eps,
+                                          out=out_buf, stats=s2)
+                return y if head is None else self._head_unfused(y, head)
+            if head is not None and self._head_fusable(out, head):
                 return ops.instance_norm_act_head(out, head[0], head[1], "leakyrelu", 0.01, res=inp, eps=self.norm2.eps,
                                                   out_dtype=head[2], stats=s2)
-            return ops.instance_norm_act(out, "leakyrelu", 0.01, res=inp, eps=self.norm2.eps, out=out_buf, stats=s2)
+            y = ops.instance_norm_act(out, "leakyrelu", 0.01, res=inp, eps=self.norm2.eps, out=out_buf, stats=s2)
+            return y if head is None else self._head_unfused(y, head)
         out = self.lrelu(self.norm1(self.conv1(inp)))
         out = self.norm2(self.conv2(out))
         res = self.norm3(self.conv3(inp)) if self.downsample else inp
@@ -175,7 +195,8 @@ class UnetrBasicBlock(nn.Module):
             if inp.dtype != sd:
                 inp = inp.to(sd)
             y = self.layer(inp) if out_buf is None else self.layer(inp, out_buf)
-            return y if out_buf is not None or y.dtype == torch.bfloat16 else y.to(torch.bfloat16)
+            od = getattr(self, "io_dtype", None) or torch.bfloat16      # activation type of the surrounding U-Net
+            return y if out_buf is not None or y.dtype == od else y.to(od)
         return self.layer(inp) if out_buf is None else self.layer(inp, out_buf)
 
 
@@ -194,7 +215,7 @@ class UnetrUpBlock(nn.Module):
         tc = self.transp_conv.conv
         if cat_buf is not None:
             c = tc.out_channels
-            if (inp.dtype == torch.bfloat16 and tc.kernel_size == (2, 2, 2) and tc.stride == (2, 2, 2) and tc.bias is None
+            if (inp.dtype in ops.HALF_TYPES and tc.weight.dtype == inp.dtype and tc.kernel_size == (2, 2, 2) and tc.stride == (2, 2, 2) and tc.bias is None
                     and tc.in_channels % 16 == 0 and c % 16 == 0 and tc.in_channels <= 512 and inp.stride(1) == 1):
                 # kernel == stride: one tensor-core GEMM that scatters its result into the concat buffer in place
                 ops.conv_transpose3d_k2s2(inp.permute(0, 2, 3, 4, 1), tc.weight, out=cat_buf[..., :c])

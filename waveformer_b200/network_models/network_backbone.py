@@ -176,12 +176,7 @@ class Waveformer(nn.Module):
             with torch.cuda.stream(st):
                 skips[i] = block(out, cats[i][..., c:])
 
-        enc = self.waveformer_encoder
-        enc._stage_hook = on_stage
-        try:
-            outs, outs_hf = enc(x_in)
-        finally:
-            enc._stage_hook = None
+        outs, outs_hf = self.waveformer_encoder(x_in, stage_hook=on_stage)
         bb, _, dd, hh, ww = outs[0].shape
         comb = torch.empty((bb, dd, hh, ww, 3 * f[0]), dtype=dtype, device=dev)       # [up4 | up3 | dec2]
         s1.wait_stream(cur)

@@ -352,7 +352,7 @@ class Block(nn.Module):
         if cd is not None and cd != y.dtype:
             # fp32 stream: LayerNorm writes the fp32 copy (CCF_FFN's own residual, wave_helper.py:293) and the bf16 GEMM
             # operand in one pass; y + n + ffn(n) is accumulated in fp32
-            n, nop = _ln(self.norm2, y, also_bf16=True)
+            n, nop = _ln(self.norm2, y, also_bf16=cd)
             f, fb = self.mlp.ffn_fused(n, nop, defer_bias=True)
             y = ops.residual_sum(y, n, f, fb)          # y + n + ffn(n) + fc bias: one pass
         else:

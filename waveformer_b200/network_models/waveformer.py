@@ -83,7 +83,9 @@ class MultiscaleTransformer(nn.Module):
         state = torch.load(pretrained, map_location='cpu')
         self.load_state_dict(state['model'] if 'model' in state else state, strict=False)
 
-    def forward_features(self, x_rgb: torch.Tensor, normalize: bool = True) -> Tuple[List[torch.Tensor], List]:
+    def forward_features(self, x_rgb: torch.Tensor, normalize: bool = True, stage_hook=None) -> Tuple[List[torch.Tensor], List]:
+        """``stage_hook(i, out)`` (optional, inference wiring of ``Waveformer._forward_forked``) is called on the current
+        stream right after stage i's output exists; it is an argument, not module state, so the forward stays re-entrant."""
         outs, outs_hf = [], []
         pe_dtype = self.patch_embed.proj.weight.dtype
         t = self.pos_drop(self.patch_embed(x_rgb if x_rgb.dtype == pe_dtype else x_rgb.to(pe_dtype)))
@@ -104,16 +106,15 @@ class MultiscaleTransformer(nn.Module):
                 o = F.layer_norm(t, [t.shape[-1]]) if normalize else t
                 o = o if o.dtype == od else o.to(od)
             outs.append(o.permute(0, 4, 1, 2, 3))
-            hook = getattr(self, "_stage_hook", None)      # Waveformer's forked inference wiring starts the stage's skip
-            if hook is not None:                           # block on a side stream as soon as the output exists
-                hook(s, outs[-1])
+            if stage_hook is not None:                     # start the stage's skip block on a side stream right away
+                stage_hook(s, outs[-1])
             if s < 3:
                 outs_hf.append(hf if hf is not None else ())
                 t = getattr(self, f"downsample_{s + 1}")(t)
         return outs, outs_hf
 
-    def forward(self, x_rgb: torch.Tensor):
-        return self.forward_features(x_rgb)
+    def forward(self, x_rgb: torch.Tensor, stage_hook=None):
+        return self.forward_features(x_rgb, stage_hook=stage_hook)
 
     def flops(self) -> int:
         return 0

@@ -23,15 +23,17 @@ def _count(n: int = 1) -> None:
     LAUNCHES += n
 
 
-def _dtype_code(t: torch.Tensor, allow_f16: bool = False) -> int:
-    if t.dtype == torch.float32:
-        return 0
-    if t.dtype == torch.bfloat16:
-        return 1
-    if allow_f16 and t.dtype == torch.float16:      # InstanceNorm kernels only (fp16 skip blocks of the precision policy)
-        return 2
-    # same convention as ptwt, which raises ValueError for dtypes it does not support
-    raise ValueError(f"waveformer_b200: dtype {t.dtype} not supported (float32 or bfloat16)")
+_CODES = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}      # wf_dtype: WF_F32, WF_BF16, WF_F16
+HALF_TYPES = (torch.bfloat16, torch.float16)                          # the two 16-bit storage / tensor-core operand formats
+
+
+def _dtype_code(t, allow_f16: bool = True) -> int:
+    dt = t if isinstance(t, torch.dtype) else t.dtype
+    code = _CODES.get(dt)
+    if code is None or (code == 2 and not allow_f16):
+        # same convention as ptwt, which raises ValueError for dtypes it does not support
+        raise ValueError(f"waveformer_b200: dtype {dt} not supported (float32, bfloat16 or float16)")
+    return code
 
 
 def _need_cuda(*tensors: Optional[torch.Tensor]) -> torch.device:
@@ -454,7 +456,7 @@ def dwconv3d_channels_last_stats(x: torch.Tensor, w27: torch.Tensor, bias: Optio
         raise ValueError("expected [B, D, H, W, C]")
     x = x.contiguous()
     B, D, H, W, C = x.shape
-    if x.dtype == torch.bfloat16 and C % 8 == 0 and W >= 8 and w27.dtype == torch.float32 and tuple(w27.shape) == (27, C) \
+    if x.dtype in HALF_TYPES and C % 8 == 0 and W >= 8 and w27.dtype == torch.float32 and tuple(w27.shape) == (27, C) \
             and w27.is_contiguous():
         y = torch.empty_like(x)
         sums = torch.empty(B * C * 2, dtype=torch.float64, device=dev)
@@ -496,7 +498,7 @@ def _instnorm_stats(v: torch.Tensor, vs: int, eps: float) -> torch.Tensor:
     sums = torch.empty(B * C * 2, dtype=torch.float64, device=dev)
     mr = torch.empty(B * C * 2, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        st = _lib.lib().wf_instnorm_stats_ndhwc(v.data_ptr(), sums.data_ptr(), mr.data_ptr(), _dtype_code(v, True), B,
+        st = _lib.lib().wf_instnorm_stats_ndhwc(v.data_ptr(), sums.data_ptr(), mr.data_ptr(), _dtype_code(v), B,
                                                 D * H * W, C, vs, float(eps), _stream(dev))
     _lib.check(st, "wf_instnorm_stats_ndhwc")
     _count(2)
@@ -533,12 +535,13 @@ def instance_norm_act(x: torch.Tensor, act: str = "none", slope: float = 0.01, r
         out = torch.empty((B, D, H, W, C), dtype=x.dtype, device=dev)
     ys = _voxel_stride(out)
     if ys is None or tuple(out.shape) != (B, D, H, W, C) or not (
-            out.dtype == x.dtype or (x.dtype in (torch.float32, torch.float16) and out.dtype == torch.bfloat16)):
-        raise ValueError("out must be a voxel-dense [B, D, H, W, C] tensor of x's dtype (or bf16 for fp32 / fp16 x)")
+            out.dtype == x.dtype or (x.dtype in (torch.float32, torch.float16) and out.dtype == torch.bfloat16)
+            or (x.dtype == torch.float32 and out.dtype == torch.float16)):
+        raise ValueError("out must be a voxel-dense [B, D, H, W, C] tensor of x's dtype (or 16-bit for fp32 x, bf16 for fp16 x)")
     with torch.cuda.device(dev):
         st = _lib.lib().wf_instnorm_apply_ndhwc(v.data_ptr(), mr.data_ptr(), _ptr(rv), _ptr(rmr), _ptr(gamma), _ptr(beta),
-                                                out.data_ptr(), _ACT[act], float(slope), _dtype_code(x, True),
-                                                _dtype_code(out, True), B, D * H * W, C, vs, rs, ys, _stream(dev))
+                                                out.data_ptr(), _ACT[act], float(slope), _dtype_code(x),
+                                                _dtype_code(out), B, D * H * W, C, vs, rs, ys, _stream(dev))
     _lib.check(st, "wf_instnorm_apply_ndhwc")
     _count()
     return out.permute(0, 4, 1, 2, 3)
@@ -576,37 +579,50 @@ def instance_norm_act_head(x: torch.Tensor, head_w: torch.Tensor, head_b: Option
     return out.permute(0, 4, 1, 2, 3)
 
 
+def _pack_cached(cache: dict, key, tag, owner: torch.Tensor, build):
+    """Repacked-weight cache shared by the tensor-core kernels: an entry is valid while its weak reference still points
+    at the very same parameter object and the parameter has not been modified (``tag``); dead entries are evicted
+    whenever the cache has grown since the last sweep, so it never outlives the models it served."""
+    hit = cache.get(key)
+    if hit is None or hit[0]() is not owner or hit[1] != tag:
+        if len(cache) >= 64:
+            for k in [k for k, v in cache.items() if v[0]() is None]:
+                del cache[k]
+        hit = (weakref.ref(owner), tag, build())
+        cache[key] = hit
+    return hit[2]
+
+
 _K3_PACK = {}
 
 
 def conv3d_k3_c48(x: torch.Tensor, weight: torch.Tensor, in_stats: Optional[torch.Tensor] = None, slope: float = 0.01,
                   eps: float = 1e-5, out: Optional[torch.Tensor] = None):
-    """3^3 convolution 48 -> 48 (padding 1, no bias) of ``x[B, 48, D, H, 128]`` (bf16, channels-last-3d strides) on the
-    tensor cores.  With ``in_stats`` (the (mean, rstd) tensor of x) the input is InstanceNorm'd + LeakyReLU'd while it is
+    """3^3 convolution 48 -> 48 (padding 1, no bias) of ``x[B, 48, D, H, 128]`` (bf16 or fp16, channels-last-3d strides) on
+    the tensor cores.  With ``in_stats`` (the (mean, rstd) tensor of x) the input is InstanceNorm'd + LeakyReLU'd while it is
     staged, i.e. the call computes ``conv(lrelu(IN(x)))``.  Returns ``(y, stats)``: y bf16 [B, 48, D, H, 128] channels-last
     and the (mean, rstd) statistics of y for the following ``instance_norm_act(stats=...)``."""
     dev = _need_cuda(x, weight, in_stats, out)
     v, vs = _ndhwc_view(x)
     B, D, H, W, C = v.shape
-    if v.dtype != torch.bfloat16 or C != 48 or W != 128 or tuple(weight.shape) != (48, 48, 3, 3, 3):
-        raise ValueError("conv3d_k3_c48: bf16 [B, 48, D, H, 128] input and a [48, 48, 3, 3, 3] weight")
-    key = id(weight)
-    tag = (weight._version, weight.data_ptr(), weight.dtype)
-    hit = _K3_PACK.get(key)
-    if hit is None or hit[0]() is not weight or hit[1] != tag:
+    if v.dtype not in HALF_TYPES or C != 48 or W != 128 or tuple(weight.shape) != (48, 48, 3, 3, 3):
+        raise ValueError("conv3d_k3_c48: bf16 / fp16 [B, 48, D, H, 128] input and a [48, 48, 3, 3, 3] weight")
+    fmt = v.dtype
+
+    def build():
         w = weight.detach().float().permute(2, 3, 4, 0, 1).reshape(3, 3, 3, 48, 3, 2, 8)   # [dz, dy, dx, n, ks, chunk, e]
-        pack = w.permute(0, 2, 4, 5, 1, 3, 6).contiguous().to(torch.bfloat16)              # [dz, dx, ks, chunk, dy, n, e]
-        hit = (weakref.ref(weight), tag, pack)
-        _K3_PACK[key] = hit
+        return w.permute(0, 2, 4, 5, 1, 3, 6).contiguous().to(fmt)                         # [dz, dx, ks, chunk, dy, n, e]
+
+    pack = _pack_cached(_K3_PACK, (id(weight), fmt), (weight._version, weight.data_ptr(), weight.dtype), weight, build)
     if out is None:
-        out = torch.empty((B, D, H, W, 48), dtype=torch.bfloat16, device=dev)
+        out = torch.empty((B, D, H, W, 48), dtype=fmt, device=dev)
     ys = _voxel_stride(out)
-    if ys is None or tuple(out.shape) != (B, D, H, W, 48) or out.dtype != torch.bfloat16:
-        raise ValueError("out must be a voxel-dense bf16 [B, D, H, 128, 48] tensor")
+    if ys is None or tuple(out.shape) != (B, D, H, W, 48) or out.dtype != fmt:
+        raise ValueError("out must be a voxel-dense [B, D, H, 128, 48] tensor of the input's 16-bit type")
     sums = torch.empty(2 * B * 48, dtype=torch.float64, device=dev)
     mr = torch.empty(2 * B * 48, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        st = _lib.lib().wf_conv3d_k3_c48_in_stats(v.data_ptr(), hit[2].data_ptr(), out.data_ptr(), sums.data_ptr(),
+        st = _lib.lib().wf_conv3d_k3_c48_in_stats(v.data_ptr(), _dtype_code(v), pack.data_ptr(), out.data_ptr(), sums.data_ptr(),
                                                   mr.data_ptr(), _ptr(in_stats), float(slope), float(eps), B, D, H, W, vs,
                                                   ys, _stream(dev))
     _lib.check(st, "wf_conv3d_k3_c48_in_stats")
@@ -618,11 +634,11 @@ _CT_PACK = {}
 
 
 def conv_transpose3d_k2s2(x: torch.Tensor, weight: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """ConvTranspose3d(k=2, s=2, bias=False) of channels-last bf16 ``x[B, D, H, W, Cin]`` with ``weight[Cin, Cout, 2, 2, 2]``
+    """ConvTranspose3d(k=2, s=2, bias=False) of channels-last bf16 / fp16 ``x[B, D, H, W, Cin]`` with ``weight[Cin, Cout, 2, 2, 2]``
     into ``out[B, 2D, 2H, 2W, Cout]`` (may be a channel slice of a wider channels-last buffer)."""
     dev = _need_cuda(x, weight, out)
-    if x.dtype != torch.bfloat16 or x.dim() != 5:
-        raise ValueError("conv_transpose3d_k2s2 takes channels-last bf16 [B, D, H, W, Cin]")
+    if x.dtype not in HALF_TYPES or x.dim() != 5:
+        raise ValueError("conv_transpose3d_k2s2 takes channels-last bf16 / fp16 [B, D, H, W, Cin]")
     xs = _voxel_stride(x)
     if xs is None:
         x = x.contiguous()
@@ -631,20 +647,16 @@ def conv_transpose3d_k2s2(x: torch.Tensor, weight: torch.Tensor, out: Optional[t
     if tuple(weight.shape[2:]) != (2, 2, 2) or weight.shape[0] != Cin:
         raise ValueError("weight must be [Cin, Cout, 2, 2, 2]")
     Cout = weight.shape[1]
-    key = id(weight)
-    tag = (weight._version, weight.data_ptr(), weight.dtype)
-    hit = _CT_PACK.get(key)
-    if hit is None or hit[0]() is not weight or hit[1] != tag:
-        pack = weight.detach().permute(2, 3, 4, 1, 0).reshape(8 * Cout, Cin).to(torch.bfloat16).contiguous()
-        hit = (weakref.ref(weight), tag, pack)
-        _CT_PACK[key] = hit
+    fmt = x.dtype
+    pack = _pack_cached(_CT_PACK, (id(weight), fmt), (weight._version, weight.data_ptr(), weight.dtype), weight,
+                        lambda: weight.detach().permute(2, 3, 4, 1, 0).reshape(8 * Cout, Cin).to(fmt).contiguous())
     if out is None:
         out = torch.empty((B, 2 * D, 2 * H, 2 * W, Cout), dtype=x.dtype, device=dev)
     ys = _voxel_stride(out)
     if ys is None or tuple(out.shape) != (B, 2 * D, 2 * H, 2 * W, Cout) or out.dtype != x.dtype:
-        raise ValueError("out must be a voxel-dense [B, 2D, 2H, 2W, Cout] bf16 tensor")
+        raise ValueError("out must be a voxel-dense [B, 2D, 2H, 2W, Cout] tensor of x's type")
     with torch.cuda.device(dev):
-        st = _lib.lib().wf_convtranspose3d_k2s2_ndhwc(x.data_ptr(), hit[2].data_ptr(), out.data_ptr(), 1, B, D, H, W, Cin,
+        st = _lib.lib().wf_convtranspose3d_k2s2_ndhwc(x.data_ptr(), pack.data_ptr(), out.data_ptr(), _dtype_code(x), B, D, H, W, Cin,
                                                       Cout, xs, ys, _stream(dev))
     _lib.check(st, "wf_convtranspose3d_k2s2_ndhwc")
     _count()
@@ -654,28 +666,29 @@ def conv_transpose3d_k2s2(x: torch.Tensor, weight: torch.Tensor, out: Optional[t
 _C4_PACK = {}
 
 
-def _pack_c4_weights(w3x3: torch.Tensor, w1x1: Optional[torch.Tensor]) -> torch.Tensor:
-    """[n0, 4, 3, 3, 3] (+ [n1, 4, 1, 1, 1]) -> bf16 [n0 + n1, 112] for wf_conv3d_c4_in_stats; cached per weight version."""
-    key = (id(w3x3), None if w1x1 is None else id(w1x1))
+def _pack_c4_weights(w3x3: torch.Tensor, w1x1: Optional[torch.Tensor], fmt: torch.dtype) -> torch.Tensor:
+    """[n0, 4, 3, 3, 3] (+ [n1, 4, 1, 1, 1]) -> ``fmt`` [n0 + n1, 112] for wf_conv3d_c4_in_stats; cached per weight version."""
+    key = (id(w3x3), None if w1x1 is None else id(w1x1), fmt)
     tag = (w3x3._version, w3x3.data_ptr(), None if w1x1 is None else (w1x1._version, w1x1.data_ptr()))
-    hit = _C4_PACK.get(key)
-    if hit is not None and hit[0]() is w3x3 and hit[1] == tag:
-        return hit[2]
-    n0 = w3x3.shape[0]
-    n1 = 0 if w1x1 is None else w1x1.shape[0]
-    pack = torch.zeros((n0 + n1, 112), dtype=torch.float32, device=w3x3.device)
-    pack[:n0, :108] = w3x3.detach().float().permute(0, 2, 3, 4, 1).reshape(n0, 108)
-    if n1:
-        pack[n0:, 52:56] = w1x1.detach().float().reshape(n1, 4)
-    pack = pack.to(torch.bfloat16).contiguous()
-    _C4_PACK[key] = (weakref.ref(w3x3), tag, pack)
-    return pack
+
+    def build():
+        n0 = w3x3.shape[0]
+        n1 = 0 if w1x1 is None else w1x1.shape[0]
+        pack = torch.zeros((n0 + n1, 112), dtype=torch.float32, device=w3x3.device)
+        pack[:n0, :108] = w3x3.detach().float().permute(0, 2, 3, 4, 1).reshape(n0, 108)
+        if n1:
+            pack[n0:, 52:56] = w1x1.detach().float().reshape(n1, 4)
+        return pack.to(fmt).contiguous()
+
+    return _pack_cached(_C4_PACK, key, tag, w3x3, build)
 
 
-def conv3d_c4_in_stats(x: torch.Tensor, w3x3: torch.Tensor, w1x1: Optional[torch.Tensor] = None, eps: float = 1e-5):
+def conv3d_c4_in_stats(x: torch.Tensor, w3x3: torch.Tensor, w1x1: Optional[torch.Tensor] = None, eps: float = 1e-5,
+                       out_dtype: Optional[torch.dtype] = None):
     """3^3 conv (+ optional 1^3 conv) of a 4-channel volume with fused InstanceNorm statistics.  ``x``: [B, 4, D, H, W]
-    with channels-last-3d strides (fp32 or bf16).  Returns ``(y0, stats0, y1, stats1)``; ``y*`` are bf16 [B, n, D, H, W]
-    channels-last-3d, ``stats*`` the (mean, rstd) tensors ``instance_norm_act(stats=...)`` takes."""
+    with channels-last-3d strides (fp32, bf16 or fp16).  Returns ``(y0, stats0, y1, stats1)``; ``y*`` are [B, n, D, H, W]
+    channels-last-3d in ``out_dtype`` (bf16 / fp16 = the tensor-core operand format; default: the weight's 16-bit type,
+    else x's, else bf16), ``stats*`` the (mean, rstd) tensors ``instance_norm_act(stats=...)`` takes."""
     dev = _need_cuda(x, w3x3, w1x1)
     v, vs = _ndhwc_view(x)
     B, D, H, W, C = v.shape
@@ -685,14 +698,17 @@ def conv3d_c4_in_stats(x: torch.Tensor, w3x3: torch.Tensor, w1x1: Optional[torch
         raise ValueError("weights must be [n0, 4, 3, 3, 3] and [n1, 4, 1, 1, 1]")
     n0 = w3x3.shape[0]
     n1 = 0 if w1x1 is None else w1x1.shape[0]
-    pack = _pack_c4_weights(w3x3, w1x1)
-    y0 = torch.empty((B, D, H, W, n0), dtype=torch.bfloat16, device=dev)
-    y1 = torch.empty((B, D, H, W, n1), dtype=torch.bfloat16, device=dev) if n1 else None
+    fmt = out_dtype or (w3x3.dtype if w3x3.dtype in HALF_TYPES else (v.dtype if v.dtype in HALF_TYPES else torch.bfloat16))
+    if fmt not in HALF_TYPES or (v.dtype != torch.float32 and v.dtype != fmt):
+        raise ValueError("conv3d_c4_in_stats: 16-bit result format; x must be fp32 or already in that format")
+    pack = _pack_c4_weights(w3x3, w1x1, fmt)
+    y0 = torch.empty((B, D, H, W, n0), dtype=fmt, device=dev)
+    y1 = torch.empty((B, D, H, W, n1), dtype=fmt, device=dev) if n1 else None
     sums = torch.empty(2 * B * (n0 + n1), dtype=torch.float64, device=dev)
     mr0 = torch.empty(2 * B * n0, dtype=torch.float32, device=dev)
     mr1 = torch.empty(2 * B * n1, dtype=torch.float32, device=dev) if n1 else None
     with torch.cuda.device(dev):
-        st = _lib.lib().wf_conv3d_c4_in_stats(v.data_ptr(), _dtype_code(v), pack.data_ptr(), y0.data_ptr(), n0, n0, _ptr(y1),
+        st = _lib.lib().wf_conv3d_c4_in_stats(v.data_ptr(), _dtype_code(v), _dtype_code(fmt), pack.data_ptr(), y0.data_ptr(), n0, n0, _ptr(y1),
                                               n1, n1, sums.data_ptr(), sums.data_ptr() + 16 * B * n0, mr0.data_ptr(),
                                               _ptr(mr1), float(eps), B, D, H, W, _stream(dev))
     _lib.check(st, "wf_conv3d_c4_in_stats")
@@ -731,8 +747,9 @@ def f32_cached(p: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 def layer_norm_cl(x: torch.Tensor, weight: Optional[torch.Tensor], bias: Optional[torch.Tensor], eps: float,
                   gelu: bool = False, out_dtype: Optional[torch.dtype] = None, also_bf16: bool = False):
     """LayerNorm over the last dim of a channels-last tensor (any leading dims, last-dim stride 1), optional GELU;
-    ``out_dtype`` may differ from the input's (fp32 stream -> bf16 operand).  ``also_bf16`` returns ``(y, y_bf16)``:
-    the same result also rounded to bf16 by the same pass (GEMM operand + fp32 copy for the residual)."""
+    ``out_dtype`` may differ from the input's (fp32 stream -> 16-bit operand).  ``also_bf16`` (True = bf16, or a 16-bit
+    dtype) returns ``(y, y16)``: the same result also rounded to 16 bits by the same pass (GEMM operand + fp32 copy for
+    the residual)."""
     dev = _need_cuda(x, weight, bias)
     C = x.shape[-1]
     if x.stride(-1) != 1:
@@ -741,10 +758,12 @@ def layer_norm_cl(x: torch.Tensor, weight: Optional[torch.Tensor], bias: Optiona
     rows = x2.shape[0]
     out_dtype = out_dtype or x.dtype
     y = torch.empty(x.shape, dtype=out_dtype, device=dev)
-    y2 = torch.empty(x.shape, dtype=torch.bfloat16, device=dev) if also_bf16 else None
+    dt2 = torch.bfloat16 if also_bf16 is True else also_bf16
+    y2 = torch.empty(x.shape, dtype=dt2, device=dev) if also_bf16 else None
     with torch.cuda.device(dev):
         st = _lib.lib().wf_layernorm_ndhwc(x2.data_ptr(), _ptr(f32_cached(weight)), _ptr(f32_cached(bias)), y.data_ptr(),
-                                           _ptr(y2), _dtype_code(x2), _dtype_code(y), rows, C, x2.stride(0), C,
+                                           _ptr(y2), _dtype_code(dt2) if also_bf16 else 1, _dtype_code(x2), _dtype_code(y),
+                                           rows, C, x2.stride(0), C,
                                            float(eps), int(gelu), _stream(dev))
     _lib.check(st, "wf_layernorm_ndhwc")
     _count()
@@ -801,7 +820,7 @@ def patch_merge_layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Ten
                            out_dtype: torch.dtype) -> Optional[torch.Tensor]:
     """Octant gather + LayerNorm over the 8C concatenation in one kernel: ``x[B, D, H, W, C]`` fp32 ->
     ``[B, D/2, H/2, W/2, 8C]``.  Returns None when the geometry is outside the kernel (the caller keeps torch.cat + LN)."""
-    if (x.dtype != torch.float32 or not x.is_contiguous() or x.dim() != 5 or out_dtype not in (torch.float32, torch.bfloat16)
+    if (x.dtype != torch.float32 or not x.is_contiguous() or x.dim() != 5 or out_dtype not in _CODES
             or gamma is None or beta is None or gamma.dtype != torch.float32 or beta.dtype != torch.float32):
         return None
     B, D, H, W, C = x.shape
@@ -854,7 +873,24 @@ def upsample_trilinear_add(srcs, size, base: Optional[torch.Tensor] = None, alig
     return y
 
 # ============================================================================================ sliding window ====
-def sw_gather(vol: torch.Tensor, starts: torch.Tensor, roi, dtype: torch.dtype, channels_last: bool) -> torch.Tensor:
+def _flip_mask(flip) -> int:
+    """``flip``: 0..7 bit mask (bit 0 / 1 / 2 = mirror z / y / x) or an iterable of spatial axes (0, 1, 2)."""
+    if flip is None:
+        return 0
+    if isinstance(flip, int):
+        m = flip
+    else:
+        m = 0
+        for a in flip:
+            if a not in (0, 1, 2):
+                raise ValueError(f"mirror axes are spatial axes 0, 1, 2; got {a}")
+            m |= 1 << a
+    if not 0 <= m <= 7:
+        raise ValueError(f"flip mask must be in 0..7, got {m}")
+    return m
+
+
+def sw_gather(vol: torch.Tensor, starts: torch.Tensor, roi, dtype: torch.dtype, channels_last: bool, flip=0) -> torch.Tensor:
     dev = _need_cuda(vol, starts)
     if vol.dtype != torch.float32 or vol.dim() != 5:
         raise ValueError("volume must be fp32 [Bv, C, D, H, W]")
@@ -866,14 +902,14 @@ def sw_gather(vol: torch.Tensor, starts: torch.Tensor, roi, dtype: torch.dtype, 
     win = torch.empty(shape, dtype=dtype, device=dev)
     with torch.cuda.device(dev):
         st = _lib.lib().wf_sw_gather(vol.data_ptr(), win.data_ptr(), starts.data_ptr(), n, _dtype_code(win),
-                                     int(channels_last), C, D, H, W, r0, r1, r2, _stream(dev))
+                                     int(channels_last), C, D, H, W, r0, r1, r2, _flip_mask(flip), _stream(dev))
     _lib.check(st, "wf_sw_gather")
     _count()
     return win
 
 
 def sw_accumulate(seg: torch.Tensor, acc: torch.Tensor, starts: torch.Tensor, gz, gy, gx, floor_w: float,
-                  channels_last: bool) -> None:
+                  channels_last: bool, flip=0) -> None:
     dev = _need_cuda(seg, acc, starts, gz, gy, gx)
     seg = seg.contiguous()
     n = seg.shape[0]
@@ -886,22 +922,30 @@ def sw_accumulate(seg: torch.Tensor, acc: torch.Tensor, starts: torch.Tensor, gz
         raise ValueError("accumulator must be contiguous fp32 [Bv, K, D, H, W]")
     with torch.cuda.device(dev):
         st = _lib.lib().wf_sw_accumulate(seg.data_ptr(), acc.data_ptr(), starts.data_ptr(), gz.data_ptr(), gy.data_ptr(),
-                                         gx.data_ptr(), float(floor_w), n, _dtype_code(seg), int(channels_last), K, D, H,
-                                         W, r0, r1, r2, _stream(dev))
+                                         gx.data_ptr(), float(floor_w), n, _dtype_code(seg), int(channels_last), K, D,
+                                         H, W, r0, r1, r2, _flip_mask(flip), _stream(dev))
     _lib.check(st, "wf_sw_accumulate")
     _count()
 
 
 def sw_finalize(acc: torch.Tensor, all_starts: torch.Tensor, gz, gy, gx, floor_w: float, roi,
-                labels: Optional[torch.Tensor] = None, z_range: Optional[Tuple[int, int]] = None) -> None:
-    """Divide the accumulated volume(s) by the recomputed count map, in place; ``z_range`` limits it to planes [a, b)."""
-    dev = _need_cuda(acc, all_starts, gz, gy, gx, labels)
+                labels: Optional[torch.Tensor] = None, z_range: Optional[Tuple[int, int]] = None, flip=0,
+                dst: Optional[torch.Tensor] = None, dst_scale: float = 1.0, dst_add: bool = False) -> None:
+    """Divide the accumulated volume(s) by the recomputed count map, in place; ``z_range`` limits it to planes [a, b).
+    ``all_starts``: int32 [n, 4] window table (slot, z, y, x); slot -1 = the window exists in every volume of ``acc``.
+    ``dst`` (optional, acc's shape): ``dst = (dst if dst_add else 0) + dst_scale * normalised`` (mirror-TTA mean)."""
+    dev = _need_cuda(acc, all_starts, gz, gy, gx, labels, dst)
     Bv, K, D, H, W = acc.shape
     r0, r1, r2 = roi
     za, zb = (0, D) if z_range is None else (int(z_range[0]), int(z_range[1]))
+    if not acc.is_contiguous() or acc.dtype != torch.float32:
+        raise ValueError("accumulator must be contiguous fp32 [Bv, K, D, H, W]")
+    if dst is not None and (dst.shape != acc.shape or dst.dtype != torch.float32 or not dst.is_contiguous()):
+        raise ValueError("dst must be a contiguous fp32 tensor of the accumulator's shape")
     with torch.cuda.device(dev):
         st = _lib.lib().wf_sw_finalize(acc.data_ptr(), _ptr(labels), all_starts.data_ptr(), all_starts.shape[0],
                                        gz.data_ptr(), gy.data_ptr(), gx.data_ptr(), float(floor_w), Bv, K, D, H, W, r0,
-                                       r1, r2, za, zb, _stream(dev))
+                                       r1, r2, za, zb, _flip_mask(flip), _ptr(dst), float(dst_scale), int(bool(dst_add)),
+                                       _stream(dev))
     _lib.check(st, "wf_sw_finalize")
     _count()

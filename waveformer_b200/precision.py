@@ -30,37 +30,49 @@ from .network_models.waveformer import MultiscaleTransformer
 
 __all__ = ["prepare_inference"]
 
+# every attribute prepare_inference may leave on a module (instance attributes only; cleared before each preparation)
+_POLICY_ATTRS = ("compute_dtype", "out_dtype", "hf_dtype", "skip_dtype", "tf32", "logits_dtype", "io_dtype")
+
 
 def prepare_inference(model: nn.Module, dtype: torch.dtype = torch.bfloat16, *, attention: str = "fp16",
-                      fp32_stream: bool = True, skip_blocks: str = "fp16") -> nn.Module:
+                      fp32_stream: bool = True, skip_blocks: str = "fp16", storage: str = "fp16") -> nn.Module:
     """Put ``model`` (a ``Waveformer``) into inference form on its current device.
 
     ``dtype=torch.float32``: nothing is rounded (parity mode, <= 1e-4 against the reference).
-    ``dtype=torch.bfloat16``: the policy in the module docstring.  ``attention`` selects the operand format of the
-    window-attention GEMMs ("fp16", "bf16" or "fp32" = CUDA-core kernels); ``fp32_stream=False`` gives the plain
-    all-bf16 model (``model.to(torch.bfloat16)``), kept for the precision study.  ``skip_blocks`` is the format of the
-    residual blocks encoder2..4: "tf32" (fp32 storage, TF32 tensor-core convolutions), "fp16" (fp16 storage and operands:
-    the same 10-bit mantissa at the cost of the bf16 kernels) or "bf16" (no special treatment).
+    ``dtype=torch.bfloat16``: the 16-bit policy in the module docstring.  ``storage`` is the 16-bit format of activations,
+    weights and tensor-core operands outside attention: "fp16" (default; 10-bit mantissa at the speed of bf16 - every such
+    tensor is InstanceNorm'd / LayerNorm'd or one GEMM away from it, so fp16's range is no concern) or "bf16" (round 1's
+    policy: 3x the logit error, 0.3 % more argmax flips).  ``attention`` selects the operand format of the
+    window-attention GEMMs ("fp16", "bf16" or "fp32" = CUDA-core kernels); ``fp32_stream=False`` gives the plain all-bf16
+    model (``model.to(torch.bfloat16)``), kept for the precision study.  ``skip_blocks`` (only with ``storage="bf16"``) is the
+    format of the residual blocks encoder2..4: "tf32" (fp32 storage, TF32 tensor-core convolutions), "fp16" (fp16 storage and
+    operands) or "bf16" (no special treatment).
     """
     model.eval()
+    # a model may be re-prepared (bf16 -> fp32 parity run -> bf16): start from a clean slate, every time
+    for m in model.modules():
+        for name in _POLICY_ATTRS:
+            if name in m.__dict__:
+                delattr(m, name)
     if dtype == torch.float32:
         model.float()
-        for m in model.modules():
-            for name in ("compute_dtype", "out_dtype"):
-                if hasattr(m, name):
-                    delattr(m, name)
         return model.to(memory_format=torch.channels_last_3d)
     if dtype != torch.bfloat16:
-        raise ValueError("prepare_inference supports float32 and bfloat16")
+        raise ValueError("prepare_inference supports float32 and bfloat16 (= the 16-bit policy)")
     if attention not in ("fp16", "bf16", "fp32"):
         raise ValueError("attention must be 'fp16', 'bf16' or 'fp32'")
     if skip_blocks not in ("tf32", "fp16", "bf16"):
         raise ValueError("skip_blocks must be 'tf32', 'fp16' or 'bf16'")
+    if storage not in ("fp16", "bf16"):
+        raise ValueError("storage must be 'fp16' or 'bf16'")
     if not fp32_stream:
         return model.to(torch.bfloat16).to(memory_format=torch.channels_last_3d)
+    h16 = torch.float16 if storage == "fp16" else torch.bfloat16
+    if storage == "fp16":
+        skip_blocks = "fp16"                           # they are ordinary members of the fp16 U-Net then
     attn_dtype = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[attention]
-    keep = set()                                       # parameters that stay fp32 (never rounded through bf16)
-    half = set()                                       # parameters stored as fp16 (skip blocks, skip_blocks="fp16")
+    keep = set()                                       # parameters that stay fp32 (never rounded to 16 bits)
+    half = set()                                       # parameters stored as fp16 inside a bf16 model (skip blocks)
 
     def keep_fp32(mod: nn.Module) -> None:
         for t in list(mod.parameters()) + list(mod.buffers()):
@@ -77,26 +89,25 @@ def prepare_inference(model: nn.Module, dtype: torch.dtype = torch.bfloat16, *, 
             keep_fp32(m)                                # the normalisation kernels read gamma / beta as fp32
         if isinstance(m, CCF_FFN):
             keep_fp32(m.dwconv)                         # depthwise stencils: the kernel takes fp32 taps
-            m.compute_dtype = torch.bfloat16            # bf16 GEMM operands, fp32 stream in / out
+            m.compute_dtype = h16                       # 16-bit GEMM operands, fp32 stream in / out
         elif isinstance(m, ProjectionUpsample):
             keep_fp32(m.conv1[1])
         elif isinstance(m, PatchMergingV2):
-            m.compute_dtype = torch.bfloat16
+            m.compute_dtype = h16
         elif isinstance(m, Block):
-            m.hf_dtype = torch.bfloat16                 # detail bands go to the bf16 decoder
+            m.hf_dtype = h16                            # detail bands go to the 16-bit decoder
         elif isinstance(m, MultiscaleTransformer):
-            # stage outputs 0..2 feed the fp32 skip blocks below, the last one the bf16 bottleneck
-            m.out_dtype = [torch.float32, torch.float32, torch.float32, torch.bfloat16]
+            # stage outputs 0..2 feed the skip blocks below (cast on entry), the last one the 16-bit bottleneck
+            m.out_dtype = [torch.float32, torch.float32, torch.float32, h16]
     # The residual blocks that turn the encoder's stage outputs into the decoder's skip connections (encoder2..4: identity
-    # shortcut, 48 / 96 / 192 channels at 64^3 / 32^3 / 16^3, 5 % of the step) keep a 10-bit mantissa: rounding their input
-    # and activations to bf16 alone accounts for half of the bf16 logit error (scripts/precision_zones.py: max-rel 1.7e-2
-    # -> 0.9e-2 with these blocks lifted), because their identity shortcut carries the stage output straight into every
-    # decoder level.  fp16 storage + fp16 tensor-core convolutions (default) or fp32 storage + TF32 convolutions measure
-    # the same error (0.97e-2 vs 1.02e-2); fp16 runs at the bf16 kernels' speed.  Their last kernel writes the bf16 concat slice.
+    # shortcut, 48 / 96 / 192 channels at 64^3 / 32^3 / 16^3, 5 % of the step) are the most rounding-sensitive convolutions
+    # of the network (scripts/precision_policy_r02.py: in bf16 they alone are half of the logit error, in fp16 still the
+    # largest single zone), because their identity shortcut carries the stage output straight into every decoder level.
     for name in ("encoder2", "encoder3", "encoder4"):
         blk = getattr(model, name, None)
         if blk is None:
             continue
+        blk.io_dtype = h16
         if skip_blocks == "bf16":
             blk.skip_dtype = torch.bfloat16             # only the fp32 stage output is cast on the way in
         elif skip_blocks == "tf32":
@@ -109,5 +120,5 @@ def prepare_inference(model: nn.Module, dtype: torch.dtype = torch.bfloat16, *, 
     model.logits_dtype = torch.float32                  # the fused output head stores its fp32 accumulators
     for t in list(model.parameters()) + list(model.buffers()):
         if t.is_floating_point():
-            t.data = t.data.float() if id(t) in keep else t.data.to(torch.float16 if id(t) in half else torch.bfloat16)
+            t.data = t.data.float() if id(t) in keep else t.data.to(torch.float16 if id(t) in half else h16)
     return model.to(memory_format=torch.channels_last_3d)

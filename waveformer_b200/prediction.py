@@ -3,8 +3,11 @@ the sliding-window inferer, the resampling of the averaged probabilities and the
 kept on the device.
 
 The reference moves each of the 2^k mirrored predictions to the host (``.cpu()`` at ``prediction.py:126,135-155``) and
-averages there - 8 device->host copies of a 143 MB volume per case with the default ``mirror_axes=[0, 1, 2]``.  Here the
-flips are device index transforms, the accumulator is one fp32 device volume, and a single copy leaves the GPU.
+averages there - 8 device->host copies of a 143 MB volume per case with the default ``mirror_axes=[0, 1, 2]`` - after
+materialising ``torch.flip(x)`` and ``torch.flip(output)`` for every pass.  Here a mirrored pass is an index transform
+inside the stitching kernels (``wf_sw_gather`` reads the mirrored window, ``wf_sw_accumulate`` scatters it back
+un-mirrored, ``wf_sw_finalize`` folds the running mean into its normalisation), so no flipped copy of the input or of a
+prediction is ever built, the accumulator is one fp32 device volume, and a single copy leaves the GPU.
 """
 from __future__ import annotations
 
@@ -35,8 +38,24 @@ class Predictor:
             model.to(device)
         x = x.to(device, non_blocking=True)
         axes = self.mirror_axes
+        from .inferers import SlidingWindowInferer
+        wi = self.window_infer
+        fused = (isinstance(wi, SlidingWindowInferer) and wi.device is None and wi.process_group is None
+                 and not (torch.distributed.is_available() and torch.distributed.is_initialized())
+                 and all(int(s) >= int(r) for s, r in zip(x.shape[2:], wi.roi_size)))
         with torch.no_grad():
-            pred = self.window_infer(x, model, **kwargs).clone()       # the inferer may reuse its accumulator
+            if fused and axes is not None:
+                assert max(axes) <= x.dim() - 3, "mirror_axes does not match the dimension of the input!"
+                # same subsets in the same order as the reference (prediction.py:134-155); every mirrored pass adds
+                # result / 2^k to the running mean from inside its normalisation kernel
+                scale = 1.0 / (2 ** len(axes))
+                pred = wi(x, model, **kwargs)
+                pred.mul_(scale)
+                for r in range(1, len(axes) + 1):
+                    for subset in itertools.combinations(sorted(axes), r):
+                        wi(x, model, flip=subset, into=(pred, scale, True), **kwargs)
+                return pred
+            pred = self.window_infer(x, model, **kwargs).clone()       # a foreign inferer may reuse its buffer
             if axes is not None:
                 assert max(axes) <= x.dim() - 3, "mirror_axes does not match the dimension of the input!"
                 # subsets in the reference's order: (0), (1), (2), (0,1), (0,2), (1,2), (0,1,2)   prediction.py:134-155
