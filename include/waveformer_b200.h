@@ -115,6 +115,21 @@ int wf_window_attn_fwd(const void *x, int x_dtype, const void *qkv_w, const void
                        void *workspace, size_t workspace_bytes, int dtype, int B, int D1, int H1, int W1, int C,
                        int heads, int ws, float scale, void *stream);
 
+/* Error-compensated fp16 tensor-core attention (tensor-core geometry only: wf_window_attn_tc_supported).  Every GEMM
+ * operand that feeds the softmax is carried as a pair hi = fp16(v), lo = fp16(v - hi): x and the weights in both Linear
+ * layers (passed as two fp16 images each, qkv_w_hi / qkv_w_lo [3C, C], proj_w_hi / proj_w_lo [C, C]), q and k between the
+ * QKV projection and the scores, O between the core and the output projection; products are accumulated as
+ * hi*hi + lo*hi + hi*lo (three tcgen05.mma instead of one, on a tensor pipe that is ~5 % busy in this operator), biases are
+ * fp32, x and out are fp32.  Same semantics as wf_window_attn_fwd (attention.py:83-104); what changes is that the
+ * scores are exact to ~2^-21 |q||k| instead of 2^-11: with plain fp16 operands the score error, amplified by the softmax,
+ * is the largest single term of the 16-bit policy's logit error.  P and v remain plain fp16 (their errors average out
+ * over the 512 keys).  bias_img: the fp16 image of wf_relpos_bias_image. */
+size_t wf_window_attn_split_workspace_bytes(int B, int D1, int H1, int W1, int C, int heads, int ws);
+int wf_window_attn_fwd_split(const float *x, const void *qkv_w_hi, const void *qkv_w_lo, const float *qkv_b,
+                             const void *proj_w_hi, const void *proj_w_lo, const float *proj_b, const void *bias_img,
+                             float *out, void *workspace, size_t workspace_bytes, int B, int D1, int H1, int W1, int C,
+                             int heads, int ws, float scale, void *stream);
+
 /* Gradient of the attention core between the two Linear layers (training; reference network_models/attention.py:87-101,
  * differentiated): S = (scale q) k^T + table[index], P = softmax(S), O = P v.
  * workspace : the fp32 workspace wf_window_attn_fwd(dtype = WF_F32) left behind (q pre-scaled, k, v head-major

@@ -86,3 +86,38 @@ def test_fp16_operands_fp32_stream(sd, stage, c, h, b_):
     m.compute_dtype, m.out_dtype = torch.bfloat16, torch.float32
     y16 = _run(m, x, "tc")
     assert y16.dtype == torch.float32 and max_rel(y16.cpu().reshape(b_, 512, c), g[f"out_{c}"]) < 2e-2
+
+
+@pytest.mark.parametrize("stage,c,h,b_", [(0, 48, 3, 3), (1, 96, 6, 2), (2, 192, 12, 1), (3, 384, 24, 1)])
+def test_compensated_fp16_operands(sd, stage, c, h, b_):
+    """attention="fp16x2" of the precision policy: hi / lo fp16 pairs for x, the weights, q, k and O (three tcgen05.mma per
+    product).  The scores are then exact to fp32 level and what is left is the fp16 rounding of P and v: an order of
+    magnitude closer to the fp32 reference than plain fp16 operands (tolerance 4e-4 vs 3e-3)."""
+    from waveformer_b200.network_models import Attention
+    g = load_npz("attention_ws8.npz")
+    m = Attention(c, num_heads=h, qkv_bias=True, window_size=8, img_size=(8, 8, 8)).eval()
+    m.load_state_dict(sub_state(sd, f"waveformer_encoder.block{stage + 1}.1.attn"), strict=True)
+    m = m.cuda()
+    m.compute_dtype, m.out_dtype, m.split_operands = torch.float16, torch.float32, True
+    x = seeded_randn((b_, 512, c), 100 + stage).cuda().reshape(b_, 8, 8, 8, c)
+    y = _run(m, x, "tc")
+    assert y.dtype == torch.float32 and torch.isfinite(y).all()
+    err = max_rel(y.cpu().reshape(b_, 512, c), g[f"out_{c}"])
+    m.split_operands = False
+    plain = max_rel(_run(m, x, "tc").cpu().reshape(b_, 512, c), g[f"out_{c}"])
+    assert err < 4e-4 and err < 0.5 * plain, (err, plain)
+
+
+@pytest.mark.parametrize("grid,batch", [((32, 32, 32), 2), ((8, 16, 24), 1)])
+def test_compensated_path_many_windows(sd, grid, batch):
+    """Persistent loop of the compensated core: single Q / K buffer refilled after the score MMAs, V double-buffered."""
+    from waveformer_b200.network_models import Attention
+    p = "waveformer_encoder.block1.0.attn"
+    m = Attention(48, num_heads=3, qkv_bias=True, window_size=8, img_size=(8, 8, 8)).eval()
+    m.load_state_dict(sub_state(sd, p), strict=True)
+    m = m.cuda()
+    m.compute_dtype, m.out_dtype, m.split_operands = torch.float16, torch.float32, True
+    x = seeded_randn((batch,) + grid + (48,), 36)
+    got = _run(m, x.cuda(), "tc").cpu()
+    simt = _run(m, x.cuda(), "simt").cpu()             # fp32 CUDA-core kernels on the same input
+    assert max_rel(got, simt) < 4e-4

@@ -129,7 +129,7 @@ def test_error_conventions():
     with pytest.raises(ValueError):
         ops.dwt3d(torch.zeros(1, 3, 4, 4, device="cuda"))            # odd extent
     with pytest.raises(ValueError):
-        ops.dwt3d(torch.zeros(1, 4, 4, 4, device="cuda", dtype=torch.float16))
+        ops.dwt3d(torch.zeros(1, 4, 4, 4, device="cuda", dtype=torch.float64))       # unsupported dtype (ptwt: ValueError too)
     with pytest.raises(RuntimeError):
         ops.dwt3d(torch.zeros(1, 4, 4, 4))                            # CPU tensor: no fallback
     from waveformer_b200.network_models import WaveletTransform3D
@@ -147,7 +147,7 @@ def test_autograd_is_the_adjoint():
     assert float((x.grad - want).abs().max()) < 1e-6
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
 def test_full_size_roundtrip_properties(dtype):
     """BASELINE config 2 size (2x48x128^3): size-independent properties instead of an oracle run - Parseval and
     reconstruction, plus a sampled comparison against the closed form."""
@@ -159,9 +159,10 @@ def test_full_size_roundtrip_properties(dtype):
     e_out = float(ll.float().pow(2).sum(dtype=torch.float64)) + float(hf.float().pow(2).sum(dtype=torch.float64))
     assert abs(e_in - e_out) < (1e-5 if dtype == torch.float32 else 2e-3) * e_in
     rec = ops.idwt3d(ll, hf)
-    err = float((rec.float() - x.float()).abs().max())
-    assert err < (1e-5 if dtype == torch.float32 else 0.15)
+    err = float((rec.float() - x.float()).abs().max()) / float(x.float().abs().max())
+    # north star: 16-bit reconstruction within 2e-2 relative (two roundings of O(|x|) coefficients); fp32 at round-off level
+    assert err < {torch.float32: 2e-6, torch.bfloat16: 2e-2, torch.float16: 2.5e-3}[dtype], err
     sub = x[1, 7, 32:40, 64:72, 96:112].float().cpu()
     want = haar.haar_cell_forward(sub.double())
     got = torch.cat([ll[1, 7, 16:20, 32:36, 48:56].unsqueeze(0), hf[:, 1, 7, 16:20, 32:36, 48:56]], 0).float().cpu()
-    assert float((got.double() - want).abs().max()) < (1e-5 if dtype == torch.float32 else 5e-2)
+    assert float((got.double() - want).abs().max()) < {torch.float32: 1e-5, torch.bfloat16: 5e-2, torch.float16: 8e-3}[dtype]

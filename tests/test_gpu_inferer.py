@@ -82,11 +82,11 @@ def test_volume_240x240x155_bf16_matches_reference():
     with torch.no_grad():
         y = inf(x.cuda(), m)
     assert y.dtype == torch.float32
-    assert max_rel(y.reshape(-1).cpu()[g["pos"]], g["logits"]) <= 2e-2      # north-star bf16 tolerance
-    # label histogram of the stitched volume: near-tied voxels may flip under bf16 (see test_gpu_model's bf16 test);
-    # the class populations must still agree to 1 %
+    assert max_rel(y.reshape(-1).cpu()[g["pos"]], g["logits"]) <= 5e-3      # north-star 16-bit tolerance 2e-2; measured ~2e-3
+    # label histogram of the stitched volume: ~0.1 % of the (near-tied) voxels flip under the 16-bit policy (see
+    # test_gpu_model); the class populations must agree to 2e-3 (fp32: 2e-4)
     hist = np.bincount(inf.labels.reshape(-1).cpu().numpy(), minlength=4)
-    assert np.abs(hist - g["label_hist"]).sum() <= 1e-2 * hist.sum()
+    assert np.abs(hist - g["label_hist"]).sum() <= 2e-3 * hist.sum(), np.abs(hist - g["label_hist"]).sum() / hist.sum()
 
 
 def test_cuda_graph_replay_matches_eager():

@@ -105,13 +105,11 @@ def test_waveformer_forward_fp32_matches_reference(sd):
 
 
 def test_waveformer_forward_bf16_matches_reference(sd):
-    """bf16 gate (north star): max-relative logit error <= 2e-2 against the fp32 reference, over EVERY voxel.
-
-    Label agreement: with these unit-gain random weights a large share of voxels has a top-1 / top-2 logit margin below
-    the 2e-2 tolerance itself, so a bf16 activation path cannot reproduce >= 99.9 % of ALL argmax decisions (rounding
-    the outputs of one residual block to bf16 already flips 0.1 %, scripts/precision_zones.py; DESIGN.md "Precision").
-    Asserted instead: >= 99.9 % agreement wherever the reference's margin exceeds the tolerance, and the measured
-    overall agreement (>= 99 %) so regressions show."""
+    """16-bit policy gate (north star) on the unit-gain STRESS weights of this suite: max-relative logit error <= 2e-2
+    against the fp32 reference over every voxel (measured 2.1e-3), argmax agreement over ALL voxels >= 99.85 % (measured
+    99.893 %: round 1's bf16-storage policy gave 99.53 %; fp16 storage and the error-compensated attention operands removed
+    three quarters of the flips).  The spec's 99.9 % on these weights is asserted by the strict-xfail test below; on the
+    reference's own random initialisation it is met (next test)."""
     g = load_npz("waveformer_128.npz")
     x = seeded_randn((1, 4, 128, 128, 128), 1)
     with torch.no_grad():
@@ -119,12 +117,41 @@ def test_waveformer_forward_bf16_matches_reference(sd):
         ref = om.waveformer_forward(sd, x, CFG)         # CPU oracle, fp32 (pinned to the reference by the fixture)
     assert max_rel(ref.reshape(-1)[g["pos"]], g["logits"]) < 1e-4
     yc = y.cpu()
-    assert max_rel(yc, ref) <= 2e-2
+    assert max_rel(yc, ref) <= 5e-3                      # gate 2e-2; measured 2.1e-3
     same = yc.argmax(1) == ref.argmax(1)
     top = ref.topk(2, dim=1).values
     clear = (top[:, 0] - top[:, 1]) > 2e-2 * float(ref.abs().max())
-    assert float(same[clear].float().mean()) >= 0.999
-    assert float(same.float().mean()) >= 0.99, float(same.float().mean())
+    assert float(same[clear].float().mean()) == 1.0      # no decision with a margin above the tolerance ever flips
+    assert float(same.float().mean()) >= 0.9985, float(same.float().mean())
+
+
+@pytest.mark.xfail(strict=True, reason="north-star gate >= 99.9 % argmax agreement over all voxels: 99.893 % measured on the "
+                                       "unit-gain stress weights (12.5 % of their voxels have a top-1 / top-2 margin below the "
+                                       "2e-2 tolerance); met on the reference's own initialisation, see the next test")
+def test_argmax_gate_on_the_stress_weights(sd):
+    x = seeded_randn((1, 4, 128, 128, 128), 1)
+    with torch.no_grad():
+        y = _model(sd, torch.bfloat16)(x.cuda()).float().cpu()
+        ref = _model(sd, torch.float32)(x.cuda()).float().cpu()      # fp32 product path: <= 1e-5 from the oracle (tested above)
+    assert float((y.argmax(1) == ref.argmax(1)).float().mean()) >= 0.999
+
+
+def test_argmax_gate_on_the_reference_initialisation():
+    """North-star gate as written - same random-init weights as the reference (its constructors' own initialisation:
+    trunc-normal 0.02 Linear layers, fan-out normal convolutions), synthetic BraTS-shaped input: max-relative logit error
+    <= 2e-2 and argmax label agreement >= 99.9 % over ALL voxels, 16-bit policy vs the fp32 CPU oracle."""
+    from waveformer_b200 import prepare_inference
+    from waveformer_b200.network_models import Waveformer
+    torch.manual_seed(0)
+    m = Waveformer(**CFG.kwargs()).eval()
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    x = seeded_randn((1, 4, 128, 128, 128), 1)
+    with torch.no_grad():
+        ref = om.waveformer_forward(sd0, x, CFG)
+        y = prepare_inference(m.cuda(), torch.bfloat16)(x.cuda()).float().cpu()
+    assert max_rel(y, ref) <= 2e-2
+    agree = float((y.argmax(1) == ref.argmax(1)).float().mean())
+    assert agree >= 0.999, agree
 
 
 def test_encoder_outputs_fp32(sd):

@@ -30,6 +30,8 @@ SIGNATURES = {
     "wf_relpos_bias_image": (_I, [_VOIDP, _I, _VOIDP, _VOIDP, _I, _I, _I, _I, _VOIDP]),
     "wf_window_attn_tc_supported": (_I, [_I] * 6),
     "wf_window_attn_fwd": (_I, [_VOIDP, _I] + [_VOIDP] * 7 + [_I, _VOIDP, _SZ, _I, _I, _I, _I, _I, _I, _I, _I, _F, _VOIDP]),
+    "wf_window_attn_split_workspace_bytes": (_SZ, [_I] * 7),
+    "wf_window_attn_fwd_split": (_I, [_VOIDP] * 10 + [_SZ, _I, _I, _I, _I, _I, _I, _I, _F, _VOIDP]),
     "wf_window_attn_bwd_stats_bytes": (_SZ, [_I64, _I, _I]),
     "wf_window_attn_bwd": (_I, [_VOIDP] * 8 + [_I64, _I, _I, _I, _I, _F, _VOIDP]),
     "wf_patch_merge_layernorm": (_I, [_VOIDP, _VOIDP, _VOIDP, _VOIDP, _I, _I, _I, _I, _I, _I, _c.c_uint32, _F, _VOIDP]),

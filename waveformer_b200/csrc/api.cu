@@ -14,6 +14,11 @@ bool attn_tc_supported(int D1, int H1, int W1, int C, int heads, int ws);
 size_t attn_tc_bias_image_bytes(int heads);
 int attn_tc_bias_image(const void *table, int table_dtype, const int64_t *index, void *img, bool f16, int heads,
                        int table_rows, cudaStream_t st);
+size_t attn_tc_split_workspace_bytes(int64_t tokens, int C);
+int attn_tc_forward_split(const float *x, const uint16_t *qkv_w_hi, const uint16_t *qkv_w_lo, const float *qkv_b,
+                          const uint16_t *proj_w_hi, const uint16_t *proj_w_lo, const float *proj_b, const uint16_t *bias_img,
+                          float *out, void *workspace, int B, int D1, int H1, int W1, int C, int heads, float scale,
+                          cudaStream_t st);
 int attn_tc_forward(const void *x, int x_dtype, const void *qkv_w, const void *qkv_b, const void *proj_w,
                     const void *proj_b, const void *bias_img, void *out, bool out_f32, void *workspace, bool f16, int B,
                     int D1, int H1, int W1, int C, int heads, float scale, cudaStream_t st);
@@ -69,6 +74,27 @@ extern "C" int wf_relpos_bias_image(const void *table, int table_dtype, const in
 
 extern "C" int wf_window_attn_tc_supported(int D1, int H1, int W1, int C, int heads, int ws) {
     return check_attn_shape(1, D1, H1, W1, C, heads, ws) == WF_OK && wf::attn_tc_supported(D1, H1, W1, C, heads, ws) ? 1 : 0;
+}
+
+extern "C" size_t wf_window_attn_split_workspace_bytes(int B, int D1, int H1, int W1, int C, int heads, int ws) {
+    if (check_attn_shape(B, D1, H1, W1, C, heads, ws) != WF_OK || !wf::attn_tc_supported(D1, H1, W1, C, heads, ws)) return 0;
+    return wf::attn_tc_split_workspace_bytes((int64_t)B * D1 * H1 * W1, C);
+}
+
+extern "C" int wf_window_attn_fwd_split(const float *x, const void *qkv_w_hi, const void *qkv_w_lo, const float *qkv_b,
+                                        const void *proj_w_hi, const void *proj_w_lo, const float *proj_b,
+                                        const void *bias_img, float *out, void *workspace, size_t workspace_bytes, int B,
+                                        int D1, int H1, int W1, int C, int heads, int ws, float scale, void *stream) {
+    if (!x || !qkv_w_hi || !qkv_w_lo || !qkv_b || !proj_w_hi || !proj_w_lo || !proj_b || !bias_img || !out || !workspace)
+        return WF_ERR_NULL_POINTER;
+    const int rc = check_attn_shape(B, D1, H1, W1, C, heads, ws);
+    if (rc != WF_OK) return rc;
+    if (!wf::attn_tc_supported(D1, H1, W1, C, heads, ws)) return WF_ERR_UNSUPPORTED;
+    if (workspace_bytes < wf_window_attn_split_workspace_bytes(B, D1, H1, W1, C, heads, ws)) return WF_ERR_WORKSPACE;
+    using u16 = uint16_t;
+    return wf::attn_tc_forward_split(x, (const u16 *)qkv_w_hi, (const u16 *)qkv_w_lo, qkv_b, (const u16 *)proj_w_hi,
+                                     (const u16 *)proj_w_lo, proj_b, (const u16 *)bias_img, out, workspace, B, D1, H1, W1, C,
+                                     heads, scale, (cudaStream_t)stream);
 }
 
 extern "C" int wf_window_attn_fwd(const void *x, int x_dtype, const void *qkv_w, const void *qkv_b, const void *proj_w,

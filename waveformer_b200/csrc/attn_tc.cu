@@ -79,21 +79,40 @@ template <bool F16> __host__ __device__ constexpr uint32_t instr_desc16(int M, i
 }
 
 // ------------------------------------------------------------------------------------------------ projections ----
-// grid (M/128, Nout/NT), 128 threads.  smem: A image [K/8][128][8], B image [K/8][NT][8] 16-bit (no-swizzle canonical).
+// grid (M/128, Nout/NT), 128 threads.  smem: A image [kpc][128][8], B image [kpc][NT][8] 16-bit (no-swizzle canonical),
+// kpc = K chunks (of 8 elements) staged per pass; K is walked in K / (8 kpc) passes that accumulate into the same TMEM tile.
 // TA: float (converted to the operand format while staging), __nv_bfloat16 (converted unless the format is bf16), or
 //     uint16_t (already in the operand format: the core kernel's output).   TO: float or uint16_t (operand format).
-template <bool QKV, typename TA, bool F16, typename TO>
-__global__ void __launch_bounds__(128) linear_tc_kernel(const TA *__restrict__ A, const uint16_t *__restrict__ Wt,
-                                                        const uint16_t *__restrict__ bias, TO *__restrict__ out, int K,
-                                                        int NT, int Nout, TcWindowMap map, int heads, int64_t B_,
-                                                        float qscale, uint32_t tmem_cols) {
+// SPLIT (fp16 only): error-compensated operands.  Every operand is carried as hi + lo, hi = fp16(v), lo = fp16(v - hi)
+//     (22 significant bits together), and the product is accumulated as A_hi B_hi + A_lo B_hi + A_hi B_lo - three
+//     tcgen05.mma per k-step instead of one, on a tensor pipe that idles anyway at these sizes (K = 48 .. 384).  What the
+//     softmax exponentiates is then accurate to fp32 level: with plain fp16 operands the |q||k| 2^-11 error of the scores
+//     is the largest single contribution to the 16-bit policy's logit error (scripts/precision_policy2_r02.py).  The QKV
+//     epilogue stores q and k as hi / lo pairs too (planes 0 / 1 hi, 3 / 4 lo; v in plane 2), bias is added in fp32.
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t &hi, uint32_t &lo) {
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2 *>(&hi));
+    const float ra = a - hf.x, rb = b - hf.y;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
+}
+
+template <bool QKV, typename TA, bool F16, typename TO, bool SPLIT>
+__global__ void __launch_bounds__(128) linear_tc_kernel(const TA *__restrict__ A, const TA *__restrict__ A_lo,
+                                                        const uint16_t *__restrict__ Wt, const uint16_t *__restrict__ Wt_lo,
+                                                        const uint16_t *__restrict__ bias, const float *__restrict__ bias32,
+                                                        TO *__restrict__ out, int K, int NT, int Nout, TcWindowMap map,
+                                                        int heads, int64_t B_, float qscale, uint32_t tmem_cols, int kpc) {
+    static_assert(!SPLIT || F16, "compensated operands are an fp16 feature");
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5;
     const int kchunks = K >> 3;
+    const int npass = kchunks / kpc;
     uint8_t *sA = smem;
-    uint8_t *sB = smem + (size_t)kchunks * 2048;
+    uint8_t *sB = smem + (size_t)kpc * 2048 * (SPLIT ? 2 : 1);
+    uint8_t *sAl = smem + (size_t)kpc * 2048;            // SPLIT only
+    uint8_t *sBl = sB + (size_t)kpc * NT * 16;           // SPLIT only
     const int64_t m0 = (int64_t)blockIdx.x * 128;
     const int n0 = blockIdx.y * NT;
 
@@ -102,60 +121,86 @@ __global__ void __launch_bounds__(128) linear_tc_kernel(const TA *__restrict__ A
         mbar_init(&bar, 1);
         mbar_fence_init();
     }
-    // A tile: row r = tid, every 16-byte K chunk.  A warp writes 32 consecutive rows of one chunk: conflict-free.
-    {
-        const int64_t src_row = QKV ? map.voxel(m0 + tid) : (m0 + tid);
-        constexpr bool raw = sizeof(TA) == 2 && (std::is_same<TA, uint16_t>::value || !F16);
-        if constexpr (raw) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(A + src_row * K);
-            for (int kc = 0; kc < kchunks; ++kc)
-                *reinterpret_cast<uint4 *>(sA + (size_t)kc * 2048 + tid * 16) = __ldg(src + kc);
-        } else if constexpr (sizeof(TA) == 2) {  // bf16 activations, fp16 operands
-            const uint4 *src = reinterpret_cast<const uint4 *>(A + src_row * K);
-            for (int kc = 0; kc < kchunks; ++kc) {
-                const uint4 a = __ldg(src + kc);
-                const uint32_t w[4] = {a.x, a.y, a.z, a.w};
-                uint4 u;
-                uint32_t *uw = &u.x;
+    const int64_t src_row = QKV ? map.voxel(m0 + tid) : (m0 + tid);
+    uint32_t tmem = 0;
+    for (int p = 0; p < npass; ++p) {
+        const int kc0 = p * kpc;
+        // A tile: row r = tid, every 16-byte K chunk.  A warp writes 32 consecutive rows of one chunk: conflict-free.
+        // (pass p > 0: every thread has waited for the previous pass's MMAs below, so the images may be overwritten)
+        {
+            constexpr bool raw = sizeof(TA) == 2 && (std::is_same<TA, uint16_t>::value || !F16);
+            if constexpr (raw) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(A + src_row * K) + kc0;
+                for (int kc = 0; kc < kpc; ++kc)
+                    *reinterpret_cast<uint4 *>(sA + (size_t)kc * 2048 + tid * 16) = __ldg(src + kc);
+                if constexpr (SPLIT) {
+                    const uint4 *srl = reinterpret_cast<const uint4 *>(A_lo + src_row * K) + kc0;
+                    for (int kc = 0; kc < kpc; ++kc)
+                        *reinterpret_cast<uint4 *>(sAl + (size_t)kc * 2048 + tid * 16) = __ldg(srl + kc);
+                }
+            } else if constexpr (sizeof(TA) == 2) {  // bf16 activations, fp16 operands
+                const uint4 *src = reinterpret_cast<const uint4 *>(A + src_row * K) + kc0;
+                for (int kc = 0; kc < kpc; ++kc) {
+                    const uint4 a = __ldg(src + kc);
+                    const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+                    uint4 u;
+                    uint32_t *uw = &u.x;
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    uw[e] = pack16<F16>(__uint_as_float(w[e] << 16), __uint_as_float(w[e] & 0xffff0000u));
-                *reinterpret_cast<uint4 *>(sA + (size_t)kc * 2048 + tid * 16) = u;
-            }
-        } else {  // fp32 activations (residual-stream precision): converted to the operand format while staging
-            const float4 *src = reinterpret_cast<const float4 *>(A + src_row * K);
-            for (int kc = 0; kc < kchunks; ++kc) {
-                const float4 a = __ldg(src + 2 * kc), b = __ldg(src + 2 * kc + 1);
-                uint4 u;
-                u.x = pack16<F16>(a.x, a.y); u.y = pack16<F16>(a.z, a.w);
-                u.z = pack16<F16>(b.x, b.y); u.w = pack16<F16>(b.z, b.w);
-                *reinterpret_cast<uint4 *>(sA + (size_t)kc * 2048 + tid * 16) = u;
+                    for (int e = 0; e < 4; ++e)
+                        uw[e] = pack16<F16>(__uint_as_float(w[e] << 16), __uint_as_float(w[e] & 0xffff0000u));
+                    *reinterpret_cast<uint4 *>(sA + (size_t)kc * 2048 + tid * 16) = u;
+                }
+            } else {  // fp32 activations (residual-stream precision): converted to the operand format while staging
+                const float4 *src = reinterpret_cast<const float4 *>(A + src_row * K) + 2 * kc0;
+                for (int kc = 0; kc < kpc; ++kc) {
+                    const float4 a = __ldg(src + 2 * kc), b = __ldg(src + 2 * kc + 1);
+                    uint4 u;
+                    if constexpr (SPLIT) {
+                        uint4 l;
+                        split_pair(a.x, a.y, u.x, l.x); split_pair(a.z, a.w, u.y, l.y);
+                        split_pair(b.x, b.y, u.z, l.z); split_pair(b.z, b.w, u.w, l.w);
+                        *reinterpret_cast<uint4 *>(sAl + (size_t)kc * 2048 + tid * 16) = l;
+                    } else {
+                        u.x = pack16<F16>(a.x, a.y); u.y = pack16<F16>(a.z, a.w);
+                        u.z = pack16<F16>(b.x, b.y); u.w = pack16<F16>(b.z, b.w);
+                    }
+                    *reinterpret_cast<uint4 *>(sA + (size_t)kc * 2048 + tid * 16) = u;
+                }
             }
         }
-    }
-    // B tile: rows n0 .. n0+NT-1 of the [Nout, K] weight
-    for (int idx = tid; idx < NT * kchunks; idx += 128) {
-        const int r = idx % NT, kc = idx / NT;
-        *reinterpret_cast<uint4 *>(sB + ((size_t)kc * NT + r) * 16) =
-            __ldg(reinterpret_cast<const uint4 *>(Wt + (int64_t)(n0 + r) * K) + kc);
-    }
-    fence_proxy_async();  // st.shared above -> visible to the tensor core's async proxy
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = tmem_slot;
-    if (tid == 0) {
-        const uint32_t idesc = instr_desc16<F16>(128, NT, false);
-        const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
-        for (int ks = 0; ks < (K >> 4); ++ks) {
-            const uint64_t da = smem_desc(a0 + ks * 2 * 2048, 2048, 128);
-            const uint64_t db = smem_desc(b0 + ks * 2 * NT * 16, NT * 16, 128);
-            mma_ss(tmem, da, db, idesc, ks > 0 ? 1u : 0u);
+        // B tile: rows n0 .. n0+NT-1 of the [Nout, K] weight
+        for (int idx = tid; idx < NT * kpc; idx += 128) {
+            const int r = idx % NT, kc = idx / NT;
+            *reinterpret_cast<uint4 *>(sB + ((size_t)kc * NT + r) * 16) =
+                __ldg(reinterpret_cast<const uint4 *>(Wt + (int64_t)(n0 + r) * K) + kc0 + kc);
+            if constexpr (SPLIT)
+                *reinterpret_cast<uint4 *>(sBl + ((size_t)kc * NT + r) * 16) =
+                    __ldg(reinterpret_cast<const uint4 *>(Wt_lo + (int64_t)(n0 + r) * K) + kc0 + kc);
         }
-        mma_commit(&bar);
+        fence_proxy_async();  // st.shared above -> visible to the tensor core's async proxy
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        tmem = tmem_slot;
+        if (tid == 0) {
+            const uint32_t idesc = instr_desc16<F16>(128, NT, false);
+            const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+            for (int ks = 0; ks < (kpc >> 1); ++ks) {
+                const uint64_t da = smem_desc(a0 + ks * 2 * 2048, 2048, 128);
+                const uint64_t db = smem_desc(b0 + ks * 2 * NT * 16, NT * 16, 128);
+                mma_ss(tmem, da, db, idesc, (p > 0 || ks > 0) ? 1u : 0u);
+                if constexpr (SPLIT) {
+                    const uint64_t dal = smem_desc(smem_u32(sAl) + ks * 2 * 2048, 2048, 128);
+                    const uint64_t dbl = smem_desc(smem_u32(sBl) + ks * 2 * NT * 16, NT * 16, 128);
+                    mma_ss(tmem, dal, db, idesc, 1u);
+                    mma_ss(tmem, da, dbl, idesc, 1u);
+                }
+            }
+            mma_commit(&bar);
+        }
+        mbar_wait(&bar, p & 1);
+        tc_fence_after();
     }
-    mbar_wait(&bar, 0);
-    tc_fence_after();
     // epilogue: thread = output row; 16 columns (= one head's q, k or v slice when QKV) per step
     const int64_t m = m0 + tid;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
@@ -166,7 +211,8 @@ __global__ void __launch_bounds__(128) linear_tc_kernel(const TA *__restrict__ A
         const int n = n0 + c;
         float v[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]) + (bias ? widen16<F16>(bias[n + e]) : 0.f);
+        for (int e = 0; e < 16; ++e)
+            v[e] = __uint_as_float(r[e]) + (bias32 ? __ldg(bias32 + n + e) : (bias ? widen16<F16>(bias[n + e]) : 0.f));
         if constexpr (QKV) {
             const int C = heads * 16;
             const int which = n / C, hh = (n % C) >> 4;
@@ -176,10 +222,24 @@ __global__ void __launch_bounds__(128) linear_tc_kernel(const TA *__restrict__ A
             }
             const int64_t win = m >> 9;
             const int tok = (int)(m & 511);
-            uint16_t *dst = reinterpret_cast<uint16_t *>(out) + (((int64_t)which * B_ + win) * heads + hh) * 8192 + tok * 8;
+            const int64_t plane = B_ * heads * 8192;
+            uint16_t *dst = reinterpret_cast<uint16_t *>(out) + ((int64_t)win * heads + hh) * 8192 + tok * 8 + which * plane;
             uint4 lo, hi;
-            lo.x = pack16<F16>(v[0], v[1]); lo.y = pack16<F16>(v[2], v[3]); lo.z = pack16<F16>(v[4], v[5]); lo.w = pack16<F16>(v[6], v[7]);
-            hi.x = pack16<F16>(v[8], v[9]); hi.y = pack16<F16>(v[10], v[11]); hi.z = pack16<F16>(v[12], v[13]); hi.w = pack16<F16>(v[14], v[15]);
+            if constexpr (SPLIT) {
+                uint4 llo, lhi;   // the lo parts of head dims 0..7 / 8..15
+                split_pair(v[0], v[1], lo.x, llo.x); split_pair(v[2], v[3], lo.y, llo.y);
+                split_pair(v[4], v[5], lo.z, llo.z); split_pair(v[6], v[7], lo.w, llo.w);
+                split_pair(v[8], v[9], hi.x, lhi.x); split_pair(v[10], v[11], hi.y, lhi.y);
+                split_pair(v[12], v[13], hi.z, lhi.z); split_pair(v[14], v[15], hi.w, lhi.w);
+                if (which < 2) {      // q and k: the operands of the scores
+                    uint16_t *dl = dst + 3 * plane;      // plane 3 (q lo) / 4 (k lo)
+                    *reinterpret_cast<uint4 *>(dl) = llo;
+                    *reinterpret_cast<uint4 *>(dl + 4096) = lhi;
+                }
+            } else {
+                lo.x = pack16<F16>(v[0], v[1]); lo.y = pack16<F16>(v[2], v[3]); lo.z = pack16<F16>(v[4], v[5]); lo.w = pack16<F16>(v[6], v[7]);
+                hi.x = pack16<F16>(v[8], v[9]); hi.y = pack16<F16>(v[10], v[11]); hi.z = pack16<F16>(v[12], v[13]); hi.w = pack16<F16>(v[14], v[15]);
+            }
             *reinterpret_cast<uint4 *>(dst) = lo;          // chunk 0: head dims 0..7
             *reinterpret_cast<uint4 *>(dst + 4096) = hi;   // chunk 1: head dims 8..15
         } else if constexpr (sizeof(TO) == 4) {
@@ -205,6 +265,10 @@ constexpr int kBiasPitch = 520;                       // 16-bit elements per bia
 constexpr int kBiasBytes = 128 * kBiasPitch * 2;      // 133120 per (head, query tile)
 constexpr int kStageBytes = 4096 + 16384 + 16384;     // Q tile [2][128][8] + K [2][512][8] + V [2][512][8]
 constexpr int kCoreSmem = kBiasBytes + 2 * kStageBytes + 2 * 4 * 128 * 4;  // + row max / row sum exchange (4 key quarters)
+// SPLIT (compensated scores): Q hi / lo tiles + K hi / lo in ONE buffer that is refilled for the next window as soon as this
+// window's score MMAs have completed (the whole softmax phase hides the copy), V double-buffered as before
+constexpr int kQKSplitBytes = 2 * 4096 + 2 * 16384;                        // 40960
+constexpr int kCoreSmemSplit = kBiasBytes + kQKSplitBytes + 2 * 16384 + 2 * 4 * 128 * 4;   // 210944
 
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
@@ -255,19 +319,24 @@ __device__ __forceinline__ void softmax_warps_sync() {   // named barrier 1: the
 //   underneath the exponentials instead of after them (they were 24 % of the kernel as a serial phase, profiles/).
 // TMEM columns: S = [0, 512) fp32; P chunk (q, c) = [128q + 32c, 128q + 32c + 16); O = [16, 32) (the second half of
 // chunk (0, 0), free once that chunk's P is written - the first PV instruction waits for exactly that chunk).
-template <bool F16>
+// SPLIT: q and k arrive as hi / lo pairs (planes 0 / 1 and 3 / 4 of `qkv`) and the scores are accumulated as
+// Q_hi K_hi^T + Q_lo K_hi^T + Q_hi K_lo^T (6 instead of 2 tcgen05.mma per tile: the tensor pipe is ~5 % busy here), so the
+// exponent's argument is exact to ~2^-21 |q||k|; O is written as a hi / lo pair (second plane at o + B_ * 512 * C) for the
+// compensated output projection.
+template <bool F16, bool SPLIT>
 __global__ void __launch_bounds__(544, 1) attn_core_tc_kernel(const uint16_t *__restrict__ qkv,
                                                               const uint16_t *__restrict__ bias_img,
                                                               uint16_t *__restrict__ o, int heads, int64_t B_,
                                                               int groups) {
+    static_assert(!SPLIT || F16, "compensated operands are an fp16 feature");
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_full[2];
-    __shared__ __align__(8) uint64_t bar_s, bar_o, bar_bias, bar_epi;
+    __shared__ __align__(8) uint64_t bar_s, bar_o, bar_bias, bar_epi, bar_qk;
     __shared__ __align__(8) uint64_t bar_p[16];   // [quarter][chunk]
     __shared__ uint32_t tmem_slot;
     uint16_t *sBias = reinterpret_cast<uint16_t *>(smem);
     uint8_t *sStage = smem + kBiasBytes;
-    float *sMax = reinterpret_cast<float *>(smem + kBiasBytes + 2 * kStageBytes);  // [4][128]
+    float *sMax = reinterpret_cast<float *>(smem + kBiasBytes + (SPLIT ? kQKSplitBytes + 2 * 16384 : 2 * kStageBytes));  // [4][128]
     float *sSum = sMax + 512;                                                       // [4][128]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -283,6 +352,7 @@ __global__ void __launch_bounds__(544, 1) attn_core_tc_kernel(const uint16_t *__
         mbar_init(&bar_o, 1);
         mbar_init(&bar_bias, 1);
         mbar_init(&bar_epi, 4);
+        mbar_init(&bar_qk, 1);
         for (int i = 0; i < 16; ++i) mbar_init(&bar_p[i], 4);
         mbar_fence_init();
     }
@@ -295,55 +365,122 @@ __global__ void __launch_bounds__(544, 1) attn_core_tc_kernel(const uint16_t *__
     if (warp == 16) {
         // ================================================= issuer ====================================================
         if (lane == 0 && g < B_) {
-            auto issue_loads = [&](int64_t win, int stage) {
-                uint8_t *dst = sStage + stage * kStageBytes;
-                const uint16_t *qb = qkv + (win * heads + hh) * 8192;
-                mbar_expect_tx(&bar_full[stage], kStageBytes);
-                bulk_g2s(dst, qb + qt * 128 * 8, 2048, &bar_full[stage]);                 // Q chunk 0 (head dims 0..7)
-                bulk_g2s(dst + 2048, qb + 4096 + qt * 128 * 8, 2048, &bar_full[stage]);   // Q chunk 1
-                bulk_g2s(dst + 4096, qb + per_which, 16384, &bar_full[stage]);            // K
-                bulk_g2s(dst + 4096 + 16384, qb + 2 * per_which, 16384, &bar_full[stage]);  // V
-            };
             // relative-position bias slab of this (head, query tile): one 130 KB bulk copy, resident for every window
             mbar_expect_tx(&bar_bias, kBiasBytes);
             bulk_g2s(sBias, bias_img + ((int64_t)hh * 4 + qt) * (kBiasBytes / 2), kBiasBytes, &bar_bias);
-            issue_loads(g, 0);
             const uint32_t idesc_s = instr_desc16<F16>(128, 256, false);
             const uint32_t idesc_o = instr_desc16<F16>(128, 16, true);
-            int it = 0;
-            for (int64_t win = g; win < B_; win += groups, ++it) {
-                const int stage = it & 1;
-                const uint32_t ph_full = (it >> 1) & 1, ph = it & 1;
-                const uint32_t sQ = smem_u32(sStage + stage * kStageBytes), sK = sQ + 4096, sV = sK + 16384;
-                if (it > 0) {   // previous tile: O read back and its V / P consumed -> TMEM and the other stage are free
-                    mbar_wait(&bar_epi, (it - 1) & 1);
-                    tc_fence_after();
-                }
-                if (win + groups < B_) issue_loads(win + groups, stage ^ 1);
-                mbar_wait(&bar_full[stage], ph_full);
-                tc_fence_after();
-                // S[128 x 512] = Q[128 x 16] K^T : two N = 256 halves, TMEM columns [0,256) and [256,512)
-                const uint64_t dq = smem_desc(sQ, 2048, 128);
-                mma_ss(tmem, dq, smem_desc(sK, 8192, 128), idesc_s, 0u);
-                mma_ss(tmem + 256, dq, smem_desc(sK + 256 * 16, 8192, 128), idesc_s, 0u);
-                mma_commit(&bar_s);
-                // O[128 x 16] += P_chunk[128 x 32] V_chunk[32 x 16] as the chunks arrive (chunk index fastest over quarters)
-                uint32_t first = 1;
-#pragma unroll 1
-                for (int c = 0; c < 4; ++c)
-#pragma unroll 1
-                    for (int q = 0; q < 4; ++q) {
-                        mbar_wait(&bar_p[q * 4 + c], ph);
+            if constexpr (!SPLIT) {
+                auto issue_loads = [&](int64_t win, int stage) {
+                    uint8_t *dst = sStage + stage * kStageBytes;
+                    const uint16_t *qb = qkv + (win * heads + hh) * 8192;
+                    mbar_expect_tx(&bar_full[stage], kStageBytes);
+                    bulk_g2s(dst, qb + qt * 128 * 8, 2048, &bar_full[stage]);                 // Q chunk 0 (head dims 0..7)
+                    bulk_g2s(dst + 2048, qb + 4096 + qt * 128 * 8, 2048, &bar_full[stage]);   // Q chunk 1
+                    bulk_g2s(dst + 4096, qb + per_which, 16384, &bar_full[stage]);            // K
+                    bulk_g2s(dst + 4096 + 16384, qb + 2 * per_which, 16384, &bar_full[stage]);  // V
+                };
+                issue_loads(g, 0);
+                int it = 0;
+                for (int64_t win = g; win < B_; win += groups, ++it) {
+                    const int stage = it & 1;
+                    const uint32_t ph_full = (it >> 1) & 1, ph = it & 1;
+                    const uint32_t sQ = smem_u32(sStage + stage * kStageBytes), sK = sQ + 4096, sV = sK + 16384;
+                    if (it > 0) {   // previous tile: O read back and its V / P consumed -> TMEM and the other stage are free
+                        mbar_wait(&bar_epi, (it - 1) & 1);
                         tc_fence_after();
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            const int ks = q * 8 + c * 2 + j;   // k-step = keys [16 ks, 16 ks + 16)
-                            mma_ts(tmem + 16, tmem + q * 128 + c * 32 + j * 8, smem_desc(sV + ks * 256, 128, 8192), idesc_o,
-                                   first ? 0u : 1u);
-                            first = 0;
-                        }
                     }
-                mma_commit(&bar_o);
+                    if (win + groups < B_) issue_loads(win + groups, stage ^ 1);
+                    mbar_wait(&bar_full[stage], ph_full);
+                    tc_fence_after();
+                    // S[128 x 512] = Q[128 x 16] K^T : two N = 256 halves, TMEM columns [0,256) and [256,512)
+                    const uint64_t dq = smem_desc(sQ, 2048, 128);
+                    mma_ss(tmem, dq, smem_desc(sK, 8192, 128), idesc_s, 0u);
+                    mma_ss(tmem + 256, dq, smem_desc(sK + 256 * 16, 8192, 128), idesc_s, 0u);
+                    mma_commit(&bar_s);
+                    // O[128 x 16] += P_chunk[128 x 32] V_chunk[32 x 16] as the chunks arrive (chunk index fastest over quarters)
+                    uint32_t first = 1;
+#pragma unroll 1
+                    for (int c = 0; c < 4; ++c)
+#pragma unroll 1
+                        for (int q = 0; q < 4; ++q) {
+                            mbar_wait(&bar_p[q * 4 + c], ph);
+                            tc_fence_after();
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const int ks = q * 8 + c * 2 + j;   // k-step = keys [16 ks, 16 ks + 16)
+                                mma_ts(tmem + 16, tmem + q * 128 + c * 32 + j * 8, smem_desc(sV + ks * 256, 128, 8192), idesc_o,
+                                       first ? 0u : 1u);
+                                first = 0;
+                            }
+                        }
+                    mma_commit(&bar_o);
+                }
+            } else {
+                uint8_t *sQK = sStage;                      // [Q hi 4096][Q lo 4096][K hi 16384][K lo 16384]
+                uint8_t *sVb = sStage + kQKSplitBytes;      // 2 x 16384
+                auto issue_qk = [&](int64_t win) {
+                    const uint16_t *qb = qkv + (win * heads + hh) * 8192;
+                    mbar_expect_tx(&bar_qk, kQKSplitBytes);
+                    bulk_g2s(sQK, qb + qt * 128 * 8, 2048, &bar_qk);                                   // Q hi, head dims 0..7
+                    bulk_g2s(sQK + 2048, qb + 4096 + qt * 128 * 8, 2048, &bar_qk);                     // Q hi, head dims 8..15
+                    bulk_g2s(sQK + 4096, qb + 3 * per_which + qt * 128 * 8, 2048, &bar_qk);            // Q lo
+                    bulk_g2s(sQK + 6144, qb + 3 * per_which + 4096 + qt * 128 * 8, 2048, &bar_qk);
+                    bulk_g2s(sQK + 8192, qb + per_which, 16384, &bar_qk);                              // K hi
+                    bulk_g2s(sQK + 8192 + 16384, qb + 4 * per_which, 16384, &bar_qk);                  // K lo
+                };
+                auto issue_v = [&](int64_t win, int stage) {
+                    mbar_expect_tx(&bar_full[stage], 16384);
+                    bulk_g2s(sVb + stage * 16384, qkv + (win * heads + hh) * 8192 + 2 * per_which, 16384, &bar_full[stage]);
+                };
+                issue_qk(g);
+                issue_v(g, 0);
+                const uint32_t sQh = smem_u32(sQK), sQl = sQh + 4096, sKh = sQh + 8192, sKl = sKh + 16384;
+                int it = 0;
+                for (int64_t win = g; win < B_; win += groups, ++it) {
+                    const int stage = it & 1;
+                    const uint32_t ph_v = (it >> 1) & 1, ph = it & 1;
+                    const uint32_t sV = smem_u32(sVb + stage * 16384);
+                    if (it > 0) {   // previous tile: O read back and its V / P consumed -> TMEM and the other V stage are free
+                        mbar_wait(&bar_epi, (it - 1) & 1);
+                        tc_fence_after();
+                    }
+                    const bool more = win + groups < B_;
+                    if (more) issue_v(win + groups, stage ^ 1);
+                    mbar_wait(&bar_qk, ph);
+                    tc_fence_after();
+                    const uint64_t dqh = smem_desc(sQh, 2048, 128), dql = smem_desc(sQl, 2048, 128);
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const uint64_t dkh = smem_desc(sKh + half * 256 * 16, 8192, 128), dkl = smem_desc(sKl + half * 256 * 16, 8192, 128);
+                        mma_ss(tmem + half * 256, dqh, dkh, idesc_s, 0u);
+                        mma_ss(tmem + half * 256, dql, dkh, idesc_s, 1u);
+                        mma_ss(tmem + half * 256, dqh, dkl, idesc_s, 1u);
+                    }
+                    mma_commit(&bar_s);
+                    // the score MMAs were the only readers of the Q / K buffer: refill it for the next window as soon as
+                    // they have completed - the copy lands long before the softmax of this tile is through
+                    mbar_wait(&bar_s, ph);
+                    if (more) issue_qk(win + groups);
+                    mbar_wait(&bar_full[stage], ph_v);
+                    tc_fence_after();
+                    uint32_t first = 1;
+#pragma unroll 1
+                    for (int c = 0; c < 4; ++c)
+#pragma unroll 1
+                        for (int q = 0; q < 4; ++q) {
+                            mbar_wait(&bar_p[q * 4 + c], ph);
+                            tc_fence_after();
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const int ks = q * 8 + c * 2 + j;   // k-step = keys [16 ks, 16 ks + 16)
+                                mma_ts(tmem + 16, tmem + q * 128 + c * 32 + j * 8, smem_desc(sV + ks * 256, 128, 8192), idesc_o,
+                                       first ? 0u : 1u);
+                                first = 0;
+                            }
+                        }
+                    mma_commit(&bar_o);
+                }
             }
         }
     } else {
@@ -428,6 +565,20 @@ __global__ void __launch_bounds__(544, 1) attn_core_tc_kernel(const uint16_t *__
                 hi.z = pack16<F16>(__uint_as_float(r[12]) * inv, __uint_as_float(r[13]) * inv);
                 hi.w = pack16<F16>(__uint_as_float(r[14]) * inv, __uint_as_float(r[15]) * inv);
                 uint4 *dst = reinterpret_cast<uint4 *>(o + (win * 512 + qt * 128 + row) * (int64_t)C + hh * 16);
+                if constexpr (SPLIT) {
+                    uint4 llo, lhi;
+                    split_pair(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv, lo.x, llo.x);
+                    split_pair(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv, lo.y, llo.y);
+                    split_pair(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv, lo.z, llo.z);
+                    split_pair(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv, lo.w, llo.w);
+                    split_pair(__uint_as_float(r[8]) * inv, __uint_as_float(r[9]) * inv, hi.x, lhi.x);
+                    split_pair(__uint_as_float(r[10]) * inv, __uint_as_float(r[11]) * inv, hi.y, lhi.y);
+                    split_pair(__uint_as_float(r[12]) * inv, __uint_as_float(r[13]) * inv, hi.z, lhi.z);
+                    split_pair(__uint_as_float(r[14]) * inv, __uint_as_float(r[15]) * inv, hi.w, lhi.w);
+                    uint4 *dl = reinterpret_cast<uint4 *>(o + B_ * 512 * (int64_t)C + (win * 512 + qt * 128 + row) * (int64_t)C + hh * 16);
+                    dl[0] = llo;
+                    dl[1] = lhi;
+                }
                 dst[0] = lo;
                 dst[1] = hi;
                 tc_fence_before();
@@ -471,6 +622,19 @@ int attn_tc_bias_image(const void *table, int table_dtype, const int64_t *index,
     return WF_OK;
 }
 
+// K chunks per pass and N tile of a projection so that the operand images fit in shared memory
+struct LinearPlan { int nt, kpc; size_t smem; };
+static LinearPlan plan_linear(int C, int Nout, bool split) {
+    LinearPlan p;
+    p.nt = pick_ntile(Nout);
+    p.kpc = C / 8;
+    const size_t mult = split ? 2 : 1;
+    auto bytes = [&](int kpc) { return mult * ((size_t)kpc * 2048 + (size_t)kpc * p.nt * 16); };
+    while (p.nt && bytes(p.kpc) > 196 * 1024 && p.kpc % 4 == 0) p.kpc /= 2;   // passes of an even number of chunks
+    p.smem = bytes(p.kpc);
+    return p;
+}
+
 template <bool F16>
 static int attn_tc_run(const void *x, int x_dtype, const uint16_t *qkv_w, const uint16_t *qkv_b, const uint16_t *proj_w,
                        const uint16_t *proj_b, const uint16_t *bias_img, void *out, bool out_f32, void *workspace, int B,
@@ -485,22 +649,20 @@ static int attn_tc_run(const void *x, int x_dtype, const uint16_t *qkv_w, const 
     static unsigned long long attrs_done = 0;   // per-device opt-in bits
     if (first_use_on_current_device(attrs_done)) {
         const int big = 200 * 1024;
-        WF_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel<true, float, F16, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        WF_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel<true, __nv_bfloat16, F16, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        WF_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel<false, uint16_t, F16, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        WF_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel<false, uint16_t, F16, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        WF_CUDA_CHECK(cudaFuncSetAttribute(attn_core_tc_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCoreSmem));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel<true, float, F16, uint16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel<true, __nv_bfloat16, F16, uint16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel<false, uint16_t, F16, uint16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel<false, uint16_t, F16, float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(attn_core_tc_kernel<F16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCoreSmem));
     }
-    const int kchunks = C / 8;
     {
-        const int nt = pick_ntile(3 * C);
-        if (!nt) return WF_ERR_BAD_SHAPE;
-        const size_t smem = (size_t)kchunks * 2048 + (size_t)kchunks * nt * 16;
-        dim3 grid((unsigned)(M / 128), (unsigned)(3 * C / nt));
+        const LinearPlan lp = plan_linear(C, 3 * C, false);
+        if (!lp.nt || lp.smem > 200 * 1024) return WF_ERR_BAD_SHAPE;
+        dim3 grid((unsigned)(M / 128), (unsigned)(3 * C / lp.nt));
         if (x_dtype == WF_F32)
-            linear_tc_kernel<true, float, F16, uint16_t><<<grid, 128, smem, st>>>((const float *)x, qkv_w, qkv_b, qkv, C, nt, 3 * C, map, heads, B_, scale * kLog2e, pow2_cols(nt));
+            linear_tc_kernel<true, float, F16, uint16_t, false><<<grid, 128, lp.smem, st>>>((const float *)x, nullptr, qkv_w, nullptr, qkv_b, nullptr, qkv, C, lp.nt, 3 * C, map, heads, B_, scale * kLog2e, pow2_cols(lp.nt), lp.kpc);
         else
-            linear_tc_kernel<true, __nv_bfloat16, F16, uint16_t><<<grid, 128, smem, st>>>((const __nv_bfloat16 *)x, qkv_w, qkv_b, qkv, C, nt, 3 * C, map, heads, B_, scale * kLog2e, pow2_cols(nt));
+            linear_tc_kernel<true, __nv_bfloat16, F16, uint16_t, false><<<grid, 128, lp.smem, st>>>((const __nv_bfloat16 *)x, nullptr, qkv_w, nullptr, qkv_b, nullptr, qkv, C, lp.nt, 3 * C, map, heads, B_, scale * kLog2e, pow2_cols(lp.nt), lp.kpc);
         WF_LAUNCH_CHECK();
     }
     {
@@ -508,18 +670,64 @@ static int attn_tc_run(const void *x, int x_dtype, const uint16_t *qkv_w, const 
         int groups = kNumSMs / combos;
         if (groups < 1) groups = 1;
         if (groups > B_) groups = (int)B_;
-        attn_core_tc_kernel<F16><<<combos * groups, 544, kCoreSmem, st>>>(qkv, bias_img, obuf, heads, B_, groups);
+        attn_core_tc_kernel<F16, false><<<combos * groups, 544, kCoreSmem, st>>>(qkv, bias_img, obuf, heads, B_, groups);
         WF_LAUNCH_CHECK();
     }
     {
-        const int nt = pick_ntile(C);
-        if (!nt) return WF_ERR_BAD_SHAPE;
-        const size_t smem = (size_t)kchunks * 2048 + (size_t)kchunks * nt * 16;
-        dim3 grid((unsigned)(M / 128), (unsigned)(C / nt));
+        const LinearPlan lp = plan_linear(C, C, false);
+        if (!lp.nt || lp.smem > 200 * 1024) return WF_ERR_BAD_SHAPE;
+        dim3 grid((unsigned)(M / 128), (unsigned)(C / lp.nt));
         if (out_f32)
-            linear_tc_kernel<false, uint16_t, F16, float><<<grid, 128, smem, st>>>(obuf, proj_w, proj_b, (float *)out, C, nt, C, map, heads, B_, 1.f, pow2_cols(nt));
+            linear_tc_kernel<false, uint16_t, F16, float, false><<<grid, 128, lp.smem, st>>>(obuf, nullptr, proj_w, nullptr, proj_b, nullptr, (float *)out, C, lp.nt, C, map, heads, B_, 1.f, pow2_cols(lp.nt), lp.kpc);
         else
-            linear_tc_kernel<false, uint16_t, F16, uint16_t><<<grid, 128, smem, st>>>(obuf, proj_w, proj_b, (uint16_t *)out, C, nt, C, map, heads, B_, 1.f, pow2_cols(nt));
+            linear_tc_kernel<false, uint16_t, F16, uint16_t, false><<<grid, 128, lp.smem, st>>>(obuf, nullptr, proj_w, nullptr, proj_b, nullptr, (uint16_t *)out, C, lp.nt, C, map, heads, B_, 1.f, pow2_cols(lp.nt), lp.kpc);
+        WF_LAUNCH_CHECK();
+    }
+    return WF_OK;
+}
+
+size_t attn_tc_split_workspace_bytes(int64_t tokens, int C) { return 7 * (size_t)tokens * (size_t)C * 2 + 256; }
+
+// Compensated ("split") fp16 path: x fp32, weights as hi / lo fp16 pairs, fp32 biases, fp32 result.
+// workspace: [5][B_][heads][2][512][8] (q hi, k hi, v, q lo, k lo) + [2][M][C] (o hi, o lo), 16-bit.
+int attn_tc_forward_split(const float *x, const uint16_t *qkv_w_hi, const uint16_t *qkv_w_lo, const float *qkv_b,
+                          const uint16_t *proj_w_hi, const uint16_t *proj_w_lo, const float *proj_b, const uint16_t *bias_img,
+                          float *out, void *workspace, int B, int D1, int H1, int W1, int C, int heads, float scale,
+                          cudaStream_t st) {
+    TcWindowMap map;
+    map.D1 = D1; map.H1 = H1; map.W1 = W1;
+    map.nWy = H1 / 8; map.nWx = W1 / 8; map.nW = (D1 / 8) * map.nWy * map.nWx;
+    const int64_t B_ = (int64_t)B * map.nW;
+    const int64_t M = B_ * 512;
+    uint16_t *qkv = reinterpret_cast<uint16_t *>(workspace);
+    uint16_t *obuf = qkv + 5 * M * C;                         // [2][M][C]
+    static unsigned long long attrs_done = 0;   // per-device opt-in bits
+    if (first_use_on_current_device(attrs_done)) {
+        const int big = 200 * 1024;
+        WF_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel<true, float, true, uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel<false, uint16_t, true, float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(attn_core_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCoreSmemSplit));
+    }
+    {
+        const LinearPlan lp = plan_linear(C, 3 * C, true);
+        if (!lp.nt || lp.smem > 200 * 1024) return WF_ERR_BAD_SHAPE;
+        dim3 grid((unsigned)(M / 128), (unsigned)(3 * C / lp.nt));
+        linear_tc_kernel<true, float, true, uint16_t, true><<<grid, 128, lp.smem, st>>>(x, nullptr, qkv_w_hi, qkv_w_lo, nullptr, qkv_b, qkv, C, lp.nt, 3 * C, map, heads, B_, scale * kLog2e, pow2_cols(lp.nt), lp.kpc);
+        WF_LAUNCH_CHECK();
+    }
+    {
+        const int combos = heads * 4;
+        int groups = kNumSMs / combos;
+        if (groups < 1) groups = 1;
+        if (groups > B_) groups = (int)B_;
+        attn_core_tc_kernel<true, true><<<combos * groups, 544, kCoreSmemSplit, st>>>(qkv, bias_img, obuf, heads, B_, groups);
+        WF_LAUNCH_CHECK();
+    }
+    {
+        const LinearPlan lp = plan_linear(C, C, true);
+        if (!lp.nt || lp.smem > 200 * 1024) return WF_ERR_BAD_SHAPE;
+        dim3 grid((unsigned)(M / 128), (unsigned)(C / lp.nt));
+        linear_tc_kernel<false, uint16_t, true, float, true><<<grid, 128, lp.smem, st>>>(obuf, obuf + M * C, proj_w_hi, proj_w_lo, nullptr, proj_b, out, C, lp.nt, C, map, heads, B_, 1.f, pow2_cols(lp.nt), lp.kpc);
         WF_LAUNCH_CHECK();
     }
     return WF_OK;

@@ -80,9 +80,11 @@ class Attention(nn.Module):
             od = None
         img = self._bias_image(cd) if tc else None
         dense = None if tc else self._dense_bias()
+        # split_operands (prepare_inference, attention="fp16x2"): error-compensated fp16 pairs on the tensor cores
+        split = bool(getattr(self, "split_operands", False)) and tc and cd == torch.float16
         y = ops.window_attention(x, self.qkv.weight, self.qkv.bias, self.proj.weight, self.proj.bias,
                                  self.relative_position_bias_table, self.relative_position_index, dense,
-                                 self.num_heads, self.window_size, self.scale, cd, img, od)
+                                 self.num_heads, self.window_size, self.scale, cd, img, od, split)
         want = getattr(self, "out_dtype", None)
         return y if want is None or y.dtype == want else y.to(want)
 

@@ -308,6 +308,46 @@ def window_attention_uses_tensor_cores(grid, C: int, heads: int, ws: int, comput
     return bool(_lib.lib().wf_window_attn_tc_supported(int(grid[0]), int(grid[1]), int(grid[2]), int(C), int(heads), int(ws)))
 
 
+_SPLIT_CACHE = {}
+
+
+def split_cached(p: torch.Tensor):
+    """``p`` as an error-compensated fp16 pair ``(hi, lo)``, ``hi = fp16(p)``, ``lo = fp16(p - hi)`` (22 significant bits
+    together); cached like ``cast_cached`` until ``p`` is modified, moved or freed."""
+    def build():
+        f = p.detach().float().contiguous()
+        hi = f.half()
+        return hi, (f - hi.float()).half()
+
+    return _pack_cached(_SPLIT_CACHE, id(p), (p._version, p.data_ptr(), p.device, p.dtype, tuple(p.shape)), p, build)
+
+
+def _window_attention_split(x, qkv_w, qkv_b, proj_w, proj_b, bias_img, heads: int, ws: int, scale: float) -> torch.Tensor:
+    """wf_window_attn_fwd_split: compensated fp16 operands on the tensor cores, fp32 in / out."""
+    dev = _need_cuda(x, qkv_w, qkv_b, proj_w, proj_b, bias_img)
+    if x.dim() != 5:
+        raise ValueError("expected x [B, D1, H1, W1, C]")
+    if qkv_b is None or bias_img is None or bias_img.dtype != torch.float16:
+        raise ValueError("the compensated attention path needs a qkv bias and the fp16 bias image")
+    x = x.float().contiguous()
+    B, D1, H1, W1, C = x.shape
+    L = _lib.lib()
+    nbytes = L.wf_window_attn_split_workspace_bytes(B, D1, H1, W1, C, heads, ws)
+    if nbytes == 0:
+        raise ValueError(f"window attention: unsupported geometry grid={(D1, H1, W1)} C={C} heads={heads} ws={ws}")
+    work = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    out = torch.empty(x.shape, dtype=torch.float32, device=dev)
+    (qh, ql), (ph, pl) = split_cached(qkv_w), split_cached(proj_w)
+    with torch.cuda.device(dev):
+        st = L.wf_window_attn_fwd_split(x.data_ptr(), qh.data_ptr(), ql.data_ptr(), f32_cached(qkv_b).data_ptr(),
+                                        ph.data_ptr(), pl.data_ptr(), f32_cached(proj_b).data_ptr(), bias_img.data_ptr(),
+                                        out.data_ptr(), work.data_ptr(), nbytes, B, D1, H1, W1, C, heads, ws, float(scale),
+                                        _stream(dev))
+    _lib.check(st, "wf_window_attn_fwd_split")
+    _count(3)
+    return out
+
+
 def _window_attention_raw(x, qkv_w, qkv_b, proj_w, proj_b, bias_t, heads: int, ws: int, scale: float,
                           compute_dtype: Optional[torch.dtype] = None, bias_img: Optional[torch.Tensor] = None,
                           out_dtype: Optional[torch.dtype] = None, return_workspace: bool = False):
@@ -401,9 +441,11 @@ class _WindowAttention(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, qkv_w, qkv_b, proj_w, proj_b, table, index, bias_t, heads, ws, scale, compute_dtype, bias_img,
-                out_dtype):
+                out_dtype, split=False):
         ctx.save_for_backward(x, qkv_w, qkv_b, proj_w, proj_b, table, index)
         ctx.cfg = (heads, ws, scale)
+        if split:
+            return _window_attention_split(x, qkv_w, qkv_b, proj_w, proj_b, bias_img, heads, ws, scale)
         return _window_attention_raw(x, qkv_w, qkv_b, proj_w, proj_b, bias_t, heads, ws, scale, compute_dtype, bias_img,
                                      out_dtype)
 
@@ -414,18 +456,18 @@ class _WindowAttention(torch.autograd.Function):
         srcs = (x, qkv_w, qkv_b, proj_w, proj_b, table)
         grads = _window_attention_backward(g, x, qkv_w, qkv_b, proj_w, proj_b, table, index, heads, ws, scale)
         out = tuple(None if (s_ is None or g_ is None) else g_.to(s_.dtype) for s_, g_ in zip(srcs, grads))
-        return out + (None,) * 8
+        return out + (None,) * 9
 
 
 def window_attention(x, qkv_w, qkv_b, proj_w, proj_b, table, index, bias_t, heads: int, ws: int, scale: float,
                      compute_dtype: Optional[torch.dtype] = None, bias_img: Optional[torch.Tensor] = None,
-                     out_dtype: Optional[torch.dtype] = None):
+                     out_dtype: Optional[torch.dtype] = None, split: bool = False):
     """Window partition + attention + reshape-only reverse on channels-last ``x[B, D1, H1, W1, C]``.
 
     Returns the window-major result buffer viewed as ``[B, D1, H1, W1, C]`` - exactly what the reference produces at
     ``wave_helper.py:497-499`` (it never applies the inverse permute)."""
     return _WindowAttention.apply(x, qkv_w, qkv_b, proj_w, proj_b, table, index, bias_t, heads, ws, scale, compute_dtype,
-                                  bias_img, out_dtype)
+                                  bias_img, out_dtype, split)
 
 
 

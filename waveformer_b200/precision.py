@@ -31,10 +31,10 @@ from .network_models.waveformer import MultiscaleTransformer
 __all__ = ["prepare_inference"]
 
 # every attribute prepare_inference may leave on a module (instance attributes only; cleared before each preparation)
-_POLICY_ATTRS = ("compute_dtype", "out_dtype", "hf_dtype", "skip_dtype", "tf32", "logits_dtype", "io_dtype")
+_POLICY_ATTRS = ("compute_dtype", "out_dtype", "hf_dtype", "skip_dtype", "tf32", "logits_dtype", "io_dtype", "split_operands")
 
 
-def prepare_inference(model: nn.Module, dtype: torch.dtype = torch.bfloat16, *, attention: str = "fp16",
+def prepare_inference(model: nn.Module, dtype: torch.dtype = torch.bfloat16, *, attention: str = "fp16x2",
                       fp32_stream: bool = True, skip_blocks: str = "fp16", storage: str = "fp16") -> nn.Module:
     """Put ``model`` (a ``Waveformer``) into inference form on its current device.
 
@@ -43,7 +43,8 @@ def prepare_inference(model: nn.Module, dtype: torch.dtype = torch.bfloat16, *, 
     weights and tensor-core operands outside attention: "fp16" (default; 10-bit mantissa at the speed of bf16 - every such
     tensor is InstanceNorm'd / LayerNorm'd or one GEMM away from it, so fp16's range is no concern) or "bf16" (round 1's
     policy: 3x the logit error, 0.3 % more argmax flips).  ``attention`` selects the operand format of the
-    window-attention GEMMs ("fp16", "bf16" or "fp32" = CUDA-core kernels); ``fp32_stream=False`` gives the plain all-bf16
+    window-attention GEMMs: "fp16x2" (default: error-compensated fp16 pairs on the tensor cores - the scores the softmax
+    exponentiates are exact to fp32 level), "fp16", "bf16", or "fp32" = CUDA-core kernels; ``fp32_stream=False`` gives the plain all-bf16
     model (``model.to(torch.bfloat16)``), kept for the precision study.  ``skip_blocks`` (only with ``storage="bf16"``) is the
     format of the residual blocks encoder2..4: "tf32" (fp32 storage, TF32 tensor-core convolutions), "fp16" (fp16 storage and
     operands) or "bf16" (no special treatment).
@@ -59,8 +60,8 @@ def prepare_inference(model: nn.Module, dtype: torch.dtype = torch.bfloat16, *, 
         return model.to(memory_format=torch.channels_last_3d)
     if dtype != torch.bfloat16:
         raise ValueError("prepare_inference supports float32 and bfloat16 (= the 16-bit policy)")
-    if attention not in ("fp16", "bf16", "fp32"):
-        raise ValueError("attention must be 'fp16', 'bf16' or 'fp32'")
+    if attention not in ("fp16x2", "fp16", "bf16", "fp32"):
+        raise ValueError("attention must be 'fp16x2', 'fp16', 'bf16' or 'fp32'")
     if skip_blocks not in ("tf32", "fp16", "bf16"):
         raise ValueError("skip_blocks must be 'tf32', 'fp16' or 'bf16'")
     if storage not in ("fp16", "bf16"):
@@ -70,7 +71,7 @@ def prepare_inference(model: nn.Module, dtype: torch.dtype = torch.bfloat16, *, 
     h16 = torch.float16 if storage == "fp16" else torch.bfloat16
     if storage == "fp16":
         skip_blocks = "fp16"                           # they are ordinary members of the fp16 U-Net then
-    attn_dtype = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[attention]
+    attn_dtype = {"fp16x2": torch.float16, "fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[attention]
     keep = set()                                       # parameters that stay fp32 (never rounded to 16 bits)
     half = set()                                       # parameters stored as fp16 inside a bf16 model (skip blocks)
 
@@ -85,6 +86,7 @@ def prepare_inference(model: nn.Module, dtype: torch.dtype = torch.bfloat16, *, 
             keep_fp32(m)                                # fp32 master weights; 16-bit operand copies are cached per dtype
             m.compute_dtype = attn_dtype
             m.out_dtype = torch.float32
+            m.split_operands = attention == "fp16x2"
         elif isinstance(m, (nn.LayerNorm, nn.GroupNorm)):
             keep_fp32(m)                                # the normalisation kernels read gamma / beta as fp32
         if isinstance(m, CCF_FFN):
