@@ -218,6 +218,47 @@ def test_training_step_gradients_match_oracle():
     assert checked > 120
 
 
+def test_bf16_autocast_training_step_gradients_match_oracle():
+    """BASELINE configs[4]: a bf16-autocast training step (forward + backward, Dice + CE loss) at the window geometry
+    the tensor-core kernels need (128^3: 512-token windows), through the custom DWT / attention / IDWT kernels, vs fp32
+    autograd through the CPU oracle: loss within 1 %, per-parameter gradient cosine >= 0.99 (north star / SURVEY 8d)."""
+    import torch.nn.functional as F
+    from waveformer_b200 import ops
+    from waveformer_b200.losses import DiceCELoss
+    from waveformer_b200.network_models import Waveformer
+    cfg = ModelConfig(img_size=(128,) * 3)
+    sd0 = make_state_dict(cfg, seed=3)
+    x = seeded_randn((1, 4, 128, 128, 128), 5)
+    y = torch.randint(0, 4, (1, 1, 128, 128, 128), generator=torch.Generator().manual_seed(6))
+    loss_fn = DiceCELoss(to_onehot_y=True, softmax=True)
+    kw = dict(cfg.kwargs())
+    kw["drop_path_rate"] = 0.0
+    m = Waveformer(**kw).train()
+    m.load_state_dict(sd0, strict=True)
+    m = m.cuda()
+    before = ops.LAUNCHES
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        logits = m(x.cuda())
+    loss = loss_fn(logits, y.cuda())
+    loss.backward()
+    assert ops.LAUNCHES - before > 60          # the custom kernels (DWT, attention fwd / bwd, IDWT) are in the graph
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd0.items()}
+    ref_loss = loss_fn(om.waveformer_forward(sd, x, cfg), y)
+    ref_loss.backward()
+    assert abs(float(loss) - float(ref_loss)) < 1e-2 * max(1.0, abs(float(ref_loss)))
+    scale = max(float(v.grad.abs().max()) for v in sd.values() if v.grad is not None)
+    checked, worst = 0, (1.0, "")
+    for name, p in m.named_parameters():
+        g_ref = sd[name].grad
+        assert p.grad is not None, f"{name} received no gradient"
+        if g_ref is None or float(g_ref.abs().max()) < 1e-4 * scale:     # (near-)zero gradients: noise on both sides
+            continue
+        cos = float(F.cosine_similarity(p.grad.flatten().cpu().double(), g_ref.flatten().double(), dim=0))
+        worst = min(worst, (cos, name))
+        checked += 1
+    assert checked > 100 and worst[0] >= 0.99, worst
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
 def test_reference_default_constructor_geometry(dtype, tol):
     """The reference's own default arguments (network_backbone.py:134-152): img 96^3, in_chans 1, out_chans 13 -> window

@@ -179,6 +179,9 @@ for case, shape, shard in cases:
         assert owned == ([0] if rank == 0 else []) and (y is None) == (rank != 0)
     if case == "whole-volumes":
         assert owned == [rank]                      # contiguous runs of whole volumes: no collective at all
+        # the same cohort as a list in which a rank only holds the volume it stitches
+        y2 = inf([x[i] if i == rank else None for i in range(shape[0])], net)
+        assert inf.owned_volumes == [rank] and float((y2 - y).abs().max()) == 0.0
     got_owned = [None] * world
     dist.all_gather_object(got_owned, owned)
     assert sorted(v for o in got_owned for v in o) == list(range(shape[0])), got_owned   # every volume exactly once

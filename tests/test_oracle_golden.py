@@ -134,3 +134,22 @@ def test_sliding_window_identity_network_returns_input():
     x = seeded_randn((1, 3, 40, 24, 30), 9)
     y = osw.sliding_window_inference(x, (16, 16, 16), 2, lambda p: p, 0.5, "gaussian")
     assert float((y - x).abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("name,kw", [("default", dict(to_onehot_y=True, softmax=True)),
+                                     ("nobg_sq", dict(to_onehot_y=True, softmax=True, include_background=False, squared_pred=True,
+                                                      lambda_dice=0.7, lambda_ce=1.3)),
+                                     ("jaccard_batch", dict(to_onehot_y=True, softmax=True, jaccard=True, batch=True))])
+def test_dice_ce_loss_matches_reference_golden(name, kw):
+    """waveformer_b200.losses.DiceCELoss (BASELINE configs[4]: Dice + CE) vs the reference's vendored MONAI loss
+    (scripts/make_golden_loss.py), value and gradient; also under bf16 logits (autocast training)."""
+    from waveformer_b200.losses import DiceCELoss
+    g = load_npz("dice_ce_loss.npz")
+    x = (seeded_randn((2, 4, 12, 10, 14), 40) * 2.0).requires_grad_(True)
+    y = torch.randint(0, 4, (2, 1, 12, 10, 14), generator=torch.Generator().manual_seed(41))
+    loss = DiceCELoss(**kw)(x, y)
+    loss.backward()
+    assert abs(float(loss) - float(g[f"{name}_loss"])) < 1e-6
+    assert float((x.grad - torch.from_numpy(g[f"{name}_grad"])).abs().max()) < 1e-7
+    lb = DiceCELoss(**kw)(x.detach().bfloat16(), y)
+    assert lb.dtype == torch.float32 and abs(float(lb) - float(g[f"{name}_loss"])) < 2e-2

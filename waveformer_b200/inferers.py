@@ -309,7 +309,18 @@ def _run(inputs, roi_size, sw_batch_size, network, overlap, mode, sigma_scale, p
          host_holder: Optional[dict] = None, flip=0, into=None):
     """Returns ``(logits, labels, owned)``: ``logits[i]`` is the stitched fp32 volume ``owned[i]`` (indices into the
     input batch).  Single process: ``owned`` is every volume, i.e. exactly the reference's return value."""
-    if inputs.dim() != 5:
+    seq = None
+    if isinstance(inputs, (list, tuple)):
+        # volumes as a list ([C, D, H, W] or [1, C, D, H, W] each, one shape): with a process group a rank only needs the
+        # entries it stitches, the others may be None - nobody has to hold (or pin) the whole cohort
+        seq = [None if t is None else (t if t.dim() == 4 else t[0]) for t in inputs]
+        first = next((t for t in seq if t is not None), None)
+        if first is None or first.dim() != 4 or any(t is not None and t.shape != first.shape for t in seq):
+            raise ValueError("a list input needs at least one volume, and all volumes [C, D, H, W] of one shape")
+        probe = first[None]
+    else:
+        probe = inputs
+    if probe.dim() != 5:
         raise ValueError("the B200 inferer handles 3D volumes: inputs must be [B, C, D, H, W]")
     nsp = 3
     ov = tuple(overlap) if isinstance(overlap, (tuple, list)) else (overlap,) * nsp
@@ -325,9 +336,9 @@ def _run(inputs, roi_size, sw_batch_size, network, overlap, mode, sigma_scale, p
         import torch.distributed as dist
 
         world, rank = dist.get_world_size(group), dist.get_rank(group)
-    dev = inputs.device if inputs.is_cuda else _default_device(network)
-    batch = inputs.shape[0]
-    orig = tuple(inputs.shape[2:])
+    dev = probe.device if probe.is_cuda else _default_device(network)
+    batch = len(seq) if seq is not None else inputs.shape[0]
+    orig = tuple(probe.shape[2:])
     roi = tuple(int(r) if r and r > 0 else int(o) for r, o in zip(roi_size, orig))
     size = tuple(max(o, r) for o, r in zip(orig, roi))
     pad = []
@@ -348,24 +359,33 @@ def _run(inputs, roi_size, sw_batch_size, network, overlap, mode, sigma_scale, p
     in_events = None
     vol = None
     if plan.local_vols:
-        vol = inputs[plan.lo:plan.hi]
-        if not vol.is_cuda and vol.dtype == torch.float32 and not any(pad) and not flip and plan.tables:
+        if seq is not None:
+            parts = seq[plan.lo:plan.hi]
+            if any(t is None for t in parts):
+                raise ValueError(f"rank {rank} stitches volumes [{plan.lo}, {plan.hi}) and needs all of them in the list")
+        else:
+            vol = inputs[plan.lo:plan.hi]
+            parts = [vol[i] for i in range(vol.shape[0])]
+        on_host = not parts[0].is_cuda
+        if on_host and parts[0].dtype == torch.float32 and not any(pad) and not flip and plan.tables:
             # streamed H2D: z-slabs in the order the windows need them, one contiguous copy per (volume, channel, slab)
-            src = vol.contiguous()
-            vol = torch.empty(src.shape, dtype=torch.float32, device=dev)
+            srcs = [t.contiguous() for t in parts]
+            vol = torch.empty((len(srcs),) + tuple(srcs[0].shape), dtype=torch.float32, device=dev)
             cs = _copy_stream(dev)
             cs.wait_stream(cur)
             in_events = {}
             with torch.cuda.stream(cs):
-                for v in range(src.shape[0]):
+                for v, src in enumerate(srcs):
                     a = 0
                     for si, b in enumerate(plan.slab_ends):
-                        for c in range(src.shape[1]):
-                            vol[v, c, a:b].copy_(src[v, c, a:b], non_blocking=True)
+                        for c in range(src.shape[0]):
+                            vol[v, c, a:b].copy_(src[c, a:b], non_blocking=True)
                         in_events[(v, si)] = cs.record_event()
                         a = b
             vol.record_stream(cs)
-        elif not vol.is_cuda:
+        elif seq is not None:
+            vol = torch.stack([t.to(dev, non_blocking=True) for t in parts])
+        elif on_host:
             vol = vol.to(dev, non_blocking=True)
         if vol.dtype != torch.float32:
             vol = vol.float()

@@ -70,6 +70,14 @@ class Attention(nn.Module):
         # on the tensor cores, fp32 on CUDA cores) and the result type; x may be an fp32 residual stream either way
         cd = getattr(self, "compute_dtype", None) or x.dtype
         od = getattr(self, "out_dtype", None)
+        if torch.is_autocast_enabled() and getattr(self, "compute_dtype", None) is None and x.is_cuda:
+            # mixed-precision training (BASELINE configs[4]: bf16 autocast): the forward GEMMs take the autocast dtype on
+            # the tensor cores and return fp32 like every autocast Linear feeding a LayerNorm'd stream; the backward
+            # (ops._window_attention_backward) recomputes in fp32
+            cd = torch.get_autocast_dtype("cuda")
+            od = torch.float32
+            if x.dtype not in (torch.float32, torch.bfloat16):
+                x = x.float()
         tc = ops.window_attention_uses_tensor_cores(x.shape[1:4], self.dim, self.num_heads, self.window_size, cd)
         if os.environ.get("WF_ATTN_IMPL", "").startswith("s") or self.qkv.bias is None:
             tc = False   # tests force the CUDA-core kernels to cross-check the two device implementations
@@ -85,7 +93,7 @@ class Attention(nn.Module):
         y = ops.window_attention(x, self.qkv.weight, self.qkv.bias, self.proj.weight, self.proj.bias,
                                  self.relative_position_bias_table, self.relative_position_index, dense,
                                  self.num_heads, self.window_size, self.scale, cd, img, od, split)
-        want = getattr(self, "out_dtype", None)
+        want = getattr(self, "out_dtype", None) or (od if torch.is_autocast_enabled() else None)
         return y if want is None or y.dtype == want else y.to(want)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:

@@ -85,6 +85,14 @@ class UnetrIDWTBlock(nn.Module):
         n_levels = len(hf_coeffs)
         fuse_cat = not torch.is_grad_enabled()                          # write level-0 output straight into the concat buffer
         for i, det in enumerate(hf_coeffs):
+            if torch.is_autocast_enabled() and isinstance(det, dict) and len(det) and cur.dtype != next(iter(det.values())).dtype:
+                # mixed-precision training: conv_lf_block ran in the autocast dtype while the encoder's detail bands are
+                # fp32 (they come from the fp32 LayerNorm output).  ptwt.waverec3 rejects such a mix (and the reference
+                # therefore trains with autocast disabled, trainer.py:454); here the synthesis simply runs in the wider
+                # type - the residual block behind it is autocast again.
+                wide = torch.promote_types(cur.dtype, next(iter(det.values())).dtype)
+                cur = cur.to(wide)
+                det = {k: v.to(wide) for k, v in det.items()}
             like = cur.permute(0, 4, 1, 2, 3)
             stack = self._channels_last_stack(det, like)
             gate = None
