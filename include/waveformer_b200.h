@@ -235,6 +235,20 @@ int wf_upsample_trilinear_add_ndhwc(const void *const *srcs, const int *src_dims
                                     int src_dtype, int io_dtype, int align_corners, int B, int D, int H, int W, int C,
                                     int64_t base_vox_stride, int64_t y_vox_stride, void *stream);
 
+/* CCF_FFN's two pointwise GEMMs fused with the normalisations around them (tcgen05; C = 48 or 96, i.e. encoder stages 1
+ * and 2).  Reference: `x = x + drop_path(mlp(norm2(x)))` (network_models/wave_helper.py:509) with CCF_FFN.forward
+ * (wave_helper.py:260-294) = n + fc(GELU(LN(dwconv(GELU(LN(pwconv(n))))))), n = norm2(x).
+ *   wf_ffn_front: t1[r, :4C] = GELU(LayerNorm_4C(pw_w . LayerNorm_C(x[r, :C]) + pw_b))     x fp32 -> t1 16-bit (dtype)
+ *   wf_ffn_back : out[r, :C] = x[r] + LayerNorm_C(x[r]) + fc_w . GELU(LayerNorm_4C(t2[r, :4C])) + fc_b      -> fp32
+ * (the depthwise 3^3 stencil between them is wf_dwconv3d_ndhwc).  pw_w [4C, C] and fc_w [C, 4C] are in `dtype`
+ * (WF_BF16 / WF_F16), every bias / gamma / beta is fp32 (NULL = identity), rows are voxels (dense). */
+int wf_ffn_front(const float *x, const float *norm2_w, const float *norm2_b, float norm2_eps, const void *pw_w,
+                 const float *pw_b, const float *ln_w, const float *ln_b, float ln_eps, void *t1, int dtype, int64_t rows,
+                 int C, void *stream);
+int wf_ffn_back(const void *t2, int dtype, const float *ln_w, const float *ln_b, float ln_eps, const void *fc_w,
+                const float *fc_b, const float *x, const float *norm2_w, const float *norm2_b, float norm2_eps, float *out,
+                int64_t rows, int C, void *stream);
+
 /* 3x3x3 convolution (padding 1, no bias) of a 4-channel channels-last volume x [B, D, H, W, 4] (op_dtype WF_BF16 or
  * WF_F16 = format of the tensor-core operands, of wpack and of both results; x_dtype = WF_F32 - converted while gathered -
  * or op_dtype; fp32 accumulation), fused with an optional 1x1x1 convolution of the same input and with the InstanceNorm

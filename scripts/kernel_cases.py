@@ -59,6 +59,30 @@ elif args.case == "attn":    # stage-1 level-1 attention at sw_batch 2
     att.compute_dtype, att.out_dtype = torch.float16, torch.float32
     x = rn(2, 32, 32, 32, 48)
     fns = {"window_attention_s1L1": lambda: att.forward_grid(x)}
+elif args.case == "ffn":     # CCF_FFN stage 1 (2 x 64^3 x 48 -> 192 -> 48) and stage 2, fused front / back kernels vs the launches they replace
+    import torch.nn as nn
+    fns = {}
+    for C, n in ((48, 2 * 64 ** 3), (96, 2 * 32 ** 3)):
+        x = rn(n, C)
+        norm2, ln = nn.LayerNorm(C, eps=1e-6).cuda(), nn.LayerNorm(4 * C).cuda()
+        w1, b1, wfc, bfc = rn(4 * C, C) / C ** 0.5, rn(4 * C) * 0.1, rn(C, 4 * C) / (4 * C) ** 0.5, rn(C) * 0.1
+        t2 = rn(n, 4 * C).half()
+        w1h, wfch = w1.half(), wfc.half()
+        fns[f"ffn_front C={C}"] = lambda x=x, norm2=norm2, w1=w1, b1=b1, ln=ln: ops.ffn_front(x, norm2, w1, b1, ln, torch.float16)
+        fns[f"ffn_back C={C}"] = lambda t2=t2, ln=ln, wfc=wfc, bfc=bfc, x=x, norm2=norm2: ops.ffn_back(t2, ln, wfc, bfc, x, norm2)
+
+        def unfused_front(x=x, norm2=norm2, w1h=w1h, b1=b1, ln=ln):
+            n_, nop = ops.layer_norm_cl(x, norm2.weight, norm2.bias, norm2.eps, also_bf16=torch.float16)
+            t = torch.nn.functional.linear(nop, w1h, b1.half())
+            return ops.layer_norm_cl(t, ln.weight, ln.bias, ln.eps, gelu=True)
+
+        def unfused_back(t2=t2, ln=ln, wfch=wfch, bfc=bfc, x=x):
+            t = ops.layer_norm_cl(t2, ln.weight, ln.bias, ln.eps, gelu=True)
+            f = torch.mm(t, wfch.t(), out_dtype=torch.float32)
+            return ops.residual_sum(x, x, f, bfc)
+
+        fns[f"unfused front (LN + GEMM + LN/GELU) C={C}"] = unfused_front
+        fns[f"unfused back (LN/GELU + GEMM + residual) C={C}"] = unfused_back
 else:
     raise SystemExit("unknown case")
 

@@ -5,6 +5,7 @@ import torch
 import torch.nn.functional as F
 
 from helpers import max_rel, seeded_randn
+from oracle.state import ModelConfig, make_state_dict
 
 pytestmark = pytest.mark.gpu
 
@@ -343,3 +344,52 @@ def test_depthwise_conv_with_fused_statistics(shape):
     want = ops.instance_norm_stats(want_y.permute(0, 4, 1, 2, 3), eps=1e-5)
     assert max_rel(mr.view(-1, 2)[:, 0].cpu(), want.view(-1, 2)[:, 0].cpu()) < 1e-4
     assert max_rel(mr.view(-1, 2)[:, 1].cpu(), want.view(-1, 2)[:, 1].cpu()) < 1e-4
+
+
+@pytest.mark.parametrize("C,rows", [(48, 128 * 37 + 5), (96, 128 * 9 + 77), (48, 64)])
+@pytest.mark.parametrize("fmt,tol", [(torch.float16, 2e-3), (torch.bfloat16, 1.5e-2)])
+def test_fused_ffn_kernels_match_module_math(C, rows, fmt, tol):
+    """wf_ffn_front / wf_ffn_back (CCF_FFN's pointwise GEMMs fused with norm2, both LayerNorm + GELU stages, the fc bias and
+    both residuals; reference wave_helper.py:260-294,509) vs the same arithmetic in fp32 torch ops."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from waveformer_b200 import ops
+    g = torch.Generator().manual_seed(C + rows)
+    x = (torch.randn((rows, C), generator=g) * 1.5 + 0.3).cuda()
+    norm2 = nn.LayerNorm(C, eps=1e-6).cuda()
+    ln1, ln2 = nn.LayerNorm(4 * C).cuda(), nn.LayerNorm(4 * C).cuda()
+    for ln in (norm2, ln1, ln2):
+        ln.weight.data = (1.0 + 0.2 * torch.randn(ln.weight.shape, generator=g)).cuda()
+        ln.bias.data = (0.1 * torch.randn(ln.bias.shape, generator=g)).cuda()
+    w1 = (torch.randn((4 * C, C), generator=g) / C ** 0.5).cuda()
+    b1 = (0.2 * torch.randn((4 * C,), generator=g)).cuda()
+    wfc = (torch.randn((C, 4 * C), generator=g) / (4 * C) ** 0.5).cuda()
+    bfc = (0.2 * torch.randn((C,), generator=g)).cuda()
+    with torch.no_grad():
+        n = norm2(x)
+        want1 = F.gelu(ln1(F.linear(n, w1, b1)))
+        got1 = ops.ffn_front(x, norm2, w1, b1, ln1, fmt)
+        assert got1.dtype == fmt and tuple(got1.shape) == (rows, 4 * C)
+        assert max_rel(got1.float(), want1) < tol
+        t2 = (torch.randn((rows, 4 * C), generator=g) * 0.7 + 0.1).cuda().to(fmt)
+        want2 = x + n + F.linear(F.gelu(ln2(t2.float())), wfc, bfc)
+        got2 = ops.ffn_back(t2, ln2, wfc, bfc, x, norm2)
+        assert got2.dtype == torch.float32 and max_rel(got2, want2) < tol
+
+
+def test_block_with_fused_ffn_equals_unfused_path(monkeypatch):
+    """A stage-1 block under the 16-bit policy: the fused FFN kernels and the unfused sequence of launches agree."""
+    from waveformer_b200 import prepare_inference
+    from waveformer_b200.network_models import Waveformer
+    cfg = ModelConfig(img_size=(64,) * 3)
+    m = Waveformer(**cfg.kwargs()).eval()
+    m.load_state_dict(make_state_dict(cfg, seed=0), strict=True)
+    m = prepare_inference(m.cuda(), torch.bfloat16)
+    blk = m.waveformer_encoder.block1[0]
+    x = seeded_randn((2, 32, 32, 32, 48), 123).cuda()
+    with torch.no_grad():
+        monkeypatch.setenv("WF_FFN_FUSED", "0")
+        want, _ = blk(x)
+        monkeypatch.setenv("WF_FFN_FUSED", "1")
+        got, _ = blk(x)
+    assert max_rel(got, want) < 2e-3

@@ -7,6 +7,7 @@ reference checkpoint loads with ``strict=True``.
 from __future__ import annotations
 
 import itertools
+import os
 from typing import Optional
 
 import torch
@@ -349,7 +350,14 @@ class Block(nn.Module):
         else:
             y = x + coarse[0] if len(coarse) == 1 else x + sum(coarse)
         cd = getattr(self.mlp, "compute_dtype", None)
-        if cd is not None and cd != y.dtype:
+        mlp = self.mlp
+        if (cd is not None and ops.ffn_fused_supported(y, mlp.C_hid, cd) and isinstance(mlp.act, nn.GELU)
+                and getattr(mlp.act, "approximate", "none") == "none" and os.environ.get("WF_FFN_FUSED", "1") != "0"):
+            # stages 1 / 2: norm2 + pwconv + LN + GELU in one kernel, the stencil, LN + GELU + fc + both residuals in another
+            t = ops.ffn_front(y, self.norm2, mlp.pwconv.weight, mlp.pwconv.bias, mlp.norm1, cd)
+            t = ops.dwconv3d_channels_last(t, *mlp._packed_dwconv())
+            y = ops.ffn_back(t, mlp.norm2, mlp.fc.weight, mlp.fc.bias, y, self.norm2)
+        elif cd is not None and cd != y.dtype:
             # fp32 stream: LayerNorm writes the fp32 copy (CCF_FFN's own residual, wave_helper.py:293) and the bf16 GEMM
             # operand in one pass; y + n + ffn(n) is accumulated in fp32
             n, nop = _ln(self.norm2, y, also_bf16=cd)

@@ -812,6 +812,50 @@ def layer_norm_cl(x: torch.Tensor, weight: Optional[torch.Tensor], bias: Optiona
     return (y, y2) if also_bf16 else y
 
 
+def ffn_fused_supported(x: torch.Tensor, C_hid: int, fmt: Optional[torch.dtype]) -> bool:
+    """wf_ffn_front / wf_ffn_back cover the fp32-stream, 16-bit-operand FFN of encoder stages 1 and 2 (C = 48 / 96, 4C hidden)."""
+    return (x.is_cuda and x.dtype == torch.float32 and fmt in HALF_TYPES and x.shape[-1] in (48, 96)
+            and C_hid == 4 * x.shape[-1] and x.is_contiguous())
+
+
+def ffn_front(x: torch.Tensor, norm2: torch.nn.LayerNorm, pw_weight: torch.Tensor, pw_bias: Optional[torch.Tensor],
+              ln: torch.nn.LayerNorm, fmt: torch.dtype) -> torch.Tensor:
+    """``GELU(ln(pwconv(norm2(x))))`` for the fp32 stream ``x[..., C]`` -> ``[..., 4C]`` in ``fmt`` (one kernel)."""
+    dev = _need_cuda(x, pw_weight, pw_bias)
+    C = x.shape[-1]
+    rows = x.numel() // C
+    t1 = torch.empty(x.shape[:-1] + (4 * C,), dtype=fmt, device=dev)
+    w = cast_cached(pw_weight, fmt).view(4 * C, C)
+    with torch.cuda.device(dev):
+        st = _lib.lib().wf_ffn_front(x.data_ptr(), _ptr(f32_cached(norm2.weight)), _ptr(f32_cached(norm2.bias)), float(norm2.eps),
+                                     w.data_ptr(), _ptr(f32_cached(pw_bias)), _ptr(f32_cached(ln.weight)),
+                                     _ptr(f32_cached(ln.bias)), float(ln.eps), t1.data_ptr(), _dtype_code(fmt), rows, C,
+                                     _stream(dev))
+    _lib.check(st, "wf_ffn_front")
+    _count()
+    return t1
+
+
+def ffn_back(t2: torch.Tensor, ln: torch.nn.LayerNorm, fc_weight: torch.Tensor, fc_bias: Optional[torch.Tensor],
+             x: torch.Tensor, norm2: torch.nn.LayerNorm) -> torch.Tensor:
+    """``x + norm2(x) + fc(GELU(ln(t2)))`` -> fp32 ``[..., C]`` (one kernel; ``t2[..., 4C]`` 16-bit, ``x`` the fp32 stream)."""
+    dev = _need_cuda(t2, fc_weight, fc_bias, x)
+    C = x.shape[-1]
+    rows = x.numel() // C
+    if not t2.is_contiguous() or t2.shape[-1] != 4 * C or t2.numel() != rows * 4 * C:
+        raise ValueError("ffn_back: t2 must be the dense [..., 4C] companion of x")
+    out = torch.empty_like(x)
+    w = cast_cached(fc_weight, t2.dtype)
+    with torch.cuda.device(dev):
+        st = _lib.lib().wf_ffn_back(t2.data_ptr(), _dtype_code(t2), _ptr(f32_cached(ln.weight)), _ptr(f32_cached(ln.bias)),
+                                    float(ln.eps), w.data_ptr(), _ptr(f32_cached(fc_bias)), x.data_ptr(),
+                                    _ptr(f32_cached(norm2.weight)), _ptr(f32_cached(norm2.bias)), float(norm2.eps),
+                                    out.data_ptr(), rows, C, _stream(dev))
+    _lib.check(st, "wf_ffn_back")
+    _count()
+    return out
+
+
 def gelu_(x: torch.Tensor) -> torch.Tensor:
     """In-place exact (erf) GELU of a contiguous bf16 / fp32 tensor."""
     dev = _need_cuda(x)
