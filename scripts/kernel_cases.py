@@ -29,8 +29,8 @@ elif args.case == "c4":      # encoder1: 2 x 4 x 128^3 fp32 window -> conv1 + co
     w1, w3 = (rn(48, 4, 3, 3, 3) * 0.1).bfloat16(), (rn(48, 4, 1, 1, 1) * 0.5).bfloat16()
     fns = {"conv3d_c4_in_stats": lambda: ops.conv3d_c4_in_stats(x, w1, w3)}
 elif args.case == "k3":      # encoder1 / decoder1 conv2: 48 -> 48 at 2 x 128^3, fused input IN + lrelu and output statistics
-    x = rn(2, 128, 128, 128, 48).bfloat16().permute(0, 4, 1, 2, 3)
-    w = (rn(48, 48, 3, 3, 3) / 36).bfloat16()
+    x = rn(2, 128, 128, 128, 48).half().permute(0, 4, 1, 2, 3)          # fp16: the 16-bit policy's storage format
+    w = (rn(48, 48, 3, 3, 3) / 36).half()
     st = ops.instance_norm_stats(x)
     fns = {"conv3d_k3_c48 (fused in-norm + stats)": lambda: ops.conv3d_k3_c48(x, w, in_stats=st),
            "conv3d_k3_c48 (plain + stats)": lambda: ops.conv3d_k3_c48(x, w),
@@ -56,9 +56,12 @@ elif args.case == "head":    # decoder1's last kernel: IN + IN(res) + lrelu + 1x
 elif args.case == "attn":    # stage-1 level-1 attention at sw_batch 2
     from waveformer_b200.network_models import Attention
     att = Attention(48, num_heads=3, qkv_bias=True, window_size=8).cuda().eval()
-    att.compute_dtype, att.out_dtype = torch.float16, torch.float32
+    att.compute_dtype, att.out_dtype, att.split_operands = torch.float16, torch.float32, True
+    att2 = Attention(48, num_heads=3, qkv_bias=True, window_size=8).cuda().eval()
+    att2.compute_dtype, att2.out_dtype = torch.float16, torch.float32
     x = rn(2, 32, 32, 32, 48)
-    fns = {"window_attention_s1L1": lambda: att.forward_grid(x)}
+    fns = {"window_attention_s1L1 (fp16x2: compensated operands, the policy's default)": lambda: att.forward_grid(x),
+           "window_attention_s1L1 (plain fp16 operands)": lambda: att2.forward_grid(x)}
 elif args.case == "ffn":     # CCF_FFN stage 1 (2 x 64^3 x 48 -> 192 -> 48) and stage 2, fused front / back kernels vs the launches they replace
     import torch.nn as nn
     fns = {}

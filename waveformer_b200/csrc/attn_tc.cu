@@ -127,55 +127,97 @@ __global__ void __launch_bounds__(128) linear_tc_kernel(const TA *__restrict__ A
         const int kc0 = p * kpc;
         // A tile: row r = tid, every 16-byte K chunk.  A warp writes 32 consecutive rows of one chunk: conflict-free.
         // (pass p > 0: every thread has waited for the previous pass's MMAs below, so the images may be overwritten)
+        // Chunks are handled four at a time with all their global loads issued before the first conversion: the
+        // single-window stages (C = 192 / 384) launch a handful of CTAs whose time IS this loop's load latency.
         {
             constexpr bool raw = sizeof(TA) == 2 && (std::is_same<TA, uint16_t>::value || !F16);
             if constexpr (raw) {
                 const uint4 *src = reinterpret_cast<const uint4 *>(A + src_row * K) + kc0;
-                for (int kc = 0; kc < kpc; ++kc)
-                    *reinterpret_cast<uint4 *>(sA + (size_t)kc * 2048 + tid * 16) = __ldg(src + kc);
-                if constexpr (SPLIT) {
-                    const uint4 *srl = reinterpret_cast<const uint4 *>(A_lo + src_row * K) + kc0;
-                    for (int kc = 0; kc < kpc; ++kc)
-                        *reinterpret_cast<uint4 *>(sAl + (size_t)kc * 2048 + tid * 16) = __ldg(srl + kc);
+                const uint4 *srl = SPLIT ? reinterpret_cast<const uint4 *>(A_lo + src_row * K) + kc0 : nullptr;
+                for (int kc = 0; kc < kpc; kc += 4) {
+                    uint4 h[4], l[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (kc + u < kpc) {
+                            h[u] = __ldg(src + kc + u);
+                            if constexpr (SPLIT) l[u] = __ldg(srl + kc + u);
+                        }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (kc + u < kpc) {
+                            *reinterpret_cast<uint4 *>(sA + (size_t)(kc + u) * 2048 + tid * 16) = h[u];
+                            if constexpr (SPLIT) *reinterpret_cast<uint4 *>(sAl + (size_t)(kc + u) * 2048 + tid * 16) = l[u];
+                        }
                 }
             } else if constexpr (sizeof(TA) == 2) {  // bf16 activations, fp16 operands
                 const uint4 *src = reinterpret_cast<const uint4 *>(A + src_row * K) + kc0;
-                for (int kc = 0; kc < kpc; ++kc) {
-                    const uint4 a = __ldg(src + kc);
-                    const uint32_t w[4] = {a.x, a.y, a.z, a.w};
-                    uint4 u;
-                    uint32_t *uw = &u.x;
+                for (int kc = 0; kc < kpc; kc += 4) {
+                    uint4 h[4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        uw[e] = pack16<F16>(__uint_as_float(w[e] << 16), __uint_as_float(w[e] & 0xffff0000u));
-                    *reinterpret_cast<uint4 *>(sA + (size_t)kc * 2048 + tid * 16) = u;
+                    for (int u = 0; u < 4; ++u)
+                        if (kc + u < kpc) h[u] = __ldg(src + kc + u);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (kc + u < kpc) {
+                            const uint32_t w[4] = {h[u].x, h[u].y, h[u].z, h[u].w};
+                            uint4 o;
+                            uint32_t *ow = &o.x;
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                ow[e] = pack16<F16>(__uint_as_float(w[e] << 16), __uint_as_float(w[e] & 0xffff0000u));
+                            *reinterpret_cast<uint4 *>(sA + (size_t)(kc + u) * 2048 + tid * 16) = o;
+                        }
                 }
             } else {  // fp32 activations (residual-stream precision): converted to the operand format while staging
                 const float4 *src = reinterpret_cast<const float4 *>(A + src_row * K) + 2 * kc0;
-                for (int kc = 0; kc < kpc; ++kc) {
-                    const float4 a = __ldg(src + 2 * kc), b = __ldg(src + 2 * kc + 1);
-                    uint4 u;
-                    if constexpr (SPLIT) {
-                        uint4 l;
-                        split_pair(a.x, a.y, u.x, l.x); split_pair(a.z, a.w, u.y, l.y);
-                        split_pair(b.x, b.y, u.z, l.z); split_pair(b.z, b.w, u.w, l.w);
-                        *reinterpret_cast<uint4 *>(sAl + (size_t)kc * 2048 + tid * 16) = l;
-                    } else {
-                        u.x = pack16<F16>(a.x, a.y); u.y = pack16<F16>(a.z, a.w);
-                        u.z = pack16<F16>(b.x, b.y); u.w = pack16<F16>(b.z, b.w);
-                    }
-                    *reinterpret_cast<uint4 *>(sA + (size_t)kc * 2048 + tid * 16) = u;
+                for (int kc = 0; kc < kpc; kc += 4) {
+                    float4 va[4], vb[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (kc + u < kpc) {
+                            va[u] = __ldg(src + 2 * (kc + u));
+                            vb[u] = __ldg(src + 2 * (kc + u) + 1);
+                        }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (kc + u < kpc) {
+                            const float4 a = va[u], b = vb[u];
+                            uint4 o;
+                            if constexpr (SPLIT) {
+                                uint4 l;
+                                split_pair(a.x, a.y, o.x, l.x); split_pair(a.z, a.w, o.y, l.y);
+                                split_pair(b.x, b.y, o.z, l.z); split_pair(b.z, b.w, o.w, l.w);
+                                *reinterpret_cast<uint4 *>(sAl + (size_t)(kc + u) * 2048 + tid * 16) = l;
+                            } else {
+                                o.x = pack16<F16>(a.x, a.y); o.y = pack16<F16>(a.z, a.w);
+                                o.z = pack16<F16>(b.x, b.y); o.w = pack16<F16>(b.z, b.w);
+                            }
+                            *reinterpret_cast<uint4 *>(sA + (size_t)(kc + u) * 2048 + tid * 16) = o;
+                        }
                 }
             }
         }
-        // B tile: rows n0 .. n0+NT-1 of the [Nout, K] weight
-        for (int idx = tid; idx < NT * kpc; idx += 128) {
-            const int r = idx % NT, kc = idx / NT;
-            *reinterpret_cast<uint4 *>(sB + ((size_t)kc * NT + r) * 16) =
-                __ldg(reinterpret_cast<const uint4 *>(Wt + (int64_t)(n0 + r) * K) + kc0 + kc);
-            if constexpr (SPLIT)
-                *reinterpret_cast<uint4 *>(sBl + ((size_t)kc * NT + r) * 16) =
-                    __ldg(reinterpret_cast<const uint4 *>(Wt_lo + (int64_t)(n0 + r) * K) + kc0 + kc);
+        // B tile: rows n0 .. n0+NT-1 of the [Nout, K] weight (four cells per thread and step, loads first)
+        for (int base = tid; base < NT * kpc; base += 4 * 128) {
+            uint4 h[4], l[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = base + u * 128;
+                if (idx < NT * kpc) {
+                    const int r = idx % NT, kc = idx / NT;
+                    h[u] = __ldg(reinterpret_cast<const uint4 *>(Wt + (int64_t)(n0 + r) * K) + kc0 + kc);
+                    if constexpr (SPLIT) l[u] = __ldg(reinterpret_cast<const uint4 *>(Wt_lo + (int64_t)(n0 + r) * K) + kc0 + kc);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = base + u * 128;
+                if (idx < NT * kpc) {
+                    const int r = idx % NT, kc = idx / NT;
+                    *reinterpret_cast<uint4 *>(sB + ((size_t)kc * NT + r) * 16) = h[u];
+                    if constexpr (SPLIT) *reinterpret_cast<uint4 *>(sBl + ((size_t)kc * NT + r) * 16) = l[u];
+                }
+            }
         }
         fence_proxy_async();  // st.shared above -> visible to the tensor core's async proxy
         tc_fence_before();
