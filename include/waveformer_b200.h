@@ -21,7 +21,7 @@ extern "C" {
 
 typedef enum {
     WF_OK = 0,
-    WF_ERR_BAD_DTYPE = -1,     /* dtype is neither WF_F32 nor WF_BF16 */
+    WF_ERR_BAD_DTYPE = -1,     /* dtype (or the dtype combination) is not one the entry point is built for */
     WF_ERR_BAD_SHAPE = -2,     /* odd extent, zero size, head_dim unsupported, window does not tile the grid ... */
     WF_ERR_NULL_POINTER = -3,
     WF_ERR_MISALIGNED = -4,    /* a pointer / stride breaks the 16-byte alignment the vector path needs */
@@ -30,9 +30,9 @@ typedef enum {
     WF_ERR_UNSUPPORTED = -7
 } wf_status;
 
-/* WF_F16 is accepted as the operand format of the tensor-core window attention (`dtype` of wf_window_attn_fwd and
- * `fmt` of wf_relpos_bias_image) and as the activation type of the two InstanceNorm entry points (fp16 skip blocks of the
- * precision policy); everything else stores activations as WF_F32 or WF_BF16. */
+/* Storage / operand formats.  WF_BF16 and WF_F16 are interchangeable 16-bit formats everywhere a 16-bit activation, weight
+ * or tensor-core operand appears (same tcgen05 rate; fp16 carries 3 more mantissa bits and is the 16-bit precision policy's
+ * default: every such tensor on this path is normalised or one GEMM away from a normalisation, so its range suffices). */
 typedef enum { WF_F32 = 0, WF_BF16 = 1, WF_F16 = 2 } wf_dtype;
 
 const char *wf_version(void);
@@ -183,7 +183,7 @@ int wf_instnorm_stats_ndhwc(const void *x, double *sums, float *mean_rstd, int d
  * Fuses norm + residual add + activation of dynunet_block.py:100-110; with gamma / beta it is GroupNorm(num_groups = C)
  * of ProjectionUpsample.norm (reference network_models/wave_helper.py:59,74).  x and res share `dtype`; y_dtype is `dtype`, or
  * WF_BF16 with dtype WF_F32 / WF_F16 (a block kept in fp32-TF32 or fp16 by the precision policy writing into a bf16 concat
- * buffer).  WF_F16 activations are accepted by these two InstanceNorm entry points (stats and apply) only. */
+ * buffer). */
 int wf_instnorm_apply_ndhwc(const void *x, const float *mean_rstd, const void *res, const float *res_mean_rstd,
                             const float *gamma, const float *beta, void *y, int act, float slope, int dtype, int y_dtype,
                             int B, int64_t S, int C, int64_t x_vox_stride, int64_t res_vox_stride, int64_t y_vox_stride,

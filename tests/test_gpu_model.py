@@ -317,3 +317,40 @@ def test_idwt_block_with_hf_refinement_gate_fp32():
     with torch.no_grad():
         y = dec(inp, skip, hf)
     assert max_rel(y.cpu(), g["out"]) < 5e-5
+
+
+def test_reprepared_model_round_trip(sd):
+    """prepare_inference clears every policy attribute before it applies a policy: 16-bit -> fp32 -> 16-bit on ONE model
+    object gives the fp32 parity result in the middle and the first 16-bit result again at the end."""
+    from waveformer_b200 import prepare_inference
+    from waveformer_b200.network_models import Waveformer
+    cfg = ModelConfig(img_size=(64,) * 3)
+    sd64 = make_state_dict(cfg, seed=0)
+    m = Waveformer(**cfg.kwargs()).eval()
+    m.load_state_dict(sd64, strict=True)
+    x = seeded_randn((1, 4, 64, 64, 64), 3)
+    with torch.no_grad():
+        ref = om.waveformer_forward(sd64, x, cfg)
+        a = prepare_inference(m.cuda(), torch.bfloat16)(x.cuda()).float().cpu()
+        m.load_state_dict(sd64, strict=True)                       # restore the fp32 master values the policy rounded
+        b = prepare_inference(m, torch.float32)(x.cuda()).float().cpu()
+        c = prepare_inference(m, torch.bfloat16)(x.cuda()).float().cpu()
+    assert max_rel(b, ref) < 1e-4
+    assert max_rel(a, ref) < 2e-2 and torch.equal(a, c)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+def test_wide_output_head_falls_back(dtype, tol):
+    """out_chans = 20 exceeds the fused InstanceNorm + head kernel (<= 16 logits): the block must hand over to
+    InstanceNorm + activation followed by the library 1^3 convolution instead of raising (the reference allows any width)."""
+    from waveformer_b200 import prepare_inference
+    from waveformer_b200.network_models import Waveformer
+    cfg = ModelConfig(img_size=(64,) * 3, out_chans=20)
+    sd20 = make_state_dict(cfg, seed=11)
+    m = Waveformer(**cfg.kwargs()).eval()
+    m.load_state_dict(sd20, strict=True)
+    x = seeded_randn((1, 4, 64, 64, 64), 12)
+    with torch.no_grad():
+        y = prepare_inference(m.cuda(), dtype)(x.cuda()).float().cpu()
+        ref = om.waveformer_forward(sd20, x, cfg)
+    assert y.shape == (1, 20, 64, 64, 64) and max_rel(y, ref) < tol

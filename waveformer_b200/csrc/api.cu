@@ -31,7 +31,7 @@ extern "C" int wf_last_cuda_error(void) { return wf::g_last_cuda_error; }
 extern "C" const char *wf_error_string(int status) {
     switch (status) {
         case WF_OK: return "ok";
-        case WF_ERR_BAD_DTYPE: return "unsupported dtype (expected WF_F32 or WF_BF16; WF_F16 only as the window-attention operand format)";
+        case WF_ERR_BAD_DTYPE: return "unsupported dtype or dtype combination (WF_F32, WF_BF16, WF_F16)";
         case WF_ERR_BAD_SHAPE: return "bad shape (odd extent, empty tensor, window does not tile the grid, or unsupported head_dim)";
         case WF_ERR_NULL_POINTER: return "null pointer";
         case WF_ERR_MISALIGNED: return "pointer or stride not 16-byte aligned";
