@@ -235,6 +235,14 @@ int wf_upsample_trilinear_add_ndhwc(const void *const *srcs, const int *src_dims
                                     int src_dtype, int io_dtype, int align_corners, int B, int D, int H, int W, int C,
                                     int64_t base_vox_stride, int64_t y_vox_stride, void *stream);
 
+/* Patch embedding for 4 input channels: Conv3d(4 -> Cout, kernel = stride = 2, bias) of a channels-last window x
+ * [B, D, H, W, 4] (x_dtype fp32 / bf16 / fp16) written as the channels-last fp32 residual stream y [B, D/2, H/2, W/2, Cout]
+ * (exact fp32 arithmetic).  Replaces PatchEmbed.proj + the rearrange at the top of MultiscaleTransformer.forward_features
+ * (reference monai/networks/blocks/patchembedding.py:196-225, network_models/waveformer.py:260-270).
+ * wpack: fp32 [8 taps = (dz, dy, dx)][4][Cout]; bias fp32 [Cout] or NULL; Cout a multiple of 12. */
+int wf_patch_embed_k2s2_c4(const void *x, int x_dtype, const float *wpack, const float *bias, float *y, int B, int D, int H,
+                           int W, int Cout, void *stream);
+
 /* CCF_FFN's two pointwise GEMMs fused with the normalisations around them (tcgen05; C = 48 or 96, i.e. encoder stages 1
  * and 2).  Reference: `x = x + drop_path(mlp(norm2(x)))` (network_models/wave_helper.py:509) with CCF_FFN.forward
  * (wave_helper.py:260-294) = n + fc(GELU(LN(dwconv(GELU(LN(pwconv(n))))))), n = norm2(x).

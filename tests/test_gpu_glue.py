@@ -393,3 +393,25 @@ def test_block_with_fused_ffn_equals_unfused_path(monkeypatch):
         monkeypatch.setenv("WF_FFN_FUSED", "1")
         got, _ = blk(x)
     assert max_rel(got, want) < 2e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape,cout", [((2, 4, 16, 24, 32), 48), ((1, 4, 6, 10, 14), 96)])
+def test_patch_embed_kernel_matches_conv3d(shape, cout, dtype):
+    """wf_patch_embed_k2s2_c4 (PatchEmbed.proj + the rearrange, patchembedding.py:196-225 / waveformer.py:260-270) vs the
+    library convolution in fp32 without TF32: exact-fp32 arithmetic, channels-last stream out."""
+    from waveformer_b200 import ops
+    g = torch.Generator().manual_seed(cout)
+    x = torch.randn(shape, generator=g).cuda().to(dtype).contiguous(memory_format=torch.channels_last_3d)
+    w = (torch.randn((cout, 4, 2, 2, 2), generator=g) * 0.3).cuda()
+    b = (torch.randn((cout,), generator=g) * 0.1).cuda()
+    got = ops.patch_embed_k2s2(x, w, b)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        want = F.conv3d(x.float(), w, b, stride=2).permute(0, 2, 3, 4, 1)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert got.dtype == torch.float32 and got.is_contiguous() and tuple(got.shape) == tuple(want.shape)
+    assert max_rel(got, want) < 2e-6
+    assert ops.patch_embed_k2s2(x[:, :3], w[:, :3], b) is None          # other channel counts keep the library path

@@ -332,8 +332,9 @@ def test_reprepared_model_round_trip(sd):
     with torch.no_grad():
         ref = om.waveformer_forward(sd64, x, cfg)
         a = prepare_inference(m.cuda(), torch.bfloat16)(x.cuda()).float().cpu()
-        m.load_state_dict(sd64, strict=True)                       # restore the fp32 master values the policy rounded
-        b = prepare_inference(m, torch.float32)(x.cuda()).float().cpu()
+        m = prepare_inference(m, torch.float32)                    # clears the policy; parameters are fp32 again ...
+        m.load_state_dict(sd64, strict=True)                       # ... and get back the master values the policy rounded
+        b = m(x.cuda()).float().cpu()
         c = prepare_inference(m, torch.bfloat16)(x.cuda()).float().cpu()
     assert max_rel(b, ref) < 1e-4
     assert max_rel(a, ref) < 2e-2 and torch.equal(a, c)

@@ -44,6 +44,7 @@ SIGNATURES = {
     "wf_gelu_inplace": (_I, [_VOIDP, _I, _I64, _VOIDP]),
     "wf_residual_sum": (_I, [_VOIDP, _VOIDP, _VOIDP, _I, _VOIDP, _VOIDP, _I64, _I, _VOIDP]),
     "wf_layernorm_ndhwc": (_I, [_VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _I, _I, _I, _I64, _I, _I64, _I64, _F, _I, _VOIDP]),
+    "wf_patch_embed_k2s2_c4": (_I, [_VOIDP, _I, _VOIDP, _VOIDP, _VOIDP, _I, _I, _I, _I, _I, _VOIDP]),
     "wf_ffn_front": (_I, [_VOIDP, _VOIDP, _VOIDP, _F, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _F, _VOIDP, _I, _I64, _I, _VOIDP]),
     "wf_ffn_back": (_I, [_VOIDP, _I, _VOIDP, _VOIDP, _F, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _F, _VOIDP, _I64, _I, _VOIDP]),
     "wf_upsample_trilinear_add_ndhwc": (_I, [_VOIDP, _VOIDP, _I, _VOIDP, _VOIDP, _I, _I, _I, _I, _I, _I, _I, _I, _I64, _I64, _VOIDP]),

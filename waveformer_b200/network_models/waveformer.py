@@ -87,11 +87,18 @@ class MultiscaleTransformer(nn.Module):
         """``stage_hook(i, out)`` (optional, inference wiring of ``Waveformer._forward_forked``) is called on the current
         stream right after stage i's output exists; it is an argument, not module state, so the forward stays re-entrant."""
         outs, outs_hf = [], []
-        pe_dtype = self.patch_embed.proj.weight.dtype
-        t = self.pos_drop(self.patch_embed(x_rgb if x_rgb.dtype == pe_dtype else x_rgb.to(pe_dtype)))
-        t = t.permute(0, 2, 3, 4, 1)                                           # [B, D, H, W, C]
-        if not t.is_contiguous():
-            t = t.contiguous()
+        pe = self.patch_embed
+        pe_dtype = pe.proj.weight.dtype
+        t = None
+        if (x_rgb.is_cuda and not torch.is_grad_enabled() and pe.norm is None and pe_dtype == torch.float32
+                and tuple(pe.patch_size) == (2, 2, 2) and self.pos_drop.p == 0):
+            # 4 input channels, 2^3 patches: one exact-fp32 kernel that writes the channels-last stream directly
+            t = ops.patch_embed_k2s2(x_rgb, pe.proj.weight, pe.proj.bias)
+        if t is None:
+            t = self.pos_drop(pe(x_rgb if x_rgb.dtype == pe_dtype else x_rgb.to(pe_dtype)))
+            t = t.permute(0, 2, 3, 4, 1)                                       # [B, D, H, W, C]
+            if not t.is_contiguous():
+                t = t.contiguous()
         for s in range(4):
             hf = ()
             for blk in getattr(self, f"block{s + 1}"):

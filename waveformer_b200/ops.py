@@ -812,6 +812,33 @@ def layer_norm_cl(x: torch.Tensor, weight: Optional[torch.Tensor], bias: Optiona
     return (y, y2) if also_bf16 else y
 
 
+_PE_PACK = {}
+
+
+def patch_embed_k2s2(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """``Conv3d(4 -> C, kernel = stride = 2)`` of ``x[B, 4, D, H, W]`` (channels-last-3d strides) as the channels-last fp32
+    stream ``[B, D/2, H/2, W/2, C]`` in one exact-fp32 pass.  Returns None when the geometry is outside the kernel (the
+    caller keeps the library convolution)."""
+    if (x.dim() != 5 or x.shape[1] != 4 or tuple(weight.shape[1:]) != (4, 2, 2, 2) or weight.shape[0] % 12 or weight.shape[0] > 384
+            or x.dtype not in _CODES or any(v % 2 for v in x.shape[2:]) or weight.dtype != torch.float32):
+        return None
+    dev = _need_cuda(x, weight, bias)
+    v, vs = _ndhwc_view(x)
+    if vs != 4:
+        return None
+    B, D, H, W, _ = v.shape
+    C = weight.shape[0]
+    pack = _pack_cached(_PE_PACK, id(weight), (weight._version, weight.data_ptr(), weight.dtype), weight,
+                        lambda: weight.detach().float().permute(2, 3, 4, 1, 0).reshape(32, C).contiguous())
+    y = torch.empty((B, D // 2, H // 2, W // 2, C), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        st = _lib.lib().wf_patch_embed_k2s2_c4(v.data_ptr(), _dtype_code(v), pack.data_ptr(), _ptr(f32_cached(bias)), y.data_ptr(),
+                                               B, D, H, W, C, _stream(dev))
+    _lib.check(st, "wf_patch_embed_k2s2_c4")
+    _count()
+    return y
+
+
 def ffn_fused_supported(x: torch.Tensor, C_hid: int, fmt: Optional[torch.dtype]) -> bool:
     """wf_ffn_front / wf_ffn_back cover the fp32-stream, 16-bit-operand FFN of encoder stages 1 and 2 (C = 48 / 96, 4C hidden)."""
     return (x.is_cuda and x.dtype == torch.float32 and fmt in HALF_TYPES and x.shape[-1] in (48, 96)
