@@ -235,6 +235,11 @@ int wf_upsample_trilinear_add_ndhwc(const void *const *srcs, const int *src_dims
                                     int src_dtype, int io_dtype, int align_corners, int B, int D, int H, int W, int C,
                                     int64_t base_vox_stride, int64_t y_vox_stride, void *stream);
 
+/* hi = fp16(x), lo = fp16(x - hi) for n fp32 values (n % 4 == 0): an error-compensated fp16 pair.  conv(hi) + conv(lo) is the
+ * convolution of the unrounded input; used for the first convolution of the skip blocks encoder2..4 (reference
+ * network_models/network_backbone.py:387-389 -> monai/networks/blocks/dynunet_block.py:98). */
+int wf_split_f16(const float *x, void *hi, void *lo, int64_t n, void *stream);
+
 /* Patch embedding for 4 input channels: Conv3d(4 -> Cout, kernel = stride = 2, bias) of a channels-last window x
  * [B, D, H, W, 4] (x_dtype fp32 / bf16 / fp16) written as the channels-last fp32 residual stream y [B, D/2, H/2, W/2, Cout]
  * (exact fp32 arithmetic).  Replaces PatchEmbed.proj + the rearrange at the top of MultiscaleTransformer.forward_features

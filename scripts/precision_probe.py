@@ -49,6 +49,7 @@ POLICIES = [("pure bf16 (model.to(bf16))", dict(fp32_stream=False)),
             ("r01 policy: bf16 storage, attn fp16", dict(storage="bf16", attention="fp16")),
             ("fp16 storage, attn fp16", dict(attention="fp16")),
             ("r02 policy: fp16 storage, attn fp16x2 (default)", dict()),
+            ("r02 policy without the skip blocks' input pair", dict(skip_split_input=False)),
             ("fp16 storage, attention fp32 CUDA cores", dict(attention="fp32")),
             ("bf16 storage, attention fp32 CUDA cores", dict(storage="bf16", attention="fp32"))]
 if len(sys.argv) > 1:

@@ -41,6 +41,7 @@ SIGNATURES = {
     "wf_instnorm_apply_ndhwc": (_I, [_VOIDP] * 7 + [_I, _F, _I, _I, _I, _I64, _I, _I64, _I64, _I64, _VOIDP]),
     "wf_instnorm_apply_head_ndhwc": (_I, [_VOIDP] * 7 + [_I, _F, _I, _I, _I, _I64, _I, _I, _I64, _I64, _VOIDP]),
     "wf_groupnorm_fold_linear": (_I, [_VOIDP] * 7 + [_I, _I, _I, _I, _I, _VOIDP]),
+    "wf_split_f16": (_I, [_VOIDP, _VOIDP, _VOIDP, _I64, _VOIDP]),
     "wf_gelu_inplace": (_I, [_VOIDP, _I, _I64, _VOIDP]),
     "wf_residual_sum": (_I, [_VOIDP, _VOIDP, _VOIDP, _I, _VOIDP, _VOIDP, _I64, _I, _VOIDP]),
     "wf_layernorm_ndhwc": (_I, [_VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _I, _I, _I, _I64, _I, _I64, _I64, _F, _I, _VOIDP]),

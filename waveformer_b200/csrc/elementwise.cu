@@ -58,6 +58,21 @@ __global__ void __launch_bounds__(256) gelu_inplace_kernel(T *__restrict__ x, in
     reinterpret_cast<typename Pack<T>::raw *>(x)[i] = Pack<T>::pack(f);
 }
 
+// x (fp32) -> hi = fp16(x), lo = fp16(x - hi): an error-compensated fp16 pair (22 significant bits).  A convolution is linear
+// in its input, so conv(hi) + conv(lo) reproduces conv(x) without the input's rounding error; used for the first
+// convolution of the skip blocks encoder2..4, whose InstanceNorm amplifies exactly that error.
+__global__ void __launch_bounds__(256) split_f16_kernel(const float4 *__restrict__ x, uint2 *__restrict__ hi, uint2 *__restrict__ lo,
+                                                        int64_t packets) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= packets) return;
+    const float4 v = __ldcs(x + i);
+    const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+    hi[i] = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+    lo[i] = make_uint2(*reinterpret_cast<const uint32_t *>(&l0), *reinterpret_cast<const uint32_t *>(&l1));
+}
+
 // GroupNorm(num_groups = C) followed by a 1x1x1 convolution = one per-sample linear map: with (mean, rstd) of every
 // (sample, channel), a = rstd * gamma and d = beta - mean * a,   W'[b] = W diag(a[b]),   b'[b] = bias + W d[b].
 // One block per (output row n, sample b): replaces ~20 tiny library launches per ProjectionUpsample call.
@@ -112,6 +127,16 @@ extern "C" int wf_groupnorm_fold_linear(const float *mean_rstd, const float *gam
                                                                        (__half *)w_folded, (__half *)b_folded, C, N);
     else
         return WF_ERR_BAD_DTYPE;
+    WF_LAUNCH_CHECK();
+    return WF_OK;
+}
+
+extern "C" int wf_split_f16(const float *x, void *hi, void *lo, int64_t n, void *stream) {
+    if (!x || !hi || !lo) return WF_ERR_NULL_POINTER;
+    if (n <= 0 || n % 4) return WF_ERR_BAD_SHAPE;
+    if (!wf::aligned16(x) || (reinterpret_cast<uintptr_t>(hi) & 7u) || (reinterpret_cast<uintptr_t>(lo) & 7u)) return WF_ERR_MISALIGNED;
+    wf::split_f16_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4 *>(x), reinterpret_cast<uint2 *>(hi), reinterpret_cast<uint2 *>(lo), n / 4);
     WF_LAUNCH_CHECK();
     return WF_OK;
 }

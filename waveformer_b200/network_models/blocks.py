@@ -122,8 +122,9 @@ class UnetResBlock(nn.Module):
         out = F.conv3d(y, w.to(y.dtype), None if b is None else b.to(y.dtype))
         return out if od is None or out.dtype == od else out.to(od)
 
-    def forward(self, inp: torch.Tensor, out_buf: torch.Tensor = None, head=None) -> torch.Tensor:
-        """``out_buf`` (inference only): a [B, D, H, W, C] channels-last destination - typically the skip half of a
+    def forward(self, inp: torch.Tensor, out_buf: torch.Tensor = None, head=None, lo: torch.Tensor = None) -> torch.Tensor:
+        """``lo`` (inference only): low part of an error-compensated input pair (``inp`` = hi); conv1 sees hi + lo.
+        ``out_buf`` (inference only): a [B, D, H, W, C] channels-last destination - typically the skip half of a
         decoder's concatenation buffer - the block's last kernel writes into (the torch.cat copy disappears).
         ``head`` (inference only) = (weight [K, C, 1, 1, 1], bias, out_dtype) of a 1^3 convolution that is the block's only
         consumer: the last kernel then emits the K-channel result and the block's own output is never stored."""
@@ -136,7 +137,10 @@ class UnetResBlock(nn.Module):
                                          out=out_buf, stats=s2)
         if use_fused(inp):
             # InstanceNorm + LeakyReLU, and InstanceNorm (+ InstanceNorm'd shortcut) + add + LeakyReLU: one kernel each
-            out, s2 = self._conv2_after_norm(self.conv1(inp), None)
+            c1 = self.conv1(inp)
+            if lo is not None:
+                c1 = c1 + self.conv1(lo)       # conv is linear: conv(hi) + conv(lo) = conv of the unrounded input
+            out, s2 = self._conv2_after_norm(c1, None)
             if self.downsample:
                 c3 = self.conv3.conv
                 if c3.kernel_size == (1, 1, 1) and c3.stride == (1, 1, 1) and inp.stride(1) == 1:
@@ -197,9 +201,17 @@ class UnetrBasicBlock(nn.Module):
         sd = getattr(self, "skip_dtype", None)
         if sd is not None and use_fused(inp):
             # precision policy, fp16 variant: fp16 storage / operands (10-bit mantissa like TF32) at the cost of the bf16 path
-            if inp.dtype != sd:
+            lo = None
+            if (getattr(self, "split_input", False) and sd == torch.float16 and inp.dtype == torch.float32
+                    and isinstance(self.layer, UnetResBlock) and not self.layer.downsample and inp.numel() % 4 == 0):
+                # the fp32 stage output as an fp16 pair: conv1's InstanceNorm amplifies the input's rounding error ~5x
+                inp, lo = ops.split_f16(inp)
+            elif inp.dtype != sd:
                 inp = inp.to(sd)
-            y = self.layer(inp) if out_buf is None else self.layer(inp, out_buf)
+            if lo is not None:
+                y = self.layer(inp, out_buf, None, lo)
+            else:
+                y = self.layer(inp) if out_buf is None else self.layer(inp, out_buf)
             od = getattr(self, "io_dtype", None) or torch.bfloat16      # activation type of the surrounding U-Net
             return y if out_buf is not None or y.dtype == od else y.to(od)
         return self.layer(inp) if out_buf is None else self.layer(inp, out_buf)

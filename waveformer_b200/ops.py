@@ -883,6 +883,23 @@ def ffn_back(t2: torch.Tensor, ln: torch.nn.LayerNorm, fc_weight: torch.Tensor, 
     return out
 
 
+def split_f16(x: torch.Tensor):
+    """fp32 ``x`` (any dense layout) -> ``(hi, lo)`` fp16 tensors of x's shape and strides with ``hi + lo == x`` to 22 bits."""
+    dev = _need_cuda(x)
+    if x.dtype != torch.float32 or x.numel() % 4:
+        raise ValueError("split_f16: fp32 tensor with a multiple of 4 elements")
+    hi = torch.empty_like(x, dtype=torch.float16)
+    if hi.stride() != x.stride():          # not a dense tensor: fall back to its contiguous form
+        x = x.contiguous()
+        hi = torch.empty_like(x, dtype=torch.float16)
+    lo = torch.empty_like(hi)
+    with torch.cuda.device(dev):
+        st = _lib.lib().wf_split_f16(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), _stream(dev))
+    _lib.check(st, "wf_split_f16")
+    _count()
+    return hi, lo
+
+
 def gelu_(x: torch.Tensor) -> torch.Tensor:
     """In-place exact (erf) GELU of a contiguous bf16 / fp32 tensor."""
     dev = _need_cuda(x)

@@ -34,11 +34,12 @@ from .network_models.waveformer import MultiscaleTransformer
 __all__ = ["prepare_inference"]
 
 # every attribute prepare_inference may leave on a module (instance attributes only; cleared before each preparation)
-_POLICY_ATTRS = ("compute_dtype", "out_dtype", "hf_dtype", "skip_dtype", "tf32", "logits_dtype", "io_dtype", "split_operands")
+_POLICY_ATTRS = ("compute_dtype", "out_dtype", "hf_dtype", "skip_dtype", "tf32", "logits_dtype", "io_dtype", "split_operands", "split_input")
 
 
 def prepare_inference(model: nn.Module, dtype: torch.dtype = torch.bfloat16, *, attention: str = "fp16x2",
-                      fp32_stream: bool = True, skip_blocks: str = "fp16", storage: str = "fp16") -> nn.Module:
+                      fp32_stream: bool = True, skip_blocks: str = "fp16", storage: str = "fp16",
+                      skip_split_input: bool = True) -> nn.Module:
     """Put ``model`` (a ``Waveformer``) into inference form on its current device.
 
     ``dtype=torch.float32``: nothing is rounded (parity mode, <= 1e-4 against the reference).
@@ -50,7 +51,8 @@ def prepare_inference(model: nn.Module, dtype: torch.dtype = torch.bfloat16, *, 
     exponentiates are exact to fp32 level), "fp16", "bf16", or "fp32" = CUDA-core kernels; ``fp32_stream=False`` gives the plain all-bf16
     model (``model.to(torch.bfloat16)``), kept for the precision study.  ``skip_blocks`` (only with ``storage="bf16"``) is the
     format of the residual blocks encoder2..4: "tf32" (fp32 storage, TF32 tensor-core convolutions), "fp16" (fp16 storage and
-    operands) or "bf16" (no special treatment).
+    operands) or "bf16" (no special treatment).  ``skip_split_input``: hand the fp32 stage outputs to those blocks as
+    error-compensated fp16 pairs (conv1(hi) + conv1(lo)): their first InstanceNorm amplifies the input's rounding error ~5x.
     """
     model.eval()
     # a model may be re-prepared (bf16 -> fp32 parity run -> bf16): start from a clean slate, every time
@@ -113,6 +115,7 @@ def prepare_inference(model: nn.Module, dtype: torch.dtype = torch.bfloat16, *, 
         if blk is None:
             continue
         blk.io_dtype = h16
+        blk.split_input = bool(skip_split_input) and skip_blocks == "fp16"
         if skip_blocks == "bf16":
             blk.skip_dtype = torch.bfloat16             # only the fp32 stage output is cast on the way in
         elif skip_blocks == "tf32":
