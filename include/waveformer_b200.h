@@ -290,6 +290,26 @@ int wf_conv3d_k3_c48_in_stats(const void *x, int dtype, const void *wpack, void 
                               const float *in_mean_rstd, float slope, float eps, int B, int D, int H, int W,
                               int64_t x_vox_stride, int64_t y_vox_stride, void *stream);
 
+/* The same 48 -> 48 convolution (rolling-row kernel, no input normalisation) with an optional 16-bit `addend` laid out like y
+ * that is added to the fp32 accumulators before rounding: y = conv(x) + addend.  Two launches compute a 3x3x3 convolution whose
+ * 96 input channels are two 48-channel halves of a concatenation buffer - y1 = conv_a(cat[..., :48]), y = conv_b(cat[..., 48:])
+ * + y1 - which is how decoder1's first convolution runs (reference monai/networks/blocks/dynunet_block.py:98 on the
+ * torch.cat of monai/networks/blocks/unetr_block.py:83-84).  addend may be NULL; statistics are those of the final y. */
+int wf_conv3d_k3_c48_add_stats(const void *x, int dtype, const void *wpack, const void *addend, void *y, double *sums,
+                               float *mean_rstd, float eps, int B, int D, int H, int W, int64_t x_vox_stride,
+                               int64_t add_vox_stride, int64_t y_vox_stride, void *stream);
+
+/* Diagnostic twin of wf_conv3d_k3_c48_in_stats (fp16 only): same computation, and every CTA also reports how many clocks each of
+ * its warp roles spent in each phase.  Rolling-row kernel (in_mean_rstd == NULL): clocks [grid][3 roles][8] with
+ *   loader   {wait: free ring slot, wait: own cp.async copies, cp.async issue, fence + arrive, -, -, -, total}
+ *   issuer   {wait: free accumulator slot, wait: staged row, tcgen05.mma issue + commit, -, -, -, -, total}
+ *   epilogue {wait: finished row, tcgen05.ld, zero + release, staging barrier, copy-out, statistics, -, total};
+ * block kernel (in_mean_rstd != NULL): clocks [grid][8] = {loader: wait slot, wait copies, total; issuer: wait accumulator, wait
+ * row, total; epilogue: wait accumulators, total}.  The stage that never waits is the kernel's limiter. */
+int wf_conv3d_k3_c48_stage_clocks(const void *x, int dtype, const void *wpack, void *y, double *sums, float *mean_rstd,
+                                  const float *in_mean_rstd, float slope, float eps, int B, int D, int H, int W,
+                                  int64_t x_vox_stride, int64_t y_vox_stride, long long *clocks, void *stream);
+
 /* ConvTranspose3d(kernel 2, stride 2, no bias) on channels-last 16-bit activations (dtype WF_BF16 or WF_F16: x, wpack
  * and y share it) as one tensor-core GEMM whose epilogue
  * writes every output voxel in place, e.g. into channels [0, Cout) of a concatenation buffer (y_vox_stride = 2 * Cout).

@@ -35,6 +35,10 @@ elif args.case == "k3":      # encoder1 / decoder1 conv2: 48 -> 48 at 2 x 128^3,
     fns = {"conv3d_k3_c48 (fused in-norm + stats)": lambda: ops.conv3d_k3_c48(x, w, in_stats=st),
            "conv3d_k3_c48 (plain + stats)": lambda: ops.conv3d_k3_c48(x, w),
            "cudnn conv3d 48->48 (library, for comparison)": lambda: torch.nn.functional.conv3d(x, w, padding=1)}
+    x96 = rn(2, 128, 128, 128, 96).half().permute(0, 4, 1, 2, 3)
+    w96 = (rn(48, 96, 3, 3, 3) / 50).half()
+    fns["conv3d_k3_c96_c48 (two passes + stats)"] = lambda: ops.conv3d_k3_c96_c48(x96, w96)
+    fns["cudnn conv3d 96->48 (library, for comparison)"] = lambda: torch.nn.functional.conv3d(x96, w96, padding=1)
 elif args.case == "dwconv":  # CCF_FFN stage 1: 2 x 64^3 x 192
     x = rn(2, 64, 64, 64, 192).bfloat16()
     w27, b = rn(27, 192) * 0.2, rn(192) * 0.05

@@ -238,7 +238,7 @@ def test_gelu_inplace_matches_torch(dtype, tol):
     assert got.dtype == dtype and max_rel(got.float().cpu(), want.cpu()) < tol
 
 
-@pytest.mark.parametrize("shape", [(1, 2, 4, 128), (2, 3, 6, 128), (1, 5, 9, 128), (2, 24, 40, 128), (2, 128, 128, 128)])
+@pytest.mark.parametrize("shape", [(1, 2, 4, 128), (2, 3, 6, 128), (1, 5, 9, 128), (1, 1, 1, 128), (2, 37, 11, 128), (2, 24, 40, 128), (2, 128, 128, 128)])
 @pytest.mark.parametrize("fused_input_norm", [False, True])
 def test_conv3d_k3_c48_producer_consumer_kernel(shape, fused_input_norm):
     """tcgen05 3^3 convolution 48 -> 48 on rows of 128 voxels (ring-staged input rows, shifted-descriptor dx taps, double-
@@ -260,6 +260,29 @@ def test_conv3d_k3_c48_producer_consumer_kernel(shape, fused_input_norm):
     y, st = ops.conv3d_k3_c48(x, w, in_stats=stats, slope=0.01)
     assert y.dtype == torch.bfloat16 and tuple(y.shape) == tuple(want.shape)
     assert max_rel(y.float().cpu(), want.cpu()) < 8e-3
+    f = y.float()
+    mean = f.mean(dim=(2, 3, 4)).reshape(-1)
+    rstd = (f.var(dim=(2, 3, 4), unbiased=False) + 1e-5).rsqrt().reshape(-1)
+    got = st.reshape(-1, 2)
+    assert float((got[:, 0] - mean).abs().max()) < 2e-5 * max(1.0, float(mean.abs().max()))
+    assert max_rel(got[:, 1].cpu(), rstd.cpu()) < 1e-4
+
+
+@pytest.mark.parametrize("shape", [(1, 2, 4, 128), (2, 3, 7, 128), (1, 1, 1, 128), (2, 37, 11, 128), (2, 128, 128, 128)])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_conv3d_k3_c96_c48_two_pass(shape, dtype):
+    """decoder1's first convolution (3^3, 96 -> 48 on the concatenation buffer) as two passes of the rolling-row 48 -> 48 kernel,
+    the second adding the first's result to its fp32 accumulators: vs torch's convolution of the same 16-bit operands (the
+    partial sum is rounded to 16 bits once: tolerance 2 roundings).  Odd D / H make the per-CTA runs of output rows start and
+    end mid-plane and cross planes and batch elements; the last shape is BASELINE's full size."""
+    from waveformer_b200 import ops
+    B, D, H, W = shape
+    x = (seeded_randn((B, 96, D, H, W), 170) * 1.1 - 0.1).cuda().to(dtype).contiguous(memory_format=torch.channels_last_3d)
+    w = (seeded_randn((48, 96, 3, 3, 3), 171) / (27 * 96) ** 0.5).cuda().to(dtype)
+    want = F.conv3d(x.float(), w.float(), padding=1)
+    y, st = ops.conv3d_k3_c96_c48(x, w)
+    assert y.dtype == dtype and tuple(y.shape) == tuple(want.shape)
+    assert max_rel(y.float().cpu(), want.cpu()) < (2e-3 if dtype == torch.float16 else 1.2e-2)
     f = y.float()
     mean = f.mean(dim=(2, 3, 4)).reshape(-1)
     rstd = (f.var(dim=(2, 3, 4), unbiased=False) + 1e-5).rsqrt().reshape(-1)

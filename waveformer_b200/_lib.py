@@ -51,6 +51,8 @@ SIGNATURES = {
     "wf_upsample_trilinear_add_ndhwc": (_I, [_VOIDP, _VOIDP, _I, _VOIDP, _VOIDP, _I, _I, _I, _I, _I, _I, _I, _I, _I64, _I64, _VOIDP]),
     "wf_conv3d_c4_in_stats": (_I, [_VOIDP, _I, _I, _VOIDP, _VOIDP, _I64, _I, _VOIDP, _I64, _I, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _F, _I, _I, _I, _I, _VOIDP]),
     "wf_conv3d_k3_c48_in_stats": (_I, [_VOIDP, _I, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _F, _F, _I, _I, _I, _I, _I64, _I64, _VOIDP]),
+    "wf_conv3d_k3_c48_add_stats": (_I, [_VOIDP, _I, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _F, _I, _I, _I, _I, _I64, _I64, _I64, _VOIDP]),
+    "wf_conv3d_k3_c48_stage_clocks": (_I, [_VOIDP, _I, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _F, _F, _I, _I, _I, _I, _I64, _I64, _VOIDP, _VOIDP]),
     "wf_convtranspose3d_k2s2_ndhwc": (_I, [_VOIDP, _VOIDP, _VOIDP, _I, _I, _I, _I, _I, _I, _I, _I64, _I64, _VOIDP]),
     "wf_sw_gather": (_I, [_VOIDP, _VOIDP, _VOIDP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VOIDP]),
     "wf_sw_accumulate": (_I, [_VOIDP] * 6 + [_F, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VOIDP]),

@@ -18,9 +18,12 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// Spins on try_wait.  Watchdog: a wait that lasts longer than ~4 s of wall clock (a protocol bug - no kernel of this library runs
+// that long) traps, so a deadlock surfaces as a CUDA error instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
-    uint32_t done;
+    uint32_t done, polls = 0;
+    unsigned long long t0 = 0;
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -29,6 +32,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             : "=r"(done)
             : "r"(addr), "r"(parity)
             : "memory");
+        if (!done && (++polls & 0xfffu) == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) __trap();
+        }
     } while (!done);
 }
 
@@ -62,6 +71,44 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ void mma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
+}
+
+// ---- warp-uniform issue ------------------------------------------------------------------------------------------------
+// tcgen05.mma / tcgen05.commit are warp-level ("uniform datapath") instructions.  Issued from inside an `if (lane == 0)` block
+// the compiler keeps their operands in per-thread registers and wraps EVERY instruction in an ELECT loop with ~7
+// R2UR.BROADCAST moves: ~20 dependent instructions = ~140 clk per MMA from the single issuing thread, above the 72-clk tensor
+// floor of a 128 x 144 x 16 MMA (scripts/mma_probe.cu measures max(66, N / 2) clk per MMA for every operand layout when the
+// descriptors already sit in uniform registers).  The helpers below are called by ALL 32 lanes of a converged warp with
+// warp-uniform arguments; one elected lane issues.  Descriptors travel as (lo, hi) words so that advancing the 14-bit address
+// field is one 32-bit add.
+__device__ __forceinline__ uint32_t warp_idx_uniform() { return __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0); }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t e;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(e));
+    return e != 0;
+}
+__device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity) {   // all lanes call; one polls
+    if (elect_one()) mbar_wait(bar, parity);
+    __syncwarp();
+}
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16); }
+__device__ __forceinline__ uint32_t smem_desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }   // version 1, no swizzle
+__device__ __forceinline__ void mma_ss_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit_w(uint64_t *bar) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+        : "memory");
 }
 
 // ---- descriptors -----------------------------------------------------------------------------------------------------

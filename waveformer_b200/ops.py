@@ -639,11 +639,12 @@ _K3_PACK = {}
 
 
 def conv3d_k3_c48(x: torch.Tensor, weight: torch.Tensor, in_stats: Optional[torch.Tensor] = None, slope: float = 0.01,
-                  eps: float = 1e-5, out: Optional[torch.Tensor] = None):
+                  eps: float = 1e-5, out: Optional[torch.Tensor] = None, stage_clocks: Optional[torch.Tensor] = None):
     """3^3 convolution 48 -> 48 (padding 1, no bias) of ``x[B, 48, D, H, 128]`` (bf16 or fp16, channels-last-3d strides) on
     the tensor cores.  With ``in_stats`` (the (mean, rstd) tensor of x) the input is InstanceNorm'd + LeakyReLU'd while it is
     staged, i.e. the call computes ``conv(lrelu(IN(x)))``.  Returns ``(y, stats)``: y bf16 [B, 48, D, H, 128] channels-last
-    and the (mean, rstd) statistics of y for the following ``instance_norm_act(stats=...)``."""
+    and the (mean, rstd) statistics of y for the following ``instance_norm_act(stats=...)``.  ``stage_clocks`` (diagnostic,
+    fp16 only): an int64 [148, 3, 8] tensor that receives every CTA's per-role phase clocks (``wf_conv3d_k3_c48_stage_clocks``)."""
     dev = _need_cuda(x, weight, in_stats, out)
     v, vs = _ndhwc_view(x)
     B, D, H, W, C = v.shape
@@ -664,11 +665,56 @@ def conv3d_k3_c48(x: torch.Tensor, weight: torch.Tensor, in_stats: Optional[torc
     sums = torch.empty(2 * B * 48, dtype=torch.float64, device=dev)
     mr = torch.empty(2 * B * 48, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        st = _lib.lib().wf_conv3d_k3_c48_in_stats(v.data_ptr(), _dtype_code(v), pack.data_ptr(), out.data_ptr(), sums.data_ptr(),
-                                                  mr.data_ptr(), _ptr(in_stats), float(slope), float(eps), B, D, H, W, vs,
-                                                  ys, _stream(dev))
+        if stage_clocks is not None:
+            if stage_clocks.dtype != torch.int64 or stage_clocks.numel() < 148 * 8 * (1 if in_stats is not None else 3) or not stage_clocks.is_contiguous():
+                raise ValueError("stage_clocks: contiguous int64 tensor of at least 148 * 8 elements")
+            st = _lib.lib().wf_conv3d_k3_c48_stage_clocks(v.data_ptr(), _dtype_code(v), pack.data_ptr(), out.data_ptr(), sums.data_ptr(),
+                                                          mr.data_ptr(), _ptr(in_stats), float(slope), float(eps), B, D, H, W, vs,
+                                                          ys, stage_clocks.data_ptr(), _stream(dev))
+        else:
+            st = _lib.lib().wf_conv3d_k3_c48_in_stats(v.data_ptr(), _dtype_code(v), pack.data_ptr(), out.data_ptr(), sums.data_ptr(),
+                                                      mr.data_ptr(), _ptr(in_stats), float(slope), float(eps), B, D, H, W, vs,
+                                                      ys, _stream(dev))
     _lib.check(st, "wf_conv3d_k3_c48_in_stats")
     _count(2)
+    return out.permute(0, 4, 1, 2, 3), mr
+
+
+def conv3d_k3_c96_c48(x: torch.Tensor, weight: torch.Tensor, eps: float = 1e-5, out: Optional[torch.Tensor] = None):
+    """3^3 convolution 96 -> 48 (padding 1, no bias) of ``x[B, 96, D, H, 128]`` (bf16 / fp16, channels-last-3d strides - typically a
+    decoder's concatenation buffer) as two passes of the 48 -> 48 tensor-core kernel: ``y1 = conv(x[:, :48], w[:, :48])``, then
+    ``y = conv(x[:, 48:], w[:, 48:]) + y1`` with y1 added to the fp32 accumulators before rounding.  Returns ``(y, stats)`` like
+    :func:`conv3d_k3_c48`."""
+    dev = _need_cuda(x, weight, out)
+    v, vs = _ndhwc_view(x)
+    B, D, H, W, C = v.shape
+    if v.dtype not in HALF_TYPES or C != 96 or W != 128 or tuple(weight.shape) != (48, 96, 3, 3, 3):
+        raise ValueError("conv3d_k3_c96_c48: bf16 / fp16 [B, 96, D, H, 128] input and a [48, 96, 3, 3, 3] weight")
+    fmt = v.dtype
+
+    def build():
+        w = weight.detach().float().permute(2, 3, 4, 0, 1).reshape(3, 3, 3, 48, 2, 3, 2, 8)   # [dz, dy, dx, n, half, ks, chunk, e]
+        return w.permute(4, 0, 2, 5, 6, 1, 3, 7).contiguous().to(fmt)                         # [half][dz, dx, ks, chunk, dy, n, e]
+
+    pack = _pack_cached(_K3_PACK, (id(weight), fmt, "c96"), (weight._version, weight.data_ptr(), weight.dtype), weight, build)
+    if out is None:
+        out = torch.empty((B, D, H, W, 48), dtype=fmt, device=dev)
+    ys = _voxel_stride(out)
+    if ys is None or tuple(out.shape) != (B, D, H, W, 48) or out.dtype != fmt:
+        raise ValueError("out must be a voxel-dense [B, D, H, 128, 48] tensor of the input's 16-bit type")
+    part = torch.empty((B, D, H, W, 48), dtype=fmt, device=dev)
+    sums = torch.empty(2 * B * 48, dtype=torch.float64, device=dev)
+    mr = torch.empty(2 * B * 48, dtype=torch.float32, device=dev)
+    esz = v.element_size()
+    with torch.cuda.device(dev):
+        fn = _lib.lib().wf_conv3d_k3_c48_add_stats
+        st = fn(v.data_ptr(), _dtype_code(v), pack[0].data_ptr(), None, part.data_ptr(), sums.data_ptr(), mr.data_ptr(), float(eps),
+                B, D, H, W, vs, 0, 48, _stream(dev))
+        _lib.check(st, "wf_conv3d_k3_c48_add_stats")
+        st = fn(v.data_ptr() + 48 * esz, _dtype_code(v), pack[1].data_ptr(), part.data_ptr(), out.data_ptr(), sums.data_ptr(),
+                mr.data_ptr(), float(eps), B, D, H, W, vs, 48, ys, _stream(dev))
+        _lib.check(st, "wf_conv3d_k3_c48_add_stats")
+    _count(4)
     return out.permute(0, 4, 1, 2, 3), mr
 
 
