@@ -301,9 +301,10 @@ int wf_conv3d_k3_c48_add_stats(const void *x, int dtype, const void *wpack, cons
 
 /* Diagnostic twin of wf_conv3d_k3_c48_in_stats (fp16 only): same computation, and every CTA also reports how many clocks each of
  * its warp roles spent in each phase.  Rolling-row kernel (in_mean_rstd == NULL): clocks [grid][3 roles][8] with
- *   loader   {wait: free ring slot, wait: own cp.async copies, cp.async issue, fence + arrive, -, -, -, total}
+ *   producer {wait: free ring slot, -, -, -, -, -, -, total}
  *   issuer   {wait: free accumulator slot, wait: staged row, tcgen05.mma issue + commit, -, -, -, -, total}
- *   epilogue {wait: finished row, tcgen05.ld, zero + release, staging barrier, copy-out, statistics, -, total};
+ *   epilogue {wait: finished row, tcgen05.ld, zero + release, staging tile free, pack + statistics + st.shared, fence + barrier +
+ *             bulk store, -, total};
  * block kernel (in_mean_rstd != NULL): clocks [grid][8] = {loader: wait slot, wait copies, total; issuer: wait accumulator, wait
  * row, total; epilogue: wait accumulators, total}.  The stage that never waits is the kernel's limiter. */
 int wf_conv3d_k3_c48_stage_clocks(const void *x, int dtype, const void *wpack, void *y, double *sums, float *mean_rstd,

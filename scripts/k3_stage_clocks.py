@@ -19,9 +19,10 @@ for _ in range(3):
     ops.conv3d_k3_c48(x, w, stage_clocks=clk)
 torch.cuda.synchronize()
 c = clk.double().cpu().mean(0)
-names = [("loader", ["wait: free ring slot", "wait: own cp.async copies", "cp.async issue", "fence + arrive"]),
-         ("issuer", ["wait: free accumulator slot", "wait: staged row", "tcgen05.mma issue + commit"]),
-         ("epilogue", ["wait: finished row", "tcgen05.ld", "zero + release", "staging barrier", "copy-out", "statistics"])]
+names = [("producer", ["wait: free ring slot"]),
+         ("issuer", ["wait: free accumulator slot", "wait: staged row (TMA)", "tcgen05.mma issue + commit"]),
+         ("epilogue", ["wait: finished row", "tcgen05.ld", "zero + release", "staging tile free (barrier)", "pack + statistics + st.shared",
+                       "fence + barrier + bulk store"])]
 rows = 2 * 128 * 128 / 148
 print(f"rolling-row kernel: {c[0, 7]:.0f} clocks per CTA, {c[0, 7] / rows:.0f} per output row")
 for r, (role, phases) in enumerate(names):

@@ -98,10 +98,16 @@ with torch.no_grad():
         for _ in range(2):
             fn()
         torch.cuda.synchronize()
+        # replayed as a CUDA graph: device time only (an eager loop of ~0.3 ms kernels can be bound by the host's launch path)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(args.iters):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
         a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for _ in range(args.iters):
-            fn()
+        g.replay()
         b_.record()
         torch.cuda.synchronize()
         print(f"{name}: {a.elapsed_time(b_) / args.iters * 1e3:.1f} us per call")

@@ -223,6 +223,87 @@ __global__ void __launch_bounds__(288, 1) timing_interf_kernel(TimingCfg c, int 
     if (tid < 32) tmem_dealloc(tmem, 512);
 }
 
+// Rolling-accumulator study: the 3^3 convolution's MMA stream in isolation.  27 MMAs of N = 144 accumulate into one 144-column
+// window of a 480-column ring; the window then moves on by 48 columns (splitting in two where the ring wraps).  Options (bits):
+//   1: tcgen05.commit after every 9 MMAs and after every 27 (arrivals on barriers nobody waits for)
+//   2: four other warps keep reading (tcgen05.ld) and zeroing (tcgen05.st) 48-column slots the MMAs are not using
+//   4: a bulk copy (TMA engine) of 16 KB global -> shared lands in a free operand slot every 9 MMAs (fire and forget)
+//   8: the window does NOT move (control)
+//  16: tcgen05.fence::after_thread_sync before every group of 9 MMAs;  32: a (satisfied) mbarrier wait by the elected lane + __syncwarp too
+__global__ void __launch_bounds__(192, 1) roll_probe_kernel(int opts, int steps, const uint8_t *gsrc, long long *out, unsigned *sink) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar, bar_sink, bar_tma, bar_done0;
+    __shared__ uint32_t slot;
+    __shared__ volatile int done, cur_step;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < 200 * 1024 / 4; i += 192) reinterpret_cast<uint32_t *>(smem)[i] = 0x3c003c00u;
+    if (tid < 32) tmem_alloc(&slot, 512);
+    if (tid == 0) { mbar_init(&bar, 1); mbar_init(&bar_sink, 1u << 20); mbar_init(&bar_tma, 1u << 20); mbar_init(&bar_done0, 1); mbar_fence_init(); done = 0; cur_step = 0;
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar_done0)) : "memory"); }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = slot;
+    if (warp == 1) {
+        // converged warp, elected lane issues (as the convolution does)
+        const uint32_t idesc3 = instr_desc_h16<true>(128, 144, false), idesc2 = instr_desc_h16<true>(128, 96, false), idesc1 = instr_desc_h16<true>(128, 48, false);
+        const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem), 16), a_hi = smem_desc_hi(1024) | (2u << 29);             // SW128 images, 17 KB apart
+        const uint32_t w_lo0 = smem_desc_lo(smem_u32(smem) + 4 * 17408, 144 * 16), w_hi = smem_desc_hi(128);       // 27 weight tiles
+        const long long t0 = clock64();
+        int ring = 0, cm = 0;
+        for (int st = 0; st < steps; ++st) {
+            const int s_hi = (opts & 8) ? 0 : 9 - cm;
+            const int n1 = min(3, 10 - s_hi);
+            for (int dz = 0; dz < 3; ++dz) {
+                if (opts & 32) mbar_wait_warp(&bar_done0, 0);
+                if (opts & 16) tc_fence_after();
+                const uint32_t a_lo = a_lo0 + ring * (17408 / 16), w_lo = w_lo0 + dz * 9 * (4608 / 16);
+#pragma unroll
+                for (int j = 0; j < 9; ++j)
+                    mma_ss_w(tmem + s_hi * 48, a_lo + (j / 3) * 8 + (j % 3) * 2, a_hi, w_lo + j * (4608 / 16), w_hi, n1 == 3 ? idesc3 : (n1 == 2 ? idesc2 : idesc1), 1u);
+                if (n1 < 3) {
+#pragma unroll
+                    for (int j = 0; j < 9; ++j)
+                        mma_ss_w(tmem, a_lo + (j / 3) * 8 + (j % 3) * 2, a_hi, w_lo + j * (4608 / 16) + n1 * 48, w_hi, n1 == 1 ? idesc2 : idesc1, 1u);
+                }
+                if (opts & 1) mma_commit_w(&bar_sink);
+                if ((opts & 4) && elect_one()) {
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     smem_u32(smem) + ((ring + 2) & 3) * 17408),
+                                 "l"(gsrc + (size_t)blockIdx.x * 65536 + ((st * 3 + dz) & 3) * 16384), "r"(16384), "r"(smem_u32(&bar_tma))
+                                 : "memory");
+                }
+                __syncwarp();
+                ring = (ring + 1) & 3;
+            }
+            if (opts & 1) mma_commit_w(&bar_sink);
+            if (++cm == 10) cm = 0;
+            if (lane == 0) cur_step = st;
+        }
+        mma_commit_w(&bar);
+        mbar_wait_warp(&bar, 0);
+        if (lane == 0) { out[blockIdx.x] = clock64() - t0; done = 1; }
+    } else if (warp >= 2 && (opts & 2)) {
+        // epilogue-like traffic on the slot 5 positions behind the window
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        unsigned acc = 0;
+        while (!done) {
+            const int sl = (9 - (cur_step % 10) + 5) % 10;
+            uint32_t r[16];
+            for (int c = 0; c < 48; c += 16) { tmem_ld16(tmem + lane_base + sl * 48 + c, r); tmem_wait_ld(); acc += r[3]; }
+            for (int i = 0; i < 16; ++i) r[i] = 0;
+            for (int c = 0; c < 48; c += 16) tmem_st16(tmem + lane_base + sl * 48 + c, r);
+            tmem_wait_st();
+            __nanosleep(500);
+        }
+        if (acc == 0xdeadbeef) sink[0] = acc;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32) tmem_dealloc(tmem, 512);
+}
+
 // ---- semantics --------------------------------------------------------------------------------------------------------------
 struct SemCfg {
     uint32_t layout_a, lbo_a, sbo_a, start_off_a, base_off_a;   // A descriptor (start = image base + start_off_a)
@@ -270,14 +351,33 @@ static uint32_t swz(uint32_t p, int xbytes) {   // address-based XOR swizzle of 
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
 
-int main() {
+int main(int argc, char **argv) {
     CK(cudaFuncSetAttribute(timing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(timing_lean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(timing_pace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(timing_interf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(roll_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(sem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
     long long *d_out;
     CK(cudaMalloc(&d_out, 148 * sizeof(long long)));
+    {
+        uint8_t *gsrc; unsigned *sink;
+        CK(cudaMalloc(&gsrc, (size_t)148 * 65536)); CK(cudaMemset(gsrc, 0x3c, (size_t)148 * 65536)); CK(cudaMalloc(&sink, 4));
+        const int steps = 222;
+        for (int rep = 0; rep < 2; ++rep)
+            for (int opts : {8, 7, 7 + 16, 7 + 32, 7 + 48}) {
+                roll_probe_kernel<<<148, 192, 200 * 1024>>>(opts, steps, gsrc, d_out, sink);
+                CK(cudaDeviceSynchronize());
+                std::vector<long long> t(148);
+                CK(cudaMemcpy(t.data(), d_out, 148 * sizeof(long long), cudaMemcpyDeviceToHost));
+                long long mx = 0, mn = 1ll << 60; double mean = 0;
+                for (long long v : t) { mx = v > mx ? v : mx; mn = v < mn ? v : mn; mean += (double)v / 148; }
+                printf("roll opts %2d (%s%s%s%s%s%s): clocks per step min / mean / max %7.0f / %7.0f / %7.0f  (27 MMAs of N = 144: floor 1944)\n", opts,
+                       (opts & 8) ? "fixed window " : "moving window ", (opts & 1) ? "+commits " : "", (opts & 2) ? "+tcgen05.ld/st traffic " : "",
+                       (opts & 4) ? "+bulk copies into operand slots " : "", (opts & 16) ? "+fence::after_thread_sync per 9 " : "", (opts & 32) ? "+mbarrier wait per 9" : "", (double)mn / steps, mean / steps, (double)mx / steps);
+            }
+        if (argc > 1) return 0;
+    }
     // ------------------------------------------------ semantics ------------------------------------------------------
     // A image: logical rows R = 0..143 of 16 fp16 (32 bytes), value (R * 16 + k) & 2047; row pitch X in {32, 64, 128} bytes with
     // the X-byte swizzle (the k-step occupies bytes [koff, koff + 32) of the row), or the no-swizzle chunk-plane layout.

@@ -20,7 +20,10 @@
 //   * Accumulators: 4 output rows x 48 columns, double buffered in TMEM (2 x 192 columns), so the epilogue of a block
 //     (TMEM -> bf16 -> staging -> coalesced stores + per-channel sum / sum of squares) overlaps the MMAs of the next one.
 // Warp roles (288 threads): warps 0-3 loaders (+ optional input normalisation), warp 4 MMA issuer, warps 5-8 epilogue.
+#include <cstdlib>
 #include <type_traits>
+
+#include <cuda.h>
 
 #include "tc_common.cuh"
 #include "wf_common.cuh"
@@ -353,43 +356,61 @@ __global__ void __launch_bounds__(288, 1) conv3d_k3_c48_kernel(K3Args a) {
 
 // ------------------------------------------------------------------------------------------------------------------------------
 // Rolling-row variant (the default when the input needs no normalisation).  What the stage clocks of the block kernel above
-// showed (scripts/k3_stage_clocks.py): its loader warps are busy 89 % of the time - a thread copying "its" voxel makes every
-// warp-wide cp.async touch 24 different 128-byte lines - the issuer waits for staged rows, and a third of the MMAs are edge
-// rows of a 4-row block with N = 48 / 96, which cost the same 66-72 clk as N = 144 (scripts/mma_probe.cu).  Here:
+// showed (scripts/k3_stage_clocks.py, profiles/r02_k3_stage_clocks.txt): every role was busy - the SM's load / store pipe was the
+// shared limiter (cp.async copies of 16 bytes per thread, a fence + mbarrier arrival per thread and row, ld.shared + st.global of
+// the staged result, 32 ld.shared per thread and row for the statistics), and a third of the MMAs were edge rows of a 4-row block
+// with N = 48 / 96, which occupy the tensor pipe as long as N = 144 does (scripts/mma_probe.cu: max(66, N / 2) clk per MMA, whatever
+// the operand layout).  Here:
 //   * a CTA owns a contiguous RUN of output rows (B * D * H rows split evenly over the grid) and walks it in y.  The accumulators
 //     of the output rows in flight form a ring of 10 TMEM slots (48 columns each); the input row (z + dz, y') feeds the output
 //     rows y' - 1, y', y' + 1, whose slots are adjacent, so EVERY MMA is 128 x 144 x 16 (two smaller ones where the ring wraps or a
 //     run starts / ends): 27 MMAs and 3 staged input rows per output row instead of 40.5 and 4.5;
-//   * an output row is complete one step after its own y, the epilogue drains it (TMEM -> 16 bit -> staging -> coalesced stores +
-//     statistics) while the tensor pipe is three rows ahead, zeroes the slot and hands it back;
-//   * loader threads copy CONSECUTIVE 16-byte chunks of the row (chunk q = voxel * 6 + channel chunk), so a warp-wide cp.async
-//     reads 512 contiguous bytes; the issuer is one converged warp (tc_common.cuh, "warp-uniform issue").
+//   * an input row is ONE cp.async.bulk.tensor (TMA) instruction issued by one thread: box [64 channels x 130 voxels] at x = -1
+//     of a tensor map [48 channels][128 x][rows]: the two halo rows and channels 48..63 are the out-of-bounds zero fill, and the
+//     image lands 128-byte swizzled, K-major, 128 bytes per voxel - the operand of tap dx / k-step ks is the same image with its
+//     descriptor start advanced by dx * 128 + ks * 32 bytes (scripts/tma_probe.cu checks exactly this);
+//   * an output row is complete one step after its own y; four epilogue warps drain it (TMEM -> 16 bit, per-thread running
+//     sum / sum of squares of its 48 channels in registers, dense staging tile, ONE bulk store of the 12 KB row) while the tensor
+//     pipe is rows ahead, zero the slot and hand it back.
 // `addend` (optional): a second 16-bit tensor laid out like y that is added to the accumulators before rounding - the second
 // pass of a convolution whose input channels are split over two launches (decoder1.conv1: 96 = 48 + 48 input channels).
 constexpr int kRollSlots = 10;                                 // accumulator ring: output rows in flight
-constexpr int kRollRing = 6;                                   // staged input rows
-constexpr int kRollStage = 128 * (kK3C + 8) * 2;               // one output row, 16 bit, 112-byte pitch: 14336 bytes
-constexpr int kRollSmem = kK3WBytes + kRollRing * kK3RowImg + 2 * kRollStage;   // 229120
+constexpr int kRollImgBytes = 130 * 128;                       // what one TMA box delivers
+constexpr int kRollImg = 17 * 1024;                            // slot pitch: 1024-byte aligned (swizzle atoms are 8 rows x 128 bytes)
+constexpr int kRollStage = 128 * kK3C * 2;                     // one dense output row: 12288 bytes
+constexpr int roll_smem(int ring, int nstage) { return ring * kRollImg + kK3WBytes + nstage * kRollStage; }   // 4 slots, 2 tiles: 218624; 5, 1: 223744
+constexpr int kRollThreads = 192;                              // warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue
 
 struct K3RollArgs {
-    const uint16_t *x;          // [B, D, H, 128, 48 of xs]
     const uint16_t *wpack;      // as K3Args
     uint16_t *y;                // [B, D, H, 128, 48 of ys]
     const uint16_t *addend;     // optional, voxel stride as_
     double *sums;
-    int64_t xs, ys, as_;
+    int64_t ys, as_;
     int B, D, H;
+    int no_bulk;                // tuning switch: copy the staged row out with the threads instead of one bulk store
     long long *prof;
 };
 
-template <bool F16, bool PROF = false>
-__global__ void __launch_bounds__(288, 1) conv3d_k3_c48_roll_kernel(K3RollArgs a) {
-    extern __shared__ __align__(128) uint8_t smem[];
+__device__ __forceinline__ void tma_load_row(void *dst, const CUtensorMap *map, int row, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(map), "r"(0), "r"(-1), "r"(row), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// kRollRing staged input rows, kRollNStage output staging tiles
+template <bool F16, int kRollRing, int kRollNStage, bool PROF = false>
+__global__ void __launch_bounds__(kRollThreads, 1) conv3d_k3_c48_roll_kernel(const __grid_constant__ CUtensorMap xmap, K3RollArgs a) {
+    unsigned long long gt_entry = 0;
+    if constexpr (PROF) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_entry));
+    extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_full[kRollRing], bar_empty[kRollRing], bar_row_full[kRollSlots], bar_row_empty[kRollSlots];
     __shared__ uint32_t tmem_slot;
-    uint8_t *sW = smem;
-    uint8_t *sRing = smem + kK3WBytes;
-    uint8_t *sStage = smem + kK3WBytes + kRollRing * kK3RowImg;
+    __shared__ float s_red[4][2 * kK3C];
+    uint8_t *sRing = smem;
+    uint8_t *sW = smem + kRollRing * kRollImg;
+    uint8_t *sStage = sW + kK3WBytes;
     const int tid = threadIdx.x, warp = (int)warp_idx_uniform(), lane = tid & 31;
     constexpr int W = 128;
     // this CTA's run of output rows [r0, r1) in (b, z, y) order
@@ -399,7 +420,7 @@ __global__ void __launch_bounds__(288, 1) conv3d_k3_c48_roll_kernel(K3RollArgs a
     if (warp == 0) tmem_alloc(&tmem_slot, 512);
     if (tid == 0) {
         for (int i = 0; i < kRollRing; ++i) {
-            mbar_init(&bar_full[i], 128);        // one deferred arrival per loader thread
+            mbar_init(&bar_full[i], 1);          // the producer's arrive.expect_tx; the TMA completes the transaction bytes
             mbar_init(&bar_empty[i], 1);         // tcgen05.commit
         }
         for (int i = 0; i < kRollSlots; ++i) {
@@ -408,14 +429,8 @@ __global__ void __launch_bounds__(288, 1) conv3d_k3_c48_roll_kernel(K3RollArgs a
         }
         mbar_fence_init();
     }
-    for (int i = tid; i < kK3WBytes / 16; i += 288)
+    for (int i = tid; i < kK3WBytes / 16; i += kRollThreads)
         reinterpret_cast<uint4 *>(sW)[i] = __ldg(reinterpret_cast<const uint4 *>(a.wpack) + i);
-    for (int i = tid; i < kRollRing * kK3Chunks * 4; i += 288) {        // zero halo rows 0, 129, 130, 131 of every chunk plane
-        const int slot = i / (kK3Chunks * 4), r = i % (kK3Chunks * 4);
-        const int ch = r >> 2, which = r & 3;
-        const int row = which == 0 ? 0 : 128 + which;
-        *reinterpret_cast<uint4 *>(sRing + slot * kK3RowImg + (ch * kK3Rows + row) * 16) = make_uint4(0u, 0u, 0u, 0u);
-    }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -425,138 +440,154 @@ __global__ void __launch_bounds__(288, 1) conv3d_k3_c48_roll_kernel(K3RollArgs a
     const long long p_t0 = PROF ? clock64() : 0;
 #define K3_TIMED(idx, ...) do { if constexpr (PROF) { const long long t_ = clock64(); __VA_ARGS__; pw[idx] += clock64() - t_; } else { __VA_ARGS__; } } while (0)
 
-    if (warp < 4) {
-        // ================================================= loaders ====================================================
-        // chunk q = it * 128 + tid of a row: voxel q / 6, channel chunk q % 6 (consecutive threads -> consecutive 16 bytes)
-        int soff[kK3Chunks], doff[kK3Chunks];
-#pragma unroll
-        for (int it = 0; it < kK3Chunks; ++it) {
-            const int q = it * 128 + tid, vx = q / kK3Chunks, ch = q - vx * kK3Chunks;
-            soff[it] = (int)(vx * a.xs) + ch * 8;
-            doff[it] = (ch * kK3Rows + vx + 1) * 16;
-        }
-        uint32_t n_loaded = 0, n_arrived = 0;
-        auto announce_upto = [&](uint32_t upto) {
-            for (; n_arrived < upto; ++n_arrived) {
-                fence_proxy_async();
-                mbar_arrive_k3(&bar_full[n_arrived % kRollRing]);
-            }
-        };
-        for (int64_t r = r0; r < r1;) {
-            const int64_t p = r / a.H;
-            const int ya = (int)(r - p * a.H);
-            const int n = (int)min((int64_t)(a.H - ya), r1 - r);
-            const int yb = ya + n - 1;
-            const int64_t b = p / a.D;
-            const int z = (int)(p - b * a.D);
-            const int ys = max(ya - 1, 0), ye = min(yb + 1, a.H - 1);
-            for (int yy = ys; yy <= ye; ++yy)
-                for (int dz = -1; dz <= 1; ++dz) {
-                    const int zz = z + dz;
-                    if ((unsigned)zz >= (unsigned)a.D) continue;
-                    const int slot = n_loaded % kRollRing;
-                    const uint32_t use = n_loaded / kRollRing;
-                    if (use > 0) K3_TIMED(0, mbar_wait(&bar_empty[slot], (use - 1) & 1));
-                    uint8_t *img = sRing + slot * kK3RowImg;
-                    const uint16_t *src = a.x + ((((int64_t)b * a.D + zz) * a.H + yy) * W) * a.xs;
-                    K3_TIMED(2, {
-#pragma unroll
-                    for (int it = 0; it < kK3Chunks; ++it) cp_async16_k3(img + doff[it], src + soff[it]);
-                    asm volatile("cp.async.commit_group;" ::: "memory"); });
-                    if (n_loaded + 1 - n_arrived > kK3Lag) {
-                        K3_TIMED(1, asm volatile("cp.async.wait_group %0;" ::"n"(kK3Lag) : "memory"));
-                        K3_TIMED(3, announce_upto(n_loaded + 1 - kK3Lag));
-                    }
-                    ++n_loaded;
-                }
-            r += n;
-        }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        announce_upto(n_loaded);
-        if constexpr (PROF)
-            if (tid == 0) {
-                for (int q = 0; q < 7; ++q) a.prof[(blockIdx.x * 3 + 0) * 8 + q] = pw[q];
-                a.prof[(blockIdx.x * 3 + 0) * 8 + 7] = clock64() - p_t0;
-            }
-    } else if (warp == 4) {
-        // ================================================= issuer =====================================================
-        const uint32_t idesc1 = instr_desc_h16<F16>(128, kK3C, false), idesc2 = instr_desc_h16<F16>(128, 2 * kK3C, false),
-                       idesc3 = instr_desc_h16<F16>(128, 3 * kK3C, false);
-        const uint32_t a_lo0 = smem_desc_lo(smem_u32(sRing), kK3Rows * 16), a_hi = smem_desc_hi(128);
-        const uint32_t w_lo0 = smem_desc_lo(smem_u32(sW), 3 * kK3C * 16), w_hi = smem_desc_hi(128);
-        auto mma_set = [&](uint32_t a_lo, uint32_t w_lo, uint32_t acc, int nrows) {
-            const uint32_t idesc = nrows == 3 ? idesc3 : (nrows == 2 ? idesc2 : idesc1);
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx)
-#pragma unroll
-                for (int ks = 0; ks < 3; ++ks)
-                    mma_ss_w(acc, a_lo + (uint32_t)(ks * 2 * kK3Rows + dx), a_hi, w_lo + (uint32_t)((dx * 3 + ks) * (kK3WTile3 / 16)), w_hi,
-                             idesc, 1u);
-        };
-        uint32_t n_used = 0;
-        int64_t c0 = 0, c_ready = 0;     // output-row counters of this CTA: first row of the segment / rows whose slot is known free
+    if (warp == 0) {
+        // ================================================= producer ===================================================
+        int slot = 0;
+        uint32_t ph = 1;                 // parity of the "slot is free" phase to wait for; the first pass over the ring is free
+        bool first_pass = true;
         for (int64_t r = r0; r < r1;) {
             const int64_t p = r / a.H;
             const int ya = (int)(r - p * a.H);
             const int n = (int)min((int64_t)(a.H - ya), r1 - r);
             const int yb = ya + n - 1;
             const int z = (int)(p % a.D);
-            const int ys = max(ya - 1, 0), ye = min(yb + 1, a.H - 1);
-            for (int yy = ys; yy <= ye; ++yy) {
-                // output rows fed by the input rows at yy: lo .. hi; row hi sits in the LOWEST slot (slots descend with the row
-                // counter so that ascending TMEM columns meet the weight tile's ascending dy order)
-                const int lo = max(yy - 1, ya), hi = min(yy + 1, yb);
-                const int64_t chi = c0 + (hi - ya);
-                for (; c_ready <= chi; ++c_ready)
-                    K3_TIMED(0, mbar_wait_warp(&bar_row_empty[kRollSlots - 1 - (int)(c_ready % kRollSlots)], (uint32_t)(c_ready / kRollSlots) & 1));
-                tc_fence_after();
-                const int nrows = hi - lo + 1;
-                const int s_hi = kRollSlots - 1 - (int)(chi % kRollSlots);
-                const int n1 = min(nrows, kRollSlots - s_hi);            // rows before the ring wraps
-                const uint32_t wrow = (uint32_t)((yy - hi + 1) * kK3C);    // first weight row: dy of row hi = yy - hi
+            // Every step loads three rows, whatever the position: a row outside the volume (z + dz or yy out of range) is fetched
+            // at row coordinate -1, i.e. entirely from the tensor map's out-of-bounds zero fill, and contributes nothing.  The
+            // pipeline therefore has ONE shape (3 rows and 27 MMAs per step) from the first step to the last.
+            for (int yy = ya - 1; yy <= yb + 1; ++yy)
                 for (int dz = -1; dz <= 1; ++dz) {
-                    if ((unsigned)(z + dz) >= (unsigned)a.D) continue;
-                    const int slot = n_used % kRollRing;
-                    K3_TIMED(1, mbar_wait_warp(&bar_full[slot], (n_used / kRollRing) & 1));
-                    tc_fence_after();
-                    const uint32_t a_lo = a_lo0 + (uint32_t)(slot * (kK3RowImg / 16));
-                    const uint32_t w_lo = w_lo0 + (uint32_t)((dz + 1) * 9 * (kK3WTile3 / 16)) + wrow;
-                    K3_TIMED(2, {
-                    mma_set(a_lo, w_lo, tmem + (uint32_t)(s_hi * kK3C), n1);
-                    if (n1 < nrows) mma_set(a_lo, w_lo + (uint32_t)(n1 * kK3C), tmem, nrows - n1);
-                    mma_commit_w(&bar_empty[slot]); });
-                    ++n_used;
+                    const bool inside = (unsigned)(z + dz) < (unsigned)a.D && (unsigned)yy < (unsigned)a.H;
+                    if (!first_pass) K3_TIMED(0, mbar_wait_warp_relaxed(&bar_empty[slot], ph));   // the MMAs that read this slot are done
+                    if ((a.no_bulk & 2) && !first_pass) {                  // experiment: no TMA traffic after the first pass over the ring
+                        if (elect_one()) mbar_arrive_k3(&bar_full[slot]);
+                    } else if (elect_one()) {
+                        mbar_expect_tx(&bar_full[slot], kRollImgBytes);
+                        tma_load_row(sRing + slot * kRollImg, &xmap, inside ? (int)((p + dz) * a.H + yy) : -1, &bar_full[slot]);
+                    }
+                    __syncwarp();
+                    if (++slot == kRollRing) { slot = 0; ph ^= 1; first_pass = false; }
                 }
-                if (yy - 1 >= ya) mma_commit_w(&bar_row_full[kRollSlots - 1 - (int)((c0 + (yy - 1 - ya)) % kRollSlots)]);
-                if (yy == ye && yy == yb) mma_commit_w(&bar_row_full[kRollSlots - 1 - (int)((c0 + (yb - ya)) % kRollSlots)]);
-            }
-            c0 += n;
             r += n;
         }
         if constexpr (PROF)
             if (lane == 0) {
-                for (int q = 0; q < 7; ++q) a.prof[(blockIdx.x * 3 + 1) * 8 + q] = pw[q];
+                for (int q = 0; q < 6; ++q) a.prof[(blockIdx.x * 3 + 0) * 8 + q] = pw[q];
+                a.prof[(blockIdx.x * 3 + 0) * 8 + 6] = (long long)gt_entry;                 // wall clock (ns) at kernel entry
+                a.prof[(blockIdx.x * 3 + 0) * 8 + 7] = clock64() - p_t0;
+            }
+    } else if (warp == 1) {
+        // ================================================= issuer =====================================================
+        // The issue loop is kept SMALL on purpose (one copy of the nine tcgen05.mma of a (dz, part), runtime loops around it): with
+        // the three dz taps and the ring-wrap split unrolled the kernel had 102 MMA sites in 200 KB of code, and CTAs fell for
+        // hundreds of steps into a mode of ~550 clk per MMA (profiles/r02_k3_roll_notes.txt) - the issuing warp starved for
+        // instructions - while scripts/mma_probe.cu runs the same stream at ~90 clk per MMA.  The MMA queue is shallow: whatever the
+        // issuing warp does between two MMAs (barrier polls, address arithmetic) is exposed as tensor-pipe idle time.
+        const uint32_t idesc0 = instr_desc_h16<F16>(128, 0, false);                  // N field (bits 17..22, N >> 3) added per call
+        // A: 128-byte swizzle, K-major: 8-row groups 1024 bytes apart (the leading-dimension field is unused); layout type 2 sits
+        // in bits 61..63 of the descriptor.  Weights: no swizzle, tile (dz, dx, ks) = [2 chunks][144 = dy x out][8]
+        const uint32_t a_lo0 = smem_desc_lo(smem_u32(sRing), 16), a_hi = smem_desc_hi(1024) | (2u << 29);
+        const uint32_t w_lo0 = smem_desc_lo(smem_u32(sW), 3 * kK3C * 16), w_hi = smem_desc_hi(128);
+        // ring positions are kept as (index, phase) pairs advanced by hand: no 64-bit division in the issue loop
+        int ring_i = 0;                  // staged-row slot to consume next
+        uint32_t ring_ph = 0;
+        int c0m = 0;                     // (output-row counter of the segment's first row) mod kRollSlots
+        int ready_m = 0, ready_rows = 0; // counter of the next row whose slot must be confirmed free: mod kRollSlots / absolute
+        uint32_t ready_ph = 0;
+        int c0 = 0;                      // output-row counter (rows per CTA fit 31 bits)
+        int trace_n = 0;                 // PROF + tuning bit 8: clock at every y step -> clocks[148 * 24 + cta * 512 + step]
+        for (int64_t r = r0; r < r1;) {
+            const int64_t p = r / a.H;
+            const int ya = (int)(r - p * a.H);
+            const int n = (int)min((int64_t)(a.H - ya), r1 - r);
+            const int yb = ya + n - 1;
+            for (int yy = ya - 1; yy <= yb + 1; ++yy) {
+                if constexpr (PROF)
+                    if ((a.no_bulk & 8) && lane == 0 && trace_n < 512) a.prof[148 * 24 + blockIdx.x * 512 + trace_n++] = clock64() - p_t0;
+                // output rows fed by the input rows at yy: lo .. hi; row hi sits in the LOWEST slot (slots descend with the row
+                // counter so that ascending TMEM columns meet the weight tile's ascending dy order)
+                const int lo = max(yy - 1, ya), hi = min(yy + 1, yb);
+                const int chi = c0 + (hi - ya);
+                while (ready_rows <= chi) {
+                    K3_TIMED(0, mbar_wait_warp(&bar_row_empty[kRollSlots - 1 - ready_m], ready_ph));
+                    ++ready_rows;
+                    if (++ready_m == kRollSlots) { ready_m = 0; ready_ph ^= 1; }
+                }
+                tc_fence_after();
+                const int nrows = hi - lo + 1;
+                const int him = (c0m + (hi - ya)) % kRollSlots;
+                const int s_hi = kRollSlots - 1 - him;
+                const int n1 = min(nrows, kRollSlots - s_hi);            // rows before the ring wraps
+                const uint32_t wrow = (uint32_t)((yy - hi + 1) * kK3C);    // first weight row: dy of row hi = yy - hi
+#pragma unroll 1
+                for (int dz = 0; dz < 3; ++dz) {
+                    K3_TIMED(1, mbar_wait_warp(&bar_full[ring_i], ring_ph));     // TMA data: the barrier's acquire is all it needs
+                    const uint32_t a_lo = a_lo0 + (uint32_t)(ring_i * (kRollImg / 16));
+                    const uint32_t w_lo = w_lo0 + (uint32_t)(dz * 9 * (kK3WTile3 / 16)) + wrow;
+                    K3_TIMED(2, {
+#pragma unroll 1
+                        for (int part = 0; part < (n1 < nrows ? 2 : 1); ++part) {
+                            const uint32_t acc = part ? tmem : tmem + (uint32_t)(s_hi * kK3C);
+                            const int nr = part ? nrows - n1 : n1;
+                            const uint32_t wl = w_lo + (uint32_t)(part ? n1 * kK3C : 0);
+                            const uint32_t idesc = idesc0 + ((uint32_t)(nr * (kK3C >> 3)) << 17);
+#pragma unroll
+                            for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+                                for (int ks = 0; ks < 3; ++ks)
+                                    mma_ss_w(acc, a_lo + (uint32_t)(dx * 8 + ks * 2), a_hi, wl + (uint32_t)((dx * 3 + ks) * (kK3WTile3 / 16)), w_hi, idesc, 1u);
+                        }
+                        mma_commit_w(&bar_empty[ring_i]);
+                    });
+                    if (++ring_i == kRollRing) { ring_i = 0; ring_ph ^= 1; }
+                }
+                // row yy - 1 has received its three input rows
+                if (yy - 1 >= ya) mma_commit_w(&bar_row_full[kRollSlots - 1 - (c0m + (yy - 1 - ya)) % kRollSlots]);
+            }
+            c0 += n;
+            c0m = (c0m + n) % kRollSlots;
+            r += n;
+        }
+        if constexpr (PROF)
+            if (lane == 0) {
+                for (int q = 0; q < 6; ++q) a.prof[(blockIdx.x * 3 + 1) * 8 + q] = pw[q];
+                unsigned long long gt_now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_now));
+                a.prof[(blockIdx.x * 3 + 1) * 8 + 6] = (long long)gt_now;                   // wall clock (ns) when the issuer is done
                 a.prof[(blockIdx.x * 3 + 1) * 8 + 7] = clock64() - p_t0;
             }
     } else {
         // ================================================ epilogue ====================================================
-        const int quad = warp & 3;
+        const int quad = warp & 3;                          // a warp may touch TMEM lanes 32 * (warp id % 4) .. + 31 only
         const int et = quad * 32 + lane;                    // voxel x of this thread's TMEM lane
+        const int ew = warp - 2;                            // 0..3
+        const bool leader = warp == 2 && lane == 0;         // issues the bulk stores
         const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-        constexpr int pitch = kK3C + 8;
-        double acc_s[2] = {0.0, 0.0}, acc_q[2] = {0.0, 0.0};
-        int64_t acc_b = -1;
-        const int cpair = et % 24, rq = et / 24;
-        auto flush = [&]() {
-            if (et < 96 && acc_b >= 0) {
+        const bool dense = a.ys == kK3C && !(a.no_bulk & 1);
+        float st_s[kK3C], st_q[kK3C];                       // running sum / sum of squares of this thread's voxel column, per channel
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    double *dst = a.sums + (acc_b * kK3C + 2 * cpair + e) * 2;
-                    atomicAdd(dst, acc_s[e]);
-                    atomicAdd(dst + 1, acc_q[e]);
+        for (int i = 0; i < kK3C; ++i) st_s[i] = st_q[i] = 0.f;
+        int64_t acc_b = -1;
+        auto flush = [&]() {
+            // reduce over the 128 voxel columns: butterfly inside each warp, the four warps through shared memory, one fp64 atomic
+            // per (channel, moment) and CTA
+            if (acc_b >= 0) {
+#pragma unroll
+                for (int i = 0; i < kK3C; ++i) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        st_s[i] += __shfl_xor_sync(0xffffffffu, st_s[i], o);
+                        st_q[i] += __shfl_xor_sync(0xffffffffu, st_q[i], o);
+                    }
+                    if (lane == 0) { s_red[ew][2 * i] = st_s[i]; s_red[ew][2 * i + 1] = st_q[i]; }
                 }
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                const int idx = ew * 32 + lane;
+                if (idx < 2 * kK3C)
+                    atomicAdd(a.sums + acc_b * 2 * kK3C + idx, (double)s_red[0][idx] + (double)s_red[1][idx] + (double)s_red[2][idx] + (double)s_red[3][idx]);
+                asm volatile("bar.sync 2, 128;" ::: "memory");
             }
-            acc_s[0] = acc_s[1] = acc_q[0] = acc_q[1] = 0.0;
+#pragma unroll
+            for (int i = 0; i < kK3C; ++i) st_s[i] = st_q[i] = 0.f;
         };
         auto zero_and_release = [&](int slot) {
             uint32_t zeros[16];
@@ -570,76 +601,99 @@ __global__ void __launch_bounds__(288, 1) conv3d_k3_c48_roll_kernel(K3RollArgs a
             if (lane == 0) mbar_arrive_k3(&bar_row_empty[slot]);
         };
         for (int sl = 0; sl < kRollSlots; ++sl) zero_and_release(sl);
-        int64_t c = 0;
+        int cm = 0, cstage = 0;          // output-row counter mod kRollSlots / mod kRollNStage
+        uint32_t cph = 0;
         for (int64_t r = r0; r < r1;) {
             const int64_t p = r / a.H;
             const int ya = (int)(r - p * a.H);
             const int n = (int)min((int64_t)(a.H - ya), r1 - r);
             const int64_t b = p / a.D;
             if (b != acc_b) { flush(); acc_b = b; }
-            for (int y = ya; y < ya + n; ++y, ++c) {
-                const int slot = kRollSlots - 1 - (int)(c % kRollSlots);
-                uint16_t *stage = reinterpret_cast<uint16_t *>(sStage + (c & 1) * kRollStage);
+            for (int y = ya; y < ya + n; ++y) {
+                const int slot = kRollSlots - 1 - cm;
+                const uint32_t slot_ph = cph;
+                uint16_t *stage = reinterpret_cast<uint16_t *>(sStage + cstage * kRollStage);
+                if (++cm == kRollSlots) { cm = 0; cph ^= 1; }
+                if (++cstage == kRollNStage) cstage = 0;
                 const int64_t v0 = (p * a.H + y) * W;              // first voxel of the output row
                 uint4 add[kK3Chunks];
                 if (a.addend != nullptr) {
 #pragma unroll
                     for (int k = 0; k < kK3Chunks; ++k) add[k] = *reinterpret_cast<const uint4 *>(a.addend + (v0 + et) * a.as_ + k * 8);
                 }
-                K3_TIMED(0, mbar_wait(&bar_row_full[slot], (uint32_t)(c / kRollSlots) & 1));
+                K3_TIMED(0, mbar_wait_warp_relaxed(&bar_row_full[slot], slot_ph));
                 tc_fence_after();
                 uint32_t rr[3][16];
                 K3_TIMED(1, {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) tmem_ld16(tmem + lane_base + slot * kK3C + k * 16, rr[k]);
-                tmem_wait_ld(); });
+                    for (int k = 0; k < 3; ++k) tmem_ld16(tmem + lane_base + slot * kK3C + k * 16, rr[k]);
+                    tmem_wait_ld();
+                });
                 K3_TIMED(2, zero_and_release(slot));
+                // the staging tile this row goes to was last read by the bulk store of row c - kRollNStage
+                K3_TIMED(3, {
+                    if (leader) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kRollNStage - 1) : "memory");
+                    asm volatile("bar.sync 2, 128;" ::: "memory");
+                });
+                K3_TIMED(4, {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    float f[16];
+                    for (int k = 0; k < 3; ++k) {
+                        float f[16];
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(rr[k][e]);
-                    if (a.addend != nullptr) {
-                        const uint4 a0 = add[2 * k], a1 = add[2 * k + 1];
-                        const uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                        for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(rr[k][e]);
+                        if (a.addend != nullptr) {
+                            const uint4 a0 = add[2 * k], a1 = add[2 * k + 1];
+                            const uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const float2 t = unpack_h16<F16>(aw[e]);
+                                f[2 * e] += t.x;
+                                f[2 * e + 1] += t.y;
+                            }
+                        }
+                        uint32_t w8[8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
-                            const float2 t = unpack_h16<F16>(aw[e]);
-                            f[2 * e] += t.x;
-                            f[2 * e + 1] += t.y;
+                            w8[e] = pack_h16<F16>(f[2 * e], f[2 * e + 1]);
+                            stat_h16x2<F16>(w8[e], st_s[k * 16 + 2 * e], st_s[k * 16 + 2 * e + 1], st_q[k * 16 + 2 * e], st_q[k * 16 + 2 * e + 1]);
                         }
+                        uint4 *dst = reinterpret_cast<uint4 *>(stage + (size_t)et * kK3C + k * 16);
+                        dst[0] = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+                        dst[1] = make_uint4(w8[4], w8[5], w8[6], w8[7]);
                     }
-                    uint4 lo4, hi4;
-                    lo4.x = pack_h16<F16>(f[0], f[1]);   lo4.y = pack_h16<F16>(f[2], f[3]);   lo4.z = pack_h16<F16>(f[4], f[5]);   lo4.w = pack_h16<F16>(f[6], f[7]);
-                    hi4.x = pack_h16<F16>(f[8], f[9]);   hi4.y = pack_h16<F16>(f[10], f[11]); hi4.z = pack_h16<F16>(f[12], f[13]); hi4.w = pack_h16<F16>(f[14], f[15]);
-                    uint4 *dst = reinterpret_cast<uint4 *>(stage + (size_t)et * pitch + k * 16);
-                    dst[0] = lo4;
-                    dst[1] = hi4;
-                }
-                // staging of this row complete (epilogue warps only); the other staging buffer's readers all passed this barrier too
-                K3_TIMED(3, asm volatile("bar.sync 2, 128;" ::: "memory"));
-                K3_TIMED(4, {
-                for (int i = et; i < 128 * kK3Chunks; i += 128) {
-                    const int vx = i / kK3Chunks, pc = i - vx * kK3Chunks;
-                    *reinterpret_cast<uint4 *>(a.y + (v0 + vx) * a.ys + pc * 8) = *reinterpret_cast<const uint4 *>(stage + (size_t)vx * pitch + pc * 8);
-                } });
-                const long long t_stats = PROF ? clock64() : 0;
-                if (et < 96) {
-                    const uint32_t *col = reinterpret_cast<const uint32_t *>(stage) + cpair;
-                    constexpr int wpitch = pitch / 2;
-                    float s0 = 0.f, s1 = 0.f, qq0 = 0.f, qq1 = 0.f;
-#pragma unroll 8
-                    for (int q = rq * 32; q < rq * 32 + 32; ++q) stat_h16x2<F16>(col[(size_t)q * wpitch], s0, s1, qq0, qq1);
-                    acc_s[0] += (double)s0; acc_s[1] += (double)s1; acc_q[0] += (double)qq0; acc_q[1] += (double)qq1;
-                }
-                if constexpr (PROF) pw[5] += clock64() - t_stats;
+                });
+                K3_TIMED(5, {
+                    if (a.no_bulk & 4) {                                    // experiment: the result is not stored
+                    } else if (dense) {
+                        fence_proxy_async();                                // my staging writes -> visible to the bulk-copy engine
+                        asm volatile("bar.sync 2, 128;" ::: "memory");
+                        if (leader) {
+                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(a.y + v0 * kK3C), "r"(smem_u32(stage)),
+                                         "r"(kRollStage)
+                                         : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                    } else {
+                        // y is a channel slice of a wider buffer: 96-byte pieces, copied by the threads
+                        asm volatile("bar.sync 2, 128;" ::: "memory");
+                        for (int i = et; i < 128 * kK3Chunks; i += 128) {
+                            const int vx = i / kK3Chunks, pc = i - vx * kK3Chunks;
+                            *reinterpret_cast<uint4 *>(a.y + (v0 + vx) * a.ys + pc * 8) = *reinterpret_cast<const uint4 *>(stage + (size_t)vx * kK3C + pc * 8);
+                        }
+                        if constexpr (kRollNStage == 1) asm volatile("bar.sync 2, 128;" ::: "memory");
+                    }
+                });
             }
             r += n;
         }
         flush();
+        if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         if constexpr (PROF)
             if (et == 0) {
-                for (int q = 0; q < 7; ++q) a.prof[(blockIdx.x * 3 + 2) * 8 + q] = pw[q];
+                for (int q = 0; q < 6; ++q) a.prof[(blockIdx.x * 3 + 2) * 8 + q] = pw[q];
+                uint32_t smid;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                a.prof[(blockIdx.x * 3 + 2) * 8 + 6] = (long long)smid;
                 a.prof[(blockIdx.x * 3 + 2) * 8 + 7] = clock64() - p_t0;
             }
     }
@@ -674,31 +728,49 @@ static int k3_launch(const void *x, int dtype, const void *wpack, const void *ad
     if (addend && (in_mean_rstd || add_vox_stride < kK3C || add_vox_stride % 8)) return WF_ERR_BAD_SHAPE;
     if (addend && !aligned16(addend)) return WF_ERR_MISALIGNED;
     if (prof && dtype != WF_F16) return WF_ERR_BAD_DTYPE;
-    if ((int64_t)127 * x_vox_stride + 40 > 0x7fffffff) return WF_ERR_BAD_SHAPE;
     cudaStream_t st = (cudaStream_t)stream;
     static unsigned long long attr_done = 0;   // per-device opt-in bits
     if (first_use_on_current_device(attr_done)) {
         WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_k3_c48_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kK3Smem));
         WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_k3_c48_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kK3Smem));
         WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_k3_c48_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kK3Smem));
-        WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_k3_c48_roll_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRollSmem));
-        WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_k3_c48_roll_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRollSmem));
-        WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_k3_c48_roll_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRollSmem));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_k3_c48_roll_kernel<false, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, roll_smem(4, 2)));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_k3_c48_roll_kernel<true, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, roll_smem(4, 2)));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_k3_c48_roll_kernel<true, 4, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, roll_smem(4, 2)));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_k3_c48_roll_kernel<true, 5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, roll_smem(5, 1)));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_k3_c48_roll_kernel<true, 5, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, roll_smem(5, 1)));
     }
     WF_CUDA_CHECK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)B * kK3C, st));
     if (in_mean_rstd == nullptr) {
-        // rolling-row kernel: the run of B * D * H output rows is split evenly over one CTA per SM
-        K3RollArgs r;
-        r.x = (const uint16_t *)x; r.wpack = (const uint16_t *)wpack; r.y = (uint16_t *)y; r.addend = (const uint16_t *)addend;
-        r.sums = sums; r.xs = x_vox_stride; r.ys = y_vox_stride; r.as_ = add_vox_stride; r.B = B; r.D = D; r.H = H; r.prof = prof;
+        // rolling-row kernel: the run of B * D * H output rows is split evenly over one CTA per SM.  The input is described by a
+        // TMA tensor map [48 channels][128 x][B * D * H rows] (fp16 and bf16 are both "16-bit, no conversion" to the copy engine).
         const int64_t rows = (int64_t)B * D * H;
-        const int grid = (int)(rows < kNumSMs ? rows : kNumSMs);
-        if (prof != nullptr)
-            conv3d_k3_c48_roll_kernel<true, true><<<grid, 288, kRollSmem, st>>>(r);
-        else if (dtype == WF_F16)
-            conv3d_k3_c48_roll_kernel<true><<<grid, 288, kRollSmem, st>>>(r);
-        else
-            conv3d_k3_c48_roll_kernel<false><<<grid, 288, kRollSmem, st>>>(r);
+        if (rows > 0x7fffffff) return WF_ERR_BAD_SHAPE;
+        CUtensorMap xmap;
+        const cuuint64_t gdim[3] = {(cuuint64_t)kK3C, 128, (cuuint64_t)rows};
+        const cuuint64_t gstr[2] = {(cuuint64_t)x_vox_stride * 2, (cuuint64_t)x_vox_stride * 2 * 128};
+        const cuuint32_t box[3] = {64, 130, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        if (cuTensorMapEncodeTiled(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(x), gdim, gstr, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return WF_ERR_CUDA;
+        K3RollArgs r;
+        r.wpack = (const uint16_t *)wpack; r.y = (uint16_t *)y; r.addend = (const uint16_t *)addend;
+        r.sums = sums; r.ys = y_vox_stride; r.as_ = add_vox_stride; r.B = B; r.D = D; r.H = H; r.prof = prof;
+        static const int no_bulk = getenv("WF_K3_NOBULK") ? atoi(getenv("WF_K3_NOBULK")) : 0;
+        r.no_bulk = no_bulk;
+        int grid = (int)(rows < kNumSMs ? rows : kNumSMs);
+        if (getenv("WF_K3_GRID")) grid = atoi(getenv("WF_K3_GRID"));
+        static const int cfg51 = getenv("WF_K3_ROLL_51") != nullptr;     // tuning switch: 5 ring slots + 1 staging tile
+        if (prof != nullptr) {
+            if (cfg51) conv3d_k3_c48_roll_kernel<true, 5, 1, true><<<grid, kRollThreads, roll_smem(5, 1), st>>>(xmap, r);
+            else conv3d_k3_c48_roll_kernel<true, 4, 2, true><<<grid, kRollThreads, roll_smem(4, 2), st>>>(xmap, r);
+        } else if (dtype == WF_F16) {
+            if (cfg51) conv3d_k3_c48_roll_kernel<true, 5, 1><<<grid, kRollThreads, roll_smem(5, 1), st>>>(xmap, r);
+            else conv3d_k3_c48_roll_kernel<true, 4, 2><<<grid, kRollThreads, roll_smem(4, 2), st>>>(xmap, r);
+        } else
+            conv3d_k3_c48_roll_kernel<false, 4, 2><<<grid, kRollThreads, roll_smem(4, 2), st>>>(xmap, r);
     } else {
         K3Args a;
         a.x = (const uint16_t *)x; a.wpack = (const uint16_t *)wpack; a.y = (uint16_t *)y; a.sums = sums;

@@ -91,6 +91,35 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity) {
     if (elect_one()) mbar_wait(bar, parity);
     __syncwarp();
 }
+// The same for roles with slack (producers waiting for a free slot, epilogues waiting for a result): the polling lane sleeps
+// between tries.  128 threads spinning on try_wait compete with the tensor core's operand fetch for the shared-memory pipe; with
+// every thread of the four epilogue warps polling, a few CTAs per launch of the rolling-row convolution fell into a slow mode
+// (2.8x the clocks of their neighbours, MMAs completing every ~200 clk) and set the kernel's duration.
+__device__ __forceinline__ void mbar_wait_warp_relaxed(uint64_t *bar, uint32_t parity) {
+    if (elect_one()) {
+        const uint32_t addr = smem_u32(bar);
+        uint32_t done, polls = 0;
+        unsigned long long t0 = 0;
+        for (;;) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(addr), "r"(parity)
+                : "memory");
+            if (done) break;
+            __nanosleep(64);
+            if ((++polls & 0x3ffu) == 0) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 4000000000ull) __trap();
+            }
+        }
+    }
+    __syncwarp();
+}
 __device__ __forceinline__ uint32_t smem_desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16); }
 __device__ __forceinline__ uint32_t smem_desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }   // version 1, no swizzle
 __device__ __forceinline__ void mma_ss_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
