@@ -1,8 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 120 ./scripts/_build/mma_probe > gpurun_out/mma_probe.log 2>&1; echo "probe rc $?"
-grep -E "^lean|grid 148" gpurun_out/mma_probe.log | tail -50
-for b in 2 3 6 9 18; do
+for b in 2 3 6 9; do
   (timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-extras --no-kernel-rooflines --sw-batch $b > gpurun_out/bench_swb$b.log 2> gpurun_out/bench_swb$b.err; echo "exit $?" >> gpurun_out/bench_swb$b.log)
   python - <<PY
 import json

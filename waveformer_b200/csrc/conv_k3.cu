@@ -20,7 +20,6 @@
 //   * Accumulators: 4 output rows x 48 columns, double buffered in TMEM (2 x 192 columns), so the epilogue of a block
 //     (TMEM -> bf16 -> staging -> coalesced stores + per-channel sum / sum of squares) overlaps the MMAs of the next one.
 // Warp roles (288 threads): warps 0-3 loaders (+ optional input normalisation), warp 4 MMA issuer, warps 5-8 epilogue.
-#include <cstdlib>
 #include <type_traits>
 
 #include <cuda.h>
@@ -388,7 +387,6 @@ struct K3RollArgs {
     double *sums;
     int64_t ys, as_;
     int B, D, H;
-    int no_bulk;                // tuning switch: copy the staged row out with the threads instead of one bulk store
     long long *prof;
 };
 
@@ -458,9 +456,7 @@ __global__ void __launch_bounds__(kRollThreads, 1) conv3d_k3_c48_roll_kernel(con
                 for (int dz = -1; dz <= 1; ++dz) {
                     const bool inside = (unsigned)(z + dz) < (unsigned)a.D && (unsigned)yy < (unsigned)a.H;
                     if (!first_pass) K3_TIMED(0, mbar_wait_warp_relaxed(&bar_empty[slot], ph));   // the MMAs that read this slot are done
-                    if ((a.no_bulk & 2) && !first_pass) {                  // experiment: no TMA traffic after the first pass over the ring
-                        if (elect_one()) mbar_arrive_k3(&bar_full[slot]);
-                    } else if (elect_one()) {
+                    if (elect_one()) {
                         mbar_expect_tx(&bar_full[slot], kRollImgBytes);
                         tma_load_row(sRing + slot * kRollImg, &xmap, inside ? (int)((p + dz) * a.H + yy) : -1, &bar_full[slot]);
                     }
@@ -494,21 +490,18 @@ __global__ void __launch_bounds__(kRollThreads, 1) conv3d_k3_c48_roll_kernel(con
         int ready_m = 0, ready_rows = 0; // counter of the next row whose slot must be confirmed free: mod kRollSlots / absolute
         uint32_t ready_ph = 0;
         int c0 = 0;                      // output-row counter (rows per CTA fit 31 bits)
-        int trace_n = 0;                 // PROF + tuning bit 8: clock at every y step -> clocks[148 * 24 + cta * 512 + step]
         for (int64_t r = r0; r < r1;) {
             const int64_t p = r / a.H;
             const int ya = (int)(r - p * a.H);
             const int n = (int)min((int64_t)(a.H - ya), r1 - r);
             const int yb = ya + n - 1;
             for (int yy = ya - 1; yy <= yb + 1; ++yy) {
-                if constexpr (PROF)
-                    if ((a.no_bulk & 8) && lane == 0 && trace_n < 512) a.prof[148 * 24 + blockIdx.x * 512 + trace_n++] = clock64() - p_t0;
                 // output rows fed by the input rows at yy: lo .. hi; row hi sits in the LOWEST slot (slots descend with the row
                 // counter so that ascending TMEM columns meet the weight tile's ascending dy order)
                 const int lo = max(yy - 1, ya), hi = min(yy + 1, yb);
                 const int chi = c0 + (hi - ya);
                 while (ready_rows <= chi) {
-                    K3_TIMED(0, mbar_wait_warp(&bar_row_empty[kRollSlots - 1 - ready_m], ready_ph));
+                    K3_TIMED(0, mbar_wait_lean(&bar_row_empty[kRollSlots - 1 - ready_m], ready_ph));
                     ++ready_rows;
                     if (++ready_m == kRollSlots) { ready_m = 0; ready_ph ^= 1; }
                 }
@@ -520,7 +513,7 @@ __global__ void __launch_bounds__(kRollThreads, 1) conv3d_k3_c48_roll_kernel(con
                 const uint32_t wrow = (uint32_t)((yy - hi + 1) * kK3C);    // first weight row: dy of row hi = yy - hi
 #pragma unroll 1
                 for (int dz = 0; dz < 3; ++dz) {
-                    K3_TIMED(1, mbar_wait_warp(&bar_full[ring_i], ring_ph));     // TMA data: the barrier's acquire is all it needs
+                    K3_TIMED(1, mbar_wait_lean(&bar_full[ring_i], ring_ph));     // TMA data: the barrier's acquire is all it needs
                     const uint32_t a_lo = a_lo0 + (uint32_t)(ring_i * (kRollImg / 16));
                     const uint32_t w_lo = w_lo0 + (uint32_t)(dz * 9 * (kK3WTile3 / 16)) + wrow;
                     K3_TIMED(2, {
@@ -562,7 +555,7 @@ __global__ void __launch_bounds__(kRollThreads, 1) conv3d_k3_c48_roll_kernel(con
         const int ew = warp - 2;                            // 0..3
         const bool leader = warp == 2 && lane == 0;         // issues the bulk stores
         const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-        const bool dense = a.ys == kK3C && !(a.no_bulk & 1);
+        const bool dense = a.ys == kK3C;
         float st_s[kK3C], st_q[kK3C];                       // running sum / sum of squares of this thread's voxel column, per channel
 #pragma unroll
         for (int i = 0; i < kK3C; ++i) st_s[i] = st_q[i] = 0.f;
@@ -663,8 +656,7 @@ __global__ void __launch_bounds__(kRollThreads, 1) conv3d_k3_c48_roll_kernel(con
                     }
                 });
                 K3_TIMED(5, {
-                    if (a.no_bulk & 4) {                                    // experiment: the result is not stored
-                    } else if (dense) {
+                    if (dense) {
                         fence_proxy_async();                                // my staging writes -> visible to the bulk-copy engine
                         asm volatile("bar.sync 2, 128;" ::: "memory");
                         if (leader) {
@@ -737,8 +729,6 @@ static int k3_launch(const void *x, int dtype, const void *wpack, const void *ad
         WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_k3_c48_roll_kernel<false, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, roll_smem(4, 2)));
         WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_k3_c48_roll_kernel<true, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, roll_smem(4, 2)));
         WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_k3_c48_roll_kernel<true, 4, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, roll_smem(4, 2)));
-        WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_k3_c48_roll_kernel<true, 5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, roll_smem(5, 1)));
-        WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_k3_c48_roll_kernel<true, 5, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, roll_smem(5, 1)));
     }
     WF_CUDA_CHECK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)B * kK3C, st));
     if (in_mean_rstd == nullptr) {
@@ -758,18 +748,13 @@ static int k3_launch(const void *x, int dtype, const void *wpack, const void *ad
         K3RollArgs r;
         r.wpack = (const uint16_t *)wpack; r.y = (uint16_t *)y; r.addend = (const uint16_t *)addend;
         r.sums = sums; r.ys = y_vox_stride; r.as_ = add_vox_stride; r.B = B; r.D = D; r.H = H; r.prof = prof;
-        static const int no_bulk = getenv("WF_K3_NOBULK") ? atoi(getenv("WF_K3_NOBULK")) : 0;
-        r.no_bulk = no_bulk;
-        int grid = (int)(rows < kNumSMs ? rows : kNumSMs);
-        if (getenv("WF_K3_GRID")) grid = atoi(getenv("WF_K3_GRID"));
-        static const int cfg51 = getenv("WF_K3_ROLL_51") != nullptr;     // tuning switch: 5 ring slots + 1 staging tile
-        if (prof != nullptr) {
-            if (cfg51) conv3d_k3_c48_roll_kernel<true, 5, 1, true><<<grid, kRollThreads, roll_smem(5, 1), st>>>(xmap, r);
-            else conv3d_k3_c48_roll_kernel<true, 4, 2, true><<<grid, kRollThreads, roll_smem(4, 2), st>>>(xmap, r);
-        } else if (dtype == WF_F16) {
-            if (cfg51) conv3d_k3_c48_roll_kernel<true, 5, 1><<<grid, kRollThreads, roll_smem(5, 1), st>>>(xmap, r);
-            else conv3d_k3_c48_roll_kernel<true, 4, 2><<<grid, kRollThreads, roll_smem(4, 2), st>>>(xmap, r);
-        } else
+        const int grid = (int)(rows < kNumSMs ? rows : kNumSMs);
+        // 4 ring slots + 2 staging tiles; 5 + 1 (the other split of the 227 KB) measured the same 0.47 ms
+        if (prof != nullptr)
+            conv3d_k3_c48_roll_kernel<true, 4, 2, true><<<grid, kRollThreads, roll_smem(4, 2), st>>>(xmap, r);
+        else if (dtype == WF_F16)
+            conv3d_k3_c48_roll_kernel<true, 4, 2><<<grid, kRollThreads, roll_smem(4, 2), st>>>(xmap, r);
+        else
             conv3d_k3_c48_roll_kernel<false, 4, 2><<<grid, kRollThreads, roll_smem(4, 2), st>>>(xmap, r);
     } else {
         K3Args a;

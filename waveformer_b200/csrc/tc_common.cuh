@@ -91,6 +91,20 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity) {
     if (elect_one()) mbar_wait(bar, parity);
     __syncwarp();
 }
+// Issuer flavour: one try_wait by every lane (no election, no loop) when the barrier has usually completed already; the polling
+// path only when it has not.  The MMA queue is shallow, so every instruction the issuing warp spends between two MMAs is
+// tensor-pipe idle time.
+__device__ __forceinline__ void mbar_wait_lean(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (__any_sync(0xffffffffu, done == 0)) mbar_wait_warp(bar, parity);
+}
 // The same for roles with slack (producers waiting for a free slot, epilogues waiting for a result): the polling lane sleeps
 // between tries.  128 threads spinning on try_wait compete with the tensor core's operand fetch for the shared-memory pipe; with
 // every thread of the four epilogue warps polling, a few CTAs per launch of the rolling-row convolution fell into a slow mode

@@ -137,10 +137,18 @@ class UnetResBlock(nn.Module):
                                          out=out_buf, stats=s2)
         if use_fused(inp):
             # InstanceNorm + LeakyReLU, and InstanceNorm (+ InstanceNorm'd shortcut) + add + LeakyReLU: one kernel each
-            c1 = self.conv1(inp)
-            if lo is not None:
-                c1 = c1 + self.conv1(lo)       # conv is linear: conv(hi) + conv(lo) = conv of the unrounded input
-            out, s2 = self._conv2_after_norm(c1, None)
+            k1, s1 = self.conv1.conv, None
+            if (lo is None and inp.dtype in ops.HALF_TYPES and k1.weight.dtype == inp.dtype and k1.in_channels == 96
+                    and k1.out_channels == 48 and k1.kernel_size == (3, 3, 3) and k1.stride == (1, 1, 1) and k1.bias is None
+                    and inp.shape[-1] == 128 and inp.stride(1) == 1):
+                # decoder1's first convolution on the [upsampled | skip] concatenation buffer: two passes of the rolling-row
+                # tensor-core kernel (48 input channels each) that also deliver norm1's statistics
+                c1, s1 = ops.conv3d_k3_c96_c48(inp, k1.weight, eps=self.norm1.eps)
+            else:
+                c1 = self.conv1(inp)
+                if lo is not None:
+                    c1 = c1 + self.conv1(lo)       # conv is linear: conv(hi) + conv(lo) = conv of the unrounded input
+            out, s2 = self._conv2_after_norm(c1, s1)
             if self.downsample:
                 c3 = self.conv3.conv
                 if c3.kernel_size == (1, 1, 1) and c3.stride == (1, 1, 1) and inp.stride(1) == 1:
