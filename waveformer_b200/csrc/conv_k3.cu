@@ -709,6 +709,22 @@ __global__ void k3_finalize_kernel(const double *__restrict__ sums, float *__res
 
 using namespace wf;
 
+// cuTensorMapEncodeTiled is a DRIVER entry point: it is looked up through the runtime at first use, so the library carries no
+// link-time dependency on libcuda.so.1 and still loads (for the symbol check) on a machine without a driver.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
 static int k3_launch(const void *x, int dtype, const void *wpack, const void *addend, void *y, double *sums, float *mean_rstd,
                      const float *in_mean_rstd, float slope, float eps, int B, int D, int H, int W,
                      int64_t x_vox_stride, int64_t add_vox_stride, int64_t y_vox_stride, long long *prof, void *stream) {
@@ -741,9 +757,10 @@ static int k3_launch(const void *x, int dtype, const void *wpack, const void *ad
         const cuuint64_t gstr[2] = {(cuuint64_t)x_vox_stride * 2, (cuuint64_t)x_vox_stride * 2 * 128};
         const cuuint32_t box[3] = {64, 130, 1};
         const cuuint32_t estr[3] = {1, 1, 1};
-        if (cuTensorMapEncodeTiled(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(x), gdim, gstr, box, estr,
-                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        const EncodeTiledFn encode = encode_tiled_fn();
+        if (encode == nullptr ||
+            encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return WF_ERR_CUDA;
         K3RollArgs r;
         r.wpack = (const uint16_t *)wpack; r.y = (uint16_t *)y; r.addend = (const uint16_t *)addend;
