@@ -39,6 +39,17 @@ elif args.case == "k3":      # encoder1 / decoder1 conv2: 48 -> 48 at 2 x 128^3,
     w96 = (rn(48, 96, 3, 3, 3) / 50).half()
     fns["conv3d_k3_c96_c48 (two passes + stats)"] = lambda: ops.conv3d_k3_c96_c48(x96, w96)
     fns["cudnn conv3d 96->48 (library, for comparison)"] = lambda: torch.nn.functional.conv3d(x96, w96, padding=1)
+elif args.case == "instnorm":   # the InstanceNorm passes of the 128^3 residual blocks (2 windows, fp16)
+    x = rn(2, 128, 128, 128, 48).half().permute(0, 4, 1, 2, 3)
+    r = rn(2, 128, 128, 128, 48).half().permute(0, 4, 1, 2, 3)
+    st, rst = ops.instance_norm_stats(x), ops.instance_norm_stats(r)
+    x96 = rn(2, 64, 64, 64, 96).half().permute(0, 4, 1, 2, 3)
+    st96 = ops.instance_norm_stats(x96)
+    fns = {"instance_norm_stats 2x48x128^3 (403 MB read)": lambda: ops.instance_norm_stats(x),
+           "instance_norm_act lrelu 2x48x128^3 (403 MB in + 403 MB out)": lambda: ops.instance_norm_act(x, "leakyrelu", 0.01, stats=st),
+           "instance_norm_act + IN(res) + lrelu 2x48x128^3 (805 MB in + 403 MB out)":
+               lambda: ops.instance_norm_act(x, "leakyrelu", 0.01, res=r, res_norm=True, stats=st, res_stats=rst),
+           "instance_norm_act lrelu 2x96x64^3 (101 MB in + 101 MB out)": lambda: ops.instance_norm_act(x96, "leakyrelu", 0.01, stats=st96)}
 elif args.case == "dwconv":  # CCF_FFN stage 1: 2 x 64^3 x 192
     x = rn(2, 64, 64, 64, 192).bfloat16()
     w27, b = rn(27, 192) * 0.2, rn(192) * 0.05
