@@ -1,6 +1,16 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 scripts/mgpu_check.py > gpurun_out/mgpu_check.log 2>&1; echo "mgpu_check exit $?" >> gpurun_out/mgpu_check.log
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/bench_n2.log 2>&1; echo "bench n2 exit $?" >> gpurun_out/bench_n2.log
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --impl reference --steps 1 --warmup 1 > gpurun_out/bench_ref_n2.log 2>&1; echo "bench ref exit $?" >> gpurun_out/bench_ref_n2.log
-grep -v Warning gpurun_out/mgpu_check.log | tail -5; tail -c 900 gpurun_out/bench_n2.log; tail -c 600 gpurun_out/bench_ref_n2.log
+(timeout 600 python -m pytest tests -m gpu -q -x -k "nccl or two_gpu or 2gpu or sharded" > gpurun_out/pytest_2gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_2gpu.log)
+tail -3 gpurun_out/pytest_2gpu.log | cut -c1-200
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/bench_n2.log 2> gpurun_out/bench_n2.err; echo "bench n2 exit $?" >> gpurun_out/bench_n2.log
+tail -3 gpurun_out/bench_n2.err | cut -c1-300
+python - <<'PY'
+import json
+for l in open('gpurun_out/bench_n2.log'):
+    if l.startswith('{'):
+        d=json.loads(l)
+        for k in ('value','ms_per_step','n_gpus','scaling','e2e','strong','clocks'):
+            print(k, d.get(k))
+        print(d['config']['workload'])
+    else: print(l.strip()[:300])
+PY

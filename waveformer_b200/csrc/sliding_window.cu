@@ -69,6 +69,78 @@ __global__ void __launch_bounds__(256) sw_accumulate_kernel(const T *__restrict_
     atomicAdd(acc + ((((int64_t)b * K + c) * D + pz) * H + py) * (int64_t)W + px, v);
 }
 
+// Channels-last fast paths: one thread per window VOXEL (grid.y = window), 32-bit index arithmetic, the C channel planes read /
+// updated as C coalesced accesses (consecutive threads = consecutive x) and the voxel's C values moved as one packet.  The
+// per-element kernels above (one thread per value, 64-bit divisions, a warp touching every channel plane in each load) ran at
+// 1.2 TB/s: 0.33 ms per 6-window gather where the traffic is worth 0.07 ms.
+template <typename T, int C>
+__global__ void __launch_bounds__(256) sw_gather_voxel_kernel(const float *__restrict__ vol, T *__restrict__ win,
+                                                              const int32_t *__restrict__ starts, int D, int H, int W, int r0, int r1,
+                                                              int r2, int flip) {
+    const uint32_t nvox = (uint32_t)r0 * r1 * r2;
+    const uint32_t v = blockIdx.x * 256u + threadIdx.x;
+    if (v >= nvox) return;
+    const int n = blockIdx.y;
+    const uint32_t x = v % (uint32_t)r2, q = v / (uint32_t)r2, y = q % (uint32_t)r1, z = q / (uint32_t)r1;
+    const int b = starts[4 * n];
+    int pz = starts[4 * n + 1] + (int)z, py = starts[4 * n + 2] + (int)y, px = starts[4 * n + 3] + (int)x;
+    if (flip & 1) pz = D - 1 - pz;
+    if (flip & 2) py = H - 1 - py;
+    if (flip & 4) px = W - 1 - px;
+    const int64_t plane = (int64_t)D * H * W;
+    const float *src = vol + (int64_t)b * C * plane + ((int64_t)pz * H + py) * W + px;
+    float f[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) f[c] = __ldg(src + c * plane);
+    T *dst = win + ((int64_t)n * nvox + v) * C;
+    if constexpr (C == 4 && sizeof(T) == 4) {
+        *reinterpret_cast<float4 *>(dst) = make_float4(f[0], f[1], f[2], f[3]);
+    } else if constexpr (C == 4 && sizeof(T) == 2) {
+        T h[4] = {from_f32<T>(f[0]), from_f32<T>(f[1]), from_f32<T>(f[2]), from_f32<T>(f[3])};
+        *reinterpret_cast<uint2 *>(dst) = *reinterpret_cast<const uint2 *>(h);
+    } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) dst[c] = from_f32<T>(f[c]);
+    }
+}
+
+template <typename T, int K>
+__global__ void __launch_bounds__(256) sw_accumulate_voxel_kernel(const T *__restrict__ seg, float *__restrict__ acc,
+                                                                  const int32_t *__restrict__ starts, const float *__restrict__ gz,
+                                                                  const float *__restrict__ gy, const float *__restrict__ gx,
+                                                                  float floor_w, int D, int H, int W, int r0, int r1, int r2, int flip) {
+    const uint32_t nvox = (uint32_t)r0 * r1 * r2;
+    const uint32_t v = blockIdx.x * 256u + threadIdx.x;
+    if (v >= nvox) return;
+    const int n = blockIdx.y;
+    const uint32_t x = v % (uint32_t)r2, q = v / (uint32_t)r2, y = q % (uint32_t)r1, z = q / (uint32_t)r1;
+    const int b = starts[4 * n];
+    // importance weight exactly as compute_importance_map builds it: ((gz*gy)*gx) in fp32, clamped from below
+    const float wgt = fmaxf((gz[z] * gy[y]) * gx[x], floor_w);
+    const T *src = seg + ((int64_t)n * nvox + v) * K;
+    float f[K];
+    if constexpr (K == 4 && sizeof(T) == 4) {
+        const float4 t = *reinterpret_cast<const float4 *>(src);
+        f[0] = t.x; f[1] = t.y; f[2] = t.z; f[3] = t.w;
+    } else if constexpr (K == 4 && sizeof(T) == 2) {
+        const uint2 t = *reinterpret_cast<const uint2 *>(src);
+        const T *h = reinterpret_cast<const T *>(&t);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) f[c] = to_f32(h[c]);
+    } else {
+#pragma unroll
+        for (int c = 0; c < K; ++c) f[c] = to_f32(src[c]);
+    }
+    int pz = starts[4 * n + 1] + (int)z, py = starts[4 * n + 2] + (int)y, px = starts[4 * n + 3] + (int)x;
+    if (flip & 1) pz = D - 1 - pz;
+    if (flip & 2) py = H - 1 - py;
+    if (flip & 4) px = W - 1 - px;
+    const int64_t plane = (int64_t)D * H * W;
+    float *dst = acc + (int64_t)b * K * plane + ((int64_t)pz * H + py) * W + px;
+#pragma unroll
+    for (int c = 0; c < K; ++c) atomicAdd(dst + c * plane, f[c] * wgt);   // same product, same rounding as the per-element kernel
+}
+
 // one thread per voxel: count = sum of window weights covering it; acc[:, k] /= count; optional argmax
 __global__ void __launch_bounds__(256) sw_finalize_kernel(float *__restrict__ acc, uint8_t *__restrict__ labels,
                                                           const int32_t *__restrict__ all_starts, int nall,
@@ -127,6 +199,16 @@ extern "C" int wf_sw_gather(const float *vol, void *win, const int32_t *starts, 
     if (nwin <= 0 || C <= 0 || r0 <= 0 || r1 <= 0 || r2 <= 0 || r0 > D || r1 > H || r2 > W) return WF_ERR_BAD_SHAPE;
     const int64_t total = (int64_t)nwin * C * r0 * r1 * r2;
     cudaStream_t st = (cudaStream_t)stream;
+    if (channels_last && C == 4 && nwin <= 65535 && (int64_t)r0 * r1 * r2 < 0x7fffffffLL &&
+        (reinterpret_cast<uintptr_t>(win) & 15u) == 0) {
+        const dim3 grid((unsigned)(((int64_t)r0 * r1 * r2 + 255) / 256), (unsigned)nwin);
+        if (dtype == WF_F32) sw_gather_voxel_kernel<float, 4><<<grid, 256, 0, st>>>(vol, (float *)win, starts, D, H, W, r0, r1, r2, flip);
+        else if (dtype == WF_BF16) sw_gather_voxel_kernel<__nv_bfloat16, 4><<<grid, 256, 0, st>>>(vol, (__nv_bfloat16 *)win, starts, D, H, W, r0, r1, r2, flip);
+        else if (dtype == WF_F16) sw_gather_voxel_kernel<__half, 4><<<grid, 256, 0, st>>>(vol, (__half *)win, starts, D, H, W, r0, r1, r2, flip);
+        else return WF_ERR_BAD_DTYPE;
+        WF_LAUNCH_CHECK();
+        return WF_OK;
+    }
 #define WF_G(T_, CL_) sw_gather_kernel<T_, CL_><<<blocks_for(total), 256, 0, st>>>(vol, (T_ *)win, starts, total, C, D, H, W, r0, r1, r2, flip)
     if (dtype == WF_F32) { if (channels_last) WF_G(float, true); else WF_G(float, false); }
     else if (dtype == WF_BF16) { if (channels_last) WF_G(__nv_bfloat16, true); else WF_G(__nv_bfloat16, false); }
@@ -145,6 +227,16 @@ extern "C" int wf_sw_accumulate(const void *seg, float *acc, const int32_t *star
     if (nwin <= 0 || K <= 0 || r0 <= 0 || r1 <= 0 || r2 <= 0 || r0 > D || r1 > H || r2 > W) return WF_ERR_BAD_SHAPE;
     const int64_t total = (int64_t)nwin * K * r0 * r1 * r2;
     cudaStream_t st = (cudaStream_t)stream;
+    if (channels_last && K == 4 && nwin <= 65535 && (int64_t)r0 * r1 * r2 < 0x7fffffffLL &&
+        (reinterpret_cast<uintptr_t>(seg) & 15u) == 0) {
+        const dim3 grid((unsigned)(((int64_t)r0 * r1 * r2 + 255) / 256), (unsigned)nwin);
+        if (dtype == WF_F32) sw_accumulate_voxel_kernel<float, 4><<<grid, 256, 0, st>>>((const float *)seg, acc, starts, gz, gy, gx, floor_w, D, H, W, r0, r1, r2, flip);
+        else if (dtype == WF_BF16) sw_accumulate_voxel_kernel<__nv_bfloat16, 4><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)seg, acc, starts, gz, gy, gx, floor_w, D, H, W, r0, r1, r2, flip);
+        else if (dtype == WF_F16) sw_accumulate_voxel_kernel<__half, 4><<<grid, 256, 0, st>>>((const __half *)seg, acc, starts, gz, gy, gx, floor_w, D, H, W, r0, r1, r2, flip);
+        else return WF_ERR_BAD_DTYPE;
+        WF_LAUNCH_CHECK();
+        return WF_OK;
+    }
 #define WF_A(T_, CL_) sw_accumulate_kernel<T_, CL_><<<blocks_for(total), 256, 0, st>>>((const T_ *)seg, acc, starts, gz, gy, gx, floor_w, total, K, D, H, W, r0, r1, r2, flip)
     if (dtype == WF_F32) { if (channels_last) WF_A(float, true); else WF_A(float, false); }
     else if (dtype == WF_BF16) { if (channels_last) WF_A(__nv_bfloat16, true); else WF_A(__nv_bfloat16, false); }
