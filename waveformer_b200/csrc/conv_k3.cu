@@ -374,10 +374,15 @@ __global__ void __launch_bounds__(288, 1) conv3d_k3_c48_kernel(K3Args a) {
 // `addend` (optional): a second 16-bit tensor laid out like y that is added to the accumulators before rounding - the second
 // pass of a convolution whose input channels are split over two launches (decoder1.conv1: 96 = 48 + 48 input channels).
 constexpr int kRollSlots = 10;                                 // accumulator ring: output rows in flight
-constexpr int kRollImgBytes = 130 * 128;                       // what one TMA box delivers
-constexpr int kRollImg = 17 * 1024;                            // slot pitch: 1024-byte aligned (swizzle atoms are 8 rows x 128 bytes)
+// A staged input row = two TMA boxes: channels 0..31 as a 64-byte-swizzled image [130 voxels][64 B] (k-steps 0 and 1) and channels
+// 32..47 as a 32-byte-swizzled image [130][32 B] (k-step 2).  One 128-byte-swizzled image [130][128 B] with channels 48..63 zero
+// filled works the same (first version) but a quarter of it is padding: 4 ring slots instead of 6 beside the 124 KB of weights.
+constexpr int kRollImgA = 130 * 64, kRollImgB = 130 * 32;      // bytes the two boxes deliver
+constexpr int kRollImgBytes = kRollImgA + kRollImgB;
+constexpr int kRollOffB = 17 * 512;                            // 8704: the 32-channel image padded to whole 8-row swizzle atoms (512 B)
+constexpr int kRollImg = 26 * 512;                             // slot pitch 13312: keeps both images aligned to their atoms (512 / 256 B)
 constexpr int kRollStage = 128 * kK3C * 2;                     // one dense output row: 12288 bytes
-constexpr int roll_smem(int ring, int nstage) { return ring * kRollImg + kK3WBytes + nstage * kRollStage; }   // 4 slots, 2 tiles: 218624; 5, 1: 223744
+constexpr int roll_smem(int ring, int nstage) { return ring * kRollImg + kK3WBytes + nstage * kRollStage; }   // 6 slots, 2 tiles: 228864
 constexpr int kRollThreads = 192;                              // warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue
 
 struct K3RollArgs {
@@ -390,16 +395,17 @@ struct K3RollArgs {
     long long *prof;
 };
 
-__device__ __forceinline__ void tma_load_row(void *dst, const CUtensorMap *map, int row, uint64_t *bar) {
+__device__ __forceinline__ void tma_load_row(void *dst, const CUtensorMap *map, int c0, int row, uint64_t *bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
                      smem_u32(dst)),
-                 "l"(map), "r"(0), "r"(-1), "r"(row), "r"(smem_u32(bar))
+                 "l"(map), "r"(c0), "r"(-1), "r"(row), "r"(smem_u32(bar))
                  : "memory");
 }
 
 // kRollRing staged input rows, kRollNStage output staging tiles
 template <bool F16, int kRollRing, int kRollNStage, bool PROF = false>
-__global__ void __launch_bounds__(kRollThreads, 1) conv3d_k3_c48_roll_kernel(const __grid_constant__ CUtensorMap xmap, K3RollArgs a) {
+__global__ void __launch_bounds__(kRollThreads, 1) conv3d_k3_c48_roll_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap xmap_hi,
+                                                                             K3RollArgs a) {
     unsigned long long gt_entry = 0;
     if constexpr (PROF) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_entry));
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -458,7 +464,9 @@ __global__ void __launch_bounds__(kRollThreads, 1) conv3d_k3_c48_roll_kernel(con
                     if (!first_pass) K3_TIMED(0, mbar_wait_warp_relaxed(&bar_empty[slot], ph));   // the MMAs that read this slot are done
                     if (elect_one()) {
                         mbar_expect_tx(&bar_full[slot], kRollImgBytes);
-                        tma_load_row(sRing + slot * kRollImg, &xmap, inside ? (int)((p + dz) * a.H + yy) : -1, &bar_full[slot]);
+                        const int row = inside ? (int)((p + dz) * a.H + yy) : -1;
+                        tma_load_row(sRing + slot * kRollImg, &xmap, 0, row, &bar_full[slot]);
+                        tma_load_row(sRing + slot * kRollImg + kRollOffB, &xmap_hi, 32, row, &bar_full[slot]);
                     }
                     __syncwarp();
                     if (++slot == kRollRing) { slot = 0; ph ^= 1; first_pass = false; }
@@ -479,9 +487,10 @@ __global__ void __launch_bounds__(kRollThreads, 1) conv3d_k3_c48_roll_kernel(con
         // instructions - while scripts/mma_probe.cu runs the same stream at ~90 clk per MMA.  The MMA queue is shallow: whatever the
         // issuing warp does between two MMAs (barrier polls, address arithmetic) is exposed as tensor-pipe idle time.
         const uint32_t idesc0 = instr_desc_h16<F16>(128, 0, false);                  // N field (bits 17..22, N >> 3) added per call
-        // A: 128-byte swizzle, K-major: 8-row groups 1024 bytes apart (the leading-dimension field is unused); layout type 2 sits
-        // in bits 61..63 of the descriptor.  Weights: no swizzle, tile (dz, dx, ks) = [2 chunks][144 = dy x out][8]
-        const uint32_t a_lo0 = smem_desc_lo(smem_u32(sRing), 16), a_hi = smem_desc_hi(1024) | (2u << 29);
+        // A, k-steps 0 / 1: 64-byte swizzle, K-major, 8-row groups 512 bytes apart (layout type 4 in bits 61..63; the leading-dimension
+        // field is unused); k-step 2: 32-byte swizzle, groups 256 bytes apart (type 6).  Tap dx = start advanced by dx rows, k-step 1 = by
+        // 32 bytes inside the row.  Weights: no swizzle, tile (dz, dx, ks) = [2 chunks][144 = dy x out][8]
+        const uint32_t a_lo0 = smem_desc_lo(smem_u32(sRing), 16), a_hi = smem_desc_hi(512) | (4u << 29), a_hi2 = smem_desc_hi(256) | (6u << 29);
         const uint32_t w_lo0 = smem_desc_lo(smem_u32(sW), 3 * kK3C * 16), w_hi = smem_desc_hi(128);
         // ring positions are kept as (index, phase) pairs advanced by hand: no 64-bit division in the issue loop
         int ring_i = 0;                  // staged-row slot to consume next
@@ -490,6 +499,7 @@ __global__ void __launch_bounds__(kRollThreads, 1) conv3d_k3_c48_roll_kernel(con
         int ready_m = 0, ready_rows = 0; // counter of the next row whose slot must be confirmed free: mod kRollSlots / absolute
         uint32_t ready_ph = 0;
         int c0 = 0;                      // output-row counter (rows per CTA fit 31 bits)
+        uint32_t peek = r0 < r1 ? mbar_peek(&bar_full[0], 0) : 1u;   // try_wait result for the slot consumed NEXT (see mbar_peek)
         for (int64_t r = r0; r < r1;) {
             const int64_t p = r / a.H;
             const int ya = (int)(r - p * a.H);
@@ -513,8 +523,11 @@ __global__ void __launch_bounds__(kRollThreads, 1) conv3d_k3_c48_roll_kernel(con
                 const uint32_t wrow = (uint32_t)((yy - hi + 1) * kK3C);    // first weight row: dy of row hi = yy - hi
 #pragma unroll 1
                 for (int dz = 0; dz < 3; ++dz) {
-                    K3_TIMED(1, mbar_wait_lean(&bar_full[ring_i], ring_ph));     // TMA data: the barrier's acquire is all it needs
-                    const uint32_t a_lo = a_lo0 + (uint32_t)(ring_i * (kRollImg / 16));
+                    K3_TIMED(1, mbar_wait_peeked(peek, &bar_full[ring_i], ring_ph));     // TMA data: the barrier's acquire is all it needs
+                    const int cur_i = ring_i;
+                    if (++ring_i == kRollRing) { ring_i = 0; ring_ph ^= 1; }
+                    peek = mbar_peek(&bar_full[ring_i], ring_ph);                // the next slot's poll runs under this group's MMAs
+                    const uint32_t a_lo = a_lo0 + (uint32_t)(cur_i * (kRollImg / 16));
                     const uint32_t w_lo = w_lo0 + (uint32_t)(dz * 9 * (kK3WTile3 / 16)) + wrow;
                     K3_TIMED(2, {
 #pragma unroll 1
@@ -527,11 +540,11 @@ __global__ void __launch_bounds__(kRollThreads, 1) conv3d_k3_c48_roll_kernel(con
                             for (int dx = 0; dx < 3; ++dx)
 #pragma unroll
                                 for (int ks = 0; ks < 3; ++ks)
-                                    mma_ss_w(acc, a_lo + (uint32_t)(dx * 8 + ks * 2), a_hi, wl + (uint32_t)((dx * 3 + ks) * (kK3WTile3 / 16)), w_hi, idesc, 1u);
+                                    mma_ss_w(acc, a_lo + (uint32_t)(ks < 2 ? dx * 4 + ks * 2 : kRollOffB / 16 + dx * 2), ks < 2 ? a_hi : a_hi2,
+                                             wl + (uint32_t)((dx * 3 + ks) * (kK3WTile3 / 16)), w_hi, idesc, 1u);
                         }
-                        mma_commit_w(&bar_empty[ring_i]);
+                        mma_commit_w(&bar_empty[cur_i]);
                     });
-                    if (++ring_i == kRollRing) { ring_i = 0; ring_ph ^= 1; }
                 }
                 // row yy - 1 has received its three input rows
                 if (yy - 1 >= ya) mma_commit_w(&bar_row_full[kRollSlots - 1 - (c0m + (yy - 1 - ya)) % kRollSlots]);
@@ -742,9 +755,9 @@ static int k3_launch(const void *x, int dtype, const void *wpack, const void *ad
         WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_k3_c48_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kK3Smem));
         WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_k3_c48_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kK3Smem));
         WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_k3_c48_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kK3Smem));
-        WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_k3_c48_roll_kernel<false, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, roll_smem(4, 2)));
-        WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_k3_c48_roll_kernel<true, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, roll_smem(4, 2)));
-        WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_k3_c48_roll_kernel<true, 4, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, roll_smem(4, 2)));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_k3_c48_roll_kernel<false, 6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, roll_smem(6, 2)));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_k3_c48_roll_kernel<true, 6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, roll_smem(6, 2)));
+        WF_CUDA_CHECK(cudaFuncSetAttribute(conv3d_k3_c48_roll_kernel<true, 6, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, roll_smem(6, 2)));
     }
     WF_CUDA_CHECK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)B * kK3C, st));
     if (in_mean_rstd == nullptr) {
@@ -752,27 +765,29 @@ static int k3_launch(const void *x, int dtype, const void *wpack, const void *ad
         // TMA tensor map [48 channels][128 x][B * D * H rows] (fp16 and bf16 are both "16-bit, no conversion" to the copy engine).
         const int64_t rows = (int64_t)B * D * H;
         if (rows > 0x7fffffff) return WF_ERR_BAD_SHAPE;
-        CUtensorMap xmap;
+        CUtensorMap xmap, xmap_hi;
         const cuuint64_t gdim[3] = {(cuuint64_t)kK3C, 128, (cuuint64_t)rows};
         const cuuint64_t gstr[2] = {(cuuint64_t)x_vox_stride * 2, (cuuint64_t)x_vox_stride * 2 * 128};
-        const cuuint32_t box[3] = {64, 130, 1};
+        const cuuint32_t box_lo[3] = {32, 130, 1}, box_hi[3] = {16, 130, 1};
         const cuuint32_t estr[3] = {1, 1, 1};
         const EncodeTiledFn encode = encode_tiled_fn();
         if (encode == nullptr ||
-            encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(x), gdim, gstr, box_lo, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS ||
+            encode(&xmap_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(x), gdim, gstr, box_hi, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return WF_ERR_CUDA;
         K3RollArgs r;
         r.wpack = (const uint16_t *)wpack; r.y = (uint16_t *)y; r.addend = (const uint16_t *)addend;
         r.sums = sums; r.ys = y_vox_stride; r.as_ = add_vox_stride; r.B = B; r.D = D; r.H = H; r.prof = prof;
         const int grid = (int)(rows < kNumSMs ? rows : kNumSMs);
-        // 4 ring slots + 2 staging tiles; 5 + 1 (the other split of the 227 KB) measured the same 0.47 ms
+        // 6 ring slots + 2 staging tiles
         if (prof != nullptr)
-            conv3d_k3_c48_roll_kernel<true, 4, 2, true><<<grid, kRollThreads, roll_smem(4, 2), st>>>(xmap, r);
+            conv3d_k3_c48_roll_kernel<true, 6, 2, true><<<grid, kRollThreads, roll_smem(6, 2), st>>>(xmap, xmap_hi, r);
         else if (dtype == WF_F16)
-            conv3d_k3_c48_roll_kernel<true, 4, 2><<<grid, kRollThreads, roll_smem(4, 2), st>>>(xmap, r);
+            conv3d_k3_c48_roll_kernel<true, 6, 2><<<grid, kRollThreads, roll_smem(6, 2), st>>>(xmap, xmap_hi, r);
         else
-            conv3d_k3_c48_roll_kernel<false, 4, 2><<<grid, kRollThreads, roll_smem(4, 2), st>>>(xmap, r);
+            conv3d_k3_c48_roll_kernel<false, 6, 2><<<grid, kRollThreads, roll_smem(6, 2), st>>>(xmap, xmap_hi, r);
     } else {
         K3Args a;
         a.x = (const uint16_t *)x; a.wpack = (const uint16_t *)wpack; a.y = (uint16_t *)y; a.sums = sums;

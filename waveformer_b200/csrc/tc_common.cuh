@@ -105,6 +105,23 @@ __device__ __forceinline__ void mbar_wait_lean(uint64_t *bar, uint32_t parity) {
         : "memory");
     if (__any_sync(0xffffffffu, done == 0)) mbar_wait_warp(bar, parity);
 }
+// Split form for software pipelining: mbar_peek issues the try_wait (every lane) and returns its raw result; mbar_wait_peeked
+// completes the wait later - a vote, and the polling path only if the barrier had not completed when peeked.  The issuer peeks at
+// the NEXT operand slot's barrier before issuing the current group of MMAs, so the poll's latency runs under queued MMAs.
+__device__ __forceinline__ uint32_t mbar_peek(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done;
+}
+__device__ __forceinline__ void mbar_wait_peeked(uint32_t peeked, uint64_t *bar, uint32_t parity) {
+    if (__any_sync(0xffffffffu, peeked == 0)) mbar_wait_warp(bar, parity);
+}
 // The same for roles with slack (producers waiting for a free slot, epilogues waiting for a result): the polling lane sleeps
 // between tries.  128 threads spinning on try_wait compete with the tensor core's operand fetch for the shared-memory pipe; with
 // every thread of the four epilogue warps polling, a few CTAs per launch of the rolling-row convolution fell into a slow mode
