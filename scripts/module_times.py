@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""CUDA-event time per sub-module of one batch-2 Waveformer forward (bf16 policy): where the step goes."""
+"""CUDA-event time per sub-module of one Waveformer forward (16-bit policy; --batch N windows, default 2): where the step goes."""
 import os
 import sys
 
@@ -14,7 +14,8 @@ if os.environ.get("WF_CUDNN_BENCHMARK"):
     torch.backends.cudnn.benchmark = True
 m = prepare_inference(Waveformer(img_size=(128,) * 3, patch_size=2, in_chans=4, out_chans=4, depths=[2] * 4,
                                  feat_size=[48, 96, 192, 384], num_heads=[3, 6, 12, 24]).eval().cuda(), torch.bfloat16)
-x = torch.randn(2, 4, 128, 128, 128, device="cuda").contiguous(memory_format=torch.channels_last_3d)
+BATCH = int(sys.argv[sys.argv.index("--batch") + 1]) if "--batch" in sys.argv else 2
+x = torch.randn(BATCH, 4, 128, 128, 128, device="cuda").contiguous(memory_format=torch.channels_last_3d)
 names = {}
 for n, mod in m.named_modules():
     depth = n.count(".")
