@@ -540,10 +540,10 @@ def main():
         dominant = dict(kernels["conv3d_k3_c48_tc"])
         dominant["kernel"] = "conv3d_k3_c48_roll_kernel on 2x48x128^3 (conv2 of encoder1 / decoder1, both passes of decoder1.conv1)"
         dominant["share_of_forward"] = "4 launches of the window forward (ncu launch list, profiles/r02_launch_summary.txt)"
-        # dram bytes per launch from `ncu --set full` (profiles/r02_ncu_k3_roll.json): 1 212 MB read + 384 MB written for 403 + 403 MB
-        # algorithmic.  The input is fetched ~3x: a CTA's run is 1.73 planes long, so the CTAs working on neighbouring planes are 93 rows
-        # out of phase and the rows they share have left the 126 MB L2 in between.  DRAM is 43 % busy: not the limiter.
-        dominant["traffic"] = 1595500000
+        # dram bytes per launch from ncu (profiles/r02_k3_roll_dram.csv): 751 MB read + 381 MB written for 403 + 403 MB algorithmic.  Each
+        # input row is needed by three planes; the CTAs walk their first plane in lockstep (neighbours share through L2), the evenly split
+        # remainder of the planes still re-reads (with one contiguous run per CTA the input was read three times: 1 212 MB).
+        dominant["traffic"] = 1132000000
     extras = {}
     if world == 1 and not args.no_extras:
         if dtype == torch.bfloat16:

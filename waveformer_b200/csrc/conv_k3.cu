@@ -417,9 +417,19 @@ __global__ void __launch_bounds__(kRollThreads, 1) conv3d_k3_c48_roll_kernel(con
     uint8_t *sStage = sW + kK3WBytes;
     const int tid = threadIdx.x, warp = (int)warp_idx_uniform(), lane = tid & 31;
     constexpr int W = 128;
-    // this CTA's run of output rows [r0, r1) in (b, z, y) order
-    const int64_t R = (int64_t)a.B * a.D * a.H;
-    const int64_t r0 = R * blockIdx.x / gridDim.x, r1 = R * (blockIdx.x + 1) / gridDim.x;
+    // This CTA's output rows, in (b, z, y) order, come in pieces: first `whole` entire planes (plane j * grid + cta for j < whole), walked
+    // by all CTAs in lockstep - neighbouring CTAs work on neighbouring planes at the same y, so the input rows they share (each row is
+    // needed by the planes z - 1, z, z + 1) are fetched from DRAM once and hit in L2 twice - then an even share of the rows of the
+    // remaining planes.  (One contiguous run of rows per CTA - 1.73 planes at BASELINE size - leaves the CTAs of neighbouring planes 93
+    // rows out of phase: ncu showed the input being read three times from DRAM.)
+    const int64_t planes = (int64_t)a.B * a.D;
+    const int64_t whole = planes / gridDim.x;
+    const int64_t rem_base = whole * gridDim.x * a.H, rem_rows = (planes - whole * gridDim.x) * a.H;
+#define ROLL_PIECES_BEGIN                                                                                                             \
+    for (int64_t piece_ = 0; piece_ <= whole; ++piece_) {                                                                              \
+        const int64_t r0 = piece_ < whole ? (piece_ * gridDim.x + blockIdx.x) * a.H : rem_base + rem_rows * blockIdx.x / gridDim.x;    \
+        const int64_t r1 = piece_ < whole ? r0 + a.H : rem_base + rem_rows * (blockIdx.x + 1) / gridDim.x;
+#define ROLL_PIECES_END }
 
     if (warp == 0) tmem_alloc(&tmem_slot, 512);
     if (tid == 0) {
@@ -449,6 +459,7 @@ __global__ void __launch_bounds__(kRollThreads, 1) conv3d_k3_c48_roll_kernel(con
         int slot = 0;
         uint32_t ph = 1;                 // parity of the "slot is free" phase to wait for; the first pass over the ring is free
         bool first_pass = true;
+        ROLL_PIECES_BEGIN
         for (int64_t r = r0; r < r1;) {
             const int64_t p = r / a.H;
             const int ya = (int)(r - p * a.H);
@@ -473,6 +484,7 @@ __global__ void __launch_bounds__(kRollThreads, 1) conv3d_k3_c48_roll_kernel(con
                 }
             r += n;
         }
+        ROLL_PIECES_END
         if constexpr (PROF)
             if (lane == 0) {
                 for (int q = 0; q < 6; ++q) a.prof[(blockIdx.x * 3 + 0) * 8 + q] = pw[q];
@@ -499,7 +511,8 @@ __global__ void __launch_bounds__(kRollThreads, 1) conv3d_k3_c48_roll_kernel(con
         int ready_m = 0, ready_rows = 0; // counter of the next row whose slot must be confirmed free: mod kRollSlots / absolute
         uint32_t ready_ph = 0;
         int c0 = 0;                      // output-row counter (rows per CTA fit 31 bits)
-        uint32_t peek = r0 < r1 ? mbar_peek(&bar_full[0], 0) : 1u;   // try_wait result for the slot consumed NEXT (see mbar_peek)
+        uint32_t peek = mbar_peek(&bar_full[0], 0);   // try_wait result for the slot consumed NEXT (see mbar_peek)
+        ROLL_PIECES_BEGIN
         for (int64_t r = r0; r < r1;) {
             const int64_t p = r / a.H;
             const int ya = (int)(r - p * a.H);
@@ -553,6 +566,7 @@ __global__ void __launch_bounds__(kRollThreads, 1) conv3d_k3_c48_roll_kernel(con
             c0m = (c0m + n) % kRollSlots;
             r += n;
         }
+        ROLL_PIECES_END
         if constexpr (PROF)
             if (lane == 0) {
                 for (int q = 0; q < 6; ++q) a.prof[(blockIdx.x * 3 + 1) * 8 + q] = pw[q];
@@ -609,6 +623,7 @@ __global__ void __launch_bounds__(kRollThreads, 1) conv3d_k3_c48_roll_kernel(con
         for (int sl = 0; sl < kRollSlots; ++sl) zero_and_release(sl);
         int cm = 0, cstage = 0;          // output-row counter mod kRollSlots / mod kRollNStage
         uint32_t cph = 0;
+        ROLL_PIECES_BEGIN
         for (int64_t r = r0; r < r1;) {
             const int64_t p = r / a.H;
             const int ya = (int)(r - p * a.H);
@@ -691,6 +706,7 @@ __global__ void __launch_bounds__(kRollThreads, 1) conv3d_k3_c48_roll_kernel(con
             }
             r += n;
         }
+        ROLL_PIECES_END
         flush();
         if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         if constexpr (PROF)
@@ -703,6 +719,8 @@ __global__ void __launch_bounds__(kRollThreads, 1) conv3d_k3_c48_roll_kernel(con
             }
     }
 #undef K3_TIMED
+#undef ROLL_PIECES_BEGIN
+#undef ROLL_PIECES_END
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 512);
