@@ -375,6 +375,155 @@ __global__ void __launch_bounds__(128) ffn_back_kernel(FfnBackArgs a) {
     if (warp == 0) tmem_dealloc(tmem_slot, TMEM_COLS);
 }
 
+// --------------------------------------------------------------------------------------- ProjectionUpsample tail ------
+// out[r, :N] = W1 . GELU(h[r, :K1]) + b1  +  W2 . u[r, :K2] + b2        (16-bit in, fp32 accumulate, 16-bit out, row pitch `os`)
+//
+// Reference: the end of ProjectionUpsample.forward (network_models/wave_helper.py:75-81): `x = self.conv3(self.act(x))` (single
+// conv, or the last conv of the double-conv Sequential after its own GELU) and `x = x + self.res_conv(input)`, where res_conv =
+// Upsample + 1^3 convolution - its upsampled operand u is shared with the main branch here.  Unfused this is a GELU pass over h
+// (read + write), two library GEMMs with dense temporaries and an add into the strided concatenation slice: ~3.4 GB per six windows
+// for learnable_up3 where h + u + out are 1.06 GB.  One persistent kernel, 256 threads: the two A images are staged with
+// coalesced cp.async (a thread copies chunks q, q + 256, ...), the GELU is applied in place to the cells a thread copied itself,
+// one converged warp issues K1 / 16 + K2 / 16 tcgen05.mma of N columns, the epilogue (thread = row) adds the biases and writes
+// the row into the destination slice while the next tile's images are already loading.
+struct PwTailArgs {
+    const uint16_t *h, *u;       // [M, K1], [M, K2] dense
+    const uint16_t *w1, *w2;     // [N, K1], [N, K2]
+    const float *b1, *b2;        // fp32 [N] or NULL
+    uint16_t *out;               // [M, N], row pitch os elements
+    int64_t M, ntiles, os;
+};
+
+template <bool F16, int K1, int K2, int N>
+__global__ void __launch_bounds__(256) pw_gelu_dual_kernel(PwTailArgs a) {
+    using T16 = typename std::conditional<F16, __half, __nv_bfloat16>::type;
+    constexpr int KCH1 = K1 / 8, KCH2 = K2 / 8;
+    constexpr uint32_t TMEM_COLS = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    uint8_t *sB1 = smem;                                     // [KCH1][N][16 B]
+    uint8_t *sB2 = sB1 + (size_t)KCH1 * N * 16;              // [KCH2][N][16 B]
+    uint8_t *sA1 = sB2 + (size_t)KCH2 * N * 16;              // [KCH1][128][16 B]
+    uint8_t *sA2 = sA1 + (size_t)KCH1 * 2048;                // [KCH2][128][16 B]
+    float *sBias = reinterpret_cast<float *>(sA2 + (size_t)KCH2 * 2048);   // b1 + b2, N floats
+    const int tid = threadIdx.x, warp = (int)warp_idx_uniform();
+
+    if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    for (int idx = tid; idx < N * KCH1; idx += 256) {
+        const int r = idx % N, kc = idx / N;
+        *reinterpret_cast<uint4 *>(sB1 + ((size_t)kc * N + r) * 16) = __ldg(reinterpret_cast<const uint4 *>(a.w1 + (int64_t)r * K1) + kc);
+    }
+    for (int idx = tid; idx < N * KCH2; idx += 256) {
+        const int r = idx % N, kc = idx / N;
+        *reinterpret_cast<uint4 *>(sB2 + ((size_t)kc * N + r) * 16) = __ldg(reinterpret_cast<const uint4 *>(a.w2 + (int64_t)r * K2) + kc);
+    }
+    for (int i = tid; i < N; i += 256) sBias[i] = (a.b1 ? a.b1[i] : 0.f) + (a.b2 ? a.b2[i] : 0.f);
+    // chunk q of a tile's h block: row q / KCH1, 16-byte chunk q % KCH1 (consecutive threads -> consecutive 16 bytes of global memory)
+    auto stage = [&](int64_t tile) {
+        const int64_t m0 = tile * 128;
+        for (int q = tid; q < 128 * KCH1; q += 256) {
+            const int row = q / KCH1, kc = q - row * KCH1;
+            uint8_t *dst = sA1 + (size_t)kc * 2048 + row * 16;
+            if (m0 + row < a.M) ffn_cp_async16(dst, a.h + (m0 + row) * K1 + kc * 8);
+            else *reinterpret_cast<uint4 *>(dst) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        for (int q = tid; q < 128 * KCH2; q += 256) {
+            const int row = q / KCH2, kc = q - row * KCH2;
+            uint8_t *dst = sA2 + (size_t)kc * 2048 + row * 16;
+            if (m0 + row < a.M) ffn_cp_async16(dst, a.u + (m0 + row) * K2 + kc * 8);
+            else *reinterpret_cast<uint4 *>(dst) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    uint32_t phase = 0;
+    const uint32_t idesc = instr_desc_h16<F16>(128, N, false);
+    if ((int64_t)blockIdx.x < a.ntiles) stage(blockIdx.x);
+    fence_proxy_async();          // the weight images (generic-proxy stores) -> visible to the tensor core
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        // GELU of h, in place, on the cells this thread copied itself (elementwise: no cross-thread dependency)
+        for (int q = tid; q < 128 * KCH1; q += 256) {
+            const int row = q / KCH1, kc = q - row * KCH1;
+            uint4 *cell = reinterpret_cast<uint4 *>(sA1 + (size_t)kc * 2048 + row * 16);
+            float f[8];
+            Pack<T16>::unpack(*cell, f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = ffn_gelu(f[e]);
+            *cell = Pack<T16>::pack(f);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();      // both images complete; the previous tile's accumulators have been read by the epilogue warps
+        tc_fence_after();
+        if (warp == 4) {      // one converged warp issues (tc_common.cuh, "warp-uniform issue")
+            const uint32_t a1 = smem_desc_lo(smem_u32(sA1), 2048), a2 = smem_desc_lo(smem_u32(sA2), 2048), ah = smem_desc_hi(128);
+            const uint32_t b1 = smem_desc_lo(smem_u32(sB1), N * 16), b2 = smem_desc_lo(smem_u32(sB2), N * 16), bh = smem_desc_hi(128);
+#pragma unroll 1
+            for (int ks = 0; ks < K1 / 16; ++ks)
+                mma_ss_w(tmem, a1 + (uint32_t)(ks * 2 * 2048 / 16), ah, b1 + (uint32_t)(ks * 2 * N), bh, idesc, ks > 0 ? 1u : 0u);
+#pragma unroll 1
+            for (int ks = 0; ks < K2 / 16; ++ks)
+                mma_ss_w(tmem, a2 + (uint32_t)(ks * 2 * 2048 / 16), ah, b2 + (uint32_t)(ks * 2 * N), bh, idesc, 1u);
+            mma_commit_w(&bar);
+        }
+        mbar_wait(&bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        // the images are free again: the next tile's copies run underneath the epilogue
+        const int64_t next = tile + gridDim.x;
+        if (next < a.ntiles) stage(next);
+        if (warp < 4) {
+            const int64_t m = tile * 128 + (warp & 3) * 32 + (tid & 31);
+            uint16_t *dst = a.out + m * a.os;
+#pragma unroll
+            for (int c = 0; c < N; c += 16) {
+                uint32_t r[16];
+                tmem_ld16(tmem + lane_base + c, r);
+                tmem_wait_ld();
+                if (m < a.M) {
+                    float f[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(r[e]) + sBias[c + e];
+                    uint4 lo, hi;
+                    lo.x = pack_h16<F16>(f[0], f[1]);   lo.y = pack_h16<F16>(f[2], f[3]);   lo.z = pack_h16<F16>(f[4], f[5]);   lo.w = pack_h16<F16>(f[6], f[7]);
+                    hi.x = pack_h16<F16>(f[8], f[9]);   hi.y = pack_h16<F16>(f[10], f[11]); hi.z = pack_h16<F16>(f[12], f[13]); hi.w = pack_h16<F16>(f[14], f[15]);
+                    *reinterpret_cast<uint4 *>(dst + c) = lo;
+                    *reinterpret_cast<uint4 *>(dst + c + 8) = hi;
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_slot, TMEM_COLS);
+}
+
+template <bool F16, int K1, int K2, int N>
+static int pw_tail_launch(const PwTailArgs &a, cudaStream_t st) {
+    const size_t smem = (size_t)(K1 / 8 + K2 / 8) * N * 16 + (size_t)(K1 / 8 + K2 / 8) * 2048 + N * sizeof(float);
+    static unsigned long long attr_done = 0;
+    if (first_use_on_current_device(attr_done))
+        WF_CUDA_CHECK(cudaFuncSetAttribute(pw_gelu_dual_kernel<F16, K1, K2, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int per_sm = (int)((224 * 1024) / (smem + 1024)) < 1 ? 1 : (int)((224 * 1024) / (smem + 1024));
+    const int64_t want = (int64_t)kNumSMs * (per_sm > 2 ? 2 : per_sm);
+    const int64_t grid = a.ntiles < want ? a.ntiles : want;
+    pw_gelu_dual_kernel<F16, K1, K2, N><<<(unsigned)grid, 256, smem, st>>>(a);
+    WF_LAUNCH_CHECK();
+    return WF_OK;
+}
+
 template <bool F16, int C>
 static int ffn_front_launch(const FfnFrontArgs &a, cudaStream_t st) {
     constexpr int N = 4 * C, KCH = C / 8;
@@ -438,4 +587,20 @@ extern "C" int wf_ffn_back(const void *t2, int dtype, const float *ln_w, const f
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == WF_F16) return C == 48 ? ffn_back_launch<true, 48>(a, st) : ffn_back_launch<true, 96>(a, st);
     return C == 48 ? ffn_back_launch<false, 48>(a, st) : ffn_back_launch<false, 96>(a, st);
+}
+
+extern "C" int wf_pw_gelu_dual(const void *h, const void *u, int dtype, const void *w1, const float *b1, const void *w2, const float *b2,
+                               void *out, int64_t rows, int K1, int K2, int N, int64_t out_row_stride, void *stream) {
+    if (!h || !u || !w1 || !w2 || !out) return WF_ERR_NULL_POINTER;
+    if (rows <= 0 || out_row_stride < N || out_row_stride % 8) return WF_ERR_BAD_SHAPE;
+    if (dtype != WF_BF16 && dtype != WF_F16) return WF_ERR_BAD_DTYPE;
+    if (!aligned16(h) || !aligned16(u) || !aligned16(w1) || !aligned16(w2) || !aligned16(out)) return WF_ERR_MISALIGNED;
+    PwTailArgs a;
+    a.h = (const uint16_t *)h; a.u = (const uint16_t *)u; a.w1 = (const uint16_t *)w1; a.w2 = (const uint16_t *)w2; a.b1 = b1; a.b2 = b2;
+    a.out = (uint16_t *)out; a.M = rows; a.ntiles = (rows + 127) / 128; a.os = out_row_stride;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool f16 = dtype == WF_F16;
+    if (K1 == 192 && K2 == 96 && N == 48) return f16 ? pw_tail_launch<true, 192, 96, 48>(a, st) : pw_tail_launch<false, 192, 96, 48>(a, st);
+    if (K1 == 192 && K2 == 192 && N == 48) return f16 ? pw_tail_launch<true, 192, 192, 48>(a, st) : pw_tail_launch<false, 192, 192, 48>(a, st);
+    return WF_ERR_UNSUPPORTED;
 }

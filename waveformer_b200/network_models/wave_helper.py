@@ -455,12 +455,17 @@ class ProjectionUpsample(nn.Module):
         h = torch.empty(dw.shape[:-1] + (c_mid,), dtype=dw.dtype, device=dw.device)
         for i in range(B):      # one GEMM per sample (its own folded weights); a broadcast-bias baddbmm measured 4x slower
             torch.addmm(bf_[i], dw[i].reshape(-1, c_in), wf_[i].t(), out=h[i].view(-1, c_mid))
-        h = self._gelu(h)
         if self.use_double_conv:
-            h = self._pointwise(self._gelu(self._pointwise(h, self.conv3[0])), self.conv3[2])
+            h = self._pointwise(self._gelu(h), self.conv3[0])       # the Sequential's own GELU is applied by the consumer below
+            last = self.conv3[2]
         else:
-            h = self._pointwise(h, self.conv3)
-        dst = out_buf if out_buf is not None else torch.empty_like(h)
+            last = self.conv3
+        dst = out_buf if out_buf is not None else torch.empty(h.shape[:-1] + (last.out_channels,), dtype=h.dtype, device=h.device)
+        if self.do_res and ops.pw_gelu_dual_supported(h, up, last.out_channels, dst):
+            # last 1^3 convolution on GELU(h) + the residual projection of the shared upsampled input, written into the slice: one kernel
+            ops.pw_gelu_dual(h, up, last.weight, last.bias, self.res_conv[1].weight, self.res_conv[1].bias, dst)
+            return dst.permute(0, 4, 1, 2, 3)
+        h = self._pointwise(self._gelu(h), last)
         if self.do_res:
             # (writing the last GEMM into the strided concat slice and accumulating the residual GEMM into it with beta = 1
             # measured slower than two dense GEMMs + this add: the library copies around a strided output)

@@ -929,6 +929,47 @@ def ffn_back(t2: torch.Tensor, ln: torch.nn.LayerNorm, fc_weight: torch.Tensor, 
     return out
 
 
+def _row_stride(t: torch.Tensor) -> Optional[int]:
+    """Row pitch (elements) of a [..., N] tensor whose rows are dense and equally spaced (e.g. a channel slice of a channels-last
+    buffer); None if the leading dimensions do not collapse into one."""
+    if t.dim() < 2 or t.stride(-1) != 1:
+        return None
+    pitch = t.stride(-2)
+    for i in range(t.dim() - 3, -1, -1):
+        if t.shape[i] != 1 and t.stride(i) != t.stride(i + 1) * t.shape[i + 1]:
+            return None
+    return int(pitch) if pitch >= t.shape[-1] else None
+
+
+def pw_gelu_dual_supported(h: torch.Tensor, u: torch.Tensor, n_out: int, out: torch.Tensor) -> bool:
+    """Shapes / types ``pw_gelu_dual`` is built for (the reference configuration's learnable_up3 / learnable_up4)."""
+    return (h.is_cuda and h.dtype in HALF_TYPES and u.dtype == h.dtype and out.dtype == h.dtype and h.is_contiguous() and u.is_contiguous()
+            and (h.shape[-1], u.shape[-1], n_out) in ((192, 96, 48), (192, 192, 48)) and out.shape[-1] == n_out
+            and h.numel() // h.shape[-1] == u.numel() // u.shape[-1] == out.numel() // n_out
+            and _row_stride(out) is not None and _row_stride(out) % 8 == 0 and out.data_ptr() % 16 == 0)
+
+
+def pw_gelu_dual(h: torch.Tensor, u: torch.Tensor, w1: torch.Tensor, b1: Optional[torch.Tensor], w2: torch.Tensor,
+                 b2: Optional[torch.Tensor], out: torch.Tensor) -> torch.Tensor:
+    """``out[..., :N] = GELU(h) @ w1.T + b1 + u @ w2.T + b2`` in one tensor-core kernel (``wf_pw_gelu_dual``): the tail of
+    ``ProjectionUpsample``.  ``h[..., K1]``, ``u[..., K2]`` dense 16-bit; ``out[..., N]`` voxel-dense, possibly a channel slice
+    of a wider channels-last buffer; ``w1`` / ``w2`` any tensor viewable as [N, K1] / [N, K2]."""
+    dev = _need_cuda(h, u, w1, b1, w2, b2, out)
+    n = out.shape[-1]
+    if not pw_gelu_dual_supported(h, u, n, out):
+        raise ValueError("pw_gelu_dual: unsupported shapes / types (see pw_gelu_dual_supported)")
+    k1, k2 = h.shape[-1], u.shape[-1]
+    w1c = cast_cached(w1, h.dtype).reshape(n, k1)
+    w2c = cast_cached(w2, h.dtype).reshape(n, k2)
+    rows = h.numel() // k1
+    with torch.cuda.device(dev):
+        st = _lib.lib().wf_pw_gelu_dual(h.data_ptr(), u.data_ptr(), _dtype_code(h), w1c.data_ptr(), _ptr(f32_cached(b1)), w2c.data_ptr(),
+                                        _ptr(f32_cached(b2)), out.data_ptr(), rows, k1, k2, n, _row_stride(out), _stream(dev))
+    _lib.check(st, "wf_pw_gelu_dual")
+    _count()
+    return out
+
+
 def split_f16(x: torch.Tensor):
     """fp32 ``x`` (any dense layout) -> ``(hi, lo)`` fp16 tensors of x's shape and strides with ``hi + lo == x`` to 22 bits."""
     dev = _need_cuda(x)
