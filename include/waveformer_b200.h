@@ -262,14 +262,18 @@ int wf_ffn_back(const void *t2, int dtype, const float *ln_w, const float *ln_b,
                 const float *fc_b, const float *x, const float *norm2_w, const float *norm2_b, float norm2_eps, float *out,
                 int64_t rows, int C, void *stream);
 
-/* Tail of ProjectionUpsample (reference network_models/wave_helper.py:75-81): out[r, :N] = w1 . GELU(h[r, :K1]) + b1 + w2 . u[r, :K2] + b2
- * - the last 1^3 convolution of `conv3` applied to the (exact, erf) GELU of its input, plus `res_conv`'s 1^3 convolution of the
- * upsampled input u, written straight into a channel slice of the decoder's concatenation buffer (row pitch out_row_stride
- * elements).  h, u, w1 [N, K1], w2 [N, K2] and out are 16-bit (dtype: WF_BF16 or WF_F16), biases fp32 or NULL, accumulation fp32.
- * One tcgen05 kernel instead of a GELU pass, two library GEMMs and an add.  (K1, K2, N) in {(192, 96, 48), (192, 192, 48)} - the
- * reference configuration's learnable_up3 / learnable_up4 - otherwise WF_ERR_UNSUPPORTED. */
+/* Tail of ProjectionUpsample (reference network_models/wave_helper.py:75-81):
+ *     out[r, :N] = w1 . GELU(h[r, :K1]) + b1  +  w2 . u[r, :K2] + b2  +  addend[r, :N]
+ * - the last 1^3 convolution of `conv3` applied to the (exact, erf) GELU of its input, plus the residual branch `res_conv` (Upsample +
+ * 1^3 convolution of the module's input) either as a second product on the upsampled input u (K2 > 0) or, because a 1^3
+ * convolution commutes with trilinear interpolation, as the fp32 `addend` = Upsample(res_conv's convolution at LOW resolution)
+ * (K2 = 0: u, w2, b2 ignored) - written straight into a channel slice of the decoder's concatenation buffer (row pitch
+ * out_row_stride elements).  h, u, w1 [N, K1], w2 [N, K2] and out are 16-bit (dtype: WF_BF16 or WF_F16), biases fp32 or NULL, addend
+ * fp32 dense [rows, N] or NULL, accumulation fp32.  One tcgen05 kernel instead of a GELU pass, two library GEMMs and an add.
+ * (K1, K2, N) in {(192, 0, 48), (192, 96, 48), (192, 192, 48)} - the reference configuration's learnable_up3 / learnable_up4 -
+ * otherwise WF_ERR_UNSUPPORTED. */
 int wf_pw_gelu_dual(const void *h, const void *u, int dtype, const void *w1, const float *b1, const void *w2, const float *b2,
-                    void *out, int64_t rows, int K1, int K2, int N, int64_t out_row_stride, void *stream);
+                    const float *addend, void *out, int64_t rows, int K1, int K2, int N, int64_t out_row_stride, void *stream);
 
 /* 3x3x3 convolution (padding 1, no bias) of a 4-channel channels-last volume x [B, D, H, W, 4] (op_dtype WF_BF16 or
  * WF_F16 = format of the tensor-core operands, of wpack and of both results; x_dtype = WF_F32 - converted while gathered -

@@ -312,23 +312,30 @@ def test_patch_merge_gather_layernorm_fused(shape, out_dtype, tol, v2):
     assert ops.patch_merge_layer_norm(x[:, :, :, :-1].contiguous().cuda(), gam.cuda(), bet.cuda(), 1e-5, octs, out_dtype) is None
 
 
-@pytest.mark.parametrize("k2,rows", [(96, 128), (96, 1000), (192, 257), (192, 4 * 32 * 32 * 32)])
+@pytest.mark.parametrize("k2,rows", [(0, 128), (0, 777), (96, 128), (96, 1000), (192, 257), (192, 4 * 32 * 32 * 32)])
 @pytest.mark.parametrize("dtype,tol", [(torch.float16, 3e-3), (torch.bfloat16, 2e-2)])
 def test_pw_gelu_dual_tail_kernel(k2, rows, dtype, tol):
     """Tail of ProjectionUpsample in one tcgen05 kernel: out = W1 . GELU(h) + b1 + W2 . u + b2 written into a channel slice of a
     wider channels-last buffer (row pitch 144), vs fp64 torch on the same 16-bit operands; partial last tile, several tiles per CTA."""
     from waveformer_b200 import ops
     h = (seeded_randn((rows, 192), 180) * 1.5).cuda().to(dtype)
-    u = seeded_randn((rows, k2), 181).cuda().to(dtype)
     w1 = (seeded_randn((48, 192, 1, 1, 1), 182) / 192 ** 0.5).cuda()
-    w2 = (seeded_randn((48, k2, 1, 1, 1), 183) / k2 ** 0.5).cuda()
     b1, b2 = (0.1 * seeded_randn((48,), 184)).cuda(), (0.1 * seeded_randn((48,), 185)).cuda()
     comb = torch.full((rows, 144), 7.0, device="cuda", dtype=dtype)
     out = comb[:, 48:96]
-    assert ops.pw_gelu_dual_supported(h, u, 48, out)
-    ops.pw_gelu_dual(h, u, w1, b1, w2, b2, out)
-    w1h, w2h = w1.view(48, 192).to(dtype).double(), w2.view(48, k2).to(dtype).double()
-    want = F.gelu(h.double()) .to(dtype).double() @ w1h.t() + b1.double() + u.double() @ w2h.t() + b2.double()
+    w1h = w1.view(48, 192).to(dtype).double()
+    want = F.gelu(h.double()) .to(dtype).double() @ w1h.t() + b1.double()
+    if k2:      # residual as a second product on the upsampled input
+        u = seeded_randn((rows, k2), 181).cuda().to(dtype)
+        w2 = (seeded_randn((48, k2, 1, 1, 1), 183) / k2 ** 0.5).cuda()
+        assert ops.pw_gelu_dual_supported(h, u, 48, out)
+        ops.pw_gelu_dual(h, u, w1, b1, w2, b2, out)
+        want = want + u.double() @ w2.view(48, k2).to(dtype).double().t() + b2.double()
+    else:       # residual as an fp32 addend (the commuted low-resolution convolution, upsampled)
+        add = seeded_randn((rows, 48), 186).cuda()
+        assert ops.pw_gelu_dual_supported(h, None, 48, out)
+        ops.pw_gelu_dual(h, None, w1, b1, None, None, out, addend=add)
+        want = want + add.double()
     assert max_rel(out.double().cpu(), want.cpu()) < tol
     assert bool((comb[:, :48] == 7.0).all()) and bool((comb[:, 96:] == 7.0).all())      # neighbouring slices untouched
 

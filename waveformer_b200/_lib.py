@@ -47,7 +47,7 @@ SIGNATURES = {
     "wf_layernorm_ndhwc": (_I, [_VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _I, _I, _I, _I64, _I, _I64, _I64, _F, _I, _VOIDP]),
     "wf_patch_embed_k2s2_c4": (_I, [_VOIDP, _I, _VOIDP, _VOIDP, _VOIDP, _I, _I, _I, _I, _I, _VOIDP]),
     "wf_ffn_front": (_I, [_VOIDP, _VOIDP, _VOIDP, _F, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _F, _VOIDP, _I, _I64, _I, _VOIDP]),
-    "wf_pw_gelu_dual": (_I, [_VOIDP, _VOIDP, _I, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _I64, _I, _I, _I, _I64, _VOIDP]),
+    "wf_pw_gelu_dual": (_I, [_VOIDP, _VOIDP, _I, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _I64, _I, _I, _I, _I64, _VOIDP]),
     "wf_ffn_back": (_I, [_VOIDP, _I, _VOIDP, _VOIDP, _F, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _F, _VOIDP, _I64, _I, _VOIDP]),
     "wf_upsample_trilinear_add_ndhwc": (_I, [_VOIDP, _VOIDP, _I, _VOIDP, _VOIDP, _I, _I, _I, _I, _I, _I, _I, _I, _I64, _I64, _VOIDP]),
     "wf_conv3d_c4_in_stats": (_I, [_VOIDP, _I, _I, _VOIDP, _VOIDP, _I64, _I, _VOIDP, _I64, _I, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _F, _I, _I, _I, _I, _VOIDP]),

@@ -390,6 +390,7 @@ struct PwTailArgs {
     const uint16_t *h, *u;       // [M, K1], [M, K2] dense
     const uint16_t *w1, *w2;     // [N, K1], [N, K2]
     const float *b1, *b2;        // fp32 [N] or NULL
+    const float *addend;         // optional fp32 [M, N] dense, added before rounding
     uint16_t *out;               // [M, N], row pitch os elements
     int64_t M, ntiles, os;
 };
@@ -494,6 +495,14 @@ __global__ void __launch_bounds__(256) pw_gelu_dual_kernel(PwTailArgs a) {
                     float f[16];
 #pragma unroll
                     for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(r[e]) + sBias[c + e];
+                    if (a.addend != nullptr) {
+                        const float4 *ad = reinterpret_cast<const float4 *>(a.addend + m * N + c);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 t = __ldg(ad + i);
+                            f[4 * i] += t.x; f[4 * i + 1] += t.y; f[4 * i + 2] += t.z; f[4 * i + 3] += t.w;
+                        }
+                    }
                     uint4 lo, hi;
                     lo.x = pack_h16<F16>(f[0], f[1]);   lo.y = pack_h16<F16>(f[2], f[3]);   lo.z = pack_h16<F16>(f[4], f[5]);   lo.w = pack_h16<F16>(f[6], f[7]);
                     hi.x = pack_h16<F16>(f[8], f[9]);   hi.y = pack_h16<F16>(f[10], f[11]); hi.z = pack_h16<F16>(f[12], f[13]); hi.w = pack_h16<F16>(f[14], f[15]);
@@ -517,7 +526,7 @@ static int pw_tail_launch(const PwTailArgs &a, cudaStream_t st) {
     if (first_use_on_current_device(attr_done))
         WF_CUDA_CHECK(cudaFuncSetAttribute(pw_gelu_dual_kernel<F16, K1, K2, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int per_sm = (int)((224 * 1024) / (smem + 1024)) < 1 ? 1 : (int)((224 * 1024) / (smem + 1024));
-    const int64_t want = (int64_t)kNumSMs * (per_sm > 2 ? 2 : per_sm);
+    const int64_t want = (int64_t)kNumSMs * (per_sm > 3 ? 3 : per_sm);
     const int64_t grid = a.ntiles < want ? a.ntiles : want;
     pw_gelu_dual_kernel<F16, K1, K2, N><<<(unsigned)grid, 256, smem, st>>>(a);
     WF_LAUNCH_CHECK();
@@ -590,16 +599,18 @@ extern "C" int wf_ffn_back(const void *t2, int dtype, const float *ln_w, const f
 }
 
 extern "C" int wf_pw_gelu_dual(const void *h, const void *u, int dtype, const void *w1, const float *b1, const void *w2, const float *b2,
-                               void *out, int64_t rows, int K1, int K2, int N, int64_t out_row_stride, void *stream) {
-    if (!h || !u || !w1 || !w2 || !out) return WF_ERR_NULL_POINTER;
+                               const float *addend, void *out, int64_t rows, int K1, int K2, int N, int64_t out_row_stride, void *stream) {
+    if (!h || !w1 || !out || (K2 > 0 && (!u || !w2))) return WF_ERR_NULL_POINTER;
     if (rows <= 0 || out_row_stride < N || out_row_stride % 8) return WF_ERR_BAD_SHAPE;
     if (dtype != WF_BF16 && dtype != WF_F16) return WF_ERR_BAD_DTYPE;
-    if (!aligned16(h) || !aligned16(u) || !aligned16(w1) || !aligned16(w2) || !aligned16(out)) return WF_ERR_MISALIGNED;
+    if (!aligned16(h) || !aligned16(w1) || !aligned16(out) || (K2 > 0 && (!aligned16(u) || !aligned16(w2))) || (addend && !aligned16(addend)))
+        return WF_ERR_MISALIGNED;
     PwTailArgs a;
-    a.h = (const uint16_t *)h; a.u = (const uint16_t *)u; a.w1 = (const uint16_t *)w1; a.w2 = (const uint16_t *)w2; a.b1 = b1; a.b2 = b2;
-    a.out = (uint16_t *)out; a.M = rows; a.ntiles = (rows + 127) / 128; a.os = out_row_stride;
+    a.h = (const uint16_t *)h; a.u = (const uint16_t *)u; a.w1 = (const uint16_t *)w1; a.w2 = (const uint16_t *)w2; a.b1 = b1; a.b2 = K2 > 0 ? b2 : nullptr;
+    a.addend = addend; a.out = (uint16_t *)out; a.M = rows; a.ntiles = (rows + 127) / 128; a.os = out_row_stride;
     cudaStream_t st = (cudaStream_t)stream;
     const bool f16 = dtype == WF_F16;
+    if (K1 == 192 && K2 == 0 && N == 48) return f16 ? pw_tail_launch<true, 192, 0, 48>(a, st) : pw_tail_launch<false, 192, 0, 48>(a, st);
     if (K1 == 192 && K2 == 96 && N == 48) return f16 ? pw_tail_launch<true, 192, 96, 48>(a, st) : pw_tail_launch<false, 192, 96, 48>(a, st);
     if (K1 == 192 && K2 == 192 && N == 48) return f16 ? pw_tail_launch<true, 192, 192, 48>(a, st) : pw_tail_launch<false, 192, 192, 48>(a, st);
     return WF_ERR_UNSUPPORTED;

@@ -941,30 +941,37 @@ def _row_stride(t: torch.Tensor) -> Optional[int]:
     return int(pitch) if pitch >= t.shape[-1] else None
 
 
-def pw_gelu_dual_supported(h: torch.Tensor, u: torch.Tensor, n_out: int, out: torch.Tensor) -> bool:
-    """Shapes / types ``pw_gelu_dual`` is built for (the reference configuration's learnable_up3 / learnable_up4)."""
-    return (h.is_cuda and h.dtype in HALF_TYPES and u.dtype == h.dtype and out.dtype == h.dtype and h.is_contiguous() and u.is_contiguous()
-            and (h.shape[-1], u.shape[-1], n_out) in ((192, 96, 48), (192, 192, 48)) and out.shape[-1] == n_out
-            and h.numel() // h.shape[-1] == u.numel() // u.shape[-1] == out.numel() // n_out
+def pw_gelu_dual_supported(h: torch.Tensor, u: Optional[torch.Tensor], n_out: int, out: torch.Tensor) -> bool:
+    """Shapes / types ``pw_gelu_dual`` is built for (the reference configuration's learnable_up3 / learnable_up4).  ``u=None``:
+    the variant whose residual arrives as an fp32 addend."""
+    k2 = 0 if u is None else u.shape[-1]
+    return (h.is_cuda and h.dtype in HALF_TYPES and out.dtype == h.dtype and h.is_contiguous()
+            and (u is None or (u.dtype == h.dtype and u.is_contiguous() and u.numel() // k2 == h.numel() // h.shape[-1]))
+            and (h.shape[-1], k2, n_out) in ((192, 0, 48), (192, 96, 48), (192, 192, 48)) and out.shape[-1] == n_out
+            and h.numel() // h.shape[-1] == out.numel() // n_out
             and _row_stride(out) is not None and _row_stride(out) % 8 == 0 and out.data_ptr() % 16 == 0)
 
 
-def pw_gelu_dual(h: torch.Tensor, u: torch.Tensor, w1: torch.Tensor, b1: Optional[torch.Tensor], w2: torch.Tensor,
-                 b2: Optional[torch.Tensor], out: torch.Tensor) -> torch.Tensor:
-    """``out[..., :N] = GELU(h) @ w1.T + b1 + u @ w2.T + b2`` in one tensor-core kernel (``wf_pw_gelu_dual``): the tail of
-    ``ProjectionUpsample``.  ``h[..., K1]``, ``u[..., K2]`` dense 16-bit; ``out[..., N]`` voxel-dense, possibly a channel slice
-    of a wider channels-last buffer; ``w1`` / ``w2`` any tensor viewable as [N, K1] / [N, K2]."""
-    dev = _need_cuda(h, u, w1, b1, w2, b2, out)
+def pw_gelu_dual(h: torch.Tensor, u: Optional[torch.Tensor], w1: torch.Tensor, b1: Optional[torch.Tensor], w2: Optional[torch.Tensor],
+                 b2: Optional[torch.Tensor], out: torch.Tensor, addend: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``out[..., :N] = GELU(h) @ w1.T + b1 + u @ w2.T + b2 + addend`` in one tensor-core kernel (``wf_pw_gelu_dual``): the tail of
+    ``ProjectionUpsample``.  ``h[..., K1]``, ``u[..., K2]`` dense 16-bit (``u``, ``w2``, ``b2`` may be None); ``addend`` fp32
+    dense ``[..., N]`` or None; ``out[..., N]`` row-dense, possibly a channel slice of a wider channels-last buffer; ``w1`` / ``w2`` any
+    tensor viewable as [N, K1] / [N, K2]."""
+    dev = _need_cuda(h, u, w1, b1, w2, b2, out, addend)
     n = out.shape[-1]
     if not pw_gelu_dual_supported(h, u, n, out):
         raise ValueError("pw_gelu_dual: unsupported shapes / types (see pw_gelu_dual_supported)")
-    k1, k2 = h.shape[-1], u.shape[-1]
-    w1c = cast_cached(w1, h.dtype).reshape(n, k1)
-    w2c = cast_cached(w2, h.dtype).reshape(n, k2)
+    k1, k2 = h.shape[-1], 0 if u is None else u.shape[-1]
     rows = h.numel() // k1
+    if addend is not None and (addend.dtype != torch.float32 or not addend.is_contiguous() or addend.numel() != rows * n):
+        raise ValueError("pw_gelu_dual: addend must be a dense fp32 [..., N] tensor")
+    w1c = cast_cached(w1, h.dtype).reshape(n, k1)
+    w2c = None if u is None else cast_cached(w2, h.dtype).reshape(n, k2)
     with torch.cuda.device(dev):
-        st = _lib.lib().wf_pw_gelu_dual(h.data_ptr(), u.data_ptr(), _dtype_code(h), w1c.data_ptr(), _ptr(f32_cached(b1)), w2c.data_ptr(),
-                                        _ptr(f32_cached(b2)), out.data_ptr(), rows, k1, k2, n, _row_stride(out), _stream(dev))
+        st = _lib.lib().wf_pw_gelu_dual(h.data_ptr(), _ptr(u), _dtype_code(h), w1c.data_ptr(), _ptr(f32_cached(b1)), _ptr(w2c),
+                                        _ptr(f32_cached(b2)) if u is not None else None, _ptr(addend), out.data_ptr(), rows, k1, k2, n,
+                                        _row_stride(out), _stream(dev))
     _lib.check(st, "wf_pw_gelu_dual")
     _count()
     return out
