@@ -406,10 +406,13 @@ __global__ void __launch_bounds__(544, 1) attn_core_tc_kernel(const uint16_t *__
 
     if (warp == 16) {
         // ================================================= issuer ====================================================
-        if (lane == 0 && g < B_) {
+        if (g < B_ && (SPLIT || lane == 0)) {      // SPLIT: the whole (converged) warp runs the issue loop, one elected lane issues
             // relative-position bias slab of this (head, query tile): one 130 KB bulk copy, resident for every window
-            mbar_expect_tx(&bar_bias, kBiasBytes);
-            bulk_g2s(sBias, bias_img + ((int64_t)hh * 4 + qt) * (kBiasBytes / 2), kBiasBytes, &bar_bias);
+            if (lane == 0) {
+                mbar_expect_tx(&bar_bias, kBiasBytes);
+                bulk_g2s(sBias, bias_img + ((int64_t)hh * 4 + qt) * (kBiasBytes / 2), kBiasBytes, &bar_bias);
+            }
+            __syncwarp(SPLIT ? 0xffffffffu : 1u);
             const uint32_t idesc_s = instr_desc16<F16>(128, 256, false);
             const uint32_t idesc_o = instr_desc16<F16>(128, 16, true);
             if constexpr (!SPLIT) {
@@ -461,67 +464,77 @@ __global__ void __launch_bounds__(544, 1) attn_core_tc_kernel(const uint16_t *__
             } else {
                 uint8_t *sQK = sStage;                      // [Q hi 4096][Q lo 4096][K hi 16384][K lo 16384]
                 uint8_t *sVb = sStage + kQKSplitBytes;      // 2 x 16384
+                // Warp-uniform issue (tc_common.cuh): stage clocks of the single-thread issuer (profiles/r02_attn_stage_clocks_before.txt)
+                // showed the 32 small PV instructions lagging ~2 400 clk behind the softmax warps at the end of every tile - every
+                // tcgen05.mma issued from inside `if (lane == 0)` is wrapped in an ELECT loop with ~7 R2UR moves (~140 clk apiece).
                 auto issue_qk = [&](int64_t win) {
-                    const uint16_t *qb = qkv + (win * heads + hh) * 8192;
-                    mbar_expect_tx(&bar_qk, kQKSplitBytes);
-                    bulk_g2s(sQK, qb + qt * 128 * 8, 2048, &bar_qk);                                   // Q hi, head dims 0..7
-                    bulk_g2s(sQK + 2048, qb + 4096 + qt * 128 * 8, 2048, &bar_qk);                     // Q hi, head dims 8..15
-                    bulk_g2s(sQK + 4096, qb + 3 * per_which + qt * 128 * 8, 2048, &bar_qk);            // Q lo
-                    bulk_g2s(sQK + 6144, qb + 3 * per_which + 4096 + qt * 128 * 8, 2048, &bar_qk);
-                    bulk_g2s(sQK + 8192, qb + per_which, 16384, &bar_qk);                              // K hi
-                    bulk_g2s(sQK + 8192 + 16384, qb + 4 * per_which, 16384, &bar_qk);                  // K lo
+                    if (elect_one()) {
+                        const uint16_t *qb = qkv + (win * heads + hh) * 8192;
+                        mbar_expect_tx(&bar_qk, kQKSplitBytes);
+                        bulk_g2s(sQK, qb + qt * 128 * 8, 2048, &bar_qk);                                   // Q hi, head dims 0..7
+                        bulk_g2s(sQK + 2048, qb + 4096 + qt * 128 * 8, 2048, &bar_qk);                     // Q hi, head dims 8..15
+                        bulk_g2s(sQK + 4096, qb + 3 * per_which + qt * 128 * 8, 2048, &bar_qk);            // Q lo
+                        bulk_g2s(sQK + 6144, qb + 3 * per_which + 4096 + qt * 128 * 8, 2048, &bar_qk);
+                        bulk_g2s(sQK + 8192, qb + per_which, 16384, &bar_qk);                              // K hi
+                        bulk_g2s(sQK + 8192 + 16384, qb + 4 * per_which, 16384, &bar_qk);                  // K lo
+                    }
+                    __syncwarp();
                 };
                 auto issue_v = [&](int64_t win, int stage) {
-                    mbar_expect_tx(&bar_full[stage], 16384);
-                    bulk_g2s(sVb + stage * 16384, qkv + (win * heads + hh) * 8192 + 2 * per_which, 16384, &bar_full[stage]);
+                    if (elect_one()) {
+                        mbar_expect_tx(&bar_full[stage], 16384);
+                        bulk_g2s(sVb + stage * 16384, qkv + (win * heads + hh) * 8192 + 2 * per_which, 16384, &bar_full[stage]);
+                    }
+                    __syncwarp();
                 };
                 issue_qk(g);
                 issue_v(g, 0);
                 const uint32_t sQh = smem_u32(sQK), sQl = sQh + 4096, sKh = sQh + 8192, sKl = sKh + 16384;
+                const uint32_t q_hi = smem_desc_hi(128), dqh = smem_desc_lo(sQh, 2048), dql = smem_desc_lo(sQl, 2048);   // Q: [2][128][8]
+                const uint32_t k_hi = smem_desc_hi(128), v_hi = smem_desc_hi(8192);
                 int it = 0;
                 for (int64_t win = g; win < B_; win += groups, ++it) {
                     const int stage = it & 1;
                     const uint32_t ph_v = (it >> 1) & 1, ph = it & 1;
                     const uint32_t sV = smem_u32(sVb + stage * 16384);
                     if (it > 0) {   // previous tile: O read back and its V / P consumed -> TMEM and the other V stage are free
-                        mbar_wait(&bar_epi, (it - 1) & 1);
+                        mbar_wait_warp(&bar_epi, (it - 1) & 1);
                         tc_fence_after();
                     }
                     const bool more = win + groups < B_;
                     if (more) issue_v(win + groups, stage ^ 1);
-                    mbar_wait(&bar_qk, ph);
+                    mbar_wait_warp(&bar_qk, ph);
                     tc_fence_after();
-                    const uint64_t dqh = smem_desc(sQh, 2048, 128), dql = smem_desc(sQl, 2048, 128);
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
-                        const uint64_t dkh = smem_desc(sKh + half * 256 * 16, 8192, 128), dkl = smem_desc(sKl + half * 256 * 16, 8192, 128);
-                        mma_ss(tmem + half * 256, dqh, dkh, idesc_s, 0u);
-                        mma_ss(tmem + half * 256, dql, dkh, idesc_s, 1u);
-                        mma_ss(tmem + half * 256, dqh, dkl, idesc_s, 1u);
+                        const uint32_t dkh = smem_desc_lo(sKh + half * 256 * 16, 8192), dkl = smem_desc_lo(sKl + half * 256 * 16, 8192);
+                        mma_ss_w(tmem + half * 256, dqh, q_hi, dkh, k_hi, idesc_s, 0u);
+                        mma_ss_w(tmem + half * 256, dql, q_hi, dkh, k_hi, idesc_s, 1u);
+                        mma_ss_w(tmem + half * 256, dqh, q_hi, dkl, k_hi, idesc_s, 1u);
                     }
-                    mma_commit(&bar_s);
+                    mma_commit_w(&bar_s);
                     // the score MMAs were the only readers of the Q / K buffer: refill it for the next window as soon as
                     // they have completed - the copy lands long before the softmax of this tile is through
-                    mbar_wait(&bar_s, ph);
+                    mbar_wait_warp(&bar_s, ph);
                     if (more) issue_qk(win + groups);
-                    mbar_wait(&bar_full[stage], ph_v);
+                    mbar_wait_warp(&bar_full[stage], ph_v);
                     tc_fence_after();
+                    const uint32_t dv = smem_desc_lo(sV, 128);
                     uint32_t first = 1;
 #pragma unroll 1
                     for (int c = 0; c < 4; ++c)
 #pragma unroll 1
                         for (int q = 0; q < 4; ++q) {
-                            mbar_wait(&bar_p[q * 4 + c], ph);
+                            mbar_wait_lean(&bar_p[q * 4 + c], ph);
                             tc_fence_after();
 #pragma unroll
                             for (int j = 0; j < 2; ++j) {
                                 const int ks = q * 8 + c * 2 + j;   // k-step = keys [16 ks, 16 ks + 16)
-                                mma_ts(tmem + 16, tmem + q * 128 + c * 32 + j * 8, smem_desc(sV + ks * 256, 128, 8192), idesc_o,
-                                       first ? 0u : 1u);
+                                mma_ts_w(tmem + 16, tmem + q * 128 + c * 32 + j * 8, dv + (uint32_t)(ks * 256 / 16), v_hi, idesc_o, first ? 0u : 1u);
                                 first = 0;
                             }
                         }
-                    mma_commit(&bar_o);
+                    mma_commit_w(&bar_o);
                 }
             }
         }
