@@ -406,60 +406,65 @@ __global__ void __launch_bounds__(544, 1) attn_core_tc_kernel(const uint16_t *__
 
     if (warp == 16) {
         // ================================================= issuer ====================================================
-        if (g < B_ && (SPLIT || lane == 0)) {      // SPLIT: the whole (converged) warp runs the issue loop, one elected lane issues
+        if (g < B_) {      // the whole (converged) warp runs the issue loop, one elected lane issues each instruction
             // relative-position bias slab of this (head, query tile): one 130 KB bulk copy, resident for every window
             if (lane == 0) {
                 mbar_expect_tx(&bar_bias, kBiasBytes);
                 bulk_g2s(sBias, bias_img + ((int64_t)hh * 4 + qt) * (kBiasBytes / 2), kBiasBytes, &bar_bias);
             }
-            __syncwarp(SPLIT ? 0xffffffffu : 1u);
+            __syncwarp();
             const uint32_t idesc_s = instr_desc16<F16>(128, 256, false);
             const uint32_t idesc_o = instr_desc16<F16>(128, 16, true);
             if constexpr (!SPLIT) {
+                // (warp-uniform issue like the compensated branch below: all 32 lanes run the loop, one elected lane issues)
                 auto issue_loads = [&](int64_t win, int stage) {
-                    uint8_t *dst = sStage + stage * kStageBytes;
-                    const uint16_t *qb = qkv + (win * heads + hh) * 8192;
-                    mbar_expect_tx(&bar_full[stage], kStageBytes);
-                    bulk_g2s(dst, qb + qt * 128 * 8, 2048, &bar_full[stage]);                 // Q chunk 0 (head dims 0..7)
-                    bulk_g2s(dst + 2048, qb + 4096 + qt * 128 * 8, 2048, &bar_full[stage]);   // Q chunk 1
-                    bulk_g2s(dst + 4096, qb + per_which, 16384, &bar_full[stage]);            // K
-                    bulk_g2s(dst + 4096 + 16384, qb + 2 * per_which, 16384, &bar_full[stage]);  // V
+                    if (elect_one()) {
+                        uint8_t *dst = sStage + stage * kStageBytes;
+                        const uint16_t *qb = qkv + (win * heads + hh) * 8192;
+                        mbar_expect_tx(&bar_full[stage], kStageBytes);
+                        bulk_g2s(dst, qb + qt * 128 * 8, 2048, &bar_full[stage]);                 // Q chunk 0 (head dims 0..7)
+                        bulk_g2s(dst + 2048, qb + 4096 + qt * 128 * 8, 2048, &bar_full[stage]);   // Q chunk 1
+                        bulk_g2s(dst + 4096, qb + per_which, 16384, &bar_full[stage]);            // K
+                        bulk_g2s(dst + 4096 + 16384, qb + 2 * per_which, 16384, &bar_full[stage]);  // V
+                    }
+                    __syncwarp();
                 };
                 issue_loads(g, 0);
+                const uint32_t qk_hi = smem_desc_hi(128), v_hi = smem_desc_hi(8192);
                 int it = 0;
                 for (int64_t win = g; win < B_; win += groups, ++it) {
                     const int stage = it & 1;
                     const uint32_t ph_full = (it >> 1) & 1, ph = it & 1;
                     const uint32_t sQ = smem_u32(sStage + stage * kStageBytes), sK = sQ + 4096, sV = sK + 16384;
                     if (it > 0) {   // previous tile: O read back and its V / P consumed -> TMEM and the other stage are free
-                        mbar_wait(&bar_epi, (it - 1) & 1);
+                        mbar_wait_warp(&bar_epi, (it - 1) & 1);
                         tc_fence_after();
                     }
                     if (win + groups < B_) issue_loads(win + groups, stage ^ 1);
-                    mbar_wait(&bar_full[stage], ph_full);
+                    mbar_wait_warp(&bar_full[stage], ph_full);
                     tc_fence_after();
                     // S[128 x 512] = Q[128 x 16] K^T : two N = 256 halves, TMEM columns [0,256) and [256,512)
-                    const uint64_t dq = smem_desc(sQ, 2048, 128);
-                    mma_ss(tmem, dq, smem_desc(sK, 8192, 128), idesc_s, 0u);
-                    mma_ss(tmem + 256, dq, smem_desc(sK + 256 * 16, 8192, 128), idesc_s, 0u);
-                    mma_commit(&bar_s);
+                    const uint32_t dq = smem_desc_lo(sQ, 2048);
+                    mma_ss_w(tmem, dq, qk_hi, smem_desc_lo(sK, 8192), qk_hi, idesc_s, 0u);
+                    mma_ss_w(tmem + 256, dq, qk_hi, smem_desc_lo(sK + 256 * 16, 8192), qk_hi, idesc_s, 0u);
+                    mma_commit_w(&bar_s);
                     // O[128 x 16] += P_chunk[128 x 32] V_chunk[32 x 16] as the chunks arrive (chunk index fastest over quarters)
+                    const uint32_t dv = smem_desc_lo(sV, 128);
                     uint32_t first = 1;
 #pragma unroll 1
                     for (int c = 0; c < 4; ++c)
 #pragma unroll 1
                         for (int q = 0; q < 4; ++q) {
-                            mbar_wait(&bar_p[q * 4 + c], ph);
+                            mbar_wait_lean(&bar_p[q * 4 + c], ph);
                             tc_fence_after();
 #pragma unroll
                             for (int j = 0; j < 2; ++j) {
                                 const int ks = q * 8 + c * 2 + j;   // k-step = keys [16 ks, 16 ks + 16)
-                                mma_ts(tmem + 16, tmem + q * 128 + c * 32 + j * 8, smem_desc(sV + ks * 256, 128, 8192), idesc_o,
-                                       first ? 0u : 1u);
+                                mma_ts_w(tmem + 16, tmem + q * 128 + c * 32 + j * 8, dv + (uint32_t)(ks * 256 / 16), v_hi, idesc_o, first ? 0u : 1u);
                                 first = 0;
                             }
                         }
-                    mma_commit(&bar_o);
+                    mma_commit_w(&bar_o);
                 }
             } else {
                 uint8_t *sQK = sStage;                      // [Q hi 4096][Q lo 4096][K hi 16384][K lo 16384]
