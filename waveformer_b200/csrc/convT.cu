@@ -88,14 +88,14 @@ __global__ void __launch_bounds__(256) convT_k2s2_kernel(const uint16_t *__restr
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
-    if (tid == 0) {
+    if ((tid >> 5) == 0) {     // warp 0, converged: one elected lane issues (tc_common.cuh, "warp-uniform issue")
         const uint32_t idesc = instr_desc_h16<F16>(128, NT, false);
-        const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+        const uint32_t al = smem_desc_lo(smem_u32(sA), 2048), bl = smem_desc_lo(smem_u32(sB), NT * 16), dh = smem_desc_hi(128);
         for (int t = 0; t < ntiles; ++t)
             for (int ks = 0; ks < (K >> 4); ++ks)
-                mma_ss(tmem + t * NT, smem_desc(a0 + ks * 2 * 2048, 2048, 128),
-                       smem_desc(b0 + (t * kchunks + ks * 2) * NT * 16, NT * 16, 128), idesc, ks > 0 ? 1u : 0u);
-        mma_commit(&bar);
+                mma_ss_w(tmem + t * NT, al + (uint32_t)(ks * 2 * 2048 / 16), dh, bl + (uint32_t)((t * kchunks + ks * 2) * NT), dh, idesc,
+                         ks > 0 ? 1u : 0u);
+        mma_commit_w(&bar);
     }
     mbar_wait(&bar, 0);
     tc_fence_after();

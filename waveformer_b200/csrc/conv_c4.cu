@@ -175,13 +175,13 @@ __global__ void __launch_bounds__(128, 4) conv3d_c4_kernel(const TIN *__restrict
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();   // A image complete
-        if (tid == 0) {
+        if ((tid >> 5) == 0) {     // warp 0, converged: one elected lane issues (tc_common.cuh, "warp-uniform issue")
             tc_fence_after();
+            const uint32_t al = smem_desc_lo(a0, 2048), bl = smem_desc_lo(b0, N * 16), dh = smem_desc_hi(128);
 #pragma unroll
             for (int ks = 0; ks < kC4K / 16; ++ks)
-                mma_ss(tmem, smem_desc(a0 + ks * 2 * 2048, 2048, 128), smem_desc(b0 + ks * 2 * N * 16, N * 16, 128), idesc,
-                       ks > 0 ? 1u : 0u);
-            mma_commit(&bar);
+                mma_ss_w(tmem, al + (uint32_t)(ks * 2 * 2048 / 16), dh, bl + (uint32_t)(ks * 2 * N), dh, idesc, ks > 0 ? 1u : 0u);
+            mma_commit_w(&bar);
         }
         mbar_wait(&bar, phase);
         phase ^= 1;
