@@ -244,3 +244,16 @@ def test_output_schedule_tiles_every_volume():
         assert cover[v][0][0] == 0 and cover[v][-1][1] == size[0]
         assert all(a[1] == b[0] for a, b in zip(cover[v], cover[v][1:]))
     assert cover[0] == [(0, 64), (64, 112), (112, 240)]
+
+
+def test_row_stride_of_channel_slices():
+    """``ops._row_stride``: the row pitch the tail kernel of ProjectionUpsample is given for a channel slice of a channels-last buffer."""
+    import torch
+    from waveformer_b200 import ops
+    comb = torch.zeros(2, 4, 4, 4, 144)
+    assert ops._row_stride(comb[..., 48:96]) == 144
+    assert ops._row_stride(comb) == 144
+    assert ops._row_stride(torch.zeros(10, 48)) == 48
+    assert ops._row_stride(comb[:, ::2, :, :, :48]) is None          # rows not equally spaced
+    assert ops._row_stride(comb.permute(0, 4, 1, 2, 3)) is None      # channels not innermost
+    assert ops._row_stride(torch.zeros(5)) is None
