@@ -189,6 +189,17 @@ int wf_instnorm_apply_ndhwc(const void *x, const float *mean_rstd, const void *r
                             int B, int64_t S, int C, int64_t x_vox_stride, int64_t res_vox_stride, int64_t y_vox_stride,
                             void *stream);
 
+/* y = act((x - mean) * rstd + (conv3(xin) - mean_r) * rstd_r), where conv3 is the 1x1x1 shortcut convolution of a FOUR-channel
+ * input: the last pass of the network's first residual block (MONAI UnetResBlock.forward, monai/networks/blocks/
+ * dynunet_block.py:104-110: `residual = norm3(conv3(inp)); out += residual; out = lrelu(out)`) with the shortcut recomputed per
+ * voxel instead of being read back - together with wf_conv3d_c4_in_stats(y1 = NULL), which still delivers res_mean_rstd, the
+ * C-channel shortcut tensor never exists in memory.  x, y: [B, S, C] 16-bit (`dtype` WF_BF16 / WF_F16) with voxel strides;
+ * xin: [B, S, 4] dense, xin_dtype = WF_F32 (rounded to `dtype` per value, as the convolution kernel does) or `dtype`;
+ * w4: fp32 [C][4] = the operand-format weights of conv3 widened to fp32.  act as in wf_instnorm_apply_ndhwc. */
+int wf_instnorm_apply_shortcut4_ndhwc(const void *x, const float *mean_rstd, const void *xin, int xin_dtype, const float *w4,
+                                      const float *res_mean_rstd, void *y, int act, float slope, int dtype, int B, int64_t S, int C,
+                                      int64_t x_vox_stride, int64_t y_vox_stride, void *stream);
+
 /* out[b, v, k] = head_b[k] + sum_c head_w[k, c] * act(norm(x)[b, v, c] + R): wf_instnorm_apply_ndhwc fused with the 1x1x1
  * output convolution that is its only consumer (Waveformer.out, reference network_models/network_backbone.py:407;
  * UnetOutBlock, monai/networks/blocks/dynunet_block.py:266), so the last C-channel activation is never written.
@@ -283,7 +294,8 @@ int wf_pw_gelu_dual(const void *h, const void *u, int dtype, const void *w1, con
  * monai/networks/blocks/dynunet_block.py:98-111).
  * wpack: bf16 [n0 + n1][112], k = tap * 4 + channel with tap = (dz+1)*9 + (dy+1)*3 + (dx+1), zero padded to 112; rows
  *        >= n0 carry the 1x1x1 weights in the centre tap (k = 52..55).
- * y0 / y1: bf16 [B, D, H, W, n0 / n1] with voxel strides (channel slices of wider buffers allowed); n1 may be 0.
+ * y0 / y1: bf16 [B, D, H, W, n0 / n1] with voxel strides (channel slices of wider buffers allowed); n1 may be 0; y1 may be
+ *        NULL with n1 > 0: only the statistics of the 1x1x1 result are produced (see wf_instnorm_apply_shortcut4_ndhwc).
  * sums0 / sums1: fp64 scratch [B * n * 2]; mean_rstd0 / mean_rstd1: fp32 [B * n * 2] = (mean, 1/sqrt(var + eps)). */
 int wf_conv3d_c4_in_stats(const void *x, int x_dtype, int op_dtype, const void *wpack, void *y0, int64_t y0_vox_stride, int n0,
                           void *y1, int64_t y1_vox_stride, int n1, double *sums0, double *sums1, float *mean_rstd0,

@@ -107,6 +107,57 @@ def test_conv3d_c4_with_fused_shortcut_and_statistics(shape, in_dtype):
     assert y1b is None and s1b is None and torch.equal(y0b, y0)
 
 
+@pytest.mark.parametrize("shape", [(2, 4, 16, 24, 32), (3, 4, 5, 7, 9), (1, 4, 40, 40, 40)])
+@pytest.mark.parametrize("in_dtype,op_dtype", [(torch.float32, torch.float16), (torch.float16, torch.float16),
+                                               (torch.bfloat16, torch.bfloat16)])
+def test_first_block_shortcut_recomputed_in_the_last_pass(shape, in_dtype, op_dtype):
+    """conv3d_c4_in_stats(store_shortcut=False) + instance_norm_act_shortcut4 (the 1^3 shortcut `norm3(conv3(inp))` of
+    dynunet_block.py:104-110 recomputed per voxel from the 4-channel input) vs the stored-shortcut path and vs torch."""
+    from waveformer_b200 import ops
+    x = seeded_randn(shape, 73).cuda().to(in_dtype).contiguous(memory_format=torch.channels_last_3d)
+    w1 = (seeded_randn((48, 4, 3, 3, 3), 71) / 108 ** 0.5).cuda().to(op_dtype)
+    w3 = (seeded_randn((48, 4, 1, 1, 1), 72) / 2.0).cuda().to(op_dtype)
+    y0, s0, y1, s1 = ops.conv3d_c4_in_stats(x, w1, w3, eps=1e-5)
+    y0n, s0n, y1n, s1n = ops.conv3d_c4_in_stats(x, w1, w3, eps=1e-5, store_shortcut=False)
+    assert y1n is None and torch.equal(y0n, y0) and torch.equal(s0n, s0) and torch.equal(s1n, s1)
+    stored = ops.instance_norm_act(y0, "leakyrelu", 0.01, res=y1, res_norm=True, stats=s0, res_stats=s1)
+    buf = torch.full(tuple(y0.permute(0, 2, 3, 4, 1).shape[:-1]) + (64,), 3.0, device="cuda", dtype=op_dtype)
+    got = ops.instance_norm_act_shortcut4(y0, x, w3, s0, s1, "leakyrelu", 0.01, out=buf[..., 8:56])
+    assert torch.equal(got.permute(0, 2, 3, 4, 1), buf[..., 8:56]) and bool((buf[..., :8] == 3).all()) and bool((buf[..., 56:] == 3).all())
+    xr = x.to(op_dtype).float()
+    want = F.leaky_relu(F.instance_norm(y0.float()) + F.instance_norm(F.conv3d(xr, w3.float())), 0.01)
+    tol = 1e-2 if op_dtype == torch.bfloat16 else 2e-3
+    assert max_rel(got.float().cpu(), want.cpu()) < tol
+    assert max_rel(got.float().cpu(), stored.float().cpu()) < 2 * tol      # the stored shortcut is rounded to 16 bit first
+
+
+@pytest.mark.parametrize("shape,dtype", [((2, 48, 20, 24, 28), torch.float16), ((1, 96, 9, 11, 13), torch.bfloat16),
+                                         ((3, 144, 5, 6, 7), torch.float16), ((2, 16, 33, 8, 8), torch.float32),
+                                         ((1, 384, 4, 4, 4), torch.float16)])
+@pytest.mark.parametrize("mode", ["plain", "res", "res_norm", "affine"])
+def test_instance_norm_act_register_constant_kernel(shape, dtype, mode):
+    """The register-constant, software-pipelined InstanceNorm pass (same-width packets) on ragged sizes: every residual mode
+    and the GroupNorm affine, against torch in fp32."""
+    from waveformer_b200 import ops
+    x = (seeded_randn(shape, 54) * 1.3 + 0.4).cuda().to(dtype).contiguous(memory_format=torch.channels_last_3d)
+    r = seeded_randn(shape, 55).cuda().to(dtype).contiguous(memory_format=torch.channels_last_3d)
+    c = shape[1]
+    g = (1.0 + 0.1 * seeded_randn((c,), 56)).cuda()
+    b = (0.05 * seeded_randn((c,), 57)).cuda()
+    want = F.instance_norm(x.float())
+    if mode == "plain":
+        got = ops.instance_norm_act(x, "leakyrelu", 0.01)
+    elif mode == "res":
+        got, want = ops.instance_norm_act(x, "leakyrelu", 0.01, res=r), want + r.float()
+    elif mode == "res_norm":
+        got, want = ops.instance_norm_act(x, "leakyrelu", 0.01, res=r, res_norm=True), want + F.instance_norm(r.float())
+    else:
+        got, want = ops.instance_norm_act(x, "leakyrelu", 0.01, gamma=g, beta=b), want * g.view(1, -1, 1, 1, 1) + b.view(1, -1, 1, 1, 1)
+    want = F.leaky_relu(want, 0.01)
+    tol = 5e-6 if dtype == torch.float32 else (1e-2 if dtype == torch.bfloat16 else 2e-3)
+    assert got.dtype == dtype and max_rel(got.float().cpu(), want.cpu()) < tol
+
+
 @pytest.mark.parametrize("rows,c", [(1000, 48), (513, 96), (300, 192), (77, 384), (40, 768), (9, 1536), (64, 20), (50, 8)])
 @pytest.mark.parametrize("in_dtype,out_dtype", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16),
                                                 (torch.bfloat16, torch.bfloat16)])

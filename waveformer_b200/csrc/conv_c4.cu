@@ -13,7 +13,10 @@
 //   centre tap), resident in shared memory for the CTA's lifetime; 7 x tcgen05.mma 128 x N x 16 into TMEM;
 //   epilogue: TMEM -> bf16 -> shared staging tile -> coalesced 16-byte stores to the two outputs, and per-channel
 //   sum / sum of squares of the ROUNDED outputs (thread t < N owns channel t; fp32 per tile, fp64 per CTA, one fp64
-//   atomicAdd per CTA and channel at the end), so InstanceNorm needs no separate statistics pass.
+//   atomicAdd per CTA and channel at the end), so InstanceNorm needs no separate statistics pass.  y1 == NULL: only the
+//   statistics of the shortcut are produced - its values are a 4-term dot product per channel that the block's last
+//   InstanceNorm pass recomputes from the input voxel (wf_instnorm_apply_shortcut4_ndhwc), which saves one write and one
+//   read of a full-resolution 48-channel tensor.
 // Persistent CTAs (grid = min(tiles, 4 per SM)); traffic = one read of the input (L2-resident) + one write of the output.
 #include <type_traits>
 
@@ -206,11 +209,11 @@ __global__ void __launch_bounds__(128, 4) conv3d_c4_kernel(const TIN *__restrict
         // ---- coalesced stores: voxel rows of n0 (y0) and n1 (y1) channels ----
         const int64_t v0 = tile * 128;
         const int rows = (int)min((int64_t)128, g.total - v0);
-        if (ys0 == n0 && (n1 == 0 || ys1 == n1)) {   // dense outputs: the tile is contiguous in global memory too
+        if (ys0 == n0 && (n1 == 0 || y1 == nullptr || ys1 == n1)) {   // dense outputs: the tile is contiguous in global memory too
             const uint4 *s0 = reinterpret_cast<const uint4 *>(sOut0);
             uint4 *d0 = reinterpret_cast<uint4 *>(y0 + v0 * n0);
             for (int i = tid; i < rows * (n0 >> 3); i += 128) d0[i] = s0[i];
-            if (n1 > 0) {
+            if (n1 > 0 && y1 != nullptr) {
                 const uint4 *s1 = reinterpret_cast<const uint4 *>(sOut1);
                 uint4 *d1 = reinterpret_cast<uint4 *>(y1 + v0 * n1);
                 for (int i = tid; i < rows * (n1 >> 3); i += 128) d1[i] = s1[i];
@@ -221,7 +224,7 @@ __global__ void __launch_bounds__(128, 4) conv3d_c4_kernel(const TIN *__restrict
                 const int r = i / per0, p = i % per0;
                 *reinterpret_cast<uint4 *>(y0 + (v0 + r) * ys0 + p * 8) = *reinterpret_cast<const uint4 *>(sOut0 + (size_t)r * n0 + p * 8);
             }
-            const int per1 = n1 >> 3;
+            const int per1 = y1 != nullptr ? n1 >> 3 : 0;
             for (int i = tid; i < rows * per1; i += 128) {
                 const int r = i / per1, p = i % per1;
                 *reinterpret_cast<uint4 *>(y1 + (v0 + r) * ys1 + p * 8) = *reinterpret_cast<const uint4 *>(sOut1 + (size_t)r * n1 + p * 8);
@@ -285,14 +288,14 @@ extern "C" int wf_conv3d_c4_in_stats(const void *x, int x_dtype, int op_dtype, c
                                      float *mean_rstd0, float *mean_rstd1, float eps, int B, int D, int H, int W,
                                      void *stream) {
     if (!x || !wpack || !y0 || !sums0 || !mean_rstd0) return WF_ERR_NULL_POINTER;
-    if (n1 > 0 && (!y1 || !sums1 || !mean_rstd1)) return WF_ERR_NULL_POINTER;
+    if (n1 > 0 && (!sums1 || !mean_rstd1)) return WF_ERR_NULL_POINTER;   // y1 == NULL: statistics of the second output only
     if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return WF_ERR_BAD_SHAPE;
     const int N = n0 + n1;
     if (n0 <= 0 || n1 < 0 || n0 % 8 || n1 % 8 || N % 16 || N > 128 || (n1 > 0 && n0 % 16)) return WF_ERR_BAD_SHAPE;
-    if (y0_vox_stride < n0 || (n1 > 0 && y1_vox_stride < n1) || y0_vox_stride % 8 || (n1 > 0 && y1_vox_stride % 8)) return WF_ERR_BAD_SHAPE;
+    if (y0_vox_stride < n0 || (n1 > 0 && y1 && y1_vox_stride < n1) || y0_vox_stride % 8 || (n1 > 0 && y1 && y1_vox_stride % 8)) return WF_ERR_BAD_SHAPE;
     if (op_dtype != WF_BF16 && op_dtype != WF_F16) return WF_ERR_BAD_DTYPE;
     if (x_dtype != WF_F32 && x_dtype != op_dtype) return WF_ERR_BAD_DTYPE;
-    if (!aligned16(x) || !aligned16(wpack) || !aligned16(y0) || (n1 > 0 && !aligned16(y1))) return WF_ERR_MISALIGNED;
+    if (!aligned16(x) || !aligned16(wpack) || !aligned16(y0) || (n1 > 0 && y1 && !aligned16(y1))) return WF_ERR_MISALIGNED;
     cudaStream_t st = (cudaStream_t)stream;
     C4Geom g;
     g.B = B; g.D = D; g.H = H; g.W = W;

@@ -6,6 +6,8 @@
 // torch's instance_norm copies channels-last tensors to NCDHW and back (35 % of the step before this kernel).
 // Two streaming passes: per-(b, c) sum / sum-of-squares (fp32 per thread, fp64 across blocks, so E[x^2]-E[x]^2 does
 // not cancel), then y = act((x - mean) * rstd [+ (r - mean_r) * rstd_r | + r]).
+#include <type_traits>
+
 #include "wf_common.cuh"
 
 namespace wf {
@@ -20,6 +22,19 @@ template <typename T, int VEC> struct NVec {
         else *reinterpret_cast<typename Pack<T>::raw *>(p) = Pack<T>::pack(v);
     }
 };
+
+// four fp32 values -> four 16-bit values of type TO in one 8-byte store (fp32 blocks writing a 16-bit concat slice)
+template <typename TO> __device__ __forceinline__ void store_narrow4(TO *p, const float (&f)[4]) {
+    uint32_t lo, hi;
+    if constexpr (std::is_same<TO, __half>::value) {
+        __half2 a = __floats2half2_rn(f[0], f[1]), b = __floats2half2_rn(f[2], f[3]);
+        lo = *reinterpret_cast<uint32_t *>(&a); hi = *reinterpret_cast<uint32_t *>(&b);
+    } else {
+        __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]), b = __floats2bfloat162_rn(f[2], f[3]);
+        lo = *reinterpret_cast<uint32_t *>(&a); hi = *reinterpret_cast<uint32_t *>(&b);
+    }
+    *reinterpret_cast<uint2 *>(p) = make_uint2(lo, hi);
+}
 
 // grid (chunks, B); each block reduces `vox_per_block` voxels of one batch element for all channels.
 // Sums are taken of (x - pivot) with pivot = the channel's value at voxel 0 of the batch element, so that
@@ -161,12 +176,11 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(const T *__restrict
         }
         if constexpr (sizeof(TO) == sizeof(T)) {
             NVec<TO, VEC>::store(y + vox[u] * ys + c0, f[u]);
-        } else {  // fp32 in, bf16 out: 4 channels -> 8 bytes
+        } else {  // fp32 in, 16-bit out: 4 channels -> 8 bytes
             if constexpr (VEC == 1) {
                 y[vox[u] * ys + c0] = from_f32<TO>(f[u][0]);
             } else {
-                __nv_bfloat162 a = __floats2bfloat162_rn(f[u][0], f[u][1]), b2 = __floats2bfloat162_rn(f[u][2], f[u][3]);
-                *reinterpret_cast<uint2 *>(y + vox[u] * ys + c0) = make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b2));
+                store_narrow4<TO>(y + vox[u] * ys + c0, f[u]);
             }
         }
     }
@@ -231,10 +245,130 @@ __global__ void __launch_bounds__(256) instnorm_apply_fast_kernel(const T *__res
         if (p0 + u * 256u < per_sample) {
             if constexpr (sizeof(TO) == sizeof(T)) {
                 NVec<TO, VEC>::store(y + vox * ys + c0[u], f);
-            } else {  // fp32 in, bf16 out: 4 channels -> 8 bytes
-                __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]), b2 = __floats2bfloat162_rn(f[2], f[3]);
-                *reinterpret_cast<uint2 *>(y + vox * ys + c0[u]) = make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b2));
+            } else {  // fp32 in, 16-bit out: 4 channels -> 8 bytes
+                store_narrow4<TO>(y + vox * ys + c0[u], f);
             }
+        }
+    }
+}
+
+// Register-constant, software-pipelined form of the same map (same-width input and output packets, at most 256 channel packets per
+// voxel).  A block has group * cvecs threads (group = 256 / cvecs voxels per sweep), so a thread keeps ONE channel packet for its whole
+// life: the folded constants  y = x * (rstd * gamma) + (beta - mean * rstd * gamma - mean_r * rstd_r) + r * rstd_r  sit in registers
+// instead of being re-read for every packet (four 16-byte constant loads per 16-byte data packet in the kernels above), the index
+// arithmetic is one add per packet, and the loads of sweep i + U are issued before sweep i is processed, so a thread always has U
+// packets in flight.
+// RES: 0 none, 1 residual tensor (raw, or InstanceNorm'd when res_mr is given), 2 the residual is the InstanceNorm'd 1x1x1 shortcut
+// convolution of a FOUR-channel input (MONAI UnetResBlock.conv3 / norm3 of the network's first block, dynunet_block.py:104-108),
+// recomputed per voxel from the 8- or 16-byte input voxel and w4[C][4] (fp32 copies of the operand-format weights) with rstd_r folded
+// in: the 48-channel shortcut tensor is then neither written by the convolution kernel nor read here.
+template <typename T, typename TO, typename XT, int VEC, int RES, int U>
+__global__ void __launch_bounds__(256) instnorm_apply_reg_kernel(const T *__restrict__ x, const float *__restrict__ mr,
+                                                                 const T *__restrict__ res, const float *__restrict__ res_mr,
+                                                                 const XT *__restrict__ xin4, const float *__restrict__ w4,
+                                                                 TO *__restrict__ y, uint32_t S, int C, uint32_t cvecs, uint32_t vpb,
+                                                                 int64_t xs, int64_t rs, int64_t ys, int act, float slope,
+                                                                 const float *__restrict__ gamma, const float *__restrict__ beta) {
+    using Raw = typename Pack<T>::raw;
+    using XRaw = typename std::conditional<sizeof(XT) == 4, float4, uint2>::type;
+    const uint32_t vg = threadIdx.x / cvecs, cv = threadIdx.x - vg * cvecs, group = blockDim.x / cvecs;
+    const int64_t b = blockIdx.y;
+    const int c0 = (int)cv * VEC;
+    float sc[VEC], sh[VEC], rsc[VEC];
+    float w[RES == 2 ? VEC : 1][4];
+    {
+        const float *m = mr + (b * C + c0) * 2;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const float r = m[2 * e + 1] * (gamma != nullptr ? gamma[c0 + e] : 1.f);
+            sc[e] = r;
+            sh[e] = fmaf(-m[2 * e], r, beta != nullptr ? beta[c0 + e] : 0.f);
+            rsc[e] = 1.f;
+        }
+        if (RES != 0 && res_mr != nullptr) {
+            const float *m2 = res_mr + (b * C + c0) * 2;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                rsc[e] = m2[2 * e + 1];
+                sh[e] = fmaf(-m2[2 * e], rsc[e], sh[e]);
+            }
+        }
+        if constexpr (RES == 2) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) w[e][k] = w4[(c0 + e) * 4 + k] * rsc[e];
+        }
+    }
+    const uint32_t v_begin = blockIdx.x * vpb, v_end = min(S, v_begin + vpb);
+    const uint32_t nsweeps = (v_end - v_begin + group - 1) / group;
+    const T *xb = x + b * (int64_t)S * xs + c0;
+    const T *rb = RES == 1 ? res + b * (int64_t)S * rs + c0 : nullptr;
+    const XT *ib = RES == 2 ? xin4 + b * (int64_t)S * 4 : nullptr;
+    TO *yb = y + b * (int64_t)S * ys + c0;
+    Raw cur[U], rcur[RES == 1 ? U : 1];
+    XRaw icur[RES == 2 ? U : 1];
+    auto load = [&](uint32_t sweep, Raw &xr, Raw &rr, XRaw &ir) {
+        const int64_t v = min(v_begin + vg + sweep * group, S - 1);      // clamped: lanes past the end recompute the last voxel, never store
+        xr = *reinterpret_cast<const Raw *>(xb + v * xs);
+        if constexpr (RES == 1) rr = *reinterpret_cast<const Raw *>(rb + v * rs);
+        if constexpr (RES == 2) ir = *reinterpret_cast<const XRaw *>(ib + v * 4);
+    };
+#pragma unroll
+    for (int u = 0; u < U; ++u) load(u, cur[u], rcur[RES == 1 ? u : 0], icur[RES == 2 ? u : 0]);
+    for (uint32_t s0 = 0; s0 < nsweeps; s0 += U) {
+        Raw nxt[U], rnxt[RES == 1 ? U : 1];
+        XRaw inxt[RES == 2 ? U : 1];
+        if (s0 + U < nsweeps) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) load(s0 + U + u, nxt[u], rnxt[RES == 1 ? u : 0], inxt[RES == 2 ? u : 0]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t v = v_begin + vg + (s0 + u) * group;
+            float f[VEC];
+            Pack<T>::unpack(cur[u], f);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) f[e] = fmaf(f[e], sc[e], sh[e]);
+            if constexpr (RES == 1) {
+                float r[VEC];
+                Pack<T>::unpack(rcur[u], r);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) f[e] = fmaf(r[e], rsc[e], f[e]);
+            }
+            if constexpr (RES == 2) {
+                float xi[4];
+                if constexpr (sizeof(XT) == 4) {      // fp32 input: rounded to the operand format exactly as the convolution kernel does
+                    const float4 t = *reinterpret_cast<const float4 *>(&icur[u]);
+                    xi[0] = to_f32(from_f32<T>(t.x)); xi[1] = to_f32(from_f32<T>(t.y)); xi[2] = to_f32(from_f32<T>(t.z)); xi[3] = to_f32(from_f32<T>(t.w));
+                } else {
+                    const uint2 t = *reinterpret_cast<const uint2 *>(&icur[u]);
+                    if constexpr (std::is_same<T, __half>::value) {
+                        const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&t.x)), c = __half22float2(*reinterpret_cast<const __half2 *>(&t.y));
+                        xi[0] = a.x; xi[1] = a.y; xi[2] = c.x; xi[3] = c.y;
+                    } else {
+                        xi[0] = __uint_as_float(t.x << 16); xi[1] = __uint_as_float(t.x & 0xffff0000u);
+                        xi[2] = __uint_as_float(t.y << 16); xi[3] = __uint_as_float(t.y & 0xffff0000u);
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < VEC; ++e)
+                    f[e] += fmaf(w[e][3], xi[3], fmaf(w[e][2], xi[2], fmaf(w[e][1], xi[1], w[e][0] * xi[0])));
+            }
+            if (act == 1) {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) f[e] = fmaxf(f[e], 0.f);
+            } else if (act == 2) {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) f[e] = f[e] > 0.f ? f[e] : f[e] * slope;
+            }
+            if (v < v_end) *reinterpret_cast<typename Pack<TO>::raw *>(yb + (int64_t)v * ys) = Pack<TO>::pack(f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            cur[u] = nxt[u];
+            if constexpr (RES == 1) rcur[u] = rnxt[u];
+            if constexpr (RES == 2) icur[u] = inxt[u];
         }
     }
 }
@@ -506,6 +640,23 @@ static int stats_launch(const T *x, double *sums, float *mr, int B, int64_t S, i
     return WF_OK;
 }
 
+template <typename T, typename TO, typename XT, int RES>
+static int apply_reg_launch(const T *x, const float *mr, const T *res, const float *res_mr, const XT *xin4, const float *w4, TO *y, int B,
+                            int64_t S, int C, int64_t xs, int64_t rs, int64_t ys, int act, float slope, const float *gamma,
+                            const float *beta, cudaStream_t st) {
+    constexpr int V = Pack<T>::VEC, U = 4;
+    const uint32_t cvecs = (uint32_t)(C / V), group = 256u / cvecs;
+    // sweeps per block: enough blocks for ~16 per SM when the tensor is large, never fewer than one pipeline step
+    int64_t steps = (S * B) / ((int64_t)group * U * kNumSMs * 16);
+    steps = steps < 1 ? 1 : (steps > 8 ? 8 : steps);
+    const uint32_t vpb = group * U * (uint32_t)steps;
+    const dim3 grid((unsigned)((S + vpb - 1) / vpb), (unsigned)B);
+    instnorm_apply_reg_kernel<T, TO, XT, V, RES, U><<<grid, group * cvecs, 0, st>>>(x, mr, res, res_mr, xin4, w4, y, (uint32_t)S, C, cvecs, vpb, xs,
+                                                                                   rs, ys, act, slope, gamma, beta);
+    WF_LAUNCH_CHECK();
+    return WF_OK;
+}
+
 template <typename T, typename TO>
 static int apply_launch(const T *x, const float *mr, const T *res, const float *res_mr, TO *y, int B, int64_t S, int C,
                         int64_t xs, int64_t rs, int64_t ys, int act, float slope, const float *gamma, const float *beta,
@@ -518,6 +669,12 @@ static int apply_launch(const T *x, const float *mr, const T *res, const float *
                      (reinterpret_cast<uintptr_t>(y) % out_packet) == 0 && (ys * sizeof(TO)) % out_packet == 0 &&
                      (res == nullptr || (aligned16(res) && (rs * e) % 16 == 0));
     const int64_t per_sample = S * (C / V);
+    if constexpr (sizeof(TO) == sizeof(T) && V > 1) {
+        if (vec && B <= 65535 && C / V <= 256 && S < 0x7fffffffLL) {
+            if (res == nullptr) return apply_reg_launch<T, TO, uint16_t, 0>(x, mr, nullptr, nullptr, nullptr, nullptr, y, B, S, C, xs, rs, ys, act, slope, gamma, beta, st);
+            return apply_reg_launch<T, TO, uint16_t, 1>(x, mr, res, res_mr, nullptr, nullptr, y, B, S, C, xs, rs, ys, act, slope, gamma, beta, st);
+        }
+    }
     if (vec && V > 1 && B <= 65535 && per_sample * (C / V) < 0xffffffffLL && per_sample + 255 < 0xffffffffLL) {
         const uint32_t cvecs = (uint32_t)(C / V);
         const uint32_t magic = cvecs == 1 ? 0u : (uint32_t)((0x100000000ULL + cvecs - 1) / cvecs);   // exact for p * cvecs < 2^32
@@ -581,6 +738,31 @@ extern "C" int wf_instnorm_apply_ndhwc(const void *x, const float *mean_rstd, co
         return wf::apply_launch<float, __half>((const float *)x, mean_rstd, (const float *)res, res_mean_rstd, (__half *)y, B, S,
                                                C, x_vox_stride, res_vox_stride, y_vox_stride, act, slope, gamma, beta, st);
     return WF_ERR_BAD_DTYPE;
+}
+
+extern "C" int wf_instnorm_apply_shortcut4_ndhwc(const void *x, const float *mean_rstd, const void *xin, int xin_dtype, const float *w4,
+                                                 const float *res_mean_rstd, void *y, int act, float slope, int dtype, int B, int64_t S,
+                                                 int C, int64_t x_vox_stride, int64_t y_vox_stride, void *stream) {
+    if (!x || !mean_rstd || !xin || !w4 || !res_mean_rstd || !y) return WF_ERR_NULL_POINTER;
+    if (B <= 0 || B > 65535 || S <= 0 || S >= 0x7fffffffLL || C <= 0 || C % 8 || C / 8 > 256 || x_vox_stride < C || y_vox_stride < C ||
+        x_vox_stride % 8 || y_vox_stride % 8)
+        return WF_ERR_BAD_SHAPE;
+    if (act < 0 || act > 2) return WF_ERR_UNSUPPORTED;
+    if (dtype != WF_BF16 && dtype != WF_F16) return WF_ERR_BAD_DTYPE;
+    if (xin_dtype != WF_F32 && xin_dtype != dtype) return WF_ERR_BAD_DTYPE;
+    if (!wf::aligned16(x) || !wf::aligned16(y) || !wf::aligned16(xin)) return WF_ERR_MISALIGNED;
+    cudaStream_t st = (cudaStream_t)stream;
+    using bf = __nv_bfloat16;
+#define WF_SC4(T_, XT_)                                                                                                               \
+    return wf::apply_reg_launch<T_, T_, XT_, 2>((const T_ *)x, mean_rstd, nullptr, res_mean_rstd, (const XT_ *)xin, w4, (T_ *)y, B, S, C, \
+                                                x_vox_stride, C, y_vox_stride, act, slope, nullptr, nullptr, st)
+    if (dtype == WF_F16) {
+        if (xin_dtype == WF_F32) WF_SC4(__half, float);
+        WF_SC4(__half, uint16_t);
+    }
+    if (xin_dtype == WF_F32) WF_SC4(bf, float);
+    WF_SC4(bf, uint16_t);
+#undef WF_SC4
 }
 
 extern "C" int wf_instnorm_apply_head_ndhwc(const void *x, const float *mean_rstd, const void *res, const float *res_mean_rstd,

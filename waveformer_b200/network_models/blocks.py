@@ -131,8 +131,17 @@ class UnetResBlock(nn.Module):
         if use_fused(inp) and self._c4_fused(inp):
             # 4-channel input (the network's first block): conv1, the 1^3 shortcut conv3 and both InstanceNorm statistics
             # in one tcgen05 kernel (the library convolution needs 3.3 ms for this K = 108 problem)
-            c1, s1, c3, s3 = ops.conv3d_c4_in_stats(inp, self.conv1.conv.weight, self.conv3.conv.weight, eps=self.norm1.eps)
+            # the shortcut's values are a 4-term dot product per channel: only its statistics come out of the convolution kernel,
+            # the last pass recomputes it from the input voxel (no 48-channel shortcut tensor is written or read back)
+            w3 = self.conv3.conv.weight
+            recompute = (w3.dtype == self.conv1.conv.weight.dtype and self.norm2.eps == self.norm3.eps
+                         and (out_buf is None or out_buf.dtype == w3.dtype))
+            c1, s1, c3, s3 = ops.conv3d_c4_in_stats(inp, self.conv1.conv.weight, w3, eps=self.norm1.eps, store_shortcut=not recompute)
             out, s2 = self._conv2_after_norm(c1, s1)
+            if s2 is None:
+                s2 = ops.instance_norm_stats(out, eps=self.norm2.eps)
+            if recompute:
+                return ops.instance_norm_act_shortcut4(out, inp, w3, s2, s3, "leakyrelu", 0.01, out=out_buf)
             return ops.instance_norm_act(out, "leakyrelu", 0.01, res=c3, res_norm=True, eps=self.norm2.eps, res_stats=s3,
                                          out=out_buf, stats=s2)
         if use_fused(inp):

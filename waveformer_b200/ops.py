@@ -589,6 +589,35 @@ def instance_norm_act(x: torch.Tensor, act: str = "none", slope: float = 0.01, r
     return out.permute(0, 4, 1, 2, 3)
 
 
+def instance_norm_act_shortcut4(x: torch.Tensor, xin: torch.Tensor, w1x1: torch.Tensor, stats: torch.Tensor, res_stats: torch.Tensor,
+                                act: str = "leakyrelu", slope: float = 0.01, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``act(InstanceNorm(x) + InstanceNorm(conv1x1(xin)))`` for a 16-bit ``x[B, C, D, H, W]`` and a FOUR-channel ``xin``
+    (fp32 or x's dtype, dense channels-last-3d): the shortcut of the network's first residual block, recomputed per voxel from
+    ``w1x1`` ([C, 4, 1, 1, 1], x's dtype) instead of being read back.  ``stats`` / ``res_stats``: the (mean, rstd) tensors of
+    ``x`` and of the shortcut as ``conv3d_c4_in_stats(..., store_shortcut=False)`` returns them."""
+    dev = _need_cuda(x, xin, w1x1, out)
+    v, vs = _ndhwc_view(x)
+    iv, ivs = _ndhwc_view(xin)
+    B, D, H, W, C = v.shape
+    if x.dtype not in HALF_TYPES or w1x1.dtype != x.dtype or tuple(w1x1.shape) != (C, 4, 1, 1, 1):
+        raise ValueError("instance_norm_act_shortcut4: 16-bit x and a [C, 4, 1, 1, 1] weight of the same type")
+    if tuple(iv.shape) != (B, D, H, W, 4) or ivs != 4 or iv.dtype not in (torch.float32, x.dtype):
+        raise ValueError("instance_norm_act_shortcut4: xin must be a dense 4-channel channels-last volume (fp32 or x's dtype)")
+    if out is None:
+        out = torch.empty((B, D, H, W, C), dtype=x.dtype, device=dev)
+    ys = _voxel_stride(out)
+    if ys is None or tuple(out.shape) != (B, D, H, W, C) or out.dtype != x.dtype:
+        raise ValueError("out must be a voxel-dense [B, D, H, W, C] tensor of x's dtype")
+    w4 = f32_cached(w1x1).reshape(C, 4)
+    with torch.cuda.device(dev):
+        st = _lib.lib().wf_instnorm_apply_shortcut4_ndhwc(v.data_ptr(), stats.data_ptr(), iv.data_ptr(), _dtype_code(iv), w4.data_ptr(),
+                                                          res_stats.data_ptr(), out.data_ptr(), _ACT[act], float(slope),
+                                                          _dtype_code(x), B, D * H * W, C, vs, ys, _stream(dev))
+    _lib.check(st, "wf_instnorm_apply_shortcut4_ndhwc")
+    _count()
+    return out.permute(0, 4, 1, 2, 3)
+
+
 def instance_norm_act_head(x: torch.Tensor, head_w: torch.Tensor, head_b: Optional[torch.Tensor], act: str = "none",
                            slope: float = 0.01, res: Optional[torch.Tensor] = None, res_norm: bool = False,
                            eps: float = 1e-5, stats: Optional[torch.Tensor] = None,
@@ -772,11 +801,12 @@ def _pack_c4_weights(w3x3: torch.Tensor, w1x1: Optional[torch.Tensor], fmt: torc
 
 
 def conv3d_c4_in_stats(x: torch.Tensor, w3x3: torch.Tensor, w1x1: Optional[torch.Tensor] = None, eps: float = 1e-5,
-                       out_dtype: Optional[torch.dtype] = None):
+                       out_dtype: Optional[torch.dtype] = None, store_shortcut: bool = True):
     """3^3 conv (+ optional 1^3 conv) of a 4-channel volume with fused InstanceNorm statistics.  ``x``: [B, 4, D, H, W]
     with channels-last-3d strides (fp32, bf16 or fp16).  Returns ``(y0, stats0, y1, stats1)``; ``y*`` are [B, n, D, H, W]
     channels-last-3d in ``out_dtype`` (bf16 / fp16 = the tensor-core operand format; default: the weight's 16-bit type,
-    else x's, else bf16), ``stats*`` the (mean, rstd) tensors ``instance_norm_act(stats=...)`` takes."""
+    else x's, else bf16), ``stats*`` the (mean, rstd) tensors ``instance_norm_act(stats=...)`` takes.  ``store_shortcut=False``:
+    ``y1`` is not written (returned as None) - only its statistics, for ``instance_norm_act_shortcut4``."""
     dev = _need_cuda(x, w3x3, w1x1)
     v, vs = _ndhwc_view(x)
     B, D, H, W, C = v.shape
@@ -791,7 +821,7 @@ def conv3d_c4_in_stats(x: torch.Tensor, w3x3: torch.Tensor, w1x1: Optional[torch
         raise ValueError("conv3d_c4_in_stats: 16-bit result format; x must be fp32 or already in that format")
     pack = _pack_c4_weights(w3x3, w1x1, fmt)
     y0 = torch.empty((B, D, H, W, n0), dtype=fmt, device=dev)
-    y1 = torch.empty((B, D, H, W, n1), dtype=fmt, device=dev) if n1 else None
+    y1 = torch.empty((B, D, H, W, n1), dtype=fmt, device=dev) if (n1 and store_shortcut) else None
     sums = torch.empty(2 * B * (n0 + n1), dtype=torch.float64, device=dev)
     mr0 = torch.empty(2 * B * n0, dtype=torch.float32, device=dev)
     mr1 = torch.empty(2 * B * n1, dtype=torch.float32, device=dev) if n1 else None
