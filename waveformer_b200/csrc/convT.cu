@@ -318,7 +318,7 @@ extern "C" int wf_convtranspose3d_k2s2_ndhwc(const void *x, const void *wpack, v
     // persistent kernel: weights resident, needs a staging area of its own and whole output positions per accumulator tile
     const size_t smem_p = images + (size_t)128 * (NT + 8) * 2;
     const int64_t mtiles = (M + 127) / 128;
-    if (smem_p <= 220 * 1024 && NT % Cout == 0 && (NT / 2) % 16 == 0 && mtiles > kNumSMs) {
+    if (!ab_old() && smem_p <= 220 * 1024 && NT % Cout == 0 && (NT / 2) % 16 == 0 && mtiles > kNumSMs) {
         static unsigned long long attr_p = 0;
         if (first_use_on_current_device(attr_p)) {
             WF_CUDA_CHECK(cudaFuncSetAttribute(convT_k2s2_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));

@@ -139,7 +139,7 @@ extern "C" int wf_patch_embed_k2s2_c4(const void *x, int x_dtype, const float *w
     if (!wf::aligned16(x) || !wf::aligned16(y) || !wf::aligned16(wpack)) return WF_ERR_MISALIGNED;
     const size_t smem = (size_t)33 * Cout * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
-    if ((W / 2) % 4 == 0) {     // four output voxels per thread
+    if (!wf::ab_old() && (W / 2) % 4 == 0) {     // four output voxels per thread
         const int64_t total4 = (int64_t)B * (D / 2) * (H / 2) * (W / 8) * (Cout / 12);
         const unsigned grid4 = (unsigned)((total4 + 255) / 256);
         if (x_dtype == WF_F32)

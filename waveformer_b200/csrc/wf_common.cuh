@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <stdint.h>
 
 #include "../../include/waveformer_b200.h"
@@ -29,6 +30,13 @@ inline int cuda_fail(cudaError_t e) {
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 constexpr int kNumSMs = 148;  // B200
+
+// WF_AB_OLD=1 routes the kernels that have a newer variant (persistent convT, 4-voxel patch embedding, 2-voxel output head, z-walking
+// upsample) back to their predecessors: same-box A/B timing only (the boxes differ by +-3 % in the clocks their power cap allows).
+inline bool ab_old() {
+    static const bool v = getenv("WF_AB_OLD") != nullptr && getenv("WF_AB_OLD")[0] == '1';
+    return v;
+}
 
 // Function attributes (the > 48 KB dynamic shared-memory opt-in) are per DEVICE: one flag word per call site, one bit per
 // device ordinal, so a process that drives several GPUs opts in on each of them.  Returns true the first time the calling
