@@ -259,14 +259,24 @@ __global__ void __launch_bounds__(128) ffn_back_kernel(FfnBackArgs a) {
         sConst[2 * K + C + i] = a.g2 ? a.g2[i] : 1.f;
         sConst[2 * K + 2 * C + i] = a.b2 ? a.b2[i] : 0.f;
     }
-    auto stage_row = [&](int64_t tile) {       // this thread's row of t2 -> its cells of the A image (asynchronous)
-        const int64_t m = tile * 128 + tid;
-        if (m < a.M) {
-            const uint16_t *src = a.t2 + m * K;
-#pragma unroll 8
-            for (int kc = 0; kc < KCH; ++kc) ffn_cp_async16(sA + (size_t)kc * 2048 + tid * 16, src + kc * 8);
-        } else {
-            for (int kc = 0; kc < KCH; ++kc) *reinterpret_cast<uint4 *>(sA + (size_t)kc * 2048 + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
+    // Tile of t2 -> A image (asynchronous).  One instruction of a warp copies 64 contiguous bytes (two whole sectors) of each of 8
+    // rows: lane = (row % 8) + 8 * (chunk % 4), i.e. conflict-free shared-memory writes and no half-used sectors (a thread copying
+    // its own row fetched every 32-byte sector twice, 16 bytes at a time).
+    const int st_lr = tid & 7, st_lc = (tid >> 3) & 3;
+    auto stage_row = [&](int64_t tile) {
+        const int64_t m0 = tile * 128;
+#pragma unroll 2
+        for (int rg = warp; rg < 16; rg += 4) {
+            const int r = rg * 8 + st_lr;
+            const bool live_r = m0 + r < a.M;
+            const uint16_t *src = a.t2 + (m0 + r) * K;
+#pragma unroll 4
+            for (int cg = 0; cg < KCH / 4; ++cg) {
+                const int kc = cg * 4 + st_lc;
+                uint8_t *dst = sA + (size_t)kc * 2048 + r * 16;
+                if (live_r) ffn_cp_async16(dst, src + kc * 8);
+                else *reinterpret_cast<uint4 *>(dst) = make_uint4(0u, 0u, 0u, 0u);
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -292,7 +302,8 @@ __global__ void __launch_bounds__(128) ffn_back_kernel(FfnBackArgs a) {
             for (int i = 0; i < C; ++i) xr[i] = 0.f;
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        // ---- LayerNorm(4C) + GELU of this thread's own row, in place in the A image (no cross-thread dependency) ----
+        __syncthreads();      // the tile was copied cooperatively: every thread's copies have landed
+        // ---- LayerNorm(4C) + GELU of this thread's own row, in place in the A image ----
         float sum = 0.f, sq = 0.f;
 #pragma unroll 4
         for (int kc = 0; kc < KCH; ++kc) {
@@ -425,19 +436,29 @@ __global__ void __launch_bounds__(256) pw_gelu_dual_kernel(PwTailArgs a) {
     }
     for (int i = tid; i < N; i += 256) sBias[i] = (a.b1 ? a.b1[i] : 0.f) + (a.b2 ? a.b2[i] : 0.f);
     // chunk q of a tile's h block: row q / KCH1, 16-byte chunk q % KCH1 (consecutive threads -> consecutive 16 bytes of global memory)
+    // one instruction of a warp copies 64 contiguous bytes of each of 8 rows: lane = (row % 8) + 8 * (chunk % 4) - whole sectors on
+    // the global side, conflict-free 16-byte writes on the shared side (consecutive lanes on consecutive chunks of one row wrote
+    // 2048 bytes apart: the same bank group)
+    const int st_lr = tid & 7, st_lc = (tid >> 3) & 3;
     auto stage = [&](int64_t tile) {
         const int64_t m0 = tile * 128;
-        for (int q = tid; q < 128 * KCH1; q += 256) {
-            const int row = q / KCH1, kc = q - row * KCH1;
-            uint8_t *dst = sA1 + (size_t)kc * 2048 + row * 16;
-            if (m0 + row < a.M) ffn_cp_async16(dst, a.h + (m0 + row) * K1 + kc * 8);
-            else *reinterpret_cast<uint4 *>(dst) = make_uint4(0u, 0u, 0u, 0u);
-        }
-        for (int q = tid; q < 128 * KCH2; q += 256) {
-            const int row = q / KCH2, kc = q - row * KCH2;
-            uint8_t *dst = sA2 + (size_t)kc * 2048 + row * 16;
-            if (m0 + row < a.M) ffn_cp_async16(dst, a.u + (m0 + row) * K2 + kc * 8);
-            else *reinterpret_cast<uint4 *>(dst) = make_uint4(0u, 0u, 0u, 0u);
+        for (int rg = warp; rg < 16; rg += 8) {
+            const int row = rg * 8 + st_lr;
+            const bool live_r = m0 + row < a.M;
+#pragma unroll 2
+            for (int cg = 0; cg < KCH1 / 4; ++cg) {
+                const int kc = cg * 4 + st_lc;
+                uint8_t *dst = sA1 + (size_t)kc * 2048 + row * 16;
+                if (live_r) ffn_cp_async16(dst, a.h + (m0 + row) * K1 + kc * 8);
+                else *reinterpret_cast<uint4 *>(dst) = make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll 2
+            for (int cg = 0; cg < KCH2 / 4; ++cg) {
+                const int kc = cg * 4 + st_lc;
+                uint8_t *dst = sA2 + (size_t)kc * 2048 + row * 16;
+                if (live_r) ffn_cp_async16(dst, a.u + (m0 + row) * K2 + kc * 8);
+                else *reinterpret_cast<uint4 *>(dst) = make_uint4(0u, 0u, 0u, 0u);
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -453,14 +474,17 @@ __global__ void __launch_bounds__(256) pw_gelu_dual_kernel(PwTailArgs a) {
     for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         // GELU of h, in place, on the cells this thread copied itself (elementwise: no cross-thread dependency)
-        for (int q = tid; q < 128 * KCH1; q += 256) {
-            const int row = q / KCH1, kc = q - row * KCH1;
-            uint4 *cell = reinterpret_cast<uint4 *>(sA1 + (size_t)kc * 2048 + row * 16);
-            float f[8];
-            Pack<T16>::unpack(*cell, f);
+        for (int rg = warp; rg < 16; rg += 8) {
+            const int row = rg * 8 + st_lr;
+            for (int cg = 0; cg < KCH1 / 4; ++cg) {
+                const int kc = cg * 4 + st_lc;
+                uint4 *cell = reinterpret_cast<uint4 *>(sA1 + (size_t)kc * 2048 + row * 16);
+                float f[8];
+                Pack<T16>::unpack(*cell, f);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = ffn_gelu(f[e]);
-            *cell = Pack<T16>::pack(f);
+                for (int e = 0; e < 8; ++e) f[e] = ffn_gelu(f[e]);
+                *cell = Pack<T16>::pack(f);
+            }
         }
         fence_proxy_async();
         tc_fence_before();

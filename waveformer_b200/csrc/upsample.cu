@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(128) upsample_cell_kernel(UpArgs a, const TB *
 // keyed by their source index, and interpolates only the planes it has not seen: one new plane (9 loads, 120 FMAs) + the z pass
 // (96 FMAs) per cell.  The z coordinate is uniform over the block, so the look-up is uniform control flow with static register
 // indexing.  Results are bit-identical to the cell kernel (same operations in the same order per output).
-template <typename TS, typename TB, typename TO, int ZC>
+template <typename TS, typename TB, typename TO, int ZC, int NSRC>
 __global__ void __launch_bounds__(128) upsample_cell_zwalk_kernel(UpArgs a, const TB *__restrict__ base, TO *__restrict__ y, int D,
                                                                   int H, int W, int C, int c4s, int64_t bs, int64_t ys) {
     const int i = blockIdx.x * 128 + threadIdx.x;
@@ -255,11 +255,12 @@ __global__ void __launch_bounds__(128) upsample_cell_zwalk_kernel(UpArgs a, cons
     const int zchunk = blockIdx.z % nchunk;
     const int64_t b = blockIdx.z / nchunk;
     const int c0 = cv * 4;
-    const UpSrc &u = a.src[0];
-    const AxisPair ay = axis_pair(2 * yc, u.sy, u.h, a.align);
-    const AxisPair ax = axis_pair(2 * xc, u.sx, u.w, a.align);
-    const TS *p = reinterpret_cast<const TS *>(u.ptr) + (int64_t)b * u.d * u.h * u.w * C + c0;
-    auto plane = [&](int zs, float (&ty)[2][2][4]) {     // x / y interpolation of source plane zs for this thread's 2 x 2 output columns
+    // x / y interpolation of plane zs of source s for this thread's 2 x 2 output columns (static s: the by-value argument struct is
+    // only ever indexed with compile-time constants)
+    auto plane = [&](const UpSrc &u, int zs, float (&ty)[2][2][4]) {
+        const AxisPair ay = axis_pair(2 * yc, u.sy, u.h, a.align);
+        const AxisPair ax = axis_pair(2 * xc, u.sx, u.w, a.align);
+        const TS *p = reinterpret_cast<const TS *>(u.ptr) + (int64_t)b * u.d * u.h * u.w * C + c0;
 #pragma unroll
         for (int yo = 0; yo < 2; ++yo)
 #pragma unroll
@@ -295,25 +296,12 @@ __global__ void __launch_bounds__(128) upsample_cell_zwalk_kernel(UpArgs a, cons
 #pragma unroll
                 for (int e = 0; e < 4; ++e) d[yo][xo][e] = s[yo][xo][e];
     };
-    float P[3][2][2][4];
-    int q0 = -1, q1 = -1, q2 = -1;          // source planes held in P[0..2]
+    float P[NSRC][3][2][2][4];
+    int q[NSRC][3];                          // source planes held in P[s][0..2]
+#pragma unroll
+    for (int s = 0; s < NSRC; ++s) q[s][0] = q[s][1] = q[s][2] = -1;
     const int zc_end = min(D >> 1, (zchunk + 1) * ZC);
     for (int zc = zchunk * ZC; zc < zc_end; ++zc) {
-        const AxisPair az = axis_pair(2 * zc, u.sz, u.d, a.align);
-        float N[3][2][2][4];
-#pragma unroll
-        for (int iz = 0; iz < 3; ++iz) {
-            const int want = az.p[iz];
-            if (want == q0) copy(N[iz], P[0]);
-            else if (want == q1) copy(N[iz], P[1]);
-            else if (want == q2) copy(N[iz], P[2]);
-            else if (iz > 0 && want == az.p[iz - 1]) copy(N[iz], N[iz - 1]);
-            else if (iz > 1 && want == az.p[0]) copy(N[iz], N[0]);
-            else plane(want, N[iz]);
-        }
-#pragma unroll
-        for (int iz = 0; iz < 3; ++iz) copy(P[iz], N[iz]);
-        q0 = az.p[0]; q1 = az.p[1]; q2 = az.p[2];
         float out[2][2][2][4];
 #pragma unroll
         for (int zo = 0; zo < 2; ++zo)
@@ -324,16 +312,38 @@ __global__ void __launch_bounds__(128) upsample_cell_zwalk_kernel(UpArgs a, cons
 #pragma unroll
                     for (int e = 0; e < 4; ++e) out[zo][yo][xo][e] = 0.f;
 #pragma unroll
-        for (int iz = 0; iz < 3; ++iz)
+        for (int s = 0; s < NSRC; ++s) {
+            const UpSrc &u = a.src[s];
+            const AxisPair az = axis_pair(2 * zc, u.sz, u.d, a.align);
+            float N[3][2][2][4];
 #pragma unroll
-            for (int yo = 0; yo < 2; ++yo)
+            for (int iz = 0; iz < 3; ++iz) {
+                const int want = az.p[iz];
+                if (want == q[s][0]) copy(N[iz], P[s][0]);
+                else if (want == q[s][1]) copy(N[iz], P[s][1]);
+                else if (want == q[s][2]) copy(N[iz], P[s][2]);
+                else if (iz > 0 && want == az.p[iz - 1]) copy(N[iz], N[iz - 1]);
+                else if (iz > 1 && want == az.p[0]) copy(N[iz], N[0]);
+                else plane(u, want, N[iz]);
+            }
 #pragma unroll
-                for (int xo = 0; xo < 2; ++xo)
+            for (int iz = 0; iz < 3; ++iz) {
+                copy(P[s][iz], N[iz]);
+                q[s][iz] = az.p[iz];
+            }
+            // z pass, accumulated across the sources in level order: the association of the cell kernel above (bit-identical results)
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        out[0][yo][xo][e] = fmaf(az.wa[iz], P[iz][yo][xo][e], out[0][yo][xo][e]);
-                        out[1][yo][xo][e] = fmaf(az.wb[iz], P[iz][yo][xo][e], out[1][yo][xo][e]);
-                    }
+            for (int iz = 0; iz < 3; ++iz)
+#pragma unroll
+                for (int yo = 0; yo < 2; ++yo)
+#pragma unroll
+                    for (int xo = 0; xo < 2; ++xo)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            out[0][yo][xo][e] = fmaf(az.wa[iz], N[iz][yo][xo][e], out[0][yo][xo][e]);
+                            out[1][yo][xo][e] = fmaf(az.wb[iz], N[iz][yo][xo][e], out[1][yo][xo][e]);
+                        }
+        }
 #pragma unroll
         for (int zo = 0; zo < 2; ++zo)
 #pragma unroll
@@ -367,12 +377,15 @@ static int upsample_launch(const UpArgs &a, const TB *base, TO *y, int B, int D,
     bool vec = (C % V == 0) && aligned16(y) && (base == nullptr || aligned16(base)) && (bs * sizeof(TB)) % 16 == 0 &&
                (ys * sizeof(TO)) % 16 == 0;
     for (int s = 0; s < a.nsrc; ++s) vec = vec && aligned16(a.src[s].ptr);
-    if (!ab_old() && vec && a.nsrc == 1 && cell_ok(a, D, H, W, C) && (D >> 1) >= 16) {      // one source, deep volume: walk along z
+    // one source, deep volume: walk along z.  (Two / three sources were measured too - the plane caches of all levels in registers:
+    // 254 registers without spills at two levels, 61 vs 59 us; 255 registers + 200 bytes of spills at three, 392 vs 322 us for the
+    // stage-1 block at six windows - so the multi-level sums keep the cell kernel.)
+    if (!ab_old() && vec && a.nsrc == 1 && cell_ok(a, D, H, W, C) && (D >> 1) >= 16) {
         constexpr int ZC = 8;
         const int nchunk = ((D >> 1) + ZC - 1) / ZC;
         if ((int64_t)B * nchunk <= 65535) {
             dim3 grid((unsigned)(((W >> 1) * (C / 4) + 127) / 128), (unsigned)(H >> 1), (unsigned)(B * nchunk));
-            upsample_cell_zwalk_kernel<TS, TB, TO, ZC><<<grid, 128, 0, st>>>(a, base, y, D, H, W, C, C / 4, bs, ys);
+            upsample_cell_zwalk_kernel<TS, TB, TO, ZC, 1><<<grid, 128, 0, st>>>(a, base, y, D, H, W, C, C / 4, bs, ys);
             WF_LAUNCH_CHECK();
             return WF_OK;
         }
