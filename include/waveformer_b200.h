@@ -200,6 +200,14 @@ int wf_instnorm_apply_shortcut4_ndhwc(const void *x, const float *mean_rstd, con
                                       const float *res_mean_rstd, void *y, int act, float slope, int dtype, int B, int64_t S, int C,
                                       int64_t x_vox_stride, int64_t y_vox_stride, void *stream);
 
+/* InstanceNorm statistics (mean, 1/sqrt(var + eps), biased variance) of the 1x1x1 shortcut convolution y_c = sum_k w4[c][k] x_k of a
+ * FOUR-channel volume x [B, S, 4], derived from the 4 first and 10 second moments of x per sample (mean_c = w_c . m, var_c =
+ * w_c^T Cov w_c) - the statistics half of `norm3(conv3(inp))` (monai/networks/blocks/dynunet_block.py:104-106) without computing
+ * conv3.  x_dtype WF_F32 (each value rounded to op_dtype first, as the convolution kernel does) or op_dtype (WF_BF16 / WF_F16);
+ * w4 fp32 [C][4]; sums: fp64 scratch [B * 14]; mean_rstd: fp32 [B * C * 2]. */
+int wf_shortcut4_stats(const void *x, int x_dtype, int op_dtype, const float *w4, double *sums, float *mean_rstd, float eps, int B,
+                       int64_t S, int C, void *stream);
+
 /* out[b, v, k] = head_b[k] + sum_c head_w[k, c] * act(norm(x)[b, v, c] + R): wf_instnorm_apply_ndhwc fused with the 1x1x1
  * output convolution that is its only consumer (Waveformer.out, reference network_models/network_backbone.py:407;
  * UnetOutBlock, monai/networks/blocks/dynunet_block.py:266), so the last C-channel activation is never written.

@@ -124,8 +124,17 @@ def test_first_block_shortcut_recomputed_in_the_last_pass(shape, in_dtype, op_dt
     buf = torch.full(tuple(y0.permute(0, 2, 3, 4, 1).shape[:-1]) + (64,), 3.0, device="cuda", dtype=op_dtype)
     got = ops.instance_norm_act_shortcut4(y0, x, w3, s0, s1, "leakyrelu", 0.01, out=buf[..., 8:56])
     assert torch.equal(got.permute(0, 2, 3, 4, 1), buf[..., 8:56]) and bool((buf[..., :8] == 3).all()) and bool((buf[..., 56:] == 3).all())
+    # the shortcut's statistics from the moments of the 4-channel input (no convolution): against those of the unrounded shortcut
     xr = x.to(op_dtype).float()
+    c3 = F.conv3d(xr.double(), w3.double())
+    sm = ops.shortcut4_stats(x, w3, eps=1e-5).reshape(-1, 2)
+    mean = c3.mean(dim=(2, 3, 4)).reshape(-1)
+    rstd = (c3.var(dim=(2, 3, 4), unbiased=False) + 1e-5).rsqrt().reshape(-1)
+    assert float((sm[:, 0].double() - mean).abs().max()) < 2e-6 * max(1.0, float(mean.abs().max()))
+    assert max_rel(sm[:, 1].cpu(), rstd.float().cpu()) < 1e-5
+    got_m = ops.instance_norm_act_shortcut4(y0, x, w3, s0, sm.reshape(-1), "leakyrelu", 0.01)
     want = F.leaky_relu(F.instance_norm(y0.float()) + F.instance_norm(F.conv3d(xr, w3.float())), 0.01)
+    assert max_rel(got_m.float().cpu(), want.cpu()) < (1e-2 if op_dtype == torch.bfloat16 else 2e-3)
     tol = 1e-2 if op_dtype == torch.bfloat16 else 2e-3
     assert max_rel(got.float().cpu(), want.cpu()) < tol
     assert max_rel(got.float().cpu(), stored.float().cpu()) < 2 * tol      # the stored shortcut is rounded to 16 bit first

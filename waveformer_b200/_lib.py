@@ -40,6 +40,7 @@ SIGNATURES = {
     "wf_instnorm_stats_ndhwc": (_I, [_VOIDP, _VOIDP, _VOIDP, _I, _I, _I64, _I, _I64, _F, _VOIDP]),
     "wf_instnorm_apply_ndhwc": (_I, [_VOIDP] * 7 + [_I, _F, _I, _I, _I, _I64, _I, _I64, _I64, _I64, _VOIDP]),
     "wf_instnorm_apply_shortcut4_ndhwc": (_I, [_VOIDP, _VOIDP, _VOIDP, _I, _VOIDP, _VOIDP, _VOIDP, _I, _F, _I, _I, _I64, _I, _I64, _I64, _VOIDP]),
+    "wf_shortcut4_stats": (_I, [_VOIDP, _I, _I, _VOIDP, _VOIDP, _VOIDP, _F, _I, _I64, _I, _VOIDP]),
     "wf_instnorm_apply_head_ndhwc": (_I, [_VOIDP] * 7 + [_I, _F, _I, _I, _I, _I64, _I, _I, _I64, _I64, _VOIDP]),
     "wf_groupnorm_fold_linear": (_I, [_VOIDP] * 7 + [_I, _I, _I, _I, _I, _VOIDP]),
     "wf_split_f16": (_I, [_VOIDP, _VOIDP, _VOIDP, _I64, _VOIDP]),

@@ -834,6 +834,118 @@ extern "C" int wf_instnorm_apply_ndhwc(const void *x, const float *mean_rstd, co
     return WF_ERR_BAD_DTYPE;
 }
 
+namespace wf {
+
+// First and second moments of a FOUR-channel volume per sample: sums[b][0..3] = sum x_k, sums[b][4..13] = sum x_k x_l (k <= l, row-major
+// upper triangle), fp64.  The InstanceNorm statistics of ANY 1x1x1 convolution of that volume follow from these 14 numbers
+// (mean_c = w_c . m, var_c = w_c^T Cov w_c), so the first block's shortcut needs neither its own accumulator columns in the convolution
+// kernel nor a pass over its 48-channel result.  x is rounded to the operand format T first (what the convolution multiplies).
+template <typename T, typename XT>
+__global__ void __launch_bounds__(256) moments4_kernel(const XT *__restrict__ x, double *__restrict__ sums, int64_t S, int64_t vpb) {
+    using XRaw = typename std::conditional<sizeof(XT) == 4, float4, uint2>::type;
+    const int64_t b = blockIdx.y;
+    const int64_t v0 = (int64_t)blockIdx.x * vpb, v1 = min(S, v0 + vpb);
+    const XT *xb = x + b * S * 4;
+    float m[14];
+#pragma unroll
+    for (int i = 0; i < 14; ++i) m[i] = 0.f;
+    for (int64_t v = v0 + threadIdx.x; v < v1; v += 256) {      // <= vpb / 256 values per thread and fp32 partial (vpb = 8192: 32)
+        const XRaw raw = *reinterpret_cast<const XRaw *>(xb + v * 4);
+        float f[4];
+        if constexpr (sizeof(XT) == 4) {
+            const float4 t = *reinterpret_cast<const float4 *>(&raw);
+            f[0] = to_f32(from_f32<T>(t.x)); f[1] = to_f32(from_f32<T>(t.y)); f[2] = to_f32(from_f32<T>(t.z)); f[3] = to_f32(from_f32<T>(t.w));
+        } else {
+            const uint2 t = *reinterpret_cast<const uint2 *>(&raw);
+            if constexpr (std::is_same<T, __half>::value) {
+                const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&t.x)), c = __half22float2(*reinterpret_cast<const __half2 *>(&t.y));
+                f[0] = a.x; f[1] = a.y; f[2] = c.x; f[3] = c.y;
+            } else {
+                f[0] = __uint_as_float(t.x << 16); f[1] = __uint_as_float(t.x & 0xffff0000u);
+                f[2] = __uint_as_float(t.y << 16); f[3] = __uint_as_float(t.y & 0xffff0000u);
+            }
+        }
+        int i = 4;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            m[k] += f[k];
+#pragma unroll
+            for (int l = k; l < 4; ++l) { m[i] = fmaf(f[k], f[l], m[i]); ++i; }
+        }
+    }
+    __shared__ double red[8][14];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 14; ++i) {
+        double d = (double)m[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        if (lane == 0) red[warp][i] = d;
+    }
+    __syncthreads();
+    if (threadIdx.x < 14) {
+        double d = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) d += red[w][threadIdx.x];
+        atomicAdd(sums + b * 14 + threadIdx.x, d);
+    }
+}
+
+// mr[(b * C + c) * 2] = mean, + 1 = 1 / sqrt(var + eps) of y_c = sum_k w4[c][k] x_k from the moments above
+__global__ void shortcut4_stats_finalize_kernel(const double *__restrict__ sums, const float *__restrict__ w4, float *__restrict__ mr,
+                                                int n, int C, double inv_s, double eps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // b * C + c
+    if (i >= n) return;
+    const int b = i / C, c = i - b * C;
+    const double *sm = sums + (int64_t)b * 14;
+    double mean[4], cov[4][4];
+    for (int k = 0; k < 4; ++k) mean[k] = sm[k] * inv_s;
+    int j = 4;
+    for (int k = 0; k < 4; ++k)
+        for (int l = k; l < 4; ++l) {
+            cov[k][l] = cov[l][k] = sm[j] * inv_s - mean[k] * mean[l];
+            ++j;
+        }
+    double w[4];
+    for (int k = 0; k < 4; ++k) w[k] = (double)w4[c * 4 + k];
+    double mu = 0.0, var = 0.0;
+    for (int k = 0; k < 4; ++k) {
+        mu += w[k] * mean[k];
+        for (int l = 0; l < 4; ++l) var += w[k] * w[l] * cov[k][l];
+    }
+    var = var < 0.0 ? 0.0 : var;
+    mr[2 * i] = (float)mu;
+    mr[2 * i + 1] = (float)(1.0 / sqrt(var + eps));
+}
+
+}  // namespace wf
+
+extern "C" int wf_shortcut4_stats(const void *x, int x_dtype, int op_dtype, const float *w4, double *sums, float *mean_rstd, float eps,
+                                  int B, int64_t S, int C, void *stream) {
+    if (!x || !w4 || !sums || !mean_rstd) return WF_ERR_NULL_POINTER;
+    if (B <= 0 || B > 65535 || S <= 0 || C <= 0) return WF_ERR_BAD_SHAPE;
+    if (op_dtype != WF_BF16 && op_dtype != WF_F16) return WF_ERR_BAD_DTYPE;
+    if (x_dtype != WF_F32 && x_dtype != op_dtype) return WF_ERR_BAD_DTYPE;
+    if (!wf::aligned16(x)) return WF_ERR_MISALIGNED;
+    cudaStream_t st = (cudaStream_t)stream;
+    WF_CUDA_CHECK(cudaMemsetAsync(sums, 0, sizeof(double) * 14 * (size_t)B, st));
+    const int64_t vpb = 8192;
+    const dim3 grid((unsigned)((S + vpb - 1) / vpb), (unsigned)B);
+    using bf = __nv_bfloat16;
+    if (op_dtype == WF_F16) {
+        if (x_dtype == WF_F32) wf::moments4_kernel<__half, float><<<grid, 256, 0, st>>>((const float *)x, sums, S, vpb);
+        else wf::moments4_kernel<__half, uint16_t><<<grid, 256, 0, st>>>((const uint16_t *)x, sums, S, vpb);
+    } else {
+        if (x_dtype == WF_F32) wf::moments4_kernel<bf, float><<<grid, 256, 0, st>>>((const float *)x, sums, S, vpb);
+        else wf::moments4_kernel<bf, uint16_t><<<grid, 256, 0, st>>>((const uint16_t *)x, sums, S, vpb);
+    }
+    WF_LAUNCH_CHECK();
+    const int n = B * C;
+    wf::shortcut4_stats_finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(sums, w4, mean_rstd, n, C, 1.0 / (double)S, (double)eps);
+    WF_LAUNCH_CHECK();
+    return WF_OK;
+}
+
 extern "C" int wf_instnorm_apply_shortcut4_ndhwc(const void *x, const float *mean_rstd, const void *xin, int xin_dtype, const float *w4,
                                                  const float *res_mean_rstd, void *y, int act, float slope, int dtype, int B, int64_t S,
                                                  int C, int64_t x_vox_stride, int64_t y_vox_stride, void *stream) {

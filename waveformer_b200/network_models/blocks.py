@@ -10,6 +10,8 @@ from __future__ import annotations
 
 from typing import Sequence, Tuple, Union
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -136,7 +138,15 @@ class UnetResBlock(nn.Module):
             w3 = self.conv3.conv.weight
             recompute = (w3.dtype == self.conv1.conv.weight.dtype and self.norm2.eps == self.norm3.eps
                          and (out_buf is None or out_buf.dtype == w3.dtype))
-            c1, s1, c3, s3 = ops.conv3d_c4_in_stats(inp, self.conv1.conv.weight, w3, eps=self.norm1.eps, store_shortcut=not recompute)
+            if recompute and os.environ.get("WF_C4_SHORTCUT_STATS", "moments") == "kernel":     # same-box A/B: statistics from the convolution kernel
+                c1, s1, c3, s3 = ops.conv3d_c4_in_stats(inp, self.conv1.conv.weight, w3, eps=self.norm1.eps, store_shortcut=False)
+            elif recompute:
+                # ... and its statistics follow from the 14 first / second moments of the 4-channel input, so the convolution kernel
+                # carries no accumulator columns for it at all (N = 48 instead of 96)
+                c1, s1, c3, _ = ops.conv3d_c4_in_stats(inp, self.conv1.conv.weight, None, eps=self.norm1.eps)
+                s3 = ops.shortcut4_stats(inp, w3, eps=self.norm3.eps)
+            else:
+                c1, s1, c3, s3 = ops.conv3d_c4_in_stats(inp, self.conv1.conv.weight, w3, eps=self.norm1.eps)
             out, s2 = self._conv2_after_norm(c1, s1)
             if s2 is None:
                 s2 = ops.instance_norm_stats(out, eps=self.norm2.eps)

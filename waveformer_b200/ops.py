@@ -589,6 +589,26 @@ def instance_norm_act(x: torch.Tensor, act: str = "none", slope: float = 0.01, r
     return out.permute(0, 4, 1, 2, 3)
 
 
+def shortcut4_stats(xin: torch.Tensor, w1x1: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """(mean, rstd) per (sample, channel) of ``conv1x1(xin)`` for a FOUR-channel ``xin`` (fp32 or the weight's 16-bit type, dense
+    channels-last-3d) as a flat fp32 tensor [B * C * 2], from the input's first and second moments - the convolution is not run."""
+    dev = _need_cuda(xin, w1x1)
+    iv, ivs = _ndhwc_view(xin)
+    B, D, H, W, cin = iv.shape
+    C = w1x1.shape[0]
+    if cin != 4 or ivs != 4 or w1x1.dtype not in HALF_TYPES or tuple(w1x1.shape) != (C, 4, 1, 1, 1) or iv.dtype not in (torch.float32, w1x1.dtype):
+        raise ValueError("shortcut4_stats: dense 4-channel channels-last volume (fp32 or the weight's type) and a 16-bit [C, 4, 1, 1, 1] weight")
+    w4 = f32_cached(w1x1).reshape(C, 4)
+    sums = torch.empty(14 * B, dtype=torch.float64, device=dev)
+    mr = torch.empty(2 * B * C, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        st = _lib.lib().wf_shortcut4_stats(iv.data_ptr(), _dtype_code(iv), _dtype_code(w1x1), w4.data_ptr(), sums.data_ptr(), mr.data_ptr(),
+                                           float(eps), B, D * H * W, C, _stream(dev))
+    _lib.check(st, "wf_shortcut4_stats")
+    _count(2)
+    return mr
+
+
 def instance_norm_act_shortcut4(x: torch.Tensor, xin: torch.Tensor, w1x1: torch.Tensor, stats: torch.Tensor, res_stats: torch.Tensor,
                                 act: str = "leakyrelu", slope: float = 0.01, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``act(InstanceNorm(x) + InstanceNorm(conv1x1(xin)))`` for a 16-bit ``x[B, C, D, H, W]`` and a FOUR-channel ``xin``
