@@ -107,6 +107,20 @@ def test_conv3d_c4_with_fused_shortcut_and_statistics(shape, in_dtype):
     assert y1b is None and s1b is None and torch.equal(y0b, y0)
 
 
+@pytest.mark.parametrize("out_dtype", [torch.float16, torch.bfloat16])
+def test_instance_norm_fp32_block_writes_16bit_slice(out_dtype):
+    """An fp32 block writing into a 16-bit concatenation slice (8-byte narrow stores): fp16 destinations used to receive bf16 bit
+    patterns."""
+    from waveformer_b200 import ops
+    x = (seeded_randn((2, 16, 6, 10, 12), 58) * 2.0 + 0.5).cuda().contiguous(memory_format=torch.channels_last_3d)
+    buf = torch.zeros((2, 6, 10, 12, 40), device="cuda", dtype=out_dtype)
+    y = ops.instance_norm_act(x, "leakyrelu", 0.01, out=buf[..., 8:24])
+    want = F.leaky_relu(F.instance_norm(x), 0.01)
+    assert y.dtype == out_dtype and torch.equal(y.permute(0, 2, 3, 4, 1), buf[..., 8:24])
+    assert max_rel(y.float().cpu(), want.cpu()) < (1e-2 if out_dtype == torch.bfloat16 else 2e-3)
+    assert bool((buf[..., :8] == 0).all()) and bool((buf[..., 24:] == 0).all())
+
+
 @pytest.mark.parametrize("shape", [(2, 4, 16, 24, 32), (3, 4, 5, 7, 9), (1, 4, 40, 40, 40)])
 @pytest.mark.parametrize("in_dtype,op_dtype", [(torch.float32, torch.float16), (torch.float16, torch.float16),
                                                (torch.bfloat16, torch.bfloat16)])
