@@ -183,6 +183,26 @@ def kernel_rooflines(pk):
                                        note="decoder1.conv1 on the concatenation buffer: two passes of the rolling-row kernel, the second "
                                             "adds the first's 16-bit result to its accumulators")
     del x96, w96
+    # InstanceNorm + LeakyReLU pass of the 128^3 residual blocks on the bench's six windows (1.2 GB in + 1.2 GB out, fp16): the
+    # register-constant, software-pipelined kernel; and the output head (InstanceNorm + InstanceNorm'd residual + LeakyReLU + 1^3 conv)
+    xi = torch.randn((6, 128, 128, 128, 48), device="cuda").half().permute(0, 4, 1, 2, 3)
+    sti = ops.instance_norm_stats(xi)
+    with torch.no_grad():
+        t = event_ms(lambda: ops.instance_norm_act(xi, "leakyrelu", 0.01, stats=sti), 10)
+    alg = 2 * xi.numel() * 2
+    gbs = alg / (t * 1e-3) / 1e9
+    out["instnorm_apply_f16"] = dict(bound="hbm", achieved=round(gbs, 1), peak=pk["hbm_gbs"], unit="GB/s", frac=round(gbs / pk["hbm_gbs"], 4),
+                                     ms=round(t, 4), algorithmic_bytes=alg, note="6 x 48 x 128^3: one read + one write, DESIGN.md 4")
+    wh, bh = torch.randn((4, 48, 1, 1, 1), device="cuda") / 7, torch.randn(4, device="cuda") * 0.1
+    with torch.no_grad():
+        ri = torch.randn((6, 128, 128, 128, 48), device="cuda").half().permute(0, 4, 1, 2, 3)
+        t = event_ms(lambda: ops.instance_norm_act_head(xi, wh, bh, "leakyrelu", 0.01, res=ri, res_norm=True, stats=sti, res_stats=sti), 10)
+    alg = 2 * xi.numel() * 2 + 6 * 128 ** 3 * 4 * 4
+    gbs = alg / (t * 1e-3) / 1e9
+    out["instnorm_apply_head_f16"] = dict(bound="hbm", achieved=round(gbs, 1), peak=pk["hbm_gbs"], unit="GB/s",
+                                          frac=round(gbs / pk["hbm_gbs"], 4), ms=round(t, 4), algorithmic_bytes=alg,
+                                          note="6 x 48 x 128^3 activation + residual in, 4 fp32 logits per voxel out")
+    del xi, sti, ri
     del xk, wk
     torch.cuda.empty_cache()
     return out
