@@ -237,30 +237,37 @@ __global__ void __launch_bounds__(128) upsample_cell_kernel(UpArgs a, const TB *
             }
 }
 
-// ---- z-walking cell variant (one source) -----------------------------------------------------------------------------
-// The cell kernel above re-interpolates all three source planes of every cell (27 loads, ~450 FMAs per 32 outputs x 4 channels) and
-// is bound by instruction issue (SM busy 81 % in ncu, 0.41 ms for a 0.6 GB output).  Consecutive cells along z share two of their
-// three source planes, so a thread that walks ZC cells keeps the x/y-interpolated planes ([2 y][2 x][4 channels] each) in registers,
-// keyed by their source index, and interpolates only the planes it has not seen: one new plane (9 loads, 120 FMAs) + the z pass
-// (96 FMAs) per cell.  The z coordinate is uniform over the block, so the look-up is uniform control flow with static register
-// indexing.  Results are bit-identical to the cell kernel (same operations in the same order per output).
+// ---- z-walking cell variant: plane rings in shared memory -----------------------------------------------------------------------
+// The cell kernel above re-interpolates all three source planes of every cell and level (27 loads, ~450 FMAs per level and 32 outputs
+// x 4 channels) and is bound by instruction issue (SM busy 70-81 % in ncu).  Consecutive cells along z share source planes, so a
+// thread walks ZC cells and keeps the x/y-interpolated planes ([2 y][2 x][4 channels] each) of every level in a ring in shared memory:
+// plane p of level s in slot p % 3, as four 16-byte words per thread in thread-private columns ([level][slot][word][thread]:
+// conflict-free, no barrier needed).  The planes a cell needs are consecutive source indices, so they never collide in the ring; a
+// plane is interpolated only when its slot does not hold it yet - every cell at scale 2, every second at scale 4, every fourth at
+// scale 8 - and the z pass reads three slots per level.  The z coordinate is uniform over the block: uniform control flow.  Same
+// operations in the same order per output as the cell kernel: bit-identical results.  (Register caches instead of the ring were
+// measured first: one level 329 us against the ring's 246 us and the cell kernel's 399 us - the slot rotation costs ~100 register
+// moves per cell; two / three levels need 254 / 255 registers + spills and were no faster / slower than the cell kernel.)
 template <typename TS, typename TB, typename TO, int ZC, int NSRC>
-__global__ void __launch_bounds__(128) upsample_cell_zwalk_kernel(UpArgs a, const TB *__restrict__ base, TO *__restrict__ y, int D,
-                                                                  int H, int W, int C, int c4s, int64_t bs, int64_t ys) {
+__global__ void __launch_bounds__(128) upsample_cell_ring_kernel(UpArgs a, const TB *__restrict__ base, TO *__restrict__ y, int D,
+                                                                 int H, int W, int C, int c4s, int64_t bs, int64_t ys) {
+    extern __shared__ __align__(16) float4 ring[];       // [NSRC][3 slots][4 words][128 threads]
     const int i = blockIdx.x * 128 + threadIdx.x;
-    if (i >= (W >> 1) * c4s) return;
+    if (i >= (W >> 1) * c4s) return;                     // (no block-wide barrier below)
     const int xc = i / c4s, cv = i - xc * c4s;
     const int yc = blockIdx.y;
     const int nchunk = ((D >> 1) + ZC - 1) / ZC;
     const int zchunk = blockIdx.z % nchunk;
     const int64_t b = blockIdx.z / nchunk;
     const int c0 = cv * 4;
-    // x / y interpolation of plane zs of source s for this thread's 2 x 2 output columns (static s: the by-value argument struct is
-    // only ever indexed with compile-time constants)
-    auto plane = [&](const UpSrc &u, int zs, float (&ty)[2][2][4]) {
+    int have[NSRC][3];
+#pragma unroll
+    for (int s = 0; s < NSRC; ++s) have[s][0] = have[s][1] = have[s][2] = -1;
+    auto plane = [&](const UpSrc &u, int zs, float4 *dst) {      // dst: this thread's column of the slot (stride 128 float4 per word)
         const AxisPair ay = axis_pair(2 * yc, u.sy, u.h, a.align);
         const AxisPair ax = axis_pair(2 * xc, u.sx, u.w, a.align);
         const TS *p = reinterpret_cast<const TS *>(u.ptr) + (int64_t)b * u.d * u.h * u.w * C + c0;
+        float ty[2][2][4];
 #pragma unroll
         for (int yo = 0; yo < 2; ++yo)
 #pragma unroll
@@ -287,19 +294,11 @@ __global__ void __launch_bounds__(128) upsample_cell_zwalk_kernel(UpArgs a, cons
                     ty[1][xo][e] = fmaf(ay.wb[iy], tx[xo][e], ty[1][xo][e]);
                 }
         }
-    };
-    auto copy = [](float (&d)[2][2][4], const float (&s)[2][2][4]) {
 #pragma unroll
         for (int yo = 0; yo < 2; ++yo)
 #pragma unroll
-            for (int xo = 0; xo < 2; ++xo)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) d[yo][xo][e] = s[yo][xo][e];
+            for (int xo = 0; xo < 2; ++xo) dst[(yo * 2 + xo) * 128] = make_float4(ty[yo][xo][0], ty[yo][xo][1], ty[yo][xo][2], ty[yo][xo][3]);
     };
-    float P[NSRC][3][2][2][4];
-    int q[NSRC][3];                          // source planes held in P[s][0..2]
-#pragma unroll
-    for (int s = 0; s < NSRC; ++s) q[s][0] = q[s][1] = q[s][2] = -1;
     const int zc_end = min(D >> 1, (zchunk + 1) * ZC);
     for (int zc = zchunk * ZC; zc < zc_end; ++zc) {
         float out[2][2][2][4];
@@ -315,34 +314,34 @@ __global__ void __launch_bounds__(128) upsample_cell_zwalk_kernel(UpArgs a, cons
         for (int s = 0; s < NSRC; ++s) {
             const UpSrc &u = a.src[s];
             const AxisPair az = axis_pair(2 * zc, u.sz, u.d, a.align);
-            float N[3][2][2][4];
+            float4 *lvl = ring + (size_t)s * 3 * 4 * 128 + threadIdx.x;
 #pragma unroll
             for (int iz = 0; iz < 3; ++iz) {
-                const int want = az.p[iz];
-                if (want == q[s][0]) copy(N[iz], P[s][0]);
-                else if (want == q[s][1]) copy(N[iz], P[s][1]);
-                else if (want == q[s][2]) copy(N[iz], P[s][2]);
-                else if (iz > 0 && want == az.p[iz - 1]) copy(N[iz], N[iz - 1]);
-                else if (iz > 1 && want == az.p[0]) copy(N[iz], N[0]);
-                else plane(u, want, N[iz]);
+                const int want = az.p[iz], slot = want % 3;
+                // (static indexing of have[][]: the slot is found by comparison, not by a dynamic register index)
+                const bool hit = (slot == 0 && have[s][0] == want) || (slot == 1 && have[s][1] == want) || (slot == 2 && have[s][2] == want);
+                if (!hit) {
+                    plane(u, want, lvl + slot * 4 * 128);
+                    if (slot == 0) have[s][0] = want; else if (slot == 1) have[s][1] = want; else have[s][2] = want;
+                }
             }
+            // z pass, accumulated across the sources in level order: the association of the cell kernel (bit-identical results)
 #pragma unroll
             for (int iz = 0; iz < 3; ++iz) {
-                copy(P[s][iz], N[iz]);
-                q[s][iz] = az.p[iz];
-            }
-            // z pass, accumulated across the sources in level order: the association of the cell kernel above (bit-identical results)
-#pragma unroll
-            for (int iz = 0; iz < 3; ++iz)
+                const float4 *src = lvl + (az.p[iz] % 3) * 4 * 128;
 #pragma unroll
                 for (int yo = 0; yo < 2; ++yo)
 #pragma unroll
-                    for (int xo = 0; xo < 2; ++xo)
+                    for (int xo = 0; xo < 2; ++xo) {
+                        const float4 t = src[(yo * 2 + xo) * 128];
+                        const float tv[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            out[0][yo][xo][e] = fmaf(az.wa[iz], N[iz][yo][xo][e], out[0][yo][xo][e]);
-                            out[1][yo][xo][e] = fmaf(az.wb[iz], N[iz][yo][xo][e], out[1][yo][xo][e]);
+                            out[0][yo][xo][e] = fmaf(az.wa[iz], tv[e], out[0][yo][xo][e]);
+                            out[1][yo][xo][e] = fmaf(az.wb[iz], tv[e], out[1][yo][xo][e]);
                         }
+                    }
+            }
         }
 #pragma unroll
         for (int zo = 0; zo < 2; ++zo)
@@ -377,15 +376,22 @@ static int upsample_launch(const UpArgs &a, const TB *base, TO *y, int B, int D,
     bool vec = (C % V == 0) && aligned16(y) && (base == nullptr || aligned16(base)) && (bs * sizeof(TB)) % 16 == 0 &&
                (ys * sizeof(TO)) % 16 == 0;
     for (int s = 0; s < a.nsrc; ++s) vec = vec && aligned16(a.src[s].ptr);
-    // one source, deep volume: walk along z.  (Two / three sources were measured too - the plane caches of all levels in registers:
-    // 254 registers without spills at two levels, 61 vs 59 us; 255 registers + 200 bytes of spills at three, 392 vs 322 us for the
-    // stage-1 block at six windows - so the multi-level sums keep the cell kernel.)
-    if (!ab_old() && vec && a.nsrc == 1 && cell_ok(a, D, H, W, C) && (D >> 1) >= 16) {
+    if (!ab_old() && vec && cell_ok(a, D, H, W, C) && (D >> 1) >= 16) {      // deep volume: walk along z with plane rings in shared memory
         constexpr int ZC = 8;
         const int nchunk = ((D >> 1) + ZC - 1) / ZC;
         if ((int64_t)B * nchunk <= 65535) {
             dim3 grid((unsigned)(((W >> 1) * (C / 4) + 127) / 128), (unsigned)(H >> 1), (unsigned)(B * nchunk));
-            upsample_cell_zwalk_kernel<TS, TB, TO, ZC, 1><<<grid, 128, 0, st>>>(a, base, y, D, H, W, C, C / 4, bs, ys);
+            const size_t smem = (size_t)a.nsrc * 3 * 4 * 128 * sizeof(float4);
+            if (a.nsrc == 1) {
+                upsample_cell_ring_kernel<TS, TB, TO, ZC, 1><<<grid, 128, smem, st>>>(a, base, y, D, H, W, C, C / 4, bs, ys);
+            } else if (a.nsrc == 2) {
+                upsample_cell_ring_kernel<TS, TB, TO, ZC, 2><<<grid, 128, smem, st>>>(a, base, y, D, H, W, C, C / 4, bs, ys);
+            } else {
+                static unsigned long long attr_done = 0;
+                if (first_use_on_current_device(attr_done))
+                    WF_CUDA_CHECK(cudaFuncSetAttribute(upsample_cell_ring_kernel<TS, TB, TO, ZC, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                upsample_cell_ring_kernel<TS, TB, TO, ZC, 3><<<grid, 128, smem, st>>>(a, base, y, D, H, W, C, C / 4, bs, ys);
+            }
             WF_LAUNCH_CHECK();
             return WF_OK;
         }
